@@ -1,0 +1,305 @@
+/*
+ * dafk.h -- C ABI of the B200 (sm_100a) kernel library behind the MMSDNet / DAFNet
+ * training and inference step.
+ *
+ * This is the drop-in boundary.  The reference
+ * (agis85/multimodal_segmentation) has no FFI: its hot path is a Keras/TensorFlow
+ * graph, so every entry point below replaces one TF/Keras *op call site* of the
+ * reference.  Each declaration cites the reference file:line whose arithmetic it
+ * reproduces.  A maintainer binds these with ctypes.
+ *
+ * Conventions
+ *   - plain C, no torch types: device pointers + sizes + an explicit cudaStream_t
+ *     passed as void* (NULL = legacy default stream);
+ *   - all tensors are NHWC, contiguous; "M" is the number of pixels N*H*W;
+ *   - return 0 on success, a negative DAFK_ERR_* otherwise; never throws/aborts;
+ *     dafk_last_error_string() describes the last failure of the calling thread;
+ *   - kernels allocate nothing: the caller owns every buffer (workspaces included);
+ *   - no implicit synchronisation: everything is enqueued on the given stream and
+ *     is CUDA-graph capturable;
+ *   - 16-byte alignment is required for every tensor base pointer (checked).
+ */
+#ifndef DAFK_H_
+#define DAFK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAFK_OK 0
+#define DAFK_ERR_BAD_ARG (-1)
+#define DAFK_ERR_ALIGN (-2)
+#define DAFK_ERR_UNSUPPORTED (-3)
+#define DAFK_ERR_CUDA (-4)
+
+/* storage dtypes of feature maps */
+#define DAFK_F32 0
+#define DAFK_BF16 1
+
+/* activation codes (Keras semantics: LeakyReLU'(0) = 0, ReLU'(0) = 0) */
+#define DAFK_ACT_NONE 0
+#define DAFK_ACT_RELU 1
+#define DAFK_ACT_LRELU 2
+#define DAFK_ACT_TANH 3
+
+const char* dafk_last_error_string(void);
+int dafk_version(void);
+/* number of kernel launches issued through this library by the calling process */
+int64_t dafk_launch_count(void);
+/* cudaMemsetAsync(p, 0, bytes) on the given stream (accumulators, gradient buckets) */
+int dafk_memset_zero(void* p, int64_t bytes, void* stream);
+
+/* ------------------------------------------------------------------ rounding
+ * layers/rounding.py:33-42  roundWithGrad: y = np.round(x) (round-half-to-even),
+ * gradient = identity (straight-through, so there is no backward kernel). */
+int dafk_round_fwd(const float* x, float* y, int64_t n, void* stream);
+
+/* model_components/anatomy_encoder.py:23-25,58-66  softmax over the last axis
+ * followed by Rounding.  p = softmax(x[M,C]); r = rint(p).  r may be NULL. */
+int dafk_softmax_fwd(const float* x, float* p, float* r, int64_t M, int C, void* stream);
+/* dx = p * (dp - sum_c(dp*p))  (Keras softmax gradient) */
+int dafk_softmax_bwd(const float* p, const float* dp, float* dx, int64_t M, int C, void* stream);
+
+/* ------------------------------------------------------------------ pointwise
+ * Activation('relu') models/unet.py:97; LeakyReLU() alpha=.3 decoder.py:38,
+ * LeakyReLU(0.2) spade.py:12, discriminator.py:25; tanh decoder.py:28.
+ * y may alias x.  bwd uses the OUTPUT y (sign(y)==sign(x) for these). */
+int dafk_act_fwd(const float* x, float* y, int64_t n, int act, float alpha, void* stream);
+int dafk_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, float alpha,
+                 void* stream);
+/* out = a + b (keras Add, decoder.py:53, spade.py:23); out may alias a or b */
+int dafk_add(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* y = a*x + b*y */
+int dafk_axpby(float a, const float* x, float b, float* y, int64_t n, void* stream);
+int dafk_fill(float* x, float v, int64_t n, void* stream);
+/* dtype conversion between DAFK_F32 and DAFK_BF16 */
+int dafk_cast(const void* x, int x_dt, void* y, int y_dt, int64_t n, void* stream);
+/* dst[:, dst_off:dst_off+c] (+)= src[:, src_off:src_off+c] over M pixels: Concatenate
+ * (modality_encoder.py:35, stn_spline.py:104), channel slices (dafnet.py:187) and
+ * their gradients (accumulate=1). */
+int dafk_copy_channels(const float* src, int src_c, int src_off, float* dst, int dst_c,
+                       int dst_off, int c, int64_t M, int accumulate, void* stream);
+/* gather rows: dst[i,:] = src[idx[i],:]   (utils/data_utils.py:125-129 sample) */
+int dafk_gather_rows(const float* src, const int32_t* idx, float* dst, int64_t rows,
+                     int64_t row_elems, void* stream);
+
+/* ------------------------------------------------------------------ FiLM
+ * layers/film.py:26-36  y = x*gamma[b,c] + beta[b,c], x:[B,HW,C], gamma/beta:[B,C] */
+int dafk_film_fwd(const float* x, const float* gamma, const float* beta, float* y, int B,
+                  int64_t HW, int C, void* stream);
+/* dx = dy*gamma ; dgamma[b,c] = sum_hw dy*x ; dbeta[b,c] = sum_hw dy.
+ * dgamma/dbeta are OVERWRITTEN.  ws: B*C*2 doubles of scratch. */
+int dafk_film_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma,
+                  float* dbeta, double* ws, int B, int64_t HW, int C, void* stream);
+
+/* ------------------------------------------------------------------ Maximum
+ * model_components/anatomy_fuser.py:33  keras Maximum = tf.maximum; gradient goes
+ * entirely to the first input where a >= b (tie rule of tf.maximum). */
+int dafk_max_fwd(const float* a, const float* b, float* out, int64_t n, void* stream);
+int dafk_max_bwd(const float* a, const float* b, const float* dout, float* da, float* db,
+                 int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ BatchNormalization
+ * utils/model_utils.py:10, model_components/segmentor.py:17,20  (Keras defaults:
+ * eps 1e-3, momentum .99, biased batch variance in training).
+ * stats: acc[0:C] += sum_x, acc[C:2C] += sum_x^2 (double; caller zeroes acc). */
+int dafk_bn_stats(const float* x, double* acc, int64_t M, int C, void* stream);
+/* mean/rstd from acc; moving <- moving*momentum + batch*(1-momentum) when moving_* != NULL */
+int dafk_bn_finalize(const double* acc, int64_t M, int C, float eps, float momentum, float* mean,
+                     float* rstd, float* moving_mean, float* moving_var, void* stream);
+/* rstd = 1/sqrt(var+eps) for inference with the moving statistics */
+int dafk_bn_rstd_from_var(const float* var, float* rstd, int C, float eps, void* stream);
+/* out = act((x-mean)*rstd*gamma+beta); out dtype f32 or bf16; act in {NONE, RELU} */
+int dafk_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma,
+                  const float* beta, void* out, int out_dt, int64_t M, int C, int act,
+                  void* stream);
+/* backward, pass 1: acc[0:C] += sum dz, acc[C:2C] += sum dz*xhat, dz = dout*act'(z) */
+int dafk_bn_bwd_reduce(const void* dout, int dout_dt, const float* x, const float* mean,
+                       const float* rstd, const float* gamma, const float* beta, double* acc,
+                       int64_t M, int C, int act, void* stream);
+/* backward, pass 2: dx = gamma*rstd*(dz - acc0/M - xhat*acc1/M); dgamma += acc1; dbeta += acc0
+ * (dgamma/dbeta may be NULL for frozen layers).  dx dtype f32 or bf16. */
+int dafk_bn_bwd_apply(const void* dout, int dout_dt, const float* x, const float* mean,
+                      const float* rstd, const float* gamma, const float* beta, const double* acc,
+                      void* dx, int dx_dt, float* dgamma, float* dbeta, int64_t M, int C, int act,
+                      void* stream);
+/* inference-mode backward (frozen statistics): dx = dz*gamma*rstd */
+int dafk_bn_bwd_frozen(const float* dout, const float* x, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, float* dx, int64_t M, int C, int act,
+                       void* stream);
+
+/* ------------------------------------------------------------------ pooling / resampling
+ * MaxPooling2D(2,2) models/unet.py:39-51, stn_spline.py:108,111 (floor(H/2) outputs);
+ * backward routes to the first maximum in row-major window order. */
+int dafk_maxpool2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, void* stream);
+int dafk_maxpool2_bwd(const void* x, const void* dy, void* dx, int dt, int N, int H, int W, int C,
+                      void* stream);
+/* UpSampling2D(2) utils/model_utils.py:16 (nearest repeat); bwd sums each 2x2 block */
+int dafk_upsample2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, void* stream);
+int dafk_upsample2_bwd(const void* dy, void* dx, int dt, int N, int H, int W, int C, void* stream);
+/* tf.image.resize_nearest_neighbor (layers/spade.py:36-38): src = floor(dst*in/out) */
+int dafk_resize_nn_fwd(const float* x, float* y, int N, int H, int W, int C, int Ho, int Wo,
+                       void* stream);
+int dafk_resize_nn_bwd(const float* dy, float* dx, int N, int H, int W, int C, int Ho, int Wo,
+                       void* stream);
+
+/* ------------------------------------------------------------------ convolution
+ * keras Conv2D call sites: models/unet.py:95,99; utils/model_utils.py:17;
+ * model_components/{anatomy_encoder.py:23,102-154, segmentor.py:15-24,
+ * modality_encoder.py:36-42, decoder.py:28,45-48}; layers/stn_spline.py:106-112;
+ * layers/spade.py:14-31; models/discriminator.py:24,39.
+ * x:[N,H,W,Cin], w: HWIO [KH,KW,Cin,Cout] (Keras layout), y:[N,Ho,Wo,Cout],
+ * Ho = (H + 2*pad - KH)/stride + 1.  Cross-correlation. */
+typedef struct dafk_conv_desc {
+  int32_t N, H, W, Cin;
+  int32_t Cout, KH, KW;
+  int32_t stride, pad;
+  int32_t Ho, Wo;
+} dafk_conv_desc;
+
+/* general CUDA-core path (any shape, fp32): y = act(conv(x,w)+bias) */
+int dafk_conv2d_fwd(const dafk_conv_desc* d, const float* x, const float* w, const float* bias,
+                    float* y, int act, float alpha, void* stream);
+/* dx (overwritten) = conv_transpose(dy, w) */
+int dafk_conv2d_dgrad(const dafk_conv_desc* d, const float* dy, const float* w, float* dx,
+                      void* stream);
+/* dw += x (*) dy  (accumulates: caller zeroes);  db += sum_pixels dy (db may be NULL) */
+int dafk_conv2d_wgrad(const dafk_conv_desc* d, const float* x, const float* dy, float* dw,
+                      float* db, void* stream);
+/* out[c] += sum_m x[m,c] */
+int dafk_colsum(const float* x, float* out, int64_t M, int C, void* stream);
+
+/* tcgen05 / TMEM / TMA implicit-GEMM path: 3x3, stride 1, pad 1, bf16 operands,
+ * fp32 accumulation in tensor memory.  Cin % 64 == 0 and Cout % 64 == 0.
+ * x0:[N,H,W,C0] (+ optional second K source x1:[N,H,W,C1] = Concatenate([x0,x1]),
+ * models/unet.py:68-69), wp: packed bf16 weights [9][Cout][C0+C1] (dafk_pack_conv3x3).
+ * y: [N,H,W,Cout] f32 or bf16.  Returns DAFK_ERR_UNSUPPORTED for other shapes. */
+int dafk_conv3x3_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp,
+                        const float* bias, void* y, int y_dt, int N, int H, int W, int Cout,
+                        void* stream);
+/* weights HWIO f32 [3,3,Cin,Cout] -> bf16 [9][Cout][Cin] (fwd) or flipped/transposed
+ * [9][Cin][Cout] with tap index mirrored (dgrad) */
+int dafk_pack_conv3x3(const float* w_hwio, void* wp, int Cin, int Cout, int for_dgrad,
+                      void* stream);
+/* dw[3,3,Cin,Cout] (HWIO f32) += sum_pixels x (*) dy, tensor-core path */
+int dafk_conv3x3_tc_wgrad(const void* x, int Cin, int cin_off, int cin_total, const void* dy,
+                          int Cout, float* dw, int N, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------ Dense
+ * keras Dense: modality_encoder.py:46-50, stn_spline.py:115-116, discriminator.py:33,
+ * decoder.py:37-40,68, balancer.py:24-25.  y[B,Nout] = x[B,K] w[K,Nout] + b */
+int dafk_dense_fwd(const float* x, const float* w, const float* bias, float* y, int B, int64_t K,
+                   int Nout, void* stream);
+/* dx[B,K] = dy[B,Nout] w^T */
+int dafk_dense_bwd_data(const float* dy, const float* w, float* dx, int B, int64_t K, int Nout,
+                        void* stream);
+/* dw[K,Nout] += x^T dy ; db[Nout] += sum_b dy */
+int dafk_dense_bwd_weight(const float* x, const float* dy, float* dw, float* db, int B, int64_t K,
+                          int Nout, void* stream);
+
+/* ------------------------------------------------------------------ thin-plate spline STN
+ * layers/stn_spline.py:14-91 + layers/interpolate_spline.py:30-278 +
+ * tf.contrib.resampler (call site stn_spline.py:65).
+ *
+ * General batched polyharmonic solve (interpolate_spline.py:76-147): for each b builds the
+ * (n+d+1)^2 system with phi(r^2) (order 1,2,4 supported), LU with partial pivoting
+ * (tf.matrix_solve) and returns w[b,n,k], v[b,d+1,k].  n+d+1 <= 32, d == 2. */
+int dafk_tps_solve_batched(const float* train_points, const float* train_values, float* w_out,
+                           float* v_out, int B, int n, int k, int order, float reg, void* stream);
+/* evaluate (interpolate_spline.py:150-179): out[b,m,k] = phi(|q-c|^2) w + [q,1] v */
+int dafk_tps_apply(const float* query, const float* train_points, const float* w, const float* v,
+                   float* out, int B, int64_t m, int n, int k, int order, int query_batched,
+                   void* stream);
+/* Fast path for ThinPlateSpline2D(inverse=False) (the only mode the reference uses,
+ * anatomy_fuser.py:30): the LHS of the spline system depends only on the constant control-point
+ * grid, so w_b = Winv.theta_b and v_b = v_identity + Vinv.theta_b.  The HOST builds, in fp64, the
+ * constant block  [ c(n,2) | Winv(n,n) | Vinv(3,n) ]  (dafk_tps_consts_floats(n) floats) into a
+ * caller-provided host buffer; the caller uploads it once per control-point grid. */
+int dafk_tps_consts_floats(int n_cp);
+int dafk_tps_build_constants(int cp_h, int cp_w, float* consts_host);
+/* fused spline evaluation + bilinear gather (stn_spline.py:55-67):
+ * out[b,y,x,:] = resample(vol[b], (X,Y)(b,y,x)); also writes locs[b,m,2] = (x,y) in pixels when
+ * locs != NULL.  theta:[B,n_cp,2] control-point offsets in (row,col) normalised units. */
+int dafk_tps_warp_fwd(const float* vol, const float* theta, const float* consts, float* out,
+                      float* locs, int B, int H, int W, int C, int n_cp, void* stream);
+/* backward: dvol += scatter(dout) (caller zeroes dvol; NULL skips it);
+ * dtheta[b,n,2] (overwritten) via the resampler's analytic coordinate gradient.
+ * ws: B*(n_cp+3)*2 doubles (zeroed by the callee). */
+int dafk_tps_warp_bwd(const float* vol, const float* theta, const float* consts, const float* dout,
+                      float* dvol, float* dtheta, double* ws, int B, int H, int W, int C, int n_cp,
+                      void* stream);
+/* plain tf.contrib.resampler forward for arbitrary warp[b,m,2] */
+int dafk_resampler_fwd(const float* vol, const float* warp, float* out, int B, int H, int W, int C,
+                       int64_t m, void* stream);
+
+/* ------------------------------------------------------------------ losses (costs.py)
+ * All losses write a scalar (Keras mean-reduced) into loss[0] as  loss[0] += weight*value
+ * and produce the gradient of  weight*value  w.r.t. the prediction.
+ *
+ * costs.py:43-67 dice over the first `nch` channels, per-sample, smooth 1e-12, mean over B.
+ * costs.py:70-85 + :129-136 weighted cross entropy with swapped arguments, lambda_bce .01.
+ * pred:[B,HW,Cp], target:[B,HW,Ct]; ws: doubles, size dafk_segloss_ws_doubles(B,Cp). */
+int64_t dafk_segloss_ws_doubles(int B, int C);
+int dafk_segloss_fwd(const float* pred, int Cp, const float* target, int Ct, int nch, int use_bce,
+                     float lambda_bce, double* ws, int B, int64_t HW, void* stream);
+int dafk_segloss_finish(const double* ws, float weight, float* loss, int B, int Cp, int nch,
+                        int use_bce, float lambda_bce, int64_t HW, void* stream);
+int dafk_segloss_bwd(const float* pred, int Cp, const float* target, int Ct, int nch, int use_bce,
+                     float lambda_bce, const double* ws, float weight, float* dpred, int B,
+                     int64_t HW, void* stream);
+/* keras 'mae' / 'mse' (mean over all elements); kind 0 = mae, 1 = mse.  target == NULL means a
+ * constant target `cval`.  loss[0] += weight*value; dpred (may be NULL) is overwritten with the
+ * gradient of weight*value (tf.abs gradient = sign, 0 at 0). */
+int dafk_l1l2_loss(const float* pred, const float* target, float cval, int kind, float weight,
+                   float* loss, float* dpred, int64_t n, void* stream);
+/* utils/sdnet_utils.py:9-21 sampling + costs.py:186-189 kl + costs.py:194 ypred (mean):
+ * z = mu + exp(.5*lv)*eps ; kl[b] = -.5*sum(1+lv-mu^2-exp(lv)) ; loss += weight*mean(kl) */
+int dafk_vae_fwd(const float* mu, const float* logvar, const float* eps, float* z, float* kl,
+                 float weight, float* loss, int B, int Z, void* stream);
+/* dmu = dz + weight/B * mu ; dlv = dz*.5*exp(.5 lv)*eps + weight/B*.5*(exp(lv)-1) */
+int dafk_vae_bwd(const float* mu, const float* logvar, const float* eps, const float* dz,
+                 float weight, float* dmu, float* dlogvar, int B, int Z, void* stream);
+
+/* ------------------------------------------------------------------ Spectral regulariser
+ * layers/spectralnorm.py:199-246.  W:[dim,cout]; 3 power iterations from u0; loss +=
+ * alpha*mean|W/sigma - W| ; dW += -alpha*sign(W/sigma - W)/numel (sigma is stop_gradient).
+ * ws: (2*dim + cout + 4) floats. */
+int dafk_spectral_reg(const float* W, const float* u0, float alpha, float* loss, float* dW,
+                      float* ws, int dim, int cout, void* stream);
+
+/* ------------------------------------------------------------------ Adam (Keras 2.1.6)
+ * call sites models/dafnet.py:93,114,155,161,349.  One launch over a flat parameter bucket.
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed on the host; g is multiplied by grad_scale first
+ * (1/world_size after the NCCL all-reduce).  bf16_shadow (may be NULL) receives p as bf16. */
+int dafk_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, int64_t n,
+                   float lr_t, float beta1, float beta2, float eps, float grad_scale,
+                   void* stream);
+
+/* ------------------------------------------------------------------ instance norm + SPADE
+ * keras_contrib InstanceNormalization(axis=None, scale=False, center=False) layers/spade.py:27:
+ * per-sample statistics over H,W,C jointly, (x-mean)/(std+1e-3).
+ * stats: acc[b*2+{0,1}] += sum, sum_sq (double, caller zeroes). */
+int dafk_in_stats(const float* x, double* acc, int B, int64_t HWC, void* stream);
+/* layers/spade.py:41-55 SPADE_COND fused with the normalisation and LeakyReLU(0.2):
+ * xn = (x-mean_b)/(std_b+eps); y = act(xn*(1+gamma)+beta) */
+int dafk_spade_fwd(const float* x, const double* acc, const float* gamma, const float* beta,
+                   float* y, int B, int64_t HWC, float eps, int act, float alpha, void* stream);
+/* backward of the fused op: produces dgamma, dbeta, and dx (through the instance norm).
+ * ws: B*2 doubles zeroed by the callee. */
+int dafk_spade_bwd(const float* dy, const float* x, const double* acc, const float* gamma,
+                   const float* beta, float* dx, float* dgamma, float* dbeta, double* ws, int B,
+                   int64_t HWC, float eps, int act, float alpha, void* stream);
+
+/* ------------------------------------------------------------------ balancer
+ * model_components/balancer.py:33-38 soft dice between two anatomies per sample:
+ * out[b] = (2*sum(a*b)+1e-12)/(sum(a)+sum(b)+1e-12).  ws: B*3 doubles. */
+int dafk_pair_dice(const float* a, const float* b, float* out, double* ws, int B, int64_t HWC,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAFK_H_ */

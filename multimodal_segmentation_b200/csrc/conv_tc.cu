@@ -1,0 +1,599 @@
+// Tensor-core convolution for sm_100a: implicit GEMM on tcgen05.mma with the accumulator in
+// tensor memory (TMEM), operands staged in shared memory by TMA (cp.async.bulk.tensor) through an
+// mbarrier ring, warp-specialised (1 TMA warp, 1 MMA warp, 4 epilogue warps).
+//
+//   forward / data-gradient (same kernel, different packed weights):
+//     D[pixel, co] = sum_{tap, ci} X[pixel + tap, ci] * Wp[tap][co][ci]
+//     A = activations, bf16 NHWC, read with a 4-D tiled tensor map: one box = (64 ch, TW, TH, TN)
+//         = 128 pixels x 128 B, 128B-swizzled, K-major.  Padding comes for free: out-of-bounds box
+//         coordinates are zero-filled by TMA.  A second tensor map gives the second K source of a
+//         Concatenate([x0, x1]) without materialising it (models/unet.py:68-69).
+//     B = packed weights [tap][Cout][Cin] (K-major), 2-D tensor map, box = (64, BLOCK_N).
+//   weight gradient:
+//     dW[tap][ci][co] += sum_pixels X[pixel + tap, ci] * dY[pixel, co]
+//     both operands are the same 128-pixel boxes used as MN-major UMMA operands (the reduction
+//     runs over pixels), split-K over pixel tiles, fp32 atomics into the HWIO gradient.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace dafk {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a pipeline bug must surface as a trapped launch (reported through
+// dafk_last_error_string by the next call), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("dafk: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp of CUTLASS 4.x, re-derived here)
+// ---------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | base_offset [49,52) | layout_type [61,64) (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor, kind::f16: c_format=F32 [4,6)=1 | a_format=BF16 [7,10)=1 | b_format=BF16 [10,13)=1 |
+// a_major [15] | b_major [16] (0 = K-major, 1 = MN-major) | N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int TILE_PIX = 128;                 // pixels per M tile (UMMA_M)
+constexpr int KBLK = 64;                      // channels per k-block (128 B of bf16 = one swizzle row)
+constexpr int A_BYTES = TILE_PIX * KBLK * 2;  // 16 KB
+constexpr int TC_THREADS = 192;
+
+struct TileGeom {
+  int TW, TH, TN;            // box extents (pixels x, y, images); TW*TH*TN == 128
+  int tiles_x, tiles_y, tiles_n;
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                                 const __grid_constant__ CUtensorMap tmA1,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const float* __restrict__ bias, void* __restrict__ y,
+                                                                 int y_dt, int N, int H, int W, int Cout, int C0, int C1,
+                                                                 int KH, int KW, int pad, TileGeom g, int n_blocks) {
+  constexpr int B_BYTES = BLOCK_N * KBLK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = blockIdx.x % n_blocks;
+  int tile = blockIdx.x / n_blocks;
+  const int txi = tile % g.tiles_x; tile /= g.tiles_x;
+  const int tyi = tile % g.tiles_y; tile /= g.tiles_y;
+  const int tni = tile;
+  const int x0 = txi * g.TW, y0 = tyi * g.TH, img0 = tni * g.TN;
+  const int n0 = nb * BLOCK_N;
+  const int taps = KH * KW;
+  const int num_kb = taps * ((C0 + C1) / KBLK);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (C1 > 0) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int kb = 0;
+      for (int src = 0; src < 2; ++src) {
+        const int Cs = src == 0 ? C0 : C1;
+        const CUtensorMap* mA = src == 0 ? &tmA0 : &tmA1;
+        const int koff = src == 0 ? 0 : C0;
+        for (int cb = 0; cb < Cs / KBLK; ++cb) {
+          for (int tap = 0; tap < taps; ++tap, ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(empty_bar + s, ph ^ 1);
+            mbar_expect_tx(full_bar + s, STAGE_BYTES);
+            const int r = tap / KW, q = tap % KW;
+            uint8_t* sa = smem + s * STAGE_BYTES;
+            tma_load_4d(sa, mA, full_bar + s, cb * KBLK, x0 + q - pad, y0 + r - pad, img0);
+            tma_load_2d(sa + A_BYTES, &tmB, full_bar + s, koff + cb * KBLK, tap * Cout + n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE_PIX, BLOCK_N, 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < KBLK / 16; ++k) {
+          // K-major SW128: 8-row groups 1024 B apart; advance 32 B per UMMA_K inside the swizzle row
+          uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
+          uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar + s);   // frees the smem slot when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);     // accumulator ready
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
+    const int m = q4 * 32 + lane;            // row of the tile = pixel
+    const int tx = m % g.TW, ty = (m / g.TW) % g.TH, tn = m / (g.TW * g.TH);
+    const int px = x0 + tx, py = y0 + ty, img = img0 + tn;
+    const bool live = px < W && py < H && img < N;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int64_t pix = ((int64_t)img * H + py) * W + px;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (live) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c + j) : 0.f);
+        if (y_dt == DAFK_F32) {
+          float* o = reinterpret_cast<float*>(y) + pix * Cout + n0 + c;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + pix * Cout + n0 + c;
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight-gradient kernel.  grid = (units, splits); unit = (tap, co-block, ci-block)
+//   D[co (M = BM), ci (N = BN)] += sum over this CTA's pixel tiles of dY^T * X_shift
+// ---------------------------------------------------------------------------------------------
+template <int BM, int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                   const __grid_constant__ CUtensorMap tmDY,
+                                                                   float* __restrict__ dw, int Cin, int cin_off,
+                                                                   int cin_total, int Cout, int KH, int KW, int pad,
+                                                                   TileGeom g, int tiles_per_split) {
+  constexpr int SA = (BM / 64) * A_BYTES;   // dY boxes
+  constexpr int SB = (BN / 64) * A_BYTES;   // X boxes
+  constexpr int STAGE_BYTES = SA + SB;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci_blocks = Cin / BN, co_blocks = Cout / BM;
+  int unit = blockIdx.x;
+  const int cib = unit % ci_blocks; unit /= ci_blocks;
+  const int cob = unit % co_blocks; unit /= co_blocks;
+  const int tap = unit;
+  const int r = tap / KW, q = tap % KW;
+  const int total_tiles = g.tiles_x * g.tiles_y * g.tiles_n;
+  const int t_begin = blockIdx.y * tiles_per_split;
+  const int t_end = min(total_tiles, t_begin + tiles_per_split);
+  const int num_kb = t_end - t_begin;   // one k-block = one 128-pixel tile
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          int t = t_begin + kb;
+          const int txi = t % g.tiles_x; t /= g.tiles_x;
+          const int tyi = t % g.tiles_y; t /= g.tiles_y;
+          const int x0 = txi * g.TW, y0 = tyi * g.TH, img0 = t * g.TN;
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          mbar_expect_tx(full_bar + s, STAGE_BYTES);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+#pragma unroll
+          for (int i = 0; i < BM / 64; ++i)
+            tma_load_4d(sa + i * A_BYTES, &tmDY, full_bar + s, cob * BM + i * 64, x0, y0, img0);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(sa + SA + j * A_BYTES, &tmX, full_bar + s, cib * BN + j * 64, x0 + q - pad, y0 + r - pad,
+                        img0);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);   // both operands MN-major
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + SA;
+#pragma unroll
+          for (int k = 0; k < TILE_PIX / 16; ++k) {
+            // MN-major SW128: one atom = 64 channels (128 B) x 8 pixels; pixel groups of 8 are 1024 B apart
+            // (SBO), the next 64 channels are one whole box = 16 KB away (LBO); 16 pixels per MMA = 2048 B.
+            uint64_t da = make_smem_desc(a_addr + k * 2048, A_BYTES, 1024);
+            uint64_t db = make_smem_desc(b_addr + k * 2048, A_BYTES, 1024);
+            umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + s);
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else {
+      const int q4 = warp & 3;
+      // accumulator row -> TMEM lane: M=128: row = lane index; M=64: rows 16*q..16*q+15 sit in the first
+      // 16 lanes of sub-partition q (lanes 32*q .. 32*q+15)
+      const int row = (BM == 128) ? q4 * 32 + lane : q4 * 16 + lane;
+      const bool row_ok = (BM == 128) || lane < 16;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const int co = cob * BM + row;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ci = cin_off + cib * BN + c + j;
+            atomicAdd(dw + ((int64_t)tap * cin_total + ci) * Cout + co, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: HWIO f32 -> bf16 [tap][Cout][Cin]  (fwd)  or  [tap'][Cin][Cout] with tap' mirrored (dgrad)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int KH, int KW, int Cin,
+                              int Cout, int for_dgrad) {
+  int64_t total = (int64_t)KH * KW * Cin * Cout;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    // i indexes the destination
+    if (!for_dgrad) {
+      int ci = (int)(i % Cin);
+      int64_t t = i / Cin;
+      int co = (int)(t % Cout);
+      int tap = (int)(t / Cout);
+      wp[i] = __float2bfloat16_rn(w[((int64_t)tap * Cin + ci) * Cout + co]);
+    } else {
+      int co = (int)(i % Cout);
+      int64_t t = i / Cout;
+      int ci = (int)(t % Cin);
+      int tapd = (int)(t / Cin);
+      int tap = KH * KW - 1 - tapd;   // mirrored in both axes
+      wp[i] = __float2bfloat16_rn(w[((int64_t)tap * Cin + ci) * Cout + co]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 4-D NHWC bf16 activation map; box = (64 ch, TW, TH, TN)
+static int make_act_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, const TileGeom& g) {
+  PFN_encodeTiled enc = get_encode();
+  DAFK_REQUIRE(enc != nullptr, DAFK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)KBLK, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TN};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DAFK_REQUIRE(r == CUDA_SUCCESS, DAFK_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed with %d", (int)r);
+  return DAFK_OK;
+}
+
+static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  DAFK_REQUIRE(enc != nullptr, DAFK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)KBLK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DAFK_REQUIRE(r == CUDA_SUCCESS, DAFK_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+  return DAFK_OK;
+}
+
+// pick the power-of-two box (TW,TH,TN), TW*TH*TN = 128, that wastes the fewest MMA rows
+static TileGeom pick_geom(int N, int H, int W) {
+  TileGeom best{};
+  double best_eff = -1.0;
+  for (int tw = 1; tw <= 128; tw <<= 1)
+    for (int th = 1; tw * th <= 128; th <<= 1) {
+      int tn = 128 / (tw * th);
+      if (tw > 256 || th > 256 || tn > 256) continue;
+      int64_t cx = (W + tw - 1) / tw, cy = (H + th - 1) / th, cn = (N + tn - 1) / tn;
+      double eff = ((double)N * H * W) / ((double)cx * cy * cn * 128.0);
+      // prefer wider boxes on ties (longer contiguous runs per TMA row)
+      if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && tw > best.TW)) {
+        best_eff = eff;
+        best = TileGeom{tw, th, tn, (int)cx, (int)cy, (int)cn};
+      }
+    }
+  return best;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const float* bias, void* y,
+                      int y_dt, int N, int H, int W, int Cout, int C0, int C1, int KH, int KW, int pad,
+                      const TileGeom& g, cudaStream_t s) {
+  constexpr int smem = STAGES * (A_BYTES + BLOCK_N * KBLK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_fwd_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_fwd) failed: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  int n_blocks = Cout / BLOCK_N;
+  int64_t tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n;
+  dim3 grid((unsigned)(tiles * n_blocks));
+  conv_tc_fwd_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a0, a1, b, bias, y, y_dt, N, H, W, Cout, C0, C1, KH,
+                                                                    KW, pad, g, n_blocks);
+  return check_launch("dafk_conv3x3_tc_fwd");
+}
+
+template <int BM, int BN, int STAGES>
+static int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mdy, float* dw, int Cin, int cin_off, int cin_total,
+                        int Cout, int KH, int KW, int pad, const TileGeom& g, cudaStream_t s) {
+  constexpr int smem = STAGES * ((BM / 64) + (BN / 64)) * A_BYTES + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<BM, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_wgrad) failed: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  int units = KH * KW * (Cout / BM) * (Cin / BN);
+  int total_tiles = g.tiles_x * g.tiles_y * g.tiles_n;
+  int want = (kNumSMs * 2 + units - 1) / units;
+  if (want > total_tiles) want = total_tiles;
+  if (want < 1) want = 1;
+  int per = (total_tiles + want - 1) / want;
+  int splits = (total_tiles + per - 1) / per;
+  conv_tc_wgrad_kernel<BM, BN, STAGES><<<dim3(units, splits), TC_THREADS, smem, s>>>(mx, mdy, dw, Cin, cin_off, cin_total,
+                                                                                    Cout, KH, KW, pad, g, per);
+  return check_launch("dafk_conv3x3_tc_wgrad");
+}
+
+}  // namespace dafk
+
+using namespace dafk;
+
+extern "C" {
+
+int dafk_conv3x3_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp, const float* bias, void* y,
+                        int y_dt, int N, int H, int W, int Cout, void* stream) {
+  DAFK_REQUIRE(N > 0 && H > 0 && W > 0 && C0 > 0 && C1 >= 0 && Cout > 0, DAFK_ERR_BAD_ARG, "dafk_conv3x3_tc_fwd: bad shape");
+  DAFK_REQUIRE(x0 && wp && y && (C1 == 0 || x1), DAFK_ERR_BAD_ARG, "dafk_conv3x3_tc_fwd: null pointer");
+  DAFK_REQUIRE(C0 % KBLK == 0 && C1 % KBLK == 0 && Cout % 64 == 0, DAFK_ERR_UNSUPPORTED,
+               "dafk_conv3x3_tc_fwd: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
+  DAFK_REQUIRE(y_dt == DAFK_F32 || y_dt == DAFK_BF16, DAFK_ERR_BAD_ARG, "dafk_conv3x3_tc_fwd: bad output dtype");
+  DAFK_REQUIRE(DAFK_ALIGNED16(x0) && DAFK_ALIGNED16(x1) && DAFK_ALIGNED16(wp) && DAFK_ALIGNED16(y), DAFK_ERR_ALIGN,
+               "dafk_conv3x3_tc_fwd: pointers must be 16-byte aligned");
+  TileGeom g = pick_geom(N, H, W);
+  CUtensorMap a0, a1, b;
+  int rc = make_act_map(&a0, x0, N, H, W, C0, g);
+  if (rc) return rc;
+  if (C1 > 0) { rc = make_act_map(&a1, x1, N, H, W, C1, g); if (rc) return rc; } else a1 = a0;
+  cudaStream_t s = as_stream(stream);
+  if (Cout % 128 == 0) {
+    rc = make_w_map(&b, wp, 9 * Cout, C0 + C1, 128);
+    if (rc) return rc;
+    return launch_fwd<128, 3>(a0, a1, b, bias, y, y_dt, N, H, W, Cout, C0, C1, 3, 3, 1, g, s);
+  }
+  rc = make_w_map(&b, wp, 9 * Cout, C0 + C1, 64);
+  if (rc) return rc;
+  return launch_fwd<64, 4>(a0, a1, b, bias, y, y_dt, N, H, W, Cout, C0, C1, 3, 3, 1, g, s);
+}
+
+int dafk_pack_conv3x3(const float* w_hwio, void* wp, int Cin, int Cout, int for_dgrad, void* stream) {
+  DAFK_REQUIRE(w_hwio && wp && Cin > 0 && Cout > 0, DAFK_ERR_BAD_ARG, "dafk_pack_conv3x3: bad argument");
+  int64_t total = (int64_t)9 * Cin * Cout;
+  pack_w_kernel<<<bw_grid(total, 256), 256, 0, as_stream(stream)>>>(w_hwio, (__nv_bfloat16*)wp, 3, 3, Cin, Cout, for_dgrad);
+  return check_launch("dafk_pack_conv3x3");
+}
+
+int dafk_conv3x3_tc_wgrad(const void* x, int Cin, int cin_off, int cin_total, const void* dy, int Cout, float* dw,
+                          int N, int H, int W, void* stream) {
+  DAFK_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && cin_off >= 0 && cin_off + Cin <= cin_total,
+               DAFK_ERR_BAD_ARG, "dafk_conv3x3_tc_wgrad: bad shape");
+  DAFK_REQUIRE(x && dy && dw, DAFK_ERR_BAD_ARG, "dafk_conv3x3_tc_wgrad: null pointer");
+  DAFK_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, DAFK_ERR_UNSUPPORTED,
+               "dafk_conv3x3_tc_wgrad: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
+  DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(dy) && DAFK_ALIGNED16(dw), DAFK_ERR_ALIGN,
+               "dafk_conv3x3_tc_wgrad: pointers must be 16-byte aligned");
+  TileGeom g = pick_geom(N, H, W);
+  CUtensorMap mx, mdy;
+  // x is addressed inside its own tensor of Cin channels; cin_off/cin_total place the block inside dw
+  int rc = make_act_map(&mx, x, N, H, W, Cin, g);
+  if (rc) return rc;
+  rc = make_act_map(&mdy, dy, N, H, W, Cout, g);
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  // the kernel adds cin_off to the X channel coordinate; X here is the un-concatenated source, so shift back
+  // by passing cin_off only for the dw placement: handled by giving the kernel a zero-based map.
+  if (Cout % 128 == 0 && Cin % 128 == 0)
+    return launch_wgrad<128, 128, 3>(mx, mdy, dw, Cin, cin_off, cin_total, Cout, 3, 3, 1, g, s);
+  if (Cout % 128 == 0) return launch_wgrad<128, 64, 4>(mx, mdy, dw, Cin, cin_off, cin_total, Cout, 3, 3, 1, g, s);
+  if (Cin % 128 == 0) return launch_wgrad<64, 128, 4>(mx, mdy, dw, Cin, cin_off, cin_total, Cout, 3, 3, 1, g, s);
+  return launch_wgrad<64, 64, 4>(mx, mdy, dw, Cin, cin_off, cin_total, Cout, 3, 3, 1, g, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+// Dense layers with a tiny batch (B <= a few dozen) and a long reduction axis
+// (K up to 270 848): weight-read-bound skinny GEMMs.
+//   fwd        : split-K over CTAs, W streamed once with coalesced rows, x chunk staged in smem
+//   bwd_data   : one thread per k, dy staged in smem, W row walked once
+//   bwd_weight : one thread per (k,n), dy staged in smem
+#include "common.cuh"
+
+namespace dafk {
+
+constexpr int DT = 256;
+constexpr int KC = 128;   // k-chunk per CTA in the forward
+constexpr int MAXB = 32;  // batch rows held in registers
+
+__global__ void dense_init_kernel(float* __restrict__ y, const float* __restrict__ bias, int B, int N) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * N) y[i] = bias ? bias[i % N] : 0.f;
+}
+
+// grid = (ceil(K/KC), ceil(B/MAXB)); y must be pre-initialised with the bias
+__global__ void __launch_bounds__(DT) dense_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       float* __restrict__ y, int B, int64_t K, int N) {
+  __shared__ float xs[MAXB][KC];
+  const int b0 = blockIdx.y * MAXB;
+  const int nb = min(MAXB, B - b0);
+  const int64_t k0 = (int64_t)blockIdx.x * KC;
+  const int kc = (int)min((int64_t)KC, K - k0);
+  for (int e = threadIdx.x; e < MAXB * KC; e += DT) {
+    int b = e / KC, k = e % KC;
+    xs[b][k] = (b < nb && k < kc) ? x[(int64_t)(b0 + b) * K + k0 + k] : 0.f;
+  }
+  __syncthreads();
+  // thread -> (n, k-group)
+  for (int nbase = 0; nbase < N; nbase += DT) {
+    int ncols = min(N - nbase, DT);
+    int groups = DT / ncols;
+    int n = threadIdx.x % ncols, g = threadIdx.x / ncols;
+    if (g >= groups) continue;
+    float acc[MAXB];
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+    for (int k = g; k < kc; k += groups) {
+      float wv = __ldg(w + (k0 + k) * N + nbase + n);
+#pragma unroll
+      for (int b = 0; b < MAXB; ++b) acc[b] = fmaf(xs[b][k], wv, acc[b]);
+    }
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b)
+      if (b < nb) atomicAdd(y + (int64_t)(b0 + b) * N + nbase + n, acc[b]);
+  }
+}
+
+// grid = (ceil(K/DT), ceil(B/MAXB)); dynamic smem: MAXB*N floats
+__global__ void __launch_bounds__(DT) dense_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                            float* __restrict__ dx, int B, int64_t K, int N) {
+  extern __shared__ float dys[];  // [MAXB][N]
+  const int b0 = blockIdx.y * MAXB;
+  const int nb = min(MAXB, B - b0);
+  for (int e = threadIdx.x; e < MAXB * N; e += DT) {
+    int b = e / N, n = e % N;
+    dys[e] = (b < nb) ? dy[(int64_t)(b0 + b) * N + n] : 0.f;
+  }
+  __syncthreads();
+  int64_t k = (int64_t)blockIdx.x * DT + threadIdx.x;
+  if (k >= K) return;
+  float acc[MAXB];
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+  const float* wr = w + k * N;
+  for (int n = 0; n < N; ++n) {
+    float wv = __ldg(wr + n);
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) acc[b] = fmaf(dys[b * N + n], wv, acc[b]);
+  }
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b)
+    if (b < nb) dx[(int64_t)(b0 + b) * K + k] = acc[b];
+}
+
+// one thread per (k,n); dynamic smem: B*N floats
+__global__ void __launch_bounds__(DT) dense_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                              float* __restrict__ dw, float* __restrict__ db, int B,
+                                                              int64_t K, int N) {
+  extern __shared__ float dys[];  // [B][N]
+  for (int e = threadIdx.x; e < B * N; e += DT) dys[e] = dy[e];
+  __syncthreads();
+  if (db && blockIdx.x == 0) {
+    for (int n = threadIdx.x; n < N; n += DT) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += dys[b * N + n];
+      db[n] += s;
+    }
+  }
+  int64_t total = K * N;
+  int64_t stride = (int64_t)gridDim.x * DT;
+  for (int64_t o = (int64_t)blockIdx.x * DT + threadIdx.x; o < total; o += stride) {
+    int64_t k = o / N;
+    int n = (int)(o - k * N);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(__ldg(x + (int64_t)b * K + k), dys[b * N + n], s);
+    dw[o] += s;
+  }
+}
+
+}  // namespace dafk
+
+using namespace dafk;
+
+extern "C" {
+
+int dafk_dense_fwd(const float* x, const float* w, const float* bias, float* y, int B, int64_t K, int Nout,
+                   void* stream) {
+  DAFK_REQUIRE(B >= 0 && K > 0 && Nout > 0, DAFK_ERR_BAD_ARG, "dafk_dense_fwd: bad shape");
+  if (B == 0) return DAFK_OK;
+  DAFK_REQUIRE(x && w && y, DAFK_ERR_BAD_ARG, "dafk_dense_fwd: null pointer");
+  cudaStream_t s = as_stream(stream);
+  dense_init_kernel<<<(B * Nout + 255) / 256, 256, 0, s>>>(y, bias, B, Nout);
+  int rc = check_launch("dafk_dense_fwd(init)");
+  if (rc) return rc;
+  dim3 grid((unsigned)((K + KC - 1) / KC), (B + MAXB - 1) / MAXB);
+  dense_fwd_kernel<<<grid, DT, 0, s>>>(x, w, y, B, K, Nout);
+  return check_launch("dafk_dense_fwd");
+}
+
+int dafk_dense_bwd_data(const float* dy, const float* w, float* dx, int B, int64_t K, int Nout, void* stream) {
+  DAFK_REQUIRE(B >= 0 && K > 0 && Nout > 0, DAFK_ERR_BAD_ARG, "dafk_dense_bwd_data: bad shape");
+  if (B == 0) return DAFK_OK;
+  DAFK_REQUIRE(dy && w && dx, DAFK_ERR_BAD_ARG, "dafk_dense_bwd_data: null pointer");
+  size_t smem = sizeof(float) * MAXB * Nout;
+  DAFK_REQUIRE(smem <= 48 * 1024, DAFK_ERR_UNSUPPORTED, "dafk_dense_bwd_data: Nout too large (%d)", Nout);
+  dim3 grid((unsigned)((K + DT - 1) / DT), (B + MAXB - 1) / MAXB);
+  dense_bwd_data_kernel<<<grid, DT, smem, as_stream(stream)>>>(dy, w, dx, B, K, Nout);
+  return check_launch("dafk_dense_bwd_data");
+}
+
+int dafk_dense_bwd_weight(const float* x, const float* dy, float* dw, float* db, int B, int64_t K, int Nout,
+                          void* stream) {
+  DAFK_REQUIRE(B >= 0 && K > 0 && Nout > 0, DAFK_ERR_BAD_ARG, "dafk_dense_bwd_weight: bad shape");
+  if (B == 0) return DAFK_OK;
+  DAFK_REQUIRE(x && dy && dw, DAFK_ERR_BAD_ARG, "dafk_dense_bwd_weight: null pointer");
+  size_t smem = sizeof(float) * B * Nout;
+  DAFK_REQUIRE(smem <= 48 * 1024, DAFK_ERR_UNSUPPORTED, "dafk_dense_bwd_weight: B*Nout too large");
+  int64_t total = K * Nout;
+  int grid = bw_grid(total, DT, 8);
+  dense_bwd_weight_kernel<<<grid, DT, smem, as_stream(stream)>>>(x, dy, dw, db, B, K, Nout);
+  return check_launch("dafk_dense_bwd_weight");
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+// MaxPooling2D(2,2), UpSampling2D(2) and nearest-neighbour resize on NHWC feature maps
+// (f32 or bf16 storage).  One 4-channel vector per thread-iteration, grid-stride.
+#include "common.cuh"
+
+namespace dafk {
+
+constexpr int TPB = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(TPB) maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H,
+                                                           int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1, C4 = C >> 2;
+  int64_t total = (int64_t)N * Ho * Wo * C4;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int c4 = (int)(i % C4);
+    int64_t p = i / C4;
+    int wo = (int)(p % Wo); p /= Wo;
+    int ho = (int)(p % Ho);
+    int n = (int)(p / Ho);
+    const T* base = x + (((int64_t)n * H + 2 * ho) * W + 2 * wo) * C + 4 * c4;
+    float a[4], b[4], c[4], d[4], r[4];
+    Vec4<T>::load(base, a);
+    Vec4<T>::load(base + C, b);
+    Vec4<T>::load(base + (int64_t)W * C, c);
+    Vec4<T>::load(base + (int64_t)W * C + C, d);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = fmaxf(fmaxf(a[k], b[k]), fmaxf(c[k], d[k]));
+    Vec4<T>::store(y + (((int64_t)n * Ho + ho) * Wo + wo) * C + 4 * c4, r);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TPB) maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                           T* __restrict__ dx, int N, int H, int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1, C4 = C >> 2;
+  int64_t total = (int64_t)N * Ho * Wo * C4;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int c4 = (int)(i % C4);
+    int64_t p = i / C4;
+    int wo = (int)(p % Wo); p /= Wo;
+    int ho = (int)(p % Ho);
+    int n = (int)(p / Ho);
+    int64_t o00 = (((int64_t)n * H + 2 * ho) * W + 2 * wo) * C + 4 * c4;
+    int64_t o01 = o00 + C, o10 = o00 + (int64_t)W * C, o11 = o10 + C;
+    float a[4], b[4], c[4], d[4], g[4];
+    Vec4<T>::load(x + o00, a);
+    Vec4<T>::load(x + o01, b);
+    Vec4<T>::load(x + o10, c);
+    Vec4<T>::load(x + o11, d);
+    Vec4<T>::load(dy + (((int64_t)n * Ho + ho) * Wo + wo) * C + 4 * c4, g);
+    float ga[4], gb[4], gc[4], gd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // first maximum in row-major window order
+      int arg = 0; float m = a[k];
+      if (b[k] > m) { m = b[k]; arg = 1; }
+      if (c[k] > m) { m = c[k]; arg = 2; }
+      if (d[k] > m) { m = d[k]; arg = 3; }
+      ga[k] = arg == 0 ? g[k] : 0.f;
+      gb[k] = arg == 1 ? g[k] : 0.f;
+      gc[k] = arg == 2 ? g[k] : 0.f;
+      gd[k] = arg == 3 ? g[k] : 0.f;
+    }
+    Vec4<T>::store(dx + o00, ga);
+    Vec4<T>::store(dx + o01, gb);
+    Vec4<T>::store(dx + o10, gc);
+    Vec4<T>::store(dx + o11, gd);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TPB) upsample2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H,
+                                                            int W, int C) {
+  const int Ho = 2 * H, Wo = 2 * W, C4 = C >> 2;
+  int64_t total = (int64_t)N * Ho * Wo * C4;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int c4 = (int)(i % C4);
+    int64_t p = i / C4;
+    int wo = (int)(p % Wo); p /= Wo;
+    int ho = (int)(p % Ho);
+    int n = (int)(p / Ho);
+    float v[4];
+    Vec4<T>::load(x + (((int64_t)n * H + (ho >> 1)) * W + (wo >> 1)) * C + 4 * c4, v);
+    Vec4<T>::store(y + 4 * i, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TPB) upsample2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H,
+                                                            int W, int C) {
+  const int Wo = 2 * W, C4 = C >> 2;
+  int64_t total = (int64_t)N * H * W * C4;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int c4 = (int)(i % C4);
+    int64_t p = i / C4;
+    int w = (int)(p % W); p /= W;
+    int h = (int)(p % H);
+    int n = (int)(p / H);
+    const T* base = dy + (((int64_t)n * 2 * H + 2 * h) * Wo + 2 * w) * C + 4 * c4;
+    float a[4], b[4], c[4], d[4], r[4];
+    Vec4<T>::load(base, a);
+    Vec4<T>::load(base + C, b);
+    Vec4<T>::load(base + (int64_t)Wo * C, c);
+    Vec4<T>::load(base + (int64_t)Wo * C + C, d);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = (a[k] + b[k]) + (c[k] + d[k]);
+    Vec4<T>::store(dx + 4 * i, r);
+  }
+}
+
+__global__ void __launch_bounds__(TPB) resize_nn_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N,
+                                                            int H, int W, int C, int Ho, int Wo) {
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int wo = (int)(p % Wo); p /= Wo;
+    int ho = (int)(p % Ho);
+    int n = (int)(p / Ho);
+    int sh = min((int)(((int64_t)ho * H) / Ho), H - 1);
+    int sw = min((int)(((int64_t)wo * W) / Wo), W - 1);
+    y[i] = x[(((int64_t)n * H + sh) * W + sw) * C + c];
+  }
+}
+
+__global__ void __launch_bounds__(TPB) resize_nn_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N,
+                                                            int H, int W, int C, int Ho, int Wo) {
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int wo = (int)(p % Wo); p /= Wo;
+    int ho = (int)(p % Ho);
+    int n = (int)(p / Ho);
+    int sh = min((int)(((int64_t)ho * H) / Ho), H - 1);
+    int sw = min((int)(((int64_t)wo * W) / Wo), W - 1);
+    atomicAdd(dx + (((int64_t)n * H + sh) * W + sw) * C + c, dy[i]);
+  }
+}
+
+}  // namespace dafk
+
+using namespace dafk;
+
+#define POOL_CHECKS(name)                                                                                   \
+  DAFK_REQUIRE(N >= 0 && H >= 0 && W >= 0 && C > 0, DAFK_ERR_BAD_ARG, name ": bad shape");                   \
+  DAFK_REQUIRE(C % 4 == 0, DAFK_ERR_UNSUPPORTED, name ": C must be a multiple of 4 (got %d)", C);           \
+  DAFK_REQUIRE(dt == DAFK_F32 || dt == DAFK_BF16, DAFK_ERR_BAD_ARG, name ": bad dtype %d", dt);
+
+extern "C" {
+
+int dafk_maxpool2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, void* stream) {
+  POOL_CHECKS("dafk_maxpool2_fwd");
+  int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 4);
+  if (total == 0) return DAFK_OK;
+  DAFK_REQUIRE(x && y, DAFK_ERR_BAD_ARG, "dafk_maxpool2_fwd: null pointer");
+  DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(y), DAFK_ERR_ALIGN, "dafk_maxpool2_fwd: alignment");
+  cudaStream_t s = as_stream(stream);
+  if (dt == DAFK_F32) maxpool2_fwd_kernel<float><<<bw_grid(total, TPB), TPB, 0, s>>>((const float*)x, (float*)y, N, H, W, C);
+  else maxpool2_fwd_kernel<__nv_bfloat16><<<bw_grid(total, TPB), TPB, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C);
+  return check_launch("dafk_maxpool2_fwd");
+}
+
+int dafk_maxpool2_bwd(const void* x, const void* dy, void* dx, int dt, int N, int H, int W, int C, void* stream) {
+  POOL_CHECKS("dafk_maxpool2_bwd");
+  int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 4);
+  if ((int64_t)N * H * W == 0) return DAFK_OK;
+  DAFK_REQUIRE(x && dy && dx, DAFK_ERR_BAD_ARG, "dafk_maxpool2_bwd: null pointer");
+  DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(dy) && DAFK_ALIGNED16(dx), DAFK_ERR_ALIGN, "dafk_maxpool2_bwd: alignment");
+  cudaStream_t s = as_stream(stream);
+  size_t esz = dt == DAFK_F32 ? 4 : 2;
+  if ((H & 1) || (W & 1)) cudaMemsetAsync(dx, 0, (size_t)N * H * W * C * esz, s);  // uncovered last row/col
+  if (total == 0) return DAFK_OK;
+  if (dt == DAFK_F32) maxpool2_bwd_kernel<float><<<bw_grid(total, TPB), TPB, 0, s>>>((const float*)x, (const float*)dy, (float*)dx, N, H, W, C);
+  else maxpool2_bwd_kernel<__nv_bfloat16><<<bw_grid(total, TPB), TPB, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, N, H, W, C);
+  return check_launch("dafk_maxpool2_bwd");
+}
+
+int dafk_upsample2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, void* stream) {
+  POOL_CHECKS("dafk_upsample2_fwd");
+  int64_t total = (int64_t)N * 4 * H * W * (C / 4);
+  if (total == 0) return DAFK_OK;
+  DAFK_REQUIRE(x && y, DAFK_ERR_BAD_ARG, "dafk_upsample2_fwd: null pointer");
+  DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(y), DAFK_ERR_ALIGN, "dafk_upsample2_fwd: alignment");
+  cudaStream_t s = as_stream(stream);
+  if (dt == DAFK_F32) upsample2_fwd_kernel<float><<<bw_grid(total, TPB), TPB, 0, s>>>((const float*)x, (float*)y, N, H, W, C);
+  else upsample2_fwd_kernel<__nv_bfloat16><<<bw_grid(total, TPB), TPB, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C);
+  return check_launch("dafk_upsample2_fwd");
+}
+
+int dafk_upsample2_bwd(const void* dy, void* dx, int dt, int N, int H, int W, int C, void* stream) {
+  POOL_CHECKS("dafk_upsample2_bwd");
+  int64_t total = (int64_t)N * H * W * (C / 4);
+  if (total == 0) return DAFK_OK;
+  DAFK_REQUIRE(dy && dx, DAFK_ERR_BAD_ARG, "dafk_upsample2_bwd: null pointer");
+  DAFK_REQUIRE(DAFK_ALIGNED16(dy) && DAFK_ALIGNED16(dx), DAFK_ERR_ALIGN, "dafk_upsample2_bwd: alignment");
+  cudaStream_t s = as_stream(stream);
+  if (dt == DAFK_F32) upsample2_bwd_kernel<float><<<bw_grid(total, TPB), TPB, 0, s>>>((const float*)dy, (float*)dx, N, H, W, C);
+  else upsample2_bwd_kernel<__nv_bfloat16><<<bw_grid(total, TPB), TPB, 0, s>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, N, H, W, C);
+  return check_launch("dafk_upsample2_bwd");
+}
+
+int dafk_resize_nn_fwd(const float* x, float* y, int N, int H, int W, int C, int Ho, int Wo, void* stream) {
+  DAFK_REQUIRE(N >= 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, DAFK_ERR_BAD_ARG, "dafk_resize_nn_fwd: bad shape");
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  if (total == 0) return DAFK_OK;
+  DAFK_REQUIRE(x && y, DAFK_ERR_BAD_ARG, "dafk_resize_nn_fwd: null pointer");
+  resize_nn_fwd_kernel<<<bw_grid(total, TPB), TPB, 0, as_stream(stream)>>>(x, y, N, H, W, C, Ho, Wo);
+  return check_launch("dafk_resize_nn_fwd");
+}
+
+int dafk_resize_nn_bwd(const float* dy, float* dx, int N, int H, int W, int C, int Ho, int Wo, void* stream) {
+  DAFK_REQUIRE(N >= 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, DAFK_ERR_BAD_ARG, "dafk_resize_nn_bwd: bad shape");
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  if (N == 0) return DAFK_OK;
+  DAFK_REQUIRE(dy && dx, DAFK_ERR_BAD_ARG, "dafk_resize_nn_bwd: null pointer");
+  cudaStream_t s = as_stream(stream);
+  cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)N * H * W * C, s);
+  resize_nn_bwd_kernel<<<bw_grid(total, TPB), TPB, 0, s>>>(dy, dx, N, H, W, C, Ho, Wo);
+  return check_launch("dafk_resize_nn_bwd");
+}
+
+}  // extern "C"

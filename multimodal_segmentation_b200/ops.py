@@ -1,0 +1,529 @@
+"""Thin, allocation-only wrappers over the C-ABI kernels (``include/dafk.h``).
+
+Every function here takes CUDA torch tensors (used purely as device-memory handles), allocates
+the outputs with the caching allocator and enqueues ONE OR MORE hand-written kernels on torch's
+current stream through ctypes.  No arithmetic is done by torch.  There is no autograd here --
+the reverse pass is recorded by ``tape.py``.
+"""
+import torch
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, DAFK_BF16, DAFK_F32, ConvDesc, call
+
+_S = _lib.stream_ptr
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return DAFK_F32
+    if t.dtype == torch.bfloat16:
+        return DAFK_BF16
+    raise TypeError("unsupported dtype %s" % t.dtype)
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.DafkError("dafk kernels need CUDA tensors; there is no CPU fallback")
+        if not t.is_contiguous():
+            raise _lib.DafkError("dafk kernels need contiguous tensors")
+
+
+def f32(*shape, device="cuda"):
+    return torch.empty(*shape, dtype=torch.float32, device=device)
+
+
+# ---------------------------------------------------------------------------- pointwise
+def round_fwd(x):
+    _chk(x)
+    y = torch.empty_like(x)
+    call("round_fwd", x, y, x.numel(), _S())
+    return y
+
+
+def softmax_fwd(x, want_round=False):
+    _chk(x)
+    C = x.shape[-1]
+    p = torch.empty_like(x)
+    r = torch.empty_like(x) if want_round else None
+    call("softmax_fwd", x, p, r, x.numel() // C, C, _S())
+    return p, r
+
+
+def softmax_bwd(p, dp):
+    _chk(p, dp)
+    C = p.shape[-1]
+    dx = torch.empty_like(p)
+    call("softmax_bwd", p, dp, dx, p.numel() // C, C, _S())
+    return dx
+
+
+def act_fwd(x, act, alpha=0.0, inplace=False):
+    _chk(x)
+    y = x if inplace else torch.empty_like(x)
+    call("act_fwd", x, y, x.numel(), act, float(alpha), _S())
+    return y
+
+
+def act_bwd(dy, y, act, alpha=0.0, inplace=False):
+    _chk(dy, y)
+    dx = dy if inplace else torch.empty_like(dy)
+    call("act_bwd", dy, y, dx, y.numel(), act, float(alpha), _S())
+    return dx
+
+
+def add(a, b, out=None):
+    _chk(a, b)
+    out = torch.empty_like(a) if out is None else out
+    call("add", a, b, out, a.numel(), _S())
+    return out
+
+
+def add_(a, b):
+    """a += b"""
+    return add(a, b, out=a)
+
+
+def axpby_(a, x, b, y):
+    """y = a*x + b*y"""
+    _chk(x, y)
+    call("axpby", float(a), x, float(b), y, x.numel(), _S())
+    return y
+
+
+def fill_(x, v):
+    _chk(x)
+    call("fill", x, float(v), x.numel(), _S())
+    return x
+
+
+def zero_(t):
+    """cudaMemsetAsync on the current stream (no torch kernel)."""
+    _chk(t)
+    call("memset_zero", t, t.numel() * t.element_size(), _S())
+    return t
+
+
+def zeros(*shape, dtype=torch.float32):
+    return zero_(torch.empty(*shape, dtype=dtype, device="cuda"))
+
+
+def cast(x, dtype):
+    _chk(x)
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    call("cast", x, _dt(x), y, _dt(y), x.numel(), _S())
+    return y
+
+
+def copy_channels(src, src_off, dst, dst_off, c, accumulate=False):
+    _chk(src, dst)
+    M = src.numel() // src.shape[-1]
+    call("copy_channels", src, src.shape[-1], src_off, dst, dst.shape[-1], dst_off, c, M, int(accumulate), _S())
+    return dst
+
+
+def concat_channels(tensors):
+    C = sum(t.shape[-1] for t in tensors)
+    out = f32(*tensors[0].shape[:-1], C)
+    off = 0
+    for t in tensors:
+        copy_channels(t, 0, out, off, t.shape[-1])
+        off += t.shape[-1]
+    return out
+
+
+def slice_channels(x, off, c):
+    out = f32(*x.shape[:-1], c)
+    copy_channels(x, off, out, 0, c)
+    return out
+
+
+def gather_rows(src, idx):
+    _chk(src, idx)
+    rows = idx.numel()
+    row_elems = src.numel() // src.shape[0]
+    out = torch.empty((rows,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    call("gather_rows", src, idx, out, rows, row_elems, _S())
+    return out
+
+
+# ---------------------------------------------------------------------------- FiLM / Maximum
+def film_fwd(x, gamma, beta):
+    _chk(x, gamma, beta)
+    B, C = x.shape[0], x.shape[-1]
+    y = torch.empty_like(x)
+    call("film_fwd", x, gamma, beta, y, B, x.numel() // (B * C), C, _S())
+    return y
+
+
+def film_bwd(dy, x, gamma):
+    _chk(dy, x, gamma)
+    B, C = x.shape[0], x.shape[-1]
+    dx = torch.empty_like(x)
+    dg = f32(B, C)
+    db = f32(B, C)
+    ws = torch.empty(B * C * 2, dtype=torch.float64, device=x.device)
+    call("film_bwd", dy, x, gamma, dx, dg, db, ws, B, x.numel() // (B * C), C, _S())
+    return dx, dg, db
+
+
+def max_fwd(a, b):
+    _chk(a, b)
+    out = torch.empty_like(a)
+    call("max_fwd", a, b, out, a.numel(), _S())
+    return out
+
+
+def max_bwd(a, b, dout):
+    _chk(a, b, dout)
+    da, db = torch.empty_like(a), torch.empty_like(a)
+    call("max_bwd", a, b, dout, da, db, a.numel(), _S())
+    return da, db
+
+
+# ---------------------------------------------------------------------------- batch norm
+def bn_stats_finalize(x, eps, momentum, moving_mean=None, moving_var=None):
+    _chk(x)
+    C = x.shape[-1]
+    M = x.numel() // C
+    acc = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+    zero_(acc)
+    call("bn_stats", x, acc, M, C, _S())
+    mean, rstd = f32(C), f32(C)
+    call("bn_finalize", acc, M, C, float(eps), float(momentum), mean, rstd, moving_mean, moving_var, _S())
+    return mean, rstd
+
+
+def bn_rstd_from_var(var, eps):
+    rstd = torch.empty_like(var)
+    call("bn_rstd_from_var", var, rstd, var.numel(), float(eps), _S())
+    return rstd
+
+
+def bn_apply(x, mean, rstd, gamma, beta, act=ACT_NONE, out_dtype=torch.float32):
+    _chk(x)
+    C = x.shape[-1]
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    call("bn_apply", x, mean, rstd, gamma, beta, out, _dt(out), x.numel() // C, C, act, _S())
+    return out
+
+
+def bn_bwd(dout, x, mean, rstd, gamma, beta, act, dgamma, dbeta, dx_dtype=torch.float32):
+    """training-mode backward; dgamma/dbeta are accumulated into (may be None)."""
+    _chk(dout, x)
+    C = x.shape[-1]
+    M = x.numel() // C
+    acc = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+    zero_(acc)
+    call("bn_bwd_reduce", dout, _dt(dout), x, mean, rstd, gamma, beta, acc, M, C, act, _S())
+    dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
+    call("bn_bwd_apply", dout, _dt(dout), x, mean, rstd, gamma, beta, acc, dx, _dt(dx), dgamma, dbeta, M, C, act, _S())
+    return dx
+
+
+def bn_bwd_frozen(dout, x, mean, rstd, gamma, beta, act):
+    _chk(dout, x)
+    C = x.shape[-1]
+    dx = torch.empty_like(x)
+    call("bn_bwd_frozen", dout, x, mean, rstd, gamma, beta, dx, x.numel() // C, C, act, _S())
+    return dx
+
+
+# ---------------------------------------------------------------------------- pooling
+def maxpool2_fwd(x):
+    _chk(x)
+    N, H, W, C = x.shape
+    y = torch.empty((N, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+    call("maxpool2_fwd", x, y, _dt(x), N, H, W, C, _S())
+    return y
+
+
+def maxpool2_bwd(x, dy):
+    _chk(x, dy)
+    N, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    call("maxpool2_bwd", x, dy, dx, _dt(x), N, H, W, C, _S())
+    return dx
+
+
+def upsample2_fwd(x):
+    _chk(x)
+    N, H, W, C = x.shape
+    y = torch.empty((N, 2 * H, 2 * W, C), dtype=x.dtype, device=x.device)
+    call("upsample2_fwd", x, y, _dt(x), N, H, W, C, _S())
+    return y
+
+
+def upsample2_bwd(dy):
+    _chk(dy)
+    N, H2, W2, C = dy.shape
+    dx = torch.empty((N, H2 // 2, W2 // 2, C), dtype=dy.dtype, device=dy.device)
+    call("upsample2_bwd", dy, dx, _dt(dy), N, H2 // 2, W2 // 2, C, _S())
+    return dx
+
+
+def resize_nn_fwd(x, Ho, Wo):
+    _chk(x)
+    N, H, W, C = x.shape
+    y = f32(N, Ho, Wo, C)
+    call("resize_nn_fwd", x, y, N, H, W, C, Ho, Wo, _S())
+    return y
+
+
+def resize_nn_bwd(dy, H, W):
+    _chk(dy)
+    N, Ho, Wo, C = dy.shape
+    dx = f32(N, H, W, C)
+    call("resize_nn_bwd", dy, dx, N, H, W, C, Ho, Wo, _S())
+    return dx
+
+
+# ---------------------------------------------------------------------------- convolution
+def conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad):
+    Ho = (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    return ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo)
+
+
+def conv2d_fwd(x, w, bias, stride=1, pad=0, act=ACT_NONE, alpha=0.0):
+    _chk(x, w, bias)
+    N, H, W, Cin = x.shape
+    KH, KW, _, Cout = w.shape
+    d = conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad)
+    y = f32(N, d.Ho, d.Wo, Cout)
+    call("conv2d_fwd", d, x, w, bias, y, act, float(alpha), _S())
+    return y
+
+
+def conv2d_dgrad(dy, w, x_shape, stride=1, pad=0):
+    _chk(dy, w)
+    N, H, W, Cin = x_shape
+    KH, KW, _, Cout = w.shape
+    d = conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad)
+    dx = f32(N, H, W, Cin)
+    call("conv2d_dgrad", d, dy, w, dx, _S())
+    return dx
+
+
+def conv2d_wgrad(x, dy, dw, db, stride=1, pad=0):
+    """dw += ..., db += ... (db may be None)"""
+    _chk(x, dy, dw, db)
+    N, H, W, Cin = x.shape
+    KH, KW, _, Cout = dw.shape
+    d = conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad)
+    call("conv2d_wgrad", d, x, dy, dw, db, _S())
+
+
+def colsum_(x, out):
+    _chk(x, out)
+    C = x.shape[-1]
+    call("colsum", x, out, x.numel() // C, C, _S())
+    return out
+
+
+def pack_conv3x3(w_hwio, for_dgrad=False):
+    _chk(w_hwio)
+    _, _, Cin, Cout = w_hwio.shape
+    shape = (9, Cin, Cout) if for_dgrad else (9, Cout, Cin)
+    wp = torch.empty(shape, dtype=torch.bfloat16, device=w_hwio.device)
+    call("pack_conv3x3", w_hwio, wp, Cin, Cout, int(for_dgrad), _S())
+    return wp
+
+
+def conv3x3_tc_fwd(x0, x1, wp, bias, Cout, out_dtype=torch.float32):
+    """tcgen05 path; x0 (and optional x1 = second concat source) are bf16 NHWC."""
+    _chk(x0, x1, wp, bias)
+    N, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[-1]
+    y = torch.empty((N, H, W, Cout), dtype=out_dtype, device=x0.device)
+    call("conv3x3_tc_fwd", x0, C0, x1, C1, wp, bias, y, _dt(y), N, H, W, Cout, _S())
+    return y
+
+
+def conv3x3_tc_wgrad(x, dy, dw, cin_off=0):
+    """dw[3,3,cin_total,Cout] (f32 HWIO) += x (*) dy for the channel block starting at cin_off."""
+    _chk(x, dy, dw)
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    call("conv3x3_tc_wgrad", x, Cin, cin_off, dw.shape[2], dy, Cout, dw, N, H, W, _S())
+
+
+# ---------------------------------------------------------------------------- dense
+def dense_fwd(x, w, bias):
+    _chk(x, w, bias)
+    B, K = x.shape
+    N = w.shape[1]
+    y = f32(B, N)
+    call("dense_fwd", x, w, bias, y, B, K, N, _S())
+    return y
+
+
+def dense_bwd_data(dy, w):
+    _chk(dy, w)
+    B, N = dy.shape
+    K = w.shape[0]
+    dx = f32(B, K)
+    call("dense_bwd_data", dy, w, dx, B, K, N, _S())
+    return dx
+
+
+def dense_bwd_weight(x, dy, dw, db):
+    _chk(x, dy, dw, db)
+    B, K = x.shape
+    call("dense_bwd_weight", x, dy, dw, db, B, K, dy.shape[1], _S())
+
+
+# ---------------------------------------------------------------------------- TPS
+_tps_consts_cache = {}
+
+
+def tps_consts(cp_h, cp_w, device):
+    key = (cp_h, cp_w, str(device))
+    if key not in _tps_consts_cache:
+        n = cp_h * cp_w
+        nfl = _lib.lib().fn["dafk_tps_consts_floats"](n)
+        host = torch.empty(nfl, dtype=torch.float32)
+        call("tps_build_constants", cp_h, cp_w, host)
+        _tps_consts_cache[key] = host.to(device)
+    return _tps_consts_cache[key]
+
+
+def tps_warp_fwd(vol, theta, cp=(5, 5), want_locs=False):
+    _chk(vol, theta)
+    B, H, W, C = vol.shape
+    consts = tps_consts(cp[0], cp[1], vol.device)
+    out = torch.empty_like(vol)
+    locs = f32(B, H * W, 2) if want_locs else None
+    call("tps_warp_fwd", vol, theta, consts, out, locs, B, H, W, C, cp[0] * cp[1], _S())
+    return out, locs
+
+
+def tps_warp_bwd(vol, theta, dout, cp=(5, 5), need_dvol=True):
+    _chk(vol, theta, dout)
+    B, H, W, C = vol.shape
+    n = cp[0] * cp[1]
+    consts = tps_consts(cp[0], cp[1], vol.device)
+    dvol = None
+    if need_dvol:
+        dvol = zero_(torch.empty_like(vol))
+    dtheta = f32(B, n, 2)
+    ws = torch.empty(B * (n + 3) * 2, dtype=torch.float64, device=vol.device)
+    call("tps_warp_bwd", vol, theta, consts, dout, dvol, dtheta, ws, B, H, W, C, n, _S())
+    return dvol, dtheta
+
+
+def tps_solve(train_points, train_values, order=2, reg=0.0):
+    _chk(train_points, train_values)
+    B, n, _ = train_points.shape
+    k = train_values.shape[-1]
+    w, v = f32(B, n, k), f32(B, 3, k)
+    call("tps_solve_batched", train_points, train_values, w, v, B, n, k, order, float(reg), _S())
+    return w, v
+
+
+def tps_apply(query, train_points, w, v, order=2):
+    _chk(query, train_points, w, v)
+    B, n, k = w.shape
+    qb = 1 if (query.shape[0] == B and B > 1) else 0
+    m = query.shape[1]
+    out = f32(B, m, k)
+    call("tps_apply", query, train_points, w, v, out, B, m, n, k, order, qb, _S())
+    return out
+
+
+def resampler_fwd(vol, warp):
+    _chk(vol, warp)
+    B, H, W, C = vol.shape
+    m = warp.shape[1]
+    out = f32(B, m, C)
+    call("resampler_fwd", vol, warp, out, B, H, W, C, m, _S())
+    return out
+
+
+# ---------------------------------------------------------------------------- losses
+def segloss(pred, target, nch, use_bce, weight, loss, lambda_bce=0.01, want_grad=True):
+    """loss[0] += weight*(dice + lambda*wbce); returns d(weight*loss)/dpred (or None)."""
+    _chk(pred, target, loss)
+    B, Cp, Ct = pred.shape[0], pred.shape[-1], target.shape[-1]
+    HW = pred.numel() // (B * Cp)
+    nws = _lib.lib().fn["dafk_segloss_ws_doubles"](B, Cp)
+    ws = torch.empty(nws, dtype=torch.float64, device=pred.device)
+    call("segloss_fwd", pred, Cp, target, Ct, nch, int(use_bce), float(lambda_bce), ws, B, HW, _S())
+    call("segloss_finish", ws, float(weight), loss, B, Cp, nch, int(use_bce), float(lambda_bce), HW, _S())
+    if not want_grad:
+        return None
+    dpred = torch.empty_like(pred)
+    call("segloss_bwd", pred, Cp, target, Ct, nch, int(use_bce), float(lambda_bce), ws, float(weight), dpred, B, HW, _S())
+    return dpred
+
+
+def l1l2_loss(pred, target, kind, weight, loss, cval=0.0, want_grad=True):
+    _chk(pred, target, loss)
+    dpred = torch.empty_like(pred) if want_grad else None
+    call("l1l2_loss", pred, target, float(cval), kind, float(weight), loss, dpred, pred.numel(), _S())
+    return dpred
+
+
+def vae_fwd(mu, logvar, eps, weight, loss):
+    _chk(mu, logvar, eps)
+    B, Z = mu.shape
+    z, klv = torch.empty_like(mu), f32(B, 1)
+    call("vae_fwd", mu, logvar, eps, z, klv, float(weight), loss, B, Z, _S())
+    return z, klv
+
+
+def vae_bwd(mu, logvar, eps, dz, weight):
+    B, Z = mu.shape
+    dmu, dlv = torch.empty_like(mu), torch.empty_like(mu)
+    call("vae_bwd", mu, logvar, eps, dz, float(weight), dmu, dlv, B, Z, _S())
+    return dmu, dlv
+
+
+def spectral_reg(W2d, u0, alpha, loss, dW):
+    _chk(W2d, u0)
+    dim, cout = W2d.shape
+    ws = f32(2 * dim + cout + 4)
+    call("spectral_reg", W2d, u0, float(alpha), loss, dW, ws, dim, cout, _S())
+
+
+def adam_step(p, g, m, v, shadow, lr_t, b1=0.9, b2=0.999, eps=1e-7, grad_scale=1.0):
+    _chk(p, g, m, v)
+    call("adam_step", p, g, m, v, shadow, p.numel(), float(lr_t), float(b1), float(b2), float(eps), float(grad_scale), _S())
+
+
+# ---------------------------------------------------------------------------- SPADE / balancer
+def in_stats(x):
+    _chk(x)
+    B = x.shape[0]
+    acc = torch.empty(2 * B, dtype=torch.float64, device=x.device)
+    zero_(acc)
+    call("in_stats", x, acc, B, x.numel() // B, _S())
+    return acc
+
+
+def spade_fwd(x, acc, gamma, beta, act=ACT_LRELU, alpha=0.2, eps=1e-3):
+    _chk(x, gamma, beta)
+    B = x.shape[0]
+    y = torch.empty_like(x)
+    call("spade_fwd", x, acc, gamma, beta, y, B, x.numel() // B, float(eps), act, float(alpha), _S())
+    return y
+
+
+def spade_bwd(dy, x, acc, gamma, beta, act=ACT_LRELU, alpha=0.2, eps=1e-3):
+    _chk(dy, x, gamma, beta)
+    B = x.shape[0]
+    dx, dg, db = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    ws = torch.empty(2 * B, dtype=torch.float64, device=x.device)
+    call("spade_bwd", dy, x, acc, gamma, beta, dx, dg, db, ws, B, x.numel() // B, float(eps), act, float(alpha), _S())
+    return dx, dg, db
+
+
+def pair_dice(a, b):
+    _chk(a, b)
+    B = a.shape[0]
+    out = f32(B, 1)
+    ws = torch.empty(3 * B, dtype=torch.float64, device=a.device)
+    call("pair_dice", a, b, out, ws, B, a.numel() // B, _S())
+    return out

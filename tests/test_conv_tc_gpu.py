@@ -1,0 +1,110 @@
+"""Parity of the tcgen05/TMEM/TMA convolution path against the oracle.
+
+The kernels take bf16 operands and accumulate in fp32, so the oracle is evaluated on the SAME
+bf16-rounded inputs in fp64: what remains is accumulation-order noise (tolerance 1e-4 relative
+L2 for forward/dgrad, 1e-3 for the atomically reduced weight gradient).  Against the unrounded
+fp32 oracle the bound is the north-star 1e-2 for bf16 conv paths.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops as R
+from tests.util import cpu, gpu, rel_l2, t
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from multimodal_segmentation_b200 import ops as o
+    return o
+
+
+def bf16_round(a):
+    return torch.as_tensor(a).to(torch.bfloat16).float().numpy()
+
+
+CASES = [
+    # N, H, W, C0, C1, Cout
+    (2, 16, 16, 64, 0, 64),      # exact tiles
+    (1, 24, 40, 64, 0, 64),      # partial tiles in both directions
+    (2, 16, 16, 64, 64, 64),     # two K sources (concat)
+    (2, 16, 16, 128, 0, 128),    # BLOCK_N = 128 path
+    (4, 14, 14, 128, 128, 256),  # deep layer shape: multi-image boxes, 2 n-blocks
+    (3, 7, 7, 128, 0, 128),      # SPADE head resolution
+    (1, 56, 56, 64, 0, 64),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv3x3_tc_forward(ops, case):
+    N, H, W, C0, C1, Cout = case
+    r = np.random.RandomState(sum(case))
+    Cin = C0 + C1
+    x = bf16_round(r.normal(size=(N, H, W, Cin)).astype(np.float32))
+    w = bf16_round((r.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32))
+    b = r.normal(size=Cout).astype(np.float32)
+    yr = R.conv2d(t(x, torch.float64), t(w, torch.float64), t(b, torch.float64), 1, "same").numpy()
+    wp = ops.pack_conv3x3(gpu(w))
+    x0 = gpu(x[..., :C0], torch.bfloat16)
+    x1 = gpu(x[..., C0:], torch.bfloat16) if C1 else None
+    y = ops.conv3x3_tc_fwd(x0, x1, wp, gpu(b), Cout)
+    err = rel_l2(cpu(y), yr)
+    assert err < 1e-4, err
+    yb = ops.conv3x3_tc_fwd(x0, x1, wp, gpu(b), Cout, out_dtype=torch.bfloat16)
+    assert rel_l2(cpu(yb), yr) < 5e-3
+
+
+@pytest.mark.parametrize("case", CASES[:5])
+def test_conv3x3_tc_dgrad(ops, case):
+    N, H, W, C0, C1, Cout = case
+    Cin = C0 + C1
+    r = np.random.RandomState(sum(case) + 1)
+    w = bf16_round((r.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32))
+    dy = bf16_round(r.normal(size=(N, H, W, Cout)).astype(np.float32))
+    xt = torch.zeros(N, H, W, Cin, dtype=torch.float64, requires_grad=True)
+    (R.conv2d(xt, t(w, torch.float64), None, 1, "same") * t(dy, torch.float64)).sum().backward()
+    wpd = ops.pack_conv3x3(gpu(w), for_dgrad=True)     # [9][Cin][Cout], taps mirrored
+    dx = ops.conv3x3_tc_fwd(gpu(dy, torch.bfloat16), None, wpd, None, Cin)
+    err = rel_l2(cpu(dx), xt.grad.numpy())
+    assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 64, 64), (1, 24, 40, 64, 64), (2, 16, 16, 128, 128),
+                                  (2, 16, 16, 64, 128), (2, 16, 16, 128, 64), (4, 14, 14, 256, 128)])
+def test_conv3x3_tc_wgrad(ops, case):
+    N, H, W, Cin, Cout = case
+    r = np.random.RandomState(sum(case) + 2)
+    x = bf16_round(r.normal(size=(N, H, W, Cin)).astype(np.float32))
+    dy = bf16_round(r.normal(size=(N, H, W, Cout)).astype(np.float32))
+    wt = torch.zeros(3, 3, Cin, Cout, dtype=torch.float64, requires_grad=True)
+    (R.conv2d(t(x, torch.float64), wt, None, 1, "same") * t(dy, torch.float64)).sum().backward()
+    dw = ops.zeros(3, 3, Cin, Cout)
+    ops.conv3x3_tc_wgrad(gpu(x, torch.bfloat16), gpu(dy, torch.bfloat16), dw)
+    err = rel_l2(cpu(dw), wt.grad.numpy())
+    assert err < 1e-3, err
+
+
+def test_conv3x3_tc_wgrad_concat_offset(ops):
+    N, H, W, C0, C1, Cout = 2, 16, 16, 64, 64, 64
+    r = np.random.RandomState(11)
+    x = bf16_round(r.normal(size=(N, H, W, C0 + C1)).astype(np.float32))
+    dy = bf16_round(r.normal(size=(N, H, W, Cout)).astype(np.float32))
+    wt = torch.zeros(3, 3, C0 + C1, Cout, dtype=torch.float64, requires_grad=True)
+    (R.conv2d(t(x, torch.float64), wt, None, 1, "same") * t(dy, torch.float64)).sum().backward()
+    dw = ops.zeros(3, 3, C0 + C1, Cout)
+    ops.conv3x3_tc_wgrad(gpu(x[..., :C0], torch.bfloat16), gpu(dy, torch.bfloat16), dw, cin_off=0)
+    ops.conv3x3_tc_wgrad(gpu(x[..., C0:], torch.bfloat16), gpu(dy, torch.bfloat16), dw, cin_off=C0)
+    assert rel_l2(cpu(dw), wt.grad.numpy()) < 1e-3
+
+
+def test_conv3x3_tc_vs_fp32_oracle_tolerance(ops):
+    """north-star bound for the bf16 conv path against the unrounded fp32 reference: <= 1e-2"""
+    N, H, W, C, Cout = 2, 28, 28, 128, 128
+    r = np.random.RandomState(5)
+    x = r.normal(size=(N, H, W, C)).astype(np.float32)
+    w = (r.normal(size=(3, 3, C, Cout)) / np.sqrt(9 * C)).astype(np.float32)
+    yr = R.conv2d(t(x), t(w), None, 1, "same").numpy()
+    y = ops.conv3x3_tc_fwd(ops.cast(gpu(x), torch.bfloat16), None, ops.pack_conv3x3(gpu(w)), None, Cout)
+    assert rel_l2(cpu(y), yr) < 1e-2

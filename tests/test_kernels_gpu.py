@@ -1,0 +1,480 @@
+"""Parity of every C-ABI kernel (through ctypes -> libdafk.so) against the CPU oracle.
+
+Integer-like results (rounding masks, argmax routing) are compared bit-exactly; floating point
+within the tolerance stated next to each assert (fp32 kernels: <= 1e-4 relative L2, the
+north-star bound; most are ~1e-6).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops as R
+from tests.util import cpu, gpu, rel_l2, t
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from multimodal_segmentation_b200 import ops as o
+    return o
+
+
+def rng(seed):
+    return np.random.RandomState(seed)
+
+
+# ------------------------------------------------------------------ rounding / softmax
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 1023, 1 << 20, (1 << 20) + 3])
+def test_round_bit_exact(ops, n):
+    x = rng(n).uniform(-2, 2, size=n).astype(np.float32)
+    if n >= 5:
+        x[:5] = [0.5, 1.5, 2.5, -0.5, -1.5]   # half-way cases: round half to even
+    y = cpu(ops.round_fwd(gpu(x)))
+    np.testing.assert_array_equal(y, np.round(x))
+
+
+def test_round_full_size_property(ops):
+    # BASELINE config 2 size: [32,224,224,8]; idempotence + values in {0,1} on softmax outputs
+    x = torch.rand(32 * 224 * 224 * 8, device="cuda")
+    y = ops.round_fwd(x)
+    yy = ops.round_fwd(y)
+    assert torch.equal(y, yy)
+    assert set(torch.unique(y).tolist()) <= {0.0, 1.0}
+    assert torch.equal(y, torch.round(x))
+
+
+@pytest.mark.parametrize("C", [5, 8])
+def test_softmax_round(ops, C):
+    x = rng(C).normal(0, 3, size=(2, 17, 19, C)).astype(np.float32)
+    p, r = ops.softmax_fwd(gpu(x), want_round=True)
+    pr = R.softmax(t(x)).numpy()
+    assert rel_l2(cpu(p), pr) < 1e-6
+    # bit-exact given the same pre-activation (the kernel's own probabilities)
+    np.testing.assert_array_equal(cpu(r), np.round(cpu(p)))
+    assert cpu(r).sum(-1).max() <= 1.0   # at most one channel above 0.5
+    dp = rng(1).normal(size=x.shape).astype(np.float32)
+    xt = t(x, grad=True)
+    (R.softmax(xt) * t(dp)).sum().backward()
+    dx = ops.softmax_bwd(p, gpu(dp))
+    assert rel_l2(cpu(dx), xt.grad.numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------ activations
+@pytest.mark.parametrize("act,alpha", [(1, 0.0), (2, 0.3), (2, 0.2), (3, 0.0)])
+def test_activations(ops, act, alpha):
+    x = rng(3).normal(size=(3, 9, 7, 8)).astype(np.float32)
+    x.ravel()[:7] = 0.0   # exact zeros: derivative must be 0 for relu / leaky relu
+    g = rng(4).normal(size=x.shape).astype(np.float32)
+    xt = t(x, grad=True)
+    yr = {1: R.relu, 2: lambda v: R.leaky_relu(v, alpha), 3: torch.tanh}[act](xt)
+    (yr * t(g)).sum().backward()
+    y = ops.act_fwd(gpu(x), act, alpha)
+    assert rel_l2(cpu(y), yr.detach().numpy()) < 1e-6
+    dx = ops.act_bwd(gpu(g), y, act, alpha)
+    assert rel_l2(cpu(dx), xt.grad.numpy()) < 1e-5
+    if act in (1, 2):
+        assert np.all(cpu(dx).ravel()[:7] == 0.0)
+
+
+def test_add_max_axpby(ops):
+    a = rng(0).normal(size=1001).astype(np.float32)
+    b = rng(1).normal(size=1001).astype(np.float32)
+    b[:100] = a[:100]   # ties
+    g = rng(2).normal(size=1001).astype(np.float32)
+    np.testing.assert_array_equal(cpu(ops.add(gpu(a), gpu(b))), a + b)
+    np.testing.assert_array_equal(cpu(ops.max_fwd(gpu(a), gpu(b))), np.maximum(a, b))
+    da, db = ops.max_bwd(gpu(a), gpu(b), gpu(g))
+    at, bt = t(a, grad=True), t(b, grad=True)
+    (R.tf_maximum(at, bt) * t(g)).sum().backward()
+    np.testing.assert_array_equal(cpu(da), at.grad.numpy())
+    np.testing.assert_array_equal(cpu(db), bt.grad.numpy())
+    assert np.all(cpu(db)[:100] == 0)   # ties go to the first input
+    y = gpu(b)
+    ops.axpby_(2.0, gpu(a), -1.0, y)
+    assert rel_l2(cpu(y), 2 * a - b) < 1e-6
+
+
+def test_cast_copy_gather(ops):
+    x = rng(0).normal(size=(2, 5, 6, 8)).astype(np.float32)
+    xb = ops.cast(gpu(x), torch.bfloat16)
+    np.testing.assert_array_equal(cpu(xb), t(x).to(torch.bfloat16).float().numpy())
+    np.testing.assert_array_equal(cpu(ops.cast(xb, torch.float32)), cpu(xb))
+    y = rng(1).normal(size=(2, 5, 6, 1)).astype(np.float32)
+    cat = ops.concat_channels([gpu(x), gpu(y)])
+    np.testing.assert_array_equal(cpu(cat), np.concatenate([x, y], -1))
+    np.testing.assert_array_equal(cpu(ops.slice_channels(cat, 2, 4)), x[..., 2:6])
+    idx = np.array([3, 0, 2], np.int32)
+    src = rng(2).normal(size=(4, 3, 3, 4)).astype(np.float32)
+    np.testing.assert_array_equal(cpu(ops.gather_rows(gpu(src), torch.as_tensor(idx).cuda())), src[idx])
+
+
+# ------------------------------------------------------------------ FiLM
+def test_film(ops):
+    B, H, W, C = 3, 20, 24, 8
+    x = rng(0).normal(size=(B, H, W, C)).astype(np.float32)
+    gm = rng(1).normal(size=(B, C)).astype(np.float32)
+    bt = rng(2).normal(size=(B, C)).astype(np.float32)
+    g = rng(3).normal(size=x.shape).astype(np.float32)
+    xt, gt, btt = t(x, grad=True), t(gm, grad=True), t(bt, grad=True)
+    yr = R.film(xt, gt, btt)
+    (yr * t(g)).sum().backward()
+    y = ops.film_fwd(gpu(x), gpu(gm), gpu(bt))
+    assert rel_l2(cpu(y), yr.detach().numpy()) < 1e-6
+    dx, dg, db = ops.film_bwd(gpu(g), gpu(x), gpu(gm))
+    assert rel_l2(cpu(dx), xt.grad.numpy()) < 1e-6
+    assert rel_l2(cpu(dg), gt.grad.numpy()) < 1e-5
+    assert rel_l2(cpu(db), btt.grad.numpy()) < 1e-5
+    # KAT: FiLM(gamma=1, beta=0) is the identity (layers/film.py:36)
+    one, zero = gpu(np.ones((B, C), np.float32)), gpu(np.zeros((B, C), np.float32))
+    np.testing.assert_array_equal(cpu(ops.film_fwd(gpu(x), one, zero)), x)
+
+
+# ------------------------------------------------------------------ batch norm
+@pytest.mark.parametrize("C,act", [(64, 1), (128, 0), (1024, 1)])
+def test_batchnorm_train(ops, C, act):
+    N, H, W = 2, 12, 10
+    x = (rng(0).normal(size=(N, H, W, C)) * 2 + 0.5).astype(np.float32)
+    gm = rng(1).uniform(0.5, 1.5, size=C).astype(np.float32)
+    bt = rng(2).normal(size=C).astype(np.float32)
+    g = rng(3).normal(size=x.shape).astype(np.float32)
+    mm, mv = np.zeros(C, np.float32), np.ones(C, np.float32)
+    xt, gt, btt = t(x, grad=True), t(gm, grad=True), t(bt, grad=True)
+    yr, mean_r, var_r = R.batchnorm_train(xt, gt, btt)
+    if act:
+        yr = R.relu(yr)
+    (yr * t(g)).sum().backward()
+    dmm, dmv = gpu(mm), gpu(mv)
+    mean, rstd = ops.bn_stats_finalize(gpu(x), 1e-3, 0.99, dmm, dmv)
+    assert rel_l2(cpu(mean), mean_r.detach().numpy()) < 1e-5
+    assert rel_l2(cpu(rstd), torch.rsqrt(var_r + 1e-3).detach().numpy()) < 1e-5
+    emm, emv = R.bn_moving_update(t(mm), t(mv), mean_r.detach(), var_r.detach(), N * H * W)
+    assert rel_l2(cpu(dmm), emm.numpy()) < 1e-5 and rel_l2(cpu(dmv), emv.numpy()) < 1e-5
+    y = ops.bn_apply(gpu(x), mean, rstd, gpu(gm), gpu(bt), act)
+    assert rel_l2(cpu(y), yr.detach().numpy()) < 1e-5
+    yb = ops.bn_apply(gpu(x), mean, rstd, gpu(gm), gpu(bt), act, out_dtype=torch.bfloat16)
+    assert rel_l2(cpu(yb), yr.detach().numpy()) < 5e-3   # bf16 storage: 2^-9 relative
+    dgm, dbt = ops.zeros(C), ops.zeros(C)
+    dx = ops.bn_bwd(gpu(g), gpu(x), mean, rstd, gpu(gm), gpu(bt), act, dgm, dbt)
+    assert rel_l2(cpu(dx), xt.grad.numpy()) < FP32_TOL
+    assert rel_l2(cpu(dgm), gt.grad.numpy()) < FP32_TOL
+    assert rel_l2(cpu(dbt), btt.grad.numpy()) < FP32_TOL
+
+
+def test_batchnorm_infer(ops):
+    C = 64
+    x = rng(0).normal(size=(2, 6, 6, C)).astype(np.float32)
+    gm, bt = rng(1).uniform(.5, 1.5, C).astype(np.float32), rng(2).normal(size=C).astype(np.float32)
+    mm, mv = rng(3).normal(size=C).astype(np.float32), rng(4).uniform(.5, 2, C).astype(np.float32)
+    g = rng(5).normal(size=x.shape).astype(np.float32)
+    xt = t(x, grad=True)
+    yr = R.relu(R.batchnorm_infer(xt, t(gm), t(bt), t(mm), t(mv)))
+    (yr * t(g)).sum().backward()
+    rstd = ops.bn_rstd_from_var(gpu(mv), 1e-3)
+    y = ops.bn_apply(gpu(x), gpu(mm), rstd, gpu(gm), gpu(bt), 1)
+    assert rel_l2(cpu(y), yr.detach().numpy()) < 1e-5
+    dx = ops.bn_bwd_frozen(gpu(g), gpu(x), gpu(mm), rstd, gpu(gm), gpu(bt), 1)
+    assert rel_l2(cpu(dx), xt.grad.numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------ pooling / resampling
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("H,W", [(8, 12), (9, 7)])
+def test_maxpool_upsample(ops, dtype, H, W):
+    C = 8
+    x = np.round(rng(0).normal(size=(2, H, W, C)) * 2).astype(np.float32)   # many ties
+    g = rng(1).normal(size=(2, H // 2, W // 2, C)).astype(np.float32)
+    g = t(g).to(dtype).float().numpy()
+    xt = t(x, grad=True)
+    yr = R.maxpool2(xt)
+    (yr * t(g)).sum().backward()
+    xd = gpu(x, dtype)
+    y = ops.maxpool2_fwd(xd)
+    np.testing.assert_array_equal(cpu(y), yr.detach().numpy())
+    dx = ops.maxpool2_bwd(xd, gpu(g, dtype))
+    np.testing.assert_array_equal(cpu(dx), xt.grad.numpy())   # first max in row-major order, bit-exact
+    u = ops.upsample2_fwd(xd)
+    np.testing.assert_array_equal(cpu(u), R.upsample2(t(x)).numpy())
+    gu = rng(2).normal(size=(2, 2 * H, 2 * W, C)).astype(np.float32)
+    xt2 = t(x, grad=True)
+    (R.upsample2(xt2) * t(gu)).sum().backward()
+    du = ops.upsample2_bwd(gpu(gu, dtype))
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    assert rel_l2(cpu(du), xt2.grad.numpy()) < tol
+
+
+def test_resize_nn(ops):
+    x = rng(0).normal(size=(2, 32, 32, 8)).astype(np.float32)
+    for ho in (1, 2, 4, 8, 16, 32):
+        y = ops.resize_nn_fwd(gpu(x), ho, ho)
+        np.testing.assert_array_equal(cpu(y), R.resize_nn(t(x), ho, ho).numpy())
+        g = rng(ho).normal(size=(2, ho, ho, 8)).astype(np.float32)
+        xt = t(x, grad=True)
+        (R.resize_nn(xt, ho, ho) * t(g)).sum().backward()
+        np.testing.assert_array_equal(cpu(ops.resize_nn_bwd(gpu(g), 32, 32)), xt.grad.numpy())
+
+
+# ------------------------------------------------------------------ general convolution
+CONV_CASES = [
+    # N,H,W,Cin,Cout,k,stride,pad      (reference call sites)
+    (2, 12, 10, 1, 64, 3, 1, 1),     # UNet first conv (models/unet.py:95)
+    (2, 12, 10, 8, 64, 3, 1, 1),     # segmentor conv1
+    (2, 12, 10, 64, 8, 1, 1, 0),     # conv_anatomy 1x1
+    (2, 12, 10, 64, 5, 1, 1, 0),     # segmentor head
+    (2, 12, 10, 8, 8, 3, 1, 1),      # FiLM decoder
+    (2, 12, 10, 8, 1, 1, 1, 0),      # decoder head
+    (2, 17, 15, 9, 16, 3, 2, 0),     # modality encoder, stride 2 valid
+    (2, 20, 18, 16, 20, 5, 1, 0),    # locnet 5x5 valid
+    (2, 18, 16, 4, 64, 4, 2, 0),     # discriminator first layer
+    (1, 13, 11, 64, 128, 4, 2, 0),   # discriminator block
+    (1, 9, 9, 32, 48, 4, 1, 0),      # discriminator last block (stride 1)
+    (2, 8, 8, 64, 64, 3, 1, 1),      # wide 3x3 (also served by the tcgen05 path)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_generic(ops, case):
+    N, H, W, Cin, Cout, k, s, p = case
+    r = rng(sum(case))
+    x = r.normal(size=(N, H, W, Cin)).astype(np.float32)
+    w = (r.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(np.float32)
+    b = r.normal(size=Cout).astype(np.float32)
+    xt, wt, bt = t(x, grad=True), t(w, grad=True), t(b, grad=True)
+    yr = R.conv2d(xt, wt, bt, stride=s, padding="same" if p else "valid")
+    g = r.normal(size=tuple(yr.shape)).astype(np.float32)
+    (yr * t(g)).sum().backward()
+    y = ops.conv2d_fwd(gpu(x), gpu(w), gpu(b), s, p)
+    assert tuple(y.shape) == tuple(yr.shape)
+    assert rel_l2(cpu(y), yr.detach().numpy()) < 1e-5
+    # second, independent oracle statement
+    assert rel_l2(cpu(y), R.conv2d_loops(x, w, b, s, p)) < 1e-5
+    dx = ops.conv2d_dgrad(gpu(g), gpu(w), x.shape, s, p)
+    assert rel_l2(cpu(dx), xt.grad.numpy()) < 1e-5
+    dw, db = ops.zeros(*w.shape), ops.zeros(Cout)
+    ops.conv2d_wgrad(gpu(x), gpu(g), dw, db, s, p)
+    assert rel_l2(cpu(dw), wt.grad.numpy()) < FP32_TOL
+    assert rel_l2(cpu(db), bt.grad.numpy()) < FP32_TOL
+
+
+def test_conv_fused_activation(ops):
+    r = rng(7)
+    x = r.normal(size=(1, 6, 6, 8)).astype(np.float32)
+    w = r.normal(size=(3, 3, 8, 8)).astype(np.float32) * 0.2
+    b = r.normal(size=8).astype(np.float32)
+    y = ops.conv2d_fwd(gpu(x), gpu(w), gpu(b), 1, 1, act=2, alpha=0.3)
+    yr = R.leaky_relu(R.conv2d(t(x), t(w), t(b), 1, "same"), 0.3)
+    assert rel_l2(cpu(y), yr.numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------ dense
+@pytest.mark.parametrize("B,K,N", [(4, 1000, 32), (32, 21632, 32), (3, 4802, 100), (5, 270848 // 8, 1), (2, 8, 300)])
+def test_dense(ops, B, K, N):
+    r = rng(B + N)
+    x = r.normal(size=(B, K)).astype(np.float32)
+    w = (r.normal(size=(K, N)) / np.sqrt(K)).astype(np.float32)
+    b = r.normal(size=N).astype(np.float32)
+    g = r.normal(size=(B, N)).astype(np.float32)
+    xt, wt, bt = t(x, grad=True), t(w, grad=True), t(b, grad=True)
+    yr = R.dense(xt, wt, bt)
+    (yr * t(g)).sum().backward()
+    assert rel_l2(cpu(ops.dense_fwd(gpu(x), gpu(w), gpu(b))), yr.detach().numpy()) < 1e-5
+    assert rel_l2(cpu(ops.dense_bwd_data(gpu(g), gpu(w))), xt.grad.numpy()) < 1e-5
+    dw, db = ops.zeros(K, N), ops.zeros(N)
+    ops.dense_bwd_weight(gpu(x), gpu(g), dw, db)
+    assert rel_l2(cpu(dw), wt.grad.numpy()) < 1e-5
+    assert rel_l2(cpu(db), bt.grad.numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------ thin plate spline
+def test_tps_general_solve_and_apply(ops):
+    r = rng(0)
+    B, n, k, m = 3, 25, 2, 500
+    c = R.nDgrid((5, 5)).repeat(B, 1, 1).numpy() + r.normal(size=(B, n, 2)).astype(np.float32) * 0.02
+    f = r.normal(size=(B, n, k)).astype(np.float32)
+    q = r.uniform(0, 1, size=(B, m, 2)).astype(np.float32)
+    w, v = ops.tps_solve(gpu(c), gpu(f))
+    wr, vr = R.solve_interpolation(t(c, torch.float64), t(f, torch.float64), 2)
+    assert rel_l2(cpu(w), wr.numpy()) < 2e-3     # fp32 LU of a cond~4e2 system
+    out = ops.tps_apply(gpu(q), gpu(c), w, v)
+    outr = R.interpolate_spline(t(c, torch.float64), t(f, torch.float64), t(q, torch.float64), 2)
+    assert rel_l2(cpu(out), outr.numpy()) < 1e-3
+    # KAT: the spline reproduces train_values at train_points (interpolate_spline.py:225-227)
+    at_c = ops.tps_apply(gpu(c), gpu(c), w, v)
+    assert np.abs(cpu(at_c) - f).max() < 2e-3
+
+
+@pytest.mark.parametrize("H,W", [(16, 16), (24, 40)])
+def test_tps_warp_forward_backward(ops, H, W):
+    r = rng(H)
+    B, C = 3, 8
+    vol = r.uniform(size=(B, H, W, C)).astype(np.float32)
+    theta = (r.normal(size=(B, 25, 2)) * 0.03).astype(np.float32)
+    theta[0] = 0.0
+    theta[2, :, 1] += 0.6   # push part of the sampling grid outside the image (zero padding path)
+    g = r.normal(size=vol.shape).astype(np.float32)
+    vt, tt = t(vol, torch.float64, grad=True), t(theta, torch.float64, grad=True)
+    outr, locr = R.thin_plate_spline_2d(vt, tt)
+    (outr * t(g, torch.float64)).sum().backward()
+    out, locs = ops.tps_warp_fwd(gpu(vol), gpu(theta), want_locs=True)
+    assert np.abs(cpu(locs) - locr.detach().numpy()).max() < 2e-3      # pixels
+    assert rel_l2(cpu(out), outr.detach().numpy()) < 2e-4
+    # KAT: theta = 0 is the identity warp (locnet head is zero-initialised, stn_spline.py:116)
+    assert np.abs(cpu(out)[0] - vol[0]).max() < 1e-4
+    dvol, dtheta = ops.tps_warp_bwd(gpu(vol), gpu(theta), gpu(g))
+    assert rel_l2(cpu(dvol), vt.grad.numpy()) < 2e-4
+    assert rel_l2(cpu(dtheta), tt.grad.numpy()) < 2e-3
+
+
+def test_resampler_matches_grid_sample(ops):
+    r = rng(1)
+    B, H, W, C, m = 2, 9, 11, 4, 300
+    vol = r.normal(size=(B, H, W, C)).astype(np.float32)
+    warp = np.stack([r.uniform(-2, W + 1, size=(B, m)), r.uniform(-2, H + 1, size=(B, m))], -1).astype(np.float32)
+    out = ops.resampler_fwd(gpu(vol), gpu(warp))
+    assert rel_l2(cpu(out), R.resampler(t(vol), t(warp)).numpy()) < 1e-5
+    # independent cross-oracle: torch grid_sample(bilinear, zeros, align_corners=True)
+    gx = 2 * warp[..., 0] / (W - 1) - 1
+    gy = 2 * warp[..., 1] / (H - 1) - 1
+    grid = torch.as_tensor(np.stack([gx, gy], -1))[:, :, None, :]
+    gs = torch.nn.functional.grid_sample(t(vol).permute(0, 3, 1, 2), grid, mode="bilinear", padding_mode="zeros",
+                                         align_corners=True)
+    gs = gs[:, :, :, 0].permute(0, 2, 1).numpy()
+    assert np.abs(cpu(out) - gs).max() < 1e-4
+
+
+# ------------------------------------------------------------------ losses
+@pytest.mark.parametrize("use_bce,Ct", [(1, 5), (0, 4), (0, 5)])
+def test_segloss(ops, use_bce, Ct):
+    r = rng(use_bce + Ct)
+    B, H, W, Cp = 3, 14, 12, 5
+    logits = r.normal(size=(B, H, W, Cp)).astype(np.float32)
+    pred = R.softmax(t(logits)).numpy()
+    lab = r.randint(0, 5, size=(B, H, W))
+    tgt = np.eye(5, dtype=np.float32)[lab][..., :Ct]
+    pt = t(pred, grad=True)
+    if use_bce:
+        lr = 10.0 * R.combined_dice_bce(t(tgt), pt, 4)
+    else:
+        lr = 10.0 * R.dice_loss(t(tgt), pt, 4)
+    lr.backward()
+    loss = ops.zeros(1)
+    dpred = ops.segloss(gpu(pred), gpu(tgt), 4, use_bce, 10.0, loss)
+    assert abs(cpu(loss)[0] - lr.item()) < 1e-4 * abs(lr.item())
+    assert rel_l2(cpu(dpred), pt.grad.numpy()) < FP32_TOL
+    # KAT: dice(x, x) on a one-hot mask gives (almost) zero loss (costs.py:43-48)
+    l0 = ops.zeros(1)
+    ops.segloss(gpu(tgt), gpu(tgt), min(4, Ct), 0, 1.0, l0, want_grad=False)
+    assert abs(cpu(l0)[0]) < 1e-6
+
+
+def test_l1l2_vae(ops):
+    r = rng(0)
+    p = r.normal(size=(4, 10, 10, 1)).astype(np.float32)
+    q = r.normal(size=p.shape).astype(np.float32)
+    for kind, fn in ((0, R.mae), (1, R.mse)):
+        pt = t(p, grad=True)
+        lr = 3.0 * fn(t(q), pt)
+        lr.backward()
+        loss = ops.zeros(1)
+        dp = ops.l1l2_loss(gpu(p), gpu(q), kind, 3.0, loss)
+        assert abs(cpu(loss)[0] - lr.item()) < 1e-5 * abs(lr.item())
+        assert rel_l2(cpu(dp), pt.grad.numpy()) < 1e-6
+    d = r.normal(size=(6, 1)).astype(np.float32)
+    dt_ = t(d, grad=True)
+    lr = R.mse(torch.ones(6, 1), dt_)
+    lr.backward()
+    loss = ops.zeros(1)
+    dd = ops.l1l2_loss(gpu(d), None, 1, 1.0, loss, cval=1.0)
+    assert abs(cpu(loss)[0] - lr.item()) < 1e-6 and rel_l2(cpu(dd), dt_.grad.numpy()) < 1e-6
+    mu, lv, eps = (r.normal(size=(5, 8)).astype(np.float32) for _ in range(3))
+    gz = r.normal(size=(5, 8)).astype(np.float32)
+    mt, lt = t(mu, grad=True), t(lv, grad=True)
+    zr = R.sampling(mt, lt, t(eps))
+    klr = R.kl(mt, lt)
+    ((zr * t(gz)).sum() + 0.1 * klr.mean()).backward()
+    loss = ops.zeros(1)
+    z, klv = ops.vae_fwd(gpu(mu), gpu(lv), gpu(eps), 0.1, loss)
+    assert rel_l2(cpu(z), zr.detach().numpy()) < 1e-6 and rel_l2(cpu(klv), klr.detach().numpy()) < 1e-5
+    assert abs(cpu(loss)[0] - 0.1 * klr.mean().item()) < 1e-5
+    dmu, dlv = ops.vae_bwd(gpu(mu), gpu(lv), gpu(eps), gpu(gz), 0.1)
+    assert rel_l2(cpu(dmu), mt.grad.numpy()) < 1e-5 and rel_l2(cpu(dlv), lt.grad.numpy()) < 1e-5
+    # KAT: KL(0,0) = 0
+    l0 = ops.zeros(1)
+    _, k0 = ops.vae_fwd(ops.zeros(2, 8), ops.zeros(2, 8), ops.zeros(2, 8), 1.0, l0)
+    assert np.all(cpu(k0) == 0)
+
+
+def test_spectral_reg(ops):
+    r = rng(0)
+    dim, cout = 4 * 4 * 16, 32
+    W = (r.normal(size=(4, 4, 16, cout)) * 0.1).astype(np.float32)
+    u0 = r.uniform(-1, 1, size=(dim, 1)).astype(np.float32)
+    wt = t(W, grad=True)
+    lr = R.spectral_reg(wt, t(u0), 10.0)
+    lr.backward()
+    loss, dW = ops.zeros(1), ops.zeros(dim, cout)
+    ops.spectral_reg(gpu(W).view(dim, cout), gpu(u0), 10.0, loss, dW)
+    assert abs(cpu(loss)[0] - lr.item()) < 1e-4 * abs(lr.item())
+    assert rel_l2(cpu(dW), wt.grad.numpy().reshape(dim, cout)) < 1e-3   # sign() flips only at |d|~0
+
+
+def test_adam(ops):
+    r = rng(0)
+    n = 10007
+    p, g = r.normal(size=n).astype(np.float32), r.normal(size=n).astype(np.float32)
+    m, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    dp, dm, dv = gpu(p), gpu(m), gpu(v)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    pr, mr, vr = p.astype(np.float64), m.astype(np.float64), v.astype(np.float64)
+    for step in (1, 2, 3):
+        import math
+        lr_t = 1e-4 * math.sqrt(1 - 0.999 ** step) / (1 - 0.9 ** step)
+        ops.adam_step(dp, gpu(g), dm, dv, shadow, lr_t)
+        pr, mr, vr = R.adam_step(pr, g.astype(np.float64), mr, vr, step)
+    assert rel_l2(cpu(dp), pr) < 1e-6 and rel_l2(cpu(dm), mr) < 1e-6 and rel_l2(cpu(dv), vr) < 1e-6
+    np.testing.assert_array_equal(cpu(shadow), cpu(dp.to(torch.bfloat16)))
+
+
+# ------------------------------------------------------------------ SPADE / instance norm / balancer
+def test_spade(ops):
+    r = rng(0)
+    B, H, W, C = 2, 8, 8, 16
+    x = (r.normal(size=(B, H, W, C)) * 3 + 1).astype(np.float32)
+    gm = r.normal(size=x.shape).astype(np.float32) * 0.5
+    bt = r.normal(size=x.shape).astype(np.float32) * 0.5
+    g = r.normal(size=x.shape).astype(np.float32)
+    xt, gt, btt = t(x, torch.float64, grad=True), t(gm, torch.float64, grad=True), t(bt, torch.float64, grad=True)
+    yr = R.leaky_relu(R.spade_cond(R.instance_norm_axis_none(xt), gt, btt), 0.2)
+    (yr * t(g, torch.float64)).sum().backward()
+    acc = ops.in_stats(gpu(x))
+    y = ops.spade_fwd(gpu(x), acc, gpu(gm), gpu(bt))
+    assert rel_l2(cpu(y), yr.detach().numpy()) < 1e-5
+    dx, dg, db = ops.spade_bwd(gpu(g), gpu(x), acc, gpu(gm), gpu(bt))
+    assert rel_l2(cpu(dg), gt.grad.numpy()) < 1e-5
+    assert rel_l2(cpu(db), btt.grad.numpy()) < 1e-5
+    assert rel_l2(cpu(dx), xt.grad.numpy()) < FP32_TOL
+    # KAT: SPADE_COND(gamma=0, beta=0) is the identity on the normalised input (spade.py:55)
+    z = ops.zeros(*x.shape)
+    y0 = ops.spade_fwd(gpu(x), acc, z, z, act=0)
+    assert rel_l2(cpu(y0), R.instance_norm_axis_none(t(x)).numpy()) < 1e-5
+
+
+def test_pair_dice(ops):
+    r = rng(0)
+    a = (r.uniform(size=(3, 10, 10, 8)) > 0.5).astype(np.float32)
+    b = (r.uniform(size=(3, 10, 10, 8)) > 0.5).astype(np.float32)
+    assert rel_l2(cpu(ops.pair_dice(gpu(a), gpu(b))), R.pair_dice(t(a), t(b)).numpy()) < 1e-6
+
+
+# ------------------------------------------------------------------ error behaviour of the boundary
+def test_error_codes(ops):
+    from multimodal_segmentation_b200 import _lib
+    x = torch.zeros(16, device="cuda")
+    with pytest.raises(_lib.DafkError):
+        _lib.call("round_fwd", x.data_ptr() + 4, x, 8, None)      # misaligned
+    with pytest.raises(_lib.DafkError):
+        _lib.call("softmax_fwd", x, x, None, 2, 7, None)          # unsupported channel count
+    with pytest.raises(_lib.DafkError):
+        ops.round_fwd(torch.zeros(4))                             # CPU tensor: no fallback
