@@ -72,6 +72,8 @@ int dafk_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act,
                  void* stream);
 /* out = a + b (keras Add, decoder.py:53, spade.py:23); out may alias a or b */
 int dafk_add(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* same for either storage dtype (gradient accumulation of bf16 feature maps) */
+int dafk_add_dt(const void* a, const void* b, void* out, int dt, int64_t n, void* stream);
 /* y = a*x + b*y */
 int dafk_axpby(float a, const float* x, float b, float* y, int64_t n, void* stream);
 int dafk_fill(float* x, float v, int64_t n, void* stream);
@@ -121,11 +123,12 @@ int dafk_bn_bwd_reduce(const void* dout, int dout_dt, const float* x, const floa
                        const float* rstd, const float* gamma, const float* beta, double* acc,
                        int64_t M, int C, int act, void* stream);
 /* backward, pass 2: dx = gamma*rstd*(dz - acc0/M - xhat*acc1/M); dgamma += acc1; dbeta += acc0
- * (dgamma/dbeta may be NULL for frozen layers).  dx dtype f32 or bf16. */
+ * (dgamma/dbeta may be NULL for frozen layers).  dx dtype f32 or bf16.
+ * dbias_prev (may be NULL): += sum_pixels dx, the bias gradient of the convolution feeding this BN. */
 int dafk_bn_bwd_apply(const void* dout, int dout_dt, const float* x, const float* mean,
                       const float* rstd, const float* gamma, const float* beta, const double* acc,
-                      void* dx, int dx_dt, float* dgamma, float* dbeta, int64_t M, int C, int act,
-                      void* stream);
+                      void* dx, int dx_dt, float* dgamma, float* dbeta, float* dbias_prev, int64_t M,
+                      int C, int act, void* stream);
 /* inference-mode backward (frozen statistics): dx = dz*gamma*rstd */
 int dafk_bn_bwd_frozen(const float* dout, const float* x, const float* mean, const float* rstd,
                        const float* gamma, const float* beta, float* dx, int64_t M, int C, int act,
@@ -169,17 +172,20 @@ int dafk_conv2d_dgrad(const dafk_conv_desc* d, const float* dy, const float* w, 
 /* dw += x (*) dy  (accumulates: caller zeroes);  db += sum_pixels dy (db may be NULL) */
 int dafk_conv2d_wgrad(const dafk_conv_desc* d, const float* x, const float* dy, float* dw,
                       float* db, void* stream);
-/* out[c] += sum_m x[m,c] */
-int dafk_colsum(const float* x, float* out, int64_t M, int C, void* stream);
+/* out[c] += sum_m x[m,c]   (bias gradients); x is f32 or bf16 */
+int dafk_colsum(const void* x, int x_dt, float* out, int64_t M, int C, void* stream);
 
 /* tcgen05 / TMEM / TMA implicit-GEMM path: 3x3, stride 1, pad 1, bf16 operands,
  * fp32 accumulation in tensor memory.  Cin % 64 == 0 and Cout % 64 == 0.
  * x0:[N,H,W,C0] (+ optional second K source x1:[N,H,W,C1] = Concatenate([x0,x1]),
  * models/unet.py:68-69), wp: packed bf16 weights [9][Cout][C0+C1] (dafk_pack_conv3x3).
- * y: [N,H,W,Cout] f32 or bf16.  Returns DAFK_ERR_UNSUPPORTED for other shapes. */
+ * y: [N,H,W,Cout] f32 or bf16.  Returns DAFK_ERR_UNSUPPORTED for other shapes.
+ * The packed weight matrix has w_rows_per_tap rows per tap; this call produces the Cout output
+ * channels whose rows start at w_row_off (w_rows_per_tap = Cout, w_row_off = 0 for a plain
+ * forward; a data-gradient towards one source of a Concatenate uses a row window). */
 int dafk_conv3x3_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp,
-                        const float* bias, void* y, int y_dt, int N, int H, int W, int Cout,
-                        void* stream);
+                        int w_rows_per_tap, int w_row_off, const float* bias, void* y, int y_dt,
+                        int N, int H, int W, int Cout, void* stream);
 /* weights HWIO f32 [3,3,Cin,Cout] -> bf16 [9][Cout][Cin] (fwd) or flipped/transposed
  * [9][Cin][Cout] with tap index mirrored (dgrad) */
 int dafk_pack_conv3x3(const float* w_hwio, void* wp, int Cin, int Cout, int for_dgrad,

@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(256) colsum_fast_kernel(const float* __restric
   channel_reduce2<256>(s, z, C, sm, acc, acc + C);
 }
 
-__global__ void __launch_bounds__(256) colsum_generic_kernel(const float* __restrict__ x, float* __restrict__ out,
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_generic_kernel(const T* __restrict__ x, float* __restrict__ out,
                                                              int64_t M, int C, int64_t rows_per_block) {
   extern __shared__ float sm[];  // C floats
   for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(256) colsum_generic_kernel(const float* __rest
   int64_t r1 = r0 + rows_per_block;
   if (r1 > M) r1 = M;
   int64_t e0 = r0 * C, e1 = r1 * C;
-  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) atomicAdd(&sm[(int)(e % C)], x[e]);
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) atomicAdd(&sm[(int)(e % C)], to_f<T>(x[e]));
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + i, sm[i]);
 }
@@ -434,7 +435,7 @@ int dafk_conv2d_wgrad(const dafk_conv_desc* d, const float* x, const float* dy, 
   return check_launch("dafk_conv2d_wgrad");
 }
 
-int dafk_colsum(const float* x, float* out, int64_t M, int C, void* stream) {
+int dafk_colsum(const void* x, int x_dt, float* out, int64_t M, int C, void* stream) {
   DAFK_REQUIRE(M >= 0 && C > 0, DAFK_ERR_BAD_ARG, "dafk_colsum: bad shape");
   if (M == 0) return DAFK_OK;
   DAFK_REQUIRE(x && out, DAFK_ERR_BAD_ARG, "dafk_colsum: null pointer");
@@ -443,7 +444,9 @@ int dafk_colsum(const float* x, float* out, int64_t M, int C, void* stream) {
   int64_t rows_per_block = (M + kNumSMs * 4 - 1) / (kNumSMs * 4);
   if (rows_per_block < 64) rows_per_block = 64;
   int blocks = (int)((M + rows_per_block - 1) / rows_per_block);
-  colsum_generic_kernel<<<blocks, 256, C * sizeof(float), s>>>(x, out, M, C, rows_per_block);
+  if (x_dt == DAFK_F32) colsum_generic_kernel<float><<<blocks, 256, C * sizeof(float), s>>>((const float*)x, out, M, C, rows_per_block);
+  else if (x_dt == DAFK_BF16) colsum_generic_kernel<__nv_bfloat16><<<blocks, 256, C * sizeof(float), s>>>((const __nv_bfloat16*)x, out, M, C, rows_per_block);
+  else { set_error("dafk_colsum: bad dtype %d", x_dt); return DAFK_ERR_BAD_ARG; }
   return check_launch("dafk_colsum");
 }
 

@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_fwd_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const float* __restrict__ bias, void* __restrict__ y,
                                                                  int y_dt, int N, int H, int W, int Cout, int C0, int C1,
-                                                                 int KH, int KW, int pad, TileGeom g, int n_blocks) {
+                                                                 int KH, int KW, int pad, TileGeom g, int n_blocks,
+                                                                 int w_rows_per_tap, int w_row_off) {
   constexpr int B_BYTES = BLOCK_N * KBLK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_fwd_kernel(const __grid_co
             const int r = tap / KW, q = tap % KW;
             uint8_t* sa = smem + s * STAGE_BYTES;
             tma_load_4d(sa, mA, full_bar + s, cb * KBLK, x0 + q - pad, y0 + r - pad, img0);
-            tma_load_2d(sa + A_BYTES, &tmB, full_bar + s, koff + cb * KBLK, tap * Cout + n0);
+            tma_load_2d(sa + A_BYTES, &tmB, full_bar + s, koff + cb * KBLK, tap * w_rows_per_tap + w_row_off + n0);
           }
         }
       }
@@ -494,7 +495,7 @@ static TileGeom pick_geom(int N, int H, int W) {
 template <int BLOCK_N, int STAGES>
 static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const float* bias, void* y,
                       int y_dt, int N, int H, int W, int Cout, int C0, int C1, int KH, int KW, int pad,
-                      const TileGeom& g, cudaStream_t s) {
+                      const TileGeom& g, int w_rows_per_tap, int w_row_off, cudaStream_t s) {
   constexpr int smem = STAGES * (A_BYTES + BLOCK_N * KBLK * 2) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
@@ -506,7 +507,7 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
   int64_t tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n;
   dim3 grid((unsigned)(tiles * n_blocks));
   conv_tc_fwd_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a0, a1, b, bias, y, y_dt, N, H, W, Cout, C0, C1, KH,
-                                                                    KW, pad, g, n_blocks);
+                                                                    KW, pad, g, n_blocks, w_rows_per_tap, w_row_off);
   return check_launch("dafk_conv3x3_tc_fwd");
 }
 
@@ -538,13 +539,17 @@ using namespace dafk;
 
 extern "C" {
 
-int dafk_conv3x3_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp, const float* bias, void* y,
-                        int y_dt, int N, int H, int W, int Cout, void* stream) {
+int dafk_conv3x3_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,
+                        int w_row_off, const float* bias, void* y, int y_dt, int N, int H, int W, int Cout,
+                        void* stream) {
   DAFK_REQUIRE(N > 0 && H > 0 && W > 0 && C0 > 0 && C1 >= 0 && Cout > 0, DAFK_ERR_BAD_ARG, "dafk_conv3x3_tc_fwd: bad shape");
   DAFK_REQUIRE(x0 && wp && y && (C1 == 0 || x1), DAFK_ERR_BAD_ARG, "dafk_conv3x3_tc_fwd: null pointer");
   DAFK_REQUIRE(C0 % KBLK == 0 && C1 % KBLK == 0 && Cout % 64 == 0, DAFK_ERR_UNSUPPORTED,
                "dafk_conv3x3_tc_fwd: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
   DAFK_REQUIRE(y_dt == DAFK_F32 || y_dt == DAFK_BF16, DAFK_ERR_BAD_ARG, "dafk_conv3x3_tc_fwd: bad output dtype");
+  DAFK_REQUIRE(w_row_off >= 0 && w_row_off + Cout <= w_rows_per_tap, DAFK_ERR_BAD_ARG,
+               "dafk_conv3x3_tc_fwd: weight row window [%d,%d) outside %d rows per tap", w_row_off, w_row_off + Cout,
+               w_rows_per_tap);
   DAFK_REQUIRE(DAFK_ALIGNED16(x0) && DAFK_ALIGNED16(x1) && DAFK_ALIGNED16(wp) && DAFK_ALIGNED16(y), DAFK_ERR_ALIGN,
                "dafk_conv3x3_tc_fwd: pointers must be 16-byte aligned");
   TileGeom g = pick_geom(N, H, W);
@@ -554,13 +559,13 @@ int dafk_conv3x3_tc_fwd(const void* x0, int C0, const void* x1, int C1, const vo
   if (C1 > 0) { rc = make_act_map(&a1, x1, N, H, W, C1, g); if (rc) return rc; } else a1 = a0;
   cudaStream_t s = as_stream(stream);
   if (Cout % 128 == 0) {
-    rc = make_w_map(&b, wp, 9 * Cout, C0 + C1, 128);
+    rc = make_w_map(&b, wp, 9 * w_rows_per_tap, C0 + C1, 128);
     if (rc) return rc;
-    return launch_fwd<128, 3>(a0, a1, b, bias, y, y_dt, N, H, W, Cout, C0, C1, 3, 3, 1, g, s);
+    return launch_fwd<128, 3>(a0, a1, b, bias, y, y_dt, N, H, W, Cout, C0, C1, 3, 3, 1, g, w_rows_per_tap, w_row_off, s);
   }
-  rc = make_w_map(&b, wp, 9 * Cout, C0 + C1, 64);
+  rc = make_w_map(&b, wp, 9 * w_rows_per_tap, C0 + C1, 64);
   if (rc) return rc;
-  return launch_fwd<64, 4>(a0, a1, b, bias, y, y_dt, N, H, W, Cout, C0, C1, 3, 3, 1, g, s);
+  return launch_fwd<64, 4>(a0, a1, b, bias, y, y_dt, N, H, W, Cout, C0, C1, 3, 3, 1, g, w_rows_per_tap, w_row_off, s);
 }
 
 int dafk_pack_conv3x3(const float* w_hwio, void* wp, int Cin, int Cout, int for_dgrad, void* stream) {

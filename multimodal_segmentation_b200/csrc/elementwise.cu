@@ -166,6 +166,22 @@ __global__ void __launch_bounds__(TPB) cast_kernel(const TI* __restrict__ x, TO*
   if (t < n) y[t] = from_f<TO>(to_f<TI>(x[t]));
 }
 
+template <typename T>
+__global__ void __launch_bounds__(TPB) add_dt_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t n) {
+  int64_t n4 = n >> 2;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float u[4], v[4];
+    Vec4<T>::load(a + 4 * i, u);
+    Vec4<T>::load(b + 4 * i, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] += v[k];
+    Vec4<T>::store(y + 4 * i, u);
+  }
+  int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) y[t] = from_f<T>(to_f<T>(a[t]) + to_f<T>(b[t]));
+}
+
 // ---------------------------------------------------------------- channel copies
 __global__ void __launch_bounds__(TPB) copy_channels_kernel(const float* __restrict__ src, int src_c, int src_off,
                                                             float* __restrict__ dst, int dst_c, int dst_off, int c,
@@ -270,6 +286,18 @@ int dafk_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act,
 
 int dafk_add(const float* a, const float* b, float* out, int64_t n, void* stream) {
   return launch_map2(a, b, out, n, AddOp{}, stream, "dafk_add");
+}
+
+int dafk_add_dt(const void* a, const void* b, void* out, int dt, int64_t n, void* stream) {
+  DAFK_REQUIRE(n >= 0, DAFK_ERR_BAD_ARG, "dafk_add_dt: negative size");
+  if (n == 0) return DAFK_OK;
+  DAFK_REQUIRE(a && b && out, DAFK_ERR_BAD_ARG, "dafk_add_dt: null pointer");
+  DAFK_REQUIRE(DAFK_ALIGNED16(a) && DAFK_ALIGNED16(b) && DAFK_ALIGNED16(out), DAFK_ERR_ALIGN, "dafk_add_dt: alignment");
+  int grid = bw_grid((n + 3) / 4, TPB);
+  if (dt == DAFK_F32) add_dt_kernel<float><<<grid, TPB, 0, as_stream(stream)>>>((const float*)a, (const float*)b, (float*)out, n);
+  else if (dt == DAFK_BF16) add_dt_kernel<__nv_bfloat16><<<grid, TPB, 0, as_stream(stream)>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, n);
+  else { set_error("dafk_add_dt: bad dtype %d", dt); return DAFK_ERR_BAD_ARG; }
+  return check_launch("dafk_add_dt");
 }
 
 int dafk_axpby(float a, const float* x, float b, float* y, int64_t n, void* stream) {

@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(TPB) bn_bwd_apply_kernel(const TD* __restrict_
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const double* __restrict__ acc, TO* __restrict__ dx,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           int64_t n4, int64_t M, int C, int act) {
+                                                           float* __restrict__ dbias, int64_t n4, int64_t M, int C,
+                                                           int act) {
+  extern __shared__ float sm[];
+  float sdx[4] = {0, 0, 0, 0};
   const int c0 = (threadIdx.x * 4) % C;
   float mu[4], rs[4], g[4], b[4], m0[4], m1[4];
   const double invM = 1.0 / (double)M;
@@ -138,8 +141,18 @@ __global__ void __launch_bounds__(TPB) bn_bwd_apply_kernel(const TD* __restrict_
       float z = xh * g[k] + b[k];
       float dz = (act == DAFK_ACT_RELU && !(z > 0.f)) ? 0.f : d[k];
       v[k] = g[k] * rs[k] * (dz - m0[k] - xh * m1[k]);
+      sdx[k] += v[k];
     }
     Vec4<TO>::store(dx + 4 * i, v);
+  }
+  if (dbias) {
+    // block-level per-channel sum of dx, then one float atomic per channel per CTA
+    for (int i = threadIdx.x; i < C; i += TPB) sm[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicAdd(&sm[c0 + k], sdx[k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += TPB) atomicAdd(dbias + i, sm[i]);
   }
 }
 
@@ -410,7 +423,7 @@ int dafk_bn_bwd_reduce(const void* dout, int dout_dt, const float* x, const floa
 
 int dafk_bn_bwd_apply(const void* dout, int dout_dt, const float* x, const float* mean, const float* rstd,
                       const float* gamma, const float* beta, const double* acc, void* dx, int dx_dt, float* dgamma,
-                      float* dbeta, int64_t M, int C, int act, void* stream) {
+                      float* dbeta, float* dbias_prev, int64_t M, int C, int act, void* stream) {
   DAFK_REQUIRE(M >= 0 && C > 0, DAFK_ERR_BAD_ARG, "dafk_bn_bwd_apply: bad shape");
   if (M == 0) return DAFK_OK;
   DAFK_REQUIRE(dout && x && mean && rstd && gamma && beta && acc && dx, DAFK_ERR_BAD_ARG, "dafk_bn_bwd_apply: null pointer");
@@ -419,7 +432,7 @@ int dafk_bn_bwd_apply(const void* dout, int dout_dt, const float* x, const float
   int64_t n4 = M * C / 4;
   cudaStream_t s = as_stream(stream);
   int grid = bn_grid(n4);
-#define LAUNCH(TD, TO) bn_bwd_apply_kernel<TD, TO><<<grid, TPB, 0, s>>>((const TD*)dout, x, mean, rstd, gamma, beta, acc, (TO*)dx, dgamma, dbeta, n4, M, C, act)
+#define LAUNCH(TD, TO) bn_bwd_apply_kernel<TD, TO><<<grid, TPB, C * sizeof(float), s>>>((const TD*)dout, x, mean, rstd, gamma, beta, acc, (TO*)dx, dgamma, dbeta, dbias_prev, n4, M, C, act)
   if (dout_dt == DAFK_F32 && dx_dt == DAFK_F32) LAUNCH(float, float);
   else if (dout_dt == DAFK_F32 && dx_dt == DAFK_BF16) LAUNCH(float, __nv_bfloat16);
   else if (dout_dt == DAFK_BF16 && dx_dt == DAFK_F32) LAUNCH(__nv_bfloat16, float);

@@ -1,0 +1,716 @@
+"""Host-side execution engine: parameter arenas, a minimal reverse-mode tape and the layer
+primitives (Conv2D, BatchNormalization, Dense, ...) that the model components are built from.
+
+Design (B200-first, not a Keras port):
+  * parameters of all components of a model live in ONE flat fp32 arena with a same-shaped flat
+    gradient arena -> one fused Adam launch per optimizer step and one NCCL all-reduce bucket;
+  * every arithmetic op is a hand-written kernel reached through ``ops`` (ctypes -> libdafk.so);
+    torch only owns the device memory;
+  * the backward pass is a list of closures recorded while the forward runs (``Tape``), so a
+    component that is called several times in one graph (Segmentor x4, Decoder x6 in
+    models/dafnet.py:163-222) simply records several nodes and accumulates into the same
+    parameter gradients;
+  * wide 3x3 convolutions run on tcgen05 with bf16 operands: the producing kernel (BN-apply,
+    pooling, upsampling) writes bf16 directly, gradients of bf16 maps are bf16.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH
+
+# Use the tcgen05 tensor-core path for eligible 3x3 convolutions (bf16 operands, fp32 accumulate).
+# Parity tests against the fp32 oracle at 1e-4 switch it off.
+USE_TC = True
+
+ACT = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU, "tanh": ACT_TANH}
+
+
+def feat_dtype():
+    return torch.bfloat16 if USE_TC else torch.float32
+
+
+# --------------------------------------------------------------------------------------------
+# tape
+# --------------------------------------------------------------------------------------------
+class Var:
+    """A value in the forward graph.  ``data`` is a CUDA tensor (f32 or bf16)."""
+    __slots__ = ("data", "grad", "requires_grad", "grad_dtype", "grad_owned", "bias_sink")
+
+    def __init__(self, data, requires_grad=False, grad_dtype=None):
+        self.data = data
+        self.grad = None
+        self.requires_grad = requires_grad
+        self.grad_dtype = grad_dtype if grad_dtype is not None else data.dtype
+        self.grad_owned = False
+        self.bias_sink = None
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+
+class Ctx:
+    """Execution context of one forward pass: ``tape`` (None = no gradient) and the Keras
+    learning phase (``training`` selects batch statistics in BatchNormalization)."""
+
+    def __init__(self, tape=None, training=False):
+        self.tape = tape
+        self.training = training
+
+    def rec(self, *inputs):
+        return self.tape is not None and any(v.requires_grad for v in inputs if v is not None)
+
+
+class Tape:
+    def __init__(self):
+        self.nodes = []
+
+    def record(self, fn):
+        self.nodes.append(fn)
+
+    def backward(self):
+        for fn in reversed(self.nodes):
+            fn()
+        self.nodes = []
+
+
+def accumulate(var, g, owned=True):
+    """var.grad += g.  ``owned`` = the caller hands over the buffer (it may be updated in place later)."""
+    if var is None or not var.requires_grad:
+        return
+    if g.dtype != var.grad_dtype:
+        g = ops.cast(g, var.grad_dtype)
+        owned = True
+    if var.grad is None:
+        var.grad = g
+        var.grad_owned = owned
+    elif var.grad_owned:
+        ops.add_(var.grad, g)
+    else:
+        var.grad = ops.add(var.grad, g)
+        var.grad_owned = True
+
+
+# --------------------------------------------------------------------------------------------
+# parameters
+# --------------------------------------------------------------------------------------------
+class Param:
+    """A trainable tensor: views into the flat parameter / gradient arenas."""
+
+    def __init__(self, name, shape, init):
+        self.name = name
+        self.shape = tuple(int(s) for s in shape)
+        self.size = int(np.prod(self.shape))
+        self.init = np.ascontiguousarray(init, dtype=np.float32).reshape(self.shape)
+        self.arena = None
+        self.offset = None
+        self.data = None
+        self.grad = None
+        self.requires_grad = True      # toggled by make_trainable (utils/sdnet_utils.py:40-53)
+
+    def numpy(self):
+        return self.data.detach().cpu().numpy().copy()
+
+
+class Arena:
+    """Flat fp32 storage for a group of parameters (+ a gradient arena of the same shape) or for
+    non-trainable state such as BatchNorm moving statistics (``with_grad=False``)."""
+
+    def __init__(self, with_grad=True):
+        self.params = []
+        self.with_grad = with_grad
+        self.flat = None
+        self.gflat = None
+        self.version = 0           # bumped by every optimizer step that touches the arena
+        self._cursor = 0
+
+    def add(self, name, shape, init):
+        p = Param(name, shape, init)
+        p.arena = self
+        p.offset = self._cursor
+        self._cursor += (p.size + 3) // 4 * 4     # keep every tensor 16-byte aligned
+        self.params.append(p)
+        return p
+
+    def to_device(self, device="cuda"):
+        host = np.zeros(max(self._cursor, 4), np.float32)
+        for p in self.params:
+            host[p.offset:p.offset + p.size] = p.init.ravel()
+        if not torch.cuda.is_available():
+            # host-only mode (CPU test box): weights can be built, inspected and exported, but nothing can
+            # be computed -- every kernel wrapper raises on a non-CUDA tensor.
+            self.flat = torch.from_numpy(host)
+            self.gflat = None
+            for p in self.params:
+                p.data = self.flat[p.offset:p.offset + p.size].view(p.shape)
+                p.grad = None
+            return self
+        self.flat = torch.from_numpy(host).to(device)
+        self.gflat = ops.zeros(self.flat.numel()) if self.with_grad else None
+        for p in self.params:
+            p.data = self.flat[p.offset:p.offset + p.size].view(p.shape)
+            p.grad = self.gflat[p.offset:p.offset + p.size].view(p.shape) if self.with_grad else None
+        return self
+
+    def numel(self):
+        return self._cursor
+
+
+class Adam:
+    """Keras 2.1.6 Adam (models/dafnet.py:155 etc.): one independent state per compiled trainer.
+    Works on merged contiguous ranges of the arenas, one fused launch per range."""
+
+    def __init__(self, params, lr=1e-4, beta_1=0.9, beta_2=0.999, eps=1e-7):
+        self.lr, self.b1, self.b2, self.eps = lr, beta_1, beta_2, eps
+        self.t = 0
+        spans = {}
+        for p in params:
+            spans.setdefault(id(p.arena), (p.arena, []))[1].append((p.offset, p.offset + (p.size + 3) // 4 * 4))
+        self.ranges = []
+        for arena, lst in spans.values():
+            lst.sort()
+            cur_a, cur_b = lst[0]
+            for a, b in lst[1:]:
+                if a <= cur_b:
+                    cur_b = max(cur_b, b)
+                else:
+                    self.ranges.append((arena, cur_a, cur_b))
+                    cur_a, cur_b = a, b
+            self.ranges.append((arena, cur_a, cur_b))
+        self.m = self.v = None      # allocated on first use (keeps host-only builds possible)
+
+    def _state(self):
+        if self.m is None:
+            self.m = [ops.zeros(b - a) for _, a, b in self.ranges]
+            self.v = [ops.zeros(b - a) for _, a, b in self.ranges]
+
+    def zero_grad(self):
+        for arena, a, b in self.ranges:
+            ops.zero_(arena.gflat[a:b])
+
+    def grad_buckets(self):
+        return [arena.gflat[a:b] for arena, a, b in self.ranges]
+
+    def step(self, grad_scale=1.0):
+        self._state()
+        self.t += 1
+        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        for (arena, a, b), m, v in zip(self.ranges, self.m, self.v):
+            ops.adam_step(arena.flat[a:b], arena.gflat[a:b], m, v, None, lr_t, self.b1, self.b2, self.eps, grad_scale)
+            arena.version += 1
+
+
+# --------------------------------------------------------------------------------------------
+# initialisers (Keras 2.1.6 VarianceScaling family), host side
+# --------------------------------------------------------------------------------------------
+def _fans(shape):
+    if len(shape) == 2:
+        return shape[0], shape[1]
+    rf = int(np.prod(shape[:-2]))
+    return shape[-2] * rf, shape[-1] * rf
+
+
+def _truncated_normal(rng, shape, stddev):
+    out = rng.normal(0.0, stddev, size=shape)
+    bad = np.abs(out) > 2 * stddev
+    while bad.any():
+        out[bad] = rng.normal(0.0, stddev, size=int(bad.sum()))
+        bad = np.abs(out) > 2 * stddev
+    return out.astype(np.float32)
+
+
+def init_weights(rng, shape, kind):
+    fan_in, fan_out = _fans(shape)
+    if kind == "he_normal":
+        return _truncated_normal(rng, shape, math.sqrt(2.0 / fan_in))
+    if kind == "glorot_normal":
+        return _truncated_normal(rng, shape, math.sqrt(2.0 / (fan_in + fan_out)))
+    if kind == "glorot_uniform":
+        lim = math.sqrt(6.0 / (fan_in + fan_out))
+        return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+    if kind == "zeros":
+        return np.zeros(shape, np.float32)
+    if kind == "ones":
+        return np.ones(shape, np.float32)
+    raise ValueError(kind)
+
+
+# --------------------------------------------------------------------------------------------
+# layers
+# --------------------------------------------------------------------------------------------
+class Conv2D:
+    """keras Conv2D(filters, k, strides, padding, kernel_initializer) -- NHWC, HWIO kernel."""
+
+    def __init__(self, arena, rng, name, cin, cout, k, stride=1, padding="valid", init="glorot_uniform",
+                 use_bias=True):
+        self.name, self.cin, self.cout, self.k, self.stride = name, cin, cout, k, stride
+        assert padding in ("valid", "same")
+        if padding == "same":
+            assert stride == 1 and k % 2 == 1
+        self.pad = k // 2 if padding == "same" else 0
+        self.kernel = arena.add(name + "/kernel", (k, k, cin, cout), init_weights(rng, (k, k, cin, cout), init))
+        self.bias = arena.add(name + "/bias", (cout,), np.zeros(cout, np.float32)) if use_bias else None
+        self._packed = None          # (arena version, wp_fwd, wp_dgrad)
+
+    def params(self):
+        return [self.kernel] + ([self.bias] if self.bias is not None else [])
+
+    def tc_eligible(self, srcs):
+        return (USE_TC and self.k == 3 and self.stride == 1 and self.pad == 1 and self.cout % 64 == 0
+                and all(s.shape[-1] % 64 == 0 for s in srcs))
+
+    def packed(self):
+        ver = self.kernel.arena.version
+        if self._packed is None or self._packed[0] != ver:
+            self._packed = (ver, ops.pack_conv3x3(self.kernel.data, False), ops.pack_conv3x3(self.kernel.data, True))
+        return self._packed[1], self._packed[2]
+
+    def __call__(self, ctx, x, act=None, alpha=0.0):
+        srcs = list(x) if isinstance(x, (list, tuple)) else [x]
+        assert sum(s.shape[-1] for s in srcs) == self.cin, (self.name, [tuple(s.shape) for s in srcs], self.cin)
+        if self.tc_eligible(srcs) and len(srcs) <= 2:
+            return self._call_tc(ctx, srcs, act, alpha)
+        return self._call_generic(ctx, srcs, act, alpha)
+
+    # ---- CUDA-core path (fp32)
+    def _call_generic(self, ctx, srcs, act, alpha):
+        code = ACT[act]
+        f32srcs = [s if s.data.dtype == torch.float32 else _cast_var(ctx, s, torch.float32) for s in srcs]
+        xin = f32srcs[0] if len(f32srcs) == 1 else concat(ctx, f32srcs)
+        bias = self.bias.data if self.bias is not None else None
+        y = Var(ops.conv2d_fwd(xin.data, self.kernel.data, bias, self.stride, self.pad, code, alpha))
+        if ctx.rec(xin, self.kernel):
+            y.requires_grad = True
+            tape_x = xin
+
+            def bw():
+                g = y.grad
+                y.grad = None
+                if g is None:
+                    return
+                if g.dtype != torch.float32:
+                    g = ops.cast(g, torch.float32)
+                if code != ACT_NONE:
+                    g = ops.act_bwd(g, y.data, code, alpha)
+                if self.kernel.requires_grad:
+                    db = self.bias.grad if (self.bias is not None and self.bias.requires_grad) else None
+                    ops.conv2d_wgrad(tape_x.data, g, self.kernel.grad, db, self.stride, self.pad)
+                if tape_x.requires_grad:
+                    accumulate(tape_x, ops.conv2d_dgrad(g, self.kernel.data, tuple(tape_x.shape), self.stride, self.pad))
+
+            ctx.tape.record(bw)
+        return y
+
+    # ---- tcgen05 path (bf16 operands, fp32 accumulate in TMEM)
+    def _call_tc(self, ctx, srcs, act, alpha):
+        bsrcs = [s if s.data.dtype == torch.bfloat16 else _cast_var(ctx, s, torch.bfloat16) for s in srcs]
+        wp_f, wp_d = self.packed()
+        bias = self.bias.data if self.bias is not None else None
+        x0 = bsrcs[0]
+        x1 = bsrcs[1] if len(bsrcs) > 1 else None
+        raw = ops.conv3x3_tc_fwd(x0.data, None if x1 is None else x1.data, wp_f, bias, self.cout, torch.float32)
+        y = Var(raw, grad_dtype=torch.bfloat16)
+        rec = ctx.rec(*bsrcs, self.kernel)
+        if rec:
+            y.requires_grad = True
+            if self.bias is not None and self.bias.requires_grad:
+                y.bias_sink = self.bias       # a following BatchNorm backward folds the bias gradient in
+
+            def bw():
+                g = y.grad
+                y.grad = None
+                if g is None:
+                    return
+                if g.dtype != torch.bfloat16:
+                    g = ops.cast(g, torch.bfloat16)
+                if y.bias_sink is not None:   # nobody consumed it: reduce here
+                    ops.colsum_(g, self.bias.grad)
+                off = 0
+                for s in bsrcs:
+                    c = s.shape[-1]
+                    if self.kernel.requires_grad:
+                        ops.conv3x3_tc_wgrad(s.data, g, self.kernel.grad, cin_off=off)
+                    if s.requires_grad:
+                        accumulate(s, ops.conv3x3_tc_fwd(g, None, wp_d, None, c, s.grad_dtype, row_off=off))
+                    off += c
+
+            ctx.tape.record(bw)
+        if ACT[act] != ACT_NONE:
+            return activation(ctx, y, act, alpha)
+        return y
+
+
+def _cast_var(ctx, v, dtype):
+    out = Var(ops.cast(v.data, dtype))
+    if ctx.rec(v):
+        out.requires_grad = True
+
+        def bw():
+            g = out.grad
+            out.grad = None
+            if g is not None:
+                accumulate(v, g)
+
+        ctx.tape.record(bw)
+    return out
+
+
+class BatchNorm:
+    """keras BatchNormalization() with its defaults (axis -1, momentum .99, epsilon 1e-3)."""
+    EPS = 1e-3
+    MOMENTUM = 0.99
+
+    def __init__(self, arena, state, name, c):
+        self.name, self.c = name, c
+        self.gamma = arena.add(name + "/gamma", (c,), np.ones(c, np.float32))
+        self.beta = arena.add(name + "/beta", (c,), np.zeros(c, np.float32))
+        self.moving_mean = state.add(name + "/moving_mean", (c,), np.zeros(c, np.float32))
+        self.moving_var = state.add(name + "/moving_variance", (c,), np.ones(c, np.float32))
+
+    def params(self):
+        return [self.gamma, self.beta]
+
+    def __call__(self, ctx, x, act=None, out_dtype=torch.float32):
+        code = ACT[act]
+        assert x.data.dtype == torch.float32
+        if ctx.training:
+            mean, rstd = ops.bn_stats_finalize(x.data, self.EPS, self.MOMENTUM, self.moving_mean.data, self.moving_var.data)
+        else:
+            mean, rstd = self.moving_mean.data, ops.bn_rstd_from_var(self.moving_var.data, self.EPS)
+        y = Var(ops.bn_apply(x.data, mean, rstd, self.gamma.data, self.beta.data, code, out_dtype))
+        if ctx.rec(x, self.gamma):
+            assert ctx.training, "BatchNorm backward is only recorded in training mode"
+            y.requires_grad = True
+
+            def bw():
+                g = y.grad
+                y.grad = None
+                if g is None:
+                    return
+                tr = self.gamma.requires_grad
+                sink = x.bias_sink
+                x.bias_sink = None
+                dx = ops.bn_bwd(g, x.data, mean, rstd, self.gamma.data, self.beta.data, code,
+                                self.gamma.grad if tr else None, self.beta.grad if tr else None,
+                                dx_dtype=x.grad_dtype, dbias_prev=None if sink is None else sink.grad)
+                accumulate(x, dx)
+
+            ctx.tape.record(bw)
+        return y
+
+
+class Dense:
+    def __init__(self, arena, rng, name, cin, cout, init="glorot_uniform", bias_init="zeros"):
+        self.name, self.cin, self.cout = name, cin, cout
+        self.kernel = arena.add(name + "/kernel", (cin, cout), init_weights(rng, (cin, cout), init))
+        self.bias = arena.add(name + "/bias", (cout,), np.zeros(cout, np.float32))
+
+    def params(self):
+        return [self.kernel, self.bias]
+
+    def __call__(self, ctx, x, act=None, alpha=0.0):
+        x2 = x.data.reshape(x.shape[0], -1)
+        assert x2.shape[1] == self.cin, (self.name, tuple(x.shape), self.cin)
+        y = Var(ops.dense_fwd(x2, self.kernel.data, self.bias.data))
+        if ctx.rec(x, self.kernel):
+            y.requires_grad = True
+
+            def bw():
+                g = y.grad
+                y.grad = None
+                if g is None:
+                    return
+                if self.kernel.requires_grad:
+                    ops.dense_bwd_weight(x2, g, self.kernel.grad, self.bias.grad)
+                if x.requires_grad:
+                    accumulate(x, ops.dense_bwd_data(g, self.kernel.data).view(x.shape))
+
+            ctx.tape.record(bw)
+        if ACT[act] != ACT_NONE:
+            return activation(ctx, y, act, alpha)
+        return y
+
+
+# --------------------------------------------------------------------------------------------
+# functional ops
+# --------------------------------------------------------------------------------------------
+def activation(ctx, x, act, alpha=0.0):
+    code = ACT[act]
+    y = Var(ops.act_fwd(x.data, code, alpha))
+    if ctx.rec(x):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is not None:
+                accumulate(x, ops.act_bwd(g, y.data, code, alpha))
+
+        ctx.tape.record(bw)
+    return y
+
+
+def add(ctx, a, b):
+    y = Var(ops.add(a.data, b.data))
+    if ctx.rec(a, b):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is not None:
+                accumulate(a, g, owned=False)
+                accumulate(b, g, owned=False)
+
+        ctx.tape.record(bw)
+    return y
+
+
+def concat(ctx, vs):
+    y = Var(ops.concat_channels([v.data for v in vs]))
+    if ctx.rec(*vs):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is None:
+                return
+            off = 0
+            for v in vs:
+                c = v.shape[-1]
+                if v.requires_grad:
+                    accumulate(v, ops.slice_channels(g, off, c))
+                off += c
+
+        ctx.tape.record(bw)
+    return y
+
+
+def slice_channels(ctx, x, off, c):
+    y = Var(ops.slice_channels(x.data, off, c))
+    if ctx.rec(x):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is None:
+                return
+            full = ops.zeros(*x.shape)
+            ops.copy_channels(g, 0, full, off, c)
+            accumulate(x, full)
+
+        ctx.tape.record(bw)
+    return y
+
+
+def maxpool2(ctx, x):
+    y = Var(ops.maxpool2_fwd(x.data))
+    if ctx.rec(x):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is not None:
+                if g.dtype != x.data.dtype:
+                    g = ops.cast(g, x.data.dtype)
+                accumulate(x, ops.maxpool2_bwd(x.data, g))
+
+        ctx.tape.record(bw)
+    return y
+
+
+def upsample2(ctx, x):
+    y = Var(ops.upsample2_fwd(x.data))
+    if ctx.rec(x):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is not None:
+                accumulate(x, ops.upsample2_bwd(g))
+
+        ctx.tape.record(bw)
+    return y
+
+
+def softmax(ctx, x, rounding=False):
+    """softmax over the last axis, optionally followed by Rounding (straight-through gradient)."""
+    p, r = ops.softmax_fwd(x.data, want_round=rounding)
+    y = Var(r if rounding else p)
+    if ctx.rec(x):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is not None:
+                accumulate(x, ops.softmax_bwd(p, g))     # Rounding gradient is the identity
+
+        ctx.tape.record(bw)
+    return y
+
+
+def rounding(ctx, x):
+    y = Var(ops.round_fwd(x.data))
+    if ctx.rec(x):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is not None:
+                accumulate(x, g, owned=False)      # straight-through: the same buffer flows on
+
+        ctx.tape.record(bw)
+    return y
+
+
+def film(ctx, x, gamma, beta):
+    y = Var(ops.film_fwd(x.data, gamma.data, beta.data))
+    if ctx.rec(x, gamma, beta):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is None:
+                return
+            dx, dg, db = ops.film_bwd(g, x.data, gamma.data)
+            accumulate(x, dx)
+            accumulate(gamma, dg)
+            accumulate(beta, db)
+
+        ctx.tape.record(bw)
+    return y
+
+
+def maximum(ctx, a, b):
+    y = Var(ops.max_fwd(a.data, b.data))
+    if ctx.rec(a, b):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is None:
+                return
+            da, db = ops.max_bwd(a.data, b.data, g)
+            accumulate(a, da)
+            accumulate(b, db)
+
+        ctx.tape.record(bw)
+    return y
+
+
+def tps_warp(ctx, vol, theta, cp=(5, 5)):
+    out, _ = ops.tps_warp_fwd(vol.data, theta.data, cp)
+    y = Var(out)
+    if ctx.rec(vol, theta):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is None:
+                return
+            dvol, dtheta = ops.tps_warp_bwd(vol.data, theta.data, g, cp, need_dvol=vol.requires_grad)
+            if vol.requires_grad:
+                accumulate(vol, dvol)
+            accumulate(theta, dtheta)
+
+        ctx.tape.record(bw)
+    return y
+
+
+def reshape(ctx, x, shape):
+    y = Var(x.data.view(shape))
+    if ctx.rec(x):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is not None:
+                accumulate(x, g.view(x.shape), owned=False)
+
+        ctx.tape.record(bw)
+    return y
+
+
+def resize_nn(ctx, x, ho, wo):
+    y = Var(ops.resize_nn_fwd(x.data, ho, wo))
+    if ctx.rec(x):
+        y.requires_grad = True
+        H, W = x.shape[1], x.shape[2]
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is not None:
+                accumulate(x, ops.resize_nn_bwd(g, H, W))
+
+        ctx.tape.record(bw)
+    return y
+
+
+def spade_norm(ctx, x, gamma, beta, act="lrelu", alpha=0.2):
+    """InstanceNormalization(axis=None, no affine) -> SPADE_COND -> activation, fused (layers/spade.py:26-32,52-55)."""
+    code = ACT[act]
+    acc = ops.in_stats(x.data)
+    y = Var(ops.spade_fwd(x.data, acc, gamma.data, beta.data, code, alpha))
+    if ctx.rec(x, gamma, beta):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is None:
+                return
+            dx, dg, db = ops.spade_bwd(g, x.data, acc, gamma.data, beta.data, code, alpha)
+            accumulate(x, dx)
+            accumulate(gamma, dg)
+            accumulate(beta, db)
+
+        ctx.tape.record(bw)
+    return y
+
+
+# --------------------------------------------------------------------------------------------
+# losses: each adds weight*value to ``loss_buf[slot]`` and seeds the gradient of its input
+# --------------------------------------------------------------------------------------------
+def loss_seg(ctx, pred, target, nch, use_bce, weight, loss_slot):
+    g = ops.segloss(pred.data, target, nch, use_bce, weight, loss_slot, want_grad=ctx.rec(pred))
+    if g is not None:
+        accumulate(pred, g)
+
+
+def loss_l1l2(ctx, pred, target, kind, weight, loss_slot, cval=0.0):
+    g = ops.l1l2_loss(pred.data, target, kind, weight, loss_slot, cval=cval, want_grad=ctx.rec(pred))
+    if g is not None:
+        accumulate(pred, g)
+
+
+def vae_sample(ctx, mu, logvar, eps, kl_weight, loss_slot):
+    """z = mu + exp(.5 lv) eps (utils/sdnet_utils.py:9-21) and the KL output whose mean is the
+    `Enc_Modality` loss (costs.py:186-195); the KL gradient is folded into the backward of z."""
+    z, klv = ops.vae_fwd(mu.data, logvar.data, eps, kl_weight, loss_slot)
+    zv = Var(z)
+    if ctx.rec(mu, logvar):
+        zv.requires_grad = True
+
+        def bw():
+            g = zv.grad
+            zv.grad = None
+            dmu, dlv = ops.vae_bwd(mu.data, logvar.data, eps, g, kl_weight)
+            accumulate(mu, dmu)
+            accumulate(logvar, dlv)
+
+        ctx.tape.record(bw)
+    return zv, klv

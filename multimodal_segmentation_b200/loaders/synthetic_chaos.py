@@ -1,0 +1,103 @@
+"""Synthetic CHAOS-shaped paired T1/T2 data (shapes and value ranges of loaders/chaos.py:25-26,242-246:
+(H,W,1) slices rescaled per slice to exactly [-1,1], 4 binary organ masks).
+
+Images: a smooth random field plus a few constant-intensity ellipses; T2 = a small smooth warp of the
+same ellipses with a different intensity map, so that registration has signal.  Masks: 4 disjoint
+binary ellipse channels.  Deterministic given the seed.
+"""
+import os
+
+import numpy as np
+
+from ..utils.data_utils import rescale
+
+DEFAULT_SHAPE = (192, 192, 1)     # loaders/chaos.py:26
+
+
+def _smooth(rng, h, w, k=9):
+    f = rng.normal(size=(h + 2 * k, w + 2 * k))
+    ker = np.ones(k) / k
+    for _ in range(2):
+        f = np.apply_along_axis(lambda m: np.convolve(m, ker, mode="same"), 0, f)
+        f = np.apply_along_axis(lambda m: np.convolve(m, ker, mode="same"), 1, f)
+    return f[k:-k, k:-k]
+
+
+def make_pairs(n, shape, num_masks=4, seed=10):
+    """-> x1[n,H,W,1], x2[n,H,W,1] in [-1,1] (float32), m1, m2 [n,H,W,num_masks] in {0,1}"""
+    rng = np.random.RandomState(seed)
+    H, W = shape[0], shape[1]
+    yy, xx = np.mgrid[:H, :W].astype(np.float32)
+    x1 = np.zeros((n, H, W, 1), np.float32)
+    x2 = np.zeros((n, H, W, 1), np.float32)
+    m1 = np.zeros((n, H, W, num_masks), np.float32)
+    m2 = np.zeros((n, H, W, num_masks), np.float32)
+    for i in range(n):
+        img1 = 0.6 * _smooth(rng, H, W)
+        img2 = 0.6 * _smooth(rng, H, W)
+        occupied1 = np.zeros((H, W), bool)
+        occupied2 = np.zeros((H, W), bool)
+        shift = rng.uniform(-0.03, 0.03, size=2) * np.array([H, W])
+        for c in range(num_masks):
+            cy, cx = rng.uniform(0.25, 0.75) * H, rng.uniform(0.25, 0.75) * W
+            ry, rx = rng.uniform(0.06, 0.16) * H, rng.uniform(0.06, 0.16) * W
+            e1 = (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2) <= 1.0
+            e2 = (((yy - cy - shift[0]) / (ry * 1.05)) ** 2 + ((xx - cx - shift[1]) / (rx * 0.95)) ** 2) <= 1.0
+            e1 &= ~occupied1
+            e2 &= ~occupied2
+            occupied1 |= e1
+            occupied2 |= e2
+            m1[i, ..., c] = e1
+            m2[i, ..., c] = e2
+            img1[e1] = rng.uniform(-1, 1)
+            img2[e2] = rng.uniform(-1, 1)
+        x1[i, ..., 0] = rescale(img1)
+        x2[i, ..., 0] = rescale(img2)
+    return x1, x2, m1, m2
+
+
+class PairedData(object):
+    """the slice of loaders/MultimodalPairedData.py used by the executors"""
+
+    def __init__(self, images, masks, volumes_per_item=12):
+        self.images = images          # list of two arrays
+        self.masks = masks
+        self.num_volumes = volumes_per_item
+
+    def size(self):
+        return self.images[0].shape[0]
+
+    def sample(self, nb_samples, seed=-1):
+        pass  # all synthetic volumes are kept (the reference sub-samples labelled volumes by l_mix)
+
+    def get_images_modi(self, i):
+        return self.images[i]
+
+    def get_masks_modi(self, i):
+        return self.masks[i]
+
+    def randomise_pairs(self, *a, **k):
+        raise NotImplementedError("pair randomisation belongs to the automated-pairing path")
+
+    def expand_pairs(self, *a, **k):
+        raise NotImplementedError("pair expansion belongs to the automated-pairing path")
+
+
+class SyntheticChaosLoader(object):
+    def __init__(self):
+        shp = os.environ.get("DAFK_INPUT_SHAPE")
+        self.input_shape = tuple(int(v) for v in shp.split("x")) if shp else DEFAULT_SHAPE
+        self.num_masks = 4
+        self.modalities = ["t1", "t2"]
+        self.num_pairs = {"training": int(os.environ.get("DAFK_TRAIN_PAIRS", "264")), "validation": 32, "test": 32}
+
+    def load_all_modalities_concatenated(self, split, split_type, downsample=1, seed=10):
+        n = self.num_pairs.get(split_type, 32)
+        off = {"training": 0, "validation": 1, "test": 2}.get(split_type, 3)
+        x1, x2, m1, m2 = make_pairs(n, self.input_shape, self.num_masks, seed=seed + 1000 * off + int(split))
+        return PairedData([x1, x2], [m1, m2])
+
+    def load_labelled_data(self, split, split_type, modality, downsample=1):
+        d = self.load_all_modalities_concatenated(split, split_type, downsample)
+        i = self.modalities.index(modality) if modality in self.modalities else 0
+        return PairedData([d.images[i], d.images[i]], [d.masks[i], d.masks[i]])

@@ -77,7 +77,7 @@ def act_bwd(dy, y, act, alpha=0.0, inplace=False):
 def add(a, b, out=None):
     _chk(a, b)
     out = torch.empty_like(a) if out is None else out
-    call("add", a, b, out, a.numel(), _S())
+    call("add_dt", a, b, out, _dt(a), a.numel(), _S())
     return out
 
 
@@ -210,8 +210,8 @@ def bn_apply(x, mean, rstd, gamma, beta, act=ACT_NONE, out_dtype=torch.float32):
     return out
 
 
-def bn_bwd(dout, x, mean, rstd, gamma, beta, act, dgamma, dbeta, dx_dtype=torch.float32):
-    """training-mode backward; dgamma/dbeta are accumulated into (may be None)."""
+def bn_bwd(dout, x, mean, rstd, gamma, beta, act, dgamma, dbeta, dx_dtype=torch.float32, dbias_prev=None):
+    """training-mode backward; dgamma/dbeta (and the producing conv's bias gradient) are accumulated into."""
     _chk(dout, x)
     C = x.shape[-1]
     M = x.numel() // C
@@ -219,7 +219,7 @@ def bn_bwd(dout, x, mean, rstd, gamma, beta, act, dgamma, dbeta, dx_dtype=torch.
     zero_(acc)
     call("bn_bwd_reduce", dout, _dt(dout), x, mean, rstd, gamma, beta, acc, M, C, act, _S())
     dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
-    call("bn_bwd_apply", dout, _dt(dout), x, mean, rstd, gamma, beta, acc, dx, _dt(dx), dgamma, dbeta, M, C, act, _S())
+    call("bn_bwd_apply", dout, _dt(dout), x, mean, rstd, gamma, beta, acc, dx, _dt(dx), dgamma, dbeta, dbias_prev, M, C, act, _S())
     return dx
 
 
@@ -319,7 +319,7 @@ def conv2d_wgrad(x, dy, dw, db, stride=1, pad=0):
 def colsum_(x, out):
     _chk(x, out)
     C = x.shape[-1]
-    call("colsum", x, out, x.numel() // C, C, _S())
+    call("colsum", x, _dt(x), out, x.numel() // C, C, _S())
     return out
 
 
@@ -332,13 +332,14 @@ def pack_conv3x3(w_hwio, for_dgrad=False):
     return wp
 
 
-def conv3x3_tc_fwd(x0, x1, wp, bias, Cout, out_dtype=torch.float32):
-    """tcgen05 path; x0 (and optional x1 = second concat source) are bf16 NHWC."""
+def conv3x3_tc_fwd(x0, x1, wp, bias, Cout, out_dtype=torch.float32, row_off=0):
+    """tcgen05 path; x0 (and optional x1 = second concat source) are bf16 NHWC.  wp is the packed
+    weight matrix [9][rows][K]; the call produces output channels rows[row_off : row_off+Cout]."""
     _chk(x0, x1, wp, bias)
     N, H, W, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[-1]
     y = torch.empty((N, H, W, Cout), dtype=out_dtype, device=x0.device)
-    call("conv3x3_tc_fwd", x0, C0, x1, C1, wp, bias, y, _dt(y), N, H, W, Cout, _S())
+    call("conv3x3_tc_fwd", x0, C0, x1, C1, wp, wp.shape[1], row_off, bias, y, _dt(y), N, H, W, Cout, _S())
     return y
 
 

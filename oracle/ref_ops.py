@@ -384,9 +384,14 @@ def spectral_reg(kernel, u0, alpha=10.0):
 
 
 def adam_step(p, g, m, v, t, lr=1e-4, b1=0.9, b2=0.999, eps=1e-7):
-    """keras 2.1.6 Adam (A9); t is the 1-based step count.  numpy in, numpy out."""
+    """keras 2.1.6 Adam (A9); t is the 1-based step count.  numpy in, numpy out.
+    beta_1/beta_2 are float32 backend variables in Keras, so (1 - beta) is formed in float32
+    (1 - float32(0.999) = 0.0010000467, not 0.001)."""
     lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
-    m = b1 * m + (1 - b1) * g
-    v = b2 * v + (1 - b2) * g * g
+    b1f, b2f = float(np.float32(b1)), float(np.float32(b2))
+    omb1 = float(np.float32(1.0) - np.float32(b1))
+    omb2 = float(np.float32(1.0) - np.float32(b2))
+    m = b1f * m + omb1 * g
+    v = b2f * v + omb2 * g * g
     p = p - lr_t * m / (np.sqrt(v) + eps)
     return p, m, v

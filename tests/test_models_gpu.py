@@ -1,0 +1,222 @@
+"""Graph-level parity: the DAFNet trainers (models/dafnet.py:140-222) and the discriminator trainers on
+the GPU against the CPU oracle graph (oracle/ref_models.py), same weights, same injected randomness.
+
+* strict test: rounding disabled (smooth network), CUDA-core fp32 path -> every loss and every
+  parameter gradient within 1e-4 .. 2e-3 relative L2 of the fp64 oracle;
+* rounding enabled: binary anatomy maps can flip where a softmax output sits within float rounding of
+  0.5, so masks are compared by mismatch fraction and losses loosely;
+* tensor-core mode (bf16 operands): the north-star bound 1e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_models as RM
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def build_net(H=64, filters=16, rounding=False, use_tc=False, decoder_type="film", seed=3):
+    from multimodal_segmentation_b200 import engine as E
+    from multimodal_segmentation_b200.configuration import dafnet_config_chaos
+    from multimodal_segmentation_b200.keras_like import EasyDict
+    from multimodal_segmentation_b200.models.dafnet import DAFNet
+    E.USE_TC = use_tc
+    conf = EasyDict(dafnet_config_chaos.get((H, H, 1), decoder_type=decoder_type))
+    conf.anatomy_encoder.filters = filters
+    conf.anatomy_encoder.rounding = rounding
+    conf.n_pairs = 1
+    conf.seed = seed
+    conf.folder = "/tmp/dafk_test_no_such_folder"
+    net = DAFNet(conf)
+    net.build()
+    # theta = 0 sits exactly on the kink of the bilinear sampler: move off it; sharpen the anatomy softmax
+    rs = np.random.RandomState(0)
+    loc = net.Anatomy_Fuser.locnet.layers[-1]
+    loc.kernel.data.copy_(torch.from_numpy((rs.normal(size=loc.kernel.shape) * 2e-3).astype(np.float32)))
+    if rounding:
+        head = net.Encoders_Anatomy[0].layers[-1]
+        head.kernel.data.mul_(40.0)
+    return net, conf
+
+
+def all_weights(net, dtype=torch.float64):
+    W = {}
+    for m in list(net.Encoders_Anatomy) + [net.Enc_Modality, net.Anatomy_Fuser, net.Segmentor, net.Decoder,
+                                           net.D_Mask, net.D_Image1, net.D_Image2]:
+        for k, v in m.named_weights().items():
+            W[k] = torch.from_numpy(v).to(dtype)
+    return W
+
+
+def make_batch(conf, B, seed=1):
+    from multimodal_segmentation_b200.loaders.synthetic_chaos import make_pairs
+    H = conf.input_shape[0]
+    x1, x2, m1, m2 = make_pairs(B, (H, H, 1), 4, seed=seed)
+    res = lambda m: np.concatenate([m, 1 - np.clip(m.sum(-1, keepdims=True), 0, 1)], -1).astype(np.float32)
+    rs = np.random.RandomState(seed)
+    z1, z2, e1, e2 = (rs.normal(size=(B, conf.num_z)).astype(np.float32) for _ in range(4))
+    return x1, x2, z1, z2, e1, e2, res(m1), res(m2)
+
+
+def oracle_step(net, conf, batch, supervised=True, dtype=torch.float64):
+    W = all_weights(net, dtype)
+    train_names = {p.name for p in net.generator_params()}
+    for k in W:
+        if k in train_names:
+            W[k].requires_grad_(True)
+    tb = [torch.from_numpy(a).to(dtype) for a in batch]
+    c = dict(num_masks=conf.num_masks, decoder_type=conf.decoder_type, w_sup_M=conf.w_sup_M, w_adv_M=conf.w_adv_M,
+             w_rec_X=conf.w_rec_X, w_adv_X=conf.w_adv_X, w_kl=conf.w_kl, w_rec_Z=conf.w_rec_Z)
+    if not conf.anatomy_encoder.rounding:
+        orig = RM.anatomy_encoder
+        RM.anatomy_encoder = lambda *a, **k: orig(*a, rounding=False, **k)
+    try:
+        total, L, inter, st = RM.dafnet_generator_loss(W, c, *tb[:6], tb[6], tb[7] if supervised else None, supervised)
+    finally:
+        if not conf.anatomy_encoder.rounding:
+            RM.anatomy_encoder = orig
+    total.backward()
+    return W, total, L, inter, st
+
+
+def product_step(net, batch, supervised=True):
+    tr = net.supervised_trainer if supervised else net.unsupervised_trainer
+    dev = [torch.from_numpy(a).cuda() for a in batch]
+    args = dev[:7] + ([dev[7]] if supervised else [])
+    tr.forward_backward(*args)
+    torch.cuda.synchronize()
+    return tr
+
+
+def compare_grads(net, W, tol, report):
+    worst = 0.0
+    num = den = 0.0
+    for p in net.generator_params():
+        g = p.grad.detach().cpu().numpy().astype(np.float64)
+        r = W[p.name].grad.numpy()
+        num += float(((g - r) ** 2).sum())
+        den += float((r ** 2).sum())
+        if np.linalg.norm(r) > 1e-7:
+            e = rel_l2(g, r)
+            report.append((e, p.name))
+            worst = max(worst, e)
+    report.sort(reverse=True)
+    return worst, (num / max(den, 1e-300)) ** 0.5
+
+
+@pytest.mark.parametrize("supervised", [True, False])
+def test_dafnet_generator_step_strict_fp32(supervised):
+    net, conf = build_net(H=64, filters=16, rounding=False, use_tc=False)
+    batch = make_batch(conf, 2)
+    W, total, L, inter, st = oracle_step(net, conf, batch, supervised)
+    tr = product_step(net, batch, supervised)
+    vals = tr.book.buf.cpu().numpy()
+    ref = np.array([v.item() for v in L.values()])
+    assert len(vals) == len(ref)
+    assert np.abs(vals - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), (vals, ref)
+    report = []
+    worst, glob = compare_grads(net, W, 2e-3, report)
+    assert glob < 1e-4, (glob, report[:5])        # north-star fp32 bound on the whole gradient
+    assert worst < 5e-3, report[:5]
+    # BatchNorm moving statistics after one step: shared layers were updated once per call site
+    for (name, key), v in list(st.moving.items())[:40]:
+        full = name + "/" + key
+        for m in list(net.Encoders_Anatomy) + [net.Segmentor]:
+            for p in m.weight_list():
+                if p.name == full:
+                    assert rel_l2(p.numpy(), v.numpy()) < 1e-4, full
+    # one Adam step (keras 2.1.6) on the same gradients
+    from oracle import ref_ops as R
+    before = {p.name: p.numpy() for p in net.generator_params()[:6]}
+    tr.apply_gradients()
+    torch.cuda.synchronize()
+    for p in net.generator_params()[:6]:
+        g = W[p.name].grad.numpy()
+        exp, _, _ = R.adam_step(before[p.name].astype(np.float64), g, 0 * g, 0 * g, 1)
+        assert np.abs(p.numpy() - exp).max() < 2e-6, p.name
+
+
+def test_dafnet_generator_step_with_rounding():
+    net, conf = build_net(H=64, filters=16, rounding=True, use_tc=False)
+    batch = make_batch(conf, 2)
+    W, total, L, inter, st = oracle_step(net, conf, batch, True)
+    s1 = net.Encoders_Anatomy[0].predict_device(torch.from_numpy(batch[0]).cuda())  # inference-phase smoke
+    assert set(torch.unique(s1).tolist()) <= {0.0, 1.0}
+    tr = product_step(net, batch, True)
+    vals = tr.book.buf.cpu().numpy()
+    ref = np.array([v.item() for v in L.values()])
+    # a flipped anatomy pixel moves the losses by O(1/pixels): loose bound
+    assert np.abs(vals - ref).max() < 2e-2 * max(1.0, np.abs(ref).max()), (vals, ref)
+    report = []
+    worst, glob = compare_grads(net, W, 1.0, report)
+    assert glob < 5e-2, (glob, report[:5])
+
+
+def test_dafnet_generator_step_tensor_core_mode():
+    net, conf = build_net(H=64, filters=64, rounding=False, use_tc=True)
+    batch = make_batch(conf, 2)
+    W, total, L, inter, st = oracle_step(net, conf, batch, True, dtype=torch.float32)
+    tr = product_step(net, batch, True)
+    vals = tr.book.buf.cpu().numpy()
+    ref = np.array([v.item() for v in L.values()])
+    assert np.abs(vals - ref).max() < 1e-2 * max(1.0, np.abs(ref).max()), (vals, ref)
+    report = []
+    worst, glob = compare_grads(net, W, 1.0, report)
+    assert glob < 1e-2, (glob, report[:8])          # bf16 conv path: <= 1e-2 relative L2
+
+
+def test_discriminator_trainers():
+    net, conf = build_net(H=64, filters=16, rounding=False, use_tc=False)
+    rs = np.random.RandomState(5)
+    for D, tr, C in ((net.D_Mask, net.D_Mask_trainer, 4), (net.D_Image1, net.D_Image1_trainer, 1)):
+        real = rs.uniform(size=(3, 64, 64, C)).astype(np.float32)
+        fake = rs.uniform(size=(3, 64, 64, C)).astype(np.float32)
+        W = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in D.named_weights().items()}
+        u0s = [torch.from_numpy(reg.u0_host).double() for _, reg in D.regularizers]
+        total, parts = RM.discriminator_trainer_loss(W, D.name, torch.from_numpy(real).double(),
+                                                     torch.from_numpy(fake).double(), u0s)
+        total.backward()
+        tr.forward_backward(torch.from_numpy(real).cuda(), torch.from_numpy(fake).cuda())
+        torch.cuda.synchronize()
+        vals = tr.book.buf.cpu().numpy()
+        assert np.abs(vals - np.array([p.item() for p in parts])).max() < 1e-4
+        for p in D.params():
+            assert rel_l2(p.grad.cpu().numpy(), W[p.name].grad.numpy()) < 2e-3, p.name
+
+
+def test_spade_decoder_matches_oracle():
+    net, conf = build_net(H=64, filters=16, rounding=False, use_tc=False, decoder_type="spade")
+    from multimodal_segmentation_b200 import engine as E
+    rs = np.random.RandomState(2)
+    s = (rs.uniform(size=(2, 64, 64, 8)) > 0.7).astype(np.float32)
+    z = rs.normal(size=(2, 8)).astype(np.float32)
+    W = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in net.Decoder.named_weights().items()}
+    yr = RM.decoder_spade(W, torch.from_numpy(s).double(), torch.from_numpy(z).double())
+    g = rs.normal(size=tuple(yr.shape)).astype(np.float32)
+    (yr * torch.from_numpy(g).double()).sum().backward()
+    tape = E.Tape()
+    ctx = E.Ctx(tape, training=True)
+    for p in net.Decoder.params():
+        p.grad.zero_()
+    y = net.Decoder(ctx, E.Var(torch.from_numpy(s).cuda()), E.Var(torch.from_numpy(z).cuda()))
+    assert rel_l2(y.data.cpu().numpy(), yr.detach().numpy()) < 1e-4
+    y.grad = torch.from_numpy(g).cuda()
+    y.requires_grad = True
+    tape.backward()
+    torch.cuda.synchronize()
+    worst = max(rel_l2(p.grad.cpu().numpy(), W[p.name].grad.numpy()) for p in net.Decoder.params())
+    assert worst < 5e-3, worst
+
+
+def test_predict_mask_simple_matches_oracle():
+    net, conf = build_net(H=64, filters=16, rounding=True, use_tc=False)
+    batch = make_batch(conf, 3)
+    W = all_weights(net)
+    ref = RM.predict_mask_simple(W, torch.from_numpy(batch[1]).double(), "enc2_", "shared_").numpy()
+    got = net.predict_mask(1, "simple", [batch[0], batch[1]])
+    assert got.shape == ref.shape
+    # argmax segmentation: bit-exact except where an anatomy pixel flipped
+    mism = np.mean(np.argmax(got, -1) != np.argmax(ref, -1))
+    assert mism < 5e-3, mism
