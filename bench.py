@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- DAFNet `train_batch` throughput on B200 (metric of BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one full ``DAFNetExecutor.train_batch`` (model_executors/dafnet_executor.py:369-387 of the
+reference: generator update + 2 mask-discriminator updates + 2 image-discriminator updates) on a
+batch of B=32 paired synthetic CHAOS-shaped 224x224 T1/T2 slices per GPU.  One slice = one pair.
+
+  value : slices/s with the inputs already resident in HBM (device-timed, max over ranks)
+  e2e   : the same metric through the public executor API (pinned host batches -> H2D every step ->
+          train_batch -> D2H of the loss slots every step)
+  roofline : the dominant kernel family (tcgen05 implicit-GEMM convolution), algorithmic FLOPs per
+          launch / CUDA-event duration of that launch, summed over the timed region
+  cpu_baseline : the CPU oracle (torch-CPU restatement of the reference graph; TF 1.4 cannot be
+          installed here) on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dafnet_film", choices=["dafnet_film", "dafnet_spade"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--l_mix", type=float, default=1.0)
+    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tc", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi, DURING the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic flops (reference layer list; SURVEY.md 8d / BASELINE.md 3)
+# ------------------------------------------------------------------------------------------------
+GF_PER_PAIR = {"dafnet_film": 1241.9, "dafnet_spade": 2192.0}
+
+
+def conf_for(args):
+    from multimodal_segmentation_b200.configuration import dafnet_config_chaos
+    from multimodal_segmentation_b200.keras_like import EasyDict
+    conf = EasyDict(dafnet_config_chaos.get((args.size, args.size, 1),
+                                            decoder_type="spade" if args.workload == "dafnet_spade" else "film"))
+    conf.batch_size = args.batch
+    conf.l_mix = args.l_mix
+    conf.n_pairs = 1
+    conf.folder = "/tmp/dafk_bench_run"
+    return conf
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle graph on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_train_batch_seconds(conf, B, seed=0):
+    """one DAFNet train_batch on the CPU oracle (generator fwd+bwd+Adam, D_Mask x2, D_Image x2 with their
+    inference passes), on B pairs.  Returns (seconds, threads)."""
+    import torch
+    from oracle import ref_step
+    torch.manual_seed(seed)
+    t0 = time.perf_counter()
+    ref_step.dafnet_train_batch_cpu(conf, B, seed)
+    return time.perf_counter() - t0, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path cannot be run (TF 1.4 / Keras 2.1.6 are not
+    installable: py3.12, no wheels, no network), so this arm times the CPU oracle = the restatement of the
+    reference graph, with all host threads, on a bounded sample (cpu-batch pairs per step)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    conf = conf_for(args)
+    B = args.cpu_batch
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, threads = cpu_train_batch_seconds(conf, B, seed=i)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1000.0 * float(np.mean(times))
+    val = B / (ms / 1000.0)
+    line = {
+        "impl": "reference", "metric": "DAFNet train slices/s @224^2", "value": val, "unit": "slices/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s train_batch l_mix=%g %dx%d, CPU sample of %d pairs per step" %
+                   (args.workload, args.l_mix, args.size, args.size, B)},
+        "cpu_baseline": {"value": val, "unit": "slices/s", "cores": threads, "kind": "port",
+                         "sample": "%d pairs per train_batch (the GPU arm uses %d per GPU); CPU restatement of the "
+                                   "reference graph, TF 1.4 is not installable" % (B, args.batch)},
+        "e2e": {"value": val, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from multimodal_segmentation_b200 import _lib, engine as E, ops
+    from multimodal_segmentation_b200 import parallel
+    from multimodal_segmentation_b200.models.dafnet import DAFNet
+    from multimodal_segmentation_b200.model_executors.dafnet_executor import DAFNetExecutor
+    from multimodal_segmentation_b200 import instrument
+
+    E.USE_TC = not args.no_tc
+    conf = conf_for(args)
+    conf.seed = 10 + rank                     # per-rank data / sampling seed; weights are broadcast from rank 0
+    os.environ["DAFK_TRAIN_PAIRS"] = str(max(4 * args.batch, 64))
+    np.random.seed(conf.seed)
+    net = DAFNet(conf)
+    net.build()
+    if world > 1:
+        parallel.enable_data_parallel(net)
+    ex = DAFNetExecutor(conf, net)
+    ex.init_train_data()
+
+    # ---- resident-input mode: pre-stage a pool of step inputs in HBM
+    pool = [ex.stage_step_inputs() for _ in range(2)]
+    torch.cuda.synchronize()
+
+    def step_resident(i):
+        ex.train_batch_on(pool[i % len(pool)])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    instrument.reset()
+    instrument.enabled = True
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step_resident(i)
+    ev1.record()
+    barrier()
+    instrument.enabled = False
+    launches = _lib.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    pairs_per_step = args.batch * (2 if 0 < args.l_mix < 1 else 1)
+    value = world * pairs_per_step * args.steps / (ms_total / 1000.0)
+    kern = instrument.summary()
+
+    # ---- end to end through the executor API (pinned host -> H2D -> train_batch -> D2H losses)
+    e2e = None
+    if not args.no_e2e:
+        ex.h2d_bytes = ex.d2h_bytes = 0
+        losses = {n: [] for n in ex.get_loss_names()}
+        for i in range(max(1, args.warmup // 2)):
+            ex.train_batch(losses)
+            ex.flush_losses(losses)
+        barrier()
+        ex.h2d_bytes = ex.d2h_bytes = 0
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            ex.train_batch(losses)
+            ex.flush_losses(losses)       # D2H read of the step's losses (synchronises)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * pairs_per_step * args.steps / dt, "unit": "slices/s",
+               "h2d_bytes_per_step": int(ex.h2d_bytes / args.steps), "d2h_bytes_per_step": int(ex.d2h_bytes / args.steps),
+               "last_loss": float(np.mean(losses["loss"][-1:])) if losses["loss"] else None}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (sustained, kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    roof = None
+    if kern:
+        dom = max(kern.values(), key=lambda k: k["ms"])
+        ach = dom["flops"] / (dom["ms"] / 1000.0) / 1e12 if dom["ms"] > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": dom["name"], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                "launches": dom["n"], "share_of_step": dom["ms"] / ms_total,
+                "all_kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["n"] / args.steps,
+                                    "TFLOP/s": (v["flops"] / (v["ms"] / 1000.0) / 1e12) if v["ms"] > 0 and v["flops"] else None,
+                                    "GB/s": (v["bytes"] / (v["ms"] / 1000.0) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
+                                for k, v in kern.items()}}
+    cpu = None
+    if not args.no_cpu_baseline:
+        dtc, threads = cpu_train_batch_seconds(conf, args.cpu_batch)
+        cpu = {"value": args.cpu_batch / dtc, "unit": "slices/s", "cores": threads, "kind": "port",
+               "sample": "one train_batch on %d pairs (%.1f s); CPU restatement of the reference graph (torch-CPU fp32), "
+                         "TF 1.4 / Keras 2.1.6 are not installable here" % (args.cpu_batch, dtc)}
+    algo_tf = GF_PER_PAIR[args.workload] * pairs_per_step / 1000.0
+    line = {
+        "metric": "DAFNet train slices/s @224^2", "value": value, "unit": "slices/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if E.USE_TC else "f32", "data": "synthetic",
+        "config": {"workload": "%s train_batch (generator + 2x D_Mask + D_Image1 + D_Image2 updates), l_mix=%g, "
+                               "%dx%d, %d pairs per GPU" % (args.workload, args.l_mix, args.size, args.size, args.batch),
+                   "parallelism": "dp%d" % world,
+                   "l2": "inputs+activations per step are tens of GB, far larger than the 126 MB L2",
+                   "algorithmic_tflop_per_step_per_gpu": algo_tf},
+        "step_tflops_per_gpu": algo_tf / (ms_step / 1000.0),
+        "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -27,4 +27,9 @@ def build(conf):
     m = Model("Anatomy_Fuser", locnet.layers, fwd, [output_shape, output_shape], [output_shape, output_shape], scope)
     m.locnet = locnet
     m.forward_deform = fwd_deform      # first output only (DAFNet trainers discard the fused map)
+
+    def predict_deform_device(a1, a2):
+        m._ensure_device()
+        return fwd_deform(E.Ctx(None, training=False), E.Var(a1), E.Var(a2)).data
+    m.predict_deform_device = predict_deform_device
     return m

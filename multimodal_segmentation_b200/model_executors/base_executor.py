@@ -1,0 +1,137 @@
+"""Base executor (reference: model_executors/base_executor.py:14-119).
+
+Data generators: the reference wraps every array in a Keras ImageDataGenerator (rotation_range 20,
+base_executor.py:103-110).  Augmentation is out of scope for the hot path (synthetic inputs), so a
+generator here is a seeded, shuffling mini-batch iterator that stages each batch in PINNED host
+memory -- the host->device copy of the step is an asynchronous cudaMemcpy from that buffer.
+"""
+import itertools
+import logging
+
+import numpy as np
+import torch
+
+from ..loaders import loader_factory
+
+log = logging.getLogger("executor")
+
+
+class BatchFlow(object):
+    """equivalent of ImageDataGenerator().flow(array, batch_size, seed) without augmentation"""
+
+    def __init__(self, array, batch_size, seed):
+        self.array = np.ascontiguousarray(array, dtype=np.float32)
+        self.batch_size = batch_size
+        self.rng = np.random.RandomState(seed)
+        self.n = self.array.shape[0]
+        self.order = None
+        self.pos = 0
+        self.pinned = [None, None]      # double-buffered pinned staging
+        self.events = [None, None]      # H2D-complete events recorded by the consumer
+        self.turn = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.order is None or self.pos >= self.n:
+            self.order = self.rng.permutation(self.n)
+            self.pos = 0
+        idx = self.order[self.pos:self.pos + self.batch_size]
+        self.pos += self.batch_size
+        shape = (len(idx),) + self.array.shape[1:]
+        if torch.cuda.is_available():
+            t = self.turn
+            self.turn ^= 1
+            if self.pinned[t] is None:
+                self.pinned[t] = torch.empty((self.batch_size,) + self.array.shape[1:], dtype=torch.float32).pin_memory()
+            if self.events[t] is not None:
+                self.events[t].synchronize()     # the copy that last read this buffer has finished
+            out = self.pinned[t][:len(idx)]
+            np.take(self.array, idx, axis=0, out=out.numpy())
+            self._last = t
+            return out
+        return torch.from_numpy(self.array[idx].reshape(shape))
+
+    def mark_copied(self):
+        """called by the consumer right after it enqueued the H2D copy of the last batch"""
+        if torch.cuda.is_available():
+            ev = torch.cuda.Event()
+            ev.record()
+            self.events[self._last] = ev
+
+
+class FlowGroup(object):
+    """zip of aligned BatchFlows (same seed -> same order), yields a tensor or a tuple of tensors"""
+
+    def __init__(self, flows):
+        self.flows = flows
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        items = [next(f) for f in self.flows]
+        return items[0] if len(items) == 1 else tuple(items)
+
+    def mark_copied(self):
+        for f in self.flows:
+            f.mark_copied()
+
+
+class Executor(object):
+    def __init__(self, conf, model):
+        self.conf = conf
+        self.model = model
+        self.loader = loader_factory.init_loader(self.conf.dataset_name)
+        self.batch = 0
+        self.epoch = 0
+
+    def init_train_data(self):
+        pass
+
+    def get_loss_names(self):
+        pass
+
+    def train(self):
+        pass
+
+    def get_data_generator(self, train_images=None, train_labels=None):
+        """base_executor.py:37-78: zip of one flow per array, all seeded with conf.seed so that the image and
+        label streams stay aligned"""
+        gens = []
+        for arrs in (train_images, train_labels):
+            if arrs is None:
+                continue
+            if type(arrs) != list:
+                arrs = [arrs]
+            for a in arrs:
+                gens.append(BatchFlow(a, self.conf.batch_size, self.conf.seed))
+        if len(gens) == 0:
+            raise Exception("No data to iterate.")
+        return FlowGroup(gens)
+
+    def validate(self, epoch_loss):
+        pass
+
+    def add_residual(self, data):
+        """base_executor.py:83-87: background channel = 1 where no mask channel is set"""
+        residual = np.ones(data.shape[:-1] + (1,), dtype=data.dtype)
+        for i in range(data.shape[-1]):
+            residual[data[..., i:i + 1] == 1] = 0
+        return np.concatenate([data, residual], axis=-1)
+
+    def test(self):
+        from ..model_tester import ModelTester
+        log.info("Evaluating model on test data")
+        tester = ModelTester(self.model, self.conf)
+        tester.run()
+
+    def get_datagen_params(self):
+        return dict(horizontal_flip=False, vertical_flip=False, rotation_range=20.,
+                    width_shift_range=0, height_shift_range=0, zoom_range=0)
+
+    def align_batches(self, array_list):
+        """base_executor.py:112-119"""
+        mn = np.min([x.shape[0] for x in array_list])
+        return [x[0:mn] for x in array_list]

@@ -1,0 +1,321 @@
+"""DAFNet executor (reference: model_executors/dafnet_executor.py:21-583).
+
+``train_batch`` keeps the reference's step schedule (dafnet_executor.py:369-387):
+  generator update (supervised and/or unsupervised trainer) -> two mask-discriminator updates ->
+  image-discriminator-1 and -2 updates, with the fake samples generated in the inference phase on
+  freshly drawn batches and randomly sub-sampled (utils/data_utils.py:125-129).
+The reference makes 25 session.run round trips per train_batch (numpy out, numpy in); here every
+intermediate stays in HBM: the only host<->device traffic of a step is the H2D copy of the input
+batches from pinned memory and the D2H read of the loss slots.
+"""
+import logging
+import os
+
+import numpy as np
+import torch
+
+from .. import costs
+from .. import ops
+from ..utils import data_utils
+from ..utils.distributions import NormalDistribution
+from .base_executor import Executor
+
+log = logging.getLogger("dafnet_executor")
+
+
+def _h2d(t):
+    return t.cuda(non_blocking=True) if torch.is_tensor(t) else torch.from_numpy(np.ascontiguousarray(t, np.float32)).cuda()
+
+
+class DAFNetExecutor(Executor):
+    def __init__(self, conf, model):
+        super(DAFNetExecutor, self).__init__(conf, model)
+        self.loader.modalities = self.conf.modality
+        self.gen_labelled = None
+        self.gen_unlabelled = None
+        self.discriminator_masks = None
+        self.discriminator_image = None
+        self.data = None
+        self.ul_data = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._pending = []
+
+    # ------------------------------------------------------------------ data
+    def init_train_data(self):
+        self.gen_labelled = self._init_labelled_data_generator()
+        self.gen_unlabelled = self._init_unlabelled_data_generator()
+        self.discriminator_masks = self._init_disciminator_mask_generator()
+        self.discriminator_image = [self._init_discriminator_image_generator(mod) for mod in self.model.modalities]
+        self.batches = int(np.ceil(self.data_len / self.conf.batch_size))
+
+    def _init_labelled_data_generator(self):
+        if self.conf.l_mix == 0:
+            return None
+        self.data = self.loader.load_all_modalities_concatenated(self.conf.split, "training", self.conf.image_downsample)
+        self.data.sample(int(np.round(self.conf.l_mix * self.data.num_volumes)), seed=self.conf.seed)
+        self.data_len = self.data.size()
+        nm = self.loader.num_masks
+        # add_residual (dafnet_executor.py:493-494) applied once when the labelled set is staged
+        masks = [self.add_residual(self.data.get_masks_modi(i)[..., 0:nm]) for i in range(2)]
+        return self.get_data_generator(train_images=[self.data.get_images_modi(i) for i in range(2)], train_labels=masks)
+
+    def _init_unlabelled_data_generator(self):
+        if self.conf.l_mix == 1:
+            return None
+        self.ul_data = self.loader.load_all_modalities_concatenated(self.conf.split, "training", self.conf.image_downsample,
+                                                                   seed=self.conf.seed + 77)
+        if self.data is None or self.ul_data.size() > self.data.size():
+            self.data_len = self.ul_data.size()
+        nm = self.loader.num_masks
+        return self.get_data_generator(train_images=[self.ul_data.get_images_modi(i) for i in range(2)],
+                                       train_labels=[self.add_residual(self.ul_data.get_masks_modi(0)[..., 0:nm])])
+
+    def _init_disciminator_mask_generator(self):
+        """real masks for D_Mask: a separate draw (dafnet_executor.py:516-519)"""
+        d = self.loader.load_all_modalities_concatenated(self.conf.split, "training", self.conf.image_downsample,
+                                                         seed=self.conf.seed + 177)
+        masks = np.concatenate([d.get_masks_modi(0), d.get_masks_modi(1)], axis=0)
+        return self.get_data_generator(train_images=None, train_labels=[masks])
+
+    def _init_discriminator_image_generator(self, modality):
+        d = self.loader.load_all_modalities_concatenated(self.conf.split, "training", self.conf.image_downsample,
+                                                         seed=self.conf.seed + 277)
+        i = self.model.modalities.index(modality)
+        return self.get_data_generator(train_images=[d.get_images_modi(i)], train_labels=None)
+
+    # ------------------------------------------------------------------ staging helpers
+    def _stage(self, gen):
+        """next(gen) -> device tensors (async copies from the pinned buffers)"""
+        item = next(gen)
+        items = list(item) if isinstance(item, tuple) else [item]
+        n = min(t.shape[0] for t in items)
+        out = []
+        for t in items:
+            t = t[:n]
+            self.h2d_bytes += t.numel() * 4
+            out.append(t.cuda(non_blocking=True))
+        gen.mark_copied()
+        return out
+
+    def _sample_z(self, B):
+        norm = NormalDistribution()
+        z = norm.sample((B, self.conf.num_z)).astype(np.float32)
+        self.h2d_bytes += z.size * 4
+        return torch.from_numpy(z).cuda(non_blocking=True)
+
+    def _sample_idx(self, n, k):
+        idx = data_utils.sample_indices(n, k).astype(np.int32)
+        self.h2d_bytes += idx.size * 4
+        return torch.from_numpy(idx).cuda(non_blocking=True)
+
+    # ------------------------------------------------------------------ training loop
+    def get_loss_names(self):
+        return ["adv_M", "adv_X1", "adv_X2", "rec_X", "dis_M", "dis_X1", "dis_X2", "val_loss", "val_loss_mod1",
+                "val_loss_mod2", "val_loss_mod2_s1def", "val_loss_mod2_fused", "supervised_Mask", "loss", "KL", "rec_Z"]
+
+    def train(self):
+        log.info("Training Model")
+        self.init_train_data()
+        os.makedirs(self.conf.folder, exist_ok=True)
+        csv_path = os.path.join(self.conf.folder, "training.csv")
+        names = self.get_loss_names()
+        best, wait = None, 0
+        with open(csv_path, "w") as f:
+            f.write("epoch," + ",".join(names) + "\n")
+        for self.epoch in range(self.conf.epochs):
+            log.info("Epoch %d/%d" % (self.epoch, self.conf.epochs))
+            epoch_loss = {n: [] for n in names}
+            for self.batch in range(self.batches):
+                self.train_batch(epoch_loss)
+            self.flush_losses(epoch_loss)
+            self.validate(epoch_loss)
+            row = [np.mean(epoch_loss[n]) if len(epoch_loss[n]) else 0.0 for n in names]
+            with open(csv_path, "a") as f:
+                f.write(str(self.epoch) + "," + ",".join("%.6g" % v for v in row) + "\n")
+            self.model.save_models()
+            # EarlyStopping(min_delta=0.01, patience=60) on val_loss_mod2_fused (dafnet_executor.py:222,263-284)
+            cur = row[names.index("val_loss_mod2_fused")]
+            if best is None or cur < best - 0.01:
+                best, wait = cur, 0
+            else:
+                wait += 1
+                if wait >= 60:
+                    log.info("Early stopping")
+                    break
+
+    def validate(self, epoch_loss):
+        """dafnet_executor.py:303-367 (expert pairing): 1 - Dice(binarised) for modality 1, modality 2 'simple',
+        's1def' and 'fused' on the validation split"""
+        valid = self.loader.load_all_modalities_concatenated(self.conf.split, "validation", self.conf.image_downsample)
+        nm = self.loader.num_masks
+        x0, x1 = valid.get_images_modi(0), valid.get_images_modi(1)
+        real0, real1 = valid.get_masks_modi(0)[..., :nm], valid.get_masks_modi(1)[..., :nm]
+        s0 = self.model.Encoders_Anatomy[0].predict(x0)
+        s1 = self.model.Encoders_Anatomy[1].predict(x1)
+        mask1 = self.model.Segmentor.predict(s0)
+        mask2 = self.model.Segmentor.predict(s1)
+        s0_def, s_fused = self.model.Anatomy_Fuser.predict([s0, s1])
+        mask3 = self.model.Segmentor.predict(s0_def)
+        mask4 = self.model.Segmentor.predict(s_fused)
+        l1 = 1 - costs.dice(real0, mask1, binarise=True)
+        l2 = 1 - costs.dice(real1, mask2, binarise=True)
+        l3 = 1 - costs.dice(real1, mask3, binarise=True)
+        l4 = 1 - costs.dice(real1, mask4, binarise=True)
+        epoch_loss["val_loss_mod1"].append(l1)
+        epoch_loss["val_loss_mod2"].append(l2)
+        epoch_loss["val_loss_mod2_s1def"].append(l3)
+        epoch_loss["val_loss_mod2_fused"].append(l4)
+        epoch_loss["val_loss"].append(np.mean([l1, l2, l3, l4]))
+
+    # ------------------------------------------------------------------ one step
+    def train_batch(self, epoch_loss):
+        """dafnet_executor.py:369-387"""
+        if self.conf.automatedpairing:
+            raise NotImplementedError("automated pairing is a 'next' row (SURVEY.md 8f-1)")
+        if self.conf.l_mix > 0:
+            self.train_supervised_expert_pairing(epoch_loss)
+            self.train_batch_mask_discriminator(epoch_loss)
+            self.train_batch_image_discriminator(epoch_loss)
+        if self.conf.l_mix < 1:
+            self.train_unsupervised_expert_pairing(epoch_loss)
+            self.train_batch_mask_discriminator(epoch_loss)
+            self.train_batch_image_discriminator(epoch_loss)
+
+    # -- staging (host -> device) is separated from the device work so that a pre-staged step can be replayed
+    def _stage_generator(self, supervised):
+        batch = self._stage(self.gen_labelled if supervised else self.gen_unlabelled)
+        B = batch[0].shape[0]
+        return batch + [self._sample_z(B) for _ in range(4)]       # z1, z2 (sampled inputs), eps1, eps2
+
+    def _stage_mask_d(self):
+        (m1,) = self._stage(self.discriminator_masks)
+        (m2,) = self._stage(self.discriminator_masks)
+        (x1,) = self._stage(self.discriminator_image[0])
+        (x2,) = self._stage(self.discriminator_image[1])
+        B = min(t.shape[0] for t in (x1, x2, m1, m2))
+        return [x1[:B], x2[:B], m1[:B].contiguous(), m2[:B].contiguous(), self._sample_idx(2 * B, B), self._sample_idx(2 * B, B)]
+
+    def _stage_image_d(self):
+        (x1,) = self._stage(self.discriminator_image[0])
+        (x2,) = self._stage(self.discriminator_image[1])
+        B = min(x1.shape[0], x2.shape[0])
+        return [x1[:B].contiguous(), x2[:B].contiguous(), self._sample_z(B), self._sample_z(B),
+                self._sample_idx(3 * B, B), self._sample_idx(3 * B, B)]
+
+    def stage_step_inputs(self):
+        """everything one train_batch reads from the host, as device tensors"""
+        step = []
+        if self.conf.l_mix > 0:
+            step.append(("sup", self._stage_generator(True), self._stage_mask_d(), self._stage_image_d()))
+        if self.conf.l_mix < 1:
+            step.append(("unsup", self._stage_generator(False), self._stage_mask_d(), self._stage_image_d()))
+        return step
+
+    def train_batch_on(self, step):
+        """train_batch on pre-staged (HBM-resident) inputs"""
+        for kind, g, dm, di in step:
+            self._run_generator(kind == "sup", g)
+            self._run_mask_d(dm)
+            self._run_image_d(di)
+
+    def train_supervised_expert_pairing(self, epoch_loss):
+        """dafnet_executor.py:389-411"""
+        self._run_generator(True, self._stage_generator(True))
+
+    def train_unsupervised_expert_pairing(self, epoch_loss):
+        """dafnet_executor.py:413-434"""
+        self._run_generator(False, self._stage_generator(False))
+
+    def train_batch_mask_discriminator(self, epoch_loss):
+        """dafnet_executor.py:511-545"""
+        self._run_mask_d(self._stage_mask_d())
+
+    def train_batch_image_discriminator(self, epoch_loss):
+        """dafnet_executor.py:547-583"""
+        self._run_image_d(self._stage_image_d())
+
+    def _run_generator(self, supervised, t):
+        if supervised:
+            x1, x2, m1, m2, z1, z2, eps1, eps2 = t
+            tr = self.model.supervised_trainer
+            tr.train_on_device(x1, x2, z1, z2, eps1, eps2, m1, m2)
+        else:
+            x1, x2, m1, z1, z2, eps1, eps2 = t
+            tr = self.model.unsupervised_trainer
+            tr.train_on_device(x1, x2, z1, z2, eps1, eps2, m1)
+        self._pending.append((tr, tr.book.snapshot(), "gen"))
+
+    def _run_mask_d(self, t):
+        x1, x2, m1, m2, idx1, idx2 = t
+        nm = self.conf.num_masks
+        B = x1.shape[0]
+        M = self.model
+        fake_s1 = M.Encoders_Anatomy[0].predict_device(x1)
+        fake_s2 = M.Encoders_Anatomy[1].predict_device(x2)
+        for real, idx, s_own, s_a, s_b in ((m1, idx1, fake_s1, fake_s2, fake_s1), (m2, idx2, fake_s2, fake_s1, fake_s2)):
+            fake_m = M.Segmentor.predict_device(s_own)
+            s_def = M.Anatomy_Fuser.predict_deform_device(s_a, s_b)
+            fake_m_def = M.Segmentor.predict_device(s_def)
+            cat = torch.empty((2 * B,) + tuple(fake_m.shape[1:3]) + (nm,), dtype=torch.float32, device="cuda")
+            ops.copy_channels(fake_m, 0, cat[:B], 0, nm)
+            ops.copy_channels(fake_m_def, 0, cat[B:], 0, nm)
+            fake = ops.gather_rows(cat, idx)
+            M.D_Mask_trainer.train_on_device(real, fake)
+            self._pending.append((M.D_Mask_trainer, M.D_Mask_trainer.book.snapshot(), "dis_M"))
+
+    def _run_image_d(self, t):
+        x1, x2, eps1, eps2, idx1, idx2 = t
+        M = self.model
+        s1 = M.Encoders_Anatomy[0].predict_device(x1)
+        s2 = M.Encoders_Anatomy[1].predict_device(x2)
+        s1_def = M.Anatomy_Fuser.predict_deform_device(s1, s2)
+        s2_def = M.Anatomy_Fuser.predict_deform_device(s2, s1)
+        z1 = self._predict_z(s1, x1, eps1)
+        z2 = self._predict_z(s2, x2, eps2)
+        ys1 = [M.Decoder.predict_device(a, z1) for a in (s1, s2_def, s1_def)]
+        ys2 = [M.Decoder.predict_device(a, z2) for a in (s2, s1_def, s2_def)]
+        y1 = ops.gather_rows(_cat_rows(ys1), idx1)
+        y2 = ops.gather_rows(_cat_rows(ys2), idx2)
+        M.D_Image1_trainer.train_on_device(x1, y1)
+        self._pending.append((M.D_Image1_trainer, M.D_Image1_trainer.book.snapshot(), "dis_X1"))
+        M.D_Image2_trainer.train_on_device(x2, y2)
+        self._pending.append((M.D_Image2_trainer, M.D_Image2_trainer.book.snapshot(), "dis_X2"))
+
+    def _predict_z(self, s, x, eps):
+        """Enc_Modality.predict -> z (inference phase)"""
+        mu, lv = self.model.Enc_Modality.predict_device(s, x)
+        z, _ = ops.vae_fwd(mu, lv, eps, 0.0, None)
+        return z
+
+    # ------------------------------------------------------------------ loss bookkeeping
+    def flush_losses(self, epoch_loss):
+        """one D2H read per trainer call; kept out of the step so the device never waits for the host"""
+        for tr, snap, kind in self._pending:
+            h = tr.book.history(snap)
+            self.d2h_bytes += snap.numel() * 4
+            if kind == "gen":
+                epoch_loss["supervised_Mask"].append(h["Segmentor_loss"][0])
+                epoch_loss["adv_M"].append(h["D_Mask_loss"][0])
+                epoch_loss["rec_X"].append(h["Decoder_loss"][0])
+                epoch_loss["adv_X1"].append(h["D_Image1_loss"][0])
+                epoch_loss["adv_X2"].append(h["D_Image2_loss"][0])
+                epoch_loss["KL"].append(h["Enc_Modality_loss"][0])
+                epoch_loss["rec_Z"].append(h["ZReconstruct_loss"][0])
+                epoch_loss["loss"].append(h["loss"][0])
+            else:
+                epoch_loss[kind].append(h["loss"][0])
+        self._pending = []
+
+
+def _cat_rows(ts):
+    """concatenate along the batch axis with our own copy kernel (flattened as one-channel rows)"""
+    n = sum(t.shape[0] for t in ts)
+    out = torch.empty((n,) + tuple(ts[0].shape[1:]), dtype=torch.float32, device="cuda")
+    off = 0
+    for t in ts:
+        flat_src = t.reshape(-1, 1)
+        flat_dst = out[off:off + t.shape[0]].reshape(-1, 1)
+        ops.copy_channels(flat_src, 0, flat_dst, 0, 1)
+        off += t.shape[0]
+    return out

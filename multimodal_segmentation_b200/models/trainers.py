@@ -41,10 +41,15 @@ class LossBook(object):
     def slot(self, i):
         return self.buf[i:i + 1]
 
-    def history(self):
+    def snapshot(self):
+        """device copy of the slots (our own copy kernel), so the read can be deferred"""
+        return ops.cast(self.buf, torch.float32)
+
+    def history(self, vals=None):
         """Keras History semantics: 'loss' = weighted total; '<name>_loss' = unweighted value of the LAST
         output carrying that name (dafnet_executor.py:502-509 reads exactly those)."""
-        vals = self.buf.detach().cpu().numpy().astype(np.float64)
+        src = self.buf if vals is None else vals
+        vals = src.detach().cpu().numpy().astype(np.float64)
         h = {"loss": [float(vals[:len(self.names)].sum())]}
         for n, w, v in zip(self.names, self.weights, vals):
             h[n + "_loss"] = [float(v / w) if w != 0 else 0.0]

@@ -7,7 +7,7 @@ the reverse pass is recorded by ``tape.py``.
 """
 import torch
 
-from . import _lib
+from . import _lib, instrument
 from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, DAFK_BF16, DAFK_F32, ConvDesc, call
 
 _S = _lib.stream_ptr
@@ -190,7 +190,7 @@ def bn_stats_finalize(x, eps, momentum, moving_mean=None, moving_var=None):
     M = x.numel() // C
     acc = torch.empty(2 * C, dtype=torch.float64, device=x.device)
     zero_(acc)
-    call("bn_stats", x, acc, M, C, _S())
+    instrument.timed("bn_stats", 0, 4.0 * x.numel(), lambda: call("bn_stats", x, acc, M, C, _S()))
     mean, rstd = f32(C), f32(C)
     call("bn_finalize", acc, M, C, float(eps), float(momentum), mean, rstd, moving_mean, moving_var, _S())
     return mean, rstd
@@ -206,7 +206,8 @@ def bn_apply(x, mean, rstd, gamma, beta, act=ACT_NONE, out_dtype=torch.float32):
     _chk(x)
     C = x.shape[-1]
     out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
-    call("bn_apply", x, mean, rstd, gamma, beta, out, _dt(out), x.numel() // C, C, act, _S())
+    instrument.timed("bn_apply", 0, 4.0 * x.numel() + out.numel() * out.element_size(),
+                     lambda: call("bn_apply", x, mean, rstd, gamma, beta, out, _dt(out), x.numel() // C, C, act, _S()))
     return out
 
 
@@ -217,9 +218,13 @@ def bn_bwd(dout, x, mean, rstd, gamma, beta, act, dgamma, dbeta, dx_dtype=torch.
     M = x.numel() // C
     acc = torch.empty(2 * C, dtype=torch.float64, device=x.device)
     zero_(acc)
-    call("bn_bwd_reduce", dout, _dt(dout), x, mean, rstd, gamma, beta, acc, M, C, act, _S())
+    nb_in = 4.0 * x.numel() + dout.numel() * dout.element_size()
+    instrument.timed("bn_bwd_reduce", 0, nb_in,
+                     lambda: call("bn_bwd_reduce", dout, _dt(dout), x, mean, rstd, gamma, beta, acc, M, C, act, _S()))
     dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
-    call("bn_bwd_apply", dout, _dt(dout), x, mean, rstd, gamma, beta, acc, dx, _dt(dx), dgamma, dbeta, dbias_prev, M, C, act, _S())
+    instrument.timed("bn_bwd_apply", 0, nb_in + dx.numel() * dx.element_size(),
+                     lambda: call("bn_bwd_apply", dout, _dt(dout), x, mean, rstd, gamma, beta, acc, dx, _dt(dx), dgamma,
+                                  dbeta, dbias_prev, M, C, act, _S()))
     return dx
 
 
@@ -293,7 +298,9 @@ def conv2d_fwd(x, w, bias, stride=1, pad=0, act=ACT_NONE, alpha=0.0):
     KH, KW, _, Cout = w.shape
     d = conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad)
     y = f32(N, d.Ho, d.Wo, Cout)
-    call("conv2d_fwd", d, x, w, bias, y, act, float(alpha), _S())
+    fl = 2.0 * N * d.Ho * d.Wo * Cout * KH * KW * Cin
+    instrument.timed("conv2d_generic_fwd", fl, 4.0 * (x.numel() + y.numel()),
+                     lambda: call("conv2d_fwd", d, x, w, bias, y, act, float(alpha), _S()))
     return y
 
 
@@ -303,7 +310,9 @@ def conv2d_dgrad(dy, w, x_shape, stride=1, pad=0):
     KH, KW, _, Cout = w.shape
     d = conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad)
     dx = f32(N, H, W, Cin)
-    call("conv2d_dgrad", d, dy, w, dx, _S())
+    fl = 2.0 * N * d.Ho * d.Wo * Cout * KH * KW * Cin
+    instrument.timed("conv2d_generic_dgrad", fl, 4.0 * (dy.numel() + dx.numel()),
+                     lambda: call("conv2d_dgrad", d, dy, w, dx, _S()))
     return dx
 
 
@@ -313,7 +322,9 @@ def conv2d_wgrad(x, dy, dw, db, stride=1, pad=0):
     N, H, W, Cin = x.shape
     KH, KW, _, Cout = dw.shape
     d = conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad)
-    call("conv2d_wgrad", d, x, dy, dw, db, _S())
+    fl = 2.0 * N * d.Ho * d.Wo * Cout * KH * KW * Cin
+    instrument.timed("conv2d_generic_wgrad", fl, 4.0 * (x.numel() + dy.numel()),
+                     lambda: call("conv2d_wgrad", d, x, dy, dw, db, _S()))
 
 
 def colsum_(x, out):
@@ -339,7 +350,11 @@ def conv3x3_tc_fwd(x0, x1, wp, bias, Cout, out_dtype=torch.float32, row_off=0):
     N, H, W, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[-1]
     y = torch.empty((N, H, W, Cout), dtype=out_dtype, device=x0.device)
-    call("conv3x3_tc_fwd", x0, C0, x1, C1, wp, wp.shape[1], row_off, bias, y, _dt(y), N, H, W, Cout, _S())
+    fl = 2.0 * N * H * W * Cout * 9 * (C0 + C1)
+    nb = 2.0 * N * H * W * (C0 + C1) + y.numel() * y.element_size()
+    instrument.timed("conv3x3_tc_fwd+dgrad (tcgen05)", fl, nb,
+                     lambda: call("conv3x3_tc_fwd", x0, C0, x1, C1, wp, wp.shape[1], row_off, bias, y, _dt(y), N, H, W,
+                                  Cout, _S()))
     return y
 
 
@@ -348,7 +363,9 @@ def conv3x3_tc_wgrad(x, dy, dw, cin_off=0):
     _chk(x, dy, dw)
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
-    call("conv3x3_tc_wgrad", x, Cin, cin_off, dw.shape[2], dy, Cout, dw, N, H, W, _S())
+    fl = 2.0 * N * H * W * Cout * 9 * Cin
+    instrument.timed("conv3x3_tc_wgrad (tcgen05)", fl, 2.0 * (x.numel() + dy.numel()),
+                     lambda: call("conv3x3_tc_wgrad", x, Cin, cin_off, dw.shape[2], dy, Cout, dw, N, H, W, _S()))
 
 
 # ---------------------------------------------------------------------------- dense
@@ -397,7 +414,8 @@ def tps_warp_fwd(vol, theta, cp=(5, 5), want_locs=False):
     consts = tps_consts(cp[0], cp[1], vol.device)
     out = torch.empty_like(vol)
     locs = f32(B, H * W, 2) if want_locs else None
-    call("tps_warp_fwd", vol, theta, consts, out, locs, B, H, W, C, cp[0] * cp[1], _S())
+    instrument.timed("tps_warp_fwd", 0, 8.0 * vol.numel(),
+                     lambda: call("tps_warp_fwd", vol, theta, consts, out, locs, B, H, W, C, cp[0] * cp[1], _S()))
     return out, locs
 
 
@@ -411,7 +429,8 @@ def tps_warp_bwd(vol, theta, dout, cp=(5, 5), need_dvol=True):
         dvol = zero_(torch.empty_like(vol))
     dtheta = f32(B, n, 2)
     ws = torch.empty(B * (n + 3) * 2, dtype=torch.float64, device=vol.device)
-    call("tps_warp_bwd", vol, theta, consts, dout, dvol, dtheta, ws, B, H, W, C, n, _S())
+    instrument.timed("tps_warp_bwd", 0, 12.0 * vol.numel(),
+                     lambda: call("tps_warp_bwd", vol, theta, consts, dout, dvol, dtheta, ws, B, H, W, C, n, _S()))
     return dvol, dtheta
 
 

@@ -1,0 +1,110 @@
+"""ORACLE -- TEST / BASELINE INFRASTRUCTURE ONLY (see oracle/ref_ops.py).
+
+One DAFNet `train_batch` on the CPU, following model_executors/dafnet_executor.py:369-583 of the
+reference with the oracle graph: generator forward+backward+Adam, two mask-discriminator updates and
+two image-discriminator updates, each with its inference-phase fake generation.  Used by bench.py as
+the `cpu_baseline` / `--impl reference` arm (TF 1.4 / Keras 2.1.6 cannot be installed here).
+"""
+import numpy as np
+import torch
+
+from . import ref_models as RM
+from . import ref_ops as R
+
+_cache = {}
+
+
+def _weights(conf):
+    """Keras-initialised weights, built once on the host by the product's builders (host-only mode is
+    not available when CUDA is present, so the numpy initial values are read from the parameter specs)."""
+    key = (tuple(conf.input_shape), conf.decoder_type)
+    if key in _cache:
+        return _cache[key]
+    from multimodal_segmentation_b200.keras_like import BuildScope
+    from multimodal_segmentation_b200.model_components import anatomy_fuser, decoder, modality_encoder, segmentor
+    from multimodal_segmentation_b200.model_components.anatomy_encoder import AnatomyEncoders
+    from multimodal_segmentation_b200.models.discriminator import Discriminator
+    rng = np.random.RandomState(0)
+    W = {}
+    with BuildScope(rng=rng) as sc:
+        AnatomyEncoders(conf.modality).build(conf.anatomy_encoder)
+        anatomy_fuser.build(conf)
+        modality_encoder.build(conf)
+        segmentor.build(conf)
+        decoder.build(conf)
+        for name, prm in (("D_Mask", conf.d_mask_params), ("D_Image1", conf.d_image_params), ("D_Image2", conf.d_image_params)):
+            prm = dict(prm)
+            prm["name"] = name
+            from multimodal_segmentation_b200.keras_like import EasyDict
+            Discriminator(EasyDict(prm)).build()
+    for p in sc.arena.params + sc.state.params:
+        W[p.name] = torch.from_numpy(p.init.copy())
+    _cache[key] = W
+    return W
+
+
+def _adam(W, names, state, lr=1e-4):
+    state["t"] = state.get("t", 0) + 1
+    for n in names:
+        g = W[n].grad
+        if g is None:
+            continue
+        m, v = state.setdefault(n, (np.zeros(g.shape, np.float32), np.zeros(g.shape, np.float32)))
+        p, m, v = R.adam_step(W[n].detach().numpy(), g.numpy(), m, v, state["t"], lr)
+        state[n] = (m.astype(np.float32), v.astype(np.float32))
+        W[n] = torch.from_numpy(p.astype(np.float32))
+
+
+def dafnet_train_batch_cpu(conf, B, seed=0):
+    from multimodal_segmentation_b200.loaders.synthetic_chaos import make_pairs
+    W = dict(_weights(conf))
+    H = conf.input_shape[0]
+    nm = conf.num_masks
+    rs = np.random.RandomState(seed)
+    x1, x2, m1, m2 = make_pairs(B, (H, H, 1), nm, seed=seed)
+    res = lambda m: np.concatenate([m, 1 - np.clip(m.sum(-1, keepdims=True), 0, 1)], -1).astype(np.float32)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32))
+    c = dict(num_masks=nm, decoder_type=conf.decoder_type, w_sup_M=conf.w_sup_M, w_adv_M=conf.w_adv_M,
+             w_rec_X=conf.w_rec_X, w_adv_X=conf.w_adv_X, w_kl=conf.w_kl, w_rec_Z=conf.w_rec_Z)
+    gen_names = [k for k in W if not k.startswith("D_") and "moving_" not in k]
+    # ---- generator step (supervised trainer)
+    for k in gen_names:
+        W[k] = W[k].clone().requires_grad_(True)
+    z = [T(rs.normal(size=(B, conf.num_z))) for _ in range(4)]
+    total, L, inter, st = RM.dafnet_generator_loss(W, c, T(x1), T(x2), z[0], z[1], z[2], z[3], T(res(m1)), T(res(m2)), True)
+    total.backward()
+    _adam(W, gen_names, {})
+    for (name, key), v in st.moving.items():
+        W[name + "/" + key] = v
+    with torch.no_grad():
+        Wd = {k: v.detach() for k, v in W.items()}
+        inf = RM.BNState(Wd, training=False)
+        # ---- mask discriminator x2 (dafnet_executor.py:511-545)
+        s1 = RM.anatomy_encoder(Wd, T(x1), inf, "enc1_", "shared_")
+        s2 = RM.anatomy_encoder(Wd, T(x2), inf, "enc2_", "shared_")
+        fakes_m = []
+        for s_own, s_a, s_b in ((s1, s2, s1), (s2, s1, s2)):
+            fm = RM.segmentor(Wd, s_own, inf)
+            sdef = RM.anatomy_fuser(Wd, s_a, s_b)[0]
+            fmd = RM.segmentor(Wd, sdef, inf)
+            cat = torch.cat([fm[..., :nm], fmd[..., :nm]], 0)
+            fakes_m.append(cat[rs.choice(2 * B, B, replace=False)])
+        # ---- image discriminators (dafnet_executor.py:547-583)
+        s1d = RM.anatomy_fuser(Wd, s1, s2)[0]
+        s2d = RM.anatomy_fuser(Wd, s2, s1)[0]
+        mu1, lv1 = RM.modality_encoder(Wd, s1, T(x1))
+        mu2, lv2 = RM.modality_encoder(Wd, s2, T(x2))
+        z1 = R.sampling(mu1, lv1, T(rs.normal(size=(B, conf.num_z))))
+        z2 = R.sampling(mu2, lv2, T(rs.normal(size=(B, conf.num_z))))
+        y1 = torch.cat([RM.decoder(Wd, a, z1, conf.decoder_type) for a in (s1, s2d, s1d)], 0)[rs.choice(3 * B, B, replace=False)]
+        y2 = torch.cat([RM.decoder(Wd, a, z2, conf.decoder_type) for a in (s2, s1d, s2d)], 0)[rs.choice(3 * B, B, replace=False)]
+    for name, real, fake in (("D_Mask", T(m1), fakes_m[0]), ("D_Mask", T(m2), fakes_m[1]),
+                             ("D_Image1", T(x1), y1), ("D_Image2", T(x2), y2)):
+        names = [k for k in W if k.startswith(name + "_")]
+        for k in names:
+            W[k] = W[k].detach().clone().requires_grad_(True)
+        u0s = [T(rs.uniform(-1, 1, size=(W["%s_conv%d/kernel" % (name, i + 1)].shape[2] * 16, 1))) for i in range(3)]
+        loss, _ = RM.discriminator_trainer_loss(W, name, real, fake, u0s)
+        loss.backward()
+        _adam(W, names, {})
+    return float(total)
