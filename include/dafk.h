@@ -186,6 +186,22 @@ int dafk_colsum(const void* x, int x_dt, float* out, int64_t M, int C, void* str
 int dafk_conv3x3_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp,
                         int w_rows_per_tap, int w_row_off, const float* bias, void* y, int y_dt,
                         int N, int H, int W, int Cout, void* stream);
+/* General form: KH x KW kernel, stride 1 or 2 (TMA traversal stride), symmetric padding `pad`,
+ * logical output Ho x Wo written through explicit element strides (y_sn, y_sy, y_sx) so that the
+ * four parity classes of a stride-2 data gradient can be scattered into one dx tensor.
+ * Serves models/discriminator.py:24,39 (4x4, stride 2 / 1, valid) on the tensor cores. */
+int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp,
+                     int w_rows_per_tap, int w_row_off, const float* bias, void* y, int y_dt, int N,
+                     int H, int W, int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo,
+                     int64_t y_sn, int64_t y_sy, int64_t y_sx, void* stream);
+/* weight packing for the tensor-core path.  mode 0: [tap][Cout][Cin] (forward); mode 1: mirrored
+ * taps, [tap][Cin][Cout] (data gradient of a stride-1 conv); mode 2: the (pa,pb) parity class of
+ * the data gradient of a stride-2 conv, [(KH/2)*(KW/2)][Cin][Cout]. */
+int dafk_pack_conv(const float* w_hwio, void* wp, int KH, int KW, int Cin, int Cout, int mode, int pa,
+                   int pb, void* stream);
+int dafk_conv_tc_wgrad(const void* x, int Cin, int cin_off, int cin_total, const void* dy, int Cout,
+                       float* dw, int N, int H, int W, int KH, int KW, int stride, int pad, int Ho,
+                       int Wo, void* stream);
 /* weights HWIO f32 [3,3,Cin,Cout] -> bf16 [9][Cout][Cin] (fwd) or flipped/transposed
  * [9][Cin][Cout] with tap index mirrored (dgrad) */
 int dafk_pack_conv3x3(const float* w_hwio, void* wp, int Cin, int Cout, int for_dgrad,

@@ -259,14 +259,39 @@ class Conv2D:
         return [self.kernel] + ([self.bias] if self.bias is not None else [])
 
     def tc_eligible(self, srcs):
-        return (USE_TC and self.k == 3 and self.stride == 1 and self.pad == 1 and self.cout % 64 == 0
-                and all(s.shape[-1] % 64 == 0 for s in srcs))
+        """tcgen05 path: >= 64-channel operands; stride 1 (any kernel / padding) or stride 2 with an even
+        kernel and no padding (the discriminator's 4x4 stride-2 layers)"""
+        if not (USE_TC and self.k > 1 and self.cout % 64 == 0 and all(s.shape[-1] % 64 == 0 for s in srcs)):
+            return False
+        return self.stride == 1 or (self.stride == 2 and self.k % 2 == 0 and self.pad == 0)
 
     def packed(self):
+        """bf16 operand copies of the kernel: forward layout + data-gradient layout(s), refreshed after
+        every optimizer step that touched the arena"""
         ver = self.kernel.arena.version
         if self._packed is None or self._packed[0] != ver:
-            self._packed = (ver, ops.pack_conv3x3(self.kernel.data, False), ops.pack_conv3x3(self.kernel.data, True))
+            w = self.kernel.data
+            if self.stride == 1:
+                d = ops.pack_conv(w, 1)
+            else:
+                d = {(pa, pb): ops.pack_conv(w, 2, pa, pb) for pa in (0, 1) for pb in (0, 1)}
+            self._packed = (ver, ops.pack_conv(w, 0), d)
         return self._packed[1], self._packed[2]
+
+    def _tc_dgrad(self, g, x_shape, c, off, out_dtype, wp_d):
+        """data gradient towards a source with `c` channels starting at channel `off` of the kernel's Cin"""
+        N, H, W, _ = x_shape
+        k = self.k
+        if self.stride == 1:
+            out = torch.empty((N, H, W, c), dtype=out_dtype, device=g.device)
+            return ops.conv_tc_fwd(g, None, wp_d, None, c, k, k, 1, k - 1 - self.pad, out_dtype, row_off=off, out=out)
+        dx = torch.empty((N, H, W, c), dtype=out_dtype, device=g.device)
+        for (pa, pb), wp in wp_d.items():
+            view = dx[:, pa::2, pb::2, :]
+            if view.shape[1] == 0 or view.shape[2] == 0:
+                continue
+            ops.conv_tc_fwd(g, None, wp, None, c, k // 2, k // 2, 1, k // 2 - 1, out_dtype, row_off=off, out=view)
+        return dx
 
     def __call__(self, ctx, x, act=None, alpha=0.0):
         srcs = list(x) if isinstance(x, (list, tuple)) else [x]
@@ -311,7 +336,8 @@ class Conv2D:
         bias = self.bias.data if self.bias is not None else None
         x0 = bsrcs[0]
         x1 = bsrcs[1] if len(bsrcs) > 1 else None
-        raw = ops.conv3x3_tc_fwd(x0.data, None if x1 is None else x1.data, wp_f, bias, self.cout, torch.float32)
+        raw = ops.conv_tc_fwd(x0.data, None if x1 is None else x1.data, wp_f, bias, self.cout, self.k, self.k,
+                              self.stride, self.pad, torch.float32)
         y = Var(raw, grad_dtype=torch.bfloat16)
         rec = ctx.rec(*bsrcs, self.kernel)
         if rec:
@@ -332,9 +358,9 @@ class Conv2D:
                 for s in bsrcs:
                     c = s.shape[-1]
                     if self.kernel.requires_grad:
-                        ops.conv3x3_tc_wgrad(s.data, g, self.kernel.grad, cin_off=off)
+                        ops.conv_tc_wgrad(s.data, g, self.kernel.grad, off, self.k, self.k, self.stride, self.pad)
                     if s.requires_grad:
-                        accumulate(s, ops.conv3x3_tc_fwd(g, None, wp_d, None, c, s.grad_dtype, row_off=off))
+                        accumulate(s, self._tc_dgrad(g, tuple(s.shape), c, off, s.grad_dtype, wp_d))
                     off += c
 
             ctx.tape.record(bw)

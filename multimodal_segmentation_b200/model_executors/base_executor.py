@@ -84,6 +84,8 @@ class Executor(object):
         self.conf = conf
         self.model = model
         self.loader = loader_factory.init_loader(self.conf.dataset_name)
+        if hasattr(self.loader, "input_shape") and hasattr(conf, "input_shape"):
+            self.loader.input_shape = tuple(conf.input_shape)     # synthetic data follows the configured size
         self.batch = 0
         self.epoch = 0
 

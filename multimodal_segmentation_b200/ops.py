@@ -352,10 +352,56 @@ def conv3x3_tc_fwd(x0, x1, wp, bias, Cout, out_dtype=torch.float32, row_off=0):
     y = torch.empty((N, H, W, Cout), dtype=out_dtype, device=x0.device)
     fl = 2.0 * N * H * W * Cout * 9 * (C0 + C1)
     nb = 2.0 * N * H * W * (C0 + C1) + y.numel() * y.element_size()
-    instrument.timed("conv3x3_tc_fwd+dgrad (tcgen05)", fl, nb,
+    instrument.timed("conv_tc_fwd+dgrad (tcgen05)", fl, nb,
                      lambda: call("conv3x3_tc_fwd", x0, C0, x1, C1, wp, wp.shape[1], row_off, bias, y, _dt(y), N, H, W,
                                   Cout, _S()))
     return y
+
+
+def pack_conv(w_hwio, mode, pa=0, pb=0):
+    """mode 0: [taps][Cout][Cin] forward; 1: mirrored [taps][Cin][Cout] (stride-1 dgrad);
+    2: stride-2 dgrad parity class (pa,pb): [(KH/2)(KW/2)][Cin][Cout]"""
+    _chk(w_hwio)
+    KH, KW, Cin, Cout = w_hwio.shape
+    if mode == 0:
+        shape = (KH * KW, Cout, Cin)
+    elif mode == 1:
+        shape = (KH * KW, Cin, Cout)
+    else:
+        shape = ((KH // 2) * (KW // 2), Cin, Cout)
+    wp = torch.empty(shape, dtype=torch.bfloat16, device=w_hwio.device)
+    call("pack_conv", w_hwio, wp, KH, KW, Cin, Cout, mode, pa, pb, _S())
+    return wp
+
+
+def conv_tc_fwd(x0, x1, wp, bias, Cout, KH, KW, stride, pad, out_dtype=torch.float32, row_off=0, out=None):
+    """general tcgen05 convolution.  ``out`` may be a strided NHWC view (e.g. dx[:, pa::2, pb::2, :]); its
+    spatial extent defines the logical output size."""
+    _chk(x0, x1, wp, bias)
+    N, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[-1]
+    if out is None:
+        Ho = (H + 2 * pad - KH) // stride + 1
+        Wo = (W + 2 * pad - KW) // stride + 1
+        out = torch.empty((N, Ho, Wo, Cout), dtype=out_dtype, device=x0.device)
+    Ho, Wo = out.shape[1], out.shape[2]
+    assert out.stride(3) == 1 and out.shape[3] == Cout
+    fl = 2.0 * N * Ho * Wo * Cout * KH * KW * (C0 + C1)
+    nb = 2.0 * x0.numel() + (0 if x1 is None else 2.0 * x1.numel()) + N * Ho * Wo * Cout * out.element_size()
+    instrument.timed("conv_tc_fwd+dgrad (tcgen05)", fl, nb,
+                     lambda: call("conv_tc_fwd", x0, C0, x1, C1, wp, wp.shape[1], row_off, bias, out, _dt(out), N, H, W,
+                                  Cout, KH, KW, stride, pad, Ho, Wo, out.stride(0), out.stride(1), out.stride(2), _S()))
+    return out
+
+
+def conv_tc_wgrad(x, dy, dw, cin_off, KH, KW, stride, pad):
+    _chk(x, dy, dw)
+    N, H, W, Cin = x.shape
+    _, Ho, Wo, Cout = dy.shape
+    fl = 2.0 * N * Ho * Wo * Cout * KH * KW * Cin
+    instrument.timed("conv_tc_wgrad (tcgen05)", fl, 2.0 * (x.numel() + dy.numel()),
+                     lambda: call("conv_tc_wgrad", x, Cin, cin_off, dw.shape[2], dy, Cout, dw, N, H, W, KH, KW, stride,
+                                  pad, Ho, Wo, _S()))
 
 
 def conv3x3_tc_wgrad(x, dy, dw, cin_off=0):
@@ -364,7 +410,7 @@ def conv3x3_tc_wgrad(x, dy, dw, cin_off=0):
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     fl = 2.0 * N * H * W * Cout * 9 * Cin
-    instrument.timed("conv3x3_tc_wgrad (tcgen05)", fl, 2.0 * (x.numel() + dy.numel()),
+    instrument.timed("conv_tc_wgrad (tcgen05)", fl, 2.0 * (x.numel() + dy.numel()),
                      lambda: call("conv3x3_tc_wgrad", x, Cin, cin_off, dw.shape[2], dy, Cout, dw, N, H, W, _S()))
 
 

@@ -29,8 +29,57 @@ class BNState(object):
         self.moving[(name, "moving_variance")] = mv
 
 
+# ---- optional emulation of the product's tensor-core operand precision ---------------------------------
+# The tcgen05 path multiplies bf16 operands (fp32 accumulate) and stores the feature maps that feed it as
+# bf16.  A deep random-init ReLU network amplifies ANY perturbation by ~1.3x per layer, so against the
+# plain fp32 oracle the 0.3 % bf16 operand noise grows to several % after 23 layers -- for every bf16
+# implementation.  With BF16_EMULATION the oracle rounds exactly the tensors the product rounds (operands
+# of the eligible 3x3 convolutions, the stored feature maps, the gradients that are kept in bf16), so the
+# comparison is again "same arithmetic up to accumulation order".
+BF16_EMULATION = False
+
+
+class _RoundBF16(torch.autograd.Function):
+    """forward: round to bf16; backward: the incoming gradient is rounded to bf16 as well (the product
+    keeps both the feature map and its gradient in bf16)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundGradBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def feat(x):
+    """a feature map that the product stores as bf16"""
+    return _RoundBF16.apply(x) if BF16_EMULATION else x
+
+
+def _tc_eligible(w, stride, padding):
+    """mirror of the product's eligibility rule (engine.Conv2D.tc_eligible)"""
+    if not (BF16_EMULATION and w.shape[0] > 1 and w.shape[2] % 64 == 0 and w.shape[3] % 64 == 0):
+        return False
+    return stride == 1 or (stride == 2 and w.shape[0] % 2 == 0 and padding == "valid")
+
+
 def conv(W, name, x, stride=1, padding="valid"):
-    return R.conv2d(x, W[name + "/kernel"], W.get(name + "/bias"), stride, padding)
+    w = W[name + "/kernel"]
+    if _tc_eligible(w, stride, padding):
+        y = R.conv2d(_RoundBF16.apply(x), _RoundBF16.apply(w), W.get(name + "/bias"), stride, padding)
+        return _RoundGradBF16.apply(y)      # the gradient w.r.t. the conv output is consumed as bf16
+    return R.conv2d(x, w, W.get(name + "/bias"), stride, padding)
 
 
 def bn(W, name, x, st):
@@ -43,15 +92,16 @@ def bn(W, name, x, st):
                              st.get(name, "moving_variance"))
 
 
-def conv_block(W, name, x, st):
+def conv_block(W, name, x, st, last_fp32=False):
     """models/unet.py:94-101"""
-    l = R.relu(bn(W, name + "_bn1", conv(W, name + "_conv1", x, 1, "same"), st))
-    return R.relu(bn(W, name + "_bn2", conv(W, name + "_conv2", l, 1, "same"), st))
+    l = feat(R.relu(bn(W, name + "_bn1", conv(W, name + "_conv1", x, 1, "same"), st)))
+    l = R.relu(bn(W, name + "_bn2", conv(W, name + "_conv2", l, 1, "same"), st))
+    return l if last_fp32 else feat(l)
 
 
 def upsample_block(W, name, x, st):
     """utils/model_utils.py:15-22 with activation='linear'"""
-    return bn(W, name + "_bn", conv(W, name + "_conv", R.upsample2(x), 1, "same"), st)
+    return feat(bn(W, name + "_bn", conv(W, name + "_conv", R.upsample2(x), 1, "same"), st))
 
 
 def anatomy_encoder(W, x, st, down_prefix, up_prefix, downsample=4, rounding=True):
@@ -67,14 +117,14 @@ def anatomy_encoder(W, x, st, down_prefix, up_prefix, downsample=4, rounding=Tru
     for i in reversed(range(downsample)):
         up = upsample_block(W, "%su%d_up" % (up_prefix, i), l, st)
         l = torch.cat([up, skips[i]], -1)              # Concatenate()([l, self.d_l3]) unet.py:68
-        l = conv_block(W, "%su%d" % (up_prefix, i), l, st)
+        l = conv_block(W, "%su%d" % (up_prefix, i), l, st, last_fp32=(i == 0))
     a = R.softmax(conv(W, "conv_anatomy", l, 1, "same"))
     return R.rounding(a) if rounding else a
 
 
 def segmentor(W, s, st):
     """model_components/segmentor.py:9-29"""
-    l = R.relu(bn(W, "seg_bn1", conv(W, "seg_conv1", s, 1, "same"), st))
+    l = feat(R.relu(bn(W, "seg_bn1", conv(W, "seg_conv1", s, 1, "same"), st)))
     l = R.relu(bn(W, "seg_bn2", conv(W, "seg_conv2", l, 1, "same"), st))
     return R.softmax(conv(W, "seg_out", l, 1, "same"))
 

@@ -108,3 +108,46 @@ def test_conv3x3_tc_vs_fp32_oracle_tolerance(ops):
     yr = R.conv2d(t(x), t(w), None, 1, "same").numpy()
     y = ops.conv3x3_tc_fwd(ops.cast(gpu(x), torch.bfloat16), None, ops.pack_conv3x3(gpu(w)), None, Cout)
     assert rel_l2(cpu(y), yr) < 1e-2
+
+
+# ------------------------------------------------------------------ general form: discriminator layers
+DISC_CASES = [
+    # N, H, W, Cin, Cout, k, stride     (models/discriminator.py:24,39 -- valid padding)
+    (2, 111, 111, 64, 128, 4, 2),
+    (2, 54, 54, 128, 256, 4, 2),
+    (2, 26, 26, 256, 512, 4, 1),
+    (3, 31, 29, 64, 64, 4, 2),      # odd sizes: uncovered last row / column in the data gradient
+    (2, 20, 22, 64, 128, 5, 1),     # another stride-1 valid shape
+]
+
+
+@pytest.mark.parametrize("case", DISC_CASES)
+def test_conv_tc_general_fwd_dgrad_wgrad(ops, case):
+    from multimodal_segmentation_b200 import engine as E
+    N, H, W, Cin, Cout, k, s = case
+    r = np.random.RandomState(sum(case))
+    x = bf16_round(r.normal(size=(N, H, W, Cin)).astype(np.float32))
+    w = bf16_round((r.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(np.float32))
+    b = r.normal(size=Cout).astype(np.float32)
+    xt, wt = t(x, torch.float64, grad=True), t(w, torch.float64, grad=True)
+    yr = R.conv2d(xt, wt, t(b, torch.float64), s, "valid")
+    dy = bf16_round(r.normal(size=tuple(yr.shape)).astype(np.float32))
+    (yr * t(dy, torch.float64)).sum().backward()
+    E.USE_TC = True
+    arena = E.Arena(True)
+    conv = E.Conv2D(arena, r, "c", Cin, Cout, k, s, "valid")
+    arena.to_device()
+    conv.kernel.data.copy_(gpu(w))
+    conv.bias.data.copy_(gpu(b))
+    tape = E.Tape()
+    ctx = E.Ctx(tape, True)
+    xv = E.Var(gpu(x, torch.bfloat16), True)
+    assert conv.tc_eligible([xv])
+    y = conv(ctx, xv)
+    assert tuple(y.shape) == tuple(yr.shape)
+    assert rel_l2(cpu(y.data), yr.detach().numpy()) < 1e-4
+    y.grad = gpu(dy, torch.bfloat16)
+    tape.backward()
+    assert rel_l2(cpu(xv.grad), xt.grad.numpy()) < 5e-3          # dx is stored as bf16
+    assert rel_l2(cpu(conv.kernel.grad), wt.grad.numpy()) < 1e-3
+    assert rel_l2(cpu(conv.bias.grad), dy.sum((0, 1, 2))) < 1e-3
