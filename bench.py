@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-tc", action="store_true")
+    ap.add_argument("--profile-all", action="store_true", help="CUDA-event time of every entry point (diagnostic)")
     return ap.parse_args()
 
 
@@ -166,6 +167,7 @@ def run_b200(args):
     from multimodal_segmentation_b200 import instrument
 
     E.USE_TC = not args.no_tc
+    _lib.PROFILE_ALL = args.profile_all
     conf = conf_for(args)
     conf.seed = 10 + rank                     # per-rank data / sampling seed; weights are broadcast from rank 0
     os.environ["DAFK_TRAIN_PAIRS"] = str(max(4 * args.batch, 64))

@@ -172,6 +172,17 @@ int dafk_conv2d_dgrad(const dafk_conv_desc* d, const float* dy, const float* w, 
 /* dw += x (*) dy  (accumulates: caller zeroes);  db += sum_pixels dy (db may be NULL) */
 int dafk_conv2d_wgrad(const dafk_conv_desc* d, const float* x, const float* dy, float* dw,
                       float* db, void* stream);
+/* direct kernels for the narrow layers (few input and/or output channels: FiLM decoder 8->8,
+ * first UNet/segmentor/discriminator layers, 1x1 heads, locnet 5x5, modality encoder); same
+ * semantics as dafk_conv2d_{fwd,dgrad,wgrad}.  dafk_conv_small_supported() tells whether the filter
+ * bank fits in shared memory; the strided data gradient additionally needs Cin <= 16. */
+int dafk_conv_small_supported(int Cin, int Cout, int KH, int KW);
+int dafk_conv_small_fwd(const dafk_conv_desc* d, const float* x, const float* w, const float* bias,
+                        float* y, int act, float alpha, void* stream);
+int dafk_conv_small_dgrad(const dafk_conv_desc* d, const float* dy, const float* w, float* dx,
+                          void* stream);
+int dafk_conv_small_wgrad(const dafk_conv_desc* d, const float* x, const float* dy, float* dw,
+                          float* db, void* stream);
 /* out[c] += sum_m x[m,c]   (bias gradients); x is f32 or bf16 */
 int dafk_colsum(const void* x, int x_dt, float* out, int64_t M, int C, void* stream);
 

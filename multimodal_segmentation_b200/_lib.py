@@ -103,11 +103,22 @@ def _ptr(x):
     return x
 
 
+PROFILE_ALL = False     # bench.py --profile-all: CUDA-event time of EVERY entry point (by name)
+
+
 def call(name, *args):
     """Call ``dafk_<name>``; tensors become device pointers; raises DafkError on a non-zero status."""
     L = lib()
     full = name if name.startswith("dafk_") else "dafk_" + name
     f = L.fn[full]
+    if PROFILE_ALL:
+        from . import instrument
+        if instrument.enabled:
+            ptrs = [_ptr(a) for a in args]
+            rc = instrument.timed("all:" + name, 0, 0, lambda: f(*ptrs))
+            if f.restype is ctypes.c_int and rc != 0:
+                raise DafkError("%s failed (%d): %s" % (full, rc, L.last_error()))
+            return rc
     rc = f(*[_ptr(a) for a in args])
     if f.restype is ctypes.c_int and rc != 0:
         raise DafkError("%s failed (%d): %s" % (full, rc, L.last_error()))

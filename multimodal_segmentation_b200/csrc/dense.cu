@@ -16,36 +16,69 @@ __global__ void dense_init_kernel(float* __restrict__ y, const float* __restrict
   if (i < B * N) y[i] = bias ? bias[i % N] : 0.f;
 }
 
-// grid = (ceil(K/KC), ceil(B/MAXB)); y must be pre-initialised with the bias
+// grid = (k-slabs, ceil(B/MAXB)); y must be pre-initialised with the bias.
+// Each CTA walks its k-slab in chunks of KC (x chunk staged in smem, W rows streamed coalesced),
+// keeps MAXB accumulators per thread in registers, then reduces across the threads that share an
+// output column (warp shuffles when the column count divides 32, shared-memory atomics otherwise)
+// and issues ONE global atomic per output per CTA.
 __global__ void __launch_bounds__(DT) dense_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                       float* __restrict__ y, int B, int64_t K, int N) {
+                                                       float* __restrict__ y, int B, int64_t K, int N,
+                                                       int64_t k_per_cta) {
   __shared__ float xs[MAXB][KC];
+  extern __shared__ float part[];   // [MAXB][ncols]
   const int b0 = blockIdx.y * MAXB;
   const int nb = min(MAXB, B - b0);
-  const int64_t k0 = (int64_t)blockIdx.x * KC;
-  const int kc = (int)min((int64_t)KC, K - k0);
-  for (int e = threadIdx.x; e < MAXB * KC; e += DT) {
-    int b = e / KC, k = e % KC;
-    xs[b][k] = (b < nb && k < kc) ? x[(int64_t)(b0 + b) * K + k0 + k] : 0.f;
-  }
-  __syncthreads();
-  // thread -> (n, k-group)
+  const int64_t kbeg = (int64_t)blockIdx.x * k_per_cta;
+  const int64_t kend = min(K, kbeg + k_per_cta);
   for (int nbase = 0; nbase < N; nbase += DT) {
-    int ncols = min(N - nbase, DT);
-    int groups = DT / ncols;
-    int n = threadIdx.x % ncols, g = threadIdx.x / ncols;
-    if (g >= groups) continue;
+    const int ncols = min(N - nbase, DT);
+    const int groups = DT / ncols;
+    const int n = threadIdx.x % ncols, g = threadIdx.x / ncols;
+    const bool active = g < groups;
     float acc[MAXB];
 #pragma unroll
     for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
-    for (int k = g; k < kc; k += groups) {
-      float wv = __ldg(w + (k0 + k) * N + nbase + n);
+    for (int64_t k0 = kbeg; k0 < kend; k0 += KC) {
+      const int kc = (int)min((int64_t)KC, kend - k0);
+      __syncthreads();
+      for (int e = threadIdx.x; e < MAXB * KC; e += DT) {
+        int b = e / KC, k = e % KC;
+        xs[b][k] = (b < nb && k < kc) ? x[(int64_t)(b0 + b) * K + k0 + k] : 0.f;
+      }
+      __syncthreads();
+      if (active) {
+        for (int k = g; k < kc; k += groups) {
+          float wv = __ldg(w + (k0 + k) * N + nbase + n);
 #pragma unroll
-      for (int b = 0; b < MAXB; ++b) acc[b] = fmaf(xs[b][k], wv, acc[b]);
+          for (int b = 0; b < MAXB; ++b) acc[b] = fmaf(xs[b][k], wv, acc[b]);
+        }
+      }
     }
+    // reduce over the k-groups
+    for (int e = threadIdx.x; e < MAXB * ncols; e += DT) part[e] = 0.f;
+    __syncthreads();
+    const bool shuffle_ok = ncols < 32 && (32 % ncols) == 0;
+    if (shuffle_ok) {
 #pragma unroll
-    for (int b = 0; b < MAXB; ++b)
-      if (b < nb) atomicAdd(y + (int64_t)(b0 + b) * N + nbase + n, acc[b]);
+      for (int b = 0; b < MAXB; ++b) {
+        float v = active ? acc[b] : 0.f;
+        for (int o = 16; o >= ncols; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[b] = v;
+      }
+      if ((threadIdx.x & 31) < ncols && active) {
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) atomicAdd(&part[b * ncols + n], acc[b]);
+      }
+    } else if (active) {
+#pragma unroll
+      for (int b = 0; b < MAXB; ++b) atomicAdd(&part[b * ncols + n], acc[b]);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nb * ncols; e += DT) {
+      int b = e / ncols, c = e % ncols;
+      atomicAdd(y + (int64_t)(b0 + b) * N + nbase + c, part[e]);
+    }
+    __syncthreads();
   }
 }
 
@@ -116,8 +149,13 @@ int dafk_dense_fwd(const float* x, const float* w, const float* bias, float* y, 
   dense_init_kernel<<<(B * Nout + 255) / 256, 256, 0, s>>>(y, bias, B, Nout);
   int rc = check_launch("dafk_dense_fwd(init)");
   if (rc) return rc;
-  dim3 grid((unsigned)((K + KC - 1) / KC), (B + MAXB - 1) / MAXB);
-  dense_fwd_kernel<<<grid, DT, 0, s>>>(x, w, y, B, K, Nout);
+  // k-slabs: about two CTAs per SM, each slab a multiple of the chunk size
+  int64_t slabs = (K + KC - 1) / KC;
+  int64_t want = 2 * kNumSMs;
+  int64_t k_per_cta = ((slabs + want - 1) / want) * KC;
+  dim3 grid((unsigned)((K + k_per_cta - 1) / k_per_cta), (B + MAXB - 1) / MAXB);
+  size_t smem = sizeof(float) * MAXB * (Nout < DT ? Nout : DT);
+  dense_fwd_kernel<<<grid, DT, smem, s>>>(x, w, y, B, K, Nout, k_per_cta);
   return check_launch("dafk_dense_fwd");
 }
 

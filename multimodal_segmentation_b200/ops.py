@@ -292,6 +292,14 @@ def conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad):
     return ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo)
 
 
+USE_SMALL = True     # direct kernels for narrow layers (tests switch it off to exercise the general path)
+
+
+def _small(Cin, Cout, KH, KW):
+    return (USE_SMALL and (Cin <= 32 or Cout <= 32)
+            and bool(_lib.lib().fn["dafk_conv_small_supported"](Cin, Cout, KH, KW)))
+
+
 def conv2d_fwd(x, w, bias, stride=1, pad=0, act=ACT_NONE, alpha=0.0):
     _chk(x, w, bias)
     N, H, W, Cin = x.shape
@@ -299,6 +307,10 @@ def conv2d_fwd(x, w, bias, stride=1, pad=0, act=ACT_NONE, alpha=0.0):
     d = conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad)
     y = f32(N, d.Ho, d.Wo, Cout)
     fl = 2.0 * N * d.Ho * d.Wo * Cout * KH * KW * Cin
+    if _small(Cin, Cout, KH, KW):
+        instrument.timed("conv_small_fwd", fl, 4.0 * (x.numel() + y.numel()),
+                         lambda: call("conv_small_fwd", d, x, w, bias, y, act, float(alpha), _S()))
+        return y
     instrument.timed("conv2d_generic_fwd", fl, 4.0 * (x.numel() + y.numel()),
                      lambda: call("conv2d_fwd", d, x, w, bias, y, act, float(alpha), _S()))
     return y
@@ -311,6 +323,10 @@ def conv2d_dgrad(dy, w, x_shape, stride=1, pad=0):
     d = conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad)
     dx = f32(N, H, W, Cin)
     fl = 2.0 * N * d.Ho * d.Wo * Cout * KH * KW * Cin
+    if _small(Cin, Cout, KH, KW) and (stride == 1 or Cin <= 16):
+        instrument.timed("conv_small_dgrad", fl, 4.0 * (dy.numel() + dx.numel()),
+                         lambda: call("conv_small_dgrad", d, dy, w, dx, _S()))
+        return dx
     instrument.timed("conv2d_generic_dgrad", fl, 4.0 * (dy.numel() + dx.numel()),
                      lambda: call("conv2d_dgrad", d, dy, w, dx, _S()))
     return dx
@@ -323,6 +339,10 @@ def conv2d_wgrad(x, dy, dw, db, stride=1, pad=0):
     KH, KW, _, Cout = dw.shape
     d = conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad)
     fl = 2.0 * N * d.Ho * d.Wo * Cout * KH * KW * Cin
+    if _small(Cin, Cout, KH, KW):
+        instrument.timed("conv_small_wgrad", fl, 4.0 * (x.numel() + dy.numel()),
+                         lambda: call("conv_small_wgrad", d, x, dy, dw, db, _S()))
+        return
     instrument.timed("conv2d_generic_wgrad", fl, 4.0 * (x.numel() + dy.numel()),
                      lambda: call("conv2d_wgrad", d, x, dy, dw, db, _S()))
 

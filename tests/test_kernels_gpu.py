@@ -231,11 +231,19 @@ CONV_CASES = [
     (1, 13, 11, 64, 128, 4, 2, 0),   # discriminator block
     (1, 9, 9, 32, 48, 4, 1, 0),      # discriminator last block (stride 1)
     (2, 8, 8, 64, 64, 3, 1, 1),      # wide 3x3 (also served by the tcgen05 path)
+    (2, 30, 26, 20, 20, 5, 1, 0),    # locnet conv2/3
+    (2, 21, 19, 16, 32, 3, 2, 0),    # modality encoder conv2
+    (2, 15, 13, 32, 64, 3, 2, 0),    # modality encoder conv3
+    (3, 18, 16, 1, 64, 4, 2, 0),     # image discriminator first layer
+    (2, 12, 10, 16, 1, 1, 1, 0),     # SPADE decoder head
 ]
 
 
+@pytest.mark.parametrize("small", [True, False])
 @pytest.mark.parametrize("case", CONV_CASES)
-def test_conv_generic(ops, case):
+def test_conv_generic(ops, case, small):
+    """small=True: the direct narrow-layer kernels where they apply; False: the general tiled path"""
+    ops.USE_SMALL = small
     N, H, W, Cin, Cout, k, s, p = case
     r = rng(sum(case))
     x = r.normal(size=(N, H, W, Cin)).astype(np.float32)
@@ -256,6 +264,7 @@ def test_conv_generic(ops, case):
     ops.conv2d_wgrad(gpu(x), gpu(g), dw, db, s, p)
     assert rel_l2(cpu(dw), wt.grad.numpy()) < FP32_TOL
     assert rel_l2(cpu(db), bt.grad.numpy()) < FP32_TOL
+    ops.USE_SMALL = True
 
 
 def test_conv_fused_activation(ops):
