@@ -167,62 +167,97 @@ __global__ void __launch_bounds__(ST) conv_small_dgrad_strided_kernel(SmallP p, 
     if (j < p.Cin) dx[m * p.Cin + j] = acc[j];
 }
 
-// weight gradient: thread = (tap, ci) row of dw; COUT_T accumulators; grid = (pixel slabs, co groups)
-template <int COUT_T>
+// weight gradient.  blockDim = (32 pixel lanes, TY tap slots); grid = (pixel slabs, ci groups, co groups).
+// A thread owns one filter tap and a CIN_T x COUT_T block of dw in registers and strides over the pixels
+// of its slab: per pixel it issues CIN_T/4 + COUT_T/4 128-bit loads (coalesced across the 32 lanes, which
+// are consecutive pixels) for CIN_T*COUT_T FMAs.  The lanes are reduced with warp shuffles and one lane
+// issues the atomics.  Tap slot 0 of ci-group 0 also reduces the bias gradient.
+template <int CIN_T, int COUT_T>
 __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(SmallP p, const float* __restrict__ x,
                                                                const float* __restrict__ dy, float* __restrict__ dw,
                                                                float* __restrict__ db, int64_t pix_per_cta) {
-  const int rows = p.KH * p.KW * p.Cin;
-  const int co0 = blockIdx.y * COUT_T;
+  const int taps = p.KH * p.KW;
+  const int ci0 = blockIdx.y * CIN_T, co0 = blockIdx.z * COUT_T;
+  const int lane = threadIdx.x;
   const int64_t P = (int64_t)p.N * p.Ho * p.Wo;
   const int64_t pbeg = (int64_t)blockIdx.x * pix_per_cta;
   const int64_t pend = min(P, pbeg + pix_per_cta);
-  const bool vec = (p.Cout & 3) == 0 && (COUT_T & 3) == 0 && co0 + COUT_T <= p.Cout;
-  for (int row = threadIdx.x; row < rows + 1; row += blockDim.x) {
-    // the extra row (row == rows) accumulates the bias gradient
-    const bool is_bias = row == rows;
-    if (is_bias && db == nullptr) continue;
-    const int ci = is_bias ? 0 : row % p.Cin;
-    const int tap = is_bias ? 0 : row / p.Cin;
+  const bool xvec = (CIN_T & 3) == 0 && (p.Cin & 3) == 0 && ci0 + CIN_T <= p.Cin;
+  const bool gvec = (COUT_T & 3) == 0 && (p.Cout & 3) == 0 && co0 + COUT_T <= p.Cout;
+  const bool do_bias = db != nullptr && blockIdx.y == 0;
+  for (int tap = threadIdx.y; tap < taps; tap += blockDim.y) {
     const int r = tap / p.KW, q = tap % p.KW;
-    float acc[COUT_T];
+    float acc[CIN_T][COUT_T];
+    float bacc[COUT_T];
 #pragma unroll
-    for (int j = 0; j < COUT_T; ++j) acc[j] = 0.f;
-    // walk the slab image-row by image-row to avoid a div/mod per pixel
-    int64_t pix = pbeg;
-    int wo = (int)(pix % p.Wo);
-    int64_t t = pix / p.Wo;
-    int ho = (int)(t % p.Ho);
-    int n = (int)(t / p.Ho);
-    for (; pix < pend; ++pix) {
-      float xv = 1.f;
-      bool ok = true;
-      if (!is_bias) {
-        const int hi = ho * p.stride - p.pad + r, wi = wo * p.stride - p.pad + q;
-        ok = hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
-        if (ok) xv = __ldg(x + (((int64_t)n * p.H + hi) * p.W + wi) * p.Cin + ci);
-      }
-      if (ok) {
-        const float* pg = dy + pix * p.Cout + co0;
-        if (vec) {
+    for (int i = 0; i < CIN_T; ++i)
 #pragma unroll
-          for (int j = 0; j < COUT_T; j += 4) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(pg + j));
-            acc[j] = fmaf(xv, g.x, acc[j]); acc[j + 1] = fmaf(xv, g.y, acc[j + 1]);
-            acc[j + 2] = fmaf(xv, g.z, acc[j + 2]); acc[j + 3] = fmaf(xv, g.w, acc[j + 3]);
-          }
-        } else {
+      for (int j = 0; j < COUT_T; ++j) acc[i][j] = 0.f;
 #pragma unroll
-          for (int j = 0; j < COUT_T; ++j)
-            if (co0 + j < p.Cout) acc[j] = fmaf(xv, __ldg(pg + j), acc[j]);
+    for (int j = 0; j < COUT_T; ++j) bacc[j] = 0.f;
+    for (int64_t pix = pbeg + lane; pix < pend; pix += 32) {
+      const int wo = (int)(pix % p.Wo);
+      const int64_t t = pix / p.Wo;
+      const int ho = (int)(t % p.Ho);
+      const int n = (int)(t / p.Ho);
+      float g[COUT_T];
+      const float* pg = dy + pix * p.Cout + co0;
+      if (gvec) {
+#pragma unroll
+        for (int j = 0; j < COUT_T; j += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(pg + j));
+          g[j] = v.x; g[j + 1] = v.y; g[j + 2] = v.z; g[j + 3] = v.w;
         }
-      }
-      if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++n; } }
-    }
-    float* out = is_bias ? db + co0 : dw + (int64_t)row * p.Cout + co0;
+      } else {
 #pragma unroll
-    for (int j = 0; j < COUT_T; ++j)
-      if (co0 + j < p.Cout) atomicAdd(out + j, acc[j]);
+        for (int j = 0; j < COUT_T; ++j) g[j] = (co0 + j < p.Cout) ? __ldg(pg + j) : 0.f;
+      }
+      if (do_bias && tap == 0) {
+#pragma unroll
+        for (int j = 0; j < COUT_T; ++j) bacc[j] += g[j];
+      }
+      const int hi = ho * p.stride - p.pad + r, wi = wo * p.stride - p.pad + q;
+      if (hi < 0 || hi >= p.H || wi < 0 || wi >= p.W) continue;
+      const float* px = x + (((int64_t)n * p.H + hi) * p.W + wi) * p.Cin + ci0;
+      float xv[CIN_T];
+      if (xvec) {
+#pragma unroll
+        for (int i = 0; i < CIN_T; i += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(px + i));
+          xv[i] = v.x; xv[i + 1] = v.y; xv[i + 2] = v.z; xv[i + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CIN_T; ++i) xv[i] = (ci0 + i < p.Cin) ? __ldg(px + i) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < CIN_T; ++i)
+#pragma unroll
+        for (int j = 0; j < COUT_T; ++j) acc[i][j] = fmaf(xv[i], g[j], acc[i][j]);
+    }
+    // reduce the 32 pixel lanes
+#pragma unroll
+    for (int i = 0; i < CIN_T; ++i)
+#pragma unroll
+      for (int j = 0; j < COUT_T; ++j) acc[i][j] = warp_sum(acc[i][j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < CIN_T; ++i) {
+        if (ci0 + i >= p.Cin) continue;
+#pragma unroll
+        for (int j = 0; j < COUT_T; ++j)
+          if (co0 + j < p.Cout) atomicAdd(dw + ((int64_t)tap * p.Cin + ci0 + i) * p.Cout + co0 + j, acc[i][j]);
+      }
+    }
+    if (do_bias && tap == 0) {
+#pragma unroll
+      for (int j = 0; j < COUT_T; ++j) bacc[j] = warp_sum(bacc[j]);
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < COUT_T; ++j)
+          if (co0 + j < p.Cout) atomicAdd(db + co0 + j, bacc[j]);
+      }
+    }
   }
 }
 
@@ -329,25 +364,30 @@ int dafk_conv_small_wgrad(const dafk_conv_desc* d, const float* x, const float* 
   DAFK_REQUIRE(x && dy && dw, DAFK_ERR_BAD_ARG, "dafk_conv_small_wgrad: null pointer");
   DAFK_REQUIRE(DAFK_ALIGNED16(dy), DAFK_ERR_ALIGN, "dafk_conv_small_wgrad: alignment");
   cudaStream_t s = as_stream(stream);
-  const int rows = p.KH * p.KW * p.Cin + 1;
-  int threads = ((rows + 31) / 32) * 32;
-  if (threads > 512) threads = 512;
+  const int taps = p.KH * p.KW;
+  const int ty = taps < 16 ? taps : 16;
   const int64_t P = (int64_t)p.N * p.Ho * p.Wo;
-#define LAUNCH_WG(T)                                                                             \
-  do {                                                                                           \
-    int groups = (p.Cout + T - 1) / T;                                                           \
-    int64_t ctas = ((int64_t)kNumSMs * 8 + groups - 1) / groups;                                  \
-    int64_t per = (P + ctas - 1) / ctas;                                                         \
-    if (per < 64) per = 64;                                                                      \
-    int slabs = (int)((P + per - 1) / per);                                                      \
-    conv_small_wgrad_kernel<T><<<dim3(slabs, groups), threads, 0, s>>>(p, x, dy, dw, db, per);   \
+#define LAUNCH_WG(CI, CO)                                                                                \
+  do {                                                                                                   \
+    int gi = (p.Cin + CI - 1) / CI, go = (p.Cout + CO - 1) / CO;                                          \
+    int64_t ctas = ((int64_t)kNumSMs * 4 + gi * go - 1) / (gi * go);                                      \
+    int64_t per = (P + ctas - 1) / ctas;                                                                 \
+    if (per < 256) per = 256;                                                                            \
+    int slabs = (int)((P + per - 1) / per);                                                              \
+    conv_small_wgrad_kernel<CI, CO><<<dim3(slabs, gi, go), dim3(32, ty), 0, s>>>(p, x, dy, dw, db, per);   \
   } while (0)
-  if (p.Cout == 1) LAUNCH_WG(1);
-  else if (p.Cout <= 4) LAUNCH_WG(4);
-  else if (p.Cout == 5) LAUNCH_WG(5);
-  else if (p.Cout <= 8) LAUNCH_WG(8);
-  else if (p.Cout == 20) LAUNCH_WG(20);
-  else LAUNCH_WG(16);
+  // register block CIN_T x COUT_T <= 64 accumulators
+  const int ci = p.Cin, co = p.Cout;
+  if (ci == 1) {
+    if (co >= 16) LAUNCH_WG(1, 16); else if (co >= 8) LAUNCH_WG(1, 8); else if (co >= 4) LAUNCH_WG(1, 4); else LAUNCH_WG(1, 1);
+  } else if (ci <= 4 || (ci & 3) != 0) {
+    // narrow or unaligned input rows (4, 5, 9 channels): 4-wide ci blocks with masking / scalar loads
+    if (co >= 16) LAUNCH_WG(4, 16); else if (co >= 8) LAUNCH_WG(4, 8); else if (co >= 4) LAUNCH_WG(4, 4); else LAUNCH_WG(4, 1);
+  } else {
+    if (co >= 8 && (co & 7) == 0) LAUNCH_WG(8, 8);
+    else if (co >= 4) LAUNCH_WG(8, 4);
+    else LAUNCH_WG(8, 1);
+  }
 #undef LAUNCH_WG
   return check_launch("dafk_conv_small_wgrad");
 }
