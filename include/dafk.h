@@ -183,6 +183,27 @@ int dafk_conv_small_dgrad(const dafk_conv_desc* d, const float* dy, const float*
                           void* stream);
 int dafk_conv_small_wgrad(const dafk_conv_desc* d, const float* x, const float* dy, float* dw,
                           float* db, void* stream);
+/* Narrow-channel convolutions on tcgen05 (csrc/conv_nc.cu): stride 1, any KH x KW (KW <= 8 for the weight
+ * gradient), few input channels (FiLM decoder 8->8 model_components/decoder.py:44-54, segmentor / UNet /
+ * discriminator first layers, locnet 5x5 layers/stn_spline.py:106-112).  x is f32 or bf16 NHWC and is
+ * converted to bf16 while it is staged; accumulation is fp32 in tensor memory.
+ * kind: 0 forward, 1 data gradient, 2 weight gradient.  Returns 1 if the geometry fits in shared memory. */
+int dafk_conv_nc_supported(int Cin, int Cout, int KH, int KW, int W, int pad, int kind);
+/* number of bf16 elements of the packed weight buffer for a kernel that reduces over Cin_k channels
+ * and produces Cout_k channels */
+int64_t dafk_conv_nc_packed_elems(int Cin_k, int Cout_k, int KH, int KW);
+/* HWIO f32 -> packed bf16.  mode 0: forward operand.  mode 1: operand of the stride-1 data gradient
+ * (taps mirrored, channels transposed): run dafk_conv_nc_fwd on dy with Cin=Cout_layer, Cout=Cin_layer,
+ * pad = K-1-pad_layer. */
+int dafk_pack_conv_nc(const float* w_hwio, void* wp, int KH, int KW, int Cin, int Cout, int mode,
+                      void* stream);
+/* y[N,Ho,Wo,Cout] = act(conv(x, w) + bias), Ho = H + 2*pad - KH + 1; y is f32 or bf16 */
+int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias, void* y, int y_dt, int N,
+                     int H, int W, int Cin, int Cout, int KH, int KW, int pad, int act, float alpha,
+                     void* stream);
+/* dw[KH,KW,Cin,Cout] (HWIO f32) += x (*) dy ; db[Cout] += sum_pixels dy (db may be NULL) */
+int dafk_conv_nc_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float* dw, float* db, int N,
+                       int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream);
 /* out[c] += sum_m x[m,c]   (bias gradients); x is f32 or bf16 */
 int dafk_colsum(const void* x, int x_dt, float* out, int64_t M, int C, void* stream);
 

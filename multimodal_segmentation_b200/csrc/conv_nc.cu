@@ -1,0 +1,724 @@
+// Narrow-channel convolutions on tcgen05 ("raster-strip implicit GEMM") for sm_100a.
+//
+// The FiLM decoder's 8->8 3x3 stack (model_components/decoder.py:44-54), the first layers of the segmentor,
+// UNet and discriminators (8->64, 1->64), and the locnet's 5x5 layers (layers/stn_spline.py:106-112) have so
+// few input channels that one pixel is only 16..48 bytes of bf16.  A 128B-swizzled TMA box would be mostly
+// padding, and CUDA-core direct convolution is FMA/LDS-bound at ~5% of the machine.  Here the tensor cores
+// are fed from an UN-SWIZZLED raster copy of the input strip instead:
+//
+//   * a CTA stages R + KH - 1 input rows of one image into shared memory as channel-group planes
+//     [cg][row * P + col][8 ch bf16 = 16 B], P = W + 2*pad (the zero halo columns are part of the raster);
+//     any dtype conversion (fp32 -> bf16) happens in this staging step, each input byte is read once;
+//   * the GEMM M index is the raster position itself: rows of the A operand for filter tap (r,q) are the
+//     raster shifted by (r*P + q) positions, i.e. the SAME shared memory with a different descriptor start
+//     address -- im2col is never materialised.  8 consecutive positions x 16 B form exactly one un-swizzled
+//     UMMA core matrix, so one tcgen05.mma (K = 16) consumes two (tap, channel-group) slices at once, the
+//     K-half stride (descriptor LBO) being the byte distance between the two slices;
+//   * outputs that fall on halo columns are computed and discarded (2/P of the tile).
+//
+//   forward / stride-1 data gradient:  D[pos, co] = sum_e A_e[pos, 0:8] . Wp[e][co][0:8]      (M=128, N=Cout)
+//   weight gradient:  dW[r][q][ci][co] = sum_pos X[pos + r*P + q][ci] . dY[pos][co]; X is the MN-major A
+//       operand whose 8 "M groups" are the taps q = 0..7 of one filter row (group stride = 16 B = one
+//       position), dY the MN-major B operand, K = positions; accumulated in TMEM over all strips of a CTA.
+#include "tc_ptx.cuh"
+
+namespace dafk {
+
+
+struct NcFwdP {
+  int N, H, W, Cin, Cout;
+  int KH, KW, pad, Ho, Wo;
+  int P, R, RS, CG, E, Npad, T, G;   // pitch, rows/strip, input rows/strip, channel groups, K entries (even),
+                                     // padded Cout, 128-position tiles per strip, tiles per TMEM group
+  int plane;                         // positions per channel-group plane
+  int S;                             // raster stages in the producer -> MMA ring
+  int strips_per_img, total_strips;
+  int x_dt, y_dt, act;
+  float alpha;
+  int dbg;
+};
+
+struct NcWgP {
+  int N, H, W, Cin, Cout;
+  int KH, KW, pad, Ho, Wo;
+  int P, R, RS, CG, COG, N8;         // N8 = Cout rounded up to 8 (UMMA N)
+  int planeX, planeY, chunks;        // positions per plane; K chunks of 16 positions per strip
+  int S;                             // stages in the producer -> MMA ring
+  int strips_per_img, total_strips;
+  int x_dt, dy_dt;
+  int tmem_cols;
+};
+
+// load 8 consecutive channels starting at p (nvalid of them exist) as floats
+template <typename T>
+__device__ __forceinline__ void nc_load8(const T* __restrict__ p, int nvalid, bool vec, float (&v)[8]);
+
+template <>
+__device__ __forceinline__ void nc_load8<float>(const float* __restrict__ p, int nvalid, bool vec, float (&v)[8]) {
+  if (vec) {   // channel count multiple of 4 and base 16B aligned
+    if (nvalid >= 4) {
+      float4 a = __ldg(reinterpret_cast<const float4*>(p));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    } else { v[0] = v[1] = v[2] = v[3] = 0.f; }
+    if (nvalid >= 8) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+      v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else { v[4] = v[5] = v[6] = v[7] = 0.f; }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = c < nvalid ? __ldg(p + c) : 0.f;
+  }
+}
+template <>
+__device__ __forceinline__ void nc_load8<__nv_bfloat16>(const __nv_bfloat16* __restrict__ p, int nvalid, bool vec,
+                                                         float (&v)[8]) {
+  if (vec && nvalid >= 8) {   // channel count multiple of 8
+    uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      v[2 * i] = __low2float(h);
+      v[2 * i + 1] = __high2float(h);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = c < nvalid ? __bfloat162float(p[c]) : 0.f;
+  }
+}
+
+__device__ __forceinline__ uint4 nc_pack8(const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ float nc_act(float z, int act, float alpha) {
+  if (act == DAFK_ACT_RELU) return z > 0.f ? z : 0.f;
+  if (act == DAFK_ACT_LRELU) return z > 0.f ? z : alpha * z;
+  if (act == DAFK_ACT_TANH) return tanhf(z);
+  return z;
+}
+
+constexpr int NC_PROD = 128;     // producer threads (warps 0..3)
+constexpr int NC_U = 8;          // image rows in flight per producer thread
+
+// Stage `rows` image rows [iy0, iy0+rows) of image n into the raster planes.  Unit of work = (pixel, channel
+// group): 8 channels = 16..32 contiguous bytes in global memory, one 16 B shared-memory store.  Within a row
+// consecutive producer threads take consecutive (pixel, group) units = consecutive global addresses; NC_U rows
+// are fetched before the first one is converted, so each thread keeps NC_U independent loads in flight.
+// `col0` is the raster column of image column 0 (= pad for inputs, 0 for output gradients).  With BSUM the
+// per-thread channel sums are accumulated (bias gradient): every thread then stays on ONE channel group,
+// which needs the thread count to be a multiple of `groups` (nthr = (NC_PROD / groups) * groups).
+template <typename T, bool BSUM>
+__device__ __forceinline__ void nc_stage_rows(const T* __restrict__ src, uint8_t* planes, int plane_pos, int n, int Himg,
+                                              int wcols, int C, int groups, int iy0, int rows, int P, int col0, int ptid,
+                                              int nthr, float (&bsum)[8]) {
+  if (ptid >= nthr) return;
+  const bool vec = (sizeof(T) == 4) ? ((C & 3) == 0) : ((C & 7) == 0);
+  const int units_row = wcols * groups;
+  const int gshift = (groups & (groups - 1)) == 0 ? 31 - __clz(groups) : -1;
+  const T* img = src + (int64_t)n * Himg * wcols * C;
+  for (int r0 = 0; r0 < rows; r0 += NC_U) {
+    for (int u = ptid; u < units_row; u += nthr) {
+      int cg, px;
+      if (gshift >= 0) { cg = u & (groups - 1); px = u >> gshift; }
+      else { px = u / groups; cg = u - px * groups; }
+      const int nvalid = min(8, C - cg * 8);
+      const T* p0 = img + (int64_t)px * C + cg * 8;
+      float v[NC_U][8];
+#pragma unroll
+      for (int k = 0; k < NC_U; ++k) {
+        const int iy = iy0 + r0 + k;
+        if (r0 + k < rows && iy >= 0 && iy < Himg) {
+          nc_load8<T>(p0 + (int64_t)iy * wcols * C, nvalid, vec, v[k]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[k][c] = 0.f;
+        }
+      }
+      uint8_t* dst = planes + ((size_t)cg * plane_pos + (size_t)r0 * P + col0 + px) * 16;
+#pragma unroll
+      for (int k = 0; k < NC_U; ++k) {
+        if (r0 + k < rows) {
+          *reinterpret_cast<uint4*>(dst + (size_t)k * P * 16) = nc_pack8(v[k]);
+          if (BSUM) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) bsum[c] += v[k][c];
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward / stride-1 data gradient.  Warp-specialised persistent CTA (one per SM):
+//   warps 0-3  producers : global -> bf16 raster planes of stage s           (full[s] / empty[s] ring)
+//   warp  4    MMA issuer: per 128-position tile E/2 tcgen05.mma into one of two TMEM buffers
+//   warps 5-8  epilogue  : TMEM -> registers -> bias/activation -> global    (tfull[b] / tempty[b])
+// smem: [wp: E*Npad*16][S stages x CG*plane*16][descA: E/2 u64][descB: E/2 u64][bias: Npad f32][barriers]
+// ---------------------------------------------------------------------------------------------
+constexpr int NC_FWD_THREADS = 288;
+constexpr int NC_MAX_STAGES = 4;
+
+template <typename TX>
+__global__ void __launch_bounds__(NC_FWD_THREADS, 1) conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x,
+                                                                        const __nv_bfloat16* __restrict__ wp,
+                                                                        const float* __restrict__ bias,
+                                                                        void* __restrict__ y) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int w_bytes = p.E * p.Npad * 16;
+  const int st_bytes = p.CG * p.plane * 16;
+  uint8_t* s_w = smem;
+  uint8_t* s_x = smem + w_bytes;
+  uint64_t* s_descA = reinterpret_cast<uint64_t*>(s_x + (size_t)p.S * st_bytes);
+  uint64_t* s_descB = s_descA + p.E / 2;
+  float* s_bias = reinterpret_cast<float*>(s_descB + p.E / 2);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + p.Npad);
+  uint64_t* empty = full + NC_MAX_STAGES;
+  uint64_t* tfull = empty + NC_MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // one-time setup: weights, bias, zeroed rasters (halo columns and slack stay zero for the CTA's lifetime)
+  for (int i = tid; i < w_bytes / 16; i += NC_FWD_THREADS)
+    reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(wp) + i);
+  for (int i = tid; i < p.S * st_bytes / 16; i += NC_FWD_THREADS) reinterpret_cast<uint4*>(s_x)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < p.Npad; i += NC_FWD_THREADS) s_bias[i] = (bias != nullptr && i < p.Cout) ? bias[i] : 0.f;
+  const int Ereal = p.CG * p.KH * p.KW;
+  for (int j = tid; j < p.E / 2; j += NC_FWD_THREADS) {
+    auto off = [&](int e) {
+      int q = e % p.KW;
+      int t = e / p.KW;
+      int r = t % p.KH;
+      int cg = t / p.KH;
+      return (uint32_t)((cg * p.plane + r * p.P + q) * 16);
+    };
+    const uint32_t o0 = off(2 * j);
+    const uint32_t lbo = (2 * j + 1 < Ereal) ? off(2 * j + 1) - o0 : 16u;
+    // K-major, un-swizzled: LBO = distance between the two K halves (the two (tap, group) slices),
+    // SBO = distance between 8-row groups (8 raster positions / 8 output channels = 128 B)
+    s_descA[j] = make_smem_desc_ns(smem_u32(s_x) + o0, lbo, 128);
+    s_descB[j] = make_smem_desc_ns(smem_u32(s_w) + (uint32_t)(2 * j * p.Npad * 16), (uint32_t)p.Npad * 16, 128);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < p.S; ++i) { mbar_init(full + i, NC_PROD); mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 128); }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    float dummy[8];
+    int it = 0;
+    for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x, ++it) {
+      const int st = it % p.S;
+      const uint32_t ph = (uint32_t)(it / p.S) & 1u;
+      const int n = s / p.strips_per_img;
+      const int y0 = (s - n * p.strips_per_img) * p.R;
+      mbar_wait(empty + st, ph ^ 1u);
+      if (!(p.dbg & 4))
+      nc_stage_rows<TX, false>(x, s_x + (size_t)st * st_bytes, p.plane, n, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P,
+                               p.pad, tid, NC_PROD, dummy);
+      fence_proxy_async();
+      mbar_arrive(full + st);
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, p.Npad, 0, 0);
+      const int nj = (p.dbg & 1) ? 1 : p.E / 2;
+      int it = 0, gc = 0;
+      for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x, ++it) {
+        const int st = it % p.S;
+        const uint32_t ph = (uint32_t)(it / p.S) & 1u;
+        const int n = s / p.strips_per_img;
+        const int y0 = (s - n * p.strips_per_img) * p.R;
+        const int rows_here = min(p.R, p.Ho - y0);
+        const int tiles_here = (rows_here * p.P + 127) / 128;
+        mbar_wait(full + st, ph);
+        tc_fence_after();
+        const uint64_t st_off = (uint64_t)((uint32_t)(st * st_bytes) >> 4);
+        for (int t0 = 0; t0 < tiles_here; t0 += p.G, ++gc) {
+          const int b = gc & 1;
+          mbar_wait(tempty + b, ((uint32_t)(gc >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const int gt = min(p.G, tiles_here - t0);
+          for (int tt = 0; tt < gt; ++tt) {
+            const uint64_t a_off = st_off + (uint64_t)((t0 + tt) * 128);   // 128 positions x 16 B, in 16 B units
+            const uint32_t d_col = tmem_base + (uint32_t)(b * 256 + tt * p.Npad);
+            for (int j = 0; j < nj; ++j) umma_bf16(d_col, s_descA[j] + a_off, s_descB[j], idesc, j > 0 ? 1u : 0u);
+          }
+          umma_commit(tfull + b);
+        }
+        umma_commit(empty + st);   // the raster of this stage has been consumed once these MMAs retire
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q4 = warp & 3;
+    const uint32_t magicP = (uint32_t)((0x100000000ULL + (uint64_t)p.P - 1) / (uint64_t)p.P);
+    int gc = 0;
+    for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x) {
+      const int n = s / p.strips_per_img;
+      const int y0 = (s - n * p.strips_per_img) * p.R;
+      const int rows_here = min(p.R, p.Ho - y0);
+      const int tiles_here = (rows_here * p.P + 127) / 128;
+      for (int t0 = 0; t0 < tiles_here; t0 += p.G, ++gc) {
+        const int b = gc & 1;
+        mbar_wait(tfull + b, (uint32_t)(gc >> 1) & 1u);
+        tc_fence_after();
+        const int gt = min(p.G, tiles_here - t0);
+        for (int tt = 0; tt < gt; ++tt) {
+          const int m = (t0 + tt) * 128 + q4 * 32 + lane;
+          const int orow = (int)__umulhi((uint32_t)m, magicP);
+          const int ocol = m - orow * p.P;
+          const bool live = orow < rows_here && ocol < p.Wo;
+          const int64_t obase = (((int64_t)n * p.Ho + y0 + orow) * p.Wo + ocol) * p.Cout;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * 256 + tt * p.Npad);
+          if (p.dbg & 2) continue;
+          for (int c0 = 0; c0 < p.Cout; c0 += 8) {
+            uint32_t v[8];
+            tmem_ld8(taddr + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (live) {
+              float f[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + bb[j];
+              if (p.act == DAFK_ACT_LRELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = f[j] > 0.f ? f[j] : p.alpha * f[j];
+              } else if (p.act == DAFK_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+              } else if (p.act == DAFK_ACT_TANH) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = tanhf(f[j]);
+              }
+              if (p.y_dt == DAFK_F32) {
+                float* o = reinterpret_cast<float*>(y) + obase + c0;
+                if ((p.Cout & 3) == 0) {
+                  *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+                  if (c0 + 4 < p.Cout) *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (c0 + j < p.Cout) o[j] = f[j];
+                }
+              } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + obase + c0;
+                if ((p.Cout & 7) == 0) {
+                  *reinterpret_cast<uint4*>(o) = nc_pack8(f);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (c0 + j < p.Cout) o[j] = __float2bfloat16_rn(f[j]);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty + b);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient (+ bias gradient).  Warp-specialised persistent CTA:
+//   warps 0-3 producers: X rows and dY rows of a strip -> raster planes of stage s;   warp 4: MMA issuer.
+//   The KH*CG accumulators [64 x N8] stay in TMEM over all strips of the CTA; the producers drain them at
+//   the end with fp32 atomics into the HWIO gradient.
+// smem: [S stages x (CG*planeX + COG*planeY)*16][bsum scratch: 128*8 f32][barriers]
+// ---------------------------------------------------------------------------------------------
+constexpr int NC_WG_THREADS = 160;
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p, const TX* __restrict__ x,
+                                                                         const TY* __restrict__ dy,
+                                                                         float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int x_bytes = p.CG * p.planeX * 16;
+  const int y_bytes = p.COG * p.planeY * 16;
+  const int st_bytes = x_bytes + y_bytes;
+  float* s_bsum = reinterpret_cast<float*>(smem + (size_t)p.S * st_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_bsum + NC_PROD * 8);
+  uint64_t* empty = full + NC_MAX_STAGES;
+  uint64_t* done = empty + NC_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < p.S * st_bytes / 16; i += NC_WG_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int i = 0; i < p.S; ++i) { mbar_init(full + i, NC_PROD); mbar_init(empty + i, 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool any = (int)blockIdx.x < p.total_strips;
+  const int nthr_y = (NC_PROD / p.COG) * p.COG;
+
+  if (warp < 4) {
+    float bsum[8], dummy[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
+    int it = 0;
+    for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x, ++it) {
+      const int st = it % p.S;
+      const uint32_t ph = (uint32_t)(it / p.S) & 1u;
+      const int n = s / p.strips_per_img;
+      const int y0 = (s - n * p.strips_per_img) * p.R;
+      uint8_t* sx = smem + (size_t)st * st_bytes;
+      mbar_wait(empty + st, ph ^ 1u);
+      nc_stage_rows<TX, false>(x, sx, p.planeX, n, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P, p.pad, tid, NC_PROD, dummy);
+      if (db != nullptr)
+        nc_stage_rows<TY, true>(dy, sx + x_bytes, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, nthr_y, bsum);
+      else
+        nc_stage_rows<TY, false>(dy, sx + x_bytes, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, NC_PROD, dummy);
+      fence_proxy_async();
+      mbar_arrive(full + st);
+    }
+    if (any) {
+      // bias gradient: per-thread partial sums -> scratch -> one atomic per channel per CTA
+      if (db != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s_bsum[tid * 8 + c] = tid < nthr_y ? bsum[c] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid < p.Cout) {
+          const int cog = tid >> 3, c = tid & 7;
+          float acc = 0.f;
+          for (int t = cog; t < nthr_y; t += p.COG) acc += s_bsum[t * 8 + c];
+          atomicAdd(db + tid, acc);
+        }
+      }
+      mbar_wait(done, 0);
+      tc_fence_after();
+      // accumulator a = (r, cg) holds rows i = q*8 + c (tap q of filter row r, channel cg*8+c), columns = co.
+      // M = 64 accumulators keep rows 16*j .. 16*j+15 in TMEM lanes 32*j .. 32*j+15.
+      const int q4 = warp & 3;
+      const int i = q4 * 16 + lane;
+      const int q = i >> 3, c = i & 7;
+      const int nacc = p.KH * p.CG;
+      for (int a = 0; a < nacc; ++a) {
+        const int r = a / p.CG, cg = a - r * p.CG;
+        const int ci = cg * 8 + c;
+        const bool ok = lane < 16 && q < p.KW && ci < p.Cin;
+        for (int c0 = 0; c0 < p.N8; c0 += 8) {
+          uint32_t v[8];
+          tmem_ld8(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * p.N8 + c0), v);
+          tmem_ld_wait();
+          if (ok) {
+            float* o = dw + ((int64_t)(r * p.KW + q) * p.Cin + ci) * p.Cout + c0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (c0 + j < p.Cout) atomicAdd(o + j, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(64, p.N8, 1, 1);
+    const int KH = p.KH, CG = p.CG, N8 = p.N8, chunks = p.chunks;
+    // MN-major, un-swizzled: LBO = distance between groups of 8 K rows (8 positions = 128 B), SBO = distance
+    // between groups of 8 MN elements (dY: the next channel-group plane; X: the next tap of the filter row =
+    // the next raster position = 16 B)
+    const uint64_t descY = make_smem_desc_ns(smem_u32(smem) + (uint32_t)x_bytes, 128, (uint32_t)p.planeY * 16u);
+    const uint64_t descX = make_smem_desc_ns(smem_u32(smem), 128, 16);
+    int it = 0;
+    for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x, ++it) {
+      const int st = it % p.S;
+      const uint32_t ph = (uint32_t)(it / p.S) & 1u;
+      mbar_wait(full + st, ph);
+      tc_fence_after();
+      const uint64_t st_off = (uint64_t)((uint32_t)(st * st_bytes) >> 4);
+      for (int c = 0; c < chunks; ++c) {
+        const uint64_t k_off = st_off + (uint64_t)(c * 16);        // 16 positions x 16 B, in 16 B units
+        const uint32_t accum = (it > 0 || c > 0) ? 1u : 0u;
+        int a = 0;
+        for (int r = 0; r < KH; ++r)
+          for (int cg = 0; cg < CG; ++cg, ++a)
+            umma_bf16(tmem_base + (uint32_t)(a * N8), descX + k_off + (uint64_t)(cg * p.planeX + r * p.P), descY + k_off,
+                      idesc, accum);
+      }
+      umma_commit(empty + st);
+    }
+    if (any) umma_commit(done);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: HWIO f32 -> bf16 [e = (cg*KH + r)*KW + q][Npad][8]; E entries (zero padded)
+//   mode 0 (forward):        Wp[e][n][c] = w[r][q][cg*8+c][n]                 (Cin_k = Cin,  Cout_k = Cout)
+//   mode 1 (data gradient):  Wp[e][n][c] = w[KH-1-r][KW-1-q][n][cg*8+c]       (Cin_k = Cout, Cout_k = Cin)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_nc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int KH, int KW, int Cin,
+                               int Cout, int mode, int E, int Npad) {
+  const int Ck = mode == 0 ? Cin : Cout;    // the kernel's reduction channels
+  const int Nk = mode == 0 ? Cout : Cin;    // the kernel's output channels
+  const int CG = (Ck + 7) / 8;
+  const int total = E * Npad * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i & 7;
+    const int nn = (i >> 3) % Npad;
+    const int e = (i >> 3) / Npad;
+    float v = 0.f;
+    if (e < CG * KH * KW) {
+      const int q = e % KW;
+      const int t = e / KW;
+      const int r = t % KH;
+      const int cg = t / KH;
+      const int ck = cg * 8 + c;
+      if (ck < Ck && nn < Nk) {
+        if (mode == 0) v = w[(((int64_t)r * KW + q) * Cin + ck) * Cout + nn];
+        else v = w[(((int64_t)(KH - 1 - r) * KW + (KW - 1 - q)) * Cin + nn) * Cout + ck];
+      }
+    }
+    wp[i] = __float2bfloat16_rn(v);
+  }
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Geometry: rows per strip R and ring depth S.  One persistent CTA per SM walks the strips round-robin, so the
+// cost of a choice is  rounds(R) * bytes moved per strip; the candidates must fit S >= 2 stages in shared memory.
+static const size_t kNcSmemMax = 200 * 1024;
+
+static bool nc_fwd_geom(NcFwdP& p, size_t& smem) {
+  p.P = p.W + 2 * p.pad;
+  p.CG = (p.Cin + 7) / 8;
+  p.E = round_up(p.CG * p.KH * p.KW, 2);
+  p.Npad = round_up(p.Cout, 16);
+  if (p.Npad > 256) return false;
+  p.G = 256 / p.Npad;
+  const size_t fixed = (size_t)p.E * p.Npad * 16 + (size_t)p.E * 16 + (size_t)p.Npad * 4 + 256 + 256;
+  double best_cost = 0;
+  int best = 0, best_S = 0;
+  size_t best_smem = 0;
+  for (int R = 1; R <= 16; R *= 2) {
+    if (R > 1 && R / 2 >= p.Ho) break;
+    const int T = (R * p.P + 127) / 128;
+    const int plane = round_up(128 * T + (p.KH - 1) * p.P + p.KW + 8, 8);
+    const size_t stage = (size_t)p.CG * plane * 16;
+    int S = (int)((kNcSmemMax - fixed) / stage);
+    if (S > 3) S = 3;
+    if (S < 2) continue;
+    const int64_t strips = (int64_t)p.N * ((p.Ho + R - 1) / R);
+    const int64_t rounds = (strips + kNumSMs - 1) / kNumSMs;
+    const double cost = (double)rounds * ((double)R * p.Wo * p.Cout * 4.0 + (double)(R + p.KH - 1) * p.W * p.Cin * 2.0 + 600.0);
+    if (!best || cost < best_cost) {
+      best = R; best_S = S; best_cost = cost; best_smem = fixed + S * stage;
+    }
+  }
+  if (!best) return false;
+  p.R = best;
+  p.S = best_S;
+  p.RS = p.R + p.KH - 1;
+  p.T = (p.R * p.P + 127) / 128;
+  p.plane = round_up(128 * p.T + (p.KH - 1) * p.P + p.KW + 8, 8);
+  p.strips_per_img = (p.Ho + p.R - 1) / p.R;
+  p.total_strips = p.N * p.strips_per_img;
+  smem = best_smem;
+  return true;
+}
+
+static bool nc_wg_geom(NcWgP& p, size_t& smem) {
+  p.P = p.W + 2 * p.pad;
+  p.CG = (p.Cin + 7) / 8;
+  p.COG = (p.Cout + 7) / 8;
+  p.N8 = p.COG * 8;
+  if (p.KW > 8 || p.N8 > 256 || p.COG > NC_PROD) return false;
+  const int cols = p.KH * p.CG * p.N8;
+  if (cols > 512) return false;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < cols) p.tmem_cols <<= 1;
+  const size_t fixed = (size_t)NC_PROD * 8 * 4 + 256 + 256;
+  double best_cost = 0;
+  int best = 0, best_S = 0;
+  size_t best_smem = 0;
+  for (int R = 1; R <= 16; R *= 2) {
+    if (R > 1 && R / 2 >= p.Ho) break;
+    const int kpos = round_up(R * p.P, 16);
+    const int planeX = kpos + (p.KH - 1) * p.P + 16;
+    const size_t stage = (size_t)p.CG * planeX * 16 + (size_t)p.COG * kpos * 16;
+    int S = (int)((kNcSmemMax - fixed) / stage);
+    if (S > 3) S = 3;
+    if (S < 2) continue;
+    const int64_t strips = (int64_t)p.N * ((p.Ho + R - 1) / R);
+    const int64_t rounds = (strips + kNumSMs - 1) / kNumSMs;
+    const double cost = (double)rounds * ((double)R * p.Wo * p.Cout * 2.0 + (double)(R + p.KH - 1) * p.W * p.Cin * 2.0 + 600.0);
+    if (!best || cost < best_cost) {
+      best = R; best_S = S; best_cost = cost; best_smem = fixed + S * stage;
+    }
+  }
+  if (!best) return false;
+  p.R = best;
+  p.S = best_S;
+  p.RS = p.R + p.KH - 1;
+  const int kpos = round_up(p.R * p.P, 16);
+  p.chunks = kpos / 16;
+  p.planeX = kpos + (p.KH - 1) * p.P + 16;
+  p.planeY = kpos;
+  p.strips_per_img = (p.Ho + p.R - 1) / p.R;
+  p.total_strips = p.N * p.strips_per_img;
+  smem = best_smem;
+  return true;
+}
+
+template <typename K>
+static int nc_set_smem(K kernel, size_t smem, const char* name) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "%s: cudaFuncSetAttribute(%zu bytes) failed: %s", name, smem,
+                 cudaGetErrorString(e));
+  }
+  return DAFK_OK;
+}
+
+}  // namespace dafk
+
+using namespace dafk;
+
+extern "C" {
+
+int dafk_conv_nc_supported(int Cin, int Cout, int KH, int KW, int W, int pad, int kind) {
+  if (kind == 2) {
+    NcWgP p{};
+    p.H = p.Ho = 1 << 20; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad;
+    size_t smem;
+    return nc_wg_geom(p, smem) ? 1 : 0;
+  }
+  NcFwdP p{};
+  p.H = p.Ho = 1 << 20; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad;
+  size_t smem;
+  return nc_fwd_geom(p, smem) ? 1 : 0;
+}
+
+int64_t dafk_conv_nc_packed_elems(int Cin_k, int Cout_k, int KH, int KW) {
+  int CG = (Cin_k + 7) / 8;
+  int E = round_up(CG * KH * KW, 2);
+  return (int64_t)E * round_up(Cout_k, 16) * 8;
+}
+
+int dafk_pack_conv_nc(const float* w_hwio, void* wp, int KH, int KW, int Cin, int Cout, int mode, void* stream) {
+  DAFK_REQUIRE(w_hwio && wp && KH > 0 && KW > 0 && Cin > 0 && Cout > 0 && (mode == 0 || mode == 1), DAFK_ERR_BAD_ARG,
+               "dafk_pack_conv_nc: bad argument");
+  const int Ck = mode == 0 ? Cin : Cout, Nk = mode == 0 ? Cout : Cin;
+  const int CG = (Ck + 7) / 8;
+  const int E = round_up(CG * KH * KW, 2), Npad = round_up(Nk, 16);
+  const int total = E * Npad * 8;
+  pack_nc_kernel<<<bw_grid(total, 256), 256, 0, as_stream(stream)>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, mode,
+                                                                     E, Npad);
+  return check_launch("dafk_pack_conv_nc");
+}
+
+int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias, void* y, int y_dt, int N, int H,
+                     int W, int Cin, int Cout, int KH, int KW, int pad, int act, float alpha, void* stream) {
+  DAFK_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && pad >= 0, DAFK_ERR_BAD_ARG,
+               "dafk_conv_nc_fwd: bad shape");
+  if (N == 0) return DAFK_OK;
+  DAFK_REQUIRE(x && wp && y, DAFK_ERR_BAD_ARG, "dafk_conv_nc_fwd: null pointer");
+  DAFK_REQUIRE((x_dt == DAFK_F32 || x_dt == DAFK_BF16) && (y_dt == DAFK_F32 || y_dt == DAFK_BF16), DAFK_ERR_BAD_ARG,
+               "dafk_conv_nc_fwd: bad dtype");
+  DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(wp) && DAFK_ALIGNED16(y), DAFK_ERR_ALIGN,
+               "dafk_conv_nc_fwd: pointers must be 16-byte aligned");
+  NcFwdP p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad;
+  p.Ho = H + 2 * pad - KH + 1;
+  p.Wo = W + 2 * pad - KW + 1;
+  DAFK_REQUIRE(p.Ho > 0 && p.Wo > 0, DAFK_ERR_BAD_ARG, "dafk_conv_nc_fwd: empty output");
+  p.x_dt = x_dt; p.y_dt = y_dt; p.act = act; p.alpha = alpha;
+  { const char* e = getenv("DAFK_NC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+  size_t smem;
+  DAFK_REQUIRE(nc_fwd_geom(p, smem), DAFK_ERR_UNSUPPORTED,
+               "dafk_conv_nc_fwd: geometry does not fit (Cin=%d Cout=%d k=%dx%d W=%d)", Cin, Cout, KH, KW, W);
+  // one persistent CTA per SM (it owns all 512 TMEM columns): request more than half of the shared memory
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  int grid = kNumSMs < p.total_strips ? kNumSMs : p.total_strips;
+  cudaStream_t s = as_stream(stream);
+  int rc;
+  if (x_dt == DAFK_F32) {
+    rc = nc_set_smem(conv_nc_fwd_kernel<float>, smem, "dafk_conv_nc_fwd");
+    if (rc) return rc;
+    conv_nc_fwd_kernel<float><<<grid, NC_FWD_THREADS, smem, s>>>(p, (const float*)x, (const __nv_bfloat16*)wp, bias, y);
+  } else {
+    rc = nc_set_smem(conv_nc_fwd_kernel<__nv_bfloat16>, smem, "dafk_conv_nc_fwd");
+    if (rc) return rc;
+    conv_nc_fwd_kernel<__nv_bfloat16><<<grid, NC_FWD_THREADS, smem, s>>>(p, (const __nv_bfloat16*)x,
+                                                                        (const __nv_bfloat16*)wp, bias, y);
+  }
+  return check_launch("dafk_conv_nc_fwd");
+}
+
+int dafk_conv_nc_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float* dw, float* db, int N, int H, int W,
+                       int Cin, int Cout, int KH, int KW, int pad, void* stream) {
+  DAFK_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && pad >= 0, DAFK_ERR_BAD_ARG,
+               "dafk_conv_nc_wgrad: bad shape");
+  if (N == 0) return DAFK_OK;
+  DAFK_REQUIRE(x && dy && dw, DAFK_ERR_BAD_ARG, "dafk_conv_nc_wgrad: null pointer");
+  DAFK_REQUIRE((x_dt == DAFK_F32 || x_dt == DAFK_BF16) && (dy_dt == DAFK_F32 || dy_dt == DAFK_BF16), DAFK_ERR_BAD_ARG,
+               "dafk_conv_nc_wgrad: bad dtype");
+  DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(dy), DAFK_ERR_ALIGN, "dafk_conv_nc_wgrad: pointers must be 16-byte aligned");
+  NcWgP p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad;
+  p.Ho = H + 2 * pad - KH + 1;
+  p.Wo = W + 2 * pad - KW + 1;
+  DAFK_REQUIRE(p.Ho > 0 && p.Wo > 0, DAFK_ERR_BAD_ARG, "dafk_conv_nc_wgrad: empty output");
+  p.x_dt = x_dt; p.dy_dt = dy_dt;
+  size_t smem;
+  DAFK_REQUIRE(nc_wg_geom(p, smem), DAFK_ERR_UNSUPPORTED,
+               "dafk_conv_nc_wgrad: geometry does not fit (Cin=%d Cout=%d k=%dx%d W=%d)", Cin, Cout, KH, KW, W);
+  if (smem < 120 * 1024) smem = 120 * 1024;     // one persistent CTA per SM
+  int grid = kNumSMs < p.total_strips ? kNumSMs : p.total_strips;
+  cudaStream_t s = as_stream(stream);
+  int rc;
+#define NC_WG(TX, TY)                                                                                   \
+  do {                                                                                                  \
+    rc = nc_set_smem(conv_nc_wgrad_kernel<TX, TY>, smem, "dafk_conv_nc_wgrad");                           \
+    if (rc) return rc;                                                                                  \
+    conv_nc_wgrad_kernel<TX, TY><<<grid, NC_WG_THREADS, smem, s>>>(p, (const TX*)x, (const TY*)dy, dw, db);  \
+  } while (0)
+  if (x_dt == DAFK_F32 && dy_dt == DAFK_F32) NC_WG(float, float);
+  else if (x_dt == DAFK_F32) NC_WG(float, __nv_bfloat16);
+  else if (dy_dt == DAFK_F32) NC_WG(__nv_bfloat16, float);
+  else NC_WG(__nv_bfloat16, __nv_bfloat16);
+#undef NC_WG
+  return check_launch("dafk_conv_nc_wgrad");
+}
+
+}  // extern "C"

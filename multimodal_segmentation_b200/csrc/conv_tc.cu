@@ -13,124 +13,9 @@
 //     dW[tap][ci][co] += sum_pixels X[pixel + tap, ci] * dY[pixel, co]
 //     both operands are the same 128-pixel boxes used as MN-major UMMA operands (the reduction
 //     runs over pixels), split-K over pixel tiles, fp32 atomics into the HWIO gradient.
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_ptx.cuh"
 
 namespace dafk {
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P1;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok;
-}
-// Bounded wait: a pipeline bug must surface as a trapped launch (reported through
-// dafk_last_error_string by the next call), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("dafk: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier once every previously issued MMA of this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// ---------------------------------------------------------------------------------------------
-// descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp of CUTLASS 4.x, re-derived here)
-// ---------------------------------------------------------------------------------------------
-// shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
-// version=1 [46,48) | base_offset [49,52) | layout_type [61,64) (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor, kind::f16: c_format=F32 [4,6)=1 | a_format=BF16 [7,10)=1 | b_format=BF16 [10,13)=1 |
-// a_major [15] | b_major [16] (0 = K-major, 1 = MN-major) | N>>3 [17,23) | M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 constexpr int TILE_PIX = 128;                 // pixels per M tile (UMMA_M)
 constexpr int KBLK = 64;                      // channels per k-block (128 B of bf16 = one swizzle row)
@@ -143,36 +28,35 @@ struct TileGeom {
 };
 
 // ---------------------------------------------------------------------------------------------
-// forward / dgrad kernel
+// forward / dgrad kernel: persistent, one CTA per SM.  Tiles (128 pixels x BLOCK_N channels) are walked
+// round-robin with the channel block fastest (CTAs that run side by side share the activation tile in L2).
+//   warp 0   TMA producer : runs ahead through the STAGES-deep smem ring, across tile boundaries
+//   warp 1   MMA issuer   : accumulates tile t into TMEM buffer t&1 while the epilogue drains tile t-1
+//   warps 2-5 epilogue    : TMEM -> registers -> (+bias) -> global
 // ---------------------------------------------------------------------------------------------
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA0,
-                                                                 const __grid_constant__ CUtensorMap tmA1,
-                                                                 const __grid_constant__ CUtensorMap tmB,
-                                                                 const float* __restrict__ bias, void* __restrict__ y,
-                                                                 int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1,
-                                                                 int KH, int KW, int stride, int pad, TileGeom g,
-                                                                 int n_blocks, int w_rows_per_tap, int w_row_off,
-                                                                 long long y_sn, long long y_sy, long long y_sx) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                                    const __grid_constant__ CUtensorMap tmA1,
+                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                    const float* __restrict__ bias, void* __restrict__ y,
+                                                                    int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1,
+                                                                    int KH, int KW, int stride, int pad, TileGeom g,
+                                                                    int n_blocks, int w_rows_per_tap, int w_row_off,
+                                                                    long long y_sn, long long y_sy, long long y_sx,
+                                                                    int total_tiles) {
   constexpr int B_BYTES = BLOCK_N * KBLK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;     // two accumulator buffers
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nb = blockIdx.x % n_blocks;
-  int tile = blockIdx.x / n_blocks;
-  const int txi = tile % g.tiles_x; tile /= g.tiles_x;
-  const int tyi = tile % g.tiles_y; tile /= g.tiles_y;
-  const int tni = tile;
-  const int x0 = txi * g.TW, y0 = tyi * g.TH, img0 = tni * g.TN;
-  const int n0 = nb * BLOCK_N;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int taps = KH * KW;
   const int num_kb = taps * ((C0 + C1) / KBLK);
 
@@ -181,7 +65,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_fwd_kernel(const __grid_co
     if (C1 > 0) tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 128); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -193,82 +77,116 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_fwd_kernel(const __grid_co
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int kb = 0;
-      for (int src = 0; src < 2; ++src) {
-        const int Cs = src == 0 ? C0 : C1;
-        const CUtensorMap* mA = src == 0 ? &tmA0 : &tmA1;
-        const int koff = src == 0 ? 0 : C0;
-        for (int cb = 0; cb < Cs / KBLK; ++cb) {
-          for (int tap = 0; tap < taps; ++tap, ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(empty_bar + s, ph ^ 1);
-            mbar_expect_tx(full_bar + s, STAGE_BYTES);
-            const int r = tap / KW, q = tap % KW;
-            uint8_t* sa = smem + s * STAGE_BYTES;
-            tma_load_4d(sa, mA, full_bar + s, cb * KBLK, x0 * stride + q - pad, y0 * stride + r - pad, img0);
-            tma_load_2d(sa + A_BYTES, &tmB, full_bar + s, koff + cb * KBLK, tap * w_rows_per_tap + w_row_off + n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nb = tile % n_blocks;
+        int mt = tile / n_blocks;
+        const int txi = mt % g.tiles_x; mt /= g.tiles_x;
+        const int tyi = mt % g.tiles_y; mt /= g.tiles_y;
+        const int x0 = txi * g.TW, y0 = tyi * g.TH, img0 = mt * g.TN;
+        const int n0 = nb * BLOCK_N;
+        for (int src = 0; src < 2; ++src) {
+          const int Cs = src == 0 ? C0 : C1;
+          const CUtensorMap* mA = src == 0 ? &tmA0 : &tmA1;
+          const int koff = src == 0 ? 0 : C0;
+          for (int cb = 0; cb < Cs / KBLK; ++cb) {
+            for (int tap = 0; tap < taps; ++tap, ++it) {
+              const int s = it % STAGES;
+              const uint32_t ph = (it / STAGES) & 1;
+              mbar_wait(empty_bar + s, ph ^ 1);
+              mbar_expect_tx(full_bar + s, STAGE_BYTES);
+              const int r = tap / KW, q = tap % KW;
+              uint8_t* sa = smem + s * STAGE_BYTES;
+              tma_load_4d(sa, mA, full_bar + s, cb * KBLK, x0 * stride + q - pad, y0 * stride + r - pad, img0);
+              tma_load_2d(sa + A_BYTES, &tmB, full_bar + s, koff + cb * KBLK, tap * w_rows_per_tap + w_row_off + n0);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_PIX, BLOCK_N, 0, 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+    // the whole warp runs the loop (warp-uniform control flow, operands in uniform registers); one elected
+    // lane issues.  Descriptors advance by plain 64-bit adds on the 16-byte-unit start-address field.
+    constexpr uint32_t idesc = make_idesc(TILE_PIX, BLOCK_N, 0, 0);
+    const uint32_t leader = elect_one();
+    const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t desc0 = make_smem_desc(smem_u32(smem), 16, 1024);
+    int it = 0, tc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+      const uint32_t b = (uint32_t)tc & 1u;
+      mbar_wait(tempty_bar + b, (((uint32_t)tc >> 1) & 1u) ^ 1u);     // epilogue has drained this buffer
+      tc_fence_after();
+      const uint32_t d_col = tmem_acc + b * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(full_bar + s, ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_BYTES;
+        if (leader) {
+          // K-major SW128: 8-row groups 1024 B apart; advance 32 B (= 2 units) per UMMA_K inside the swizzle row
+          const uint64_t da = desc0 + (uint64_t)((s * STAGE_BYTES) >> 4);
+          const uint64_t db = da + (uint64_t)(A_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < KBLK / 16; ++k) {
-          // K-major SW128: 8-row groups 1024 B apart; advance 32 B per UMMA_K inside the swizzle row
-          uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-          uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < KBLK / 16; ++k)
+            umma_bf16(d_col, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar + s);   // frees the smem slot when these MMAs retire
         }
-        umma_commit(empty_bar + s);   // frees the smem slot when these MMAs retire
+        __syncwarp();
       }
-      umma_commit(tmem_full_bar);     // accumulator ready
+      if (leader) umma_commit(tfull_bar + b);     // accumulator ready
+      __syncwarp();
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
     const int m = q4 * 32 + lane;            // row of the tile = pixel
     const int tx = m % g.TW, ty = (m / g.TW) % g.TH, tn = m / (g.TW * g.TH);
-    const int px = x0 + tx, py = y0 + ty, img = img0 + tn;
-    const bool live = px < Wo && py < Ho && img < N;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int64_t obase = (int64_t)img * y_sn + (int64_t)py * y_sy + (int64_t)px * y_sx + n0;
+    int tc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+      const int nb = tile % n_blocks;
+      int mt = tile / n_blocks;
+      const int txi = mt % g.tiles_x; mt /= g.tiles_x;
+      const int tyi = mt % g.tiles_y; mt /= g.tiles_y;
+      const int px = txi * g.TW + tx, py = tyi * g.TH + ty, img = mt * g.TN + tn;
+      const int n0 = nb * BLOCK_N;
+      const bool live = px < Wo && py < Ho && img < N;
+      const uint32_t b = (uint32_t)tc & 1u;
+      mbar_wait(tfull_bar + b, ((uint32_t)tc >> 1) & 1u);
+      tc_fence_after();
+      const int64_t obase = (int64_t)img * y_sn + (int64_t)py * y_sy + (int64_t)px * y_sx + n0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * BLOCK_N;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c, v);
-      tmem_ld_wait();
-      if (live) {
-        float f[16];
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_ld16(taddr + (uint32_t)c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        tmem_ld_wait();
+        if (live) {
+          float f[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c + j) : 0.f);
-        if (y_dt == DAFK_F32) {
-          float* o = reinterpret_cast<float*>(y) + obase + c;
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c + j) : 0.f);
+          if (y_dt == DAFK_F32) {
+            float* o = reinterpret_cast<float*>(y) + obase + c;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + obase + c;
-          uint32_t pk[8];
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + obase + c;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * i], f[j + 2 * i + 1]);
+                pk[i] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
           }
-          *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
       }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + b);
     }
   }
   tc_fence_before();
@@ -300,7 +218,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_kernel(const __grid_
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int ci_blocks = Cin / BN, co_blocks = Cout / BM;
   int unit = blockIdx.x;
   const int cib = unit % ci_blocks; unit /= ci_blocks;
@@ -348,27 +266,29 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_kernel(const __grid_
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);   // both operands MN-major
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int s = kb % STAGES;
-          const uint32_t ph = (kb / STAGES) & 1;
-          mbar_wait(full_bar + s, ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t b_addr = a_addr + SA;
+      constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);   // both operands MN-major
+      const uint32_t leader = elect_one();
+      const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_base, 0);
+      // MN-major SW128: one atom = 64 channels (128 B) x 8 pixels; pixel groups of 8 are 1024 B apart
+      // (SBO), the next 64 channels are one whole box = 16 KB away (LBO); 16 pixels per MMA = 2048 B.
+      const uint64_t desc0 = make_smem_desc(smem_u32(smem), A_BYTES, 1024);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t da = desc0 + (uint64_t)((s * STAGE_BYTES) >> 4);
+          const uint64_t db = da + (uint64_t)(SA >> 4);
 #pragma unroll
-          for (int k = 0; k < TILE_PIX / 16; ++k) {
-            // MN-major SW128: one atom = 64 channels (128 B) x 8 pixels; pixel groups of 8 are 1024 B apart
-            // (SBO), the next 64 channels are one whole box = 16 KB away (LBO); 16 pixels per MMA = 2048 B.
-            uint64_t da = make_smem_desc(a_addr + k * 2048, A_BYTES, 1024);
-            uint64_t db = make_smem_desc(b_addr + k * 2048, A_BYTES, 1024);
-            umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < TILE_PIX / 16; ++k)
+            umma_bf16(tmem_acc, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar + s);
         }
-        umma_commit(tmem_full_bar);
+        __syncwarp();
       }
+      if (leader) umma_commit(tmem_full_bar);
+      __syncwarp();
     } else {
       const int q4 = warp & 3;
       // accumulator row -> TMEM lane: M=128: row = lane index; M=64: rows 16*q..16*q+15 sit in the first
@@ -520,6 +440,7 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
                       const TileGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
                       long long y_sx, cudaStream_t s) {
   constexpr int smem = STAGES * (A_BYTES + BLOCK_N * KBLK * 2) + 1024 + 256;
+  static_assert(smem > 116 * 1024 && smem <= 227 * 1024, "one persistent CTA per SM");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_fwd_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -527,11 +448,12 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
     configured = true;
   }
   int n_blocks = Cout / BLOCK_N;
-  int64_t tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n;
-  dim3 grid((unsigned)(tiles * n_blocks));
+  int64_t tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n * n_blocks;
+  DAFK_REQUIRE(tiles < (1LL << 31), DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd: too many tiles");
+  dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
   conv_tc_fwd_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1,
                                                                     KH, KW, stride, pad, g, n_blocks, w_rows_per_tap,
-                                                                    w_row_off, y_sn, y_sy, y_sx);
+                                                                    w_row_off, y_sn, y_sy, y_sx, (int)tiles);
   return check_launch("dafk_conv_tc_fwd");
 }
 
@@ -588,15 +510,28 @@ int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void*
   if (C1 > 0) { rc = make_act_map(&a1, x1, N, H, W, C1, g, stride); if (rc) return rc; } else a1 = a0;
   cudaStream_t s = as_stream(stream);
   const int taps = KH * KW;
+  const int64_t m_tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n;
+  if (Cout % 256 == 0) {
+    // 128 x 256 tiles read 1.5 operand bytes per MAC-row instead of 2 (the 128 x 128 kernel is L2-bound), but
+    // halve the number of tiles: take them when the round-robin tail does not eat the gain
+    const int64_t r256 = (m_tiles * (Cout / 256) + kNumSMs - 1) / kNumSMs;
+    const int64_t r128 = (m_tiles * (Cout / 128) + kNumSMs - 1) / kNumSMs;
+    if ((double)r256 * 2.0 * 0.8 <= (double)r128) {
+      rc = make_w_map(&b, wp, taps * w_rows_per_tap, C0 + C1, 256);
+      if (rc) return rc;
+      return launch_fwd<256, 4>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
+                                w_row_off, y_sn, y_sy, y_sx, s);
+    }
+  }
   if (Cout % 128 == 0) {
     rc = make_w_map(&b, wp, taps * w_rows_per_tap, C0 + C1, 128);
     if (rc) return rc;
-    return launch_fwd<128, 3>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
+    return launch_fwd<128, 6>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
                               w_row_off, y_sn, y_sy, y_sx, s);
   }
   rc = make_w_map(&b, wp, taps * w_rows_per_tap, C0 + C1, 64);
   if (rc) return rc;
-  return launch_fwd<64, 4>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
+  return launch_fwd<64, 8>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
                            w_row_off, y_sn, y_sy, y_sx, s);
 }
 

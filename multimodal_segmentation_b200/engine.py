@@ -254,6 +254,7 @@ class Conv2D:
         self.kernel = arena.add(name + "/kernel", (k, k, cin, cout), init_weights(rng, (k, k, cin, cout), init))
         self.bias = arena.add(name + "/bias", (cout,), np.zeros(cout, np.float32)) if use_bias else None
         self._packed = None          # (arena version, wp_fwd, wp_dgrad)
+        self._packed_nc = None
 
     def params(self):
         return [self.kernel] + ([self.bias] if self.bias is not None else [])
@@ -300,13 +301,31 @@ class Conv2D:
             return self._call_tc(ctx, srcs, act, alpha)
         return self._call_generic(ctx, srcs, act, alpha)
 
-    # ---- CUDA-core path (fp32)
+    def packed_nc(self):
+        """bf16 operands of the narrow-channel tcgen05 kernels (forward + stride-1 data gradient)"""
+        ver = self.kernel.arena.version
+        if self._packed_nc is None or self._packed_nc[0] != ver:
+            self._packed_nc = (ver, ops.pack_conv_nc(self.kernel.data, 0), ops.pack_conv_nc(self.kernel.data, 1))
+        return self._packed_nc[1], self._packed_nc[2]
+
+    # ---- narrow layers: raster-strip tcgen05 kernels (stride 1) or the CUDA-core kernels (fp32)
     def _call_generic(self, ctx, srcs, act, alpha):
         code = ACT[act]
-        f32srcs = [s if s.data.dtype == torch.float32 else _cast_var(ctx, s, torch.float32) for s in srcs]
-        xin = f32srcs[0] if len(f32srcs) == 1 else concat(ctx, f32srcs)
+        W = srcs[0].shape[2]
+        nc = self.stride == 1 and USE_TC
+        nc_f = nc and ops.nc_supported(self.cin, self.cout, self.k, self.k, W, self.pad, 0)
+        nc_d = nc and ops.nc_supported(self.cin, self.cout, self.k, self.k, W, self.pad, 1)
+        nc_w = nc and ops.nc_supported(self.cin, self.cout, self.k, self.k, W, self.pad, 2)
+        if len(srcs) == 1 and nc_f and nc_w:
+            xin = srcs[0]                      # f32 or bf16: converted while it is staged
+        else:
+            f32srcs = [s if s.data.dtype == torch.float32 else _cast_var(ctx, s, torch.float32) for s in srcs]
+            xin = f32srcs[0] if len(f32srcs) == 1 else concat(ctx, f32srcs)
         bias = self.bias.data if self.bias is not None else None
-        y = Var(ops.conv2d_fwd(xin.data, self.kernel.data, bias, self.stride, self.pad, code, alpha))
+        if nc_f:
+            y = Var(ops.conv_nc_fwd(xin.data, self.packed_nc()[0], bias, self.cout, self.k, self.k, self.pad, code, alpha))
+        else:
+            y = Var(ops.conv2d_fwd(xin.data, self.kernel.data, bias, self.stride, self.pad, code, alpha))
         if ctx.rec(xin, self.kernel):
             y.requires_grad = True
             tape_x = xin
@@ -322,9 +341,17 @@ class Conv2D:
                     g = ops.act_bwd(g, y.data, code, alpha)
                 if self.kernel.requires_grad:
                     db = self.bias.grad if (self.bias is not None and self.bias.requires_grad) else None
-                    ops.conv2d_wgrad(tape_x.data, g, self.kernel.grad, db, self.stride, self.pad)
+                    if nc_w:
+                        ops.conv_nc_wgrad(tape_x.data, g, self.kernel.grad, db, self.pad)
+                    else:
+                        ops.conv2d_wgrad(tape_x.data, g, self.kernel.grad, db, self.stride, self.pad)
                 if tape_x.requires_grad:
-                    accumulate(tape_x, ops.conv2d_dgrad(g, self.kernel.data, tuple(tape_x.shape), self.stride, self.pad))
+                    if nc_d:
+                        dx = ops.conv_nc_fwd(g, self.packed_nc()[1], None, self.cin, self.k, self.k, self.k - 1 - self.pad,
+                                             out_dtype=tape_x.grad_dtype)
+                    else:
+                        dx = ops.conv2d_dgrad(g, self.kernel.data, tuple(tape_x.shape), self.stride, self.pad)
+                    accumulate(tape_x, dx)
 
             ctx.tape.record(bw)
         return y

@@ -434,6 +434,56 @@ def conv3x3_tc_wgrad(x, dy, dw, cin_off=0):
                      lambda: call("conv3x3_tc_wgrad", x, Cin, cin_off, dw.shape[2], dy, Cout, dw, N, H, W, _S()))
 
 
+# ---------------------------------------------------------------------------- narrow-channel tcgen05 convolution
+USE_NC = True        # tests switch it off to exercise the CUDA-core kernels
+
+
+def nc_supported(Cin, Cout, KH, KW, W, pad, kind):
+    """kind 0 forward, 1 stride-1 data gradient (pass the LAYER's Cin/Cout/pad), 2 weight gradient"""
+    if not USE_NC:
+        return False
+    f = _lib.lib().fn["dafk_conv_nc_supported"]
+    if kind == 1:
+        return bool(f(Cout, Cin, KH, KW, W + 2 * pad - KW + 1, KH - 1 - pad, 0))
+    return bool(f(Cin, Cout, KH, KW, W, pad, kind))
+
+
+def pack_conv_nc(w_hwio, mode):
+    """mode 0: forward operand; mode 1: stride-1 data-gradient operand (mirrored taps, transposed channels)"""
+    _chk(w_hwio)
+    KH, KW, Cin, Cout = w_hwio.shape
+    ck, nk = (Cin, Cout) if mode == 0 else (Cout, Cin)
+    n = _lib.lib().fn["dafk_conv_nc_packed_elems"](ck, nk, KH, KW)
+    wp = torch.empty(n, dtype=torch.bfloat16, device=w_hwio.device)
+    call("pack_conv_nc", w_hwio, wp, KH, KW, Cin, Cout, mode, _S())
+    return wp
+
+
+def conv_nc_fwd(x, wp, bias, Cout, KH, KW, pad, act=ACT_NONE, alpha=0.0, out_dtype=torch.float32):
+    """y = act(conv(x, w) + bias), stride 1; x f32/bf16 NHWC; wp from pack_conv_nc"""
+    _chk(x, wp, bias)
+    N, H, W, Cin = x.shape
+    Ho, Wo = H + 2 * pad - KH + 1, W + 2 * pad - KW + 1
+    y = torch.empty((N, Ho, Wo, Cout), dtype=out_dtype, device=x.device)
+    fl = 2.0 * N * Ho * Wo * Cout * KH * KW * Cin
+    nb = x.numel() * x.element_size() + y.numel() * y.element_size()
+    instrument.timed("conv_nc_fwd+dgrad (tcgen05)", fl, nb,
+                     lambda: call("conv_nc_fwd", x, _dt(x), wp, bias, y, _dt(y), N, H, W, Cin, Cout, KH, KW, pad, act,
+                                  float(alpha), _S()))
+    return y
+
+
+def conv_nc_wgrad(x, dy, dw, db, pad):
+    """dw[KH,KW,Cin,Cout] += x (*) dy; db += sum dy (db may be None); stride 1"""
+    _chk(x, dy, dw, db)
+    N, H, W, Cin = x.shape
+    KH, KW, _, Cout = dw.shape
+    fl = 2.0 * dy.numel() * KH * KW * Cin
+    nb = x.numel() * x.element_size() + dy.numel() * dy.element_size()
+    instrument.timed("conv_nc_wgrad (tcgen05)", fl, nb,
+                     lambda: call("conv_nc_wgrad", x, _dt(x), dy, _dt(dy), dw, db, N, H, W, Cin, Cout, KH, KW, pad, _S()))
+
+
 # ---------------------------------------------------------------------------- dense
 def dense_fwd(x, w, bias):
     _chk(x, w, bias)

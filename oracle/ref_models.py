@@ -52,6 +52,18 @@ class _RoundBF16(torch.autograd.Function):
         return g.to(torch.bfloat16).to(g.dtype)
 
 
+class _RoundFwdBF16(torch.autograd.Function):
+    """forward: round to bf16; backward: identity"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 class _RoundGradBF16(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -79,6 +91,11 @@ def conv(W, name, x, stride=1, padding="valid"):
     if _tc_eligible(w, stride, padding):
         y = R.conv2d(_RoundBF16.apply(x), _RoundBF16.apply(w), W.get(name + "/bias"), stride, padding)
         return _RoundGradBF16.apply(y)      # the gradient w.r.t. the conv output is consumed as bf16
+    if BF16_EMULATION and stride == 1:
+        # narrow stride-1 layers run on the raster-strip tcgen05 kernels (csrc/conv_nc.cu): operands and the
+        # incoming output gradient are rounded to bf16 while they are staged; the data gradient stays fp32
+        y = R.conv2d(_RoundFwdBF16.apply(x), _RoundFwdBF16.apply(w), W.get(name + "/bias"), stride, padding)
+        return _RoundGradBF16.apply(y)
     return R.conv2d(x, w, W.get(name + "/bias"), stride, padding)
 
 

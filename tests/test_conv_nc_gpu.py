@@ -1,0 +1,119 @@
+"""Parity of the narrow-channel tcgen05 convolutions (csrc/conv_nc.cu) against the oracle.
+
+Operands are rounded to bf16 by the kernel while it stages them, accumulation is fp32 in tensor
+memory; the oracle is evaluated in fp64 on the SAME bf16-rounded operands, so the tolerance
+(1e-4 forward / data gradient, 1e-3 for the atomically reduced weight gradient) only covers the
+accumulation order.  Against the unrounded fp32 oracle the bound is the north-star 1e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops as R
+from tests.util import cpu, gpu, rel_l2, t
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from multimodal_segmentation_b200 import ops as o
+    return o
+
+
+def bf16_round(a):
+    return torch.as_tensor(a).to(torch.bfloat16).float().numpy()
+
+
+CASES = [
+    # N, H, W, Cin, Cout, k, pad
+    (2, 16, 16, 8, 8, 3, 1),        # FiLM decoder layer (model_components/decoder.py:44-54)
+    (3, 37, 45, 8, 8, 3, 1),        # ragged strips / tiles
+    (2, 24, 40, 8, 64, 3, 1),       # segmentor conv1 (model_components/segmentor.py:15)
+    (2, 24, 24, 1, 64, 3, 1),       # UNet first layer (models/unet.py:95)
+    (2, 40, 36, 16, 20, 5, 0),      # locnet conv1 (layers/stn_spline.py:106)
+    (2, 30, 30, 20, 20, 5, 0),      # locnet conv2/3
+    (2, 20, 28, 8, 1, 1, 0),        # decoder output 1x1 (decoder.py:28)
+    (1, 224, 224, 8, 8, 3, 1),      # full-resolution strip geometry
+    (2, 12, 12, 9, 16, 3, 1),       # odd channel count (scalar staging path)
+    (2, 18, 22, 4, 5, 3, 1),
+]
+
+
+def _mk(case, seed):
+    N, H, W, Cin, Cout, k, pad = case
+    r = np.random.RandomState(seed)
+    x = bf16_round(r.normal(size=(N, H, W, Cin)).astype(np.float32))
+    w = bf16_round((r.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(np.float32))
+    b = r.normal(size=Cout).astype(np.float32)
+    return r, x, w, b
+
+
+def _ref_conv(x, w, b, pad):
+    return R.conv2d(t(x, torch.float64), t(w, torch.float64), None if b is None else t(b, torch.float64), 1,
+                    "same" if pad else "valid")
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("xdt", ["f32", "bf16"])
+def test_conv_nc_forward(ops, case, xdt):
+    N, H, W, Cin, Cout, k, pad = case
+    r, x, w, b = _mk(case, sum(case))
+    yr = _ref_conv(x, w, b, pad).numpy()
+    wp = ops.pack_conv_nc(gpu(w), 0)
+    xg = gpu(x, torch.float32 if xdt == "f32" else torch.bfloat16)
+    y = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad)
+    assert tuple(y.shape) == tuple(yr.shape)
+    err = rel_l2(cpu(y), yr)
+    assert err < 1e-4, err
+    # fused LeakyReLU epilogue + bf16 output
+    from multimodal_segmentation_b200._lib import ACT_LRELU
+    ya = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad, ACT_LRELU, 0.3, torch.bfloat16)
+    ref = np.where(yr > 0, yr, 0.3 * yr)
+    assert rel_l2(cpu(ya), ref) < 5e-3
+
+
+@pytest.mark.parametrize("case", CASES[:6] + CASES[8:])
+def test_conv_nc_dgrad(ops, case):
+    N, H, W, Cin, Cout, k, pad = case
+    r, x, w, b = _mk(case, sum(case) + 1)
+    xt = torch.zeros(N, H, W, Cin, dtype=torch.float64, requires_grad=True)
+    yr = R.conv2d(xt, t(w, torch.float64), None, 1, "same" if pad else "valid")
+    dy = bf16_round(r.normal(size=tuple(yr.shape)).astype(np.float32))
+    (yr * t(dy, torch.float64)).sum().backward()
+    wpd = ops.pack_conv_nc(gpu(w), 1)
+    dx = ops.conv_nc_fwd(gpu(dy), wpd, None, Cin, k, k, k - 1 - pad)
+    assert tuple(dx.shape) == (N, H, W, Cin)
+    err = rel_l2(cpu(dx), xt.grad.numpy())
+    assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("dts", [("f32", "f32"), ("bf16", "bf16")])
+def test_conv_nc_wgrad(ops, case, dts):
+    N, H, W, Cin, Cout, k, pad = case
+    r, x, w, b = _mk(case, sum(case) + 2)
+    wt = torch.zeros(k, k, Cin, Cout, dtype=torch.float64, requires_grad=True)
+    yr = R.conv2d(t(x, torch.float64), wt, None, 1, "same" if pad else "valid")
+    dy = bf16_round(r.normal(size=tuple(yr.shape)).astype(np.float32))
+    (yr * t(dy, torch.float64)).sum().backward()
+    dw = ops.zeros(k, k, Cin, Cout)
+    db = ops.zeros(Cout)
+    td = {"f32": torch.float32, "bf16": torch.bfloat16}
+    ops.conv_nc_wgrad(gpu(x, td[dts[0]]), gpu(dy, td[dts[1]]), dw, db, pad)
+    err = rel_l2(cpu(dw), wt.grad.numpy())
+    assert err < 1e-3, err
+    assert rel_l2(cpu(db), dy.sum((0, 1, 2))) < 1e-3
+    # accumulates into dw (second call doubles it), db optional
+    ops.conv_nc_wgrad(gpu(x, td[dts[0]]), gpu(dy, td[dts[1]]), dw, None, pad)
+    assert rel_l2(cpu(dw), 2 * wt.grad.numpy()) < 1e-3
+
+
+def test_conv_nc_vs_fp32_oracle_tolerance(ops):
+    """north-star bound for the bf16 conv path against the unrounded fp32 reference: <= 1e-2"""
+    r = np.random.RandomState(3)
+    x = r.normal(size=(2, 32, 32, 8)).astype(np.float32)
+    w = (r.normal(size=(3, 3, 8, 8)) / np.sqrt(72)).astype(np.float32)
+    yr = _ref_conv(x, w, None, 1).numpy()
+    y = ops.conv_nc_fwd(gpu(x), ops.pack_conv_nc(gpu(w), 0), None, 8, 3, 3, 1)
+    assert rel_l2(cpu(y), yr) < 1e-2
