@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(NC_FWD_THREADS, 1) conv_nc_fwd_kernel(NcFwdP p
   uint64_t* tfull = empty + NC_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
 
   // one-time setup: weights, bias, zeroed rasters (halo columns and slack stay zero for the CTA's lifetime)
   for (int i = tid; i < w_bytes / 16; i += NC_FWD_THREADS)
@@ -238,34 +238,44 @@ __global__ void __launch_bounds__(NC_FWD_THREADS, 1) conv_nc_fwd_kernel(NcFwdP p
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, p.Npad, 0, 0);
-      const int nj = (p.dbg & 1) ? 1 : p.E / 2;
-      int it = 0, gc = 0;
-      for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x, ++it) {
-        const int st = it % p.S;
-        const uint32_t ph = (uint32_t)(it / p.S) & 1u;
-        const int n = s / p.strips_per_img;
-        const int y0 = (s - n * p.strips_per_img) * p.R;
-        const int rows_here = min(p.R, p.Ho - y0);
-        const int tiles_here = (rows_here * p.P + 127) / 128;
-        mbar_wait(full + st, ph);
+    // warp-uniform control flow (all lanes walk the loops, one elected lane issues) keeps the operands in
+    // uniform registers; the (tap, group) descriptor pairs come from the table built above
+    const uint32_t idesc = make_idesc(128, p.Npad, 0, 0);
+    const uint32_t leader = elect_one();
+    const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int nj = (p.dbg & 1) ? 1 : p.E / 2;
+    const int G = p.G, Npad = p.Npad, S = p.S;
+    int it = 0, gc = 0;
+    for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x, ++it) {
+      const int st = it % S;
+      const uint32_t ph = (uint32_t)(it / S) & 1u;
+      const int n = s / p.strips_per_img;
+      const int y0 = (s - n * p.strips_per_img) * p.R;
+      const int rows_here = min(p.R, p.Ho - y0);
+      const int tiles_here = (rows_here * p.P + 127) / 128;
+      mbar_wait(full + st, ph);
+      tc_fence_after();
+      const uint64_t st_off = (uint64_t)((uint32_t)(st * st_bytes) >> 4);
+      for (int t0 = 0; t0 < tiles_here; t0 += G, ++gc) {
+        const uint32_t b = (uint32_t)gc & 1u;
+        mbar_wait(tempty + b, (((uint32_t)gc >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint64_t st_off = (uint64_t)((uint32_t)(st * st_bytes) >> 4);
-        for (int t0 = 0; t0 < tiles_here; t0 += p.G, ++gc) {
-          const int b = gc & 1;
-          mbar_wait(tempty + b, ((uint32_t)(gc >> 1) & 1u) ^ 1u);
-          tc_fence_after();
-          const int gt = min(p.G, tiles_here - t0);
-          for (int tt = 0; tt < gt; ++tt) {
-            const uint64_t a_off = st_off + (uint64_t)((t0 + tt) * 128);   // 128 positions x 16 B, in 16 B units
-            const uint32_t d_col = tmem_base + (uint32_t)(b * 256 + tt * p.Npad);
-            for (int j = 0; j < nj; ++j) umma_bf16(d_col, s_descA[j] + a_off, s_descB[j], idesc, j > 0 ? 1u : 0u);
+        const int gt = min(G, tiles_here - t0);
+        if (leader) {
+          for (int j = 0; j < nj; ++j) {
+            // the same (tap, group) pair for every tile of the group: descriptors are loaded once per pair
+            const uint64_t da = s_descA[j] + st_off + (uint64_t)(t0 * 128);
+            const uint64_t db = s_descB[j];
+            const uint32_t acc = j > 0 ? 1u : 0u;
+            for (int tt = 0; tt < gt; ++tt)
+              umma_bf16(tmem_acc + b * 256u + (uint32_t)(tt * Npad), da + (uint64_t)(tt * 128), db, idesc, acc);
           }
           umma_commit(tfull + b);
         }
-        umma_commit(empty + st);   // the raster of this stage has been consumed once these MMAs retire
+        __syncwarp();
       }
+      if (leader) umma_commit(empty + st);   // the raster of this stage has been consumed once these MMAs retire
+      __syncwarp();
     }
   } else {
     // ===================== epilogue =====================
@@ -370,7 +380,7 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
   uint64_t* empty = full + NC_MAX_STAGES;
   uint64_t* done = empty + NC_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
 
   for (int i = tid; i < p.S * st_bytes / 16; i += NC_WG_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
@@ -445,10 +455,12 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
         }
       }
     }
-  } else if (lane == 0) {
+  } else {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc(64, p.N8, 1, 1);
-    const int KH = p.KH, CG = p.CG, N8 = p.N8, chunks = p.chunks;
+    const uint32_t leader = elect_one();
+    const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int KH = p.KH, CG = p.CG, N8 = p.N8, chunks = p.chunks, S = p.S;
     // MN-major, un-swizzled: LBO = distance between groups of 8 K rows (8 positions = 128 B), SBO = distance
     // between groups of 8 MN elements (dY: the next channel-group plane; X: the next tap of the filter row =
     // the next raster position = 16 B)
@@ -456,23 +468,30 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
     const uint64_t descX = make_smem_desc_ns(smem_u32(smem), 128, 16);
     int it = 0;
     for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x, ++it) {
-      const int st = it % p.S;
-      const uint32_t ph = (uint32_t)(it / p.S) & 1u;
+      const int st = it % S;
+      const uint32_t ph = (uint32_t)(it / S) & 1u;
       mbar_wait(full + st, ph);
       tc_fence_after();
-      const uint64_t st_off = (uint64_t)((uint32_t)(st * st_bytes) >> 4);
-      for (int c = 0; c < chunks; ++c) {
-        const uint64_t k_off = st_off + (uint64_t)(c * 16);        // 16 positions x 16 B, in 16 B units
-        const uint32_t accum = (it > 0 || c > 0) ? 1u : 0u;
+      if (leader) {
+        const uint64_t st_off = (uint64_t)((uint32_t)(st * st_bytes) >> 4);
         int a = 0;
-        for (int r = 0; r < KH; ++r)
-          for (int cg = 0; cg < CG; ++cg, ++a)
-            umma_bf16(tmem_base + (uint32_t)(a * N8), descX + k_off + (uint64_t)(cg * p.planeX + r * p.P), descY + k_off,
-                      idesc, accum);
+        for (int r = 0; r < KH; ++r) {
+          for (int cg = 0; cg < CG; ++cg, ++a) {
+            const uint64_t dx = descX + st_off + (uint64_t)(cg * p.planeX + r * p.P);
+            const uint64_t dyd = descY + st_off;
+            const uint32_t d_col = tmem_acc + (uint32_t)(a * N8);
+            if (it == 0) umma_bf16(d_col, dx, dyd, idesc, 0u);
+            else umma_bf16(d_col, dx, dyd, idesc, 1u);
+            for (int c = 1; c < chunks; ++c)     // 16 positions x 16 B = 16 units per K chunk
+              umma_bf16(d_col, dx + (uint64_t)(c * 16), dyd + (uint64_t)(c * 16), idesc, 1u);
+          }
+        }
+        umma_commit(empty + st);
       }
-      umma_commit(empty + st);
+      __syncwarp();
     }
-    if (any) umma_commit(done);
+    if (any && leader) umma_commit(done);
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();

@@ -1,0 +1,160 @@
+"""Generate tests/golden/golden_ref.npz by EXECUTING THE REFERENCE'S OWN PYTHON SOURCE (imported unmodified from
+/root/reference) on top of the numpy TF/Keras stand-ins of tests/golden/tf_shim.py.
+
+    python tests/golden/make_golden.py          (only runs where /root/reference exists; the .npz is committed)
+
+What is pinned: layers/interpolate_spline.py (solve + apply, orders 1/2/4, regularisation), layers/stn_spline.py
+(nDgrid, ThinPlateSpline2D.interpolate_spline_batch / call), layers/film.py, layers/spade.py (SPADE_COND,
+resize_like), layers/rounding.py, layers/spectralnorm.py (Spectral.__call__), costs.py (dice, dice losses, the
+swapped-argument weighted cross entropy, combined losses, kl, ypred), utils/sdnet_utils.py (sampling),
+utils/data_utils.py (rescale, sample), utils/distributions.py, model_executors/base_executor.py (add_residual,
+align_batches).  Modules that only exist to reach the data set (loaders, model_tester, image_utils) are stubbed.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from tests.golden import tf_shim  # noqa: E402
+from tests.golden.tf_shim import t  # noqa: E402
+
+REF = "/root/reference"
+
+
+def main():
+    out = {}
+    rs = np.random.RandomState(1234)
+    with tf_shim.installed(REF):
+        # modules unrelated to the arithmetic (data set access, plotting) -> empty stubs
+        for name in ("utils.image_utils", "loaders", "loaders.loader_factory", "model_tester", "keras_contrib",
+                     "keras_contrib.layers"):
+            sys.modules[name] = types.ModuleType(name)
+        sys.modules["loaders"].loader_factory = sys.modules["loaders.loader_factory"]
+        sys.modules["model_tester"].ModelTester = object
+        sys.modules["keras_contrib.layers"].InstanceNormalization = tf_shim._Dummy
+        try:
+            from layers import interpolate_spline as ISP
+            from layers import stn_spline as STN
+            from layers import film as FILM
+            from layers import spade as SPADE
+            from layers import rounding as RND
+            from layers import spectralnorm as SN
+            import costs as COSTS
+            from utils import sdnet_utils as SDU
+            from utils import data_utils as DU
+            from utils.distributions import NormalDistribution
+            from model_executors import base_executor as BE
+
+            # ---- nDgrid (stn_spline.py:70-91)
+            out["ndgrid_5x5"] = np.asarray(STN.nDgrid([5, 5]))
+            out["ndgrid_3x4_unnorm"] = np.asarray(STN.nDgrid([3, 4], normalise=False))
+            out["ndgrid_3x4_center"] = np.asarray(STN.nDgrid([3, 4], center=True))
+
+            # ---- interpolate_spline (interpolate_spline.py:212-278), the layer's usage: b=1, n=25, d=k=2, order 2
+            cp = np.asarray(STN.nDgrid([5, 5]), np.float64)
+            q = np.asarray(STN.nDgrid([9, 7]), np.float64)
+            theta = rs.normal(size=(3, 25, 2)) * 0.08
+            res = [np.asarray(ISP.interpolate_spline(t(cp), t(cp + theta[b:b + 1]), t(q), 2)) for b in range(3)]
+            out["spline_cp"], out["spline_q"], out["spline_theta"] = cp, q, theta
+            out["spline_order2"] = np.concatenate(res, 0)
+            w, v = ISP._solve_interpolation(t(cp), t(cp + theta[0:1]), 2, 0.0)
+            out["spline_order2_w0"], out["spline_order2_v0"] = np.asarray(w), np.asarray(v)
+            # general scattered points, other orders, regularisation, batch > 1, k = 3
+            tp = rs.uniform(size=(2, 11, 2))
+            tv = rs.normal(size=(2, 11, 3))
+            qq = rs.uniform(size=(2, 17, 2))
+            out["spline_tp"], out["spline_tv"], out["spline_qq"] = tp, tv, qq
+            out["spline_order1"] = np.asarray(ISP.interpolate_spline(t(tp), t(tv), t(qq), 1))
+            out["spline_order4_reg"] = np.asarray(ISP.interpolate_spline(t(tp), t(tv), t(qq), 4, regularization_weight=0.01))
+            out["spline_order2_reg"] = np.asarray(ISP.interpolate_spline(t(tp), t(tv), t(qq), 2, regularization_weight=0.003))
+            out["spline_order3"] = np.asarray(ISP.interpolate_spline(t(tp), t(tv), t(qq), 3))
+            # float32 run of the layer usage (what TF would execute)
+            out["spline_order2_f32"] = np.concatenate(
+                [np.asarray(ISP.interpolate_spline(t(cp, np.float32), t((cp + theta[b:b + 1]), np.float32), t(q, np.float32), 2))
+                 for b in range(3)], 0)
+
+            # ---- ThinPlateSpline2D (stn_spline.py:14-67), inverse False and True
+            vol = rs.uniform(size=(3, 9, 7, 4))
+            for inv in (False, True):
+                layer = STN.ThinPlateSpline2D((9, 7), [5, 5], 4, inverse=inv)
+                layer.build(None)
+                warped = np.asarray(layer.call([t(vol), t(theta)]))
+                locs = np.stack([np.asarray(layer.interpolate_spline_batch(t(theta[b])))[0] for b in range(3)], 0)
+                out["tps_warped_inv%d" % inv] = warped
+                out["tps_locs_inv%d" % inv] = locs
+            out["tps_vol"] = vol
+
+            # ---- FiLM / SPADE_COND / resize_like / Rounding
+            x = rs.normal(size=(2, 6, 5, 8))
+            g, b_ = rs.normal(size=(2, 8)), rs.normal(size=(2, 8))
+            out["film_x"], out["film_gamma"], out["film_beta"] = x, g, b_
+            out["film_y"] = np.asarray(FILM.FiLM().call([t(x), t(g), t(b_)]))
+            gg, bb = rs.normal(size=x.shape), rs.normal(size=x.shape)
+            out["spade_gamma"], out["spade_beta"] = gg, bb
+            out["spade_y"] = np.asarray(SPADE.SPADE_COND().call([t(x), t(gg), t(bb)]))
+            big = rs.normal(size=(2, 12, 8, 3))
+            out["resize_in"] = big
+            out["resize_6x4"] = np.asarray(SPADE.resize_like(t(big), t(np.zeros((2, 6, 4, 1)))))
+            out["resize_3x2"] = np.asarray(SPADE.resize_like(t(big), t(np.zeros((2, 3, 2, 1)))))
+            rx = np.concatenate([rs.uniform(size=40), [0.5, 1.5, 2.5, -0.5, 0.49999997, 0.50000006]]).astype(np.float32)
+            out["round_x"] = rx
+            out["round_y"] = np.asarray(RND.roundWithGrad(t(rx)))
+
+            # ---- losses (costs.py)
+            logits = rs.normal(size=(3, 8, 6, 5))
+            pred = np.exp(logits) / np.exp(logits).sum(-1, keepdims=True)
+            lab = rs.randint(0, 5, size=(3, 8, 6))
+            true5 = np.eye(5)[lab]
+            out["loss_pred"], out["loss_true"] = pred, true5
+            out["dice_fnc4"] = np.asarray(COSTS.make_dice_loss_fnc(4)(t(true5), t(pred)))
+            out["dice_perbatch4"] = np.asarray(COSTS.dice_coef_perbatch(t(true5[..., :4]), t(pred[..., :4])))
+            # keras calls loss(y_true, y_pred); combined_dice_bce forwards them in that order into
+            # weighted_cross_entropy_loss(y_pred, y_true) -- the swapped-argument quirk (costs.py:70,134)
+            out["wbce_as_called"] = np.asarray(COSTS.weighted_cross_entropy_loss(t(true5), t(pred)))
+            out["combined_dice_bce4"] = np.asarray(COSTS.make_combined_dice_bce(4)(t(true5), t(pred)))
+            out["combined_perbatch4"] = np.asarray(COSTS.make_combined_dice_bce_perbatch(4)(t(true5[..., :4]), t(logits[..., :4])))
+            mu, lv = rs.normal(size=(4, 8)), rs.normal(size=(4, 8)) * 0.3
+            out["kl_mu"], out["kl_lv"] = mu, lv
+            out["kl"] = np.asarray(COSTS.kl([t(mu), t(lv)]))
+            out["ypred"] = np.asarray(COSTS.ypred(None, t(mu)))
+            out["dice_metric"] = np.asarray(COSTS.dice(true5[..., :4], pred))
+            out["dice_metric_bin"] = np.asarray(COSTS.dice(true5[..., :4], pred, binarise=True))
+
+            # ---- VAE sampling (sdnet_utils.py:9-21); the noise comes from the shim's seeded generator
+            tf_shim.RNG["rng"] = np.random.RandomState(7)
+            out["sampling_z"] = np.asarray(SDU.sampling([t(mu), t(lv)]))
+            out["sampling_eps"] = np.random.RandomState(7).normal(0.0, 1.0, (4, 8))
+
+            # ---- Spectral regulariser (spectralnorm.py:199-246)
+            np.random.seed(11)
+            reg = SN.Spectral(4 * 4 * 3, 10.)
+            out["spectral_u0"] = np.asarray(reg.u).copy()
+            Wk = rs.normal(size=(4, 4, 3, 7)) * 0.2
+            out["spectral_W"] = Wk
+            out["spectral_loss"] = np.asarray(reg(t(Wk))).reshape(())
+
+            # ---- host-side helpers of the step
+            img = rs.normal(size=(2, 8, 8, 1))
+            out["rescale_in"] = img
+            out["rescale_out"] = DU.rescale(img.copy(), -1, 1)
+            out["rescale_const"] = DU.rescale(np.full((1, 4, 4, 1), 3.0), -1, 1)
+            out["sample_seed5"] = DU.sample(np.arange(20).reshape(10, 2), 4, seed=5)
+            m4 = (rs.uniform(size=(2, 6, 6, 4)) > 0.8).astype(np.float64)
+            out["residual_in"] = m4
+            out["residual_out"] = BE.Executor.add_residual(None, m4)
+            al = BE.Executor.align_batches(None, [np.arange(10.).reshape(5, 2), np.arange(6.).reshape(3, 2)])
+            out["align_0"], out["align_1"] = al[0], al[1]
+            np.random.seed(3)
+            out["normal_dist_seed3"] = NormalDistribution().sample((3, 8))
+        finally:
+            pass
+    path = os.path.join(HERE, "golden_ref.npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024.0))
+
+
+if __name__ == "__main__":
+    main()
