@@ -204,6 +204,16 @@ int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias,
 /* dw[KH,KW,Cin,Cout] (HWIO f32) += x (*) dy ; db[Cout] += sum_pixels dy (db may be NULL) */
 int dafk_conv_nc_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float* dw, float* db, int N,
                        int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream);
+/* Space-to-depth (2x2 pixel blocks -> 4C channels, bf16 out, zero beyond odd sizes), its inverse, and the matching
+ * rearrangement of an HWIO kernel [KH,KW,C,Cout] -> [ceil(KH/2),ceil(KW/2),4C,Cout] (backward != 0: accumulate the
+ * rearranged gradient w2 back into w).  conv(x, w, stride 2, valid) == conv(s2d(x), s2d(w), stride 1, valid):
+ * the stride-2 narrow layers (model_components/modality_encoder.py:36-42, models/discriminator.py:24) run on
+ * dafk_conv_nc_* this way. */
+int dafk_space_to_depth2(const void* x, int x_dt, void* y_bf16, int N, int H, int W, int C, void* stream);
+int dafk_depth_to_space2(const void* y, int y_dt, void* x, int x_dt, int N, int H, int W, int C,
+                         void* stream);
+int dafk_conv_s2d_weights(float* w, float* w2, int KH, int KW, int C, int Cout, int backward,
+                          void* stream);
 /* out[c] += sum_m x[m,c]   (bias gradients); x is f32 or bf16 */
 int dafk_colsum(const void* x, int x_dt, float* out, int64_t M, int C, void* stream);
 
@@ -331,6 +341,13 @@ int dafk_spectral_reg(const float* W, const float* u0, float alpha, float* loss,
 int dafk_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, int64_t n,
                    float lr_t, float beta1, float beta2, float eps, float grad_scale,
                    void* stream);
+/* Same update with the schedule kept on the device (CUDA-graph capturable optimizer step):
+ * state[0] = t, state[1] = lr_t.  dafk_adam_tick advances t and recomputes lr_t (in double);
+ * dafk_adam_step_dev reads lr_t = state[1]. */
+int dafk_adam_tick(float* state, float lr, float beta1, float beta2, void* stream);
+int dafk_adam_step_dev(float* p, const float* g, float* m, float* v, void* bf16_shadow, int64_t n,
+                       const float* state, float beta1, float beta2, float eps, float grad_scale,
+                       void* stream);
 
 /* ------------------------------------------------------------------ instance norm + SPADE
  * keras_contrib InstanceNormalization(axis=None, scale=False, center=False) layers/spade.py:27:

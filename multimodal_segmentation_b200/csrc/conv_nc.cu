@@ -104,7 +104,7 @@ __device__ __forceinline__ float nc_act(float z, int act, float alpha) {
   return z;
 }
 
-constexpr int NC_PROD = 128;     // producer threads (warps 0..3)
+constexpr int NC_PROD = 256;     // producer threads (warps 0..7)
 constexpr int NC_U = 8;          // image rows in flight per producer thread
 
 // Stage `rows` image rows [iy0, iy0+rows) of image n into the raster planes.  Unit of work = (pixel, channel
@@ -123,7 +123,10 @@ __device__ __forceinline__ void nc_stage_rows(const T* __restrict__ src, uint8_t
   const int units_row = wcols * groups;
   const int gshift = (groups & (groups - 1)) == 0 ? 31 - __clz(groups) : -1;
   const T* img = src + (int64_t)n * Himg * wcols * C;
-  for (int r0 = 0; r0 < rows; r0 += NC_U) {
+  const int nbatch = (rows + NC_U - 1) / NC_U;
+  const int rpb = (rows + nbatch - 1) / nbatch;      // rows per batch (<= NC_U), evenly split
+  for (int r0 = 0; r0 < rows; r0 += rpb) {
+    const int rend = min(rows, r0 + rpb);
     for (int u = ptid; u < units_row; u += nthr) {
       int cg, px;
       if (gshift >= 0) { cg = u & (groups - 1); px = u >> gshift; }
@@ -134,7 +137,7 @@ __device__ __forceinline__ void nc_stage_rows(const T* __restrict__ src, uint8_t
 #pragma unroll
       for (int k = 0; k < NC_U; ++k) {
         const int iy = iy0 + r0 + k;
-        if (r0 + k < rows && iy >= 0 && iy < Himg) {
+        if (r0 + k < rend && iy >= 0 && iy < Himg) {
           nc_load8<T>(p0 + (int64_t)iy * wcols * C, nvalid, vec, v[k]);
         } else {
 #pragma unroll
@@ -144,7 +147,7 @@ __device__ __forceinline__ void nc_stage_rows(const T* __restrict__ src, uint8_t
       uint8_t* dst = planes + ((size_t)cg * plane_pos + (size_t)r0 * P + col0 + px) * 16;
 #pragma unroll
       for (int k = 0; k < NC_U; ++k) {
-        if (r0 + k < rows) {
+        if (r0 + k < rend) {
           *reinterpret_cast<uint4*>(dst + (size_t)k * P * 16) = nc_pack8(v[k]);
           if (BSUM) {
 #pragma unroll
@@ -158,12 +161,13 @@ __device__ __forceinline__ void nc_stage_rows(const T* __restrict__ src, uint8_t
 
 // ---------------------------------------------------------------------------------------------
 // forward / stride-1 data gradient.  Warp-specialised persistent CTA (one per SM):
-//   warps 0-3  producers : global -> bf16 raster planes of stage s           (full[s] / empty[s] ring)
-//   warp  4    MMA issuer: per 128-position tile E/2 tcgen05.mma into one of two TMEM buffers
-//   warps 5-8  epilogue  : TMEM -> registers -> bias/activation -> global    (tfull[b] / tempty[b])
+//   warps 0-7  producers : global -> bf16 raster planes of stage s           (full[s] / empty[s] ring)
+//   warp  8    MMA issuer: per 128-position tile E/2 tcgen05.mma into one of two TMEM buffers
+//   warps 9-12 epilogue  : TMEM -> registers -> bias/activation -> global    (tfull[b] / tempty[b])
 // smem: [wp: E*Npad*16][S stages x CG*plane*16][descA: E/2 u64][descB: E/2 u64][bias: Npad f32][barriers]
 // ---------------------------------------------------------------------------------------------
-constexpr int NC_FWD_THREADS = 288;
+constexpr int NC_FWD_THREADS = NC_PROD + 32 + 128;
+constexpr int NC_MMA_WARP = NC_PROD / 32;
 constexpr int NC_MAX_STAGES = 4;
 
 template <typename TX>
@@ -213,14 +217,14 @@ __global__ void __launch_bounds__(NC_FWD_THREADS, 1) conv_nc_fwd_kernel(NcFwdP p
     for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 128); }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  if (warp == NC_MMA_WARP) tmem_alloc(tmem_slot, 512);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < NC_MMA_WARP) {
     // ===================== producers =====================
     float dummy[8];
     int it = 0;
@@ -232,11 +236,11 @@ __global__ void __launch_bounds__(NC_FWD_THREADS, 1) conv_nc_fwd_kernel(NcFwdP p
       mbar_wait(empty + st, ph ^ 1u);
       if (!(p.dbg & 4))
       nc_stage_rows<TX, false>(x, s_x + (size_t)st * st_bytes, p.plane, n, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P,
-                               p.pad, tid, NC_PROD, dummy);
+                                 p.pad, tid, NC_PROD, dummy);
       fence_proxy_async();
       mbar_arrive(full + st);
     }
-  } else if (warp == 4) {
+  } else if (warp == NC_MMA_WARP) {
     // ===================== MMA issuer =====================
     // warp-uniform control flow (all lanes walk the loops, one elected lane issues) keeps the operands in
     // uniform registers; the (tap, group) descriptor pairs come from the table built above
@@ -292,53 +296,60 @@ __global__ void __launch_bounds__(NC_FWD_THREADS, 1) conv_nc_fwd_kernel(NcFwdP p
         mbar_wait(tfull + b, (uint32_t)(gc >> 1) & 1u);
         tc_fence_after();
         const int gt = min(p.G, tiles_here - t0);
-        for (int tt = 0; tt < gt; ++tt) {
-          const int m = (t0 + tt) * 128 + q4 * 32 + lane;
-          const int orow = (int)__umulhi((uint32_t)m, magicP);
-          const int ocol = m - orow * p.P;
-          const bool live = orow < rows_here && ocol < p.Wo;
-          const int64_t obase = (((int64_t)n * p.Ho + y0 + orow) * p.Wo + ocol) * p.Cout;
-          const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * 256 + tt * p.Npad);
-          if (p.dbg & 2) continue;
+        const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * 256);
+        // TMEM loads are issued EB tiles ahead of their use (one wait per batch instead of one per tile)
+        constexpr int EB = 4;
+        for (int tb = 0; tb < gt; tb += EB) {
           for (int c0 = 0; c0 < p.Cout; c0 += 8) {
-            uint32_t v[8];
-            tmem_ld8(taddr + (uint32_t)c0, v);
+            uint32_t v[EB][8];
+#pragma unroll
+            for (int e = 0; e < EB; ++e)
+              if (tb + e < gt) tmem_ld8(tbase + (uint32_t)((tb + e) * p.Npad + c0), v[e]);
             tmem_ld_wait();
-            if (live) {
-              float f[8];
-              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0);
-              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + bb[j];
-              if (p.act == DAFK_ACT_LRELU) {
+            for (int e = 0; e < EB; ++e) {
+              if (tb + e < gt) {
+                const int m = (t0 + tb + e) * 128 + q4 * 32 + lane;
+                const int orow = (int)__umulhi((uint32_t)m, magicP);
+                const int ocol = m - orow * p.P;
+                if (orow < rows_here && ocol < p.Wo) {
+                  const int64_t obase = (((int64_t)n * p.Ho + y0 + orow) * p.Wo + ocol) * p.Cout;
+                  float f[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = f[j] > 0.f ? f[j] : p.alpha * f[j];
-              } else if (p.act == DAFK_ACT_RELU) {
+                  for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[e][j]) + bb[j];
+                  if (p.act == DAFK_ACT_LRELU) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-              } else if (p.act == DAFK_ACT_TANH) {
+                    for (int j = 0; j < 8; ++j) f[j] = f[j] > 0.f ? f[j] : p.alpha * f[j];
+                  } else if (p.act == DAFK_ACT_RELU) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = tanhf(f[j]);
-              }
-              if (p.y_dt == DAFK_F32) {
-                float* o = reinterpret_cast<float*>(y) + obase + c0;
-                if ((p.Cout & 3) == 0) {
-                  *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-                  if (c0 + 4 < p.Cout) *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                } else {
+                    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                  } else if (p.act == DAFK_ACT_TANH) {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    if (c0 + j < p.Cout) o[j] = f[j];
-                }
-              } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + obase + c0;
-                if ((p.Cout & 7) == 0) {
-                  *reinterpret_cast<uint4*>(o) = nc_pack8(f);
-                } else {
+                    for (int j = 0; j < 8; ++j) f[j] = tanhf(f[j]);
+                  }
+                  if (p.y_dt == DAFK_F32) {
+                    float* o = reinterpret_cast<float*>(y) + obase + c0;
+                    if ((p.Cout & 3) == 0) {
+                      *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+                      if (c0 + 4 < p.Cout) *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                    } else {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    if (c0 + j < p.Cout) o[j] = __float2bfloat16_rn(f[j]);
+                      for (int j = 0; j < 8; ++j)
+                        if (c0 + j < p.Cout) o[j] = f[j];
+                    }
+                  } else {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + obase + c0;
+                    if ((p.Cout & 7) == 0) {
+                      *reinterpret_cast<uint4*>(o) = nc_pack8(f);
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < 8; ++j)
+                        if (c0 + j < p.Cout) o[j] = __float2bfloat16_rn(f[j]);
+                    }
+                  }
                 }
               }
             }
@@ -351,7 +362,7 @@ __global__ void __launch_bounds__(NC_FWD_THREADS, 1) conv_nc_fwd_kernel(NcFwdP p
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NC_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -359,12 +370,12 @@ __global__ void __launch_bounds__(NC_FWD_THREADS, 1) conv_nc_fwd_kernel(NcFwdP p
 
 // ---------------------------------------------------------------------------------------------
 // weight gradient (+ bias gradient).  Warp-specialised persistent CTA:
-//   warps 0-3 producers: X rows and dY rows of a strip -> raster planes of stage s;   warp 4: MMA issuer.
+//   warps 0-7 producers: X rows and dY rows of a strip -> raster planes of stage s;   warp 8: MMA issuer.
 //   The KH*CG accumulators [64 x N8] stay in TMEM over all strips of the CTA; the producers drain them at
 //   the end with fp32 atomics into the HWIO gradient.
 // smem: [S stages x (CG*planeX + COG*planeY)*16][bsum scratch: 128*8 f32][barriers]
 // ---------------------------------------------------------------------------------------------
-constexpr int NC_WG_THREADS = 160;
+constexpr int NC_WG_THREADS = NC_PROD + 32;
 
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p, const TX* __restrict__ x,
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
     mbar_init(done, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == NC_MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -397,7 +408,7 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
   const bool any = (int)blockIdx.x < p.total_strips;
   const int nthr_y = (NC_PROD / p.COG) * p.COG;
 
-  if (warp < 4) {
+  if (warp < NC_MMA_WARP) {
     float bsum[8], dummy[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
@@ -422,7 +433,7 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
       if (db != nullptr) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) s_bsum[tid * 8 + c] = tid < nthr_y ? bsum[c] : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NC_PROD) : "memory");
         if (tid < p.Cout) {
           const int cog = tid >> 3, c = tid & 7;
           float acc = 0.f;
@@ -432,6 +443,7 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
       }
       mbar_wait(done, 0);
       tc_fence_after();
+      if (warp < 4) {
       // accumulator a = (r, cg) holds rows i = q*8 + c (tap q of filter row r, channel cg*8+c), columns = co.
       // M = 64 accumulators keep rows 16*j .. 16*j+15 in TMEM lanes 32*j .. 32*j+15.
       const int q4 = warp & 3;
@@ -453,6 +465,7 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
               if (c0 + j < p.Cout) atomicAdd(o + j, __uint_as_float(v[j]));
           }
         }
+      }
       }
     }
   } else {
@@ -495,7 +508,7 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NC_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -619,13 +632,19 @@ static bool nc_wg_geom(NcWgP& p, size_t& smem) {
   return true;
 }
 
+// opt every kernel instantiation in to the full 227 KB of dynamic shared memory once (not a stream operation, so it is
+// done at the first launch and never again -- later launches may be inside a CUDA-graph capture)
 template <typename K>
 static int nc_set_smem(K kernel, size_t smem, const char* name) {
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "%s: cudaFuncSetAttribute(%zu bytes) failed: %s", name, smem,
-                 cudaGetErrorString(e));
-  }
+  static const void* done[16];
+  static int ndone = 0;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < ndone; ++i)
+    if (done[i] == key) return DAFK_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "%s: cudaFuncSetAttribute(%zu bytes) failed: %s", name, smem,
+               cudaGetErrorString(e));
+  if (ndone < 16) done[ndone++] = key;
   return DAFK_OK;
 }
 

@@ -8,8 +8,10 @@ constexpr int OT = 256;
 
 __global__ void __launch_bounds__(OT) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                   float* __restrict__ m, float* __restrict__ v,
-                                                  __nv_bfloat16* __restrict__ shadow, int64_t n, float lr_t, float b1,
-                                                  float b2, float eps, float gscale) {
+                                                  __nv_bfloat16* __restrict__ shadow, int64_t n, float lr_host,
+                                                  const float* __restrict__ lr_dev, float b1, float b2, float eps,
+                                                  float gscale) {
+  const float lr_t = lr_dev != nullptr ? __ldg(lr_dev) : lr_host;
   int64_t n4 = n >> 2;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -40,6 +42,14 @@ __global__ void __launch_bounds__(OT) adam_kernel(float* __restrict__ p, const f
     p[t] = pk; m[t] = mk; v[t] = vk;
     if (shadow) shadow[t] = __float2bfloat16_rn(pk);
   }
+}
+
+// state[0] = t (step count), state[1] = lr_t = lr*sqrt(1-b2^t)/(1-b1^t): the Keras schedule advanced on the device, so
+// that a whole optimizer step is CUDA-graph capturable (no host scalar changes between replays)
+__global__ void adam_tick_kernel(float* state, float lr, float b1, float b2) {
+  const double t = (double)state[0] + 1.0;
+  state[0] = (float)t;
+  state[1] = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
 }
 
 // ---------------------------------------------------------------- Spectral
@@ -115,8 +125,27 @@ int dafk_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shad
                    DAFK_ALIGNED16(bf16_shadow),
                DAFK_ERR_ALIGN, "dafk_adam_step: pointers must be 16-byte aligned");
   adam_kernel<<<bw_grid((n + 3) / 4, OT), OT, 0, as_stream(stream)>>>(p, g, m, v, (__nv_bfloat16*)bf16_shadow, n, lr_t,
-                                                                     beta1, beta2, eps, grad_scale);
+                                                                     nullptr, beta1, beta2, eps, grad_scale);
   return check_launch("dafk_adam_step");
+}
+
+int dafk_adam_tick(float* state, float lr, float beta1, float beta2, void* stream) {
+  DAFK_REQUIRE(state != nullptr, DAFK_ERR_BAD_ARG, "dafk_adam_tick: null pointer");
+  adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(state, lr, beta1, beta2);
+  return check_launch("dafk_adam_tick");
+}
+
+int dafk_adam_step_dev(float* p, const float* g, float* m, float* v, void* bf16_shadow, int64_t n,
+                       const float* state, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  DAFK_REQUIRE(n >= 0, DAFK_ERR_BAD_ARG, "dafk_adam_step_dev: negative size");
+  if (n == 0) return DAFK_OK;
+  DAFK_REQUIRE(p && g && m && v && state, DAFK_ERR_BAD_ARG, "dafk_adam_step_dev: null pointer");
+  DAFK_REQUIRE(DAFK_ALIGNED16(p) && DAFK_ALIGNED16(g) && DAFK_ALIGNED16(m) && DAFK_ALIGNED16(v) &&
+                   DAFK_ALIGNED16(bf16_shadow),
+               DAFK_ERR_ALIGN, "dafk_adam_step_dev: pointers must be 16-byte aligned");
+  adam_kernel<<<bw_grid((n + 3) / 4, OT), OT, 0, as_stream(stream)>>>(p, g, m, v, (__nv_bfloat16*)bf16_shadow, n, 0.f,
+                                                                     state + 1, beta1, beta2, eps, grad_scale);
+  return check_launch("dafk_adam_step_dev");
 }
 
 int dafk_spectral_reg(const float* W, const float* u0, float alpha, float* loss, float* dW, float* ws, int dim,

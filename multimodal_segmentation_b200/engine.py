@@ -186,6 +186,7 @@ class Adam:
         if self.m is None:
             self.m = [ops.zeros(b - a) for _, a, b in self.ranges]
             self.v = [ops.zeros(b - a) for _, a, b in self.ranges]
+            self.sched = ops.zeros(4)       # [t, lr_t] kept on the device: the step is CUDA-graph capturable
 
     def zero_grad(self):
         for arena, a, b in self.ranges:
@@ -197,9 +198,9 @@ class Adam:
     def step(self, grad_scale=1.0):
         self._state()
         self.t += 1
-        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        ops.adam_tick(self.sched, self.lr, self.b1, self.b2)     # t <- t+1; lr_t = lr*sqrt(1-b2^t)/(1-b1^t)
         for (arena, a, b), m, v in zip(self.ranges, self.m, self.v):
-            ops.adam_step(arena.flat[a:b], arena.gflat[a:b], m, v, None, lr_t, self.b1, self.b2, self.eps, grad_scale)
+            ops.adam_step_dev(arena.flat[a:b], arena.gflat[a:b], m, v, None, self.sched, self.b1, self.b2, self.eps, grad_scale)
             arena.version += 1
 
 
@@ -255,6 +256,7 @@ class Conv2D:
         self.bias = arena.add(name + "/bias", (cout,), np.zeros(cout, np.float32)) if use_bias else None
         self._packed = None          # (arena version, wp_fwd, wp_dgrad)
         self._packed_nc = None
+        self._packed_s2d = None
 
     def params(self):
         return [self.kernel] + ([self.bias] if self.bias is not None else [])
@@ -267,16 +269,18 @@ class Conv2D:
         return self.stride == 1 or (self.stride == 2 and self.k % 2 == 0 and self.pad == 0)
 
     def packed(self):
-        """bf16 operand copies of the kernel: forward layout + data-gradient layout(s), refreshed after
-        every optimizer step that touched the arena"""
+        """bf16 operand copies of the kernel: forward layout + data-gradient layout(s), refreshed IN PLACE after every
+        optimizer step that touched the arena (persistent buffers keep a captured CUDA graph valid)"""
         ver = self.kernel.arena.version
         if self._packed is None or self._packed[0] != ver:
             w = self.kernel.data
+            old = self._packed
             if self.stride == 1:
-                d = ops.pack_conv(w, 1)
+                d = ops.pack_conv(w, 1, out=None if old is None else old[2])
             else:
-                d = {(pa, pb): ops.pack_conv(w, 2, pa, pb) for pa in (0, 1) for pb in (0, 1)}
-            self._packed = (ver, ops.pack_conv(w, 0), d)
+                d = {(pa, pb): ops.pack_conv(w, 2, pa, pb, out=None if old is None else old[2][(pa, pb)])
+                     for pa in (0, 1) for pb in (0, 1)}
+            self._packed = (ver, ops.pack_conv(w, 0, out=None if old is None else old[1]), d)
         return self._packed[1], self._packed[2]
 
     def _tc_dgrad(self, g, x_shape, c, off, out_dtype, wp_d):
@@ -305,11 +309,71 @@ class Conv2D:
         """bf16 operands of the narrow-channel tcgen05 kernels (forward + stride-1 data gradient)"""
         ver = self.kernel.arena.version
         if self._packed_nc is None or self._packed_nc[0] != ver:
-            self._packed_nc = (ver, ops.pack_conv_nc(self.kernel.data, 0), ops.pack_conv_nc(self.kernel.data, 1))
+            old = self._packed_nc
+            self._packed_nc = (ver, ops.pack_conv_nc(self.kernel.data, 0, out=None if old is None else old[1]),
+                               ops.pack_conv_nc(self.kernel.data, 1, out=None if old is None else old[2]))
         return self._packed_nc[1], self._packed_nc[2]
+
+    def packed_s2d(self):
+        """stride-2 layer as a stride-1 layer over 2x2 pixel blocks: rearranged kernel, packed for the raster-strip
+        tcgen05 kernels (forward + data gradient)"""
+        ver = self.kernel.arena.version
+        if self._packed_s2d is None or self._packed_s2d[0] != ver:
+            old = self._packed_s2d
+            w2 = ops.conv_s2d_weights(self.kernel.data, out=None if old is None else old[3])
+            self._packed_s2d = (ver, ops.pack_conv_nc(w2, 0, out=None if old is None else old[1]),
+                                ops.pack_conv_nc(w2, 1, out=None if old is None else old[2]), w2)
+        return self._packed_s2d[1], self._packed_s2d[2]
+
+    def s2d_eligible(self, srcs):
+        """valid stride-2 convolution whose space-to-depth form (4*Cin channels, ceil(k/2) taps) fits conv_nc"""
+        if not (USE_TC and self.stride == 2 and self.pad == 0):
+            return False
+        H, W = srcs[0].shape[1], srcs[0].shape[2]
+        k2 = (self.k + 1) // 2
+        H2, W2 = (H + 1) // 2, (W + 1) // 2
+        if H2 - k2 + 1 != (H - self.k) // 2 + 1 or W2 - k2 + 1 != (W - self.k) // 2 + 1:
+            return False
+        c4 = 4 * self.cin
+        return all(ops.nc_supported(c4, self.cout, k2, k2, W2, 0, kind) for kind in (0, 1, 2))
+
+    def _call_s2d(self, ctx, srcs, act, alpha):
+        code = ACT[act]
+        xin = srcs[0] if len(srcs) == 1 else concat(ctx, [s if s.data.dtype == torch.float32 else
+                                                          _cast_var(ctx, s, torch.float32) for s in srcs])
+        N, H, W, C = xin.shape
+        k2 = (self.k + 1) // 2
+        x2 = ops.space_to_depth2(xin.data)
+        bias = self.bias.data if self.bias is not None else None
+        y = Var(ops.conv_nc_fwd(x2, self.packed_s2d()[0], bias, self.cout, k2, k2, 0, code, alpha))
+        if ctx.rec(xin, self.kernel):
+            y.requires_grad = True
+
+            def bw():
+                g = y.grad
+                y.grad = None
+                if g is None:
+                    return
+                if g.dtype != torch.float32:
+                    g = ops.cast(g, torch.float32)
+                if code != ACT_NONE:
+                    g = ops.act_bwd(g, y.data, code, alpha)
+                if self.kernel.requires_grad:
+                    db = self.bias.grad if (self.bias is not None and self.bias.requires_grad) else None
+                    dw2 = ops.zeros(k2, k2, 4 * C, self.cout)
+                    ops.conv_nc_wgrad(x2, g, dw2, db, 0)
+                    ops.conv_s2d_weights_bwd_(self.kernel.grad, dw2)
+                if xin.requires_grad:
+                    dx2 = ops.conv_nc_fwd(g, self.packed_s2d()[1], None, 4 * C, k2, k2, k2 - 1, out_dtype=torch.bfloat16)
+                    accumulate(xin, ops.depth_to_space2(dx2, H, W, xin.grad_dtype))
+
+            ctx.tape.record(bw)
+        return y
 
     # ---- narrow layers: raster-strip tcgen05 kernels (stride 1) or the CUDA-core kernels (fp32)
     def _call_generic(self, ctx, srcs, act, alpha):
+        if self.s2d_eligible(srcs):
+            return self._call_s2d(ctx, srcs, act, alpha)
         code = ACT[act]
         W = srcs[0].shape[2]
         nc = self.stride == 1 and USE_TC

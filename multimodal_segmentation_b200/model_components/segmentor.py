@@ -20,7 +20,7 @@ def build(conf):
         l = c1(ctx, x)
         l = b1(ctx, l, "relu", E.feat_dtype())
         l = c2(ctx, l)
-        l = b2(ctx, l, "relu", torch.float32)
+        l = b2(ctx, l, "relu", E.feat_dtype())
         return E.softmax(ctx, head(ctx, l))
 
     shp = tuple(conf.anatomy_encoder.output_shape)

@@ -40,6 +40,10 @@ class DAFNetExecutor(Executor):
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._pending = []
+        self._graph = None
+        self._static = None
+        self._graph_pending = []
+        self._next = None
 
     # ------------------------------------------------------------------ data
     def init_train_data(self):
@@ -173,6 +177,15 @@ class DAFNetExecutor(Executor):
         """dafnet_executor.py:369-387"""
         if self.conf.automatedpairing:
             raise NotImplementedError("automated pairing is a 'next' row (SURVEY.md 8f-1)")
+        if self._graph is not None:
+            # the snapshots of the previous replay must be read before they are overwritten
+            self.flush_losses(epoch_loss)
+            step = self._next if self._next is not None else self.stage_step_inputs()
+            self.train_batch_graph(step)
+            # prefetch: gather the next batches into pinned memory and enqueue their H2D copies while the GPU is
+            # busy with the replay that was just launched
+            self._next = self.stage_step_inputs()
+            return
         if self.conf.l_mix > 0:
             self.train_supervised_expert_pairing(epoch_loss)
             self.train_batch_mask_discriminator(epoch_loss)
@@ -214,10 +227,61 @@ class DAFNetExecutor(Executor):
 
     def train_batch_on(self, step):
         """train_batch on pre-staged (HBM-resident) inputs"""
+        if self._graph is not None:
+            return self.train_batch_graph(step)
         for kind, g, dm, di in step:
             self._run_generator(kind == "sup", g)
             self._run_mask_d(dm)
             self._run_image_d(di)
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def enable_cuda_graph(self, warmup=2):
+        """Capture one whole train_batch (every kernel of the generator update, the two mask-discriminator updates
+        and the two image-discriminator updates, ~3000 launches) into ONE CUDA graph that reads its inputs from
+        static device buffers.  A step is then: H2D of the new batch -> copy into the static buffers -> one graph
+        launch.  Everything the step needs between replays lives on the device (Adam step count / lr_t, BatchNorm
+        moving statistics, packed bf16 weight copies, loss slots)."""
+        assert self._graph is None
+        self._static = self.stage_step_inputs()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):          # steady state: allocator warm, weights packed, attributes set
+                self._pending = []
+                for kind, g, dm, di in self._static:
+                    self._run_generator(kind == "sup", g)
+                    self._run_mask_d(dm)
+                    self._run_image_d(di)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._pending = []
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for kind, g, dm, di in self._static:
+                self._run_generator(kind == "sup", g)
+                self._run_mask_d(dm)
+                self._run_image_d(di)
+        self._graph_pending = list(self._pending)     # loss snapshots live in the graph's memory pool
+        self._pending = []
+        self._graph = graph
+        return graph
+
+    def train_batch_graph(self, step):
+        if step is not self._static:
+            same = all(tuple(a.shape) == tuple(b.shape)
+                       for (_, g, dm, di), (_, sg, sdm, sdi) in zip(step, self._static)
+                       for a, b in zip(list(g) + list(dm) + list(di), list(sg) + list(sdm) + list(sdi)))
+            if not same:          # ragged last batch of an epoch: run this one step eagerly
+                graph, self._graph = self._graph, None
+                try:
+                    return self.train_batch_on(step)
+                finally:
+                    self._graph = graph
+            for (_, g, dm, di), (_, sg, sdm, sdi) in zip(step, self._static):
+                for src, dst in zip(list(g) + list(dm) + list(di), list(sg) + list(sdm) + list(sdi)):
+                    dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        self._pending = list(self._graph_pending)
 
     def train_supervised_expert_pairing(self, epoch_loss):
         """dafnet_executor.py:389-411"""

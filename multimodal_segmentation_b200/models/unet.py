@@ -108,7 +108,6 @@ class UNetUp:
         n = len(self.ups)
         for j, (u, b) in enumerate(zip(self.ups, self.blocks)):
             up = u(ctx, l)
-            last = j == n - 1
-            # the last block feeds the 1x1 conv_anatomy on the CUDA-core path -> keep fp32
-            l = b(ctx, [up, skips[n - 1 - j]], out_dtype=torch.float32 if last else None)
+            # every block (the last one feeds the 1x1 conv_anatomy on the raster-strip tcgen05 kernel) stores bf16
+            l = b(ctx, [up, skips[n - 1 - j]])
         return l

@@ -378,7 +378,7 @@ def conv3x3_tc_fwd(x0, x1, wp, bias, Cout, out_dtype=torch.float32, row_off=0):
     return y
 
 
-def pack_conv(w_hwio, mode, pa=0, pb=0):
+def pack_conv(w_hwio, mode, pa=0, pb=0, out=None):
     """mode 0: [taps][Cout][Cin] forward; 1: mirrored [taps][Cin][Cout] (stride-1 dgrad);
     2: stride-2 dgrad parity class (pa,pb): [(KH/2)(KW/2)][Cin][Cout]"""
     _chk(w_hwio)
@@ -389,7 +389,7 @@ def pack_conv(w_hwio, mode, pa=0, pb=0):
         shape = (KH * KW, Cin, Cout)
     else:
         shape = ((KH // 2) * (KW // 2), Cin, Cout)
-    wp = torch.empty(shape, dtype=torch.bfloat16, device=w_hwio.device)
+    wp = torch.empty(shape, dtype=torch.bfloat16, device=w_hwio.device) if out is None else out
     call("pack_conv", w_hwio, wp, KH, KW, Cin, Cout, mode, pa, pb, _S())
     return wp
 
@@ -448,13 +448,13 @@ def nc_supported(Cin, Cout, KH, KW, W, pad, kind):
     return bool(f(Cin, Cout, KH, KW, W, pad, kind))
 
 
-def pack_conv_nc(w_hwio, mode):
+def pack_conv_nc(w_hwio, mode, out=None):
     """mode 0: forward operand; mode 1: stride-1 data-gradient operand (mirrored taps, transposed channels)"""
     _chk(w_hwio)
     KH, KW, Cin, Cout = w_hwio.shape
     ck, nk = (Cin, Cout) if mode == 0 else (Cout, Cin)
     n = _lib.lib().fn["dafk_conv_nc_packed_elems"](ck, nk, KH, KW)
-    wp = torch.empty(n, dtype=torch.bfloat16, device=w_hwio.device)
+    wp = torch.empty(n, dtype=torch.bfloat16, device=w_hwio.device) if out is None else out
     call("pack_conv_nc", w_hwio, wp, KH, KW, Cin, Cout, mode, _S())
     return wp
 
@@ -482,6 +482,39 @@ def conv_nc_wgrad(x, dy, dw, db, pad):
     nb = x.numel() * x.element_size() + dy.numel() * dy.element_size()
     instrument.timed("conv_nc_wgrad (tcgen05)", fl, nb,
                      lambda: call("conv_nc_wgrad", x, _dt(x), dy, _dt(dy), dw, db, N, H, W, Cin, Cout, KH, KW, pad, _S()))
+
+
+def space_to_depth2(x):
+    """[N,H,W,C] -> bf16 [N,ceil(H/2),ceil(W/2),4C] (zero beyond odd sizes)"""
+    _chk(x)
+    N, H, W, C = x.shape
+    y = torch.empty((N, (H + 1) // 2, (W + 1) // 2, 4 * C), dtype=torch.bfloat16, device=x.device)
+    call("space_to_depth2", x, _dt(x), y, N, H, W, C, _S())
+    return y
+
+
+def depth_to_space2(y, H, W, out_dtype=torch.float32):
+    _chk(y)
+    N, _, _, C4 = y.shape
+    x = torch.empty((N, H, W, C4 // 4), dtype=out_dtype, device=y.device)
+    call("depth_to_space2", y, _dt(y), x, _dt(x), N, H, W, C4 // 4, _S())
+    return x
+
+
+def conv_s2d_weights(w, out=None):
+    """HWIO [KH,KW,C,Co] -> [ceil(KH/2),ceil(KW/2),4C,Co]"""
+    _chk(w)
+    KH, KW, C, Co = w.shape
+    w2 = torch.empty(((KH + 1) // 2, (KW + 1) // 2, 4 * C, Co), dtype=torch.float32, device=w.device) if out is None else out
+    call("conv_s2d_weights", w, w2, KH, KW, C, Co, 0, _S())
+    return w2
+
+
+def conv_s2d_weights_bwd_(dw, dw2):
+    """dw += rearranged^T(dw2)"""
+    _chk(dw, dw2)
+    KH, KW, C, Co = dw.shape
+    call("conv_s2d_weights", dw, dw2, KH, KW, C, Co, 1, _S())
 
 
 # ---------------------------------------------------------------------------- dense
@@ -627,6 +660,16 @@ def spectral_reg(W2d, u0, alpha, loss, dW):
 def adam_step(p, g, m, v, shadow, lr_t, b1=0.9, b2=0.999, eps=1e-7, grad_scale=1.0):
     _chk(p, g, m, v)
     call("adam_step", p, g, m, v, shadow, p.numel(), float(lr_t), float(b1), float(b2), float(eps), float(grad_scale), _S())
+
+
+def adam_tick(state, lr, b1=0.9, b2=0.999):
+    _chk(state)
+    call("adam_tick", state, float(lr), float(b1), float(b2), _S())
+
+
+def adam_step_dev(p, g, m, v, shadow, state, b1=0.9, b2=0.999, eps=1e-7, grad_scale=1.0):
+    _chk(p, g, m, v, state)
+    call("adam_step_dev", p, g, m, v, shadow, p.numel(), state, float(b1), float(b2), float(eps), float(grad_scale), _S())
 
 
 # ---------------------------------------------------------------------------- SPADE / balancer

@@ -91,9 +91,9 @@ def conv(W, name, x, stride=1, padding="valid"):
     if _tc_eligible(w, stride, padding):
         y = R.conv2d(_RoundBF16.apply(x), _RoundBF16.apply(w), W.get(name + "/bias"), stride, padding)
         return _RoundGradBF16.apply(y)      # the gradient w.r.t. the conv output is consumed as bf16
-    if BF16_EMULATION and stride == 1:
-        # narrow stride-1 layers run on the raster-strip tcgen05 kernels (csrc/conv_nc.cu): operands and the
-        # incoming output gradient are rounded to bf16 while they are staged; the data gradient stays fp32
+    if BF16_EMULATION and (stride == 1 or padding == "valid"):
+        # narrow layers run on the raster-strip tcgen05 kernels (csrc/conv_nc.cu; stride-2 valid layers through
+        # space-to-depth): operands and the incoming output gradient are rounded to bf16 while they are staged
         y = R.conv2d(_RoundFwdBF16.apply(x), _RoundFwdBF16.apply(w), W.get(name + "/bias"), stride, padding)
         return _RoundGradBF16.apply(y)
     return R.conv2d(x, w, W.get(name + "/bias"), stride, padding)
@@ -134,7 +134,7 @@ def anatomy_encoder(W, x, st, down_prefix, up_prefix, downsample=4, rounding=Tru
     for i in reversed(range(downsample)):
         up = upsample_block(W, "%su%d_up" % (up_prefix, i), l, st)
         l = torch.cat([up, skips[i]], -1)              # Concatenate()([l, self.d_l3]) unet.py:68
-        l = conv_block(W, "%su%d" % (up_prefix, i), l, st, last_fp32=(i == 0))
+        l = conv_block(W, "%su%d" % (up_prefix, i), l, st)      # with BF16_EMULATION every block stores bf16
     a = R.softmax(conv(W, "conv_anatomy", l, 1, "same"))
     return R.rounding(a) if rounding else a
 
@@ -142,7 +142,7 @@ def anatomy_encoder(W, x, st, down_prefix, up_prefix, downsample=4, rounding=Tru
 def segmentor(W, s, st):
     """model_components/segmentor.py:9-29"""
     l = feat(R.relu(bn(W, "seg_bn1", conv(W, "seg_conv1", s, 1, "same"), st)))
-    l = R.relu(bn(W, "seg_bn2", conv(W, "seg_conv2", l, 1, "same"), st))
+    l = feat(R.relu(bn(W, "seg_bn2", conv(W, "seg_conv2", l, 1, "same"), st)))
     return R.softmax(conv(W, "seg_out", l, 1, "same"))
 
 

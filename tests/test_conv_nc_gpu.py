@@ -117,3 +117,49 @@ def test_conv_nc_vs_fp32_oracle_tolerance(ops):
     yr = _ref_conv(x, w, None, 1).numpy()
     y = ops.conv_nc_fwd(gpu(x), ops.pack_conv_nc(gpu(w), 0), None, 8, 3, 3, 1)
     assert rel_l2(cpu(y), yr) < 1e-2
+
+
+# ------------------------------------------------------------------ stride-2 valid layers through space-to-depth
+S2_CASES = [
+    # N, H, W, Cin, Cout, k     (models/discriminator.py:24 first layer; model_components/modality_encoder.py:36-42)
+    (2, 32, 32, 1, 64, 4),
+    (2, 32, 40, 4, 64, 4),
+    (2, 32, 32, 9, 16, 3),
+    (2, 31, 31, 16, 32, 3),      # odd input size: zero-padded 2x2 blocks
+    (3, 27, 27, 32, 64, 3),
+]
+
+
+@pytest.mark.parametrize("case", S2_CASES)
+def test_stride2_conv_through_space_to_depth(ops, case):
+    from multimodal_segmentation_b200 import engine as E
+    N, H, W, Cin, Cout, k = case
+    r = np.random.RandomState(sum(case))
+    x = bf16_round(r.normal(size=(N, H, W, Cin)).astype(np.float32))
+    w = bf16_round((r.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(np.float32))
+    b = r.normal(size=Cout).astype(np.float32)
+    xt, wt = t(x, torch.float64, grad=True), t(w, torch.float64, grad=True)
+    yr = R.leaky_relu(R.conv2d(xt, wt, t(b, torch.float64), 2, "valid"), 0.3)
+    dy = bf16_round(r.normal(size=tuple(yr.shape)).astype(np.float32))
+    (yr * t(dy, torch.float64)).sum().backward()
+    E.USE_TC = True
+    arena = E.Arena(True)
+    conv = E.Conv2D(arena, r, "c", Cin, Cout, k, 2, "valid")
+    arena.to_device()
+    conv.kernel.data.copy_(gpu(w))
+    conv.bias.data.copy_(gpu(b))
+    tape = E.Tape()
+    ctx = E.Ctx(tape, True)
+    xv = E.Var(gpu(x), True)
+    # 4*32 input channels x 64 outputs x 2 filter rows of accumulators exceed the 512 TMEM columns of the weight
+    # gradient: that layer stays on the CUDA-core kernels (and must still be right)
+    assert conv.s2d_eligible([xv]) == (Cin * 4 * Cout * ((k + 1) // 2) <= 512 * 8)
+    y = conv(ctx, xv, "lrelu", 0.3)
+    assert tuple(y.shape) == tuple(yr.shape)
+    assert rel_l2(cpu(y.data), yr.detach().numpy()) < 1e-4
+    y.grad = gpu(dy)
+    tape.backward()
+    # the product rounds dy * act'(y) to bf16 while it stages it: 5e-3 covers that rounding
+    assert rel_l2(cpu(xv.grad), xt.grad.numpy()) < 5e-3
+    assert rel_l2(cpu(conv.kernel.grad), wt.grad.numpy()) < 5e-3
+    assert rel_l2(cpu(conv.bias.grad), (dy * (yr.detach().numpy() > 0) + 0.3 * dy * (yr.detach().numpy() < 0)).sum((0, 1, 2))) < 5e-3
