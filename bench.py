@@ -270,9 +270,18 @@ def run_b200(args):
                "h2d_bytes_per_step": int(ex.h2d_bytes / args.steps), "d2h_bytes_per_step": int(ex.d2h_bytes / args.steps),
                "last_loss": float(np.mean(losses["loss"][-1:])) if losses["loss"] else None}
 
-    if rank != 0:
+    def finish():
+        """multi-rank teardown: a captured CUDA graph that contains NCCL collectives makes
+        destroy_process_group() hang, so every rank leaves through a barrier and a hard exit"""
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     peaks = {}
@@ -298,7 +307,7 @@ def run_b200(args):
                                     "GB/s": (v["bytes"] / (v["ms"] / 1000.0) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
                                 for k, v in kern.items()}}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only
         dtc, threads = cpu_train_batch_seconds(conf, args.cpu_batch)
         cpu = {"value": args.cpu_batch / dtc, "unit": "slices/s", "cores": threads, "kind": "port",
                "sample": "one train_batch on %d pairs (%.1f s); CPU restatement of the reference graph (torch-CPU fp32), "
@@ -318,8 +327,7 @@ def run_b200(args):
         "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
