@@ -165,6 +165,7 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from multimodal_segmentation_b200 import _lib, engine as E, ops

@@ -14,6 +14,9 @@
 //     both operands are the same 128-pixel boxes used as MN-major UMMA operands (the reduction
 //     runs over pixels), split-K over pixel tiles, fp32 atomics into the HWIO gradient.
 #include "tc_ptx.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace dafk {
 
@@ -194,6 +197,212 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// "haloed-tile" forward / dgrad kernel for stride-1 convolutions.  The kernel above fetches the activation tile
+// once PER FILTER TAP (9 shifted TMA boxes for a 3x3) and is bound by the L2 -> SM bandwidth (~12 TB/s): 2 operand
+// bytes per MAC-row.  Here a CTA loads ONE haloed activation tile per 64-channel block -- (TH+KH-1) x (TWo+KW-1)
+// pixels x TN images, 128 B per pixel, 128B-swizzled by TMA -- and every tap reads it in place: the GEMM M index is
+// the raster position inside the haloed tile, so tap (r,q) is the same shared memory with the operand descriptor
+// started (r*P + q) rows later (a start that is 128-byte but not 1024-byte aligned; the 128B swizzle is a function of the
+// absolute shared-memory address, so TMA's write pattern and the MMA's read pattern agree without a base_offset).
+// G = ceil(positions / 128) accumulators share every weight tile.  Outputs on halo columns are computed and
+// dropped.  Activation traffic falls by the number of taps, weight traffic by G.
+//   warp 0: TMA producer (A ring: one box per channel block; B ring: one weight tile per tap)
+//   warp 1: MMA issuer    warps 2-5: epilogue (TMEM double-buffered over tiles)
+// ---------------------------------------------------------------------------------------------
+struct HaloGeom {
+  int TWo, TH, TN;          // valid outputs per tile
+  int Pp, RS;               // haloed row pitch (TWo+KW-1) and rows (TH+KH-1)
+  int tiles_x, tiles_y, tiles_n;
+  int G;                    // accumulators (128 raster positions each)
+  int a_bytes;              // bytes of one A stage (box + slack for the shifted reads of the last accumulator)
+  int SA, SB;               // ring depths
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                                     const __grid_constant__ CUtensorMap tmA1,
+                                                                     const __grid_constant__ CUtensorMap tmB,
+                                                                     const float* __restrict__ bias, void* __restrict__ y,
+                                                                     int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1,
+                                                                     int KH, int KW, int pad, HaloGeom g, int n_blocks,
+                                                                     int w_rows_per_tap, int w_row_off, long long y_sn,
+                                                                     long long y_sy, long long y_sx, int total_tiles) {
+  constexpr int B_BYTES = BLOCK_N * KBLK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_a = smem;
+  uint8_t* s_b = smem + g.SA * g.a_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_b + g.SB * B_BYTES);
+  uint64_t* a_empty = a_full + 4;
+  uint64_t* b_full = a_empty + 4;
+  uint64_t* b_empty = b_full + 8;
+  uint64_t* tfull_bar = b_empty + 8;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int taps = KH * KW;
+  const int ncb = (C0 + C1) / KBLK;
+  const uint32_t tmem_cols = (uint32_t)(2 * g.G * BLOCK_N) <= 32u ? 32u : (uint32_t)(2 * g.G * BLOCK_N);   // power of two by construction
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (C1 > 0) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < g.SA; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < g.SB; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int ia = 0, ib = 0;
+      const uint32_t a_box_bytes = (uint32_t)(g.TN * g.RS * g.Pp * KBLK * 2);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nb = tile % n_blocks;
+        int mt = tile / n_blocks;
+        const int txi = mt % g.tiles_x; mt /= g.tiles_x;
+        const int tyi = mt % g.tiles_y; mt /= g.tiles_y;
+        const int x0 = txi * g.TWo, y0 = tyi * g.TH, img0 = mt * g.TN;
+        const int n0 = nb * BLOCK_N;
+        for (int cb = 0; cb < ncb; ++cb, ++ia) {
+          const bool first = cb * KBLK < C0;
+          const CUtensorMap* mA = first ? &tmA0 : &tmA1;
+          const int c_in_src = first ? cb * KBLK : cb * KBLK - C0;
+          const int sa = ia % g.SA;
+          mbar_wait(a_empty + sa, ((uint32_t)(ia / g.SA) & 1u) ^ 1u);
+          mbar_expect_tx(a_full + sa, a_box_bytes);
+          tma_load_4d(s_a + sa * g.a_bytes, mA, a_full + sa, c_in_src, x0 - pad, y0 - pad, img0);
+          for (int tap = 0; tap < taps; ++tap, ++ib) {
+            const int sb = ib % g.SB;
+            mbar_wait(b_empty + sb, ((uint32_t)(ib / g.SB) & 1u) ^ 1u);
+            mbar_expect_tx(b_full + sb, B_BYTES);
+            tma_load_2d(s_b + sb * B_BYTES, &tmB, b_full + sb, cb * KBLK, tap * w_rows_per_tap + w_row_off + n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
+    constexpr uint32_t idesc = make_idesc(TILE_PIX, BLOCK_N, 0, 0);
+    const uint32_t leader = elect_one();
+    const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b);
+    const int G = g.G, Pp = g.Pp, SA = g.SA, SB = g.SB, a_bytes = g.a_bytes;
+    int ia = 0, ib = 0, tc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+      const uint32_t buf = (uint32_t)tc & 1u;
+      mbar_wait(tempty_bar + buf, (((uint32_t)tc >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_col = tmem_acc + buf * (uint32_t)(G * BLOCK_N);
+      for (int cb = 0; cb < ncb; ++cb, ++ia) {
+        const int sa = ia % SA;
+        mbar_wait(a_full + sa, (uint32_t)(ia / SA) & 1u);
+        const uint32_t a_stage = a_base + (uint32_t)(sa * a_bytes);
+        for (int r = 0; r < KH; ++r) {
+          for (int q = 0; q < KW; ++q, ++ib) {
+            const int sb = ib % SB;
+            mbar_wait(b_full + sb, (uint32_t)(ib / SB) & 1u);
+            tc_fence_after();
+            if (leader) {
+              const uint64_t db = make_smem_desc(b_base + (uint32_t)(sb * B_BYTES), 16, 1024);
+              const uint32_t a_tap = a_stage + (uint32_t)((r * Pp + q) * 128);
+              for (int gi = 0; gi < G; ++gi) {
+                // rows gi*128 .. +127 of the raster, shifted by the tap: start is 128 B- but not 1024 B-aligned
+                // (measured: the 128B swizzle is a function of the absolute shared-memory address, so a window that
+                // starts in the middle of a swizzle atom needs no base_offset -- setting it breaks the result)
+                const uint64_t da = make_smem_desc(a_tap + (uint32_t)(gi * TILE_PIX * 128), 16, 1024);
+                const uint32_t d = d_col + (uint32_t)(gi * BLOCK_N);
+                const uint32_t acc0 = (cb > 0 || r > 0 || q > 0) ? 1u : 0u;
+#pragma unroll
+                for (int k = 0; k < KBLK / 16; ++k)
+                  umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (k > 0) ? 1u : acc0);
+              }
+              umma_commit(b_empty + sb);
+            }
+            __syncwarp();
+          }
+        }
+        if (leader) umma_commit(a_empty + sa);
+        __syncwarp();
+      }
+      if (leader) umma_commit(tfull_bar + buf);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q4 = warp & 3;
+    const int img_pos = g.RS * g.Pp;
+    int tc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+      const int nb = tile % n_blocks;
+      int mt = tile / n_blocks;
+      const int txi = mt % g.tiles_x; mt /= g.tiles_x;
+      const int tyi = mt % g.tiles_y; mt /= g.tiles_y;
+      const int x0 = txi * g.TWo, y0 = tyi * g.TH, img0 = mt * g.TN;
+      const int n0 = nb * BLOCK_N;
+      const uint32_t buf = (uint32_t)tc & 1u;
+      mbar_wait(tfull_bar + buf, ((uint32_t)tc >> 1) & 1u);
+      tc_fence_after();
+      for (int gi = 0; gi < g.G; ++gi) {
+        const int m = gi * TILE_PIX + q4 * 32 + lane;
+        const int tn = m / img_pos;
+        const int rem = m - tn * img_pos;
+        const int row = rem / g.Pp, col = rem - row * g.Pp;
+        const int px = x0 + col, py = y0 + row, img = img0 + tn;
+        const bool live = tn < g.TN && row < g.TH && col < g.TWo && px < Wo && py < Ho && img < N;
+        const int64_t obase = (int64_t)img * y_sn + (int64_t)py * y_sy + (int64_t)px * y_sx + n0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * (uint32_t)(g.G * BLOCK_N) + (uint32_t)(gi * BLOCK_N);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          tmem_ld16(taddr + (uint32_t)c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+          tmem_ld_wait();
+          if (live) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c + j) : 0.f);
+            if (y_dt == DAFK_F32) {
+              float* o = reinterpret_cast<float*>(y) + obase + c;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + obase + c;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * i], f[j + 2 * i + 1]);
+                  pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -457,6 +666,126 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
   return check_launch("dafk_conv_tc_fwd");
 }
 
+// ---- haloed-tile geometry.  Estimated cycles per valid output pixel and channel block (per SM):
+//   tensor: G * taps * 4 MMAs of max(N/2, 48) cycles;  L2: (A box + taps * weight tile) bytes at ~40 B/cycle/SM
+static double halo_cost(int N, int H, int W, int KH, int KW, int bn, int two, int th, int tn, int n_blocks, HaloGeom* out) {
+  const int Pp = two + KW - 1, RS = th + KH - 1;
+  if (Pp > 256 || RS > 256) return 1e30;
+  const int mpos = (tn - 1) * RS * Pp + th * Pp;
+  const int G = (mpos + 127) / 128;
+  int cols = 2 * G * bn;
+  if (cols > 512) return 1e30;
+  if (cols & (cols - 1)) return 1e30;           // TMEM allocations are powers of two
+  const int rows_read = G * 128 + (KH - 1) * Pp + KW;
+  const int box_rows = tn * RS * Pp;
+  int a_bytes = (rows_read > box_rows ? rows_read : box_rows) * 128;
+  a_bytes = (a_bytes + 1023) / 1024 * 1024;
+  const int b_bytes = bn * 128;
+  const int budget = 200 * 1024;
+  int SA = 2;
+  if (SA * a_bytes + 3 * b_bytes > budget) return 1e30;
+  int SB = (budget - SA * a_bytes) / b_bytes;
+  if (SB > 8) SB = 8;
+  const int taps = KH * KW;
+  const int64_t tx = (W + two - 1) / two, ty = (H + th - 1) / th, tnn = (N + tn - 1) / tn;
+  const int64_t tiles = tx * ty * tnn * n_blocks;
+  const int64_t rounds = (tiles + kNumSMs - 1) / kNumSMs;
+  const double mma = (double)G * taps * 4.0 * (bn / 2 > 48 ? bn / 2 : 48);
+  const double l2 = ((double)box_rows * 128.0 + (double)taps * b_bytes) / 40.0;
+  const double per_tile = (mma > l2 ? mma : l2) + 400.0;
+  const double cost = (double)rounds * kNumSMs * per_tile / ((double)N * H * W * n_blocks);
+  if (out) {
+    out->TWo = two; out->TH = th; out->TN = tn; out->Pp = Pp; out->RS = RS;
+    out->tiles_x = (int)tx; out->tiles_y = (int)ty; out->tiles_n = (int)tnn;
+    out->G = G; out->a_bytes = a_bytes; out->SA = SA; out->SB = SB;
+  }
+  return cost;
+}
+
+struct HaloKey {
+  int N, H, W, KH, KW, bn, nb;
+  bool operator<(const HaloKey& o) const {
+    return memcmp(this, &o, sizeof(HaloKey)) < 0;
+  }
+};
+
+static double pick_halo_geom(int N, int H, int W, int KH, int KW, int bn, int n_blocks, HaloGeom* best) {
+  // memoised: the search walks ~10^4 candidates, layers repeat every step
+  static std::mutex mu;
+  static std::map<HaloKey, std::pair<double, HaloGeom>> memo;
+  const HaloKey key{N, H, W, KH, KW, bn, n_blocks};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = memo.find(key);
+    if (it != memo.end()) { *best = it->second.second; return it->second.first; }
+  }
+  double best_cost = 1e30;
+  *best = HaloGeom{};
+  for (int two = (W < 254 ? W : 254); two >= 6; --two) {
+    // among tile widths that give the same number of tiles across, only the narrowest can win (fewer wasted columns)
+    if (two > 6 && (W + two - 2) / (two - 1) == (W + two - 1) / two) continue;
+    for (int th = 1; th <= H && th <= 64; ++th) {
+      const int tn_max = (two == W && th == H) ? 8 : 1;
+      for (int tn = 1; tn <= tn_max && tn <= N; tn *= 2) {
+        HaloGeom gcur;
+        const double c = halo_cost(N, H, W, KH, KW, bn, two, th, tn, n_blocks, &gcur);
+        if (c < best_cost) { best_cost = c; *best = gcur; }
+      }
+    }
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  memo[key] = std::make_pair(best_cost, *best);
+  return best_cost;
+}
+
+// the same estimate for the tap-by-tap kernel (one 128-pixel box + one weight tile per tap)
+static double tap_kernel_cost(int N, int H, int W, int KH, int KW, int bn, int n_blocks, const TileGeom& g) {
+  const int taps = KH * KW;
+  const int64_t tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n * n_blocks;
+  const int64_t rounds = (tiles + kNumSMs - 1) / kNumSMs;
+  const double mma = taps * 4.0 * (bn / 2 > 48 ? bn / 2 : 48);
+  const double l2 = (double)taps * (A_BYTES + bn * 128.0) / 40.0;
+  const double per_tile = (mma > l2 ? mma : l2) + 400.0;
+  return (double)rounds * kNumSMs * per_tile / ((double)N * H * W * n_blocks);
+}
+
+static int make_halo_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, const HaloGeom& g) {
+  PFN_encodeTiled enc = get_encode();
+  DAFK_REQUIRE(enc != nullptr, DAFK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)KBLK, (cuuint32_t)g.Pp, (cuuint32_t)g.RS, (cuuint32_t)g.TN};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DAFK_REQUIRE(r == CUDA_SUCCESS, DAFK_ERR_CUDA, "cuTensorMapEncodeTiled(haloed activation tile) failed with %d", (int)r);
+  return DAFK_OK;
+}
+
+template <int BLOCK_N>
+static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const float* bias, void* y,
+                       int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int pad,
+                       const HaloGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
+                       long long y_sx, cudaStream_t s) {
+  const int smem = g.SA * g.a_bytes + g.SB * BLOCK_N * KBLK * 2 + 1024 + 512;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_halo) failed: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int n_blocks = Cout / BLOCK_N;
+  const int64_t tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n * n_blocks;
+  DAFK_REQUIRE(tiles < (1LL << 31), DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd: too many tiles");
+  const int smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;      // one persistent CTA per SM
+  dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
+  conv_tc_halo_kernel<BLOCK_N><<<grid, TC_THREADS, smem_req, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW,
+                                                                 pad, g, n_blocks, w_rows_per_tap, w_row_off, y_sn, y_sy,
+                                                                 y_sx, (int)tiles);
+  return check_launch("dafk_conv_tc_fwd(halo)");
+}
+
 template <int BM, int BN, int STAGES>
 static int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mdy, float* dw, int Cin, int cin_off, int cin_total,
                         int Cout, int KH, int KW, int stride, int pad, const TileGeom& g, cudaStream_t s) {
@@ -511,6 +840,34 @@ int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void*
   cudaStream_t s = as_stream(stream);
   const int taps = KH * KW;
   const int64_t m_tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n;
+  // stride-1 layers: the haloed-tile kernel reads each activation pixel once per channel block instead of once per
+  // tap; take it when the estimate says so (DAFK_CONV_HALO=0/1 forces the choice, for the tests and benchmarks)
+  if (stride == 1 && H == Ho + KH - 1 - 2 * pad && W == Wo + KW - 1 - 2 * pad && C0 % KBLK == 0) {
+    static int force = -2;
+    if (force == -2) { const char* e = getenv("DAFK_CONV_HALO"); force = e ? atoi(e) : -1; }
+    const int bn = Cout % 128 == 0 ? 128 : 64;
+    HaloGeom hg;
+    const double ch = pick_halo_geom(N, Ho, Wo, KH, KW, bn, Cout / bn, &hg);
+    double ct = tap_kernel_cost(N, Ho, Wo, KH, KW, bn, Cout / bn, g);
+    if (Cout % 256 == 0) { const double c256 = tap_kernel_cost(N, Ho, Wo, KH, KW, 256, Cout / 256, g); if (c256 < ct) ct = c256; }
+    // measured on B200 (profiles/r1_bench_tc.txt): the haloed tile wins for Cout in {64, 128} (weight tiles are small,
+    // the tap-by-tap kernel is L2-bound on the activations); with Cout >= 256 the 128 x 256 tap-by-tap tiles win
+    (void)ct;
+    const bool prefer_halo = Cout < 256;
+    if (ch < 1e29 && force != 0 && (force == 1 || prefer_halo)) {
+      CUtensorMap h0, h1;
+      rc = make_halo_map(&h0, x0, N, H, W, C0, hg);
+      if (rc) return rc;
+      if (C1 > 0) { rc = make_halo_map(&h1, x1, N, H, W, C1, hg); if (rc) return rc; } else h1 = h0;
+      rc = make_w_map(&b, wp, taps * w_rows_per_tap, C0 + C1, bn);
+      if (rc) return rc;
+      if (bn == 128)
+        return launch_halo<128>(h0, h1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, hg, w_rows_per_tap, w_row_off,
+                                y_sn, y_sy, y_sx, s);
+      return launch_halo<64>(h0, h1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, hg, w_rows_per_tap, w_row_off,
+                             y_sn, y_sy, y_sx, s);
+    }
+  }
   if (Cout % 256 == 0) {
     // 128 x 256 tiles read 1.5 operand bytes per MAC-row instead of 2 (the 128 x 128 kernel is L2-bound), but
     // halve the number of tiles: take them when the round-robin tail does not eat the gain
