@@ -107,25 +107,26 @@ int dafk_max_bwd(const float* a, const float* b, const float* dout, float* da, f
 /* ------------------------------------------------------------------ BatchNormalization
  * utils/model_utils.py:10, model_components/segmentor.py:17,20  (Keras defaults:
  * eps 1e-3, momentum .99, biased batch variance in training).
- * stats: acc[0:C] += sum_x, acc[C:2C] += sum_x^2 (double; caller zeroes acc). */
-int dafk_bn_stats(const float* x, double* acc, int64_t M, int C, void* stream);
+ * stats: acc[0:C] += sum_x, acc[C:2C] += sum_x^2 (double; caller zeroes acc).
+ * x (the convolution output) is f32 or bf16 (x_dt): the tensor-core convolutions store it as bf16. */
+int dafk_bn_stats(const void* x, int x_dt, double* acc, int64_t M, int C, void* stream);
 /* mean/rstd from acc; moving <- moving*momentum + batch*(1-momentum) when moving_* != NULL */
 int dafk_bn_finalize(const double* acc, int64_t M, int C, float eps, float momentum, float* mean,
                      float* rstd, float* moving_mean, float* moving_var, void* stream);
 /* rstd = 1/sqrt(var+eps) for inference with the moving statistics */
 int dafk_bn_rstd_from_var(const float* var, float* rstd, int C, float eps, void* stream);
 /* out = act((x-mean)*rstd*gamma+beta); out dtype f32 or bf16; act in {NONE, RELU} */
-int dafk_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma,
+int dafk_bn_apply(const void* x, int x_dt, const float* mean, const float* rstd, const float* gamma,
                   const float* beta, void* out, int out_dt, int64_t M, int C, int act,
                   void* stream);
 /* backward, pass 1: acc[0:C] += sum dz, acc[C:2C] += sum dz*xhat, dz = dout*act'(z) */
-int dafk_bn_bwd_reduce(const void* dout, int dout_dt, const float* x, const float* mean,
+int dafk_bn_bwd_reduce(const void* dout, int dout_dt, const void* x, int x_dt, const float* mean,
                        const float* rstd, const float* gamma, const float* beta, double* acc,
                        int64_t M, int C, int act, void* stream);
 /* backward, pass 2: dx = gamma*rstd*(dz - acc0/M - xhat*acc1/M); dgamma += acc1; dbeta += acc0
  * (dgamma/dbeta may be NULL for frozen layers).  dx dtype f32 or bf16.
  * dbias_prev (may be NULL): += sum_pixels dx, the bias gradient of the convolution feeding this BN. */
-int dafk_bn_bwd_apply(const void* dout, int dout_dt, const float* x, const float* mean,
+int dafk_bn_bwd_apply(const void* dout, int dout_dt, const void* x, int x_dt, const float* mean,
                       const float* rstd, const float* gamma, const float* beta, const double* acc,
                       void* dx, int dx_dt, float* dgamma, float* dbeta, float* dbias_prev, int64_t M,
                       int C, int act, void* stream);

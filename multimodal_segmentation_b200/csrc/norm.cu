@@ -15,15 +15,17 @@ static inline bool bn_channels_ok(int C) { return C >= 4 && C <= 1024 && (1024 %
 static inline int bn_grid(int64_t n4) { return bw_grid(n4, TPB, 8); }
 
 // ---------------------------------------------------------------- BN statistics
-__global__ void __launch_bounds__(TPB) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ acc,
+template <typename TX>
+__global__ void __launch_bounds__(TPB) bn_stats_kernel(const TX* __restrict__ x, double* __restrict__ acc,
                                                        int64_t n4, int C) {
   extern __shared__ float sm[];
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 v = ldg_stream4(x + 4 * i);
-    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-    q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+    float v[4];
+    Vec4<TX>::load(x + 4 * i, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s[k] += v[k]; q[k] += v[k] * v[k]; }
   }
   channel_reduce2<TPB>(s, q, C, sm, acc, acc + C);
 }
@@ -52,8 +54,8 @@ __global__ void bn_rstd_kernel(const float* __restrict__ var, float* __restrict_
 }
 
 // ---------------------------------------------------------------- BN apply
-template <typename TO>
-__global__ void __launch_bounds__(TPB) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+template <typename TX, typename TO>
+__global__ void __launch_bounds__(TPB) bn_apply_kernel(const TX* __restrict__ x, const float* __restrict__ mean,
                                                        const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, TO* __restrict__ out,
                                                        int64_t n4, int C, int act) {
@@ -63,8 +65,8 @@ __global__ void __launch_bounds__(TPB) bn_apply_kernel(const float* __restrict__
   for (int k = 0; k < 4; ++k) { mu[k] = mean[c0 + k]; rs[k] = rstd[c0 + k]; g[k] = gamma[c0 + k]; b[k] = beta[c0 + k]; }
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 t = ldg_stream4(x + 4 * i);
-    float v[4] = {t.x, t.y, t.z, t.w};
+    float v[4];
+    Vec4<TX>::load(x + 4 * i, v);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float z = (v[k] - mu[k]) * rs[k] * g[k] + b[k];
@@ -75,8 +77,8 @@ __global__ void __launch_bounds__(TPB) bn_apply_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------- BN backward
-template <typename TD>
-__global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const TD* __restrict__ dout, const float* __restrict__ x,
+template <typename TD, typename TX>
+__global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const TD* __restrict__ dout, const TX* __restrict__ x,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             double* __restrict__ acc, int64_t n4, int C, int act) {
@@ -88,8 +90,8 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const TD* __restrict
   float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 t = ldg_stream4(x + 4 * i);
-    float v[4] = {t.x, t.y, t.z, t.w};
+    float v[4];
+    Vec4<TX>::load(x + 4 * i, v);
     float d[4];
     Vec4<TD>::load(dout + 4 * i, d);
 #pragma unroll
@@ -104,8 +106,8 @@ __global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const TD* __restrict
   channel_reduce2<TPB>(s0, s1, C, sm, acc, acc + C);
 }
 
-template <typename TD, typename TO>
-__global__ void __launch_bounds__(TPB) bn_bwd_apply_kernel(const TD* __restrict__ dout, const float* __restrict__ x,
+template <typename TD, typename TX, typename TO>
+__global__ void __launch_bounds__(TPB) bn_bwd_apply_kernel(const TD* __restrict__ dout, const TX* __restrict__ x,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const double* __restrict__ acc, TO* __restrict__ dx,
@@ -131,8 +133,8 @@ __global__ void __launch_bounds__(TPB) bn_bwd_apply_kernel(const TD* __restrict_
   }
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 t = ldg_stream4(x + 4 * i);
-    float v[4] = {t.x, t.y, t.z, t.w};
+    float v[4];
+    Vec4<TX>::load(x + 4 * i, v);
     float d[4];
     Vec4<TD>::load(dout + 4 * i, d);
 #pragma unroll
@@ -360,14 +362,18 @@ using namespace dafk;
 
 extern "C" {
 
-int dafk_bn_stats(const float* x, double* acc, int64_t M, int C, void* stream) {
+int dafk_bn_stats(const void* x, int x_dt, double* acc, int64_t M, int C, void* stream) {
   DAFK_REQUIRE(M >= 0 && C > 0, DAFK_ERR_BAD_ARG, "dafk_bn_stats: bad shape");
   if (M == 0) return DAFK_OK;
   DAFK_REQUIRE(x && acc, DAFK_ERR_BAD_ARG, "dafk_bn_stats: null pointer");
   DAFK_REQUIRE(bn_channels_ok(C), DAFK_ERR_UNSUPPORTED, "dafk_bn_stats: C must be a power of two in [4,1024] (got %d)", C);
   DAFK_REQUIRE(DAFK_ALIGNED16(x), DAFK_ERR_ALIGN, "dafk_bn_stats: x must be 16-byte aligned");
   int64_t n4 = M * C / 4;
-  bn_stats_kernel<<<bn_grid(n4), TPB, 2 * C * sizeof(float), as_stream(stream)>>>(x, acc, n4, C);
+  if (x_dt == DAFK_F32)
+    bn_stats_kernel<float><<<bn_grid(n4), TPB, 2 * C * sizeof(float), as_stream(stream)>>>((const float*)x, acc, n4, C);
+  else if (x_dt == DAFK_BF16)
+    bn_stats_kernel<__nv_bfloat16><<<bn_grid(n4), TPB, 2 * C * sizeof(float), as_stream(stream)>>>((const __nv_bfloat16*)x, acc, n4, C);
+  else { set_error("dafk_bn_stats: bad dtype"); return DAFK_ERR_BAD_ARG; }
   return check_launch("dafk_bn_stats");
 }
 
@@ -385,7 +391,7 @@ int dafk_bn_rstd_from_var(const float* var, float* rstd, int C, float eps, void*
   return check_launch("dafk_bn_rstd_from_var");
 }
 
-int dafk_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+int dafk_bn_apply(const void* x, int x_dt, const float* mean, const float* rstd, const float* gamma, const float* beta,
                   void* out, int out_dt, int64_t M, int C, int act, void* stream) {
   DAFK_REQUIRE(M >= 0 && C > 0, DAFK_ERR_BAD_ARG, "dafk_bn_apply: bad shape");
   if (M == 0) return DAFK_OK;
@@ -396,14 +402,16 @@ int dafk_bn_apply(const float* x, const float* mean, const float* rstd, const fl
   int64_t n4 = M * C / 4;
   cudaStream_t s = as_stream(stream);
   if (out_dt == DAFK_F32)
-    bn_apply_kernel<float><<<bn_grid(n4), TPB, 0, s>>>(x, mean, rstd, gamma, beta, (float*)out, n4, C, act);
+    { if (x_dt == DAFK_BF16) bn_apply_kernel<__nv_bfloat16, float><<<bn_grid(n4), TPB, 0, s>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, (float*)out, n4, C, act);
+      else bn_apply_kernel<float, float><<<bn_grid(n4), TPB, 0, s>>>((const float*)x, mean, rstd, gamma, beta, (float*)out, n4, C, act); }
   else if (out_dt == DAFK_BF16)
-    bn_apply_kernel<__nv_bfloat16><<<bn_grid(n4), TPB, 0, s>>>(x, mean, rstd, gamma, beta, (__nv_bfloat16*)out, n4, C, act);
+    { if (x_dt == DAFK_BF16) bn_apply_kernel<__nv_bfloat16, __nv_bfloat16><<<bn_grid(n4), TPB, 0, s>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, (__nv_bfloat16*)out, n4, C, act);
+      else bn_apply_kernel<float, __nv_bfloat16><<<bn_grid(n4), TPB, 0, s>>>((const float*)x, mean, rstd, gamma, beta, (__nv_bfloat16*)out, n4, C, act); }
   else { set_error("dafk_bn_apply: bad out dtype %d", out_dt); return DAFK_ERR_BAD_ARG; }
   return check_launch("dafk_bn_apply");
 }
 
-int dafk_bn_bwd_reduce(const void* dout, int dout_dt, const float* x, const float* mean, const float* rstd,
+int dafk_bn_bwd_reduce(const void* dout, int dout_dt, const void* x, int x_dt, const float* mean, const float* rstd,
                        const float* gamma, const float* beta, double* acc, int64_t M, int C, int act, void* stream) {
   DAFK_REQUIRE(M >= 0 && C > 0, DAFK_ERR_BAD_ARG, "dafk_bn_bwd_reduce: bad shape");
   if (M == 0) return DAFK_OK;
@@ -414,14 +422,16 @@ int dafk_bn_bwd_reduce(const void* dout, int dout_dt, const float* x, const floa
   cudaStream_t s = as_stream(stream);
   size_t smem = 2 * C * sizeof(float);
   if (dout_dt == DAFK_F32)
-    bn_bwd_reduce_kernel<float><<<bn_grid(n4), TPB, smem, s>>>((const float*)dout, x, mean, rstd, gamma, beta, acc, n4, C, act);
+    { if (x_dt == DAFK_BF16) bn_bwd_reduce_kernel<float, __nv_bfloat16><<<bn_grid(n4), TPB, smem, s>>>((const float*)dout, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, acc, n4, C, act);
+      else bn_bwd_reduce_kernel<float, float><<<bn_grid(n4), TPB, smem, s>>>((const float*)dout, (const float*)x, mean, rstd, gamma, beta, acc, n4, C, act); }
   else if (dout_dt == DAFK_BF16)
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<bn_grid(n4), TPB, smem, s>>>((const __nv_bfloat16*)dout, x, mean, rstd, gamma, beta, acc, n4, C, act);
+    { if (x_dt == DAFK_BF16) bn_bwd_reduce_kernel<__nv_bfloat16, __nv_bfloat16><<<bn_grid(n4), TPB, smem, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, acc, n4, C, act);
+      else bn_bwd_reduce_kernel<__nv_bfloat16, float><<<bn_grid(n4), TPB, smem, s>>>((const __nv_bfloat16*)dout, (const float*)x, mean, rstd, gamma, beta, acc, n4, C, act); }
   else { set_error("dafk_bn_bwd_reduce: bad dtype"); return DAFK_ERR_BAD_ARG; }
   return check_launch("dafk_bn_bwd_reduce");
 }
 
-int dafk_bn_bwd_apply(const void* dout, int dout_dt, const float* x, const float* mean, const float* rstd,
+int dafk_bn_bwd_apply(const void* dout, int dout_dt, const void* x, int x_dt, const float* mean, const float* rstd,
                       const float* gamma, const float* beta, const double* acc, void* dx, int dx_dt, float* dgamma,
                       float* dbeta, float* dbias_prev, int64_t M, int C, int act, void* stream) {
   DAFK_REQUIRE(M >= 0 && C > 0, DAFK_ERR_BAD_ARG, "dafk_bn_bwd_apply: bad shape");
@@ -432,7 +442,15 @@ int dafk_bn_bwd_apply(const void* dout, int dout_dt, const float* x, const float
   int64_t n4 = M * C / 4;
   cudaStream_t s = as_stream(stream);
   int grid = bn_grid(n4);
-#define LAUNCH(TD, TO) bn_bwd_apply_kernel<TD, TO><<<grid, TPB, C * sizeof(float), s>>>((const TD*)dout, x, mean, rstd, gamma, beta, acc, (TO*)dx, dgamma, dbeta, dbias_prev, n4, M, C, act)
+#define LAUNCH(TD, TO)                                                                                                  \
+  do {                                                                                                                  \
+    if (x_dt == DAFK_BF16)                                                                                              \
+      bn_bwd_apply_kernel<TD, __nv_bfloat16, TO><<<grid, TPB, C * sizeof(float), s>>>(                                  \
+          (const TD*)dout, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, acc, (TO*)dx, dgamma, dbeta, dbias_prev, n4, M, C, act); \
+    else                                                                                                                \
+      bn_bwd_apply_kernel<TD, float, TO><<<grid, TPB, C * sizeof(float), s>>>(                                          \
+          (const TD*)dout, (const float*)x, mean, rstd, gamma, beta, acc, (TO*)dx, dgamma, dbeta, dbias_prev, n4, M, C, act); \
+  } while (0)
   if (dout_dt == DAFK_F32 && dx_dt == DAFK_F32) LAUNCH(float, float);
   else if (dout_dt == DAFK_F32 && dx_dt == DAFK_BF16) LAUNCH(float, __nv_bfloat16);
   else if (dout_dt == DAFK_BF16 && dx_dt == DAFK_F32) LAUNCH(__nv_bfloat16, float);

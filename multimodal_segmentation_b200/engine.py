@@ -25,6 +25,11 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH
 # Parity tests against the fp32 oracle at 1e-4 switch it off.
 USE_TC = True
 
+# Store the outputs of convolutions that feed a BatchNorm in the feature dtype (bf16 on the tensor-core path) instead of
+# fp32: halves the bytes of the largest tensors of the step (-3 % step time).  Costs one more bf16 rounding per layer
+# (what mixed-precision training does everywhere); tests/test_models_gpu.py bounds the effect with both settings.
+RAW_BF16 = True
+
 ACT = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU, "tanh": ACT_TANH}
 
 
@@ -298,12 +303,16 @@ class Conv2D:
             ops.conv_tc_fwd(g, None, wp, None, c, k // 2, k // 2, 1, k // 2 - 1, out_dtype, row_off=off, out=view)
         return dx
 
-    def __call__(self, ctx, x, act=None, alpha=0.0):
+    def __call__(self, ctx, x, act=None, alpha=0.0, out_dtype=None):
+        """out_dtype: storage of the convolution output.  The layers that feed a BatchNorm ask for the feature dtype
+        (bf16 on the tensor-core path): halves the bytes of the largest tensors of the step; the batch statistics are
+        then taken from exactly the values that get normalised."""
         srcs = list(x) if isinstance(x, (list, tuple)) else [x]
         assert sum(s.shape[-1] for s in srcs) == self.cin, (self.name, [tuple(s.shape) for s in srcs], self.cin)
+        od = torch.float32 if (out_dtype is None or not USE_TC or not RAW_BF16) else out_dtype
         if self.tc_eligible(srcs) and len(srcs) <= 2:
-            return self._call_tc(ctx, srcs, act, alpha)
-        return self._call_generic(ctx, srcs, act, alpha)
+            return self._call_tc(ctx, srcs, act, alpha, od)
+        return self._call_generic(ctx, srcs, act, alpha, od)
 
     def packed_nc(self):
         """bf16 operands of the narrow-channel tcgen05 kernels (forward + stride-1 data gradient)"""
@@ -371,7 +380,7 @@ class Conv2D:
         return y
 
     # ---- narrow layers: raster-strip tcgen05 kernels (stride 1) or the CUDA-core kernels (fp32)
-    def _call_generic(self, ctx, srcs, act, alpha):
+    def _call_generic(self, ctx, srcs, act, alpha, od=torch.float32):
         if self.s2d_eligible(srcs):
             return self._call_s2d(ctx, srcs, act, alpha)
         code = ACT[act]
@@ -387,7 +396,8 @@ class Conv2D:
             xin = f32srcs[0] if len(f32srcs) == 1 else concat(ctx, f32srcs)
         bias = self.bias.data if self.bias is not None else None
         if nc_f:
-            y = Var(ops.conv_nc_fwd(xin.data, self.packed_nc()[0], bias, self.cout, self.k, self.k, self.pad, code, alpha))
+            y = Var(ops.conv_nc_fwd(xin.data, self.packed_nc()[0], bias, self.cout, self.k, self.k, self.pad, code, alpha, od),
+                    grad_dtype=torch.float32)
         else:
             y = Var(ops.conv2d_fwd(xin.data, self.kernel.data, bias, self.stride, self.pad, code, alpha))
         if ctx.rec(xin, self.kernel):
@@ -421,14 +431,14 @@ class Conv2D:
         return y
 
     # ---- tcgen05 path (bf16 operands, fp32 accumulate in TMEM)
-    def _call_tc(self, ctx, srcs, act, alpha):
+    def _call_tc(self, ctx, srcs, act, alpha, od=torch.float32):
         bsrcs = [s if s.data.dtype == torch.bfloat16 else _cast_var(ctx, s, torch.bfloat16) for s in srcs]
         wp_f, wp_d = self.packed()
         bias = self.bias.data if self.bias is not None else None
         x0 = bsrcs[0]
         x1 = bsrcs[1] if len(bsrcs) > 1 else None
         raw = ops.conv_tc_fwd(x0.data, None if x1 is None else x1.data, wp_f, bias, self.cout, self.k, self.k,
-                              self.stride, self.pad, torch.float32)
+                              self.stride, self.pad, torch.float32 if ACT[act] != ACT_NONE else od)
         y = Var(raw, grad_dtype=torch.bfloat16)
         rec = ctx.rec(*bsrcs, self.kernel)
         if rec:
@@ -492,7 +502,6 @@ class BatchNorm:
 
     def __call__(self, ctx, x, act=None, out_dtype=torch.float32):
         code = ACT[act]
-        assert x.data.dtype == torch.float32
         if ctx.training:
             mean, rstd = ops.bn_stats_finalize(x.data, self.EPS, self.MOMENTUM, self.moving_mean.data, self.moving_var.data)
         else:

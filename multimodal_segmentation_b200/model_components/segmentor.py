@@ -17,9 +17,9 @@ def build(conf):
     head = E.Conv2D(a, r, "seg_out", 64, conf.num_masks + 1, 1, 1, "same")
 
     def fwd(ctx, x):
-        l = c1(ctx, x)
+        l = c1(ctx, x, out_dtype=E.feat_dtype())
         l = b1(ctx, l, "relu", E.feat_dtype())
-        l = c2(ctx, l)
+        l = c2(ctx, l, out_dtype=E.feat_dtype())
         l = b2(ctx, l, "relu", E.feat_dtype())
         return E.softmax(ctx, head(ctx, l))
 

@@ -34,9 +34,9 @@ class ConvBlock:
 
     def __call__(self, ctx, x, out_dtype=None):
         fd = E.feat_dtype()
-        l = self.c1(ctx, x)
+        l = self.c1(ctx, x, out_dtype=fd if self.n1 is not None else None)
         l = self.n1(ctx, l, "relu", fd) if self.n1 is not None else E.activation(ctx, l, "relu")
-        l = self.c2(ctx, l)
+        l = self.c2(ctx, l, out_dtype=fd if self.n2 is not None else None)
         od = fd if out_dtype is None else out_dtype
         return self.n2(ctx, l, "relu", od) if self.n2 is not None else E.activation(ctx, l, "relu")
 
@@ -54,7 +54,7 @@ class UpsampleBlock:
 
     def __call__(self, ctx, x):
         l = E.upsample2(ctx, x)
-        l = self.conv(ctx, l)
+        l = self.conv(ctx, l, out_dtype=E.feat_dtype() if self.norm is not None else None)
         return self.norm(ctx, l, None, E.feat_dtype()) if self.norm is not None else l
 
 

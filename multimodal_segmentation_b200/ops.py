@@ -190,7 +190,7 @@ def bn_stats_finalize(x, eps, momentum, moving_mean=None, moving_var=None):
     M = x.numel() // C
     acc = torch.empty(2 * C, dtype=torch.float64, device=x.device)
     zero_(acc)
-    instrument.timed("bn_stats", 0, 4.0 * x.numel(), lambda: call("bn_stats", x, acc, M, C, _S()))
+    instrument.timed("bn_stats", 0, float(x.element_size()) * x.numel(), lambda: call("bn_stats", x, _dt(x), acc, M, C, _S()))
     mean, rstd = f32(C), f32(C)
     call("bn_finalize", acc, M, C, float(eps), float(momentum), mean, rstd, moving_mean, moving_var, _S())
     return mean, rstd
@@ -206,8 +206,8 @@ def bn_apply(x, mean, rstd, gamma, beta, act=ACT_NONE, out_dtype=torch.float32):
     _chk(x)
     C = x.shape[-1]
     out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
-    instrument.timed("bn_apply", 0, 4.0 * x.numel() + out.numel() * out.element_size(),
-                     lambda: call("bn_apply", x, mean, rstd, gamma, beta, out, _dt(out), x.numel() // C, C, act, _S()))
+    instrument.timed("bn_apply", 0, float(x.element_size()) * x.numel() + out.numel() * out.element_size(),
+                     lambda: call("bn_apply", x, _dt(x), mean, rstd, gamma, beta, out, _dt(out), x.numel() // C, C, act, _S()))
     return out
 
 
@@ -218,12 +218,12 @@ def bn_bwd(dout, x, mean, rstd, gamma, beta, act, dgamma, dbeta, dx_dtype=torch.
     M = x.numel() // C
     acc = torch.empty(2 * C, dtype=torch.float64, device=x.device)
     zero_(acc)
-    nb_in = 4.0 * x.numel() + dout.numel() * dout.element_size()
+    nb_in = float(x.element_size()) * x.numel() + dout.numel() * dout.element_size()
     instrument.timed("bn_bwd_reduce", 0, nb_in,
-                     lambda: call("bn_bwd_reduce", dout, _dt(dout), x, mean, rstd, gamma, beta, acc, M, C, act, _S()))
+                     lambda: call("bn_bwd_reduce", dout, _dt(dout), x, _dt(x), mean, rstd, gamma, beta, acc, M, C, act, _S()))
     dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
     instrument.timed("bn_bwd_apply", 0, nb_in + dx.numel() * dx.element_size(),
-                     lambda: call("bn_bwd_apply", dout, _dt(dout), x, mean, rstd, gamma, beta, acc, dx, _dt(dx), dgamma,
+                     lambda: call("bn_bwd_apply", dout, _dt(dout), x, _dt(x), mean, rstd, gamma, beta, acc, dx, _dt(dx), dgamma,
                                   dbeta, dbias_prev, M, C, act, _S()))
     return dx
 

@@ -79,6 +79,12 @@ def feat(x):
     return _RoundBF16.apply(x) if BF16_EMULATION else x
 
 
+def raw(x):
+    """a convolution output that feeds a BatchNorm: stored as bf16 by the tensor-core convolutions (the batch statistics
+    are taken from the rounded values); its gradient comes out of the BatchNorm backward unrounded"""
+    return _RoundFwdBF16.apply(x) if BF16_EMULATION else x
+
+
 def _tc_eligible(w, stride, padding):
     """mirror of the product's eligibility rule (engine.Conv2D.tc_eligible)"""
     if not (BF16_EMULATION and w.shape[0] > 1 and w.shape[2] % 64 == 0 and w.shape[3] % 64 == 0):
@@ -111,14 +117,14 @@ def bn(W, name, x, st):
 
 def conv_block(W, name, x, st, last_fp32=False):
     """models/unet.py:94-101"""
-    l = feat(R.relu(bn(W, name + "_bn1", conv(W, name + "_conv1", x, 1, "same"), st)))
-    l = R.relu(bn(W, name + "_bn2", conv(W, name + "_conv2", l, 1, "same"), st))
+    l = feat(R.relu(bn(W, name + "_bn1", raw(conv(W, name + "_conv1", x, 1, "same")), st)))
+    l = R.relu(bn(W, name + "_bn2", raw(conv(W, name + "_conv2", l, 1, "same")), st))
     return l if last_fp32 else feat(l)
 
 
 def upsample_block(W, name, x, st):
     """utils/model_utils.py:15-22 with activation='linear'"""
-    return feat(bn(W, name + "_bn", conv(W, name + "_conv", R.upsample2(x), 1, "same"), st))
+    return feat(bn(W, name + "_bn", raw(conv(W, name + "_conv", R.upsample2(x), 1, "same")), st))
 
 
 def anatomy_encoder(W, x, st, down_prefix, up_prefix, downsample=4, rounding=True):
@@ -141,8 +147,8 @@ def anatomy_encoder(W, x, st, down_prefix, up_prefix, downsample=4, rounding=Tru
 
 def segmentor(W, s, st):
     """model_components/segmentor.py:9-29"""
-    l = feat(R.relu(bn(W, "seg_bn1", conv(W, "seg_conv1", s, 1, "same"), st)))
-    l = feat(R.relu(bn(W, "seg_bn2", conv(W, "seg_conv2", l, 1, "same"), st)))
+    l = feat(R.relu(bn(W, "seg_bn1", raw(conv(W, "seg_conv1", s, 1, "same")), st)))
+    l = feat(R.relu(bn(W, "seg_bn2", raw(conv(W, "seg_conv2", l, 1, "same")), st)))
     return R.softmax(conv(W, "seg_out", l, 1, "same"))
 
 
