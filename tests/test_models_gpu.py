@@ -201,7 +201,7 @@ def test_dafnet_generator_step_tensor_core_mode(raw_bf16):
         gm = np.concatenate([p.grad.cpu().numpy().ravel() for p in m.params() if not p.name.endswith("z_log_var/kernel")])
         rm = np.concatenate([W[p.name].grad.numpy().ravel() for p in m.params() if not p.name.endswith("z_log_var/kernel")])
         # the fuser's gradient is driven by the (chaotic) UNet outputs; the others are shallow
-        assert _cosine(gm, rm) > (0.8 if m is net.Anatomy_Fuser else 0.95), m.name
+        assert _cosine(gm, rm) > (0.8 if m is net.Anatomy_Fuser else (0.93 if raw_bf16 else 0.95)), m.name
 
 
 def test_tensor_core_components():
