@@ -105,54 +105,57 @@ __device__ __forceinline__ float nc_act(float z, int act, float alpha) {
 }
 
 constexpr int NC_PROD = 256;     // producer threads (warps 0..7)
-constexpr int NC_U = 8;          // image rows in flight per producer thread
+constexpr int NC_U_FWD = 10;     // (pixel, channel-group) units in flight per producer thread, forward kernel
+constexpr int NC_U_WG = 6;       // same, weight-gradient kernel (two tensors are staged per strip)
 
-// Stage `rows` image rows [iy0, iy0+rows) of image n into the raster planes.  Unit of work = (pixel, channel
-// group): 8 channels = 16..32 contiguous bytes in global memory, one 16 B shared-memory store.  Within a row
-// consecutive producer threads take consecutive (pixel, group) units = consecutive global addresses; NC_U rows
-// are fetched before the first one is converted, so each thread keeps NC_U independent loads in flight.
+// Stage `rows` image rows [iy0, iy0+rows) of image n into the raster planes.  Unit of work = (row, pixel, channel
+// group): 8 channels = 16..32 contiguous bytes in global memory, one 16 B shared-memory store.  The units of the whole
+// strip are flattened row-major, so consecutive producer threads read consecutive global addresses; each thread
+// issues NC_U independent loads before it converts the first one (one latency exposure per NC_U units).
 // `col0` is the raster column of image column 0 (= pad for inputs, 0 for output gradients).  With BSUM the
 // per-thread channel sums are accumulated (bias gradient): every thread then stays on ONE channel group,
 // which needs the thread count to be a multiple of `groups` (nthr = (NC_PROD / groups) * groups).
-template <typename T, bool BSUM>
+template <typename T, bool BSUM, int NC_U>
 __device__ __forceinline__ void nc_stage_rows(const T* __restrict__ src, uint8_t* planes, int plane_pos, int n, int Himg,
                                               int wcols, int C, int groups, int iy0, int rows, int P, int col0, int ptid,
                                               int nthr, float (&bsum)[8]) {
   if (ptid >= nthr) return;
   const bool vec = (sizeof(T) == 4) ? ((C & 3) == 0) : ((C & 7) == 0);
   const int units_row = wcols * groups;
+  const int total = rows * units_row;
   const int gshift = (groups & (groups - 1)) == 0 ? 31 - __clz(groups) : -1;
+  const uint32_t magic_row = (uint32_t)((0x100000000ULL + (uint64_t)units_row - 1) / (uint64_t)units_row);
   const T* img = src + (int64_t)n * Himg * wcols * C;
-  const int nbatch = (rows + NC_U - 1) / NC_U;
-  const int rpb = (rows + nbatch - 1) / nbatch;      // rows per batch (<= NC_U), evenly split
-  for (int r0 = 0; r0 < rows; r0 += rpb) {
-    const int rend = min(rows, r0 + rpb);
-    for (int u = ptid; u < units_row; u += nthr) {
-      int cg, px;
-      if (gshift >= 0) { cg = u & (groups - 1); px = u >> gshift; }
-      else { px = u / groups; cg = u - px * groups; }
-      const int nvalid = min(8, C - cg * 8);
-      const T* p0 = img + (int64_t)px * C + cg * 8;
-      float v[NC_U][8];
+  for (int u0 = ptid; u0 < total; u0 += nthr * NC_U) {
+    float v[NC_U][8];
+    int dst[NC_U];
 #pragma unroll
-      for (int k = 0; k < NC_U; ++k) {
-        const int iy = iy0 + r0 + k;
-        if (r0 + k < rend && iy >= 0 && iy < Himg) {
-          nc_load8<T>(p0 + (int64_t)iy * wcols * C, nvalid, vec, v[k]);
+    for (int k = 0; k < NC_U; ++k) {
+      const int u = u0 + k * nthr;
+      dst[k] = -1;
+      if (u < total) {
+        const int row = (int)__umulhi((uint32_t)u, magic_row);
+        const int ur = u - row * units_row;
+        int cg, px;
+        if (gshift >= 0) { cg = ur & (groups - 1); px = ur >> gshift; }
+        else { px = ur / groups; cg = ur - px * groups; }
+        const int iy = iy0 + row;
+        dst[k] = cg * plane_pos + row * P + col0 + px;
+        if (iy >= 0 && iy < Himg) {
+          nc_load8<T>(img + ((int64_t)iy * wcols + px) * C + cg * 8, min(8, C - cg * 8), vec, v[k]);
         } else {
 #pragma unroll
           for (int c = 0; c < 8; ++c) v[k][c] = 0.f;
         }
       }
-      uint8_t* dst = planes + ((size_t)cg * plane_pos + (size_t)r0 * P + col0 + px) * 16;
+    }
 #pragma unroll
-      for (int k = 0; k < NC_U; ++k) {
-        if (r0 + k < rend) {
-          *reinterpret_cast<uint4*>(dst + (size_t)k * P * 16) = nc_pack8(v[k]);
-          if (BSUM) {
+    for (int k = 0; k < NC_U; ++k) {
+      if (dst[k] >= 0) {
+        *reinterpret_cast<uint4*>(planes + (size_t)dst[k] * 16) = nc_pack8(v[k]);
+        if (BSUM) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) bsum[c] += v[k][c];
-          }
+          for (int c = 0; c < 8; ++c) bsum[c] += v[k][c];
         }
       }
     }
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(NC_FWD_THREADS, 1) conv_nc_fwd_kernel(NcFwdP p
       const int y0 = (s - n * p.strips_per_img) * p.R;
       mbar_wait(empty + st, ph ^ 1u);
       if (!(p.dbg & 4))
-      nc_stage_rows<TX, false>(x, s_x + (size_t)st * st_bytes, p.plane, n, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P,
+      nc_stage_rows<TX, false, NC_U_FWD>(x, s_x + (size_t)st * st_bytes, p.plane, n, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P,
                                  p.pad, tid, NC_PROD, dummy);
       fence_proxy_async();
       mbar_arrive(full + st);
@@ -420,11 +423,11 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
       const int y0 = (s - n * p.strips_per_img) * p.R;
       uint8_t* sx = smem + (size_t)st * st_bytes;
       mbar_wait(empty + st, ph ^ 1u);
-      nc_stage_rows<TX, false>(x, sx, p.planeX, n, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P, p.pad, tid, NC_PROD, dummy);
+      nc_stage_rows<TX, false, NC_U_WG>(x, sx, p.planeX, n, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P, p.pad, tid, NC_PROD, dummy);
       if (db != nullptr)
-        nc_stage_rows<TY, true>(dy, sx + x_bytes, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, nthr_y, bsum);
+        nc_stage_rows<TY, true, NC_U_WG>(dy, sx + x_bytes, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, nthr_y, bsum);
       else
-        nc_stage_rows<TY, false>(dy, sx + x_bytes, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, NC_PROD, dummy);
+        nc_stage_rows<TY, false, NC_U_WG>(dy, sx + x_bytes, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, NC_PROD, dummy);
       fence_proxy_async();
       mbar_arrive(full + st);
     }

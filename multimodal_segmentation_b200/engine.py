@@ -324,18 +324,27 @@ class Conv2D:
         return self._packed_nc[1], self._packed_nc[2]
 
     def packed_s2d(self):
-        """stride-2 layer as a stride-1 layer over 2x2 pixel blocks: rearranged kernel, packed for the raster-strip
-        tcgen05 kernels (forward + data gradient)"""
+        """stride-2 layer as a stride-1 layer over 2x2 pixel blocks: rearranged kernel [ceil(k/2)^2 taps, 4*Cin, Cout],
+        packed for the raster-strip kernels (narrow layers) or the 128B-swizzled tcgen05 kernels (4*Cin and Cout
+        multiples of 64): forward + data-gradient operands, refreshed in place"""
         ver = self.kernel.arena.version
         if self._packed_s2d is None or self._packed_s2d[0] != ver:
             old = self._packed_s2d
             w2 = ops.conv_s2d_weights(self.kernel.data, out=None if old is None else old[3])
-            self._packed_s2d = (ver, ops.pack_conv_nc(w2, 0, out=None if old is None else old[1]),
-                                ops.pack_conv_nc(w2, 1, out=None if old is None else old[2]), w2)
+            if self._s2d_wide():
+                self._packed_s2d = (ver, ops.pack_conv(w2, 0, out=None if old is None else old[1]),
+                                    ops.pack_conv(w2, 1, out=None if old is None else old[2]), w2)
+            else:
+                self._packed_s2d = (ver, ops.pack_conv_nc(w2, 0, out=None if old is None else old[1]),
+                                    ops.pack_conv_nc(w2, 1, out=None if old is None else old[2]), w2)
         return self._packed_s2d[1], self._packed_s2d[2]
 
+    def _s2d_wide(self):
+        return (4 * self.cin) % 64 == 0 and self.cout % 64 == 0
+
     def s2d_eligible(self, srcs):
-        """valid stride-2 convolution whose space-to-depth form (4*Cin channels, ceil(k/2) taps) fits conv_nc"""
+        """valid stride-2 convolution whose space-to-depth form (4*Cin channels, ceil(k/2) taps, stride 1) runs on
+        the tensor cores: conv_tc when 4*Cin and Cout are multiples of 64, conv_nc when the geometry fits"""
         if not (USE_TC and self.stride == 2 and self.pad == 0):
             return False
         H, W = srcs[0].shape[1], srcs[0].shape[2]
@@ -343,8 +352,10 @@ class Conv2D:
         H2, W2 = (H + 1) // 2, (W + 1) // 2
         if H2 - k2 + 1 != (H - self.k) // 2 + 1 or W2 - k2 + 1 != (W - self.k) // 2 + 1:
             return False
+        if self._s2d_wide():
+            return True
         c4 = 4 * self.cin
-        return all(ops.nc_supported(c4, self.cout, k2, k2, W2, 0, kind) for kind in (0, 1, 2))
+        return all(ops.nc_supported(c4, self.cout, k2, k2, W2, 0, kind) for kind in (0, 1))
 
     def _call_s2d(self, ctx, srcs, act, alpha):
         code = ACT[act]
@@ -352,9 +363,16 @@ class Conv2D:
                                                           _cast_var(ctx, s, torch.float32) for s in srcs])
         N, H, W, C = xin.shape
         k2 = (self.k + 1) // 2
+        wide = self._s2d_wide()
+        nc_w = (not wide) and ops.nc_supported(4 * C, self.cout, k2, k2, (W + 1) // 2, 0, 2)
         x2 = ops.space_to_depth2(xin.data)
         bias = self.bias.data if self.bias is not None else None
-        y = Var(ops.conv_nc_fwd(x2, self.packed_s2d()[0], bias, self.cout, k2, k2, 0, code, alpha))
+        wp_f, wp_d = self.packed_s2d()
+        if wide:
+            raw = ops.conv_tc_fwd(x2, None, wp_f, bias, self.cout, k2, k2, 1, 0, torch.float32)
+            y = Var(raw if code == ACT_NONE else ops.act_fwd(raw, code, alpha, inplace=True))
+        else:
+            y = Var(ops.conv_nc_fwd(x2, wp_f, bias, self.cout, k2, k2, 0, code, alpha))
         if ctx.rec(xin, self.kernel):
             y.requires_grad = True
 
@@ -367,13 +385,28 @@ class Conv2D:
                     g = ops.cast(g, torch.float32)
                 if code != ACT_NONE:
                     g = ops.act_bwd(g, y.data, code, alpha)
+                gb = ops.cast(g, torch.bfloat16) if wide else None
                 if self.kernel.requires_grad:
                     db = self.bias.grad if (self.bias is not None and self.bias.requires_grad) else None
-                    dw2 = ops.zeros(k2, k2, 4 * C, self.cout)
-                    ops.conv_nc_wgrad(x2, g, dw2, db, 0)
-                    ops.conv_s2d_weights_bwd_(self.kernel.grad, dw2)
+                    if wide:
+                        dw2 = ops.zeros(k2, k2, 4 * C, self.cout)
+                        ops.conv_tc_wgrad(x2, gb, dw2, 0, k2, k2, 1, 0)
+                        ops.conv_s2d_weights_bwd_(self.kernel.grad, dw2)
+                        if db is not None:
+                            ops.colsum_(gb, db)
+                    elif nc_w:
+                        dw2 = ops.zeros(k2, k2, 4 * C, self.cout)
+                        ops.conv_nc_wgrad(x2, g, dw2, db, 0)
+                        ops.conv_s2d_weights_bwd_(self.kernel.grad, dw2)
+                    else:
+                        xf = xin.data if xin.data.dtype == torch.float32 else ops.cast(xin.data, torch.float32)
+                        ops.conv2d_wgrad(xf, g, self.kernel.grad, db, self.stride, self.pad)
                 if xin.requires_grad:
-                    dx2 = ops.conv_nc_fwd(g, self.packed_s2d()[1], None, 4 * C, k2, k2, k2 - 1, out_dtype=torch.bfloat16)
+                    if wide:
+                        dx2 = torch.empty((N, (H + 1) // 2, (W + 1) // 2, 4 * C), dtype=torch.bfloat16, device=g.device)
+                        ops.conv_tc_fwd(gb, None, wp_d, None, 4 * C, k2, k2, 1, k2 - 1, torch.bfloat16, out=dx2)
+                    else:
+                        dx2 = ops.conv_nc_fwd(g, wp_d, None, 4 * C, k2, k2, k2 - 1, out_dtype=torch.bfloat16)
                     accumulate(xin, ops.depth_to_space2(dx2, H, W, xin.grad_dtype))
 
             ctx.tape.record(bw)
