@@ -649,6 +649,63 @@ def concat(ctx, vs):
     return y
 
 
+def concat_rows(ctx, vs):
+    """concatenate along the batch axis (one call of a weight-sharing component instead of k calls)"""
+    n = sum(v.shape[0] for v in vs)
+    out = torch.empty((n,) + tuple(vs[0].shape[1:]), dtype=vs[0].data.dtype, device=vs[0].data.device)
+    off = 0
+    for v in vs:
+        ops.copy_(out[off:off + v.shape[0]], v.data)
+        off += v.shape[0]
+    y = Var(out)
+    if ctx.rec(*vs):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is None:
+                return
+            off = 0
+            for v in vs:
+                b = v.shape[0]
+                if v.requires_grad:
+                    accumulate(v, g[off:off + b], owned=False)
+                off += b
+
+        ctx.tape.record(bw)
+    return y
+
+
+def split_rows(ctx, x, sizes):
+    """views of consecutive batch slices; the backward node gathers the slices' gradients into one tensor"""
+    parts, off = [], 0
+    for b in sizes:
+        parts.append(Var(x.data[off:off + b]))
+        off += b
+    if ctx.rec(x):
+        for p_ in parts:
+            p_.requires_grad = True
+            p_.grad_dtype = x.grad_dtype
+
+        def bw():
+            if all(p_.grad is None for p_ in parts):
+                return
+            g = torch.empty(x.data.shape, dtype=x.grad_dtype, device=x.data.device)
+            off = 0
+            for p_, b in zip(parts, sizes):
+                if p_.grad is None:
+                    ops.zero_(g[off:off + b])
+                else:
+                    ops.copy_(g[off:off + b], p_.grad)
+                    p_.grad = None
+                off += b
+            accumulate(x, g)
+
+        ctx.tape.record(bw)
+    return parts
+
+
 def slice_channels(ctx, x, off, c):
     y = Var(ops.slice_channels(x.data, off, c))
     if ctx.rec(x):

@@ -337,10 +337,11 @@ class DAFNetExecutor(Executor):
         s2_def = M.Anatomy_Fuser.predict_deform_device(s2, s1)
         z1 = self._predict_z(s1, x1, eps1)
         z2 = self._predict_z(s2, x2, eps2)
-        ys1 = [M.Decoder.predict_device(a, z1) for a in (s1, s2_def, s1_def)]
-        ys2 = [M.Decoder.predict_device(a, z2) for a in (s2, s1_def, s2_def)]
-        y1 = ops.gather_rows(_cat_rows(ys1), idx1)
-        y2 = ops.gather_rows(_cat_rows(ys2), idx2)
+        # six Decoder.predict calls (dafnet_executor.py:560-570) as one batched call: the decoder has no batch statistics
+        B = x1.shape[0]
+        ys = M.Decoder.predict_device(_cat_rows([s1, s2_def, s1_def, s2, s1_def, s2_def]), _cat_rows([z1, z1, z1, z2, z2, z2]))
+        y1 = ops.gather_rows(ys[:3 * B], idx1)
+        y2 = ops.gather_rows(ys[3 * B:], idx2)
         M.D_Image1_trainer.train_on_device(x1, y1)
         self._pending.append((M.D_Image1_trainer, M.D_Image1_trainer.book.snapshot(), "dis_X1"))
         M.D_Image2_trainer.train_on_device(x2, y2)
@@ -373,13 +374,11 @@ class DAFNetExecutor(Executor):
 
 
 def _cat_rows(ts):
-    """concatenate along the batch axis with our own copy kernel (flattened as one-channel rows)"""
+    """concatenate along the batch axis with our own copy kernel"""
     n = sum(t.shape[0] for t in ts)
-    out = torch.empty((n,) + tuple(ts[0].shape[1:]), dtype=torch.float32, device="cuda")
+    out = torch.empty((n,) + tuple(ts[0].shape[1:]), dtype=ts[0].dtype, device="cuda")
     off = 0
     for t in ts:
-        flat_src = t.reshape(-1, 1)
-        flat_dst = out[off:off + t.shape[0]].reshape(-1, 1)
-        ops.copy_channels(flat_src, 0, flat_dst, 0, 1)
+        ops.copy_(out[off:off + t.shape[0]], t)
         off += t.shape[0]
     return out

@@ -57,18 +57,23 @@ class DAFNetGeneratorTrainer(Trainer):
         # segment / decode
         M1 = n.Segmentor(ctx, s1)
         M2 = n.Segmentor(ctx, s2)
-        y1 = n.Decoder(ctx, s1, z1)
-        y2 = n.Decoder(ctx, s2, z2)
         # deform (the fused output is discarded by the DAFNet trainers, dafnet.py:193-194)
         s1_def = n.Anatomy_Fuser.forward_deform(ctx, s1, s2)
         s2_def = n.Anatomy_Fuser.forward_deform(ctx, s2, s1)
         M2_s1_def = n.Segmentor(ctx, s1_def)
         M1_s2_def = n.Segmentor(ctx, s2_def)
-        y2_s1_def = n.Decoder(ctx, s1_def, z2)
-        y1_s2_def = n.Decoder(ctx, s2_def, z1)
+        # the six Decoder call sites of the graph (dafnet.py:183-184,205-206 and the Z-regressor, :336-350) share
+        # weights and the decoder has no batch statistics, so they run as ONE call on the concatenated batch:
+        # y1 = Dec(s1,z1), y2 = Dec(s2,z2), y2_s1_def = Dec(s1_def,z2), y1_s2_def = Dec(s2_def,z1),
+        # Dec(s1,z1_in), Dec(s2,z2_in)
+        B = s1.shape[0]
+        Z1_in, Z2_in = E.Var(z1_in), E.Var(z2_in)
+        S_all = E.concat_rows(ctx, [s1, s2, s1_def, s2_def, s1, s2])
+        Z_all = E.concat_rows(ctx, [z1, z2, z2, z1, Z1_in, Z2_in])
+        y1, y2, y2_s1_def, y1_s2_def, yr1, yr2 = E.split_rows(ctx, n.Decoder(ctx, S_all, Z_all), [B] * 6)
         # Z-regressor branch
-        z1_rec = n.z_reconstruct(ctx, s1, E.Var(z1_in))
-        z2_rec = n.z_reconstruct(ctx, s2, E.Var(z2_in))
+        z1_rec = n.Enc_Modality_mu(ctx, s1, yr1)
+        z2_rec = n.Enc_Modality_mu(ctx, s2, yr2)
 
         # ---- losses
         if self.supervised:

@@ -117,6 +117,14 @@ def cast(x, dtype):
     return y
 
 
+def copy_(dst, src):
+    """dst <- src (same shape; dtype conversion allowed), our own copy kernel"""
+    _chk(dst, src)
+    assert dst.numel() == src.numel()
+    call("cast", src, _dt(src), dst, _dt(dst), src.numel(), _S())
+    return dst
+
+
 def copy_channels(src, src_off, dst, dst_off, c, accumulate=False):
     _chk(src, dst)
     M = src.numel() // src.shape[-1]
