@@ -175,7 +175,7 @@ class DAFNetExecutor(Executor):
     # ------------------------------------------------------------------ one step
     def train_batch(self, epoch_loss):
         """dafnet_executor.py:369-387"""
-        if self.conf.automatedpairing:
+        if getattr(self.conf, "automatedpairing", False):
             raise NotImplementedError("automated pairing is a 'next' row (SURVEY.md 8f-1)")
         if self._graph is not None:
             # the snapshots of the previous replay must be read before they are overwritten

@@ -127,7 +127,7 @@ def upsample_block(W, name, x, st):
     return feat(bn(W, name + "_bn", raw(conv(W, name + "_conv", R.upsample2(x), 1, "same")), st))
 
 
-def anatomy_encoder(W, x, st, down_prefix, up_prefix, downsample=4, rounding=True):
+def anatomy_encoder(W, x, st, down_prefix, up_prefix, downsample=4, rounding=True, head_prefix=""):
     """models/unet.py:37-86 + model_components/anatomy_encoder.py:13-30 (down_prefix == up_prefix == '')
     or :32-98 (private down path, shared up path)."""
     skips = []
@@ -141,7 +141,7 @@ def anatomy_encoder(W, x, st, down_prefix, up_prefix, downsample=4, rounding=Tru
         up = upsample_block(W, "%su%d_up" % (up_prefix, i), l, st)
         l = torch.cat([up, skips[i]], -1)              # Concatenate()([l, self.d_l3]) unet.py:68
         l = conv_block(W, "%su%d" % (up_prefix, i), l, st)      # with BF16_EMULATION every block stores bf16
-    a = R.softmax(conv(W, "conv_anatomy", l, 1, "same"))
+    a = R.softmax(conv(W, head_prefix + "conv_anatomy", l, 1, "same"))
     return R.rounding(a) if rounding else a
 
 
@@ -305,6 +305,48 @@ def dafnet_generator_loss(W, conf, x1, x2, z1_in, z2_in, eps1, eps2, m1, m2=None
     inter = dict(s1=s1, s2=s2, M1=M1, M2=M2, y1=y1, y2=y2, s1_def=s1_def, s2_def=s2_def, theta1=th1, theta2=th2,
                  z1=z1, z2=z2, mu1=mu1, lv1=lv1, z1_rec=z1_rec, M1_s2_def=M1_s2_def, y1_s2_def=y1_s2_def)
     return total, L, inter, st
+
+
+def mmsdnet_generator_loss(W, conf, x1, x2, eps, seg_targets, rec_targets, supervised=True, rounding=True):
+    """models/mmsdnet.py:95-192 (unsupervised / supervised trainer graphs and their loss lists) with the targets fed by
+    model_executors/mmsdnet_executor.py:257-260 / :287-290.  Two independent UNets (weights enc1_*, enc2_*), the fused
+    (Maximum) anatomies are segmented / decoded and trained, dice only, one D_Mask, six KL terms.
+    Returns (total, dict of per-output losses)."""
+    st = BNState(W, training=True)
+    nm = conf["num_masks"]
+    dt = conf.get("decoder_type", "film")
+    x = [x1, x2]
+    s = [anatomy_encoder(W, x[i], st, "enc%d_" % (i + 1), "enc%d_" % (i + 1), rounding=rounding, head_prefix="enc%d_" % (i + 1))
+         for i in range(2)]
+    mul = [modality_encoder(W, s[i], x[i]) for i in range(2)]
+    z = [R.sampling(mul[i][0], mul[i][1], eps[i]) for i in range(2)]
+    kls = [R.kl(*mul[i]) for i in range(2)]
+    m1, m2 = segmentor(W, s[0], st), segmentor(W, s[1], st)
+    rec = [decoder(W, s[i], z[i], dt) for i in range(2)]
+    s1_def, s1_fused, _ = anatomy_fuser(W, s[0], s[1])
+    s2_def, s2_fused, _ = anatomy_fuser(W, s[1], s[0])
+    fused_seg = [segmentor(W, a, st) for a in (s1_def, s1_fused, s2_def, s2_fused)]
+    m_list = ([m1, m2] + fused_seg) if supervised else ([m1] + fused_seg[2:])
+    adv_in = [m1, m2] + fused_seg
+    for j, a in enumerate((s1_def, s1_fused)):
+        mu, lv = modality_encoder(W, a, x[1])
+        kls.append(R.kl(mu, lv))
+        rec.append(decoder(W, a, R.sampling(mu, lv, eps[2 + j]), dt))
+    for j, a in enumerate((s2_def, s2_fused)):
+        mu, lv = modality_encoder(W, a, x[0])
+        kls.append(R.kl(mu, lv))
+        rec.append(decoder(W, a, R.sampling(mu, lv, eps[4 + j]), dt))
+    L = {}
+    for i, (pred, tgt) in enumerate(zip(m_list, seg_targets)):
+        L["Segmentor_%d" % i] = conf["w_sup_M"] * R.dice_loss(tgt, pred, nm)
+    for i, m in enumerate(adv_in):
+        a = discriminator(W, "D_Mask", m[..., 0:nm])
+        L["D_Mask_%d" % i] = conf["w_adv_M"] * R.mse(torch.ones_like(a), a)
+    for i, (y, tgt) in enumerate(zip(rec, rec_targets)):
+        L["Decoder_%d" % i] = conf["w_rec_X"] * R.mae(tgt, y)
+    for i, k in enumerate(kls):
+        L["KL_%d" % i] = conf["w_kl"] * k.mean()
+    return sum(L.values()), L
 
 
 def predict_mask_simple(W, x, down_prefix, up_prefix):
