@@ -61,7 +61,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int taps = KH * KW;
-  const int num_kb = taps * ((C0 + C1) / KBLK);
+  // channel counts that are not multiples of 64 are padded by TMA (out-of-range box elements are zero-filled) and by
+  // zero rows / columns of the packed weights
+  const int ncb0 = (C0 + KBLK - 1) / KBLK, ncb1 = (C1 + KBLK - 1) / KBLK;
+  const int num_kb = taps * (ncb0 + ncb1);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA0);
@@ -89,10 +92,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
         const int x0 = txi * g.TW, y0 = tyi * g.TH, img0 = mt * g.TN;
         const int n0 = nb * BLOCK_N;
         for (int src = 0; src < 2; ++src) {
-          const int Cs = src == 0 ? C0 : C1;
+          const int ncbs = src == 0 ? ncb0 : ncb1;
           const CUtensorMap* mA = src == 0 ? &tmA0 : &tmA1;
-          const int koff = src == 0 ? 0 : C0;
-          for (int cb = 0; cb < Cs / KBLK; ++cb) {
+          const int koff = src == 0 ? 0 : ncb0 * KBLK;
+          for (int cb = 0; cb < ncbs; ++cb) {
             for (int tap = 0; tap < taps; ++tap, ++it) {
               const int s = it % STAGES;
               const uint32_t ph = (it / STAGES) & 1;
@@ -167,12 +170,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
         tmem_ld_wait();
         if (live) {
           float f[32];
+          const int cvalid = Cout - (n0 + c);            // channels of this chunk that exist (Cout % 8 == 0)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c + j) : 0.f);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + n0 + c + j) : 0.f);
           if (y_dt == DAFK_F32) {
             float* o = reinterpret_cast<float*>(y) + obase + c;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            for (int j = 0; j < 32; j += 4)
+              if (j < cvalid) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + obase + c;
 #pragma unroll
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
                 __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * i], f[j + 2 * i + 1]);
                 pk[i] = *reinterpret_cast<uint32_t*>(&h);
               }
-              *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              if (j < cvalid) *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
         }
@@ -246,7 +251,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int taps = KH * KW;
-  const int ncb = (C0 + C1) / KBLK;
+  const int ncb0 = (C0 + KBLK - 1) / KBLK;
+  const int ncb = ncb0 + (C1 + KBLK - 1) / KBLK;     // partial 64-channel blocks are zero-padded by TMA / the packed weights
   const uint32_t tmem_cols = (uint32_t)(2 * g.G * BLOCK_N) <= 32u ? 32u : (uint32_t)(2 * g.G * BLOCK_N);   // power of two by construction
 
   if (threadIdx.x == 0) {
@@ -277,9 +283,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
         const int x0 = txi * g.TWo, y0 = tyi * g.TH, img0 = mt * g.TN;
         const int n0 = nb * BLOCK_N;
         for (int cb = 0; cb < ncb; ++cb, ++ia) {
-          const bool first = cb * KBLK < C0;
+          const bool first = cb < ncb0;
           const CUtensorMap* mA = first ? &tmA0 : &tmA1;
-          const int c_in_src = first ? cb * KBLK : cb * KBLK - C0;
+          const int c_in_src = first ? cb * KBLK : (cb - ncb0) * KBLK;
           const int sa = ia % g.SA;
           mbar_wait(a_empty + sa, ((uint32_t)(ia / g.SA) & 1u) ^ 1u);
           mbar_expect_tx(a_full + sa, a_box_bytes);
@@ -372,12 +378,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
           tmem_ld_wait();
           if (live) {
             float f[32];
+            const int cvalid = Cout - (n0 + c);            // channels of this chunk that exist (Cout % 8 == 0)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c + j) : 0.f);
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + n0 + c + j) : 0.f);
             if (y_dt == DAFK_F32) {
               float* o = reinterpret_cast<float*>(y) + obase + c;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              for (int j = 0; j < 32; j += 4)
+                if (j < cvalid) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             } else {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + obase + c;
 #pragma unroll
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
                   __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * i], f[j + 2 * i + 1]);
                   pk[i] = *reinterpret_cast<uint32_t*>(&h);
                 }
-                *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (j < cvalid) *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
             }
           }
@@ -428,7 +436,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  const int ci_blocks = Cin / BN, co_blocks = Cout / BM;
+  const int ci_blocks = (Cin + BN - 1) / BN, co_blocks = (Cout + BM - 1) / BM;
   int unit = blockIdx.x;
   const int cib = unit % ci_blocks; unit /= ci_blocks;
   const int cob = unit % co_blocks; unit /= co_blocks;
@@ -512,11 +520,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_kernel(const __grid_
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c, v);
         tmem_ld_wait();
-        if (row_ok) {
+        if (row_ok && co < Cout) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int ci = cin_off + cib * BN + c + j;
-            atomicAdd(dw + ((int64_t)tap * cin_total + ci) * Cout + co, __uint_as_float(v[j]));
+            const int cil = cib * BN + c + j;
+            if (cil < Cin) atomicAdd(dw + ((int64_t)tap * cin_total + cin_off + cil) * Cout + co, __uint_as_float(v[j]));
           }
         }
       }
@@ -533,26 +541,27 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------
 // weight packing: HWIO f32 -> bf16 [tap][Cout][Cin]  (fwd)  or  [tap'][Cin][Cout] with tap' mirrored (dgrad)
 // ---------------------------------------------------------------------------------------------
+// Cip / Cop = Cin / Cout rounded up to 64: the packed matrices are zero-padded so that partial channel blocks
+// contribute nothing
 __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int KH, int KW, int Cin,
-                              int Cout, int for_dgrad) {
-  int64_t total = (int64_t)KH * KW * Cin * Cout;
+                              int Cout, int Cip, int Cop, int for_dgrad) {
+  int64_t total = (int64_t)KH * KW * Cip * Cop;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     // i indexes the destination
+    int ci, co, tap;
     if (!for_dgrad) {
-      int ci = (int)(i % Cin);
-      int64_t t = i / Cin;
-      int co = (int)(t % Cout);
-      int tap = (int)(t / Cout);
-      wp[i] = __float2bfloat16_rn(w[((int64_t)tap * Cin + ci) * Cout + co]);
+      ci = (int)(i % Cip);
+      int64_t t = i / Cip;
+      co = (int)(t % Cop);
+      tap = (int)(t / Cop);
     } else {
-      int co = (int)(i % Cout);
-      int64_t t = i / Cout;
-      int ci = (int)(t % Cin);
-      int tapd = (int)(t / Cin);
-      int tap = KH * KW - 1 - tapd;   // mirrored in both axes
-      wp[i] = __float2bfloat16_rn(w[((int64_t)tap * Cin + ci) * Cout + co]);
+      co = (int)(i % Cop);
+      int64_t t = i / Cop;
+      ci = (int)(t % Cip);
+      tap = KH * KW - 1 - (int)(t / Cip);   // mirrored in both axes
     }
+    wp[i] = (ci < Cin && co < Cout) ? __float2bfloat16_rn(w[((int64_t)tap * Cin + ci) * Cout + co]) : __float2bfloat16_rn(0.f);
   }
 }
 
@@ -560,18 +569,19 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
 //   dx[2a+pa, 2b+pb, ci] = sum_{i',j' in {0..KH/2-1}} dy[a + i' - (KH/2-1), b + j' - (KW/2-1), co] * w[pa + 2(KH/2-1-i'), pb + 2(KW/2-1-j'), ci, co]
 // packed as [tap' = i'*(KW/2)+j'][Cin][Cout]
 __global__ void pack_w_s2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int KH, int KW, int Cin,
-                                 int Cout, int pa, int pb) {
+                                 int Cout, int Cip, int Cop, int pa, int pb) {
   const int kh2 = KH / 2, kw2 = KW / 2;
-  int64_t total = (int64_t)kh2 * kw2 * Cin * Cout;
+  int64_t total = (int64_t)kh2 * kw2 * Cip * Cop;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    int co = (int)(i % Cout);
-    int64_t t = i / Cout;
-    int ci = (int)(t % Cin);
-    int tapd = (int)(t / Cin);
+    int co = (int)(i % Cop);
+    int64_t t = i / Cop;
+    int ci = (int)(t % Cip);
+    int tapd = (int)(t / Cip);
     int ip = tapd / kw2, jp = tapd % kw2;
     int r = pa + 2 * (kh2 - 1 - ip), q = pb + 2 * (kw2 - 1 - jp);
-    wp[i] = __float2bfloat16_rn(w[(((int64_t)r * KW + q) * Cin + ci) * Cout + co]);
+    wp[i] = (ci < Cin && co < Cout) ? __float2bfloat16_rn(w[(((int64_t)r * KW + q) * Cin + ci) * Cout + co])
+                                    : __float2bfloat16_rn(0.f);
   }
 }
 
@@ -656,7 +666,7 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
     DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_fwd) failed: %s", cudaGetErrorString(e));
     configured = true;
   }
-  int n_blocks = Cout / BLOCK_N;
+  int n_blocks = (Cout + BLOCK_N - 1) / BLOCK_N;
   int64_t tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n * n_blocks;
   DAFK_REQUIRE(tiles < (1LL << 31), DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd: too many tiles");
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
@@ -775,7 +785,7 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_halo) failed: %s", cudaGetErrorString(e));
     configured = true;
   }
-  const int n_blocks = Cout / BLOCK_N;
+  const int n_blocks = (Cout + BLOCK_N - 1) / BLOCK_N;
   const int64_t tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n * n_blocks;
   DAFK_REQUIRE(tiles < (1LL << 31), DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd: too many tiles");
   const int smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;      // one persistent CTA per SM
@@ -796,7 +806,7 @@ static int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mdy, float* dw
     DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_wgrad) failed: %s", cudaGetErrorString(e));
     configured = true;
   }
-  int units = KH * KW * (Cout / BM) * (Cin / BN);
+  int units = KH * KW * ((Cout + BM - 1) / BM) * ((Cin + BN - 1) / BN);
   int total_tiles = g.tiles_x * g.tiles_y * g.tiles_n;
   int want = (kNumSMs * 2 + units - 1) / units;
   if (want > total_tiles) want = total_tiles;
@@ -822,8 +832,9 @@ int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void*
                DAFK_ERR_BAD_ARG, "dafk_conv_tc_fwd: bad shape");
   DAFK_REQUIRE(stride == 1 || stride == 2, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd: stride must be 1 or 2");
   DAFK_REQUIRE(x0 && wp && y && (C1 == 0 || x1), DAFK_ERR_BAD_ARG, "dafk_conv_tc_fwd: null pointer");
-  DAFK_REQUIRE(C0 % KBLK == 0 && C1 % KBLK == 0 && Cout % 64 == 0, DAFK_ERR_UNSUPPORTED,
-               "dafk_conv_tc_fwd: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
+  DAFK_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && Cout % 8 == 0 && (C1 == 0 || C0 % KBLK == 0), DAFK_ERR_UNSUPPORTED,
+               "dafk_conv_tc_fwd: input channels must be multiples of 16 (the first of two sources a multiple of 64), "
+               "output channels a multiple of 8 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
   DAFK_REQUIRE(y_dt == DAFK_F32 || y_dt == DAFK_BF16, DAFK_ERR_BAD_ARG, "dafk_conv_tc_fwd: bad output dtype");
   DAFK_REQUIRE(w_row_off >= 0 && w_row_off + Cout <= w_rows_per_tap, DAFK_ERR_BAD_ARG,
                "dafk_conv_tc_fwd: weight row window [%d,%d) outside %d rows per tap", w_row_off, w_row_off + Cout,
@@ -842,13 +853,14 @@ int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void*
   const int64_t m_tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n;
   // stride-1 layers: the haloed-tile kernel reads each activation pixel once per channel block instead of once per
   // tap; take it when the estimate says so (DAFK_CONV_HALO=0/1 forces the choice, for the tests and benchmarks)
-  if (stride == 1 && H == Ho + KH - 1 - 2 * pad && W == Wo + KW - 1 - 2 * pad && C0 % KBLK == 0) {
+  const int Kpad = ((C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK) * KBLK;     // K extent of the packed weights
+  if (stride == 1 && H == Ho + KH - 1 - 2 * pad && W == Wo + KW - 1 - 2 * pad) {
     static int force = -2;
     if (force == -2) { const char* e = getenv("DAFK_CONV_HALO"); force = e ? atoi(e) : -1; }
     const int bn = Cout % 128 == 0 ? 128 : 64;
     HaloGeom hg;
-    const double ch = pick_halo_geom(N, Ho, Wo, KH, KW, bn, Cout / bn, &hg);
-    double ct = tap_kernel_cost(N, Ho, Wo, KH, KW, bn, Cout / bn, g);
+    const double ch = pick_halo_geom(N, Ho, Wo, KH, KW, bn, (Cout + bn - 1) / bn, &hg);
+    double ct = tap_kernel_cost(N, Ho, Wo, KH, KW, bn, (Cout + bn - 1) / bn, g);
     if (Cout % 256 == 0) { const double c256 = tap_kernel_cost(N, Ho, Wo, KH, KW, 256, Cout / 256, g); if (c256 < ct) ct = c256; }
     // measured on B200 (profiles/r1_bench_tc.txt): the haloed tile wins for Cout in {64, 128} (weight tiles are small,
     // the tap-by-tap kernel is L2-bound on the activations); with Cout >= 256 the 128 x 256 tap-by-tap tiles win
@@ -859,7 +871,7 @@ int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void*
       rc = make_halo_map(&h0, x0, N, H, W, C0, hg);
       if (rc) return rc;
       if (C1 > 0) { rc = make_halo_map(&h1, x1, N, H, W, C1, hg); if (rc) return rc; } else h1 = h0;
-      rc = make_w_map(&b, wp, taps * w_rows_per_tap, C0 + C1, bn);
+      rc = make_w_map(&b, wp, taps * w_rows_per_tap, Kpad, bn);
       if (rc) return rc;
       if (bn == 128)
         return launch_halo<128>(h0, h1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, hg, w_rows_per_tap, w_row_off,
@@ -874,19 +886,19 @@ int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void*
     const int64_t r256 = (m_tiles * (Cout / 256) + kNumSMs - 1) / kNumSMs;
     const int64_t r128 = (m_tiles * (Cout / 128) + kNumSMs - 1) / kNumSMs;
     if ((double)r256 * 2.0 * 0.8 <= (double)r128) {
-      rc = make_w_map(&b, wp, taps * w_rows_per_tap, C0 + C1, 256);
+      rc = make_w_map(&b, wp, taps * w_rows_per_tap, Kpad, 256);
       if (rc) return rc;
       return launch_fwd<256, 4>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
                                 w_row_off, y_sn, y_sy, y_sx, s);
     }
   }
   if (Cout % 128 == 0) {
-    rc = make_w_map(&b, wp, taps * w_rows_per_tap, C0 + C1, 128);
+    rc = make_w_map(&b, wp, taps * w_rows_per_tap, Kpad, 128);
     if (rc) return rc;
     return launch_fwd<128, 6>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
                               w_row_off, y_sn, y_sy, y_sx, s);
   }
-  rc = make_w_map(&b, wp, taps * w_rows_per_tap, C0 + C1, 64);
+  rc = make_w_map(&b, wp, taps * w_rows_per_tap, Kpad, 64);
   if (rc) return rc;
   return launch_fwd<64, 8>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
                            w_row_off, y_sn, y_sy, y_sx, s);
@@ -903,14 +915,15 @@ int dafk_pack_conv(const float* w_hwio, void* wp, int KH, int KW, int Cin, int C
                    void* stream) {
   DAFK_REQUIRE(w_hwio && wp && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, DAFK_ERR_BAD_ARG, "dafk_pack_conv: bad argument");
   cudaStream_t s = as_stream(stream);
+  const int Cip = (Cin + 63) / 64 * 64, Cop = (Cout + 63) / 64 * 64;
   if (mode == 0 || mode == 1) {
-    int64_t total = (int64_t)KH * KW * Cin * Cout;
-    pack_w_kernel<<<bw_grid(total, 256), 256, 0, s>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, mode);
+    int64_t total = (int64_t)KH * KW * Cip * Cop;
+    pack_w_kernel<<<bw_grid(total, 256), 256, 0, s>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, Cip, Cop, mode);
   } else if (mode == 2) {
     DAFK_REQUIRE(KH % 2 == 0 && KW % 2 == 0 && (pa == 0 || pa == 1) && (pb == 0 || pb == 1), DAFK_ERR_BAD_ARG,
                  "dafk_pack_conv: stride-2 data-gradient packing needs an even kernel and a parity in {0,1}");
-    int64_t total = (int64_t)(KH / 2) * (KW / 2) * Cin * Cout;
-    pack_w_s2_kernel<<<bw_grid(total, 256), 256, 0, s>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, pa, pb);
+    int64_t total = (int64_t)(KH / 2) * (KW / 2) * Cip * Cop;
+    pack_w_s2_kernel<<<bw_grid(total, 256), 256, 0, s>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, Cip, Cop, pa, pb);
   } else {
     set_error("dafk_pack_conv: unknown mode %d", mode);
     return DAFK_ERR_BAD_ARG;
@@ -929,8 +942,8 @@ int dafk_conv_tc_wgrad(const void* x, int Cin, int cin_off, int cin_total, const
                DAFK_ERR_BAD_ARG, "dafk_conv_tc_wgrad: bad shape");
   DAFK_REQUIRE(stride == 1 || stride == 2, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_wgrad: stride must be 1 or 2");
   DAFK_REQUIRE(x && dy && dw, DAFK_ERR_BAD_ARG, "dafk_conv_tc_wgrad: null pointer");
-  DAFK_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, DAFK_ERR_UNSUPPORTED,
-               "dafk_conv_tc_wgrad: channels must be multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
+  DAFK_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, DAFK_ERR_UNSUPPORTED,
+               "dafk_conv_tc_wgrad: channels must be multiples of 16 (Cin=%d Cout=%d)", Cin, Cout);
   DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(dy) && DAFK_ALIGNED16(dw), DAFK_ERR_ALIGN,
                "dafk_conv_tc_wgrad: pointers must be 16-byte aligned");
   TileGeom g = pick_geom(N, Ho, Wo, stride);

@@ -134,6 +134,42 @@ __global__ void __launch_bounds__(DT) dense_bwd_weight_kernel(const float* __res
   }
 }
 
+// wide-output variants (SPADE decoder: Dense(8 -> H*W*128/1024), model_components/decoder.py:68): dy does not fit in
+// shared memory; dy rows are read coalesced from L2 instead
+__global__ void __launch_bounds__(DT) dense_bwd_weight_wide_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                   float* __restrict__ dw, float* __restrict__ db, int B,
+                                                                   int64_t K, int N) {
+  int64_t total = K * N;
+  int64_t stride = (int64_t)gridDim.x * DT;
+  for (int64_t o = (int64_t)blockIdx.x * DT + threadIdx.x; o < total; o += stride) {
+    int64_t k = o / N;
+    int n = (int)(o - k * N);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(__ldg(x + (int64_t)b * K + k), __ldg(dy + (int64_t)b * N + n), s);
+    dw[o] += s;
+  }
+  if (db) {
+    for (int64_t n = (int64_t)blockIdx.x * DT + threadIdx.x; n < N; n += stride) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += __ldg(dy + (int64_t)b * N + n);
+      db[n] += s;
+    }
+  }
+}
+
+// one warp per (b, k): dx[b,k] = sum_n dy[b,n] * w[k,n]
+__global__ void __launch_bounds__(DT) dense_bwd_data_wide_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                 float* __restrict__ dx, int B, int64_t K, int N) {
+  const int64_t warp = ((int64_t)blockIdx.x * DT + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (int64_t)B * K) return;
+  const int64_t b = warp / K, k = warp - b * K;
+  float s = 0.f;
+  for (int n = lane; n < N; n += 32) s = fmaf(__ldg(dy + b * N + n), __ldg(w + k * N + n), s);
+  s = warp_sum(s);
+  if (lane == 0) dx[b * K + k] = s;
+}
+
 }  // namespace dafk
 
 using namespace dafk;
@@ -164,7 +200,11 @@ int dafk_dense_bwd_data(const float* dy, const float* w, float* dx, int B, int64
   if (B == 0) return DAFK_OK;
   DAFK_REQUIRE(dy && w && dx, DAFK_ERR_BAD_ARG, "dafk_dense_bwd_data: null pointer");
   size_t smem = sizeof(float) * MAXB * Nout;
-  DAFK_REQUIRE(smem <= 48 * 1024, DAFK_ERR_UNSUPPORTED, "dafk_dense_bwd_data: Nout too large (%d)", Nout);
+  if (smem > 48 * 1024) {
+    const int64_t warps = (int64_t)B * K;
+    dense_bwd_data_wide_kernel<<<(unsigned)((warps * 32 + DT - 1) / DT), DT, 0, as_stream(stream)>>>(dy, w, dx, B, K, Nout);
+    return check_launch("dafk_dense_bwd_data");
+  }
   dim3 grid((unsigned)((K + DT - 1) / DT), (B + MAXB - 1) / MAXB);
   dense_bwd_data_kernel<<<grid, DT, smem, as_stream(stream)>>>(dy, w, dx, B, K, Nout);
   return check_launch("dafk_dense_bwd_data");
@@ -176,9 +216,12 @@ int dafk_dense_bwd_weight(const float* x, const float* dy, float* dw, float* db,
   if (B == 0) return DAFK_OK;
   DAFK_REQUIRE(x && dy && dw, DAFK_ERR_BAD_ARG, "dafk_dense_bwd_weight: null pointer");
   size_t smem = sizeof(float) * B * Nout;
-  DAFK_REQUIRE(smem <= 48 * 1024, DAFK_ERR_UNSUPPORTED, "dafk_dense_bwd_weight: B*Nout too large");
   int64_t total = K * Nout;
   int grid = bw_grid(total, DT, 8);
+  if (smem > 48 * 1024) {
+    dense_bwd_weight_wide_kernel<<<grid, DT, 0, as_stream(stream)>>>(x, dy, dw, db, B, K, Nout);
+    return check_launch("dafk_dense_bwd_weight");
+  }
   dense_bwd_weight_kernel<<<grid, DT, smem, as_stream(stream)>>>(x, dy, dw, db, B, K, Nout);
   return check_launch("dafk_dense_bwd_weight");
 }

@@ -262,14 +262,20 @@ class Conv2D:
         self._packed = None          # (arena version, wp_fwd, wp_dgrad)
         self._packed_nc = None
         self._packed_s2d = None
+        self._packed_dg = None
 
     def params(self):
         return [self.kernel] + ([self.bias] if self.bias is not None else [])
 
     def tc_eligible(self, srcs):
-        """tcgen05 path: >= 64-channel operands; stride 1 (any kernel / padding) or stride 2 with an even
-        kernel and no padding (the discriminator's 4x4 stride-2 layers)"""
-        if not (USE_TC and self.k > 1 and self.cout % 64 == 0 and all(s.shape[-1] % 64 == 0 for s in srcs)):
+        """128B-swizzled tcgen05 path: channel counts that are multiples of 16 with at least 32 input channels (fewer go
+        to the raster-strip kernels); partial 64-channel blocks are zero-padded by TMA and the packed weights.  Stride 1
+        (any kernel / padding) or stride 2 with an even kernel and no padding (the discriminator's 4x4 stride-2
+        layers).  The first of two concatenated sources must be a whole number of 64-channel blocks."""
+        cs = [s.shape[-1] for s in srcs]
+        if not (USE_TC and self.k > 1 and self.cout % 16 == 0 and all(c % 16 == 0 for c in cs) and sum(cs) >= 32):
+            return False
+        if len(cs) > 1 and cs[0] % 64 != 0:
             return False
         return self.stride == 1 or (self.stride == 2 and self.k % 2 == 0 and self.pad == 0)
 
@@ -456,6 +462,15 @@ class Conv2D:
                     if nc_d:
                         dx = ops.conv_nc_fwd(g, self.packed_nc()[1], None, self.cin, self.k, self.k, self.k - 1 - self.pad,
                                              out_dtype=tape_x.grad_dtype)
+                    elif nc and self.k > 1 and self.cout % 16 == 0 and self.cout >= 32 and self.cin % 8 == 0:
+                        # few inputs <- many outputs (SPADE's 8 -> 128 anatomy convolution, layers/spade.py:29): the data
+                        # gradient is a wide-in / narrow-out convolution for the swizzled tcgen05 kernel
+                        ver = self.kernel.arena.version
+                        if self._packed_dg is None or self._packed_dg[0] != ver:
+                            self._packed_dg = (ver, ops.pack_conv(self.kernel.data, 1,
+                                                                  out=None if self._packed_dg is None else self._packed_dg[1]))
+                        dx = ops.conv_tc_fwd(ops.cast(g, torch.bfloat16), None, self._packed_dg[1], None, self.cin, self.k,
+                                             self.k, 1, self.k - 1 - self.pad, tape_x.grad_dtype)
                     else:
                         dx = ops.conv2d_dgrad(g, self.kernel.data, tuple(tape_x.shape), self.stride, self.pad)
                     accumulate(tape_x, dx)

@@ -391,12 +391,13 @@ def pack_conv(w_hwio, mode, pa=0, pb=0, out=None):
     2: stride-2 dgrad parity class (pa,pb): [(KH/2)(KW/2)][Cin][Cout]"""
     _chk(w_hwio)
     KH, KW, Cin, Cout = w_hwio.shape
+    cip, cop = (Cin + 63) // 64 * 64, (Cout + 63) // 64 * 64      # zero-padded to whole 64-channel blocks
     if mode == 0:
-        shape = (KH * KW, Cout, Cin)
+        shape = (KH * KW, cop, cip)
     elif mode == 1:
-        shape = (KH * KW, Cin, Cout)
+        shape = (KH * KW, cip, cop)
     else:
-        shape = ((KH // 2) * (KW // 2), Cin, Cout)
+        shape = ((KH // 2) * (KW // 2), cip, cop)
     wp = torch.empty(shape, dtype=torch.bfloat16, device=w_hwio.device) if out is None else out
     call("pack_conv", w_hwio, wp, KH, KW, Cin, Cout, mode, pa, pb, _S())
     return wp

@@ -87,7 +87,7 @@ def raw(x):
 
 def _tc_eligible(w, stride, padding):
     """mirror of the product's eligibility rule (engine.Conv2D.tc_eligible)"""
-    if not (BF16_EMULATION and w.shape[0] > 1 and w.shape[2] % 64 == 0 and w.shape[3] % 64 == 0):
+    if not (BF16_EMULATION and w.shape[0] > 1 and w.shape[2] % 16 == 0 and w.shape[3] % 16 == 0 and w.shape[2] >= 32):
         return False
     return stride == 1 or (stride == 2 and w.shape[0] % 2 == 0 and padding == "valid")
 

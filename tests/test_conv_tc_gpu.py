@@ -118,6 +118,12 @@ DISC_CASES = [
     (2, 26, 26, 256, 512, 4, 1),
     (3, 31, 29, 64, 64, 4, 2),      # odd sizes: uncovered last row / column in the data gradient
     (2, 20, 22, 64, 128, 5, 1),     # another stride-1 valid shape
+    # channel counts that are not multiples of 64 (SPADE decoder, layers/spade.py:14-31): partial 64-channel blocks
+    # are zero-padded by TMA out-of-bounds fill and by the packed weights
+    (2, 20, 22, 128, 32, 3, 1),
+    (2, 20, 22, 32, 16, 3, 1),
+    (2, 16, 18, 48, 80, 3, 1),
+    (2, 28, 28, 128, 16, 3, 1),
 ]
 
 

@@ -278,7 +278,7 @@ def test_conv_fused_activation(ops):
 
 
 # ------------------------------------------------------------------ dense
-@pytest.mark.parametrize("B,K,N", [(4, 1000, 32), (32, 21632, 32), (3, 4802, 100), (5, 270848 // 8, 1), (2, 8, 300)])
+@pytest.mark.parametrize("B,K,N", [(4, 1000, 32), (32, 21632, 32), (3, 4802, 100), (5, 270848 // 8, 1), (2, 8, 300), (32, 8, 6272), (192, 8, 6272)])
 def test_dense(ops, B, K, N):
     r = rng(B + N)
     x = r.normal(size=(B, K)).astype(np.float32)
