@@ -37,7 +37,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="dafnet_film", choices=["dafnet_film", "dafnet_spade"])
+    ap.add_argument("--workload", default="dafnet_film", choices=["dafnet_film", "dafnet_spade", "inference"],
+                    help="dafnet_film = BASELINE config 2 (the metric), dafnet_spade = config 3, inference = config 5 "
+                         "(predict_mask 'simple': anatomy encoder + segmentor, use --size 512 --batch 128)")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--l_mix", type=float, default=1.0)
@@ -97,6 +99,8 @@ def conf_for(args):
     from multimodal_segmentation_b200.keras_like import EasyDict
     conf = EasyDict(dafnet_config_chaos.get((args.size, args.size, 1),
                                             decoder_type="spade" if args.workload == "dafnet_spade" else "film"))
+    if args.workload == "inference":
+        conf.folder = "/tmp/dafk_bench_infer"
     conf.batch_size = args.batch
     conf.l_mix = args.l_mix
     conf.n_pairs = 1
@@ -331,9 +335,66 @@ def run_b200(args):
     finish()
 
 
+def run_inference(args):
+    """BASELINE config 5: predict_mask(type='simple') = Segmentor(Enc_Anatomy(x)) in inference phase (models/mmsdnet.py:
+    210-224), device-timed with the images resident in HBM; replicas only at N > 1 (no collective)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ["NCCL_DEBUG"] = "WARN"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from multimodal_segmentation_b200 import _lib, engine as E
+    from multimodal_segmentation_b200.models.dafnet import DAFNet
+    E.USE_TC = not args.no_tc
+    conf = conf_for(args)
+    np.random.seed(10 + rank)
+    net = DAFNet(conf)
+    net.build()
+    B, S = args.batch, args.size
+    x = [torch.rand(B, S, S, 1, device="cuda") * 2 - 1 for _ in range(2)]
+    for _ in range(args.warmup):
+        net.predict_mask_device(1, "simple", x[0], x[1])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out = net.predict_mask_device(1, "simple", x[0], x[1])
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    gf = 104.2 * (S / 224.0) ** 2      # algorithmic GFLOP per slice (SURVEY 8d: 104.2 @224^2, 544.3 @512^2)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "segmentor-only inference slices/s @%d^2" % S, "value": world * B * args.steps / (ms / 1000.0),
+            "unit": "slices/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if E.USE_TC else "f32",
+            "data": "synthetic", "config": {"workload": "predict_mask('simple'): anatomy encoder + segmentor, %dx%d, %d per GPU"
+                                                      % (S, S, B), "parallelism": "replicas x%d" % world},
+            "step_tflops_per_gpu": gf * B / 1000.0 / (ms / args.steps / 1000.0),
+            "gpu_launches": int(_lib.launch_count() - l0), "out_shape": list(out.shape)}))
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "inference":
+        run_inference(a)
     else:
         run_b200(a)
