@@ -130,6 +130,17 @@ int dafk_bn_bwd_apply(const void* dout, int dout_dt, const void* x, int x_dt, co
                       const float* rstd, const float* gamma, const float* beta, const double* acc,
                       void* dx, int dx_dt, float* dgamma, float* dbeta, float* dbias_prev, int64_t M,
                       int C, int act, void* stream);
+/* Wide BatchNorm passes (csrc/norm_wide.cuh): C a power of two in [8,1024].  One launch does the batch statistics AND
+ * the finalize step of keras BatchNormalization (utils/model_utils.py:10: mean, 1/sqrt(var+eps), moving averages) /
+ * the two backward sums; `ws` is a caller-owned persistent workspace of dafk_bn_wide_ws_bytes(C) bytes that must be
+ * zero before the first call and is left zero by every call (kernels on one stream may share it). */
+int dafk_bn_wide_supported(int C);
+int64_t dafk_bn_wide_ws_bytes(int C);
+int dafk_bn_stats_fused(const void* x, int x_dt, void* ws, int64_t ws_bytes, int64_t M, int C, float eps, float momentum,
+                        float* mean, float* rstd, float* moving_mean, float* moving_var, void* stream);
+int dafk_bn_bwd_reduce_fused(const void* dout, int dout_dt, const void* x, int x_dt, const float* mean, const float* rstd,
+                             const float* gamma, const float* beta, double* acc, void* ws, int64_t ws_bytes, int64_t M,
+                             int C, int act, void* stream);
 /* inference-mode backward (frozen statistics): dx = dz*gamma*rstd */
 int dafk_bn_bwd_frozen(const float* dout, const float* x, const float* mean, const float* rstd,
                        const float* gamma, const float* beta, float* dx, int64_t M, int C, int act,
@@ -205,6 +216,18 @@ int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias,
 /* dw[KH,KW,Cin,Cout] (HWIO f32) += x (*) dy ; db[Cout] += sum_pixels dy (db may be NULL) */
 int dafk_conv_nc_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float* dw, float* db, int N,
                        int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream);
+/* Pointwise heads on a 64-channel bf16 feature map (csrc/conv_1x1.cu): `conv_anatomy` 64 -> 8
+ * (model_components/anatomy_encoder.py:26) and the segmentor's 64 -> num_masks+1 (model_components/segmentor.py:24).
+ * x / dx: bf16 [M,64]; w: f32 [64,Cout] (HWIO with KH=KW=1); y / dy: f32 [M,Cout]; M = N*H*W pixels.
+ * round_bf16 != 0: w and dy are rounded to bf16 as they are loaded (operand precision of the tensor-core mode).
+ * wgrad accumulates into dw / db (db may be NULL). */
+int dafk_conv1x1_supported(int Cin, int Cout);
+int dafk_conv1x1_fwd(const void* x, const float* w, const float* bias, float* y, int64_t M, int Cin, int Cout,
+                     int round_bf16, void* stream);
+int dafk_conv1x1_dgrad(const float* dy, const float* w, void* dx, int64_t M, int Cin, int Cout, int round_bf16,
+                       void* stream);
+int dafk_conv1x1_wgrad(const void* x, const float* dy, float* dw, float* db, int64_t M, int Cin, int Cout,
+                       int round_bf16, void* stream);
 /* Space-to-depth (2x2 pixel blocks -> 4C channels, bf16 out, zero beyond odd sizes), its inverse, and the matching
  * rearrangement of an HWIO kernel [KH,KW,C,Cout] -> [ceil(KH/2),ceil(KW/2),4C,Cout] (backward != 0: accumulate the
  * rearranged gradient w2 back into w).  conv(x, w, stride 2, valid) == conv(s2d(x), s2d(w), stride 1, valid):

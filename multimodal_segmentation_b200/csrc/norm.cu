@@ -4,6 +4,7 @@
 // (double atomics, one per channel per block).
 #include "common.cuh"
 #include "reduce.cuh"
+#include "norm_wide.cuh"
 
 namespace dafk {
 
@@ -401,6 +402,17 @@ int dafk_bn_apply(const void* x, int x_dt, const float* mean, const float* rstd,
   DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(out), DAFK_ERR_ALIGN, "dafk_bn_apply: alignment");
   int64_t n4 = M * C / 4;
   cudaStream_t s = as_stream(stream);
+  if (bn_wide_ok(C) && (x_dt == DAFK_F32 || x_dt == DAFK_BF16) && (out_dt == DAFK_F32 || out_dt == DAFK_BF16)) {
+    const int64_t n8 = n4 / 2;
+    const int grid = bn_wide_grid(n8, 1, 4);
+    if (out_dt == DAFK_F32)
+      { if (x_dt == DAFK_BF16) bn_apply_wide_kernel<__nv_bfloat16, float><<<grid, BW_T, 0, s>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, (float*)out, n8, C, act);
+        else bn_apply_wide_kernel<float, float><<<grid, BW_T, 0, s>>>((const float*)x, mean, rstd, gamma, beta, (float*)out, n8, C, act); }
+    else
+      { if (x_dt == DAFK_BF16) bn_apply_wide_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, BW_T, 0, s>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, (__nv_bfloat16*)out, n8, C, act);
+        else bn_apply_wide_kernel<float, __nv_bfloat16><<<grid, BW_T, 0, s>>>((const float*)x, mean, rstd, gamma, beta, (__nv_bfloat16*)out, n8, C, act); }
+    return check_launch("dafk_bn_apply");
+  }
   if (out_dt == DAFK_F32)
     { if (x_dt == DAFK_BF16) bn_apply_kernel<__nv_bfloat16, float><<<bn_grid(n4), TPB, 0, s>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, (float*)out, n4, C, act);
       else bn_apply_kernel<float, float><<<bn_grid(n4), TPB, 0, s>>>((const float*)x, mean, rstd, gamma, beta, (float*)out, n4, C, act); }
@@ -442,6 +454,26 @@ int dafk_bn_bwd_apply(const void* dout, int dout_dt, const void* x, int x_dt, co
   int64_t n4 = M * C / 4;
   cudaStream_t s = as_stream(stream);
   int grid = bn_grid(n4);
+  if (bn_wide_ok(C)) {
+    const int64_t n8 = n4 / 2;
+    const int wgrid = bn_wide_grid(n8, 1, 2);
+#define LAUNCHW(TD, TO)                                                                                                 \
+  do {                                                                                                                  \
+    if (x_dt == DAFK_BF16)                                                                                              \
+      bn_bwd_apply_wide_kernel<TD, __nv_bfloat16, TO><<<wgrid, BW_T, 0, s>>>(                                           \
+          (const TD*)dout, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, acc, (TO*)dx, dgamma, dbeta, dbias_prev, n8, M, C, act); \
+    else                                                                                                                \
+      bn_bwd_apply_wide_kernel<TD, float, TO><<<wgrid, BW_T, 0, s>>>(                                                   \
+          (const TD*)dout, (const float*)x, mean, rstd, gamma, beta, acc, (TO*)dx, dgamma, dbeta, dbias_prev, n8, M, C, act); \
+  } while (0)
+    if (dout_dt == DAFK_F32 && dx_dt == DAFK_F32) LAUNCHW(float, float);
+    else if (dout_dt == DAFK_F32 && dx_dt == DAFK_BF16) LAUNCHW(float, __nv_bfloat16);
+    else if (dout_dt == DAFK_BF16 && dx_dt == DAFK_F32) LAUNCHW(__nv_bfloat16, float);
+    else if (dout_dt == DAFK_BF16 && dx_dt == DAFK_BF16) LAUNCHW(__nv_bfloat16, __nv_bfloat16);
+    else { set_error("dafk_bn_bwd_apply: bad dtype"); return DAFK_ERR_BAD_ARG; }
+#undef LAUNCHW
+    return check_launch("dafk_bn_bwd_apply");
+  }
 #define LAUNCH(TD, TO)                                                                                                  \
   do {                                                                                                                  \
     if (x_dt == DAFK_BF16)                                                                                              \
@@ -458,6 +490,52 @@ int dafk_bn_bwd_apply(const void* dout, int dout_dt, const void* x, int x_dt, co
   else { set_error("dafk_bn_bwd_apply: bad dtype"); return DAFK_ERR_BAD_ARG; }
 #undef LAUNCH
   return check_launch("dafk_bn_bwd_apply");
+}
+
+int dafk_bn_wide_supported(int C) { return bn_wide_ok(C) ? 1 : 0; }
+int64_t dafk_bn_wide_ws_bytes(int C) { return (int64_t)bn_wide_ws_bytes(C); }
+
+int dafk_bn_stats_fused(const void* x, int x_dt, void* ws, int64_t ws_bytes, int64_t M, int C, float eps, float momentum,
+                        float* mean, float* rstd, float* moving_mean, float* moving_var, void* stream) {
+  DAFK_REQUIRE(M > 0 && C > 0, DAFK_ERR_BAD_ARG, "dafk_bn_stats_fused: bad shape");
+  DAFK_REQUIRE(bn_wide_ok(C), DAFK_ERR_UNSUPPORTED, "dafk_bn_stats_fused: C must be a power of two in [8,1024] (got %d)", C);
+  DAFK_REQUIRE(x && ws && mean && rstd, DAFK_ERR_BAD_ARG, "dafk_bn_stats_fused: null pointer");
+  DAFK_REQUIRE(ws_bytes >= (int64_t)bn_wide_ws_bytes(C), DAFK_ERR_BAD_ARG, "dafk_bn_stats_fused: workspace too small");
+  DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(ws), DAFK_ERR_ALIGN, "dafk_bn_stats_fused: alignment");
+  const int64_t n8 = M * C / 8;
+  unsigned* ticket = (unsigned*)ws;
+  double* wacc = (double*)((char*)ws + 16);
+  cudaStream_t s = as_stream(stream);
+  const int grid = bn_wide_grid(n8, 2, 4);
+  if (x_dt == DAFK_F32)
+    bn_stats_wide_kernel<float><<<grid, BW_T, 0, s>>>((const float*)x, ticket, wacc, n8, C, M, eps, momentum, mean, rstd, moving_mean, moving_var);
+  else if (x_dt == DAFK_BF16)
+    bn_stats_wide_kernel<__nv_bfloat16><<<grid, BW_T, 0, s>>>((const __nv_bfloat16*)x, ticket, wacc, n8, C, M, eps, momentum, mean, rstd, moving_mean, moving_var);
+  else { set_error("dafk_bn_stats_fused: bad dtype"); return DAFK_ERR_BAD_ARG; }
+  return check_launch("dafk_bn_stats_fused");
+}
+
+int dafk_bn_bwd_reduce_fused(const void* dout, int dout_dt, const void* x, int x_dt, const float* mean, const float* rstd,
+                             const float* gamma, const float* beta, double* acc, void* ws, int64_t ws_bytes, int64_t M,
+                             int C, int act, void* stream) {
+  DAFK_REQUIRE(M > 0 && C > 0, DAFK_ERR_BAD_ARG, "dafk_bn_bwd_reduce_fused: bad shape");
+  DAFK_REQUIRE(bn_wide_ok(C), DAFK_ERR_UNSUPPORTED, "dafk_bn_bwd_reduce_fused: C must be a power of two in [8,1024] (got %d)", C);
+  DAFK_REQUIRE(dout && x && mean && rstd && gamma && beta && acc && ws, DAFK_ERR_BAD_ARG, "dafk_bn_bwd_reduce_fused: null pointer");
+  DAFK_REQUIRE(ws_bytes >= (int64_t)bn_wide_ws_bytes(C), DAFK_ERR_BAD_ARG, "dafk_bn_bwd_reduce_fused: workspace too small");
+  DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(dout) && DAFK_ALIGNED16(ws), DAFK_ERR_ALIGN, "dafk_bn_bwd_reduce_fused: alignment");
+  const int64_t n8 = M * C / 8;
+  unsigned* ticket = (unsigned*)ws;
+  double* wacc = (double*)((char*)ws + 16);
+  cudaStream_t s = as_stream(stream);
+  const int grid = bn_wide_grid(n8, 1, 2);
+  if (dout_dt == DAFK_F32)
+    { if (x_dt == DAFK_BF16) bn_bwd_reduce_wide_kernel<float, __nv_bfloat16><<<grid, BW_T, 0, s>>>((const float*)dout, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, ticket, wacc, acc, n8, C, act);
+      else bn_bwd_reduce_wide_kernel<float, float><<<grid, BW_T, 0, s>>>((const float*)dout, (const float*)x, mean, rstd, gamma, beta, ticket, wacc, acc, n8, C, act); }
+  else if (dout_dt == DAFK_BF16)
+    { if (x_dt == DAFK_BF16) bn_bwd_reduce_wide_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, BW_T, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, ticket, wacc, acc, n8, C, act);
+      else bn_bwd_reduce_wide_kernel<__nv_bfloat16, float><<<grid, BW_T, 0, s>>>((const __nv_bfloat16*)dout, (const float*)x, mean, rstd, gamma, beta, ticket, wacc, acc, n8, C, act); }
+  else { set_error("dafk_bn_bwd_reduce_fused: bad dtype"); return DAFK_ERR_BAD_ARG; }
+  return check_launch("dafk_bn_bwd_reduce_fused");
 }
 
 int dafk_bn_bwd_frozen(const float* dout, const float* x, const float* mean, const float* rstd, const float* gamma,

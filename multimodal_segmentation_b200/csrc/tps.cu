@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) tps_apply_kernel(const float* __restrict_
 
 // ------------------------------------------------------------------ fused fast path
 constexpr int TPS_MAXN = 32;   // control points
-constexpr int TPS_BS = 8;      // samples per CTA (grid.y splits the batch)
+constexpr int TPS_BS = 2;      // samples per CTA (grid.y splits the batch): 3136 CTAs at B=32, 224^2
 constexpr int TPS_T = 256;
 
 struct Bilin {
@@ -163,7 +163,13 @@ __device__ __forceinline__ Bilin bilin_setup(float x, float y, int H, int W) {
 }
 
 // per-sample spline coefficients in smem: coef[s][j][2], j<n: w ; j=n..n+2: v   ((row,col) components)
-__device__ __forceinline__ void tps_coefs(const float* __restrict__ theta, const float* __restrict__ consts, int n,
+// `consts` points to the CTA's shared-memory copy of the constants (tps_stage_consts): the 25-term dot products
+// below would otherwise be chains of dependent L2 loads in the prologue of every CTA
+__device__ __forceinline__ void tps_stage_consts(const float* __restrict__ consts, int n, float* cst) {
+  for (int e = threadIdx.x; e < n * (n + 5); e += blockDim.x) cst[e] = consts[e];
+  __syncthreads();
+}
+__device__ __forceinline__ void tps_coefs(const float* __restrict__ theta, const float* consts, int n,
                                           int b0, int nb, float* coef /*[TPS_BS][TPS_MAXN+3][2]*/) {
   const float* Winv = consts + 2 * n;
   const float* Vinv = Winv + n * n;
@@ -186,12 +192,13 @@ template <int C>
 __global__ void __launch_bounds__(TPS_T) tps_warp_fwd_kernel(const float* __restrict__ vol, const float* __restrict__ theta,
                                                              const float* __restrict__ consts, float* __restrict__ out,
                                                              float* __restrict__ locs, int B, int H, int W, int n) {
-  __shared__ float cs[TPS_MAXN * 2];
+  __shared__ float cst[TPS_MAXN * (TPS_MAXN + 5)];
   __shared__ float coef[TPS_BS * (TPS_MAXN + 3) * 2];
+  const float* cs = cst;
   const int b0 = blockIdx.y * TPS_BS;
   const int nb = min(TPS_BS, B - b0);
-  for (int e = threadIdx.x; e < 2 * n; e += blockDim.x) cs[e] = consts[e];
-  tps_coefs(theta, consts, n, b0, nb, coef);
+  tps_stage_consts(consts, n, cst);
+  tps_coefs(theta, cst, n, b0, nb, coef);
   __syncthreads();
   const int HW = H * W;
   const int m = blockIdx.x * TPS_T + threadIdx.x;
@@ -266,12 +273,13 @@ __global__ void __launch_bounds__(TPS_T) tps_warp_bwd_kernel(const float* __rest
   constexpr int LD = TPS_T + 1;
   float* Phi = dyn;                          // [(TPS_MAXN+3)][LD]
   float* D = Phi + (TPS_MAXN + 3) * LD;      // [2*TPS_BS][LD]
-  __shared__ float cs[TPS_MAXN * 2];
+  __shared__ float cst[TPS_MAXN * (TPS_MAXN + 5)];
   __shared__ float coef[TPS_BS * (TPS_MAXN + 3) * 2];
+  const float* cs = cst;
   const int b0 = blockIdx.y * TPS_BS;
   const int nb = min(TPS_BS, B - b0);
-  for (int e = threadIdx.x; e < 2 * n; e += blockDim.x) cs[e] = consts[e];
-  tps_coefs(theta, consts, n, b0, nb, coef);
+  tps_stage_consts(consts, n, cst);
+  tps_coefs(theta, cst, n, b0, nb, coef);
   __syncthreads();
   const int HW = H * W;
   const int m = blockIdx.x * TPS_T + threadIdx.x;

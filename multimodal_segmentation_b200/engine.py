@@ -423,6 +423,10 @@ class Conv2D:
         if self.s2d_eligible(srcs):
             return self._call_s2d(ctx, srcs, act, alpha)
         code = ACT[act]
+        if (USE_TC and self.k == 1 and self.stride == 1 and len(srcs) == 1 and code == ACT_NONE
+                and od == torch.float32 and srcs[0].data.dtype == torch.bfloat16
+                and ops.conv1x1_supported(self.cin, self.cout)):
+            return self._call_1x1(ctx, srcs[0])
         W = srcs[0].shape[2]
         nc = self.stride == 1 and USE_TC
         nc_f = nc and ops.nc_supported(self.cin, self.cout, self.k, self.k, W, self.pad, 0)
@@ -474,6 +478,29 @@ class Conv2D:
                     else:
                         dx = ops.conv2d_dgrad(g, self.kernel.data, tuple(tape_x.shape), self.stride, self.pad)
                     accumulate(tape_x, dx)
+
+            ctx.tape.record(bw)
+        return y
+
+    # ---- pointwise heads on a 64-channel bf16 map (anatomy 64 -> 8, segmentor 64 -> 5): HBM-stream kernels
+    def _call_1x1(self, ctx, xin):
+        bias = self.bias.data if self.bias is not None else None
+        y = Var(ops.conv1x1_fwd(xin.data, self.kernel.data, bias), grad_dtype=torch.float32)
+        if ctx.rec(xin, self.kernel):
+            y.requires_grad = True
+
+            def bw():
+                g = y.grad
+                y.grad = None
+                if g is None:
+                    return
+                if g.dtype != torch.float32:
+                    g = ops.cast(g, torch.float32)
+                if self.kernel.requires_grad:
+                    db = self.bias.grad if (self.bias is not None and self.bias.requires_grad) else None
+                    ops.conv1x1_wgrad(xin.data, g, self.kernel.grad, db)
+                if xin.requires_grad:
+                    accumulate(xin, ops.conv1x1_dgrad(g, self.kernel.data))
 
             ctx.tape.record(bw)
         return y

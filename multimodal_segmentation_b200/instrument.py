@@ -2,7 +2,10 @@
 the timed region, on the launching stream).  Off by default: zero overhead on the product path."""
 import torch
 
+import os
+
 enabled = False
+by_shape = bool(os.environ.get("DAFK_PROFILE_SHAPES"))    # diagnostic: one record per (family, layer shape)
 _records = {}
 
 
@@ -10,9 +13,11 @@ def reset():
     _records.clear()
 
 
-def timed(name, flops, nbytes, fn):
+def timed(name, flops, nbytes, fn, tag=None):
     if not enabled:
         return fn()
+    if by_shape and tag is not None:
+        name = "%s %s" % (name, tag)
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()

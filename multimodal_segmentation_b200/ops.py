@@ -192,10 +192,34 @@ def max_bwd(a, b, dout):
 
 
 # ---------------------------------------------------------------------------- batch norm
+_bn_ws_cache = {}
+
+
+def _bn_ws(device):
+    """persistent self-resetting workspace of the wide BatchNorm reductions (zeroed once; every launch leaves it
+    zero), one per device: all kernels of a rank run on one stream"""
+    key = str(device)
+    if key not in _bn_ws_cache:
+        n = int(_lib.lib().fn["dafk_bn_wide_ws_bytes"](1024))
+        _bn_ws_cache[key] = zero_(torch.empty(n, dtype=torch.uint8, device=device))
+    return _bn_ws_cache[key]
+
+
+def _bn_wide(C, M):
+    return M > 0 and bool(_lib.lib().fn["dafk_bn_wide_supported"](C))
+
+
 def bn_stats_finalize(x, eps, momentum, moving_mean=None, moving_var=None):
     _chk(x)
     C = x.shape[-1]
     M = x.numel() // C
+    if _bn_wide(C, M):
+        ws = _bn_ws(x.device)
+        mean, rstd = f32(C), f32(C)
+        instrument.timed("bn_stats", 0, float(x.element_size()) * x.numel(),
+                         lambda: call("bn_stats_fused", x, _dt(x), ws, ws.numel(), M, C, float(eps), float(momentum), mean,
+                                      rstd, moving_mean, moving_var, _S()))
+        return mean, rstd
     acc = torch.empty(2 * C, dtype=torch.float64, device=x.device)
     zero_(acc)
     instrument.timed("bn_stats", 0, float(x.element_size()) * x.numel(), lambda: call("bn_stats", x, _dt(x), acc, M, C, _S()))
@@ -225,10 +249,16 @@ def bn_bwd(dout, x, mean, rstd, gamma, beta, act, dgamma, dbeta, dx_dtype=torch.
     C = x.shape[-1]
     M = x.numel() // C
     acc = torch.empty(2 * C, dtype=torch.float64, device=x.device)
-    zero_(acc)
     nb_in = float(x.element_size()) * x.numel() + dout.numel() * dout.element_size()
-    instrument.timed("bn_bwd_reduce", 0, nb_in,
-                     lambda: call("bn_bwd_reduce", dout, _dt(dout), x, _dt(x), mean, rstd, gamma, beta, acc, M, C, act, _S()))
+    if _bn_wide(C, M):
+        ws = _bn_ws(x.device)
+        instrument.timed("bn_bwd_reduce", 0, nb_in,
+                         lambda: call("bn_bwd_reduce_fused", dout, _dt(dout), x, _dt(x), mean, rstd, gamma, beta, acc, ws,
+                                      ws.numel(), M, C, act, _S()))
+    else:
+        zero_(acc)
+        instrument.timed("bn_bwd_reduce", 0, nb_in,
+                         lambda: call("bn_bwd_reduce", dout, _dt(dout), x, _dt(x), mean, rstd, gamma, beta, acc, M, C, act, _S()))
     dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
     instrument.timed("bn_bwd_apply", 0, nb_in + dx.numel() * dx.element_size(),
                      lambda: call("bn_bwd_apply", dout, _dt(dout), x, _dt(x), mean, rstd, gamma, beta, acc, dx, _dt(dx), dgamma,
@@ -382,7 +412,7 @@ def conv3x3_tc_fwd(x0, x1, wp, bias, Cout, out_dtype=torch.float32, row_off=0):
     nb = 2.0 * N * H * W * (C0 + C1) + y.numel() * y.element_size()
     instrument.timed("conv_tc_fwd+dgrad (tcgen05)", fl, nb,
                      lambda: call("conv3x3_tc_fwd", x0, C0, x1, C1, wp, wp.shape[1], row_off, bias, y, _dt(y), N, H, W,
-                                  Cout, _S()))
+                                  Cout, _S()), tag=(N, H, W, C0 + C1, Cout, 3, 1, str(out_dtype)[6:]))
     return y
 
 
@@ -419,7 +449,8 @@ def conv_tc_fwd(x0, x1, wp, bias, Cout, KH, KW, stride, pad, out_dtype=torch.flo
     nb = 2.0 * x0.numel() + (0 if x1 is None else 2.0 * x1.numel()) + N * Ho * Wo * Cout * out.element_size()
     instrument.timed("conv_tc_fwd+dgrad (tcgen05)", fl, nb,
                      lambda: call("conv_tc_fwd", x0, C0, x1, C1, wp, wp.shape[1], row_off, bias, out, _dt(out), N, H, W,
-                                  Cout, KH, KW, stride, pad, Ho, Wo, out.stride(0), out.stride(1), out.stride(2), _S()))
+                                  Cout, KH, KW, stride, pad, Ho, Wo, out.stride(0), out.stride(1), out.stride(2), _S()),
+                     tag=(N, H, W, C0 + C1, Cout, KH, stride, str(out.dtype)[6:], Ho))
     return out
 
 
@@ -430,7 +461,7 @@ def conv_tc_wgrad(x, dy, dw, cin_off, KH, KW, stride, pad):
     fl = 2.0 * N * Ho * Wo * Cout * KH * KW * Cin
     instrument.timed("conv_tc_wgrad (tcgen05)", fl, 2.0 * (x.numel() + dy.numel()),
                      lambda: call("conv_tc_wgrad", x, Cin, cin_off, dw.shape[2], dy, Cout, dw, N, H, W, KH, KW, stride,
-                                  pad, Ho, Wo, _S()))
+                                  pad, Ho, Wo, _S()), tag=(N, H, W, Cin, Cout, KH, stride))
 
 
 def conv3x3_tc_wgrad(x, dy, dw, cin_off=0):
@@ -440,7 +471,8 @@ def conv3x3_tc_wgrad(x, dy, dw, cin_off=0):
     Cout = dy.shape[-1]
     fl = 2.0 * N * H * W * Cout * 9 * Cin
     instrument.timed("conv_tc_wgrad (tcgen05)", fl, 2.0 * (x.numel() + dy.numel()),
-                     lambda: call("conv3x3_tc_wgrad", x, Cin, cin_off, dw.shape[2], dy, Cout, dw, N, H, W, _S()))
+                     lambda: call("conv3x3_tc_wgrad", x, Cin, cin_off, dw.shape[2], dy, Cout, dw, N, H, W, _S()),
+                     tag=(N, H, W, Cin, Cout, 3, 1))
 
 
 # ---------------------------------------------------------------------------- narrow-channel tcgen05 convolution
@@ -478,7 +510,7 @@ def conv_nc_fwd(x, wp, bias, Cout, KH, KW, pad, act=ACT_NONE, alpha=0.0, out_dty
     nb = x.numel() * x.element_size() + y.numel() * y.element_size()
     instrument.timed("conv_nc_fwd+dgrad (tcgen05)", fl, nb,
                      lambda: call("conv_nc_fwd", x, _dt(x), wp, bias, y, _dt(y), N, H, W, Cin, Cout, KH, KW, pad, act,
-                                  float(alpha), _S()))
+                                  float(alpha), _S()), tag=(N, H, W, Cin, Cout, KH, pad, str(x.dtype)[6:], str(out_dtype)[6:]))
     return y
 
 
@@ -490,7 +522,47 @@ def conv_nc_wgrad(x, dy, dw, db, pad):
     fl = 2.0 * dy.numel() * KH * KW * Cin
     nb = x.numel() * x.element_size() + dy.numel() * dy.element_size()
     instrument.timed("conv_nc_wgrad (tcgen05)", fl, nb,
-                     lambda: call("conv_nc_wgrad", x, _dt(x), dy, _dt(dy), dw, db, N, H, W, Cin, Cout, KH, KW, pad, _S()))
+                     lambda: call("conv_nc_wgrad", x, _dt(x), dy, _dt(dy), dw, db, N, H, W, Cin, Cout, KH, KW, pad, _S()),
+                     tag=(N, H, W, Cin, Cout, KH, pad, str(x.dtype)[6:], str(dy.dtype)[6:]))
+
+
+# ---------------------------------------------------------------------------- pointwise 64 -> <=8 heads
+def conv1x1_supported(Cin, Cout):
+    return USE_NC and bool(_lib.lib().fn["dafk_conv1x1_supported"](Cin, Cout))
+
+
+def conv1x1_fwd(x, w, bias, round_bf16=True):
+    """x bf16 [..,64], w f32 [1,1,64,Cout] -> y f32 [..,Cout]"""
+    _chk(x, w, bias)
+    assert x.dtype == torch.bfloat16
+    Cin, Cout = w.shape[-2], w.shape[-1]
+    M = x.numel() // Cin
+    y = f32(*x.shape[:-1], Cout)
+    instrument.timed("conv1x1 (64 -> <=8 heads)", 2.0 * M * Cin * Cout, 2.0 * x.numel() + 4.0 * y.numel(),
+                     lambda: call("conv1x1_fwd", x, w, bias, y, M, Cin, Cout, int(round_bf16), _S()), tag=("fwd", M, Cout))
+    return y
+
+
+def conv1x1_dgrad(dy, w, round_bf16=True):
+    """dy f32 [..,Cout] -> dx bf16 [..,64]"""
+    _chk(dy, w)
+    assert dy.dtype == torch.float32
+    Cin, Cout = w.shape[-2], w.shape[-1]
+    M = dy.numel() // Cout
+    dx = torch.empty(tuple(dy.shape[:-1]) + (Cin,), dtype=torch.bfloat16, device=dy.device)
+    instrument.timed("conv1x1 (64 -> <=8 heads)", 2.0 * M * Cin * Cout, 4.0 * dy.numel() + 2.0 * dx.numel(),
+                     lambda: call("conv1x1_dgrad", dy, w, dx, M, Cin, Cout, int(round_bf16), _S()), tag=("dgrad", M, Cout))
+    return dx
+
+
+def conv1x1_wgrad(x, dy, dw, db, round_bf16=True):
+    """dw[1,1,64,Cout] += x^T dy; db += sum dy (db may be None)"""
+    _chk(x, dy, dw, db)
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.float32
+    Cin, Cout = dw.shape[-2], dw.shape[-1]
+    M = x.numel() // Cin
+    instrument.timed("conv1x1 (64 -> <=8 heads)", 2.0 * M * Cin * Cout, 2.0 * x.numel() + 4.0 * dy.numel(),
+                     lambda: call("conv1x1_wgrad", x, dy, dw, db, M, Cin, Cout, int(round_bf16), _S()), tag=("wgrad", M, Cout))
 
 
 def space_to_depth2(x):
