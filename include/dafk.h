@@ -394,6 +394,32 @@ int dafk_spade_bwd(const float* dy, const float* x, const double* acc, const flo
 int dafk_pair_dice(const float* a, const float* b, float* out, double* ws, int B, int64_t HWC,
                    void* stream);
 
+/* ---- automated-pairing trainers (models/dafnet.py:224-334; csrc/pairing.cu) --------------------------------------
+ * Per-sample losses L[b] whose Balancer-weighted sum over the candidate pairs is the `SegmentorDef` / `DecoderDef`
+ * output (loss costs.ypred = mean over the batch).  The backward passes take per-sample coefficients coef[b]
+ * (= loss_weight / B * w[b,j], written by dafk_pair_combine).
+ * dafk_segloss_pb_*: costs.make_combined_dice_bce_perbatch (costs.py:138-143) = soft Dice over the first `nch`
+ *   channels + lambda_bce * weighted_cross_entropy_perbatch with the reference's swapped arguments (costs.py:88-108):
+ *   class weights from the prediction summed over the batch, log of softmax(mask); pred/target f32 [B,HW,C], C <= 8.
+ *   ws: dafk_segloss_pb_ws_doubles(B,C) doubles, written by fwd, read by bwd.
+ * dafk_mae_pb_*: costs.mae_single_input (costs.py:24-26), mean |pred - target| over the n = H*W*C values of a sample.
+ * dafk_pair_dice_bwd: backward of dafk_pair_dice (model_components/balancer.py:33-38); ws as left by the forward;
+ *   g[B] = d loss / d dice; da or db may be NULL.
+ * dafk_pair_combine: loss[0] += weight/B * sum_b sum_j w[b,j] L[j,b]; dw[b,j] = weight/B * L[j,b];
+ *   coef[j,b] = weight/B * w[b,j]   (w == NULL: all ones; dw may be NULL).  w [B,P], L and coef [P,B]. */
+int64_t dafk_segloss_pb_ws_doubles(int B, int C);
+int dafk_segloss_pb_fwd(const float* pred, const float* target, int C, int nch, float lambda_bce, double* ws, float* L,
+                        int B, int64_t HW, void* stream);
+int dafk_segloss_pb_bwd(const float* target, int C, int nch, float lambda_bce, const double* ws, const float* coef,
+                        float* dpred, int B, int64_t HW, void* stream);
+int dafk_mae_pb_fwd(const float* pred, const float* target, double* ws, float* L, int B, int64_t n, void* stream);
+int dafk_mae_pb_bwd(const float* pred, const float* target, const float* coef, float* dpred, int B, int64_t n,
+                    void* stream);
+int dafk_pair_dice_bwd(const float* a, const float* b, const double* ws, const float* g, float* da, float* db, int B,
+                       int64_t HWC, void* stream);
+int dafk_pair_combine(const float* w, const float* L, float weight, float* loss, float* dw, float* coef, int B, int P,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

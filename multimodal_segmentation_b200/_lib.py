@@ -115,7 +115,13 @@ def call(name, *args):
         from . import instrument
         if instrument.enabled:
             ptrs = [_ptr(a) for a in args]
-            rc = instrument.timed("all:" + name, 0, 0, lambda: f(*ptrs))
+            label = "all:" + name
+            if instrument.by_shape:      # diagnostic: split every entry point by its largest operand
+                ts = [a for a in args if hasattr(a, "numel")]
+                if ts:
+                    big = max(ts, key=lambda t: t.numel())
+                    label += " %s %.2fM" % (str(big.dtype)[6:], big.numel() / 1e6)
+            rc = instrument.timed(label, 0, 0, lambda: f(*ptrs))
             if f.restype is ctypes.c_int and rc != 0:
                 raise DafkError("%s failed (%d): %s" % (full, rc, L.last_error()))
             return rc

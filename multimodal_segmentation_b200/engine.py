@@ -955,6 +955,52 @@ def loss_l1l2(ctx, pred, target, kind, weight, loss_slot, cval=0.0):
         accumulate(pred, g)
 
 
+def pair_dice(ctx, a, b):
+    """model_components/balancer.py:33-38: per-sample Dice overlap [B,1], differentiable in both anatomies"""
+    out, ws = ops.pair_dice(a.data, b.data, want_ws=True)
+    y = Var(out)
+    if ctx.rec(a, b):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is None:
+                return
+            da, db = ops.pair_dice_bwd(a.data, b.data, ws, g, a.requires_grad, b.requires_grad)
+            if da is not None:
+                accumulate(a, da)
+            if db is not None:
+                accumulate(b, db)
+
+        ctx.tape.record(bw)
+    return y
+
+
+def loss_pairs(ctx, kind, preds, target, weights, weight, loss_slot, nch=None):
+    """Add()([Multiply()([w_j, PerSampleLoss([target, pred_j])]) ...]) with loss costs.ypred (models/dafnet.py:283-315):
+    loss += weight * mean_b sum_j w[b,j] * L_j[b].  kind 'seg' = make_combined_dice_bce_perbatch, 'mae' =
+    mae_single_input.  `weights` is the Balancer output Var [B,P].  Terminal node: the gradients towards the
+    predictions and the weights are produced here."""
+    P, B = len(preds), preds[0].shape[0]
+    L = torch.empty((P, B), dtype=torch.float32, device=preds[0].data.device)
+    wss = []
+    for j, p in enumerate(preds):
+        pd = p.data if p.data.dtype == torch.float32 else ops.cast(p.data, torch.float32)
+        wss.append((pd, ops.segloss_pb_fwd(pd, target, nch, L[j]) if kind == "seg" else ops.mae_pb_fwd(pd, target, L[j])))
+    need = ctx.rec(*preds) or ctx.rec(weights)
+    dw, coef = ops.pair_combine(weights.data, L, weight, loss_slot, want_dw=need)
+    if not need:
+        return
+    if weights.requires_grad:
+        accumulate(weights, dw)
+    for j, p in enumerate(preds):
+        if p.requires_grad:
+            pd, ws = wss[j]
+            g = ops.segloss_pb_bwd(pd, target, nch, ws, coef[j]) if kind == "seg" else ops.mae_pb_bwd(pd, target, coef[j])
+            accumulate(p, g)
+
+
 def vae_sample(ctx, mu, logvar, eps, kl_weight, loss_slot):
     """z = mu + exp(.5 lv) eps (utils/sdnet_utils.py:9-21) and the KL output whose mean is the
     `Enc_Modality` loss (costs.py:186-195); the KL gradient is folded into the backward of z."""

@@ -76,11 +76,63 @@ class PairedData(object):
     def get_masks_modi(self, i):
         return self.masks[i]
 
-    def randomise_pairs(self, *a, **k):
-        raise NotImplementedError("pair randomisation belongs to the automated-pairing path")
+    SLICES_PER_VOLUME = 8        # synthetic "volumes": runs of consecutive items
 
-    def expand_pairs(self, *a, **k):
-        raise NotImplementedError("pair expansion belongs to the automated-pairing path")
+    def volumes(self):
+        n = self.size()
+        return [(a, min(n, a + self.SLICES_PER_VOLUME)) for a in range(0, n, self.SLICES_PER_VOLUME)]
+
+    def randomise_pairs(self, length=3, seed=None):
+        """loaders/MultimodalPairedData.py:143-166: re-pair modality 0 with a slice up to `length` positions away
+        inside the same volume (images and masks of modality 0 move together)"""
+        if seed is not None:
+            np.random.seed(seed)
+        new_images, new_masks = [], []
+        for a, b in self.volumes():
+            images, masks = self.images[0][a:b], self.masks[0][a:b]
+            n = images.shape[0]
+            offsets = np.random.randint(-length, length, size=n)
+            for off in range(min(length, n)):
+                if offsets[off] + off < 0:
+                    offsets[off] = np.random.randint(-off, length, size=1)[0]
+            for i in range(1, min(length, n)):
+                if offsets[-i] + (n - i) >= n:
+                    offsets[-i] = np.random.randint(-length, i, size=1)[0]
+            idx = np.clip(np.arange(n) + offsets, 0, n - 1)
+            new_images.append(images[idx])
+            new_masks.append(masks[idx])
+        self.images[0] = np.concatenate(new_images, axis=0)
+        self.masks[0] = np.concatenate(new_masks, axis=0)
+
+    def expand_pairs(self, offsets, mod_i, neighborhood=2):
+        """loaders/MultimodalPairedData.py:91-141: every image of modality `mod_i` becomes `neighborhood` candidate
+        images stacked on the channel axis -- channel 0 the expertly paired slice, the others drawn without
+        replacement from the 2*offsets neighbouring slices of the same volume"""
+        assert mod_i in [0, 1], "mod_i can be in [0, 1]. It defines the neighborhood of which modality to enlarge"
+        all_images = []
+        for a, b in self.volumes():
+            img_mod1 = self.images[mod_i][a:b]
+            num_images = self.images[1 - mod_i][a:b].shape[0]
+            vol = []
+            for i in range(num_images):
+                if img_mod1.shape[0] < 2 * offsets + 1:
+                    value_range = list(range(0, img_mod1.shape[0])) + [0] * (2 * offsets + 1 - img_mod1.shape[0])
+                elif i < offsets:
+                    value_range = list(range(0, 2 * offsets + 1))
+                elif i + offsets >= num_images:
+                    value_range = list(range(num_images - (2 * offsets + 1), num_images))
+                else:
+                    value_range = list(range(i - offsets, i + offsets + 1))
+                value_range.insert(0, value_range.pop(value_range.index(i)))      # expert pair first
+                assert len(value_range) == 2 * offsets + 1
+                if len(value_range) > neighborhood:
+                    value_range = [value_range[0]] + list(np.random.choice(value_range[1:], size=neighborhood - 1,
+                                                                           replace=False))
+                vol.append(np.concatenate([img_mod1[k:k + 1] for k in value_range], axis=-1))
+            all_images.append(np.concatenate(vol, axis=0))
+        all_images = np.concatenate(all_images, axis=0)
+        assert all_images.shape[-1] == neighborhood, "%s vs %s" % (all_images.shape[-1], neighborhood)
+        self.images[mod_i] = all_images
 
 
 class SyntheticChaosLoader(object):

@@ -1,6 +1,6 @@
 """Balancer (reference: model_components/balancer.py:11-38): Dice(x1, x_i) for i=2..4 -> Dense(5, relu)
--> Dense(n_pairs, name='beta') -> softmax.  Only *used* by the automated-pairing trainers
-(models/dafnet.py:283-287); inference path implemented, its training path is a 'next' row."""
+-> Dense(n_pairs, name='beta') -> softmax.  Used by the automated-pairing trainers (models/dafnet.py:283-287,352-361);
+the overlap is differentiable in both anatomies (engine.pair_dice), so the pairing weights train the encoders too."""
 from .. import engine as E
 from .. import ops
 from ..keras_like import BuildScope, Model
@@ -19,7 +19,7 @@ def build(conf):
     beta = E.Dense(a, r, "beta", 5, conf.n_pairs)
 
     def fwd(ctx, x1, x2, x3, x4):
-        overlap = [E.Var(dice([x1.data, x.data])) for x in (x2, x3, x4)]
+        overlap = [E.pair_dice(ctx, x1, x) for x in (x2, x3, x4)]
         l = E.concat(ctx, overlap)
         l = d1(ctx, l, "relu")
         w = beta(ctx, l)

@@ -16,6 +16,9 @@ import torch
 
 from .. import costs
 from .. import ops
+from ..callbacks.swa import SWA
+from ..model_components import anatomy_encoder, anatomy_fuser, balancer, decoder, modality_encoder, segmentor
+from ..models.discriminator import Discriminator
 from ..utils import data_utils
 from ..utils.distributions import NormalDistribution
 from .base_executor import Executor
@@ -44,6 +47,66 @@ class DAFNetExecutor(Executor):
         self._static = None
         self._graph_pending = []
         self._next = None
+        self.init_swa_models()
+
+    # ------------------------------------------------------------------ stochastic weight averaging
+    SWA_EPOCH = 40
+
+    def init_swa_models(self):
+        """dafnet_executor.py:41-56"""
+        e = self.SWA_EPOCH
+        self.swa_D_Mask = SWA(e, Discriminator(self.conf.d_mask_params).build, None)
+        has_dimg = hasattr(self.conf, "d_image_params")
+        self.swa_D_Image1 = SWA(e, Discriminator(self.conf.d_image_params).build, None) if has_dimg else None
+        self.swa_D_Image2 = SWA(e, Discriminator(self.conf.d_image_params).build, None) if has_dimg else None
+        self.swa_Enc_Anatomy1 = SWA(e, anatomy_encoder.build, self.conf.anatomy_encoder)
+        self.swa_Enc_Anatomy2 = SWA(e, anatomy_encoder.build, self.conf.anatomy_encoder)
+        self.swa_Enc_Modality = SWA(e, modality_encoder.build, self.conf)
+        self.swa_Anatomy_Fuser = SWA(e, anatomy_fuser.build, self.conf)
+        self.swa_Segmentor = SWA(e, segmentor.build, self.conf)
+        self.swa_Decoder = SWA(e, decoder.build, self.conf)
+        self.swa_Balancer = SWA(e, balancer.build, self.conf) if getattr(self.model, "Balancer", None) is not None else None
+        self.set_swa_model_weights()
+
+    def set_swa_model_weights(self):
+        """dafnet_executor.py:58-68"""
+        M = self.model
+        self.swa_D_Mask.model = M.D_Mask
+        if self.swa_D_Image1 is not None:
+            self.swa_D_Image1.model = getattr(M, "D_Image1", None)
+            self.swa_D_Image2.model = getattr(M, "D_Image2", None)
+        self.swa_Enc_Anatomy1.model = M.Encoders_Anatomy[0]
+        self.swa_Enc_Anatomy2.model = M.Encoders_Anatomy[1]
+        self.swa_Enc_Modality.model = M.Enc_Modality
+        self.swa_Anatomy_Fuser.model = M.Anatomy_Fuser
+        self.swa_Segmentor.model = M.Segmentor
+        self.swa_Decoder.model = M.Decoder
+        if self.swa_Balancer is not None:
+            self.swa_Balancer.model = M.Balancer
+
+    def get_swa_models(self):
+        """dafnet_executor.py:207-210"""
+        lst = [self.swa_D_Mask, self.swa_D_Image1, self.swa_D_Image2, self.swa_Enc_Anatomy1, self.swa_Enc_Anatomy2,
+               self.swa_Enc_Modality, self.swa_Anatomy_Fuser, self.swa_Segmentor, self.swa_Decoder, self.swa_Balancer]
+        return [m for m in lst if m is not None and m.model is not None]
+
+    def save_models(self, postfix=""):
+        """dafnet_executor.py:286-301: the files hold the SWA weights (identical to the live ones until SWA_EPOCH)"""
+        if not hasattr(self.model, "_components"):
+            return self.model.save_models()         # MMSDNet keeps its single-file format (models/mmsdnet.py:42-60)
+        model_folder = self.conf.folder + "/models/"
+        os.makedirs(model_folder, exist_ok=True)
+        names = [("D_Mask", self.swa_D_Mask), ("D_Image1", self.swa_D_Image1), ("D_Image2", self.swa_D_Image2),
+                 ("Enc_Anatomy1", self.swa_Enc_Anatomy1), ("Enc_Anatomy2", self.swa_Enc_Anatomy2),
+                 ("Enc_Modality", self.swa_Enc_Modality), ("Anatomy_Fuser", self.swa_Anatomy_Fuser),
+                 ("Segmentor", self.swa_Segmentor), ("Decoder", self.swa_Decoder), ("Balancer", self.swa_Balancer)]
+        for fname, swa_m in names:
+            if swa_m is None or swa_m.model is None:
+                continue
+            # same arrays a clone would hold (get_clone_model().save_weights in the reference), without building it
+            ws = swa_m.swa_weights if swa_m.swa_weights is not None else swa_m.model.get_weights()
+            order = [p.name for p in swa_m.model.weight_list()]
+            np.savez(model_folder + fname + postfix + ".npz", __order__=np.array(order), **dict(zip(order, ws)))
 
     # ------------------------------------------------------------------ data
     def init_train_data(self):
@@ -58,6 +121,7 @@ class DAFNetExecutor(Executor):
             return None
         self.data = self.loader.load_all_modalities_concatenated(self.conf.split, "training", self.conf.image_downsample)
         self.data.sample(int(np.round(self.conf.l_mix * self.data.num_volumes)), seed=self.conf.seed)
+        self._pair_up(self.data)
         self.data_len = self.data.size()
         nm = self.loader.num_masks
         # add_residual (dafnet_executor.py:493-494) applied once when the labelled set is staged
@@ -69,11 +133,22 @@ class DAFNetExecutor(Executor):
             return None
         self.ul_data = self.loader.load_all_modalities_concatenated(self.conf.split, "training", self.conf.image_downsample,
                                                                    seed=self.conf.seed + 77)
+        self._pair_up(self.ul_data)
         if self.data is None or self.ul_data.size() > self.data.size():
             self.data_len = self.ul_data.size()
         nm = self.loader.num_masks
         return self.get_data_generator(train_images=[self.ul_data.get_images_modi(i) for i in range(2)],
                                        train_labels=[self.add_residual(self.ul_data.get_masks_modi(0)[..., 0:nm])])
+
+    def _pair_up(self, data):
+        """dafnet_executor.py:89-93,127-131: candidate pairs for the automated-pairing trainers (images get n_pairs
+        channels, channel 0 = expert pair) or randomised pairs"""
+        if getattr(self.conf, "randomise", False):
+            data.randomise_pairs(self.conf.n_pairs - 1, seed=self.conf.seed)
+        elif getattr(self.conf, "automatedpairing", False):
+            np.random.seed(self.conf.seed)
+            data.expand_pairs(self.conf.n_pairs - 1, 0, neighborhood=self.conf.n_pairs)
+            data.expand_pairs(self.conf.n_pairs - 1, 1, neighborhood=self.conf.n_pairs)
 
     def _init_disciminator_mask_generator(self):
         """real masks for D_Mask: a separate draw (dafnet_executor.py:516-519)"""
@@ -133,11 +208,14 @@ class DAFNetExecutor(Executor):
             for self.batch in range(self.batches):
                 self.train_batch(epoch_loss)
             self.flush_losses(epoch_loss)
+            self.set_swa_model_weights()
+            for swa_m in self.get_swa_models():
+                swa_m.on_epoch_end(self.epoch)
             self.validate(epoch_loss)
             row = [np.mean(epoch_loss[n]) if len(epoch_loss[n]) else 0.0 for n in names]
             with open(csv_path, "a") as f:
                 f.write(str(self.epoch) + "," + ",".join("%.6g" % v for v in row) + "\n")
-            self.model.save_models()
+            self.save_models()
             # EarlyStopping(min_delta=0.01, patience=60) on val_loss_mod2_fused (dafnet_executor.py:222,263-284)
             cur = row[names.index("val_loss_mod2_fused")]
             if best is None or cur < best - 0.01:
@@ -145,7 +223,11 @@ class DAFNetExecutor(Executor):
             else:
                 wait += 1
                 if wait >= 60:
-                    log.info("Early stopping")
+                    log.info("Finished training from early stopping criterion")
+                    # final model parameters = the stochastic weight average (dafnet_executor.py:268-284)
+                    for swa_m in self.get_swa_models():
+                        swa_m.on_train_end()
+                    self.save_models()
                     break
 
     def validate(self, epoch_loss):
@@ -155,13 +237,21 @@ class DAFNetExecutor(Executor):
         nm = self.loader.num_masks
         x0, x1 = valid.get_images_modi(0), valid.get_images_modi(1)
         real0, real1 = valid.get_masks_modi(0)[..., :nm], valid.get_masks_modi(1)[..., :nm]
-        s0 = self.model.Encoders_Anatomy[0].predict(x0)
-        s1 = self.model.Encoders_Anatomy[1].predict(x1)
-        mask1 = self.model.Segmentor.predict(s0)
-        mask2 = self.model.Segmentor.predict(s1)
-        s0_def, s_fused = self.model.Anatomy_Fuser.predict([s0, s1])
-        mask3 = self.model.Segmentor.predict(s0_def)
-        mask4 = self.model.Segmentor.predict(s_fused)
+        # the reference validates through the SWA clones (dafnet_executor.py:319-331); up to SWA_EPOCH their weights ARE
+        # the live weights, so the clones are only built once averaging has started
+        averaging = getattr(self, "epoch", 0) > self.SWA_EPOCH and self.swa_Segmentor.swa_weights is not None
+        pick = (lambda swa_m, live: swa_m.get_clone_model()) if averaging else (lambda swa_m, live: live)
+        enc0 = pick(self.swa_Enc_Anatomy1, self.model.Encoders_Anatomy[0])
+        enc1 = pick(self.swa_Enc_Anatomy2, self.model.Encoders_Anatomy[1])
+        seg = pick(self.swa_Segmentor, self.model.Segmentor)
+        fuser = pick(self.swa_Anatomy_Fuser, self.model.Anatomy_Fuser)
+        s0 = enc0.predict(x0)
+        s1 = enc1.predict(x1)
+        mask1 = seg.predict(s0)
+        mask2 = seg.predict(s1)
+        s0_def, s_fused = fuser.predict([s0, s1])
+        mask3 = seg.predict(s0_def)
+        mask4 = seg.predict(s_fused)
         l1 = 1 - costs.dice(real0, mask1, binarise=True)
         l2 = 1 - costs.dice(real1, mask2, binarise=True)
         l3 = 1 - costs.dice(real1, mask3, binarise=True)
@@ -175,8 +265,6 @@ class DAFNetExecutor(Executor):
     # ------------------------------------------------------------------ one step
     def train_batch(self, epoch_loss):
         """dafnet_executor.py:369-387"""
-        if getattr(self.conf, "automatedpairing", False):
-            raise NotImplementedError("automated pairing is a 'next' row (SURVEY.md 8f-1)")
         if self._graph is not None:
             # the snapshots of the previous replay must be read before they are overwritten
             self.flush_losses(epoch_loss)
@@ -300,6 +388,8 @@ class DAFNetExecutor(Executor):
         self._run_image_d(self._stage_image_d())
 
     def _run_generator(self, supervised, t):
+        if getattr(self.conf, "automatedpairing", False):
+            return self._run_generator_paired(supervised, t)
         if supervised:
             x1, x2, m1, m2, z1, z2, eps1, eps2 = t
             tr = self.model.supervised_trainer
@@ -309,6 +399,29 @@ class DAFNetExecutor(Executor):
             tr = self.model.unsupervised_trainer
             tr.train_on_device(x1, x2, z1, z2, eps1, eps2, m1)
         self._pending.append((tr, tr.book.snapshot(), "gen"))
+
+    def _run_generator_paired(self, supervised, t):
+        """train_{un,}supervised_automated_pairing + prepare_data_to_train (dafnet_executor.py:436-499): the staged
+        images carry n_pairs candidates on the channel axis; candidate 0 is the expert pair"""
+        P = int(self.conf.n_pairs)
+        x1p, x2p = t[0], t[1]
+        split = lambda x: [ops.slice_channels(x, i, 1) for i in range(P)]
+        x1_lst, x2_lst = split(x1p), split(x2p)
+        if supervised:
+            m1, m2, z1, z2, eps1, eps2 = t[2:]
+            tr = self.model.supervised_trainer
+            tr.train_on_device(*(x1_lst + x2_lst + [z1, z2, eps1, eps2, m1, m2]))
+        else:
+            m1, z1, z2, eps1, eps2 = t[2:]
+            tr = self.model.unsupervised_trainer
+            tr.train_on_device(*(x1_lst + x2_lst + [z1, z2, eps1, eps2, m1]))
+        self._pending.append((tr, tr.book.snapshot(), "gen"))
+
+    def train_supervised_automated_pairing(self, epoch_loss):
+        self._run_generator(True, self._stage_generator(True))
+
+    def train_unsupervised_automated_pairing(self, epoch_loss):
+        self._run_generator(False, self._stage_generator(False))
 
     def _run_mask_d(self, t):
         x1, x2, m1, m2, idx1, idx2 = t

@@ -780,10 +780,68 @@ def spade_bwd(dy, x, acc, gamma, beta, act=ACT_LRELU, alpha=0.2, eps=1e-3):
     return dx, dg, db
 
 
-def pair_dice(a, b):
+def pair_dice(a, b, want_ws=False):
     _chk(a, b)
     B = a.shape[0]
     out = f32(B, 1)
     ws = torch.empty(3 * B, dtype=torch.float64, device=a.device)
     call("pair_dice", a, b, out, ws, B, a.numel() // B, _S())
-    return out
+    return (out, ws) if want_ws else out
+
+
+def pair_dice_bwd(a, b, ws, g, need_a=True, need_b=True):
+    """g [B,1] = d loss / d dice -> (da, db)"""
+    _chk(a, b, ws, g)
+    B = a.shape[0]
+    da = torch.empty_like(a) if need_a else None
+    db = torch.empty_like(b) if need_b else None
+    call("pair_dice_bwd", a, b, ws, g, da, db, B, a.numel() // B, _S())
+    return da, db
+
+
+# ---------------------------------------------------------------------------- automated-pairing losses
+def segloss_pb_fwd(pred, target, nch, L_row, lambda_bce=0.01):
+    """per-sample dice + lambda * swapped per-batch wBCE (costs.py:88-108,138-143) -> L_row[B]; returns the workspace"""
+    _chk(pred, target, L_row)
+    B, C = pred.shape[0], pred.shape[-1]
+    assert target.shape[-1] == C
+    HW = pred.numel() // (B * C)
+    n = int(_lib.lib().fn["dafk_segloss_pb_ws_doubles"](B, C))
+    ws = torch.empty(n, dtype=torch.float64, device=pred.device)
+    call("segloss_pb_fwd", pred, target, C, nch, float(lambda_bce), ws, L_row, B, HW, _S())
+    return ws
+
+
+def segloss_pb_bwd(pred, target, nch, ws, coef_row, lambda_bce=0.01):
+    _chk(pred, target, ws, coef_row)
+    B, C = pred.shape[0], pred.shape[-1]
+    HW = pred.numel() // (B * C)
+    g = torch.empty_like(pred)
+    call("segloss_pb_bwd", target, C, nch, float(lambda_bce), ws, coef_row, g, B, HW, _S())
+    return g
+
+
+def mae_pb_fwd(pred, target, L_row):
+    _chk(pred, target, L_row)
+    B = pred.shape[0]
+    ws = torch.empty(B, dtype=torch.float64, device=pred.device)
+    call("mae_pb_fwd", pred, target, ws, L_row, B, pred.numel() // B, _S())
+    return ws
+
+
+def mae_pb_bwd(pred, target, coef_row):
+    _chk(pred, target, coef_row)
+    B = pred.shape[0]
+    g = torch.empty_like(pred)
+    call("mae_pb_bwd", pred, target, coef_row, g, B, pred.numel() // B, _S())
+    return g
+
+
+def pair_combine(w, L, weight, loss, want_dw=True):
+    """w [B,P] (or None = ones), L [P,B] -> (dw [B,P] or None, coef [P,B]); loss[0] += weight/B * sum w*L"""
+    _chk(w, L, loss)
+    P, B = L.shape
+    dw = torch.empty((B, P), dtype=torch.float32, device=L.device) if (want_dw and w is not None) else None
+    coef = torch.empty_like(L)
+    call("pair_combine", w, L, float(weight), loss, dw, coef, B, P, _S())
+    return dw, coef

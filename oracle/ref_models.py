@@ -307,6 +307,85 @@ def dafnet_generator_loss(W, conf, x1, x2, z1_in, z2_in, eps1, eps2, m1, m2=None
     return total, L, inter, st
 
 
+def balancer(W, s_mod2, s_list):
+    """model_components/balancer.py:11-31 + models/dafnet.py:352-361 -> softmax weights [B, n_pairs]"""
+    overlap = torch.cat([R.pair_dice(s_mod2, s) for s in s_list], -1)
+    l = R.relu(R.dense(overlap, W["bal_dense/kernel"], W["bal_dense/bias"]))
+    return R.softmax(R.dense(l, W["beta/kernel"], W["beta/bias"]))
+
+
+def dafnet_generator_loss_automated(W, conf, x1_lst, x2_lst, z1_in, z2_in, eps1, eps2, m1, m2=None, supervised=True):
+    """models/dafnet.py:250-334 (get_params_automated_pairing) + :229-235 (losses, weights) with the targets fed by
+    model_executors/dafnet_executor.py:447-454 / :470-477.  n_pairs candidate images per modality; candidate 0 is the
+    expertly paired one.  Every encoder / segmentor call site is a separate application (own BatchNorm statistics)."""
+    st = BNState(W, training=True)
+    nm = conf["num_masks"]
+    dt = conf.get("decoder_type", "film")
+    x1, x2 = x1_lst[0], x2_lst[0]
+    s1_lst = [anatomy_encoder(W, x, st, "enc1_", "shared_") for x in x1_lst]
+    s2_lst = [anatomy_encoder(W, x, st, "enc2_", "shared_") for x in x2_lst]
+    s1, s2 = s1_lst[0], s2_lst[0]
+    mu1, lv1 = modality_encoder(W, s1, x1)
+    mu2, lv2 = modality_encoder(W, s2, x2)
+    z1, kl1 = R.sampling(mu1, lv1, eps1), R.kl(mu1, lv1)
+    z2, kl2 = R.sampling(mu2, lv2, eps2), R.kl(mu2, lv2)
+    M1 = segmentor(W, s1, st)
+    M2 = segmentor(W, s2, st)
+    y1 = decoder(W, s1, z1, dt)
+    y2 = decoder(W, s2, z2, dt)
+    adv_m1 = discriminator(W, "D_Mask", M1[..., 0:nm])
+    adv_m2 = discriminator(W, "D_Mask", M2[..., 0:nm])
+    adv_y1 = discriminator(W, "D_Image1", y1)
+    adv_y2 = discriminator(W, "D_Image2", y2)
+    s1_def_lst = [anatomy_fuser(W, s1_i, s2)[0] for s1_i in s1_lst]
+    w1 = balancer(W, s2, s1_def_lst)
+    s2_def_lst = [anatomy_fuser(W, s2_i, s1)[0] for s2_i in s2_lst]
+    w2 = balancer(W, s1, s2_def_lst)
+    P = len(x1_lst)
+    y2_s1_def_lst = [decoder(W, sd, z2, dt) for sd in s1_def_lst]
+    y1_s2_def_lst = [decoder(W, sd, z1, dt) for sd in s2_def_lst]
+    y2_s1_def = sum(w1[:, j:j + 1] * R.mae_single_input(x2, y2_s1_def_lst[j]) for j in range(P))
+    y1_s2_def = sum(w2[:, j:j + 1] * R.mae_single_input(x1, y1_s2_def_lst[j]) for j in range(P))
+    M1_s2_def_lst = [segmentor(W, sd, st) for sd in s2_def_lst]
+    # Multiply()([w [B,1], loss [B]]): keras expands the rank-1 loss to [B,1]
+    m1_s2_def = sum(w2[:, j:j + 1] * R.combined_dice_bce_perbatch(m1, M1_s2_def_lst[j], nm)[:, None] for j in range(P))
+    M2_s1_def_lst = [segmentor(W, sd, st) for sd in s1_def_lst]
+    if supervised:
+        m2_s1_def = sum(w1[:, j:j + 1] * R.combined_dice_bce_perbatch(m2, M2_s1_def_lst[j], nm)[:, None] for j in range(P))
+    adv_m2_s1_def = discriminator(W, "D_Mask", M2_s1_def_lst[0][..., 0:nm])
+    adv_m1_s2_def = discriminator(W, "D_Mask", M1_s2_def_lst[0][..., 0:nm])
+    adv_y2_s1_def = discriminator(W, "D_Image2", y2_s1_def_lst[0])
+    adv_y1_s2_def = discriminator(W, "D_Image1", y1_s2_def_lst[0])
+    z1_rec = modality_encoder(W, s1, decoder(W, s1, z1_in, dt))[0]
+    z2_rec = modality_encoder(W, s2, decoder(W, s2, z2_in, dt))[0]
+
+    ones = lambda t: torch.ones_like(t)
+    L = {}
+    if supervised:
+        L["Segmentor_0"] = conf["w_sup_M"] * R.combined_dice_bce(m1, M1, nm)
+        L["Segmentor_1"] = conf["w_sup_M"] * R.combined_dice_bce(m2, M2, nm)
+        L["SegmentorDef_0"] = conf["w_sup_M"] * m1_s2_def.mean()          # costs.ypred
+        L["SegmentorDef_1"] = conf["w_sup_M"] * m2_s1_def.mean()
+    else:
+        L["Segmentor_0"] = conf["w_sup_M"] * R.combined_dice_bce(m1, M1, nm)
+        L["SegmentorDef_0"] = conf["w_sup_M"] * m1_s2_def.mean()
+    for i, a in enumerate((adv_m1, adv_m2, adv_m1_s2_def, adv_m2_s1_def)):
+        L["D_Mask_%d" % i] = conf["w_adv_M"] * R.mse(ones(a), a)
+    L["Decoder_0"] = conf["w_rec_X"] * R.mae(x1, y1)
+    L["Decoder_1"] = conf["w_rec_X"] * R.mae(x2, y2)
+    L["DecoderDef_0"] = conf["w_rec_X"] * y1_s2_def.mean()
+    L["DecoderDef_1"] = conf["w_rec_X"] * y2_s1_def.mean()
+    for i, a in enumerate((adv_y1, adv_y2, adv_y1_s2_def, adv_y2_s1_def)):
+        L["D_Image_%d" % i] = conf["w_adv_X"] * R.mse(ones(a), a)
+    L["KL_0"] = conf["w_kl"] * kl1.mean()
+    L["KL_1"] = conf["w_kl"] * kl2.mean()
+    L["ZRec_0"] = conf["w_rec_Z"] * R.mae(z1_in, z1_rec)
+    L["ZRec_1"] = conf["w_rec_Z"] * R.mae(z2_in, z2_rec)
+    total = sum(L.values())
+    inter = dict(s1=s1, s2=s2, w1=w1, w2=w2, M1=M1, y1=y1, s1_def_lst=s1_def_lst, s2_def_lst=s2_def_lst)
+    return total, L, inter, st
+
+
 def mmsdnet_generator_loss(W, conf, x1, x2, eps, seg_targets, rec_targets, supervised=True, rounding=True):
     """models/mmsdnet.py:95-192 (unsupervised / supervised trainer graphs and their loss lists) with the targets fed by
     model_executors/mmsdnet_executor.py:257-260 / :287-290.  Two independent UNets (weights enc1_*, enc2_*), the fused

@@ -331,6 +331,31 @@ def combined_dice_bce(y_true, y_pred, num_classes, lambda_bce=0.01):
     return dice_loss(y_true, y_pred, num_classes) + lambda_bce * weighted_cross_entropy_loss(y_true, y_pred)
 
 
+def weighted_cross_entropy_perbatch(y_pred, y_true):
+    """costs.py:88-108, with the parameter names of the reference signature -> [B] (mean over pixels per sample)."""
+    B, H, W, C = y_true.shape
+    n = y_true.sum(dim=(0, 1, 2))
+    n_tot = n.sum()
+    weights = n_tot / (n + 1e-12)
+    yp = y_pred.reshape(-1, H * W, C)
+    yt = y_true.reshape(-1, H * W, C)
+    sm = torch.softmax(yp, dim=-1)
+    w_ce = -(yt * torch.log(sm + 1e-12) * weights).sum(2)
+    return w_ce.mean(1)
+
+
+def combined_dice_bce_perbatch(y_true, y_pred, num_classes, lambda_bce=0.01):
+    """costs.py:138-143 make_combined_dice_bce_perbatch: per-sample Dice over the first num_classes channels + the
+    per-batch cross entropy, again called (y_true, y_pred) into a (y_pred, y_true) signature -> [B]."""
+    return (dice_coef_perbatch(y_true[..., :num_classes], y_pred[..., :num_classes])
+            + lambda_bce * weighted_cross_entropy_perbatch(y_true, y_pred))
+
+
+def mae_single_input(y1, y2):
+    """costs.py:24-26 -> [B, C]."""
+    return (y1 - y2).abs().mean(dim=(1, 2))
+
+
 def mae(y_true, y_pred):
     return (y_pred - y_true).abs().mean()
 

@@ -149,6 +149,20 @@ def main():
             out["align_0"], out["align_1"] = al[0], al[1]
             np.random.seed(3)
             out["normal_dist_seed3"] = NormalDistribution().sample((3, 8))
+
+            # ---- automated-pairing losses exactly as models/dafnet.py:283-315 calls them (drawn last: the arrays above
+            #      keep their values): SegmentorLoss([m_input, pred]) on 5-channel one-hot masks / softmax outputs,
+            #      DecoderLoss([x, y]), and the Balancer's overlap (model_components/balancer.py:33-38)
+            out["pb_combined5"] = np.asarray(COSTS.make_combined_dice_bce_perbatch(4)(t(true5), t(pred)))
+            out["pb_wce_as_called"] = np.asarray(COSTS.weighted_cross_entropy_perbatch(t(true5), t(pred)))
+            xa, ya = rs.uniform(-1, 1, size=(3, 8, 6, 1)), rs.uniform(-1, 1, size=(3, 8, 6, 1))
+            out["pb_mae_x"], out["pb_mae_y"] = xa, ya
+            out["pb_mae"] = np.asarray(COSTS.mae_single_input([t(xa), t(ya)]))
+            from model_components import balancer as BAL
+            sa = (rs.uniform(size=(3, 8, 6, 8)) > 0.6).astype(np.float64)
+            sb = (rs.uniform(size=(3, 8, 6, 8)) > 0.6).astype(np.float64)
+            out["bal_a"], out["bal_b"] = sa, sb
+            out["bal_dice"] = np.asarray(BAL.dice([t(sa), t(sb)]))
         finally:
             pass
     path = os.path.join(HERE, "golden_ref.npz")

@@ -79,3 +79,16 @@ def test_spectral_regulariser_matches_reference(ops):
     dW = ops.zeros(dim, cout)
     ops.spectral_reg(gpu(W).view(dim, cout), gpu(G["spectral_u0"]), 10.0, loss, dW)
     assert abs(float(cpu(loss)[0]) - float(G["spectral_loss"])) < 1e-4 * float(G["spectral_loss"])
+
+
+def test_automated_pairing_kernels_against_reference_vectors(ops):
+    """csrc/pairing.cu forward values against the vectors produced by the reference's costs.py / balancer.py"""
+    true5, pred = gpu(G["loss_true"]), gpu(G["loss_pred"])
+    B = true5.shape[0]
+    L = torch.empty(2, B, device="cuda")
+    ops.segloss_pb_fwd(pred, true5, 4, L[0])
+    ops.mae_pb_fwd(gpu(G["pb_mae_y"]), gpu(G["pb_mae_x"]), L[1])
+    assert rel_l2(cpu(L[0]), G["pb_combined5"]) < 1e-5
+    assert rel_l2(cpu(L[1]), G["pb_mae"][:, 0]) < 1e-5
+    d = ops.pair_dice(gpu(G["bal_a"]), gpu(G["bal_b"]))
+    assert rel_l2(cpu(d), G["bal_dice"]) < 1e-6

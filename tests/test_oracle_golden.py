@@ -99,3 +99,13 @@ def test_host_helpers():
     assert np.array_equal(al[0], G["align_0"]) and np.array_equal(al[1], G["align_1"])
     np.random.seed(3)
     close(NormalDistribution().sample((3, 8)), G["normal_dist_seed3"])
+
+
+def test_automated_pairing_losses():
+    """costs.make_combined_dice_bce_perbatch / weighted_cross_entropy_perbatch / mae_single_input and the Balancer's
+    Dice overlap, with the argument order of models/dafnet.py:283-315"""
+    true5, pred = T(G["loss_true"]), T(G["loss_pred"])
+    close(R.combined_dice_bce_perbatch(true5, pred, 4), G["pb_combined5"])
+    close(R.weighted_cross_entropy_perbatch(true5, pred), G["pb_wce_as_called"])
+    close(R.mae_single_input(T(G["pb_mae_x"]), T(G["pb_mae_y"])), G["pb_mae"])
+    close(R.pair_dice(T(G["bal_a"]), T(G["bal_b"])), G["bal_dice"])
