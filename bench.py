@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--l_mix", type=float, default=1.0)
-    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--cpu-batch", type=int, default=8, help="pairs per CPU train_batch sample (8 pairs ~ 15 s on 16 host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-tc", action="store_true")
@@ -300,9 +300,15 @@ def run_b200(args):
     if kern:
         dom = max(kern.values(), key=lambda k: k["ms"])
         ach = dom["flops"] / (dom["ms"] / 1000.0) / 1e12 if dom["ms"] > 0 else 0.0
+        traffic, traffic_note = None, "no ncu capture found under profiles/"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "conv_tc_traffic.json")))
+            traffic, traffic_note = tj["dram_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": dom["name"], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach / peak_tf, "traffic": None,
-                "traffic_note": "per-launch dram bytes of this kernel family: profiles/r1_conv_tc_fwd_ncu.txt",
+                "frac": ach / peak_tf, "traffic": traffic, "traffic_note": traffic_note,
+                "algorithmic_bytes_per_launch": dom["bytes"] / max(dom["n"], 1),
                 "peak_source": peak_src,
                 "launches": dom["n"], "share_of_step": (dom["ms"] / kern_steps) / ms_step,
                 "timing": "CUDA events around every launch of the family in a host-launched pass over the same step "
