@@ -96,6 +96,15 @@ int dafk_film_fwd(const float* x, const float* gamma, const float* beta, float* 
  * dgamma/dbeta are OVERWRITTEN.  ws: B*C*2 doubles of scratch. */
 int dafk_film_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma,
                   float* dbeta, double* ws, int B, int64_t HW, int C, void* stream);
+/* the tail of the decoder's FiLM layer in one pass (model_components/decoder.py:50-54):
+ *   y = res + act(x*gamma + beta)   (res may be NULL; act: NONE / RELU / LRELU with slope alpha)
+ * backward: dy is first multiplied by act'(x*gamma + beta) (recomputed), then as dafk_film_bwd; the gradient towards
+ * `res` is dy itself. */
+int dafk_film_act_add_fwd(const float* x, const float* gamma, const float* beta, const float* res, float* y, int B,
+                          int64_t HW, int C, int act, float alpha, void* stream);
+int dafk_film_act_add_bwd(const float* dy, const float* x, const float* gamma, const float* beta, float* dx,
+                          float* dgamma, float* dbeta, double* ws, int B, int64_t HW, int C, int act, float alpha,
+                          void* stream);
 
 /* ------------------------------------------------------------------ Maximum
  * model_components/anatomy_fuser.py:33  keras Maximum = tf.maximum; gradient goes

@@ -213,9 +213,21 @@ __global__ void __launch_bounds__(TPB) gather_rows_kernel(const float* __restric
 
 // ---------------------------------------------------------------- FiLM
 // x:[B,HW,C]; one float4 per thread-iteration; C % 4 == 0.
+// optional fused tail of the decoder's FiLM layer (model_components/decoder.py:50-54): y = res + lrelu(x*gamma + beta)
+__device__ __forceinline__ float film_act(float z, int act, float alpha) {
+  // __fmul_rn: the product is rounded on its own (as in the stand-alone activation kernel), never contracted into the
+  // residual add that follows
+  return (act == DAFK_ACT_LRELU) ? (z > 0.f ? z : __fmul_rn(alpha, z)) : ((act == DAFK_ACT_RELU) ? fmaxf(z, 0.f) : z);
+}
+__device__ __forceinline__ float film_act_grad(float z, int act, float alpha) {
+  if (act == DAFK_ACT_LRELU) return z > 0.f ? 1.f : (z < 0.f ? alpha : 0.f);
+  if (act == DAFK_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
 __global__ void __launch_bounds__(TPB) film_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, float* __restrict__ y,
-                                                       int64_t HWC, int C, int64_t n4) {
+                                                       const float* __restrict__ beta, const float* __restrict__ res,
+                                                       float* __restrict__ y, int64_t HWC, int C, int64_t n4, int act,
+                                                       float alpha) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     int64_t e = i << 2;
@@ -224,15 +236,21 @@ __global__ void __launch_bounds__(TPB) film_fwd_kernel(const float* __restrict__
     float4 v = ldg_stream4(x + e);
     float4 g = *reinterpret_cast<const float4*>(gamma + b * C + c);
     float4 t = *reinterpret_cast<const float4*>(beta + b * C + c);
-    v.x = v.x * g.x + t.x; v.y = v.y * g.y + t.y; v.z = v.z * g.z + t.z; v.w = v.w * g.w + t.w;
+    v.x = film_act(v.x * g.x + t.x, act, alpha); v.y = film_act(v.y * g.y + t.y, act, alpha);
+    v.z = film_act(v.z * g.z + t.z, act, alpha); v.w = film_act(v.w * g.w + t.w, act, alpha);
+    if (res) {
+      float4 r = ldg_stream4(res + e);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
     stg_stream4(y + e, v);
   }
 }
 
 // grid = (chunks, B).  Each thread owns a fixed group of 4 channels.
 __global__ void __launch_bounds__(TPB) film_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                       const float* __restrict__ gamma, float* __restrict__ dx,
-                                                       double* __restrict__ ws, int64_t HWC, int C) {
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float* __restrict__ dx, double* __restrict__ ws, int64_t HWC, int C,
+                                                       int act, float alpha) {
   extern __shared__ float sm[];
   int b = blockIdx.y;
   const float* dyb = dy + (int64_t)b * HWC;
@@ -240,12 +258,18 @@ __global__ void __launch_bounds__(TPB) film_bwd_kernel(const float* __restrict__
   float* dxb = dx + (int64_t)b * HWC;
   int c = (threadIdx.x * 4) % C;
   float4 g = *reinterpret_cast<const float4*>(gamma + (int64_t)b * C + c);
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (act != DAFK_ACT_NONE) t = *reinterpret_cast<const float4*>(beta + (int64_t)b * C + c);
   float ag[4] = {0, 0, 0, 0}, ab[4] = {0, 0, 0, 0};
   int64_t n4 = HWC >> 2;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 d = ldg_stream4(dyb + 4 * i);
     float4 v = ldg_stream4(xb + 4 * i);
+    if (act != DAFK_ACT_NONE) {      // gradient of the fused activation at z = x*gamma + beta
+      d.x *= film_act_grad(v.x * g.x + t.x, act, alpha); d.y *= film_act_grad(v.y * g.y + t.y, act, alpha);
+      d.z *= film_act_grad(v.z * g.z + t.z, act, alpha); d.w *= film_act_grad(v.w * g.w + t.w, act, alpha);
+    }
     ag[0] += d.x * v.x; ag[1] += d.y * v.y; ag[2] += d.z * v.z; ag[3] += d.w * v.w;
     ab[0] += d.x; ab[1] += d.y; ab[2] += d.z; ab[3] += d.w;
     d.x *= g.x; d.y *= g.y; d.z *= g.z; d.w *= g.w;
@@ -418,15 +442,42 @@ int dafk_film_fwd(const float* x, const float* gamma, const float* beta, float* 
   DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(y) && DAFK_ALIGNED16(gamma) && DAFK_ALIGNED16(beta),
                DAFK_ERR_ALIGN, "dafk_film_fwd: pointers must be 16-byte aligned");
   int64_t n4 = (int64_t)B * HW * C / 4;
-  film_fwd_kernel<<<bw_grid(n4, TPB), TPB, 0, as_stream(stream)>>>(x, gamma, beta, y, HW * C, C, n4);
+  film_fwd_kernel<<<bw_grid(n4, TPB), TPB, 0, as_stream(stream)>>>(x, gamma, beta, nullptr, y, HW * C, C, n4, DAFK_ACT_NONE, 0.f);
   return check_launch("dafk_film_fwd");
 }
 
+int dafk_film_act_add_fwd(const float* x, const float* gamma, const float* beta, const float* res, float* y, int B,
+                          int64_t HW, int C, int act, float alpha, void* stream) {
+  DAFK_REQUIRE(B >= 0 && HW >= 0 && C > 0, DAFK_ERR_BAD_ARG, "dafk_film_act_add_fwd: bad shape");
+  if (B == 0 || HW == 0) return DAFK_OK;
+  DAFK_REQUIRE(x && gamma && beta && y, DAFK_ERR_BAD_ARG, "dafk_film_act_add_fwd: null pointer");
+  DAFK_REQUIRE(C % 4 == 0, DAFK_ERR_UNSUPPORTED, "dafk_film_act_add_fwd: C must be a multiple of 4 (got %d)", C);
+  DAFK_REQUIRE(act == DAFK_ACT_NONE || act == DAFK_ACT_RELU || act == DAFK_ACT_LRELU, DAFK_ERR_UNSUPPORTED,
+               "dafk_film_act_add_fwd: act must be NONE, RELU or LRELU");
+  DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(y) && DAFK_ALIGNED16(gamma) && DAFK_ALIGNED16(beta) && DAFK_ALIGNED16(res),
+               DAFK_ERR_ALIGN, "dafk_film_act_add_fwd: pointers must be 16-byte aligned");
+  int64_t n4 = (int64_t)B * HW * C / 4;
+  film_fwd_kernel<<<bw_grid(n4, TPB), TPB, 0, as_stream(stream)>>>(x, gamma, beta, res, y, HW * C, C, n4, act, alpha);
+  return check_launch("dafk_film_act_add_fwd");
+}
+
+int dafk_film_act_add_bwd(const float* dy, const float* x, const float* gamma, const float* beta, float* dx,
+                          float* dgamma, float* dbeta, double* ws, int B, int64_t HW, int C, int act, float alpha,
+                          void* stream);
+
 int dafk_film_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
                   double* ws, int B, int64_t HW, int C, void* stream) {
+  return dafk_film_act_add_bwd(dy, x, gamma, nullptr, dx, dgamma, dbeta, ws, B, HW, C, DAFK_ACT_NONE, 0.f, stream);
+}
+
+int dafk_film_act_add_bwd(const float* dy, const float* x, const float* gamma, const float* beta, float* dx,
+                          float* dgamma, float* dbeta, double* ws, int B, int64_t HW, int C, int act, float alpha,
+                          void* stream) {
   DAFK_REQUIRE(B >= 0 && HW >= 0 && C > 0, DAFK_ERR_BAD_ARG, "dafk_film_bwd: bad shape");
   if (B == 0) return DAFK_OK;
   DAFK_REQUIRE(dy && x && gamma && dx && dgamma && dbeta && ws, DAFK_ERR_BAD_ARG, "dafk_film_bwd: null pointer");
+  DAFK_REQUIRE(act == DAFK_ACT_NONE || ((act == DAFK_ACT_RELU || act == DAFK_ACT_LRELU) && beta && DAFK_ALIGNED16(beta)),
+               DAFK_ERR_BAD_ARG, "dafk_film_bwd: a fused activation needs beta (16-byte aligned)");
   DAFK_REQUIRE(C >= 4 && (1024 % C) == 0, DAFK_ERR_UNSUPPORTED,
                "dafk_film_bwd: C must be a power of two in [4,1024] (got %d)", C);
   DAFK_REQUIRE(DAFK_ALIGNED16(dy) && DAFK_ALIGNED16(x) && DAFK_ALIGNED16(dx) && DAFK_ALIGNED16(gamma),
@@ -438,7 +489,7 @@ int dafk_film_bwd(const float* dy, const float* x, const float* gamma, float* dx
   int cap = (kNumSMs * 8 + B - 1) / B;
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
-  film_bwd_kernel<<<dim3(chunks, B), TPB, 2 * C * sizeof(float), s>>>(dy, x, gamma, dx, ws, HW * C, C);
+  film_bwd_kernel<<<dim3(chunks, B), TPB, 2 * C * sizeof(float), s>>>(dy, x, gamma, beta, dx, ws, HW * C, C, act, alpha);
   int rc = check_launch("dafk_film_bwd");
   if (rc) return rc;
   film_bwd_finish_kernel<<<(B * C + 127) / 128, 128, 0, s>>>(ws, dgamma, dbeta, B, C);

@@ -849,6 +849,30 @@ def film(ctx, x, gamma, beta):
     return y
 
 
+def film_act_add(ctx, x, gamma, beta, res, act, alpha=0.0):
+    """res + act(FiLM(x, gamma, beta)): the three element-wise layers that close a FiLM block
+    (model_components/decoder.py:50-54) as one forward and one backward pass"""
+    code = ACT[act]
+    y = Var(ops.film_act_add_fwd(x.data, gamma.data, beta.data, res.data, code, alpha))
+    if ctx.rec(x, gamma, beta, res):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is None:
+                return
+            if x.requires_grad or gamma.requires_grad or beta.requires_grad:
+                dx, dg, db = ops.film_act_add_bwd(g, x.data, gamma.data, beta.data, code, alpha)
+                accumulate(x, dx)
+                accumulate(gamma, dg)
+                accumulate(beta, db)
+            accumulate(res, g, owned=False)
+
+        ctx.tape.record(bw)
+    return y
+
+
 def maximum(ctx, a, b):
     y = Var(ops.max_fwd(a.data, b.data))
     if ctx.rec(a, b):

@@ -25,6 +25,10 @@ class _FilmLayer:
         l2 = self.c2(ctx, l1)
         gamma = self.g(ctx, z, "lrelu", 0.3)
         beta = self.b(ctx, z, "lrelu", 0.3)
+        if (l2.data.dtype == l1.data.dtype == gamma.data.dtype and l2.data.dtype.is_floating_point
+                and l2.data.element_size() == 4):
+            # FiLM -> LeakyReLU -> Add as one pass over the feature map (same arithmetic, same order)
+            return E.film_act_add(ctx, l2, gamma, beta, l1, "lrelu", 0.3)
         l2 = self.film(ctx, [l2, gamma, beta])
         l2 = E.activation(ctx, l2, "lrelu", 0.3)
         return E.add(ctx, l1, l2)

@@ -177,6 +177,26 @@ def film_bwd(dy, x, gamma):
     return dx, dg, db
 
 
+def film_act_add_fwd(x, gamma, beta, res, act, alpha=0.0):
+    """res + act(x*gamma + beta) in one pass (decoder.py:50-54)"""
+    _chk(x, gamma, beta, res)
+    B, C = x.shape[0], x.shape[-1]
+    y = torch.empty_like(x)
+    call("film_act_add_fwd", x, gamma, beta, res, y, B, x.numel() // (B * C), C, act, float(alpha), _S())
+    return y
+
+
+def film_act_add_bwd(dy, x, gamma, beta, act, alpha=0.0):
+    _chk(dy, x, gamma, beta)
+    B, C = x.shape[0], x.shape[-1]
+    dx = torch.empty_like(x)
+    dg = f32(B, C)
+    db = f32(B, C)
+    ws = torch.empty(B * C * 2, dtype=torch.float64, device=x.device)
+    call("film_act_add_bwd", dy, x, gamma, beta, dx, dg, db, ws, B, x.numel() // (B * C), C, act, float(alpha), _S())
+    return dx, dg, db
+
+
 def max_fwd(a, b):
     _chk(a, b)
     out = torch.empty_like(a)

@@ -132,6 +132,30 @@ def test_film(ops):
     np.testing.assert_array_equal(cpu(ops.film_fwd(gpu(x), one, zero)), x)
 
 
+def test_film_block_tail_fused(ops):
+    """l1 + LeakyReLU(0.3)(FiLM(l2, gamma, beta)) (model_components/decoder.py:50-54) as one kernel each way:
+    bit-identical to the three separate kernels forward, and the oracle's gradients backward"""
+    from multimodal_segmentation_b200._lib import ACT_LRELU
+    B, H, W, C = 3, 20, 24, 8
+    x = rng(0).normal(size=(B, H, W, C)).astype(np.float32)
+    res = rng(4).normal(size=(B, H, W, C)).astype(np.float32)
+    gm = rng(1).normal(size=(B, C)).astype(np.float32)
+    bt = rng(2).normal(size=(B, C)).astype(np.float32)
+    g = rng(3).normal(size=x.shape).astype(np.float32)
+    xt, rt, gt, btt = t(x, grad=True), t(res, grad=True), t(gm, grad=True), t(bt, grad=True)
+    yr = rt + R.leaky_relu(R.film(xt, gt, btt), 0.3)
+    (yr * t(g)).sum().backward()
+    y = ops.film_act_add_fwd(gpu(x), gpu(gm), gpu(bt), gpu(res), ACT_LRELU, 0.3)
+    sep = ops.add(gpu(res), ops.act_fwd(ops.film_fwd(gpu(x), gpu(gm), gpu(bt)), ACT_LRELU, 0.3))
+    assert torch.equal(y, sep)
+    assert rel_l2(cpu(y), yr.detach().numpy()) < 1e-6
+    dx, dg, db = ops.film_act_add_bwd(gpu(g), gpu(x), gpu(gm), gpu(bt), ACT_LRELU, 0.3)
+    assert rel_l2(cpu(dx), xt.grad.numpy()) < 1e-6
+    assert rel_l2(cpu(dg), gt.grad.numpy()) < 1e-5
+    assert rel_l2(cpu(db), btt.grad.numpy()) < 1e-5
+    assert np.array_equal(rt.grad.numpy(), g)            # the residual branch receives dy unchanged
+
+
 # ------------------------------------------------------------------ batch norm
 @pytest.mark.parametrize("C,act", [(64, 1), (128, 0), (1024, 1)])
 def test_batchnorm_train(ops, C, act):
