@@ -429,6 +429,11 @@ int dafk_pair_dice_bwd(const float* a, const float* b, const double* ws, const f
 int dafk_pair_combine(const float* w, const float* L, float weight, float* loss, float* dw, float* coef, int B, int P,
                       void* stream);
 
+/* Augmentation of a staged batch (model_executors/base_executor.py:37-78,103-110: keras ImageDataGenerator with
+ * rotation_range=20 -> scipy.ndimage.affine_transform(order=1, mode='nearest') about the image centre).
+ * x, y: f32 [B,H,W,C] (C in 1..5 or 8), distinct buffers; theta[B]: rotation angle per sample in radians. */
+int dafk_rotate_bilinear(const float* x, const float* theta, float* y, int B, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

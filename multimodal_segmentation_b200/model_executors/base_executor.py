@@ -19,10 +19,15 @@ log = logging.getLogger("executor")
 class BatchFlow(object):
     """equivalent of ImageDataGenerator().flow(array, batch_size, seed) without augmentation"""
 
-    def __init__(self, array, batch_size, seed):
+    def __init__(self, array, batch_size, seed, rotation_range=0.0):
         self.array = np.ascontiguousarray(array, dtype=np.float32)
         self.batch_size = batch_size
         self.rng = np.random.RandomState(seed)
+        # ImageDataGenerator(rotation_range): one angle per sample, theta = deg2rad(uniform(-range, range)); flows built
+        # with the same seed draw the same angles, which keeps images and masks aligned (base_executor.py:37-78).
+        # The rotation itself runs on the device after the H2D copy (ops.rotate_bilinear).
+        self.rotation_range = float(rotation_range)
+        self.last_theta = None
         self.n = self.array.shape[0]
         self.order = None
         self.pos = 0
@@ -39,6 +44,9 @@ class BatchFlow(object):
             self.pos = 0
         idx = self.order[self.pos:self.pos + self.batch_size]
         self.pos += self.batch_size
+        if self.rotation_range:
+            self.last_theta = np.deg2rad(self.rng.uniform(-self.rotation_range, self.rotation_range,
+                                                          size=len(idx))).astype(np.float32)
         shape = (len(idx),) + self.array.shape[1:]
         if torch.cuda.is_available():
             t = self.turn
@@ -74,6 +82,11 @@ class FlowGroup(object):
         items = [next(f) for f in self.flows]
         return items[0] if len(items) == 1 else tuple(items)
 
+    @property
+    def last_theta(self):
+        """rotation angles of the batch just produced (identical in every flow of the group), or None"""
+        return self.flows[0].last_theta
+
     def mark_copied(self):
         for f in self.flows:
             f.mark_copied()
@@ -108,7 +121,8 @@ class Executor(object):
             if type(arrs) != list:
                 arrs = [arrs]
             for a in arrs:
-                gens.append(BatchFlow(a, self.conf.batch_size, self.conf.seed))
+                gens.append(BatchFlow(a, self.conf.batch_size, self.conf.seed,
+                                      self.get_datagen_params()["rotation_range"] if getattr(self.conf, "augment", True) else 0.0))
         if len(gens) == 0:
             raise Exception("No data to iterate.")
         return FlowGroup(gens)

@@ -175,6 +175,12 @@ class DAFNetExecutor(Executor):
             self.h2d_bytes += t.numel() * 4
             out.append(t.cuda(non_blocking=True))
         gen.mark_copied()
+        theta = getattr(gen, "last_theta", None)
+        if theta is not None:
+            # augmentation (base_executor.py:103-110) on the device: the same angles for every array of the group
+            th = torch.from_numpy(theta[:n]).cuda(non_blocking=True)
+            self.h2d_bytes += th.numel() * 4
+            out = [ops.rotate_bilinear(t.contiguous(), th) for t in out]
         return out
 
     def _sample_z(self, B):

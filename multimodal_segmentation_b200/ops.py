@@ -819,6 +819,16 @@ def pair_dice_bwd(a, b, ws, g, need_a=True, need_b=True):
     return da, db
 
 
+# ---------------------------------------------------------------------------- augmentation
+def rotate_bilinear(x, theta):
+    """keras ImageDataGenerator(rotation_range) on a staged batch: x f32 [B,H,W,C], theta [B] radians"""
+    _chk(x, theta)
+    B, H, W, C = x.shape
+    y = torch.empty_like(x)
+    call("rotate_bilinear", x, theta, y, B, H, W, C, _S())
+    return y
+
+
 # ---------------------------------------------------------------------------- automated-pairing losses
 def segloss_pb_fwd(pred, target, nch, L_row, lambda_bce=0.01):
     """per-sample dice + lambda * swapped per-batch wBCE (costs.py:88-108,138-143) -> L_row[B]; returns the workspace"""

@@ -514,3 +514,44 @@ def test_error_codes(ops):
         _lib.call("softmax_fwd", x, x, None, 2, 7, None)          # unsupported channel count
     with pytest.raises(_lib.DafkError):
         ops.round_fwd(torch.zeros(4))                             # CPU tensor: no fallback
+
+
+# ------------------------------------------------------------------ augmentation
+def _keras_rotate(x, theta):
+    """keras 2.1.6 ImageDataGenerator.random_transform with only a rotation + apply_transform(fill_mode='nearest'),
+    restated on scipy: x [H,W,C], theta in radians"""
+    from scipy import ndimage as ndi
+    h, w = x.shape[0], x.shape[1]
+    rot = np.array([[np.cos(theta), -np.sin(theta), 0], [np.sin(theta), np.cos(theta), 0], [0, 0, 1]])
+    o_x, o_y = float(h) / 2 + 0.5, float(w) / 2 + 0.5
+    offset = np.array([[1, 0, o_x], [0, 1, o_y], [0, 0, 1]])
+    reset = np.array([[1, 0, -o_x], [0, 1, -o_y], [0, 0, 1]])
+    m = offset @ rot @ reset
+    chans = [ndi.affine_transform(x[..., c], m[:2, :2], m[:2, 2], order=1, mode="nearest", cval=0.0)
+             for c in range(x.shape[-1])]
+    return np.stack(chans, -1)
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 64, 1), (2, 37, 53, 5), (2, 48, 40, 3)])
+def test_rotation_augmentation_matches_scipy(ops, shape):
+    r = rng(7)
+    x = r.uniform(-1, 1, size=shape).astype(np.float32)
+    theta = np.deg2rad(r.uniform(-20, 20, size=shape[0])).astype(np.float32)
+    theta[0] = 0.0
+    y = cpu(ops.rotate_bilinear(gpu(x), gpu(theta)))
+    ref = np.stack([_keras_rotate(x[b].astype(np.float64), float(theta[b])) for b in range(shape[0])], 0)
+    assert np.array_equal(y[0], x[0])                 # zero angle is the identity
+    assert np.abs(y - ref).max() < 2e-4, np.abs(y - ref).max()     # fp32 coordinates vs fp64: ~1e-5 px * gradient
+
+
+def test_flows_with_one_seed_rotate_images_and_masks_together():
+    from multimodal_segmentation_b200.model_executors.base_executor import BatchFlow, FlowGroup
+    a = np.arange(40, dtype=np.float32).reshape(10, 2, 2, 1)
+    g = FlowGroup([BatchFlow(a, 4, 10, 20.0), BatchFlow(a * 2, 4, 10, 20.0)])
+    for _ in range(4):
+        xa, xb = next(g)
+        assert np.array_equal(xa.numpy() * 2, xb.numpy())                       # same order
+        assert np.array_equal(g.flows[0].last_theta, g.flows[1].last_theta)     # same angles
+        assert g.last_theta.shape == (xa.shape[0],) and np.abs(g.last_theta).max() <= np.deg2rad(20.0)
+        g.mark_copied()
+    assert BatchFlow(a, 4, 10).last_theta is None
