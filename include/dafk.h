@@ -284,6 +284,13 @@ int dafk_pack_conv3x3(const float* w_hwio, void* wp, int Cin, int Cout, int for_
 /* dw[3,3,Cin,Cout] (HWIO f32) += sum_pixels x (*) dy, tensor-core path */
 int dafk_conv3x3_tc_wgrad(const void* x, int Cin, int cin_off, int cin_total, const void* dy,
                           int Cout, float* dw, int N, int H, int W, void* stream);
+/* Same result as dafk_conv3x3_tc_wgrad (dw[3,3,cin_total,Cout] += x (*) dy for the channel block at cin_off) for
+ * Cin and Cout multiples of 64 (csrc/conv_tc_wgrad_halo.cu): one CTA owns all nine taps of a 64 x 64 block, loads a
+ * haloed X tile once per 16 x 8 pixel tile and pairs two taps per M=128 MMA.  Preferred for the 64/128-channel
+ * full-resolution layers (models/unet.py:95,99), where the per-tap kernel is bound by L2 -> SM bandwidth. */
+int dafk_conv3x3_tc_wgrad_halo_supported(int Cin, int Cout);
+int dafk_conv3x3_tc_wgrad_halo(const void* x, int Cin, int cin_off, int cin_total, const void* dy, int Cout, float* dw,
+                               int N, int H, int W, void* stream);
 
 /* ------------------------------------------------------------------ Dense
  * keras Dense: modality_encoder.py:46-50, stn_spline.py:115-116, discriminator.py:33,

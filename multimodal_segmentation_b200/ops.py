@@ -5,6 +5,8 @@ the outputs with the caching allocator and enqueues ONE OR MORE hand-written ker
 current stream through ctypes.  No arithmetic is done by torch.  There is no autograd here --
 the reverse pass is recorded by ``tape.py``.
 """
+import os
+
 import torch
 
 from . import _lib, instrument
@@ -474,10 +476,35 @@ def conv_tc_fwd(x0, x1, wp, bias, Cout, KH, KW, stride, pad, out_dtype=torch.flo
     return out
 
 
+WGRAD_HALO = os.environ.get("DAFK_WGRAD_HALO", "auto")     # "0" / "1" force the choice (tests, benchmarks)
+
+
+def _wgrad_halo(Cin, Cout, KH, KW, stride, pad):
+    if not (KH == 3 and KW == 3 and stride == 1 and pad == 1 and Cin % 64 == 0 and Cout % 64 == 0):
+        return False
+    if WGRAD_HALO in ("0", "1"):
+        return WGRAD_HALO == "1"
+    # measured on B200 (profiles/r1_bench_tc.txt): wins while a pixel carries few channels (the per-tap kernel is
+    # L2-bound there); the 128x128-tile per-tap kernel is faster from 256 channels on
+    return Cin <= 128 and Cout <= 128
+
+
+def conv3x3_tc_wgrad_halo(x, dy, dw, cin_off=0):
+    _chk(x, dy, dw)
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    fl = 2.0 * N * H * W * Cout * 9 * Cin
+    instrument.timed("conv_tc_wgrad (tcgen05)", fl, 2.0 * (x.numel() + dy.numel()),
+                     lambda: call("conv3x3_tc_wgrad_halo", x, Cin, cin_off, dw.shape[2], dy, Cout, dw, N, H, W, _S()),
+                     tag=(N, H, W, Cin, Cout, 3, 1, "halo"))
+
+
 def conv_tc_wgrad(x, dy, dw, cin_off, KH, KW, stride, pad):
     _chk(x, dy, dw)
     N, H, W, Cin = x.shape
     _, Ho, Wo, Cout = dy.shape
+    if _wgrad_halo(Cin, Cout, KH, KW, stride, pad):
+        return conv3x3_tc_wgrad_halo(x, dy, dw, cin_off)
     fl = 2.0 * N * Ho * Wo * Cout * KH * KW * Cin
     instrument.timed("conv_tc_wgrad (tcgen05)", fl, 2.0 * (x.numel() + dy.numel()),
                      lambda: call("conv_tc_wgrad", x, Cin, cin_off, dw.shape[2], dy, Cout, dw, N, H, W, KH, KW, stride,
