@@ -60,9 +60,15 @@ def main():
         wargs = [x0.data_ptr(), C0, 0, Cin, dy.data_ptr(), Cout, dw.data_ptr(), B, H, H, 3, 3, 1, 1, H, H, S]
         flw = 2.0 * B * H * H * Cout * 9 * C0
         tw = timeit(lambda: g(*wargs), reps)
+        th = None
+        if L["dafk_conv3x3_tc_wgrad_halo_supported"](C0, Cout):
+            gh = L["dafk_conv3x3_tc_wgrad_halo"]
+            hargs = [x0.data_ptr(), C0, 0, Cin, dy.data_ptr(), Cout, dw.data_ptr(), B, H, H, S]
+            th = timeit(lambda: gh(*hargs), reps)
         tot["fwd"][0] += t; tot["fwd"][1] += fl
         tot["wgrad"][0] += tw; tot["wgrad"][1] += flw
-        print("%-24s fwd %8.1f us %7.1f TF/s | wgrad(src0) %8.1f us %7.1f TF/s" % (name, t, fl / t / 1e6, tw, flw / tw / 1e6), flush=True)
+        print("%-24s fwd %8.1f us %7.1f TF/s | wgrad(src0) %8.1f us %7.1f TF/s | wgrad halo %s" %
+              (name, t, fl / t / 1e6, tw, flw / tw / 1e6, "-" if th is None else "%8.1f us %7.1f TF/s" % (th, flw / th / 1e6)), flush=True)
     for k, (t, fl) in tot.items():
         if t:
             print("total %s: %.1f us, %.1f TF/s" % (k, t, fl / t / 1e6))

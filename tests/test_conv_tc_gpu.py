@@ -86,6 +86,26 @@ def test_conv3x3_tc_wgrad(ops, case):
     assert err < 1e-3, err
 
 
+@pytest.mark.parametrize("case", [(2, 16, 16, 64, 64), (1, 24, 40, 64, 64), (3, 37, 21, 64, 64), (2, 16, 32, 128, 128),
+                                  (2, 16, 16, 64, 128), (2, 24, 16, 128, 64), (1, 56, 56, 64, 64), (2, 8, 8, 256, 64)])
+def test_conv3x3_tc_wgrad_halo(ops, case):
+    """the all-taps-per-CTA weight-gradient kernel (csrc/conv_tc_wgrad_halo.cu): tiles that overhang the image, several
+    channel blocks, more tiles than pipeline stages, and accumulation into a non-zero dw at a channel offset"""
+    N, H, W, Cin, Cout = case
+    r = np.random.RandomState(sum(case) + 5)
+    x = bf16_round(r.normal(size=(N, H, W, Cin)).astype(np.float32))
+    dy = bf16_round(r.normal(size=(N, H, W, Cout)).astype(np.float32))
+    wt = torch.zeros(3, 3, Cin, Cout, dtype=torch.float64, requires_grad=True)
+    (R.conv2d(t(x, torch.float64), wt, None, 1, "same") * t(dy, torch.float64)).sum().backward()
+    base = r.normal(size=(3, 3, Cin + 64, Cout)).astype(np.float32)
+    dw = gpu(base)
+    ops.conv3x3_tc_wgrad_halo(gpu(x, torch.bfloat16), gpu(dy, torch.bfloat16), dw, cin_off=64)
+    got = cpu(dw) - base
+    assert np.array_equal(got[:, :, :64], np.zeros_like(got[:, :, :64]))        # other channel blocks untouched
+    err = rel_l2(got[:, :, 64:], wt.grad.numpy())
+    assert err < 1e-3, err
+
+
 def test_conv3x3_tc_wgrad_concat_offset(ops):
     N, H, W, C0, C1, Cout = 2, 16, 16, 64, 64, 64
     r = np.random.RandomState(11)
