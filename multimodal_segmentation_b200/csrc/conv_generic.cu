@@ -3,6 +3,7 @@
 // This path serves the small-channel layers (Cin or Cout in {1,4,5,8,9,16,20}) that cannot
 // feed the tensor cores; the wide 3x3 layers go through conv_tc.cu.
 #include "common.cuh"
+#include "norm_wide.cuh"
 #include "reduce.cuh"
 
 namespace dafk {
@@ -441,6 +442,13 @@ int dafk_colsum(const void* x, int x_dt, float* out, int64_t M, int C, void* str
   DAFK_REQUIRE(x && out, DAFK_ERR_BAD_ARG, "dafk_colsum: null pointer");
   cudaStream_t s = as_stream(stream);
   DAFK_REQUIRE(C <= 4096, DAFK_ERR_UNSUPPORTED, "dafk_colsum: C too large");
+  if (bn_wide_ok(C) && (x_dt == DAFK_F32 || x_dt == DAFK_BF16) && DAFK_ALIGNED16(x)) {
+    const int64_t n8 = M * C / 8;
+    const int grid = bn_wide_grid(n8, 2, 4);
+    if (x_dt == DAFK_F32) colsum_wide_kernel<float><<<grid, BW_T, 0, s>>>((const float*)x, out, n8, C);
+    else colsum_wide_kernel<__nv_bfloat16><<<grid, BW_T, 0, s>>>((const __nv_bfloat16*)x, out, n8, C);
+    return check_launch("dafk_colsum");
+  }
   int64_t rows_per_block = (M + kNumSMs * 4 - 1) / (kNumSMs * 4);
   if (rows_per_block < 64) rows_per_block = 64;
   int blocks = (int)((M + rows_per_block - 1) / rows_per_block);

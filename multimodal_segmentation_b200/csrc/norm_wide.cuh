@@ -301,6 +301,54 @@ __global__ void __launch_bounds__(BW_T, 1) bn_bwd_apply_wide_kernel(const TD* __
   }
 }
 
+// out[c] += sum over rows of x[row][c] (bias gradients of the convolutions, models/discriminator.py:24,39): same
+// 8-channels-per-thread stream as the statistics pass, one float atomic per channel per CTA
+template <typename TX>
+__global__ void __launch_bounds__(BW_T, 2) colsum_wide_kernel(const TX* __restrict__ x, float* __restrict__ out,
+                                                              int64_t n8, int C) {
+  __shared__ float red[8 * BW_T];
+  float s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * BW_T;
+  int64_t i = (int64_t)blockIdx.x * BW_T + threadIdx.x;
+  for (; i + 3 * stride < n8; i += 4 * stride) {
+    W8<TX> r0, r1, r2, r3;
+    r0.load(x + 8 * i); r1.load(x + 8 * (i + stride)); r2.load(x + 8 * (i + 2 * stride)); r3.load(x + 8 * (i + 3 * stride));
+    float v[8];
+    r0.get(v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += v[k];
+    r1.get(v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += v[k];
+    r2.get(v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += v[k];
+    r3.get(v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += v[k];
+  }
+  for (; i < n8; i += stride) {
+    W8<TX> r0;
+    r0.load(x + 8 * i);
+    float v[8];
+    r0.get(v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[k * BW_T + threadIdx.x] = s[k];
+  __syncthreads();
+  const int G = C >> 3;
+  for (int c = threadIdx.x; c < C; c += BW_T) {
+    const float* row = red + (c & 7) * BW_T + (c >> 3);
+    float t = 0.f;
+    for (int j = 0; j < BW_T; j += G) t += row[j];
+    atomicAdd(out + c, t);
+  }
+}
+
 static inline int bn_wide_grid(int64_t n8, int per_sm, int unroll) {
   int64_t need = (n8 + (int64_t)BW_T * unroll - 1) / ((int64_t)BW_T * unroll);
   int64_t cap = (int64_t)kNumSMs * per_sm;

@@ -555,3 +555,17 @@ def test_flows_with_one_seed_rotate_images_and_masks_together():
         assert g.last_theta.shape == (xa.shape[0],) and np.abs(g.last_theta).max() <= np.deg2rad(20.0)
         g.mark_copied()
     assert BatchFlow(a, 4, 10).last_theta is None
+
+
+@pytest.mark.parametrize("M,C,dt", [(1000, 64, "bf16"), (3 * 54 * 54, 128, "bf16"), (777, 256, "f32"), (513, 8, "f32"),
+                                    (300, 20, "f32"), (129, 1024, "bf16")])
+def test_colsum_accumulates_bias_gradient(ops, M, C, dt):
+    """out[c] += sum_rows x[row][c]: the wide (8 channels per thread) kernel for power-of-two C, the generic one else"""
+    tdt = torch.bfloat16 if dt == "bf16" else torch.float32
+    x = rng(M + C).normal(size=(M, C)).astype(np.float32)
+    xd = gpu(x, tdt)
+    base = rng(1).normal(size=C).astype(np.float32)
+    out = gpu(base)
+    ops.colsum_(xd, out)
+    ref = base.astype(np.float64) + xd.float().cpu().numpy().astype(np.float64).sum(0)
+    assert rel_l2(cpu(out), ref) < 1e-5
