@@ -225,6 +225,7 @@ struct HaloGeom {
   int G;                    // accumulators (128 raster positions each)
   int a_bytes;              // bytes of one A stage (box + slack for the shifted reads of the last accumulator)
   int SA, SB;               // ring depths
+  int w_resident;           // all weight tiles of the layer stay in shared memory for the whole kernel (SB unused)
 };
 
 template <int BLOCK_N>
@@ -241,7 +242,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_a = smem;
   uint8_t* s_b = smem + g.SA * g.a_bytes;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_b + g.SB * B_BYTES);
+  const int w_slots = g.w_resident ? ((C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK) * KH * KW : g.SB;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_b + w_slots * B_BYTES);
   uint64_t* a_empty = a_full + 4;
   uint64_t* b_full = a_empty + 4;
   uint64_t* b_empty = b_full + 8;
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
     if (C1 > 0) tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < g.SA; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
-    for (int s = 0; s < g.SB; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int s = 0; s < (g.SB > 0 ? g.SB : 1); ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }   // slot 0 = resident weights
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 128); }
     fence_barrier_init();
   }
@@ -275,6 +277,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
     if (lane == 0) {
       int ia = 0, ib = 0;
       const uint32_t a_box_bytes = (uint32_t)(g.TN * g.RS * g.Pp * KBLK * 2);
+      if (g.w_resident) {
+        // small layers (Cin*Cout*taps*2 B fits next to the activation ring, one output-channel block): the weight tiles
+        // are loaded ONCE per CTA; afterwards only the activation tiles stream (the per-tap weight reloads made the
+        // 64-channel layers L2-bound: 72 KB of weights per 23 KB activation tile)
+        mbar_expect_tx(b_full, (uint32_t)(ncb * taps * B_BYTES));
+        for (int cb = 0; cb < ncb; ++cb)
+          for (int tap = 0; tap < taps; ++tap)
+            tma_load_2d(s_b + (cb * taps + tap) * B_BYTES, &tmB, b_full, cb * KBLK, tap * w_rows_per_tap + w_row_off);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nb = tile % n_blocks;
         int mt = tile / n_blocks;
@@ -290,6 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
           mbar_wait(a_empty + sa, ((uint32_t)(ia / g.SA) & 1u) ^ 1u);
           mbar_expect_tx(a_full + sa, a_box_bytes);
           tma_load_4d(s_a + sa * g.a_bytes, mA, a_full + sa, c_in_src, x0 - pad, y0 - pad, img0);
+          if (g.w_resident) continue;
           for (int tap = 0; tap < taps; ++tap, ++ib) {
             const int sb = ib % g.SB;
             mbar_wait(b_empty + sb, ((uint32_t)(ib / g.SB) & 1u) ^ 1u);
@@ -306,7 +318,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
     const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b);
     const int G = g.G, Pp = g.Pp, SA = g.SA, SB = g.SB, a_bytes = g.a_bytes;
+    const bool wres = g.w_resident != 0;
     int ia = 0, ib = 0, tc = 0;
+    if (wres) {
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
       const uint32_t buf = (uint32_t)tc & 1u;
       mbar_wait(tempty_bar + buf, (((uint32_t)tc >> 1) & 1u) ^ 1u);
@@ -316,11 +333,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
         const int sa = ia % SA;
         mbar_wait(a_full + sa, (uint32_t)(ia / SA) & 1u);
         const uint32_t a_stage = a_base + (uint32_t)(sa * a_bytes);
+        if (wres) tc_fence_after();
         for (int r = 0; r < KH; ++r) {
           for (int q = 0; q < KW; ++q, ++ib) {
-            const int sb = ib % SB;
-            mbar_wait(b_full + sb, (uint32_t)(ib / SB) & 1u);
-            tc_fence_after();
+            int sb;
+            if (wres) {
+              sb = cb * taps + r * KW + q;
+            } else {
+              sb = ib % SB;
+              mbar_wait(b_full + sb, (uint32_t)(ib / SB) & 1u);
+              tc_fence_after();
+            }
             if (leader) {
               const uint64_t db = make_smem_desc(b_base + (uint32_t)(sb * B_BYTES), 16, 1024);
               const uint32_t a_tap = a_stage + (uint32_t)((r * Pp + q) * 128);
@@ -335,7 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
                 for (int k = 0; k < KBLK / 16; ++k)
                   umma_bf16(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (k > 0) ? 1u : acc0);
               }
-              umma_commit(b_empty + sb);
+              if (!wres) umma_commit(b_empty + sb);
             }
             __syncwarp();
           }
@@ -678,7 +701,8 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
 
 // ---- haloed-tile geometry.  Estimated cycles per valid output pixel and channel block (per SM):
 //   tensor: G * taps * 4 MMAs of max(N/2, 48) cycles;  L2: (A box + taps * weight tile) bytes at ~40 B/cycle/SM
-static double halo_cost(int N, int H, int W, int KH, int KW, int bn, int two, int th, int tn, int n_blocks, HaloGeom* out) {
+static double halo_cost(int N, int H, int W, int KH, int KW, int bn, int two, int th, int tn, int n_blocks, HaloGeom* out,
+                        int w_res_bytes = 0) {
   const int Pp = two + KW - 1, RS = th + KH - 1;
   if (Pp > 256 || RS > 256) return 1e30;
   const int mpos = (tn - 1) * RS * Pp + th * Pp;
@@ -693,37 +717,44 @@ static double halo_cost(int N, int H, int W, int KH, int KW, int bn, int two, in
   const int b_bytes = bn * 128;
   const int budget = 200 * 1024;
   int SA = 2;
-  if (SA * a_bytes + 3 * b_bytes > budget) return 1e30;
-  int SB = (budget - SA * a_bytes) / b_bytes;
-  if (SB > 8) SB = 8;
+  int SB;
+  if (w_res_bytes > 0) {
+    if (SA * a_bytes + w_res_bytes > budget) return 1e30;
+    if (3 * a_bytes + w_res_bytes <= budget) SA = 3;
+    SB = 0;
+  } else {
+    if (SA * a_bytes + 3 * b_bytes > budget) return 1e30;
+    SB = (budget - SA * a_bytes) / b_bytes;
+    if (SB > 8) SB = 8;
+  }
   const int taps = KH * KW;
   const int64_t tx = (W + two - 1) / two, ty = (H + th - 1) / th, tnn = (N + tn - 1) / tn;
   const int64_t tiles = tx * ty * tnn * n_blocks;
   const int64_t rounds = (tiles + kNumSMs - 1) / kNumSMs;
   const double mma = (double)G * taps * 4.0 * (bn / 2 > 48 ? bn / 2 : 48);
-  const double l2 = ((double)box_rows * 128.0 + (double)taps * b_bytes) / 40.0;
+  const double l2 = ((double)box_rows * 128.0 + (w_res_bytes > 0 ? 0.0 : (double)taps * b_bytes)) / 40.0;
   const double per_tile = (mma > l2 ? mma : l2) + 400.0;
   const double cost = (double)rounds * kNumSMs * per_tile / ((double)N * H * W * n_blocks);
   if (out) {
     out->TWo = two; out->TH = th; out->TN = tn; out->Pp = Pp; out->RS = RS;
     out->tiles_x = (int)tx; out->tiles_y = (int)ty; out->tiles_n = (int)tnn;
-    out->G = G; out->a_bytes = a_bytes; out->SA = SA; out->SB = SB;
+    out->G = G; out->a_bytes = a_bytes; out->SA = SA; out->SB = SB; out->w_resident = w_res_bytes > 0 ? 1 : 0;
   }
   return cost;
 }
 
 struct HaloKey {
-  int N, H, W, KH, KW, bn, nb;
+  int N, H, W, KH, KW, bn, nb, wres;
   bool operator<(const HaloKey& o) const {
     return memcmp(this, &o, sizeof(HaloKey)) < 0;
   }
 };
 
-static double pick_halo_geom(int N, int H, int W, int KH, int KW, int bn, int n_blocks, HaloGeom* best) {
+static double pick_halo_geom(int N, int H, int W, int KH, int KW, int bn, int n_blocks, HaloGeom* best, int w_res_bytes = 0) {
   // memoised: the search walks ~10^4 candidates, layers repeat every step
   static std::mutex mu;
   static std::map<HaloKey, std::pair<double, HaloGeom>> memo;
-  const HaloKey key{N, H, W, KH, KW, bn, n_blocks};
+  const HaloKey key{N, H, W, KH, KW, bn, n_blocks, w_res_bytes};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = memo.find(key);
@@ -738,7 +769,7 @@ static double pick_halo_geom(int N, int H, int W, int KH, int KW, int bn, int n_
       const int tn_max = (two == W && th == H) ? 8 : 1;
       for (int tn = 1; tn <= tn_max && tn <= N; tn *= 2) {
         HaloGeom gcur;
-        const double c = halo_cost(N, H, W, KH, KW, bn, two, th, tn, n_blocks, &gcur);
+        const double c = halo_cost(N, H, W, KH, KW, bn, two, th, tn, n_blocks, &gcur, w_res_bytes);
         if (c < best_cost) { best_cost = c; *best = gcur; }
       }
     }
@@ -778,7 +809,8 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
                        int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int pad,
                        const HaloGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
                        long long y_sx, cudaStream_t s) {
-  const int smem = g.SA * g.a_bytes + g.SB * BLOCK_N * KBLK * 2 + 1024 + 512;
+  const int ncb_all = (C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK;
+  const int smem = g.SA * g.a_bytes + (g.w_resident ? ncb_all * KH * KW : g.SB) * BLOCK_N * KBLK * 2 + 1024 + 512;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -859,7 +891,18 @@ int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void*
     if (force == -2) { const char* e = getenv("DAFK_CONV_HALO"); force = e ? atoi(e) : -1; }
     const int bn = Cout % 128 == 0 ? 128 : 64;
     HaloGeom hg;
-    const double ch = pick_halo_geom(N, Ho, Wo, KH, KW, bn, (Cout + bn - 1) / bn, &hg);
+    double ch = pick_halo_geom(N, Ho, Wo, KH, KW, bn, (Cout + bn - 1) / bn, &hg);
+    {
+      // resident weights: one output-channel block and all (channel block, tap) tiles fit beside a 2-deep activation ring
+      static int wres_ok = -2;
+      if (wres_ok == -2) { const char* e = getenv("DAFK_CONV_WRES"); wres_ok = e ? atoi(e) : 1; }
+      const int w_bytes = (Kpad / KBLK) * taps * bn * KBLK * 2;
+      if (wres_ok && Cout <= bn && w_bytes <= 150 * 1024) {
+        HaloGeom hr;
+        const double cr = pick_halo_geom(N, Ho, Wo, KH, KW, bn, 1, &hr, w_bytes);
+        if (cr < 1e29 && cr <= ch) { ch = cr; hg = hr; }
+      }
+    }
     double ct = tap_kernel_cost(N, Ho, Wo, KH, KW, bn, (Cout + bn - 1) / bn, g);
     if (Cout % 256 == 0) { const double c256 = tap_kernel_cost(N, Ho, Wo, KH, KW, 256, Cout / 256, g); if (c256 < ct) ct = c256; }
     // measured on B200 (profiles/r1_bench_tc.txt): the haloed tile wins for Cout in {64, 128} (weight tiles are small,
