@@ -70,6 +70,8 @@ int dafk_softmax_bwd(const float* p, const float* dp, float* dx, int64_t M, int 
 int dafk_act_fwd(const float* x, float* y, int64_t n, int act, float alpha, void* stream);
 int dafk_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, float alpha,
                  void* stream);
+/* same, with dx written as bf16 (operand dtype of the tensor-core gradient kernels); n % 4 == 0 */
+int dafk_act_bwd_bf16(const float* dy, const float* y, void* dx, int64_t n, int act, float alpha, void* stream);
 /* out = a + b (keras Add, decoder.py:53, spade.py:23); out may alias a or b */
 int dafk_add(const float* a, const float* b, float* out, int64_t n, void* stream);
 /* same for either storage dtype (gradient accumulation of bf16 feature maps) */

@@ -59,6 +59,18 @@ struct ActBwd {  // (dy, y) -> dx, derivative at exactly 0 is 0 for relu/lrelu (
     return dy;
   }
 };
+// (dy, y) -> bf16(dx): the activation backward of a tensor-core layer, written directly in the operand dtype of the
+// weight- and data-gradient kernels that consume it (no fp32 intermediate)
+__global__ void __launch_bounds__(TPB) act_bwd_bf16_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                           __nv_bfloat16* __restrict__ dx, int64_t n4, ActBwd f) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 u = ldg_stream4(dy + 4 * i);
+    float4 v = ldg_stream4(y + 4 * i);
+    float r[4] = {f(u.x, v.x), f(u.y, v.y), f(u.z, v.z), f(u.w, v.w)};
+    Vec4<__nv_bfloat16>::store(dx + 4 * i, r);
+  }
+}
 struct AddOp { __device__ float operator()(float a, float b) const { return a + b; } };
 struct MaxOp { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
 struct AxpbyOp { float a, b; __device__ float operator()(float x, float y) const { return a * x + b * y; } };
@@ -306,6 +318,16 @@ int dafk_act_fwd(const float* x, float* y, int64_t n, int act, float alpha, void
 int dafk_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, float alpha, void* stream) {
   DAFK_REQUIRE(act >= 0 && act <= 3, DAFK_ERR_BAD_ARG, "dafk_act_bwd: bad activation %d", act);
   return launch_map2(dy, y, dx, n, ActBwd{act, alpha}, stream, "dafk_act_bwd");
+}
+
+int dafk_act_bwd_bf16(const float* dy, const float* y, void* dx, int64_t n, int act, float alpha, void* stream) {
+  DAFK_REQUIRE(act >= 0 && act <= 3, DAFK_ERR_BAD_ARG, "dafk_act_bwd_bf16: bad activation %d", act);
+  DAFK_REQUIRE(n >= 0 && n % 4 == 0, DAFK_ERR_BAD_ARG, "dafk_act_bwd_bf16: size must be a multiple of 4");
+  if (n == 0) return DAFK_OK;
+  DAFK_REQUIRE(dy && y && dx, DAFK_ERR_BAD_ARG, "dafk_act_bwd_bf16: null pointer");
+  DAFK_REQUIRE(DAFK_ALIGNED16(dy) && DAFK_ALIGNED16(y) && DAFK_ALIGNED16(dx), DAFK_ERR_ALIGN, "dafk_act_bwd_bf16: alignment");
+  act_bwd_bf16_kernel<<<bw_grid(n / 4, TPB), TPB, 0, as_stream(stream)>>>(dy, y, (__nv_bfloat16*)dx, n / 4, ActBwd{act, alpha});
+  return check_launch("dafk_act_bwd_bf16");
 }
 
 int dafk_add(const float* a, const float* b, float* out, int64_t n, void* stream) {

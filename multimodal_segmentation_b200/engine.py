@@ -389,9 +389,13 @@ class Conv2D:
                     return
                 if g.dtype != torch.float32:
                     g = ops.cast(g, torch.float32)
-                if code != ACT_NONE:
-                    g = ops.act_bwd(g, y.data, code, alpha)
-                gb = ops.cast(g, torch.bfloat16) if wide else None
+                if wide and code != ACT_NONE and g.numel() % 4 == 0:
+                    gb = ops.act_bwd_bf16(g, y.data, code, alpha)       # activation backward straight into bf16
+                    g = None
+                else:
+                    if code != ACT_NONE:
+                        g = ops.act_bwd(g, y.data, code, alpha)
+                    gb = ops.cast(g, torch.bfloat16) if wide else None
                 if self.kernel.requires_grad:
                     db = self.bias.grad if (self.bias is not None and self.bias.requires_grad) else None
                     if wide:
@@ -409,7 +413,7 @@ class Conv2D:
                         ops.conv2d_wgrad(xf, g, self.kernel.grad, db, self.stride, self.pad)
                 if xin.requires_grad:
                     if wide:
-                        dx2 = torch.empty((N, (H + 1) // 2, (W + 1) // 2, 4 * C), dtype=torch.bfloat16, device=g.device)
+                        dx2 = torch.empty((N, (H + 1) // 2, (W + 1) // 2, 4 * C), dtype=torch.bfloat16, device=gb.device)
                         ops.conv_tc_fwd(gb, None, wp_d, None, 4 * C, k2, k2, 1, k2 - 1, torch.bfloat16, out=dx2)
                     else:
                         dx2 = ops.conv_nc_fwd(g, wp_d, None, 4 * C, k2, k2, k2 - 1, out_dtype=torch.bfloat16)
@@ -647,7 +651,12 @@ def activation(ctx, x, act, alpha=0.0):
         def bw():
             g = y.grad
             y.grad = None
-            if g is not None:
+            if g is None:
+                return
+            if (x.grad_dtype == torch.bfloat16 and g.dtype == torch.float32 and y.data.dtype == torch.float32
+                    and g.numel() % 4 == 0 and x.requires_grad):
+                accumulate(x, ops.act_bwd_bf16(g, y.data, code, alpha))      # consumer wants bf16: no fp32 intermediate
+            else:
                 accumulate(x, ops.act_bwd(g, y.data, code, alpha))
 
         ctx.tape.record(bw)

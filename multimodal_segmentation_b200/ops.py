@@ -76,6 +76,14 @@ def act_bwd(dy, y, act, alpha=0.0, inplace=False):
     return dx
 
 
+def act_bwd_bf16(dy, y, act, alpha=0.0):
+    """bf16(act'(y) * dy) in one pass (fp32 in)"""
+    _chk(dy, y)
+    dx = torch.empty(dy.shape, dtype=torch.bfloat16, device=dy.device)
+    call("act_bwd_bf16", dy, y, dx, y.numel(), act, float(alpha), _S())
+    return dx
+
+
 def add(a, b, out=None):
     _chk(a, b)
     out = torch.empty_like(a) if out is None else out
