@@ -47,6 +47,8 @@ struct NcWgP {
   int strips_per_img, total_strips;
   int x_dt, dy_dt;
   int tmem_cols;
+  int fold;                          // Cout <= 8: the KH filter rows are folded into the MMA's N dimension
+  int yoff;                          // fold: positions of zero halo in front of the dY rows = (KH-1)*P
 };
 
 // load 8 consecutive channels starting at p (nvalid of them exist) as floats
@@ -424,10 +426,11 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
       uint8_t* sx = smem + (size_t)st * st_bytes;
       mbar_wait(empty + st, ph ^ 1u);
       nc_stage_rows<TX, false, NC_U_WG>(x, sx, p.planeX, n, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P, p.pad, tid, NC_PROD, dummy);
+      uint8_t* sy = sx + x_bytes + (size_t)p.yoff * 16;      // fold: (KH-1) zero rows stay in front of (and behind) the dY rows
       if (db != nullptr)
-        nc_stage_rows<TY, true, NC_U_WG>(dy, sx + x_bytes, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, nthr_y, bsum);
+        nc_stage_rows<TY, true, NC_U_WG>(dy, sy, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, nthr_y, bsum);
       else
-        nc_stage_rows<TY, false, NC_U_WG>(dy, sx + x_bytes, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, NC_PROD, dummy);
+        nc_stage_rows<TY, false, NC_U_WG>(dy, sy, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, NC_PROD, dummy);
       fence_proxy_async();
       mbar_arrive(full + st);
     }
@@ -454,12 +457,16 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
       const int q = i >> 3, c = i & 7;
       const int nacc = p.KH * p.CG;
       for (int a = 0; a < nacc; ++a) {
-        const int r = a / p.CG, cg = a - r * p.CG;
+        // unfolded: accumulator a = (r, cg), columns = co.  folded (N8 == 8): accumulator cg, column group g holds the
+        // filter row r = KH-1-g (the dY raster shifted by g rows)
+        int r, cg, col;
+        if (p.fold) { cg = a / p.KH; const int gq = a - cg * p.KH; r = p.KH - 1 - gq; col = a * 8; }
+        else { r = a / p.CG; cg = a - r * p.CG; col = a * p.N8; }
         const int ci = cg * 8 + c;
         const bool ok = lane < 16 && q < p.KW && ci < p.Cin;
         for (int c0 = 0; c0 < p.N8; c0 += 8) {
           uint32_t v[8];
-          tmem_ld8(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * p.N8 + c0), v);
+          tmem_ld8(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(col + c0), v);
           tmem_ld_wait();
           if (ok) {
             float* o = dw + ((int64_t)(r * p.KW + q) * p.Cin + ci) * p.Cout + c0;
@@ -488,7 +495,22 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
       const uint32_t ph = (uint32_t)(it / S) & 1u;
       mbar_wait(full + st, ph);
       tc_fence_after();
-      if (leader) {
+      if (leader && p.fold) {
+        // one accumulator per channel group: M = 64 (8 taps of a filter row x 8 channels), N = KH*8: column group g is
+        // the dY raster started g rows LATER in its zero-framed plane (SBO = P*16 B), i.e. dY shifted back by
+        // (KH-1-g) rows = filter row r = KH-1-g.  K runs over the RS = R+KH-1 input rows: KH*R/(R+KH-1) fewer MMAs.
+        const uint64_t st_off = (uint64_t)((uint32_t)(st * st_bytes) >> 4);
+        const uint32_t idf = make_idesc(64, KH * 8, 1, 1);
+        const uint64_t dyf = make_smem_desc_ns(smem_u32(smem) + (uint32_t)x_bytes, 128, (uint32_t)p.P * 16u) + st_off;
+        for (int cg = 0; cg < CG; ++cg) {
+          const uint64_t dx = descX + st_off + (uint64_t)(cg * p.planeX);
+          const uint32_t d_col = tmem_acc + (uint32_t)(cg * KH * 8);
+          if (it == 0) umma_bf16(d_col, dx, dyf, idf, 0u);
+          else umma_bf16(d_col, dx, dyf, idf, 1u);
+          for (int c = 1; c < chunks; ++c) umma_bf16(d_col, dx + (uint64_t)(c * 16), dyf + (uint64_t)(c * 16), idf, 1u);
+        }
+        umma_commit(empty + st);
+      } else if (leader) {
         const uint64_t st_off = (uint64_t)((uint32_t)(st * st_bytes) >> 4);
         int a = 0;
         for (int r = 0; r < KH; ++r) {
@@ -603,14 +625,22 @@ static bool nc_wg_geom(NcWgP& p, size_t& smem) {
   p.tmem_cols = 32;
   while (p.tmem_cols < cols) p.tmem_cols <<= 1;
   const size_t fixed = (size_t)NC_PROD * 8 * 4 + 256 + 256;
+  {
+    static int fold_ok = -2;
+    if (fold_ok == -2) { const char* e = getenv("DAFK_NC_WG_FOLD"); fold_ok = e ? atoi(e) : 1; }
+    p.fold = (fold_ok && p.COG == 1 && p.KH > 1 && p.KH * 8 <= 256) ? 1 : 0;
+  }
+  p.yoff = p.fold ? (p.KH - 1) * p.P : 0;
   double best_cost = 0;
   int best = 0, best_S = 0;
   size_t best_smem = 0;
   for (int R = 1; R <= 16; R *= 2) {
     if (R > 1 && R / 2 >= p.Ho) break;
-    const int kpos = round_up(R * p.P, 16);
-    const int planeX = kpos + (p.KH - 1) * p.P + 16;
-    const size_t stage = (size_t)p.CG * planeX * 16 + (size_t)p.COG * kpos * 16;
+    // fold: K covers the R+KH-1 input rows; the dY plane carries KH-1 zero rows on either side of its R rows
+    const int kpos = round_up((p.fold ? R + p.KH - 1 : R) * p.P, 16);
+    const int planeX = kpos + (p.fold ? 0 : (p.KH - 1) * p.P) + 16;
+    const int planeYc = p.fold ? kpos + (p.KH - 1) * p.P + 16 : kpos;
+    const size_t stage = (size_t)p.CG * planeX * 16 + (size_t)p.COG * planeYc * 16;
     int S = (int)((kNcSmemMax - fixed) / stage);
     if (S > 3) S = 3;
     if (S < 2) continue;
@@ -625,10 +655,10 @@ static bool nc_wg_geom(NcWgP& p, size_t& smem) {
   p.R = best;
   p.S = best_S;
   p.RS = p.R + p.KH - 1;
-  const int kpos = round_up(p.R * p.P, 16);
+  const int kpos = round_up((p.fold ? p.R + p.KH - 1 : p.R) * p.P, 16);
   p.chunks = kpos / 16;
-  p.planeX = kpos + (p.KH - 1) * p.P + 16;
-  p.planeY = kpos;
+  p.planeX = kpos + (p.fold ? 0 : (p.KH - 1) * p.P) + 16;
+  p.planeY = p.fold ? kpos + (p.KH - 1) * p.P + 16 : kpos;
   p.strips_per_img = (p.Ho + p.R - 1) / p.R;
   p.total_strips = p.N * p.strips_per_img;
   smem = best_smem;
