@@ -331,6 +331,15 @@ int dafk_tps_build_constants(int cp_h, int cp_w, float* consts_host);
  * locs != NULL.  theta:[B,n_cp,2] control-point offsets in (row,col) normalised units. */
 int dafk_tps_warp_fwd(const float* vol, const float* theta, const float* consts, float* out,
                       float* locs, int B, int H, int W, int C, int n_cp, void* stream);
+/* Same warp with phi(|q - c|^2) read from a per-geometry table instead of evaluated per pixel (25 logf):
+ * dafk_tps_phi_table fills table[n_cp][H*W] (dafk_tps_phi_table_floats floats, caller-owned, reusable for every call
+ * with the same H, W and control grid) with exactly the values the in-kernel evaluation produces.  The spline
+ * coefficients of the batch are computed once per call into coef_ws (B*(n_cp+3)*2 floats, caller-owned) instead of
+ * once per CTA. */
+int64_t dafk_tps_phi_table_floats(int H, int W, int n_cp);
+int dafk_tps_phi_table(const float* consts, float* table, int H, int W, int n_cp, void* stream);
+int dafk_tps_warp_fwd_tab(const float* vol, const float* theta, const float* consts, const float* phi_table,
+                          float* coef_ws, float* out, float* locs, int B, int H, int W, int C, int n_cp, void* stream);
 /* backward: dvol += scatter(dout) (caller zeroes dvol; NULL skips it);
  * dtheta[b,n,2] (overwritten) via the resampler's analytic coordinate gradient.
  * ws: B*(n_cp+3)*2 doubles (zeroed by the callee). */

@@ -263,6 +263,115 @@ __global__ void __launch_bounds__(TPS_T) tps_warp_fwd_kernel(const float* __rest
   }
 }
 
+// phi(|q - c_t|^2) for every output pixel q and control point t depends only on the geometry (H, W, control grid): it
+// is tabulated once per geometry, [n][HW] so that a warp reads 128 contiguous bytes per control point, with exactly the
+// arithmetic of the in-kernel evaluation above.  The 25 logf per pixel were ~2/3 of the forward kernel's instructions.
+__global__ void __launch_bounds__(TPS_T) tps_phi_table_kernel(const float* __restrict__ consts, float* __restrict__ tab,
+                                                              int H, int W, int n) {
+  const int HW = H * W;
+  const int m = blockIdx.x * TPS_T + threadIdx.x;
+  if (m >= HW) return;
+  const int row = m / W, col = m - row * W;
+  const float q0 = (float)((double)row / (double)(H - 1));
+  const float q1 = (float)((double)col / (double)(W - 1));
+  const float qq = q0 * q0 + q1 * q1;
+  for (int t = 0; t < n; ++t) {
+    const float c0 = consts[2 * t], c1 = consts[2 * t + 1];
+    const float r = qq - 2.f * (q0 * c0 + q1 * c1) + (c0 * c0 + c1 * c1);
+    tab[(int64_t)t * HW + m] = 0.5f * r * logf(fmaxf(r, TPS_EPS));
+  }
+}
+
+constexpr int TPS_BS_TAB = 1;      // samples per thread when phi comes from the table (1: most thread-level parallelism, fewest registers)
+
+// per-sample spline coefficients coef[b][j][2] (j < n: w, j = n..n+2: v), computed ONCE per call.  In the kernels above
+// every CTA recomputes them for its samples (25-term dot products whose theta operand comes from global memory); with
+// a few hundred CTAs per sample that prologue, not the warp itself, was most of the run time.
+__global__ void tps_coef_kernel(const float* __restrict__ theta, const float* __restrict__ consts, float* __restrict__ coef,
+                                int B, int n) {
+  const int rows = n + 3;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * rows * 2) return;
+  const int comp = e & 1;
+  const int j = (e >> 1) % rows;
+  const int b = (e >> 1) / rows;
+  const float* Winv = consts + 2 * n;
+  const float* Vinv = Winv + n * n;
+  const float* th = theta + (int64_t)b * n * 2;
+  const float* row = (j < n) ? (Winv + j * n) : (Vinv + (j - n) * n);
+  float acc = 0.f;
+  for (int t = 0; t < n; ++t) acc = fmaf(row[t], th[2 * t + comp], acc);
+  if (j == n + comp) acc += 1.f;                    // identity affine part, as in tps_coefs
+  coef[e] = acc;
+}
+
+template <int C>
+__global__ void __launch_bounds__(TPS_T) tps_warp_fwd_tab_kernel(const float* __restrict__ vol,
+                                                                 const float* __restrict__ coef_g,
+                                                                 const float* __restrict__ tab, float* __restrict__ out,
+                                                                 float* __restrict__ locs, int B, int H, int W, int n) {
+  __shared__ float coef[TPS_BS_TAB * (TPS_MAXN + 3) * 2];
+  const int b0 = blockIdx.y * TPS_BS_TAB;
+  const int nb = min(TPS_BS_TAB, B - b0);
+  const int rows2 = (n + 3) * 2;
+  for (int e = threadIdx.x; e < nb * rows2; e += TPS_T) {
+    const int s = e / rows2, r = e - s * rows2;
+    coef[s * (TPS_MAXN + 3) * 2 + r] = coef_g[(int64_t)(b0 + s) * rows2 + r];
+  }
+  __syncthreads();
+  const int HW = H * W;
+  const int m = blockIdx.x * TPS_T + threadIdx.x;
+  if (m >= HW) return;
+  const int row = m / W, col = m - row * W;
+  const float q0 = (float)((double)row / (double)(H - 1));
+  const float q1 = (float)((double)col / (double)(W - 1));
+  float ph[TPS_MAXN];
+#pragma unroll
+  for (int t = 0; t < TPS_MAXN; ++t) ph[t] = t < n ? __ldg(tab + (int64_t)t * HW + m) : 0.f;
+#pragma unroll 2
+  for (int s = 0; s < nb; ++s) {
+    const float* cf = coef + s * (TPS_MAXN + 3) * 2;
+    float lr = 0.f, lc = 0.f;
+#pragma unroll
+    for (int t = 0; t < TPS_MAXN; ++t) {
+      if (t < n) { lr = fmaf(ph[t], cf[2 * t], lr); lc = fmaf(ph[t], cf[2 * t + 1], lc); }
+    }
+    lr += q0 * cf[2 * n] + q1 * cf[2 * (n + 1)] + cf[2 * (n + 2)];
+    lc += q0 * cf[2 * n + 1] + q1 * cf[2 * (n + 1) + 1] + cf[2 * (n + 2) + 1];
+    const float x = lc * (float)(W - 1);
+    const float y = lr * (float)(H - 1);
+    const int b = b0 + s;
+    if (locs) { locs[((int64_t)b * HW + m) * 2] = x; locs[((int64_t)b * HW + m) * 2 + 1] = y; }
+    Bilin bl = bilin_setup(x, y, H, W);
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    if (bl.valid) {
+      const float* vb = vol + (int64_t)b * HW * C;
+      const int cx = bl.fx + 1, cy = bl.fy + 1;
+      const float w00 = bl.dx * bl.dy, w11 = (1.f - bl.dx) * (1.f - bl.dy);
+      const float w01 = bl.dx * (1.f - bl.dy), w10 = (1.f - bl.dx) * bl.dy;
+      const bool fxin = bl.fx >= 0 && bl.fx <= W - 1, cxin = cx >= 0 && cx <= W - 1;
+      const bool fyin = bl.fy >= 0 && bl.fy <= H - 1, cyin = cy >= 0 && cy <= H - 1;
+#pragma unroll
+      for (int c = 0; c < C; c += 4) {
+        float4 v;
+        if (fxin && fyin) { v = *reinterpret_cast<const float4*>(vb + ((int64_t)bl.fy * W + bl.fx) * C + c);
+          acc[c] += w00 * v.x; acc[c + 1] += w00 * v.y; acc[c + 2] += w00 * v.z; acc[c + 3] += w00 * v.w; }
+        if (cxin && cyin) { v = *reinterpret_cast<const float4*>(vb + ((int64_t)cy * W + cx) * C + c);
+          acc[c] += w11 * v.x; acc[c + 1] += w11 * v.y; acc[c + 2] += w11 * v.z; acc[c + 3] += w11 * v.w; }
+        if (fxin && cyin) { v = *reinterpret_cast<const float4*>(vb + ((int64_t)cy * W + bl.fx) * C + c);
+          acc[c] += w01 * v.x; acc[c + 1] += w01 * v.y; acc[c + 2] += w01 * v.z; acc[c + 3] += w01 * v.w; }
+        if (cxin && fyin) { v = *reinterpret_cast<const float4*>(vb + ((int64_t)bl.fy * W + cx) * C + c);
+          acc[c] += w10 * v.x; acc[c + 1] += w10 * v.y; acc[c + 2] += w10 * v.z; acc[c + 3] += w10 * v.w; }
+      }
+    }
+    float* ob = out + ((int64_t)b * HW + m) * C;
+#pragma unroll
+    for (int c = 0; c < C; c += 4) stg_stream4(ob + c, make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]));
+  }
+}
+
 // backward.  smem: Phi[(n+3)][257] and D[2*TPS_BS][257]; G[b][j][2] += Phi^T D
 template <int C>
 __global__ void __launch_bounds__(TPS_T) tps_warp_bwd_kernel(const float* __restrict__ vol, const float* __restrict__ theta,
@@ -548,6 +657,38 @@ int dafk_tps_warp_fwd(const float* vol, const float* theta, const float* consts,
     default: set_error("dafk_tps_warp_fwd: C must be 4, 8 or 16 (got %d)", C); return DAFK_ERR_UNSUPPORTED;
   }
   return check_launch("dafk_tps_warp_fwd");
+}
+
+int64_t dafk_tps_phi_table_floats(int H, int W, int n_cp) { return (int64_t)H * W * n_cp; }
+
+int dafk_tps_phi_table(const float* consts, float* table, int H, int W, int n_cp, void* stream) {
+  DAFK_REQUIRE(H > 1 && W > 1 && n_cp > 0 && n_cp <= TPS_MAXN, DAFK_ERR_BAD_ARG, "dafk_tps_phi_table: bad shape");
+  DAFK_REQUIRE(consts && table, DAFK_ERR_BAD_ARG, "dafk_tps_phi_table: null pointer");
+  tps_phi_table_kernel<<<(H * W + TPS_T - 1) / TPS_T, TPS_T, 0, as_stream(stream)>>>(consts, table, H, W, n_cp);
+  return check_launch("dafk_tps_phi_table");
+}
+
+int dafk_tps_warp_fwd_tab(const float* vol, const float* theta, const float* consts, const float* phi_table,
+                          float* coef_ws, float* out, float* locs, int B, int H, int W, int C, int n_cp, void* stream) {
+  DAFK_REQUIRE(B >= 0 && H > 1 && W > 1 && C > 0 && n_cp > 0, DAFK_ERR_BAD_ARG, "dafk_tps_warp_fwd_tab: bad shape");
+  DAFK_REQUIRE(n_cp <= TPS_MAXN, DAFK_ERR_UNSUPPORTED, "dafk_tps_warp_fwd_tab: at most %d control points", TPS_MAXN);
+  if (B == 0) return DAFK_OK;
+  DAFK_REQUIRE(vol && theta && consts && phi_table && coef_ws && out, DAFK_ERR_BAD_ARG, "dafk_tps_warp_fwd_tab: null pointer");
+  DAFK_REQUIRE(DAFK_ALIGNED16(vol) && DAFK_ALIGNED16(out), DAFK_ERR_ALIGN, "dafk_tps_warp_fwd_tab: alignment");
+  DAFK_REQUIRE(C == 4 || C == 8 || C == 16, DAFK_ERR_UNSUPPORTED, "dafk_tps_warp_fwd_tab: C must be 4, 8 or 16 (got %d)", C);
+  cudaStream_t s = as_stream(stream);
+  const int ncoef = B * (n_cp + 3) * 2;
+  tps_coef_kernel<<<(ncoef + 127) / 128, 128, 0, s>>>(theta, consts, coef_ws, B, n_cp);
+  int rc = check_launch("dafk_tps_warp_fwd_tab(coef)");
+  if (rc) return rc;
+  dim3 grid((H * W + TPS_T - 1) / TPS_T, (B + TPS_BS_TAB - 1) / TPS_BS_TAB);
+  switch (C) {
+    case 4: tps_warp_fwd_tab_kernel<4><<<grid, TPS_T, 0, s>>>(vol, coef_ws, phi_table, out, locs, B, H, W, n_cp); break;
+    case 8: tps_warp_fwd_tab_kernel<8><<<grid, TPS_T, 0, s>>>(vol, coef_ws, phi_table, out, locs, B, H, W, n_cp); break;
+    case 16: tps_warp_fwd_tab_kernel<16><<<grid, TPS_T, 0, s>>>(vol, coef_ws, phi_table, out, locs, B, H, W, n_cp); break;
+    default: set_error("dafk_tps_warp_fwd_tab: C must be 4, 8 or 16 (got %d)", C); return DAFK_ERR_UNSUPPORTED;
+  }
+  return check_launch("dafk_tps_warp_fwd_tab");
 }
 
 int dafk_tps_warp_bwd(const float* vol, const float* theta, const float* consts, const float* dout, float* dvol,

@@ -693,12 +693,34 @@ def tps_consts(cp_h, cp_w, device):
     return _tps_consts_cache[key]
 
 
+_tps_phi_cache = {}
+TPS_PHI_TABLE = os.environ.get("DAFK_TPS_PHI_TABLE", "1") != "0"
+
+
+def tps_phi_table(H, W, cp, device):
+    """phi(|q - c|^2) for every pixel and control point of one geometry: built once, then read by every warp"""
+    key = (H, W, cp[0], cp[1], str(device))
+    if key not in _tps_phi_cache:
+        n = cp[0] * cp[1]
+        tab = f32(int(_lib.lib().fn["dafk_tps_phi_table_floats"](H, W, n)), device=device)
+        call("tps_phi_table", tps_consts(cp[0], cp[1], device), tab, H, W, n, _S())
+        _tps_phi_cache[key] = tab
+    return _tps_phi_cache[key]
+
+
 def tps_warp_fwd(vol, theta, cp=(5, 5), want_locs=False):
     _chk(vol, theta)
     B, H, W, C = vol.shape
     consts = tps_consts(cp[0], cp[1], vol.device)
     out = torch.empty_like(vol)
     locs = f32(B, H * W, 2) if want_locs else None
+    if TPS_PHI_TABLE:
+        tab = tps_phi_table(H, W, cp, vol.device)
+        coef_ws = f32(B * (cp[0] * cp[1] + 3) * 2, device=vol.device)
+        instrument.timed("tps_warp_fwd", 0, 8.0 * vol.numel(),
+                         lambda: call("tps_warp_fwd_tab", vol, theta, consts, tab, coef_ws, out, locs, B, H, W, C,
+                                      cp[0] * cp[1], _S()))
+        return out, locs
     instrument.timed("tps_warp_fwd", 0, 8.0 * vol.numel(),
                      lambda: call("tps_warp_fwd", vol, theta, consts, out, locs, B, H, W, C, cp[0] * cp[1], _S()))
     return out, locs

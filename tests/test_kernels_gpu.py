@@ -569,3 +569,20 @@ def test_colsum_accumulates_bias_gradient(ops, M, C, dt):
     ops.colsum_(xd, out)
     ref = base.astype(np.float64) + xd.float().cpu().numpy().astype(np.float64).sum(0)
     assert rel_l2(cpu(out), ref) < 1e-5
+
+
+def test_tps_phi_table_path_is_bit_identical(ops):
+    """the per-geometry phi table (dafk_tps_phi_table + dafk_tps_warp_fwd_tab) holds exactly the values the in-kernel
+    evaluation computes, so both forward kernels return the same bits (warped volume and sampling locations)"""
+    B, H, W, C = 11, 37, 45, 8
+    vol = gpu(rng(0).uniform(size=(B, H, W, C)).astype(np.float32))
+    theta = gpu((rng(1).normal(size=(B, 25, 2)) * 0.05).astype(np.float32))
+    old = ops.TPS_PHI_TABLE
+    try:
+        ops.TPS_PHI_TABLE = True
+        a, la = ops.tps_warp_fwd(vol, theta, want_locs=True)
+        ops.TPS_PHI_TABLE = False
+        b, lb = ops.tps_warp_fwd(vol, theta, want_locs=True)
+    finally:
+        ops.TPS_PHI_TABLE = old
+    assert torch.equal(a, b) and torch.equal(la, lb)
