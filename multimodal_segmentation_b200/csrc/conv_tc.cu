@@ -228,8 +228,14 @@ struct HaloGeom {
   int w_resident;           // all weight tiles of the layer stay in shared memory for the whole kernel (SB unused)
 };
 
+// two MMA-issuing warps (1 and 6) split the accumulators of a tile: one thread issues a tcgen05.mma every ~30-40 cycles
+// (descriptor arithmetic + predicate + issue, all dependent), which is about as long as a 128 x 64 x 16 MMA runs, so a
+// single issuer left the tensor pipe 37 % active on the 64-channel layers
+constexpr int HALO_THREADS = 224;
+constexpr int HALO_MMA2_WARP = 6;
+
 template <int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
+__global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                      const __grid_constant__ CUtensorMap tmA1,
                                                                      const __grid_constant__ CUtensorMap tmB,
                                                                      const float* __restrict__ bias, void* __restrict__ y,
@@ -261,9 +267,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
     tma_prefetch_desc(&tmA0);
     if (C1 > 0) tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < g.SA; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
-    for (int s = 0; s < (g.SB > 0 ? g.SB : 1); ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }   // slot 0 = resident weights
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 1); mbar_init(tempty_bar + b, 128); }
+    // "empty" / "tile full" barriers collect one tcgen05.commit from each of the two MMA warps
+    for (int s = 0; s < g.SA; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 2); }
+    for (int s = 0; s < (g.SB > 0 ? g.SB : 1); ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 2); }   // slot 0 = resident weights
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 2); mbar_init(tempty_bar + b, 128); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -311,9 +318,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform; one elected lane issues) =====================
+  } else if (warp == 1 || warp == HALO_MMA2_WARP) {
+    // ===================== MMA issuers (warp-uniform; one elected lane of each issues) =====================
+    // warp 1 owns the even accumulators of a tile, warp 6 the odd ones: independent TMEM columns, same operand stages
     constexpr uint32_t idesc = make_idesc(TILE_PIX, BLOCK_N, 0, 0);
+    const int g_first = warp == 1 ? 0 : 1;
     const uint32_t leader = elect_one();
     const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b);
@@ -347,7 +356,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
             if (leader) {
               const uint64_t db = make_smem_desc(b_base + (uint32_t)(sb * B_BYTES), 16, 1024);
               const uint32_t a_tap = a_stage + (uint32_t)((r * Pp + q) * 128);
-              for (int gi = 0; gi < G; ++gi) {
+              for (int gi = g_first; gi < G; gi += 2) {
                 // rows gi*128 .. +127 of the raster, shifted by the tap: start is 128 B- but not 1024 B-aligned
                 // (measured: the 128B swizzle is a function of the absolute shared-memory address, so a window that
                 // starts in the middle of a swizzle atom needs no base_offset -- setting it breaks the result)
@@ -369,8 +378,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_halo_kernel(const __gri
       if (leader) umma_commit(tfull_bar + buf);
       __syncwarp();
     }
-  } else {
-    // ===================== epilogue =====================
+  } else if (warp < HALO_MMA2_WARP) {
+    // ===================== epilogue (warps 2-5) =====================
     const int q4 = warp & 3;
     const int img_pos = g.RS * g.Pp;
     int tc = 0;
@@ -822,7 +831,7 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   DAFK_REQUIRE(tiles < (1LL << 31), DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd: too many tiles");
   const int smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;      // one persistent CTA per SM
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
-  conv_tc_halo_kernel<BLOCK_N><<<grid, TC_THREADS, smem_req, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW,
+  conv_tc_halo_kernel<BLOCK_N><<<grid, HALO_THREADS, smem_req, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW,
                                                                  pad, g, n_blocks, w_rows_per_tap, w_row_off, y_sn, y_sy,
                                                                  y_sx, (int)tiles);
   return check_launch("dafk_conv_tc_fwd(halo)");

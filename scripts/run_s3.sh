@@ -1,2 +1,3 @@
-timeout 300 python -m pytest tests/test_kernels_gpu.py tests/test_golden_gpu.py -x -q -k "tps or spline or golden" 2>&1 | tail -4
-python scripts/bench_bw.py --only tps
+set -x
+python -m pytest tests -m gpu -x -q > gpurun_out/s3_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/s3_tests.log; tail -4 gpurun_out/s3_tests.log
+python bench.py --no-cpu-baseline --no-e2e > gpurun_out/s3_bench10.json 2> gpurun_out/s3_bench10.err; echo rc=$?
