@@ -15,12 +15,13 @@
 //     M=128 x N=64 accumulators (the tenth half is ignored) = 320 TMEM columns, kept over all tiles of the CTA;
 //   * split-K over pixel tiles; the epilogue adds the CTA's partial with 128-bit vector atomics.
 // Operand bytes per tile fall from 9 x 32 KB to 38.5 KB, the MMAs run at M = 128.
-//   warp 0: TMA producer    warp 1: MMA issuer (warp-uniform, one elected lane)    warps 2-5: epilogue
+//   warp 0: TMA producer    warps 1, 6: MMA issuers (warp-uniform, one elected lane each)    warps 2-5: epilogue
 #include "tc_ptx.cuh"
 
 namespace dafk {
 
-constexpr int WH_THREADS = 192;
+constexpr int WH_THREADS = 224;                      // warp 0 TMA, warps 1 and 6 MMA issue, warps 2-5 epilogue
+constexpr int WH_MMA2_WARP = 6;
 constexpr int WH_TW = 16, WH_TH = 8;                 // dY tile (pixels of one image)
 constexpr int WH_PW = WH_TW + 2, WH_PH = WH_TH + 2;  // haloed X tile
 constexpr int WH_DY_BYTES = WH_TW * WH_TH * 128;     // 16 KB
@@ -54,8 +55,9 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_tc_wgrad_halo_kernel(const
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmDY);
-    for (int s = 0; s < WH_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    mbar_init(tmem_full_bar, 1);
+    // one tcgen05.commit from each of the two issuing warps
+    for (int s = 0; s < WH_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 2); }
+    mbar_init(tmem_full_bar, 2);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, WH_TMEM_COLS);
@@ -80,8 +82,11 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_tc_wgrad_halo_kernel(const
           tma_load_4d(st + WH_DY_BYTES, &tmX, full_bar + s, cib * 64, x0 - 1, y0 - 1, img);
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == WH_MMA2_WARP) {
+      // two issuers: a single thread needs ~30-40 cycles per tcgen05.mma (descriptor arithmetic, predicate, issue) and a
+      // 128 x 64 x 16 MMA runs 48; warp 1 owns accumulators 0, 2, 4 and warp 6 accumulators 1, 3
       constexpr uint32_t idesc = make_idesc(128, 64, 1, 1);     // A (X) and B (dY) both MN-major
+      const bool first = warp == 1;
       const uint32_t leader = elect_one();
       const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t s0 = smem_u32(smem);
@@ -99,11 +104,14 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_tc_wgrad_halo_kernel(const
             const uint32_t acc = (it > 0 || y > 0) ? 1u : 0u;
             // A: tap pairs (0,0)+(0,1) | (0,2)+(1,0) | (1,1)+(1,2) | (2,0)+(2,1) | (2,2)+ignored
             const uint32_t row0 = x_s + (uint32_t)((y * WH_PW) * 128);
-            umma_bf16(tmem_acc + 0u, make_smem_desc(row0 + (0 * WH_PW + 0) * 128, 128, 1024), db, idesc, acc);
-            umma_bf16(tmem_acc + 64u, make_smem_desc(row0 + (0 * WH_PW + 2) * 128, (WH_PW - 2) * 128, 1024), db, idesc, acc);
-            umma_bf16(tmem_acc + 128u, make_smem_desc(row0 + (1 * WH_PW + 1) * 128, 128, 1024), db, idesc, acc);
-            umma_bf16(tmem_acc + 192u, make_smem_desc(row0 + (2 * WH_PW + 0) * 128, 128, 1024), db, idesc, acc);
-            umma_bf16(tmem_acc + 256u, make_smem_desc(row0 + (2 * WH_PW + 2) * 128, 128, 1024), db, idesc, acc);
+            if (first) {
+              umma_bf16(tmem_acc + 0u, make_smem_desc(row0 + (0 * WH_PW + 0) * 128, 128, 1024), db, idesc, acc);
+              umma_bf16(tmem_acc + 128u, make_smem_desc(row0 + (1 * WH_PW + 1) * 128, 128, 1024), db, idesc, acc);
+              umma_bf16(tmem_acc + 256u, make_smem_desc(row0 + (2 * WH_PW + 2) * 128, 128, 1024), db, idesc, acc);
+            } else {
+              umma_bf16(tmem_acc + 64u, make_smem_desc(row0 + (0 * WH_PW + 2) * 128, (WH_PW - 2) * 128, 1024), db, idesc, acc);
+              umma_bf16(tmem_acc + 192u, make_smem_desc(row0 + (2 * WH_PW + 0) * 128, 128, 1024), db, idesc, acc);
+            }
           }
           umma_commit(empty_bar + s);
         }
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) conv_tc_wgrad_halo_kernel(const
       }
       if (leader) umma_commit(tmem_full_bar);
       __syncwarp();
-    } else {
+    } else if (warp < WH_MMA2_WARP) {
       const int q4 = warp & 3;
       const int row = q4 * 32 + lane;                 // accumulator row = TMEM lane: [second tap of the pair][ci]
       const int half = row >> 6, ci = row & 63;
