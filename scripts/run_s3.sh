@@ -1,4 +1,3 @@
 set -x
-python -m pytest tests -m gpu -x -q > gpurun_out/s3_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/s3_tests.log; tail -4 gpurun_out/s3_tests.log
-python bench.py > gpurun_out/s3_bench11.json 2> gpurun_out/s3_bench11.err; echo rc=$?
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/s3_ref2.json 2> gpurun_out/s3_ref2.err; echo rc=$?
+ncu --metrics gpu__time_duration.sum --clock-control none -s 2600 -c 2390 --csv --log-file gpurun_out/s3_launches2.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/s3_ncu_launch2.log 2>&1; echo rc=$?
+python scripts/bench_bw.py > gpurun_out/s3_bw3.txt 2>&1; tail -3 gpurun_out/s3_bw3.txt
