@@ -1,3 +1,3 @@
-set -x
-ncu --metrics gpu__time_duration.sum --clock-control none -s 2600 -c 2390 --csv --log-file gpurun_out/s3_launches2.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/s3_ncu_launch2.log 2>&1; echo rc=$?
-python scripts/bench_bw.py > gpurun_out/s3_bw3.txt 2>&1; tail -3 gpurun_out/s3_bw3.txt
+timeout 300 python -m pytest tests/test_conv_nc_gpu.py -x -q 2>&1 | tail -3
+NC_B=192 timeout 200 python scripts/bench_nc.py film8x8 10 2>&1 | tail -3
+timeout 200 python scripts/bench_nc.py "" 10 2>&1 | tail -12
