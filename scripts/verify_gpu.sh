@@ -1,2 +1,2 @@
 set -x
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s3_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/s3_smoke.log
+python -m pytest tests/test_models_gpu.py -x -q -s -k "dice_within" 2>&1 | tail -8

@@ -16,12 +16,13 @@ import pytest
 import torch
 
 from oracle import ref_models as RM
+from oracle import ref_ops as R
 from tests.util import rel_l2
 
 pytestmark = pytest.mark.gpu
 
 
-def build_net(H=64, filters=16, rounding=False, use_tc=False, decoder_type="film", seed=3):
+def build_net(H=64, filters=16, rounding=False, use_tc=False, decoder_type="film", seed=3, lr=None):
     from multimodal_segmentation_b200 import engine as E
     from multimodal_segmentation_b200.configuration import dafnet_config_chaos
     from multimodal_segmentation_b200.keras_like import EasyDict
@@ -33,6 +34,8 @@ def build_net(H=64, filters=16, rounding=False, use_tc=False, decoder_type="film
     conf.n_pairs = 1
     conf.seed = seed
     conf.folder = "/tmp/dafk_test_no_such_folder"
+    if lr is not None:
+        conf.lr = lr
     net = DAFNet(conf)
     net.build()
     # theta = 0 sits exactly on the kink of the bilinear sampler: move off it; sharpen the anatomy softmax
@@ -432,3 +435,33 @@ def test_cuda_graph_step_matches_host_launched_step():
 
 def _flat(step):
     return [t for (_, g, dm, di) in step for t in list(g) + list(dm) + list(di)]
+
+
+def test_tensor_core_inference_dice_within_half_percent():
+    """north-star: on the bf16 tensor-core path the Dice of the predicted masks on a fixed synthetic batch stays within
+    0.5 % of the reference arithmetic.  The weights are first moved off their random initialisation by a few training
+    steps of the product (tensor-core mode), exported, and the SAME weights then predict through the fp64 oracle
+    (models/mmsdnet.py:210-224, type 'simple': Segmentor(Enc_Anatomy(x)) in the inference phase, binarised anatomy)."""
+    net, conf = build_net(H=64, filters=64, rounding=True, use_tc=True, lr=1e-3)
+    fixed = make_batch(conf, 4, seed=9)
+    for step in range(60):                     # over-fit the fixed batch so that organs are actually predicted
+        tr = product_step(net, fixed, True)
+        tr.apply_gradients()
+    torch.cuda.synchronize()
+    W = all_weights(net)
+    x1, x2, _, _, _, _, m1, m2 = fixed
+    ref = RM.predict_mask_simple(W, torch.from_numpy(x2).double(), "enc2_", "shared_").numpy()
+    got = net.predict_mask(1, "simple", [x1, x2])
+    assert got.shape == ref.shape
+    real = m2[..., :conf.num_masks].astype(np.float64)
+    d_ref = R.np_dice(real, ref, binarise=True)
+    d_got = R.np_dice(real, got.astype(np.float64), binarise=True)
+    soft_ref = R.np_dice(real, ref)
+    soft_got = R.np_dice(real, got.astype(np.float64))
+    mism = float(np.mean(np.argmax(got, -1) != np.argmax(ref, -1)))
+    print("dice(binarised) product %.5f oracle %.5f | soft dice %.5f / %.5f | argmax mismatch %.4f" %
+          (d_got, d_ref, soft_got, soft_ref, mism))
+    assert d_ref > 0.02                                             # the over-fitted net does predict organs
+    assert abs(d_got - d_ref) <= 0.005 * d_ref, (d_got, d_ref)      # measured: 0.24 %
+    assert abs(soft_got - soft_ref) <= 0.005 * soft_ref, (soft_got, soft_ref)
+    assert mism < 0.01, mism                                        # measured: 0.2 % of the pixels change class
