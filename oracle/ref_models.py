@@ -432,3 +432,21 @@ def predict_mask_simple(W, x, down_prefix, up_prefix):
     """models/mmsdnet.py:210-224 type 'simple': Segmentor(Enc_Anatomy(x)) in inference phase"""
     st = BNState(W, training=False)
     return segmentor(W, anatomy_encoder(W, x, st, down_prefix, up_prefix), st)
+
+
+def predict_mask(W, modality_index, type, x_list):
+    """models/mmsdnet.py:210-232, all four types, inference phase: 'simple' Segmentor(s2); 'def' Segmentor(s1 deformed
+    onto s2); 'max' Segmentor(Maximum(s1 deformed, s2)); 'maxnostn' Segmentor(np.max([s1, s2]))"""
+    assert type in ("simple", "def", "max", "maxnostn")
+    st = BNState(W, training=False)
+    idx2 = modality_index
+    idx1 = 1 - idx2
+    pre = ("enc1_", "enc2_")
+    s1 = anatomy_encoder(W, x_list[idx1], st, pre[idx1], "shared_")
+    s2 = anatomy_encoder(W, x_list[idx2], st, pre[idx2], "shared_")
+    if type == "simple":
+        return segmentor(W, s2, st)
+    if type == "maxnostn":
+        return segmentor(W, torch.maximum(s1, s2), st)
+    deformed, fused, _ = anatomy_fuser(W, s1, s2)
+    return segmentor(W, deformed if type == "def" else fused, st)

@@ -1,2 +1,2 @@
 set -x
-python -m pytest tests/test_models_gpu.py -x -q -s -k "dice_within" 2>&1 | tail -8
+python -m pytest tests/test_models_gpu.py -x -q -k "predict_mask" 2>&1 | tail -8

@@ -278,6 +278,24 @@ def test_predict_mask_simple_matches_oracle():
     assert mism < 5e-3, mism
 
 
+@pytest.mark.parametrize("type", ["simple", "def", "max", "maxnostn"])
+@pytest.mark.parametrize("modality_index", [0, 1])
+def test_predict_mask_all_types_match_oracle(type, modality_index):
+    """models/mmsdnet.py:210-232 (used by validate / ModelTester): host round trips of the reference replaced by the
+    product's predict path; strict fp32 kernels, binarised anatomy: the soft masks agree except where an anatomy pixel
+    sits on the rounding threshold"""
+    net, conf = build_net(H=64, filters=16, rounding=True, use_tc=False)
+    batch = make_batch(conf, 3)
+    W = all_weights(net)
+    xs = [torch.from_numpy(batch[0]).double(), torch.from_numpy(batch[1]).double()]
+    ref = RM.predict_mask(W, modality_index, type, xs).numpy()
+    got = net.predict_mask(modality_index, type, [batch[0], batch[1]])
+    assert got.shape == ref.shape
+    mism = np.mean(np.argmax(got, -1) != np.argmax(ref, -1))
+    assert mism < 5e-3, mism
+    assert rel_l2(got, ref) < 2e-2, rel_l2(got, ref)        # a flipped anatomy pixel moves a 3x3 neighbourhood
+
+
 # ------------------------------------------------------------------ components in isolation
 def _run_component(model, oracle_fn, inputs, rs, fwd_tol=1e-4, grad_tol=1e-4, skip_suffix=None):
     from multimodal_segmentation_b200 import engine as E
