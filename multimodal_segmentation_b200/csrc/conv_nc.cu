@@ -314,46 +314,69 @@ __global__ void __launch_bounds__(NC_FWD_THREADS, 1) conv_nc_fwd_kernel(NcFwdP p
             const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0);
             const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            // the EB tiles of the batch are processed in lock step, branch-free up to the (predicated) stores: a single
+            // epilogue warp per scheduler runs one dependent chain at ~1 instruction per 5 cycles, four independent
+            // chains hide that latency
+            bool ok[EB];
+            int64_t obase[EB];
 #pragma unroll
             for (int e = 0; e < EB; ++e) {
-              if (tb + e < gt) {
-                const int m = (t0 + tb + e) * 128 + q4 * 32 + lane;
-                const int orow = (int)__umulhi((uint32_t)m, magicP);
-                const int ocol = m - orow * p.P;
-                if (orow < rows_here && ocol < p.Wo) {
-                  const int64_t obase = (((int64_t)n * p.Ho + y0 + orow) * p.Wo + ocol) * p.Cout;
-                  float f[8];
+              const int m = (t0 + tb + e) * 128 + q4 * 32 + lane;
+              const int orow = (int)__umulhi((uint32_t)m, magicP);
+              const int ocol = m - orow * p.P;
+              ok[e] = (tb + e < gt) && orow < rows_here && ocol < p.Wo;
+              obase[e] = (((int64_t)n * p.Ho + y0 + orow) * p.Wo + ocol) * p.Cout + c0;
+            }
+            float f[EB][8];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[e][j]) + bb[j];
-                  if (p.act == DAFK_ACT_LRELU) {
+            for (int e = 0; e < EB; ++e) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] = f[j] > 0.f ? f[j] : p.alpha * f[j];
-                  } else if (p.act == DAFK_ACT_RELU) {
+              for (int j = 0; j < 8; ++j) f[e][j] = __uint_as_float(v[e][j]) + bb[j];
+            }
+            if (p.act == DAFK_ACT_LRELU) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-                  } else if (p.act == DAFK_ACT_TANH) {
+              for (int e = 0; e < EB; ++e)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] = tanhf(f[j]);
-                  }
+                for (int j = 0; j < 8; ++j) f[e][j] = f[e][j] > 0.f ? f[e][j] : p.alpha * f[e][j];
+            } else if (p.act == DAFK_ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < EB; ++e)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[e][j] = fmaxf(f[e][j], 0.f);
+            } else if (p.act == DAFK_ACT_TANH) {
+#pragma unroll
+              for (int e = 0; e < EB; ++e)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[e][j] = tanhf(f[e][j]);
+            }
+            if (p.y_dt == DAFK_F32 && (p.Cout & 3) == 0) {
+              const bool second = c0 + 4 < p.Cout;
+#pragma unroll
+              for (int e = 0; e < EB; ++e) {
+                if (ok[e]) {
+                  float* o = reinterpret_cast<float*>(y) + obase[e];
+                  *reinterpret_cast<float4*>(o) = make_float4(f[e][0], f[e][1], f[e][2], f[e][3]);
+                  if (second) *reinterpret_cast<float4*>(o + 4) = make_float4(f[e][4], f[e][5], f[e][6], f[e][7]);
+                }
+              }
+            } else if (p.y_dt == DAFK_BF16 && (p.Cout & 7) == 0) {
+#pragma unroll
+              for (int e = 0; e < EB; ++e)
+                if (ok[e]) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + obase[e]) = nc_pack8(f[e]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < EB; ++e) {
+                if (ok[e]) {
                   if (p.y_dt == DAFK_F32) {
-                    float* o = reinterpret_cast<float*>(y) + obase + c0;
-                    if ((p.Cout & 3) == 0) {
-                      *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-                      if (c0 + 4 < p.Cout) *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                    } else {
+                    float* o = reinterpret_cast<float*>(y) + obase[e];
 #pragma unroll
-                      for (int j = 0; j < 8; ++j)
-                        if (c0 + j < p.Cout) o[j] = f[j];
-                    }
+                    for (int j = 0; j < 8; ++j)
+                      if (c0 + j < p.Cout) o[j] = f[e][j];
                   } else {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + obase + c0;
-                    if ((p.Cout & 7) == 0) {
-                      *reinterpret_cast<uint4*>(o) = nc_pack8(f);
-                    } else {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + obase[e];
 #pragma unroll
-                      for (int j = 0; j < 8; ++j)
-                        if (c0 + j < p.Cout) o[j] = __float2bfloat16_rn(f[j]);
-                    }
+                    for (int j = 0; j < 8; ++j)
+                      if (c0 + j < p.Cout) o[j] = __float2bfloat16_rn(f[e][j]);
                   }
                 }
               }
