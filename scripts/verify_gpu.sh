@@ -1,3 +1,3 @@
-timeout 300 python -m pytest tests/test_conv_nc_gpu.py -x -q 2>&1 | tail -3
-NC_B=192 timeout 200 python scripts/bench_nc.py film8x8 10 2>&1 | tail -3
-timeout 200 python scripts/bench_nc.py "" 10 2>&1 | tail -12
+set -x
+python -m pytest tests -m gpu -x -q > gpurun_out/s3_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/s3_tests.log; tail -3 gpurun_out/s3_tests.log
+python bench.py > gpurun_out/s3_bench12.json 2> gpurun_out/s3_bench12.err; echo rc=$?
