@@ -5,7 +5,6 @@ base_executor.py:103-110).  Augmentation is out of scope for the hot path (synth
 generator here is a seeded, shuffling mini-batch iterator that stages each batch in PINNED host
 memory -- the host->device copy of the step is an asynchronous cudaMemcpy from that buffer.
 """
-import itertools
 import logging
 
 import numpy as np

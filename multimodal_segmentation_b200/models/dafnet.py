@@ -3,16 +3,11 @@ encoder, anatomy fuser (locnet + thin-plate-spline STN), segmentor, FiLM/SPADE d
 discriminators; expert-pairing trainers (dafnet.py:140-222), automated-pairing trainers with the Balancer
 (dafnet.py:224-334,352-361) and the Z-regressor (dafnet.py:336-350)."""
 import logging
-import traceback
 
-import numpy as np
-
-from .. import costs
 from .. import engine as E
 from ..keras_like import BuildScope
 from ..model_components import anatomy_fuser, balancer, decoder, modality_encoder, segmentor
 from ..model_components.anatomy_encoder import AnatomyEncoders
-from ..utils.sdnet_utils import make_trainable
 from .discriminator import Discriminator
 from .mmsdnet import MMSDNet, MuModel, to_eps
 from .trainers import DiscriminatorTrainer, Trainer

@@ -10,7 +10,7 @@ import os
 import torch
 
 from . import _lib, instrument
-from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, DAFK_BF16, DAFK_F32, ConvDesc, call
+from ._lib import ACT_LRELU, ACT_NONE, DAFK_BF16, DAFK_F32, ConvDesc, call
 
 _S = _lib.stream_ptr
 

@@ -2,7 +2,6 @@
 bucket per optimizer step, 1/world folded into the fused Adam launch.  Nothing else shards
 (SURVEY.md 8e): BatchNorm statistics and the cross-entropy class weights stay per-shard, exactly what
 Keras' fit() would do with 32-sample mini-batches."""
-import torch
 import torch.distributed as dist
 
 from .models.trainers import Trainer
