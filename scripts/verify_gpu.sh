@@ -1,3 +1,6 @@
+#!/bin/bash
+# what the driver runs at round end, in one go on a GPU box:  bash scripts/verify_gpu.sh
 set -x
-python -m pytest tests -m gpu -x -q > gpurun_out/s3_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/s3_tests.log; tail -3 gpurun_out/s3_tests.log
-python bench.py > gpurun_out/s3_bench12.json 2> gpurun_out/s3_bench12.err; echo rc=$?
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python bench.py | tee gpurun_out/bench_verify.json | cut -c1-400

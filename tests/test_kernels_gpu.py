@@ -544,18 +544,6 @@ def test_rotation_augmentation_matches_scipy(ops, shape):
     assert np.abs(y - ref).max() < 2e-4, np.abs(y - ref).max()     # fp32 coordinates vs fp64: ~1e-5 px * gradient
 
 
-def test_flows_with_one_seed_rotate_images_and_masks_together():
-    from multimodal_segmentation_b200.model_executors.base_executor import BatchFlow, FlowGroup
-    a = np.arange(40, dtype=np.float32).reshape(10, 2, 2, 1)
-    g = FlowGroup([BatchFlow(a, 4, 10, 20.0), BatchFlow(a * 2, 4, 10, 20.0)])
-    for _ in range(4):
-        xa, xb = next(g)
-        assert np.array_equal(xa.numpy() * 2, xb.numpy())                       # same order
-        assert np.array_equal(g.flows[0].last_theta, g.flows[1].last_theta)     # same angles
-        assert g.last_theta.shape == (xa.shape[0],) and np.abs(g.last_theta).max() <= np.deg2rad(20.0)
-        g.mark_copied()
-    assert BatchFlow(a, 4, 10).last_theta is None
-
 
 @pytest.mark.parametrize("M,C,dt", [(1000, 64, "bf16"), (3 * 54 * 54, 128, "bf16"), (777, 256, "f32"), (513, 8, "f32"),
                                     (300, 20, "f32"), (129, 1024, "bf16")])

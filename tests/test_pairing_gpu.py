@@ -162,26 +162,6 @@ def test_automated_pairing_generator_step(supervised):
             assert rel_l2(p.grad.cpu().numpy(), r) < 1e-3, p.name
 
 
-def test_expand_pairs_keeps_the_expert_pair_first():
-    from multimodal_segmentation_b200.loaders.synthetic_chaos import PairedData
-    n = 19
-    imgs = [np.arange(n, dtype=np.float32).reshape(n, 1, 1, 1) + 100 * m for m in range(2)]
-    d = PairedData([imgs[0].copy(), imgs[1].copy()], [np.zeros((n, 1, 1, 4), np.float32)] * 2)
-    np.random.seed(0)
-    d.expand_pairs(2, 0, neighborhood=3)
-    d.expand_pairs(2, 1, neighborhood=3)
-    for m in range(2):
-        x = d.get_images_modi(m)
-        assert x.shape == (n, 1, 1, 3)
-        assert np.array_equal(x[..., 0], imgs[m][..., 0])                  # channel 0 = the expert pair
-        for i in range(n):
-            a = (i // PairedData.SLICES_PER_VOLUME) * PairedData.SLICES_PER_VOLUME
-            vol = range(a, min(n, a + PairedData.SLICES_PER_VOLUME))
-            cands = x[i, 0, 0, 1:] - 100 * m
-            assert all(int(c) in vol for c in cands)                       # neighbours come from the same volume
-            if len(vol) >= 5:
-                assert all(abs(int(c) - i) <= 4 for c in cands) and len(set(cands)) == 2 and i not in cands
-
 
 def test_experiment_automated_pairing_one_epoch(tmp_path, monkeypatch):
     """experiment.py --automatedpairing 1: train (supervised + unsupervised paired trainers, discriminators) ->
