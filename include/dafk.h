@@ -260,6 +260,18 @@ int dafk_colsum(const void* x, int x_dt, float* out, int64_t M, int C, void* str
  * The packed weight matrix has w_rows_per_tap rows per tap; this call produces the Cout output
  * channels whose rows start at w_row_off (w_rows_per_tap = Cout, w_row_off = 0 for a plain
  * forward; a data-gradient towards one source of a Concatenate uses a row window). */
+/* dafk_conv_tc_fwd with a fused epilogue activation (NONE or RELU), and the folding of an inference-mode
+ * BatchNormalization (utils/model_utils.py:10, Keras learning phase 0) into the convolution that feeds it:
+ *   dafk_bn_fold:          scale[c] = gamma / sqrt(moving_var + eps),  bias_out[c] = (conv_bias - moving_mean) * scale + beta
+ *   dafk_pack_conv_scaled: forward operand of w[KH,KW,Cin,Cout] * scale[Cout] (as dafk_pack_conv mode 0)
+ * conv -> BN -> ReLU of a predict pass then is ONE kernel: dafk_conv_tc_fwd_act(..., bias_out, ..., DAFK_ACT_RELU). */
+int dafk_conv_tc_fwd_act(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,
+                         int w_row_off, const float* bias, void* y, int y_dt, int N, int H, int W, int Cout, int KH,
+                         int KW, int stride, int pad, int Ho, int Wo, int64_t y_sn, int64_t y_sy, int64_t y_sx, int act,
+                         void* stream);
+int dafk_bn_fold(const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
+                 const float* conv_bias, float eps, float* scale, float* bias_out, int C, void* stream);
+int dafk_pack_conv_scaled(const float* w_hwio, const float* scale, void* wp, int KH, int KW, int Cin, int Cout, void* stream);
 int dafk_conv3x3_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp,
                         int w_rows_per_tap, int w_row_off, const float* bias, void* y, int y_dt,
                         int N, int H, int W, int Cout, void* stream);

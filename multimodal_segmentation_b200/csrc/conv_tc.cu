@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
                                                                     int KH, int KW, int stride, int pad, TileGeom g,
                                                                     int n_blocks, int w_rows_per_tap, int w_row_off,
                                                                     long long y_sn, long long y_sy, long long y_sx,
-                                                                    int total_tiles) {
+                                                                    int total_tiles, int act) {
   constexpr int B_BYTES = BLOCK_N * KBLK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;     // two accumulator buffers
@@ -172,7 +172,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
           float f[32];
           const int cvalid = Cout - (n0 + c);            // channels of this chunk that exist (Cout % 8 == 0)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + n0 + c + j) : 0.f);
+          for (int j = 0; j < 32; ++j) {
+              f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + n0 + c + j) : 0.f);
+              if (act == DAFK_ACT_RELU) f[j] = fmaxf(f[j], 0.f);     // folded inference-mode BatchNorm + ReLU
+            }
           if (y_dt == DAFK_F32) {
             float* o = reinterpret_cast<float*>(y) + obase + c;
 #pragma unroll
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
                                                                      int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1,
                                                                      int KH, int KW, int pad, HaloGeom g, int n_blocks,
                                                                      int w_rows_per_tap, int w_row_off, long long y_sn,
-                                                                     long long y_sy, long long y_sx, int total_tiles) {
+                                                                     long long y_sy, long long y_sx, int total_tiles, int act) {
   constexpr int B_BYTES = BLOCK_N * KBLK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -412,7 +415,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
             float f[32];
             const int cvalid = Cout - (n0 + c);            // channels of this chunk that exist (Cout % 8 == 0)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + n0 + c + j) : 0.f);
+            for (int j = 0; j < 32; ++j) {
+              f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + n0 + c + j) : 0.f);
+              if (act == DAFK_ACT_RELU) f[j] = fmaxf(f[j], 0.f);     // folded inference-mode BatchNorm + ReLU
+            }
             if (y_dt == DAFK_F32) {
               float* o = reinterpret_cast<float*>(y) + obase + c;
 #pragma unroll
@@ -576,7 +582,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_wgrad_kernel(const __grid_
 // Cip / Cop = Cin / Cout rounded up to 64: the packed matrices are zero-padded so that partial channel blocks
 // contribute nothing
 __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int KH, int KW, int Cin,
-                              int Cout, int Cip, int Cop, int for_dgrad) {
+                              int Cout, int Cip, int Cop, int for_dgrad, const float* __restrict__ scale) {
   int64_t total = (int64_t)KH * KW * Cip * Cop;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -593,7 +599,9 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
       ci = (int)(t % Cip);
       tap = KH * KW - 1 - (int)(t / Cip);   // mirrored in both axes
     }
-    wp[i] = (ci < Cin && co < Cout) ? __float2bfloat16_rn(w[((int64_t)tap * Cin + ci) * Cout + co]) : __float2bfloat16_rn(0.f);
+    float v = (ci < Cin && co < Cout) ? w[((int64_t)tap * Cin + ci) * Cout + co] : 0.f;
+    if (scale != nullptr && co < Cout) v *= scale[co];       // folded BatchNorm: w' = w * gamma * rstd (per output channel)
+    wp[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -689,7 +697,7 @@ template <int BLOCK_N, int STAGES>
 static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const float* bias, void* y,
                       int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int stride, int pad,
                       const TileGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
-                      long long y_sx, cudaStream_t s) {
+                      long long y_sx, int act, cudaStream_t s) {
   constexpr int smem = STAGES * (A_BYTES + BLOCK_N * KBLK * 2) + 1024 + 256;
   static_assert(smem > 116 * 1024 && smem <= 227 * 1024, "one persistent CTA per SM");
   static bool configured = false;
@@ -704,7 +712,7 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
   conv_tc_fwd_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1,
                                                                     KH, KW, stride, pad, g, n_blocks, w_rows_per_tap,
-                                                                    w_row_off, y_sn, y_sy, y_sx, (int)tiles);
+                                                                    w_row_off, y_sn, y_sy, y_sx, (int)tiles, act);
   return check_launch("dafk_conv_tc_fwd");
 }
 
@@ -817,7 +825,7 @@ template <int BLOCK_N>
 static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const float* bias, void* y,
                        int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int pad,
                        const HaloGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
-                       long long y_sx, cudaStream_t s) {
+                       long long y_sx, int act, cudaStream_t s) {
   const int ncb_all = (C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK;
   const int smem = g.SA * g.a_bytes + (g.w_resident ? ncb_all * KH * KW : g.SB) * BLOCK_N * KBLK * 2 + 1024 + 512;
   static bool configured = false;
@@ -833,7 +841,7 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
   conv_tc_halo_kernel<BLOCK_N><<<grid, HALO_THREADS, smem_req, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW,
                                                                  pad, g, n_blocks, w_rows_per_tap, w_row_off, y_sn, y_sy,
-                                                                 y_sx, (int)tiles);
+                                                                 y_sx, (int)tiles, act);
   return check_launch("dafk_conv_tc_fwd(halo)");
 }
 
@@ -865,10 +873,10 @@ using namespace dafk;
 
 extern "C" {
 
-int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,
-                     int w_row_off, const float* bias, void* y, int y_dt, int N, int H, int W, int Cout, int KH,
-                     int KW, int stride, int pad, int Ho, int Wo, int64_t y_sn, int64_t y_sy, int64_t y_sx,
-                     void* stream) {
+static int conv_tc_fwd_impl(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,
+                            int w_row_off, const float* bias, void* y, int y_dt, int N, int H, int W, int Cout, int KH,
+                            int KW, int stride, int pad, int Ho, int Wo, int64_t y_sn, int64_t y_sy, int64_t y_sx,
+                            int act, void* stream) {
   DAFK_REQUIRE(N > 0 && H > 0 && W > 0 && C0 > 0 && C1 >= 0 && Cout > 0 && KH > 0 && KW > 0 && Ho > 0 && Wo > 0,
                DAFK_ERR_BAD_ARG, "dafk_conv_tc_fwd: bad shape");
   DAFK_REQUIRE(stride == 1 || stride == 2, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd: stride must be 1 or 2");
@@ -927,9 +935,9 @@ int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void*
       if (rc) return rc;
       if (bn == 128)
         return launch_halo<128>(h0, h1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, hg, w_rows_per_tap, w_row_off,
-                                y_sn, y_sy, y_sx, s);
+                                y_sn, y_sy, y_sx, act, s);
       return launch_halo<64>(h0, h1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, hg, w_rows_per_tap, w_row_off,
-                             y_sn, y_sy, y_sx, s);
+                             y_sn, y_sy, y_sx, act, s);
     }
   }
   if (Cout % 256 == 0) {
@@ -941,19 +949,36 @@ int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void*
       rc = make_w_map(&b, wp, taps * w_rows_per_tap, Kpad, 256);
       if (rc) return rc;
       return launch_fwd<256, 4>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
-                                w_row_off, y_sn, y_sy, y_sx, s);
+                                w_row_off, y_sn, y_sy, y_sx, act, s);
     }
   }
   if (Cout % 128 == 0) {
     rc = make_w_map(&b, wp, taps * w_rows_per_tap, Kpad, 128);
     if (rc) return rc;
     return launch_fwd<128, 6>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
-                              w_row_off, y_sn, y_sy, y_sx, s);
+                              w_row_off, y_sn, y_sy, y_sx, act, s);
   }
   rc = make_w_map(&b, wp, taps * w_rows_per_tap, Kpad, 64);
   if (rc) return rc;
   return launch_fwd<64, 8>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
-                           w_row_off, y_sn, y_sy, y_sx, s);
+                           w_row_off, y_sn, y_sy, y_sx, act, s);
+}
+
+int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,
+                     int w_row_off, const float* bias, void* y, int y_dt, int N, int H, int W, int Cout, int KH,
+                     int KW, int stride, int pad, int Ho, int Wo, int64_t y_sn, int64_t y_sy, int64_t y_sx,
+                     void* stream) {
+  return conv_tc_fwd_impl(x0, C0, x1, C1, wp, w_rows_per_tap, w_row_off, bias, y, y_dt, N, H, W, Cout, KH, KW, stride, pad,
+                          Ho, Wo, y_sn, y_sy, y_sx, DAFK_ACT_NONE, stream);
+}
+
+int dafk_conv_tc_fwd_act(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,
+                         int w_row_off, const float* bias, void* y, int y_dt, int N, int H, int W, int Cout, int KH,
+                         int KW, int stride, int pad, int Ho, int Wo, int64_t y_sn, int64_t y_sy, int64_t y_sx, int act,
+                         void* stream) {
+  DAFK_REQUIRE(act == DAFK_ACT_NONE || act == DAFK_ACT_RELU, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd_act: act must be NONE or RELU");
+  return conv_tc_fwd_impl(x0, C0, x1, C1, wp, w_rows_per_tap, w_row_off, bias, y, y_dt, N, H, W, Cout, KH, KW, stride, pad,
+                          Ho, Wo, y_sn, y_sy, y_sx, act, stream);
 }
 
 int dafk_conv3x3_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,
@@ -970,7 +995,7 @@ int dafk_pack_conv(const float* w_hwio, void* wp, int KH, int KW, int Cin, int C
   const int Cip = (Cin + 63) / 64 * 64, Cop = (Cout + 63) / 64 * 64;
   if (mode == 0 || mode == 1) {
     int64_t total = (int64_t)KH * KW * Cip * Cop;
-    pack_w_kernel<<<bw_grid(total, 256), 256, 0, s>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, Cip, Cop, mode);
+    pack_w_kernel<<<bw_grid(total, 256), 256, 0, s>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, Cip, Cop, mode, nullptr);
   } else if (mode == 2) {
     DAFK_REQUIRE(KH % 2 == 0 && KW % 2 == 0 && (pa == 0 || pa == 1) && (pb == 0 || pb == 1), DAFK_ERR_BAD_ARG,
                  "dafk_pack_conv: stride-2 data-gradient packing needs an even kernel and a parity in {0,1}");
@@ -981,6 +1006,34 @@ int dafk_pack_conv(const float* w_hwio, void* wp, int KH, int KW, int Cin, int C
     return DAFK_ERR_BAD_ARG;
   }
   return check_launch("dafk_pack_conv");
+}
+
+// inference-mode BatchNorm folded into the convolution that feeds it (forward operand only):
+//   scale[co] = gamma * rsqrt(var + eps),  bias'[co] = (bias - mean) * scale + beta,  wp = bf16(w * scale[co])
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var,
+                               const float* __restrict__ bias, float eps, float* __restrict__ scale,
+                               float* __restrict__ bias_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * (1.f / sqrtf(var[c] + eps));
+  scale[c] = sc;
+  bias_out[c] = ((bias ? bias[c] : 0.f) - mean[c]) * sc + beta[c];
+}
+
+int dafk_bn_fold(const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
+                 const float* conv_bias, float eps, float* scale, float* bias_out, int C, void* stream) {
+  DAFK_REQUIRE(C > 0 && gamma && beta && moving_mean && moving_var && scale && bias_out, DAFK_ERR_BAD_ARG, "dafk_bn_fold: bad argument");
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(gamma, beta, moving_mean, moving_var, conv_bias, eps, scale, bias_out, C);
+  return check_launch("dafk_bn_fold");
+}
+
+int dafk_pack_conv_scaled(const float* w_hwio, const float* scale, void* wp, int KH, int KW, int Cin, int Cout, void* stream) {
+  DAFK_REQUIRE(w_hwio && scale && wp && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, DAFK_ERR_BAD_ARG, "dafk_pack_conv_scaled: bad argument");
+  const int Cip = (Cin + 63) / 64 * 64, Cop = (Cout + 63) / 64 * 64;
+  const int64_t total = (int64_t)KH * KW * Cip * Cop;
+  pack_w_kernel<<<bw_grid(total, 256), 256, 0, as_stream(stream)>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, Cip, Cop, 0, scale);
+  return check_launch("dafk_pack_conv_scaled");
 }
 
 int dafk_pack_conv3x3(const float* w_hwio, void* wp, int Cin, int Cout, int for_dgrad, void* stream) {

@@ -263,6 +263,7 @@ class Conv2D:
         self._packed_nc = None
         self._packed_s2d = None
         self._packed_dg = None
+        self._folded = None          # ((kernel arena version, BN state version), wp, bias', scale)
 
     def params(self):
         return [self.kernel] + ([self.bias] if self.bias is not None else [])
@@ -344,6 +345,24 @@ class Conv2D:
                 self._packed_s2d = (ver, ops.pack_conv_nc(w2, 0, out=None if old is None else old[1]),
                                     ops.pack_conv_nc(w2, 1, out=None if old is None else old[2]), w2)
         return self._packed_s2d[1], self._packed_s2d[2]
+
+    def forward_folded(self, srcs, bn, code, out_dtype):
+        """predict pass: conv -> BatchNorm(moving statistics) -> [ReLU] as ONE tcgen05 kernel.  In the inference phase
+        the normalisation is a per-channel affine map: it is folded into the packed weights (w * gamma * rstd) and the
+        bias ((b - mean) * gamma * rstd + beta), the ReLU runs in the epilogue, the output is written once in its final
+        dtype.  Refreshed in place whenever the kernel or the moving statistics changed."""
+        key = (self.kernel.arena.version, bn.moving_mean.arena.version)
+        if self._folded is None or self._folded[0] != key:
+            old = self._folded
+            scale, bias2 = ops.bn_fold(bn.gamma.data, bn.beta.data, bn.moving_mean.data, bn.moving_var.data,
+                                       self.bias.data if self.bias is not None else None, bn.EPS,
+                                       out=None if old is None else (old[3], old[2]))
+            wp = ops.pack_conv_scaled(self.kernel.data, scale, out=None if old is None else old[1])
+            self._folded = (key, wp, bias2, scale)
+        _, wp, bias2, _ = self._folded
+        bs = [s.data if s.data.dtype == torch.bfloat16 else ops.cast(s.data, torch.bfloat16) for s in srcs]
+        return Var(ops.conv_tc_fwd(bs[0], bs[1] if len(bs) > 1 else None, wp, bias2, self.cout, self.k, self.k, self.stride,
+                                   self.pad, out_dtype, act=code))
 
     def _s2d_wide(self):
         return (4 * self.cin) % 64 == 0 and self.cout % 64 == 0
@@ -583,6 +602,7 @@ class BatchNorm:
         code = ACT[act]
         if ctx.training:
             mean, rstd = ops.bn_stats_finalize(x.data, self.EPS, self.MOMENTUM, self.moving_mean.data, self.moving_var.data)
+            self.moving_mean.arena.version += 1        # folded inference copies (Conv2D.forward_folded) are stale now
         else:
             mean, rstd = self.moving_mean.data, ops.bn_rstd_from_var(self.moving_var.data, self.EPS)
         y = Var(ops.bn_apply(x.data, mean, rstd, self.gamma.data, self.beta.data, code, out_dtype))
@@ -637,6 +657,21 @@ class Dense:
         if ACT[act] != ACT_NONE:
             return activation(ctx, y, act, alpha)
         return y
+
+
+FOLD_BN = True      # predict passes: fold BatchNorm (+ReLU) into the tensor-core convolution that feeds it
+
+
+def conv_bn(ctx, conv, bn, x, act=None, out_dtype=torch.float32):
+    """Conv2D -> BatchNormalization -> activation (models/unet.py:94-101, utils/model_utils.py:15-22,
+    model_components/segmentor.py:15-21).  Training phase / taped graphs: three kernels families (convolution,
+    statistics, apply).  Inference phase on the tensor-core path: one kernel (Conv2D.forward_folded)."""
+    srcs = list(x) if isinstance(x, (list, tuple)) else [x]
+    code = ACT[act]
+    if (FOLD_BN and USE_TC and not ctx.training and ctx.tape is None and code in (ACT_NONE, ACT_RELU)
+            and len(srcs) <= 2 and conv.stride == 1 and conv.tc_eligible(srcs)):
+        return conv.forward_folded(srcs, bn, code, out_dtype)
+    return bn(ctx, conv(ctx, x, out_dtype=feat_dtype()), act, out_dtype)
 
 
 # --------------------------------------------------------------------------------------------

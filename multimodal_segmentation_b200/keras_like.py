@@ -148,6 +148,7 @@ class Model:
             assert tuple(w.shape) == p.shape, (p.name, w.shape, p.shape)
             p.data.copy_(torch.from_numpy(np.ascontiguousarray(w)))
         self._scope.arena.version += 1
+        self._scope.state.version += 1          # BatchNorm moving statistics may have changed too
 
     def named_weights(self):
         return {p.name: p.numpy() for p in self.weight_list()}

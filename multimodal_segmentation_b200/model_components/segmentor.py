@@ -1,7 +1,5 @@
 """Segmentor (reference: model_components/segmentor.py:9-29): 2x [conv3x3(64, he_normal) -> BN -> ReLU]
 -> conv1x1(num_masks+1) softmax."""
-import torch
-
 from .. import engine as E
 from ..keras_like import BuildScope, Model
 
@@ -17,10 +15,8 @@ def build(conf):
     head = E.Conv2D(a, r, "seg_out", 64, conf.num_masks + 1, 1, 1, "same")
 
     def fwd(ctx, x):
-        l = c1(ctx, x, out_dtype=E.feat_dtype())
-        l = b1(ctx, l, "relu", E.feat_dtype())
-        l = c2(ctx, l, out_dtype=E.feat_dtype())
-        l = b2(ctx, l, "relu", E.feat_dtype())
+        l = E.conv_bn(ctx, c1, b1, x, "relu", E.feat_dtype())
+        l = E.conv_bn(ctx, c2, b2, l, "relu", E.feat_dtype())
         return E.softmax(ctx, head(ctx, l))
 
     shp = tuple(conf.anatomy_encoder.output_shape)

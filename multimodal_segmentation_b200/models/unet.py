@@ -5,8 +5,6 @@
 wide 3x3 convolutions run on tcgen05 with bf16 feature maps written directly by the BN-apply /
 pool / upsample kernels; the Concatenate is never materialised (two-source K loop).
 """
-import torch
-
 from .. import engine as E
 
 
@@ -34,11 +32,11 @@ class ConvBlock:
 
     def __call__(self, ctx, x, out_dtype=None):
         fd = E.feat_dtype()
-        l = self.c1(ctx, x, out_dtype=fd if self.n1 is not None else None)
-        l = self.n1(ctx, l, "relu", fd) if self.n1 is not None else E.activation(ctx, l, "relu")
-        l = self.c2(ctx, l, out_dtype=fd if self.n2 is not None else None)
         od = fd if out_dtype is None else out_dtype
-        return self.n2(ctx, l, "relu", od) if self.n2 is not None else E.activation(ctx, l, "relu")
+        l = E.conv_bn(ctx, self.c1, self.n1, x, "relu", fd) if self.n1 is not None else \
+            E.activation(ctx, self.c1(ctx, x), "relu")
+        return E.conv_bn(ctx, self.c2, self.n2, l, "relu", od) if self.n2 is not None else \
+            E.activation(ctx, self.c2(ctx, l), "relu")
 
 
 class UpsampleBlock:
@@ -54,8 +52,9 @@ class UpsampleBlock:
 
     def __call__(self, ctx, x):
         l = E.upsample2(ctx, x)
-        l = self.conv(ctx, l, out_dtype=E.feat_dtype() if self.norm is not None else None)
-        return self.norm(ctx, l, None, E.feat_dtype()) if self.norm is not None else l
+        if self.norm is None:
+            return self.conv(ctx, l)
+        return E.conv_bn(ctx, self.conv, self.norm, l, None, E.feat_dtype())
 
 
 class UNetDown:

@@ -463,7 +463,27 @@ def pack_conv(w_hwio, mode, pa=0, pb=0, out=None):
     return wp
 
 
-def conv_tc_fwd(x0, x1, wp, bias, Cout, KH, KW, stride, pad, out_dtype=torch.float32, row_off=0, out=None):
+def bn_fold(gamma, beta, moving_mean, moving_var, conv_bias, eps, out=None):
+    """inference-mode BatchNorm as a per-channel affine map folded into the producing convolution:
+    -> (scale [C], bias' [C]); ``out`` = (scale, bias') buffers to refresh in place"""
+    _chk(gamma, beta, moving_mean, moving_var, conv_bias)
+    C = gamma.numel()
+    scale, bias2 = out if out is not None else (f32(C, device=gamma.device), f32(C, device=gamma.device))
+    call("bn_fold", gamma, beta, moving_mean, moving_var, conv_bias, float(eps), scale, bias2, C, _S())
+    return scale, bias2
+
+
+def pack_conv_scaled(w_hwio, scale, out=None):
+    """forward operand [taps][Cout_pad][Cin_pad] of w * scale[Cout]"""
+    _chk(w_hwio, scale)
+    KH, KW, Cin, Cout = w_hwio.shape
+    cip, cop = (Cin + 63) // 64 * 64, (Cout + 63) // 64 * 64
+    wp = torch.empty((KH * KW, cop, cip), dtype=torch.bfloat16, device=w_hwio.device) if out is None else out
+    call("pack_conv_scaled", w_hwio, scale, wp, KH, KW, Cin, Cout, _S())
+    return wp
+
+
+def conv_tc_fwd(x0, x1, wp, bias, Cout, KH, KW, stride, pad, out_dtype=torch.float32, row_off=0, out=None, act=ACT_NONE):
     """general tcgen05 convolution.  ``out`` may be a strided NHWC view (e.g. dx[:, pa::2, pb::2, :]); its
     spatial extent defines the logical output size."""
     _chk(x0, x1, wp, bias)
@@ -478,8 +498,9 @@ def conv_tc_fwd(x0, x1, wp, bias, Cout, KH, KW, stride, pad, out_dtype=torch.flo
     fl = 2.0 * N * Ho * Wo * Cout * KH * KW * (C0 + C1)
     nb = 2.0 * x0.numel() + (0 if x1 is None else 2.0 * x1.numel()) + N * Ho * Wo * Cout * out.element_size()
     instrument.timed("conv_tc_fwd+dgrad (tcgen05)", fl, nb,
-                     lambda: call("conv_tc_fwd", x0, C0, x1, C1, wp, wp.shape[1], row_off, bias, out, _dt(out), N, H, W,
-                                  Cout, KH, KW, stride, pad, Ho, Wo, out.stride(0), out.stride(1), out.stride(2), _S()),
+                     lambda: call("conv_tc_fwd_act", x0, C0, x1, C1, wp, wp.shape[1], row_off, bias, out, _dt(out), N, H, W,
+                                  Cout, KH, KW, stride, pad, Ho, Wo, out.stride(0), out.stride(1), out.stride(2), int(act),
+                                  _S()),
                      tag=(N, H, W, C0 + C1, Cout, KH, stride, str(out.dtype)[6:], Ho))
     return out
 
