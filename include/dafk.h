@@ -220,6 +220,9 @@ int64_t dafk_conv_nc_packed_elems(int Cin_k, int Cout_k, int KH, int KW);
  * pad = K-1-pad_layer. */
 int dafk_pack_conv_nc(const float* w_hwio, void* wp, int KH, int KW, int Cin, int Cout, int mode,
                       void* stream);
+/* forward operand of w * scale[Cout] (inference-mode BatchNorm folded into a narrow layer, see dafk_bn_fold) */
+int dafk_pack_conv_nc_scaled(const float* w_hwio, const float* scale, void* wp, int KH, int KW, int Cin, int Cout,
+                             void* stream);
 /* y[N,Ho,Wo,Cout] = act(conv(x, w) + bias), Ho = H + 2*pad - KH + 1; y is f32 or bf16 */
 int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias, void* y, int y_dt, int N,
                      int H, int W, int Cin, int Cout, int KH, int KW, int pad, int act, float alpha,

@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
 //   mode 1 (data gradient):  Wp[e][n][c] = w[KH-1-r][KW-1-q][n][cg*8+c]       (Cin_k = Cout, Cout_k = Cin)
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_nc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int KH, int KW, int Cin,
-                               int Cout, int mode, int E, int Npad) {
+                               int Cout, int mode, int E, int Npad, const float* __restrict__ scale) {
   const int Ck = mode == 0 ? Cin : Cout;    // the kernel's reduction channels
   const int Nk = mode == 0 ? Cout : Cin;    // the kernel's output channels
   const int CG = (Ck + 7) / 8;
@@ -585,7 +585,7 @@ __global__ void pack_nc_kernel(const float* __restrict__ w, __nv_bfloat16* __res
       const int cg = t / KH;
       const int ck = cg * 8 + c;
       if (ck < Ck && nn < Nk) {
-        if (mode == 0) v = w[(((int64_t)r * KW + q) * Cin + ck) * Cout + nn];
+        if (mode == 0) v = w[(((int64_t)r * KW + q) * Cin + ck) * Cout + nn] * (scale ? scale[nn] : 1.f);   // folded BatchNorm
         else v = w[(((int64_t)(KH - 1 - r) * KW + (KW - 1 - q)) * Cin + nn) * Cout + ck];
       }
     }
@@ -737,8 +737,20 @@ int dafk_pack_conv_nc(const float* w_hwio, void* wp, int KH, int KW, int Cin, in
   const int E = round_up(CG * KH * KW, 2), Npad = round_up(Nk, 16);
   const int total = E * Npad * 8;
   pack_nc_kernel<<<bw_grid(total, 256), 256, 0, as_stream(stream)>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, mode,
-                                                                     E, Npad);
+                                                                     E, Npad, nullptr);
   return check_launch("dafk_pack_conv_nc");
+}
+
+int dafk_pack_conv_nc_scaled(const float* w_hwio, const float* scale, void* wp, int KH, int KW, int Cin, int Cout,
+                             void* stream) {
+  DAFK_REQUIRE(w_hwio && scale && wp && KH > 0 && KW > 0 && Cin > 0 && Cout > 0, DAFK_ERR_BAD_ARG,
+               "dafk_pack_conv_nc_scaled: bad argument");
+  const int CG = (Cin + 7) / 8;
+  const int E = round_up(CG * KH * KW, 2), Npad = round_up(Cout, 16);
+  const int total = E * Npad * 8;
+  pack_nc_kernel<<<bw_grid(total, 256), 256, 0, as_stream(stream)>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, 0, E,
+                                                                     Npad, scale);
+  return check_launch("dafk_pack_conv_nc_scaled");
 }
 
 int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias, void* y, int y_dt, int N, int H,

@@ -346,7 +346,7 @@ class Conv2D:
                                     ops.pack_conv_nc(w2, 1, out=None if old is None else old[2]), w2)
         return self._packed_s2d[1], self._packed_s2d[2]
 
-    def forward_folded(self, srcs, bn, code, out_dtype):
+    def forward_folded(self, srcs, bn, code, out_dtype, narrow=False):
         """predict pass: conv -> BatchNorm(moving statistics) -> [ReLU] as ONE tcgen05 kernel.  In the inference phase
         the normalisation is a per-channel affine map: it is folded into the packed weights (w * gamma * rstd) and the
         bias ((b - mean) * gamma * rstd + beta), the ReLU runs in the epilogue, the output is written once in its final
@@ -357,9 +357,12 @@ class Conv2D:
             scale, bias2 = ops.bn_fold(bn.gamma.data, bn.beta.data, bn.moving_mean.data, bn.moving_var.data,
                                        self.bias.data if self.bias is not None else None, bn.EPS,
                                        out=None if old is None else (old[3], old[2]))
-            wp = ops.pack_conv_scaled(self.kernel.data, scale, out=None if old is None else old[1])
+            pack = ops.pack_conv_nc_scaled if narrow else ops.pack_conv_scaled      # raster-strip / swizzled operand
+            wp = pack(self.kernel.data, scale, out=None if old is None else old[1])
             self._folded = (key, wp, bias2, scale)
         _, wp, bias2, _ = self._folded
+        if narrow:
+            return Var(ops.conv_nc_fwd(srcs[0].data, wp, bias2, self.cout, self.k, self.k, self.pad, code, 0.0, out_dtype))
         bs = [s.data if s.data.dtype == torch.bfloat16 else ops.cast(s.data, torch.bfloat16) for s in srcs]
         return Var(ops.conv_tc_fwd(bs[0], bs[1] if len(bs) > 1 else None, wp, bias2, self.cout, self.k, self.k, self.stride,
                                    self.pad, out_dtype, act=code))
@@ -671,6 +674,10 @@ def conv_bn(ctx, conv, bn, x, act=None, out_dtype=torch.float32):
     if (FOLD_BN and USE_TC and not ctx.training and ctx.tape is None and code in (ACT_NONE, ACT_RELU)
             and len(srcs) <= 2 and conv.stride == 1 and conv.tc_eligible(srcs)):
         return conv.forward_folded(srcs, bn, code, out_dtype)
+    if (FOLD_BN and USE_TC and not ctx.training and ctx.tape is None and code in (ACT_NONE, ACT_RELU) and len(srcs) == 1
+            and conv.stride == 1 and not conv.tc_eligible(srcs)
+            and ops.nc_supported(conv.cin, conv.cout, conv.k, conv.k, srcs[0].shape[2], conv.pad, 0)):
+        return conv.forward_folded(srcs, bn, code, out_dtype, narrow=True)      # first layers: 1 -> 64, 8 -> 64
     return bn(ctx, conv(ctx, x, out_dtype=feat_dtype()), act, out_dtype)
 
 

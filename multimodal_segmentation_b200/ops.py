@@ -576,6 +576,15 @@ def pack_conv_nc(w_hwio, mode, out=None):
     return wp
 
 
+def pack_conv_nc_scaled(w_hwio, scale, out=None):
+    _chk(w_hwio, scale)
+    KH, KW, Cin, Cout = w_hwio.shape
+    n = _lib.lib().fn["dafk_conv_nc_packed_elems"](Cin, Cout, KH, KW)
+    wp = torch.empty(n, dtype=torch.bfloat16, device=w_hwio.device) if out is None else out
+    call("pack_conv_nc_scaled", w_hwio, scale, wp, KH, KW, Cin, Cout, _S())
+    return wp
+
+
 def conv_nc_fwd(x, wp, bias, Cout, KH, KW, pad, act=ACT_NONE, alpha=0.0, out_dtype=torch.float32):
     """y = act(conv(x, w) + bias), stride 1; x f32/bf16 NHWC; wp from pack_conv_nc"""
     _chk(x, wp, bias)
