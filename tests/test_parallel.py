@@ -194,3 +194,21 @@ def test_two_rank_step_equals_averaged_shard_gradients():
     upd_ref, upd_dp = w_ref - w_before, w_rank0 - w_before
     close = np.abs(upd_ref - upd_dp) <= 1e-2 * np.abs(upd_ref).max()
     assert close.mean() > 0.999, close.mean()
+
+
+def test_reference_arm_line_contract():
+    """bench.py --impl reference on rank 0: one JSON line with the keys the driver reads (the CPU restatement of the
+    reference graph on a bounded sample; a tiny geometry here so that the CPU suite stays fast)"""
+    import json
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
+                          "--warmup", "0", "--size", "64", "--cpu-batch", "1"], env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().split("\n") if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "slices/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["metric"].startswith("DAFNet train slices/s") and "workload" in d["config"]
