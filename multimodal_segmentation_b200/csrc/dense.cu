@@ -82,6 +82,49 @@ __global__ void __launch_bounds__(DT) dense_fwd_kernel(const float* __restrict__
   }
 }
 
+// Few outputs (N <= 4: the discriminators' Dense(1) over 270 848 features, models/discriminator.py:41): the op is a
+// handful of long dot products per sample, bound by reading x once.  grid = (k-slabs, B); every thread streams 128-bit
+// pieces of its sample's row and of the weight slab (which stays in L2 across the samples), block-reduces N partial sums
+// and adds them to the bias-initialised output with one atomic per output per CTA.
+template <int N>
+__global__ void __launch_bounds__(DT) dense_fwd_smalln_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              float* __restrict__ y, int64_t K, int64_t k_per_cta) {
+  __shared__ float red[N][DT / 32];
+  const int b = blockIdx.y;
+  const int64_t kbeg = (int64_t)blockIdx.x * k_per_cta;
+  const int64_t kend = min(K, kbeg + k_per_cta);
+  const float* xr = x + (int64_t)b * K;
+  float acc[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) acc[n] = 0.f;
+  for (int64_t k = kbeg + 4 * (int64_t)threadIdx.x; k < kend; k += 4 * DT) {      // K % 4 == 0, slabs multiples of 4
+    const float4 xv = ldg_stream4(xr + k);
+    const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (N == 1) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
+      acc[0] = fmaf(xs4[0], wv.x, fmaf(xs4[1], wv.y, fmaf(xs4[2], wv.z, fmaf(xs4[3], wv.w, acc[0]))));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc[n] = fmaf(xs4[j], __ldg(w + (k + j) * N + n), acc[n]);
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const float v = warp_sum(acc[n]);
+    if (lane == 0) red[n][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < DT / 32; ++i) t += red[threadIdx.x][i];
+    atomicAdd(y + (int64_t)b * N + threadIdx.x, t);
+  }
+}
+
 // grid = (ceil(K/DT), ceil(B/MAXB)); dynamic smem: MAXB*N floats
 __global__ void __launch_bounds__(DT) dense_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                             float* __restrict__ dx, int B, int64_t K, int N) {
@@ -185,6 +228,20 @@ int dafk_dense_fwd(const float* x, const float* w, const float* bias, float* y, 
   dense_init_kernel<<<(B * Nout + 255) / 256, 256, 0, s>>>(y, bias, B, Nout);
   int rc = check_launch("dafk_dense_fwd(init)");
   if (rc) return rc;
+  if (Nout <= 4 && K % 4 == 0 && DAFK_ALIGNED16(x) && DAFK_ALIGNED16(w)) {
+    // few long dot products per sample: x-stationary stream (see dense_fwd_smalln_kernel)
+    int64_t per = (K / 4 + (4 * kNumSMs / B > 0 ? 4 * kNumSMs / B : 1) - 1) / (4 * kNumSMs / B > 0 ? 4 * kNumSMs / B : 1);
+    if (per < DT) per = DT;
+    const int64_t k_per = per * 4;
+    dim3 g2((unsigned)((K + k_per - 1) / k_per), (unsigned)B);
+    switch (Nout) {
+      case 1: dense_fwd_smalln_kernel<1><<<g2, DT, 0, s>>>(x, w, y, K, k_per); break;
+      case 2: dense_fwd_smalln_kernel<2><<<g2, DT, 0, s>>>(x, w, y, K, k_per); break;
+      case 3: dense_fwd_smalln_kernel<3><<<g2, DT, 0, s>>>(x, w, y, K, k_per); break;
+      default: dense_fwd_smalln_kernel<4><<<g2, DT, 0, s>>>(x, w, y, K, k_per); break;
+    }
+    return check_launch("dafk_dense_fwd");
+  }
   // k-slabs: about two CTAs per SM, each slab a multiple of the chunk size
   int64_t slabs = (K + KC - 1) / KC;
   int64_t want = 2 * kNumSMs;
