@@ -14,6 +14,7 @@ CASES = {
     "film8x8": (B, 224, 224, 8, 8, 3, 1, torch.float32),
     "film8x8_bf16": (B, 224, 224, 8, 8, 3, 1, torch.bfloat16),
     "seg8x64": (B, 224, 224, 8, 64, 3, 1, torch.float32),
+    "seg8x64_bf16": (B, 224, 224, 8, 64, 3, 1, torch.bfloat16),
     "unet1x64": (B, 224, 224, 1, 64, 3, 1, torch.float32),
     "loc16x20": (B, 224, 224, 16, 20, 5, 0, torch.float32),
     "loc20x20a": (B, 110, 110, 20, 20, 5, 0, torch.float32),

@@ -119,6 +119,40 @@ def test_conv_nc_vs_fp32_oracle_tolerance(ops):
     assert rel_l2(cpu(y), yr) < 1e-2
 
 
+# ------------------------------------------------------------------ bf16 input with 8 channels: rows staged by cp.async.bulk
+BULK_CASES = [
+    # N, H, W, Cin, Cout, k, pad
+    (2, 16, 16, 8, 8, 3, 1),
+    (3, 37, 45, 8, 8, 3, 1),        # ragged strips / tiles, W not a multiple of 8
+    (2, 24, 40, 8, 64, 3, 1),
+    (2, 20, 28, 8, 1, 1, 0),
+    (2, 30, 30, 8, 20, 5, 0),
+    (2, 30, 34, 8, 5, 5, 2),
+    (1, 224, 224, 8, 8, 3, 1),
+    (64, 160, 48, 8, 8, 3, 1),      # > 4 strips per CTA: every stage is reused, rows outside the image re-zeroed
+]
+
+
+@pytest.mark.parametrize("case", BULK_CASES)
+def test_conv_nc_bulk_rows_forward(ops, case, monkeypatch):
+    from multimodal_segmentation_b200._lib import ACT_LRELU
+    N, H, W, Cin, Cout, k, pad = case
+    r, x, w, b = _mk(case, sum(case) + 5)
+    yr = _ref_conv(x, w, b, pad).numpy()
+    wp = ops.pack_conv_nc(gpu(w), 0)
+    xg = gpu(x, torch.bfloat16)
+    monkeypatch.setenv("DAFK_NC_BULK", "0")
+    y0 = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad)
+    a0 = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad, ACT_LRELU, 0.3, torch.bfloat16)
+    monkeypatch.setenv("DAFK_NC_BULK", "1")
+    for _ in range(2):              # second launch: nothing may depend on leftovers of the first
+        y1 = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad)
+        a1 = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad, ACT_LRELU, 0.3, torch.bfloat16)
+        torch.cuda.synchronize()
+        assert rel_l2(cpu(y1), yr) < 1e-4
+        assert torch.equal(y0, y1) and torch.equal(a0, a1)      # same operands, same MMA order: bit-identical
+
+
 # ------------------------------------------------------------------ stride-2 valid layers through space-to-depth
 S2_CASES = [
     # N, H, W, Cin, Cout, k     (models/discriminator.py:24 first layer; model_components/modality_encoder.py:36-42)
