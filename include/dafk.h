@@ -108,6 +108,16 @@ int dafk_film_act_add_bwd(const float* dy, const float* x, const float* gamma, c
                           float* dgamma, float* dbeta, double* ws, int B, int64_t HW, int C, int act, float alpha,
                           void* stream);
 
+/* bf16-storage variants (x, res, y, dy, dx are bf16; gamma, beta and their gradients fp32; C % 8 == 0, for the
+ * backward C a power of two): used when the FiLM decoder keeps its activations in bf16 (engine.DEC_BF16). */
+int dafk_film_act_add_fwd_bf16(const void* x, const float* gamma, const float* beta, const void* res, void* y, int B,
+                               int64_t HW, int C, int act, float alpha, void* stream);
+int dafk_film_act_add_bwd_bf16(const void* dy, const void* x, const float* gamma, const float* beta, void* dx,
+                               float* dgamma, float* dbeta, double* ws, int B, int64_t HW, int C, int act, float alpha,
+                               void* stream);
+/* dx = dy * act'(y), y = the activation's OUTPUT; dy, y, dx bf16; n % 8 == 0 */
+int dafk_act_bwd_bf16io(const void* dy, const void* y, void* dx, int64_t n, int act, float alpha, void* stream);
+
 /* ------------------------------------------------------------------ Maximum
  * model_components/anatomy_fuser.py:33  keras Maximum = tf.maximum; gradient goes
  * entirely to the first input where a >= b (tie rule of tf.maximum). */

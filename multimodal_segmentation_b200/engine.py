@@ -14,6 +14,7 @@ Design (B200-first, not a Keras port):
     pooling, upsampling) writes bf16 directly, gradients of bf16 maps are bf16.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -30,7 +31,17 @@ USE_TC = True
 # (what mixed-precision training does everywhere); tests/test_models_gpu.py bounds the effect with both settings.
 RAW_BF16 = True
 
+# Keep the FiLM decoder's 8-channel activations (and their gradients) in bf16: halves the HBM bytes of its convolutions and
+# element-wise passes and lets the 8 -> 8 convolutions stage rows with cp.async.bulk (csrc/conv_nc.cu, DAFK_NC_BULK=1).
+# Opt-in (DAFK_DEC_BF16=1) until its effect on the reconstruction losses has been measured on the full step.
+DEC_BF16 = os.environ.get("DAFK_DEC_BF16", "0") == "1"
+
 ACT = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU, "tanh": ACT_TANH}
+
+
+def dec_dtype():
+    """storage dtype of the FiLM decoder's feature maps"""
+    return torch.bfloat16 if (USE_TC and RAW_BF16 and DEC_BF16) else torch.float32
 
 
 def feat_dtype():
@@ -264,6 +275,7 @@ class Conv2D:
         self._packed_s2d = None
         self._packed_dg = None
         self._folded = None          # ((kernel arena version, BN state version), wp, bias', scale)
+        self.bf16_grad = False       # raster-strip path: take / hand on the output gradient in bf16 (FiLM decoder)
 
     def params(self):
         return [self.kernel] + ([self.bias] if self.bias is not None else [])
@@ -464,9 +476,10 @@ class Conv2D:
             f32srcs = [s if s.data.dtype == torch.float32 else _cast_var(ctx, s, torch.float32) for s in srcs]
             xin = f32srcs[0] if len(f32srcs) == 1 else concat(ctx, f32srcs)
         bias = self.bias.data if self.bias is not None else None
+        bf16_bw = self.bf16_grad and nc_f and nc_w and od == torch.bfloat16
         if nc_f:
             y = Var(ops.conv_nc_fwd(xin.data, self.packed_nc()[0], bias, self.cout, self.k, self.k, self.pad, code, alpha, od),
-                    grad_dtype=torch.float32)
+                    grad_dtype=torch.bfloat16 if bf16_bw else torch.float32)
         else:
             y = Var(ops.conv2d_fwd(xin.data, self.kernel.data, bias, self.stride, self.pad, code, alpha))
         if ctx.rec(xin, self.kernel):
@@ -478,10 +491,14 @@ class Conv2D:
                 y.grad = None
                 if g is None:
                     return
-                if g.dtype != torch.float32:
-                    g = ops.cast(g, torch.float32)
-                if code != ACT_NONE:
-                    g = ops.act_bwd(g, y.data, code, alpha)
+                if bf16_bw and g.dtype == torch.bfloat16 and g.numel() % 8 == 0:
+                    if code != ACT_NONE:                  # bf16 gradient x bf16 activation output, no fp32 intermediate
+                        g = ops.act_bwd_bf16io(g, y.data, code, alpha)
+                else:
+                    if g.dtype != torch.float32:
+                        g = ops.cast(g, torch.float32)
+                    if code != ACT_NONE:
+                        g = ops.act_bwd(g, y.data, code, alpha)
                 if self.kernel.requires_grad:
                     db = self.bias.grad if (self.bias is not None and self.bias.requires_grad) else None
                     if nc_w:

@@ -1,5 +1,7 @@
 """Decoder (reference: model_components/decoder.py:12-81): FiLM or SPADE conditioning of the anatomy
 on the modality factor z, followed by Conv2D(1, 1, tanh, glorot_normal)."""
+import torch
+
 from .. import engine as E
 from ..keras_like import BuildScope, Model
 from ..layers.film import FiLM
@@ -16,17 +18,18 @@ class _FilmLayer:
         self.g = E.Dense(a, r, name + "_gamma", num_z, 8)
         self.b = E.Dense(a, r, name + "_beta", num_z, 8)
         self.film = FiLM()
+        self.c1.bf16_grad = self.c2.bf16_grad = True      # only takes effect with engine.DEC_BF16
 
     def layers(self):
         return [self.c1, self.c2, self.g, self.b]
 
     def __call__(self, ctx, x, z):
-        l1 = self.c1(ctx, x, "lrelu", 0.3)
-        l2 = self.c2(ctx, l1)
+        l1 = self.c1(ctx, x, "lrelu", 0.3, out_dtype=E.dec_dtype())
+        l2 = self.c2(ctx, l1, out_dtype=E.dec_dtype())
         gamma = self.g(ctx, z, "lrelu", 0.3)
         beta = self.b(ctx, z, "lrelu", 0.3)
-        if (l2.data.dtype == l1.data.dtype == gamma.data.dtype and l2.data.dtype.is_floating_point
-                and l2.data.element_size() == 4):
+        if (l2.data.dtype == l1.data.dtype and gamma.data.dtype == beta.data.dtype == torch.float32
+                and l2.data.dtype in (torch.float32, torch.bfloat16)):
             # FiLM -> LeakyReLU -> Add as one pass over the feature map (same arithmetic, same order)
             return E.film_act_add(ctx, l2, gamma, beta, l1, "lrelu", 0.3)
         l2 = self.film(ctx, [l2, gamma, beta])
@@ -45,8 +48,10 @@ def build(conf):
         out = E.Conv2D(a, r, "dec_out", 8, 1, 1, 1, "same", "glorot_normal")
         layers = [c0] + [l for f in fl for l in f.layers()] + [out]
 
+        c0.bf16_grad = True
+
         def fwd(ctx, anatomy, z):
-            l = c0(ctx, anatomy, "lrelu", 0.3)
+            l = c0(ctx, anatomy, "lrelu", 0.3, out_dtype=E.dec_dtype())
             for f in fl:
                 l = f(ctx, l, z)
             return out(ctx, l, "tanh")

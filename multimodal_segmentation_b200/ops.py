@@ -84,6 +84,15 @@ def act_bwd_bf16(dy, y, act, alpha=0.0):
     return dx
 
 
+def act_bwd_bf16io(dy, y, act, alpha=0.0):
+    """act'(y) * dy with bf16 gradient and bf16 activation output"""
+    _chk(dy, y)
+    assert dy.dtype == y.dtype == torch.bfloat16
+    dx = torch.empty_like(dy)
+    call("act_bwd_bf16io", dy, y, dx, y.numel(), act, float(alpha), _S())
+    return dx
+
+
 def add(a, b, out=None):
     _chk(a, b)
     out = torch.empty_like(a) if out is None else out
@@ -188,11 +197,13 @@ def film_bwd(dy, x, gamma):
 
 
 def film_act_add_fwd(x, gamma, beta, res, act, alpha=0.0):
-    """res + act(x*gamma + beta) in one pass (decoder.py:50-54)"""
+    """res + act(x*gamma + beta) in one pass (decoder.py:50-54); x / res f32, or both bf16 (gamma, beta stay f32)"""
     _chk(x, gamma, beta, res)
     B, C = x.shape[0], x.shape[-1]
     y = torch.empty_like(x)
-    call("film_act_add_fwd", x, gamma, beta, res, y, B, x.numel() // (B * C), C, act, float(alpha), _S())
+    name = "film_act_add_fwd_bf16" if x.dtype == torch.bfloat16 else "film_act_add_fwd"
+    assert res.dtype == x.dtype and gamma.dtype == beta.dtype == torch.float32
+    call(name, x, gamma, beta, res, y, B, x.numel() // (B * C), C, act, float(alpha), _S())
     return y
 
 
@@ -203,7 +214,9 @@ def film_act_add_bwd(dy, x, gamma, beta, act, alpha=0.0):
     dg = f32(B, C)
     db = f32(B, C)
     ws = torch.empty(B * C * 2, dtype=torch.float64, device=x.device)
-    call("film_act_add_bwd", dy, x, gamma, beta, dx, dg, db, ws, B, x.numel() // (B * C), C, act, float(alpha), _S())
+    name = "film_act_add_bwd_bf16" if x.dtype == torch.bfloat16 else "film_act_add_bwd"
+    assert dy.dtype == x.dtype and gamma.dtype == beta.dtype == torch.float32
+    call(name, dy, x, gamma, beta, dx, dg, db, ws, B, x.numel() // (B * C), C, act, float(alpha), _S())
     return dx, dg, db
 
 
