@@ -172,7 +172,7 @@ def run_b200(args):
     os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from multimodal_segmentation_b200 import _lib, engine as E, ops
+    from multimodal_segmentation_b200 import _lib, engine as E
     from multimodal_segmentation_b200 import parallel
     from multimodal_segmentation_b200.models.dafnet import DAFNet
     from multimodal_segmentation_b200.model_executors.dafnet_executor import DAFNetExecutor

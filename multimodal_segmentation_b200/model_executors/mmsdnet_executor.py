@@ -12,8 +12,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from ..utils import data_utils
-from .dafnet_executor import DAFNetExecutor, _cat_rows
+from .dafnet_executor import DAFNetExecutor
 
 log = logging.getLogger("mmsdnet_executor")
 

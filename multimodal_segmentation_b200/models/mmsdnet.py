@@ -6,11 +6,9 @@ import os
 
 import numpy as np
 
-from .. import costs
 from .. import engine as E
 from ..keras_like import BuildScope
 from ..model_components import anatomy_encoder, anatomy_fuser, decoder, modality_encoder, segmentor
-from ..utils.sdnet_utils import make_trainable
 from .basenet import BaseNet
 from .discriminator import Discriminator
 from .trainers import DiscriminatorTrainer, Trainer
