@@ -181,14 +181,21 @@ constexpr int NC_MAX_STAGES = 4;
 // image are zeroed by the warp), the halo columns keep the zeros of the one-time setup, and the freed warps 4-7 become a
 // second epilogue group: group A (warps 9-12) drains TMEM buffer 0, group B (warps 4-7) buffer 1.
 // BULK runs 12 warps (three per scheduler, 168 registers each): 0 = copies, 1 = MMA issuer, 2-3 idle, 4-11 epilogue.
+//
+// MODE 2 (opt-in, DAFK_NC_L12=1): the default role layout has 13 warps, i.e. four on one scheduler, which caps every
+// thread at 128 registers (ptxas spills 16 B).  Twelve warps -- 7 producers, MMA issuer, 4 epilogue -- get 168:
+// the same code then needs 148 registers and no stack (to be timed in round 2).
 constexpr int NC_BULK_THREADS = 384;
+constexpr int NC_MODE_DEFAULT = 0, NC_MODE_BULK = 1, NC_MODE_L12 = 2;
 
-template <typename TX, bool BULK>
-__global__ void __launch_bounds__(BULK ? NC_BULK_THREADS : NC_FWD_THREADS, 1)
+template <typename TX, int MODE>
+__global__ void __launch_bounds__(MODE == NC_MODE_DEFAULT ? NC_FWD_THREADS : NC_BULK_THREADS, 1)
 conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __restrict__ wp,
                    const float* __restrict__ bias, void* __restrict__ y) {
-  constexpr int THREADS = BULK ? NC_BULK_THREADS : NC_FWD_THREADS;
-  constexpr int MMA_WARP = BULK ? 1 : NC_MMA_WARP;
+  constexpr bool BULK = MODE == NC_MODE_BULK;
+  constexpr int THREADS = MODE == NC_MODE_DEFAULT ? NC_FWD_THREADS : NC_BULK_THREADS;
+  constexpr int PROD = MODE == NC_MODE_L12 ? 224 : NC_PROD;                 // staging threads (not BULK)
+  constexpr int MMA_WARP = BULK ? 1 : PROD / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int w_bytes = p.E * p.Npad * 16;
@@ -227,7 +234,7 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
     s_descB[j] = make_smem_desc_ns(smem_u32(s_w) + (uint32_t)(2 * j * p.Npad * 16), (uint32_t)p.Npad * 16, 128);
   }
   if (tid == 0) {
-    for (int i = 0; i < p.S; ++i) { mbar_init(full + i, BULK ? 1 : NC_PROD); mbar_init(empty + i, 1); }
+    for (int i = 0; i < p.S; ++i) { mbar_init(full + i, BULK ? 1 : PROD); mbar_init(empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 128); }
     fence_barrier_init();
   }
@@ -275,7 +282,7 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
         __syncwarp();
       }
     }
-  } else if (!BULK && warp < NC_MMA_WARP) {
+  } else if (!BULK && warp < MMA_WARP) {
     // ===================== producers =====================
     float dummy[8];
     int it = 0;
@@ -287,7 +294,7 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
       mbar_wait(empty + st, ph ^ 1u);
       if (!(p.dbg & 4))
       nc_stage_rows<TX, false, NC_U_FWD>(x, s_x + (size_t)st * st_bytes, p.plane, n, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P,
-                                 p.pad, tid, NC_PROD, dummy);
+                                 p.pad, tid, PROD, dummy);
       fence_proxy_async();
       mbar_arrive(full + st);
     }
@@ -351,7 +358,7 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
         const int gt = min(p.G, tiles_here - t0);
         const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * 256);
         // TMEM loads are issued EB tiles ahead of their use (one wait per batch instead of one per tile)
-        constexpr int EB = 4;
+        constexpr int EB = 4;   // MODE 2: 148 registers, no spills; EB = 6 / 8 spill even at 168
         for (int tb = 0; tb < gt; tb += EB) {
           for (int c0 = 0; c0 < p.Cout; c0 += 8) {
             uint32_t v[EB][8];
@@ -830,20 +837,32 @@ int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias,
   // both kernels in one process.  Measured at 32 x 224^2: 8 -> 8 37.1 -> 24.9 us, 8 -> 64 105 -> 123 us (slower).
   int bulk_ok = 0;
   { const char* e = getenv("DAFK_NC_BULK"); bulk_ok = e ? atoi(e) : 0; }
-  if (x_dt == DAFK_F32) {
-    rc = nc_set_smem(conv_nc_fwd_kernel<float, false>, smem, "dafk_conv_nc_fwd");
+  int l12 = 0;
+  { const char* e = getenv("DAFK_NC_L12"); l12 = e ? atoi(e) : 0; }
+  if (l12 && x_dt == DAFK_F32) {
+    rc = nc_set_smem(conv_nc_fwd_kernel<float, NC_MODE_L12>, smem, "dafk_conv_nc_fwd");
     if (rc) return rc;
-    conv_nc_fwd_kernel<float, false><<<grid, NC_FWD_THREADS, smem, s>>>(p, (const float*)x, (const __nv_bfloat16*)wp, bias, y);
+    conv_nc_fwd_kernel<float, NC_MODE_L12><<<grid, NC_BULK_THREADS, smem, s>>>(p, (const float*)x, (const __nv_bfloat16*)wp,
+                                                                              bias, y);
+  } else if (l12 && !(bulk_ok && Cin == 8)) {
+    rc = nc_set_smem(conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_L12>, smem, "dafk_conv_nc_fwd");
+    if (rc) return rc;
+    conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_L12><<<grid, NC_BULK_THREADS, smem, s>>>(p, (const __nv_bfloat16*)x,
+                                                                                      (const __nv_bfloat16*)wp, bias, y);
+  } else if (x_dt == DAFK_F32) {
+    rc = nc_set_smem(conv_nc_fwd_kernel<float, NC_MODE_DEFAULT>, smem, "dafk_conv_nc_fwd");
+    if (rc) return rc;
+    conv_nc_fwd_kernel<float, NC_MODE_DEFAULT><<<grid, NC_FWD_THREADS, smem, s>>>(p, (const float*)x, (const __nv_bfloat16*)wp, bias, y);
   } else if (bulk_ok && Cin == 8) {
     // one pixel = 16 B = one raster position: rows are staged by the TMA engine, two epilogue groups
-    rc = nc_set_smem(conv_nc_fwd_kernel<__nv_bfloat16, true>, smem, "dafk_conv_nc_fwd");
+    rc = nc_set_smem(conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_BULK>, smem, "dafk_conv_nc_fwd");
     if (rc) return rc;
-    conv_nc_fwd_kernel<__nv_bfloat16, true><<<grid, NC_BULK_THREADS, smem, s>>>(p, (const __nv_bfloat16*)x,
+    conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_BULK><<<grid, NC_BULK_THREADS, smem, s>>>(p, (const __nv_bfloat16*)x,
                                                                               (const __nv_bfloat16*)wp, bias, y);
   } else {
-    rc = nc_set_smem(conv_nc_fwd_kernel<__nv_bfloat16, false>, smem, "dafk_conv_nc_fwd");
+    rc = nc_set_smem(conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_DEFAULT>, smem, "dafk_conv_nc_fwd");
     if (rc) return rc;
-    conv_nc_fwd_kernel<__nv_bfloat16, false><<<grid, NC_FWD_THREADS, smem, s>>>(p, (const __nv_bfloat16*)x,
+    conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_DEFAULT><<<grid, NC_FWD_THREADS, smem, s>>>(p, (const __nv_bfloat16*)x,
                                                                                (const __nv_bfloat16*)wp, bias, y);
   }
   return check_launch("dafk_conv_nc_fwd");

@@ -153,6 +153,24 @@ def test_conv_nc_bulk_rows_forward(ops, case, monkeypatch):
         assert torch.equal(y0, y1) and torch.equal(a0, a1)      # same operands, same MMA order: bit-identical
 
 
+@pytest.mark.skipif(__import__("os").environ.get("DAFK_TEST_EXPERIMENTAL") != "1",
+                    reason="DAFK_NC_L12 role layout: compiled, not yet run on a GPU (no GPU minutes left in round 1)")
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("xdt", ["f32", "bf16"])
+def test_conv_nc_twelve_warp_layout(ops, case, xdt, monkeypatch):
+    """7 producer warps + MMA issuer + 4 epilogue warps (168-register budget) must give the default kernel's bits"""
+    N, H, W, Cin, Cout, k, pad = case
+    r, x, w, b = _mk(case, sum(case) + 7)
+    wp = ops.pack_conv_nc(gpu(w), 0)
+    xg = gpu(x, torch.float32 if xdt == "f32" else torch.bfloat16)
+    monkeypatch.setenv("DAFK_NC_L12", "0")
+    y0 = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad)
+    monkeypatch.setenv("DAFK_NC_L12", "1")
+    y1 = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad)
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1)
+
+
 # ------------------------------------------------------------------ stride-2 valid layers through space-to-depth
 S2_CASES = [
     # N, H, W, Cin, Cout, k     (models/discriminator.py:24 first layer; model_components/modality_encoder.py:36-42)
