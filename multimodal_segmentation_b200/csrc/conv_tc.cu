@@ -453,6 +453,206 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant of the haloed-tile kernel (opt-in, DAFK_CONV_HALO2=1; resident weights, one output-channel block).
+// A tcgen05.mma with both operands in shared memory is bound by the 128 B/clk shared-memory read port when N is small:
+// (A 4 KB + B N*32 B) per K=16 step = 48 cycles at N=64, 64 at N=128, against 32 / 64 cycles of tensor work.  Here two
+// CTAs on one TPC form a cluster and issue tcgen05.mma.cta_group::2 with M = 256: each CTA stages ITS OWN haloed tile
+// (at the same shared-memory offsets) and holds only HALF of every weight tile (N/2 rows), so per K step an SM reads
+// 4 KB + N*16 B: 40 cycles at N=64, 48 at N=128.
+//   both CTAs   warp 0: TMA producer (own activation tiles, own half of the weights; bytes counted on the LEADER's
+//               barriers), warps 2-5: epilogue of the own 128-row half of each accumulator (own TMEM)
+//   leader only warps 1 and 6: MMA issuers (even / odd accumulators); every tcgen05.commit is multicast to both CTAs
+// "TMEM empty" lives on the leader: 2 x 128 epilogue threads arrive there (the peer's through shared::cluster).
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, 1)
+conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                     const __grid_constant__ CUtensorMap tmBh, const float* __restrict__ bias, void* __restrict__ y, int y_dt,
+                     int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int pad, HaloGeom g,
+                     int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy, long long y_sx, int total_tiles,
+                     int act) {
+  constexpr int HB_BYTES = (BLOCK_N / 2) * KBLK * 2;       // this CTA's half of one (channel block, tap) weight tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int taps = KH * KW;
+  const int ncb0 = (C0 + KBLK - 1) / KBLK;
+  const int ncb = ncb0 + (C1 + KBLK - 1) / KBLK;
+  uint8_t* s_a = smem;
+  uint8_t* s_b = smem + g.SA * g.a_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_b + ncb * taps * HB_BYTES);
+  uint64_t* a_empty = a_full + 4;
+  uint64_t* b_full = a_empty + 4;
+  uint64_t* tfull_bar = b_full + 1;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                  // 0 = leader
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int pair_tiles = (total_tiles + 1) >> 1;            // the pair works on tiles 2*pt (leader) and 2*pt + 1 (peer)
+  const uint32_t tmem_cols = (uint32_t)(2 * g.G * BLOCK_N) <= 32u ? 32u : (uint32_t)(2 * g.G * BLOCK_N);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (C1 > 0) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmBh);
+    for (int s = 0; s < g.SA; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 2); }
+    mbar_init(b_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + b, 2); mbar_init(tempty_bar + b, 256); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers are initialised and both TMEM halves allocated before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const uint32_t a_box_bytes = (uint32_t)(g.TN * g.RS * g.Pp * KBLK * 2);
+      if (rank == 0) mbar_expect_tx(b_full, (uint32_t)(ncb * taps * HB_BYTES * 2));
+      for (int cb = 0; cb < ncb; ++cb)
+        for (int tap = 0; tap < taps; ++tap)
+          tma_load_2d_2sm(s_b + (cb * taps + tap) * HB_BYTES, &tmBh, b_full, cb * KBLK,
+                          tap * w_rows_per_tap + w_row_off + (int)rank * (BLOCK_N / 2));
+      int ia = 0;
+      for (int pt = cluster_id; pt < pair_tiles; pt += n_clusters) {
+        int mt = 2 * pt + (int)rank;                         // past the last tile: image index >= N, TMA zero-fills
+        const int txi = mt % g.tiles_x; mt /= g.tiles_x;
+        const int tyi = mt % g.tiles_y; mt /= g.tiles_y;
+        const int x0 = txi * g.TWo, y0 = tyi * g.TH, img0 = mt * g.TN;
+        for (int cb = 0; cb < ncb; ++cb, ++ia) {
+          const bool first = cb < ncb0;
+          const CUtensorMap* mA = first ? &tmA0 : &tmA1;
+          const int c_in_src = first ? cb * KBLK : (cb - ncb0) * KBLK;
+          const int sa = ia % g.SA;
+          mbar_wait(a_empty + sa, ((uint32_t)(ia / g.SA) & 1u) ^ 1u);
+          if (rank == 0) mbar_expect_tx(a_full + sa, 2u * a_box_bytes);
+          tma_load_4d_2sm(s_a + sa * g.a_bytes, mA, a_full + sa, c_in_src, x0 - pad, y0 - pad, img0);
+        }
+      }
+    }
+  } else if (warp == 1 || warp == HALO_MMA2_WARP) {
+    // ===================== MMA issuers (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * TILE_PIX, BLOCK_N, 0, 0);
+      const int g_first = warp == 1 ? 0 : 1;
+      const uint32_t leader = elect_one();
+      const uint32_t tmem_acc = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b);
+      const int G = g.G, Pp = g.Pp, SA = g.SA, a_bytes = g.a_bytes;
+      int ia = 0, tc = 0;
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+      for (int pt = cluster_id; pt < pair_tiles; pt += n_clusters, ++tc) {
+        const uint32_t buf = (uint32_t)tc & 1u;
+        mbar_wait(tempty_bar + buf, (((uint32_t)tc >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_col = tmem_acc + buf * (uint32_t)(G * BLOCK_N);
+        for (int cb = 0; cb < ncb; ++cb, ++ia) {
+          const int sa = ia % SA;
+          mbar_wait(a_full + sa, (uint32_t)(ia / SA) & 1u);
+          tc_fence_after();
+          const uint32_t a_stage = a_base + (uint32_t)(sa * a_bytes);
+          for (int r = 0; r < KH; ++r) {
+            for (int q = 0; q < KW; ++q) {
+              if (leader) {
+                const uint64_t db = make_smem_desc(b_base + (uint32_t)((cb * taps + r * KW + q) * HB_BYTES), 16, 1024);
+                const uint32_t a_tap = a_stage + (uint32_t)((r * Pp + q) * 128);
+                for (int gi = g_first; gi < G; gi += 2) {
+                  const uint64_t da = make_smem_desc(a_tap + (uint32_t)(gi * TILE_PIX * 128), 16, 1024);
+                  const uint32_t d = d_col + (uint32_t)(gi * BLOCK_N);
+                  const uint32_t acc0 = (cb > 0 || r > 0 || q > 0) ? 1u : 0u;
+#pragma unroll
+                  for (int k = 0; k < KBLK / 16; ++k)
+                    umma_bf16_2sm(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (k > 0) ? 1u : acc0);
+                }
+              }
+              __syncwarp();
+            }
+          }
+          if (leader) umma_commit_2sm(a_empty + sa, 3u);      // both CTAs' producers may refill this stage
+          __syncwarp();
+        }
+        if (leader) umma_commit_2sm(tfull_bar + buf, 3u);     // both CTAs' epilogues may drain their half
+        __syncwarp();
+      }
+    }
+  } else if (warp < HALO_MMA2_WARP) {
+    // ===================== epilogue (warps 2-5 of both CTAs: own rows of the accumulators) =====================
+    const int q4 = warp & 3;
+    const int img_pos = g.RS * g.Pp;
+    int tc = 0;
+    for (int pt = cluster_id; pt < pair_tiles; pt += n_clusters, ++tc) {
+      int mt = 2 * pt + (int)rank;
+      const bool tile_live = mt < total_tiles;
+      const int txi = mt % g.tiles_x; mt /= g.tiles_x;
+      const int tyi = mt % g.tiles_y; mt /= g.tiles_y;
+      const int x0 = txi * g.TWo, y0 = tyi * g.TH, img0 = mt * g.TN;
+      const uint32_t buf = (uint32_t)tc & 1u;
+      mbar_wait(tfull_bar + buf, ((uint32_t)tc >> 1) & 1u);
+      tc_fence_after();
+      for (int gi = 0; gi < g.G && tile_live; ++gi) {
+        const int m = gi * TILE_PIX + q4 * 32 + lane;
+        const int tn = m / img_pos;
+        const int rem = m - tn * img_pos;
+        const int row = rem / g.Pp, col = rem - row * g.Pp;
+        const int px = x0 + col, py = y0 + row, img = img0 + tn;
+        const bool live = tn < g.TN && row < g.TH && col < g.TWo && px < Wo && py < Ho && img < N;
+        const int64_t obase = (int64_t)img * y_sn + (int64_t)py * y_sy + (int64_t)px * y_sx;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * (uint32_t)(g.G * BLOCK_N) + (uint32_t)(gi * BLOCK_N);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          tmem_ld16(taddr + (uint32_t)c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+          tmem_ld_wait();
+          if (live) {
+            float f[32];
+            const int cvalid = Cout - c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + c + j) : 0.f);
+              if (act == DAFK_ACT_RELU) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (y_dt == DAFK_F32) {
+              float* o = reinterpret_cast<float*>(y) + obase + c;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (j < cvalid) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(y) + obase + c;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * i], f[j + 2 * i + 1]);
+                  pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                if (j < cvalid) *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_leader(tempty_bar + buf);
+    }
+  }
+  // the leader's MMAs read the peer's shared memory and write its TMEM: nobody leaves before both CTAs are done
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // weight-gradient kernel.  grid = (units, splits); unit = (tap, co-block, ci-block)
 //   D[co (M = BM), ci (N = BN)] += sum over this CTA's pixel tiles of dY^T * X_shift
 // ---------------------------------------------------------------------------------------------
@@ -845,6 +1045,31 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   return check_launch("dafk_conv_tc_fwd(halo)");
 }
 
+template <int BLOCK_N>
+static int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bh, const float* bias, void* y,
+                        int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int pad,
+                        const HaloGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
+                        long long y_sx, int act, cudaStream_t s) {
+  const int ncb_all = (C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK;
+  const int smem = g.SA * g.a_bytes + ncb_all * KH * KW * (BLOCK_N / 2) * KBLK * 2 + 1024 + 512;
+  DAFK_REQUIRE(smem <= 227 * 1024, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd(halo2): %d bytes of shared memory", smem);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_halo2) failed: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int64_t tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n;
+  DAFK_REQUIRE(tiles < (1LL << 30), DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd(halo2): too many tiles");
+  const int smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;      // one persistent CTA per SM
+  const int64_t pairs = (tiles + 1) / 2;
+  const int clusters = (int)(pairs < kNumSMs / 2 ? pairs : kNumSMs / 2);
+  conv_tc_halo2_kernel<BLOCK_N><<<dim3(2 * clusters), HALO_THREADS, smem_req, s>>>(
+      a0, a1, bh, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, g, w_rows_per_tap, w_row_off, y_sn, y_sy, y_sx,
+      (int)tiles, act);
+  return check_launch("dafk_conv_tc_fwd(halo2)");
+}
+
 template <int BM, int BN, int STAGES>
 static int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mdy, float* dw, int Cin, int cin_off, int cin_total,
                         int Cout, int KH, int KW, int stride, int pad, const TileGeom& g, cudaStream_t s) {
@@ -926,6 +1151,26 @@ static int conv_tc_fwd_impl(const void* x0, int C0, const void* x1, int C1, cons
     // the tap-by-tap kernel is L2-bound on the activations); with Cout >= 256 the 128 x 256 tap-by-tap tiles win
     (void)ct;
     const bool prefer_halo = Cout < 256;
+    int halo2 = 0;
+    { const char* e = getenv("DAFK_CONV_HALO2"); halo2 = e ? atoi(e) : 0; }    // opt-in CTA-pair variant, read per call
+    if (halo2 && force != 0 && prefer_halo && Cout <= bn) {
+      // each CTA of the pair keeps half of every weight tile resident
+      const int w_half = (Kpad / KBLK) * taps * (bn / 2) * KBLK * 2;
+      HaloGeom h2;
+      if (w_half <= 150 * 1024 && pick_halo_geom(N, Ho, Wo, KH, KW, bn, 1, &h2, w_half) < 1e29) {
+        CUtensorMap h0, h1, bh;
+        rc = make_halo_map(&h0, x0, N, H, W, C0, h2);
+        if (rc) return rc;
+        if (C1 > 0) { rc = make_halo_map(&h1, x1, N, H, W, C1, h2); if (rc) return rc; } else h1 = h0;
+        rc = make_w_map(&bh, wp, taps * w_rows_per_tap, Kpad, bn / 2);
+        if (rc) return rc;
+        if (bn == 128)
+          return launch_halo2<128>(h0, h1, bh, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, h2, w_rows_per_tap,
+                                   w_row_off, y_sn, y_sy, y_sx, act, s);
+        return launch_halo2<64>(h0, h1, bh, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, h2, w_rows_per_tap,
+                                w_row_off, y_sn, y_sy, y_sx, act, s);
+      }
+    }
     if (ch < 1e29 && force != 0 && (force == 1 || prefer_halo)) {
       CUtensorMap h0, h1;
       rc = make_halo_map(&h0, x0, N, H, W, C0, hg);

@@ -56,6 +56,43 @@ def test_conv3x3_tc_forward(ops, case):
     assert rel_l2(cpu(yb), yr) < 5e-3
 
 
+PAIR_CASES = [
+    # N, H, W, C0, C1, Cout      (resident half-weights per CTA: Cout <= 128, (C0 + C1) * Cout * 9 <= 150 KB per half)
+    (2, 16, 16, 64, 0, 64),
+    (3, 24, 40, 64, 0, 64),      # odd number of tiles: the peer CTA's last tile is empty
+    (2, 16, 16, 64, 64, 64),     # two K sources
+    (2, 16, 16, 64, 0, 128),
+    (2, 16, 16, 128, 0, 128),
+    (1, 56, 56, 64, 0, 64),
+    (5, 64, 64, 64, 0, 64),      # several tile pairs per cluster: both TMEM buffers and every stage are reused
+]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DAFK_TEST_EXPERIMENTAL") != "1",
+                    reason="DAFK_CONV_HALO2 (cta_group::2 pairs): compiled, not yet run on a GPU (round 1 budget spent)")
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv3x3_tc_forward_cta_pairs(ops, case, monkeypatch):
+    """tcgen05.mma.cta_group::2 variant of the haloed-tile kernel against the oracle and the single-CTA kernel"""
+    N, H, W, C0, C1, Cout = case
+    r = np.random.RandomState(sum(case) + 11)
+    Cin = C0 + C1
+    x = bf16_round(r.normal(size=(N, H, W, Cin)).astype(np.float32))
+    w = bf16_round((r.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32))
+    b = r.normal(size=Cout).astype(np.float32)
+    yr = R.conv2d(t(x, torch.float64), t(w, torch.float64), t(b, torch.float64), 1, "same").numpy()
+    wp = ops.pack_conv3x3(gpu(w))
+    x0 = gpu(x[..., :C0], torch.bfloat16)
+    x1 = gpu(x[..., C0:], torch.bfloat16) if C1 else None
+    monkeypatch.setenv("DAFK_CONV_HALO2", "0")
+    y0 = ops.conv3x3_tc_fwd(x0, x1, wp, gpu(b), Cout)
+    monkeypatch.setenv("DAFK_CONV_HALO2", "1")
+    for _ in range(2):
+        y1 = ops.conv3x3_tc_fwd(x0, x1, wp, gpu(b), Cout)
+        torch.cuda.synchronize()
+        assert rel_l2(cpu(y1), yr) < 1e-4
+        assert rel_l2(cpu(y1), cpu(y0)) < 1e-6      # same K order per accumulator
+
+
 @pytest.mark.parametrize("case", CASES[:5])
 def test_conv3x3_tc_dgrad(ops, case):
     N, H, W, C0, C1, Cout = case
