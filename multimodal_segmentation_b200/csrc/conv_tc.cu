@@ -805,6 +805,51 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
   }
 }
 
+// forward packing as a tiled transpose (opt-in, DAFK_PACK_TILED=1): the kernel above reads HWIO with the input channel
+// fastest, i.e. one 4-byte element per 4*Cout-byte stride; here a 32 ci x 32 co tile of one tap is read along co and
+// written along ci through shared memory.  Same values, same rounding.
+__global__ void __launch_bounds__(256) pack_w_fwd_tiled_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                                               int taps, int Cin, int Cout, int Cip, int Cop,
+                                                               const float* __restrict__ scale) {
+  __shared__ float tile[32][33];
+  const int tiles_ci = Cip / 32, tiles_co = Cop / 32;       // Cip, Cop are multiples of 64
+  const int64_t ntiles = (int64_t)taps * tiles_ci * tiles_co;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tco = (int)(t % tiles_co);
+    const int64_t u = t / tiles_co;
+    const int tci = (int)(u % tiles_ci);
+    const int tap = (int)(u / tiles_ci);
+    const int ci0 = tci * 32, co0 = tco * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ci = ci0 + ty + 8 * k, co = co0 + tx;
+      float v = (ci < Cin && co < Cout) ? w[((int64_t)tap * Cin + ci) * Cout + co] : 0.f;
+      if (scale != nullptr && co < Cout) v *= scale[co];
+      tile[ty + 8 * k][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int co = co0 + ty + 8 * k, ci = ci0 + tx;
+      wp[((int64_t)tap * Cop + co) * Cip + ci] = __float2bfloat16_rn(tile[tx][ty + 8 * k]);
+    }
+    __syncthreads();
+  }
+}
+
+static bool pack_tiled_enabled() {
+  const char* e = getenv("DAFK_PACK_TILED");     // read per call: a test compares both kernels in one process
+  return e != nullptr && atoi(e) != 0;
+}
+
+static void launch_pack_fwd_tiled(const float* w, __nv_bfloat16* wp, int taps, int Cin, int Cout, int Cip, int Cop,
+                                  const float* scale, cudaStream_t s) {
+  const int64_t ntiles = (int64_t)taps * (Cip / 32) * (Cop / 32);
+  const int grid = (int)(ntiles < (int64_t)kNumSMs * 8 ? ntiles : (int64_t)kNumSMs * 8);
+  pack_w_fwd_tiled_kernel<<<grid, 256, 0, s>>>(w, wp, taps, Cin, Cout, Cip, Cop, scale);
+}
+
 // data gradient of a stride-2 convolution, output parity class (pa,pb):
 //   dx[2a+pa, 2b+pb, ci] = sum_{i',j' in {0..KH/2-1}} dy[a + i' - (KH/2-1), b + j' - (KW/2-1), co] * w[pa + 2(KH/2-1-i'), pb + 2(KW/2-1-j'), ci, co]
 // packed as [tap' = i'*(KW/2)+j'][Cin][Cout]
@@ -1240,7 +1285,10 @@ int dafk_pack_conv(const float* w_hwio, void* wp, int KH, int KW, int Cin, int C
   const int Cip = (Cin + 63) / 64 * 64, Cop = (Cout + 63) / 64 * 64;
   if (mode == 0 || mode == 1) {
     int64_t total = (int64_t)KH * KW * Cip * Cop;
-    pack_w_kernel<<<bw_grid(total, 256), 256, 0, s>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, Cip, Cop, mode, nullptr);
+    if (mode == 0 && pack_tiled_enabled())
+      launch_pack_fwd_tiled(w_hwio, (__nv_bfloat16*)wp, KH * KW, Cin, Cout, Cip, Cop, nullptr, s);
+    else
+      pack_w_kernel<<<bw_grid(total, 256), 256, 0, s>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, Cip, Cop, mode, nullptr);
   } else if (mode == 2) {
     DAFK_REQUIRE(KH % 2 == 0 && KW % 2 == 0 && (pa == 0 || pa == 1) && (pb == 0 || pb == 1), DAFK_ERR_BAD_ARG,
                  "dafk_pack_conv: stride-2 data-gradient packing needs an even kernel and a parity in {0,1}");
@@ -1277,7 +1325,10 @@ int dafk_pack_conv_scaled(const float* w_hwio, const float* scale, void* wp, int
   DAFK_REQUIRE(w_hwio && scale && wp && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, DAFK_ERR_BAD_ARG, "dafk_pack_conv_scaled: bad argument");
   const int Cip = (Cin + 63) / 64 * 64, Cop = (Cout + 63) / 64 * 64;
   const int64_t total = (int64_t)KH * KW * Cip * Cop;
-  pack_w_kernel<<<bw_grid(total, 256), 256, 0, as_stream(stream)>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, Cip, Cop, 0, scale);
+  if (pack_tiled_enabled())
+    launch_pack_fwd_tiled(w_hwio, (__nv_bfloat16*)wp, KH * KW, Cin, Cout, Cip, Cop, scale, as_stream(stream));
+  else
+    pack_w_kernel<<<bw_grid(total, 256), 256, 0, as_stream(stream)>>>(w_hwio, (__nv_bfloat16*)wp, KH, KW, Cin, Cout, Cip, Cop, 0, scale);
   return check_launch("dafk_pack_conv_scaled");
 }
 

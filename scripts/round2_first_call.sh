@@ -7,6 +7,8 @@ export DAFK_TEST_EXPERIMENTAL=1
 {
   echo "== cta_group::2 haloed-tile kernel (DAFK_CONV_HALO2)"
   timeout 150 python -m pytest tests/test_conv_tc_gpu.py -m gpu -q -k cta_pairs 2>&1 | tail -15
+  echo "== tiled-transpose weight packing (DAFK_PACK_TILED)"
+  timeout 100 python -m pytest tests/test_conv_tc_gpu.py -m gpu -q -k tiled_transpose 2>&1 | tail -5
   echo "== 12-warp raster-strip layout (DAFK_NC_L12)"
   timeout 150 python -m pytest tests/test_conv_nc_gpu.py -m gpu -q -k twelve 2>&1 | tail -5
   echo "== costs.py functional helpers"
@@ -26,5 +28,9 @@ export DAFK_TEST_EXPERIMENTAL=1
     DAFK_NC_L12=$v timeout 60 python scripts/bench_nc.py seg8x64 50 2>&1 | tail -3
   done
 } > gpurun_out/r2_experimental_bench.log 2>&1
+for v in 0 1; do
+  echo "== whole step, DAFK_PACK_TILED=$v" >> gpurun_out/r2_experimental_bench.log
+  DAFK_PACK_TILED=$v timeout 150 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | cut -c1-200 >> gpurun_out/r2_experimental_bench.log
+done
 tail -40 gpurun_out/r2_experimental_tests.log
 tail -40 gpurun_out/r2_experimental_bench.log

@@ -93,6 +93,22 @@ def test_conv3x3_tc_forward_cta_pairs(ops, case, monkeypatch):
         assert rel_l2(cpu(y1), cpu(y0)) < 1e-6      # same K order per accumulator
 
 
+@pytest.mark.skipif(__import__("os").environ.get("DAFK_TEST_EXPERIMENTAL") != "1",
+                    reason="DAFK_PACK_TILED (tiled-transpose weight packing): compiled, not yet run on a GPU")
+@pytest.mark.parametrize("shape", [(3, 64, 64), (3, 64, 128), (3, 80, 72), (4, 4, 64), (3, 1024, 512), (1, 128, 8)])
+def test_pack_conv_tiled_transpose_is_bit_identical(ops, shape, monkeypatch):
+    k, Cin, Cout = shape
+    r = np.random.RandomState(sum(shape))
+    w = gpu(r.normal(size=(k, k, Cin, Cout)).astype(np.float32))
+    scale = gpu(r.uniform(0.5, 2.0, size=Cout).astype(np.float32))
+    monkeypatch.setenv("DAFK_PACK_TILED", "0")
+    p0, s0 = ops.pack_conv(w, 0), ops.pack_conv_scaled(w, scale)
+    monkeypatch.setenv("DAFK_PACK_TILED", "1")
+    p1, s1 = ops.pack_conv(w, 0), ops.pack_conv_scaled(w, scale)
+    torch.cuda.synchronize()
+    assert torch.equal(p0, p1) and torch.equal(s0, s1)
+
+
 @pytest.mark.parametrize("case", CASES[:5])
 def test_conv3x3_tc_dgrad(ops, case):
     N, H, W, C0, C1, Cout = case
