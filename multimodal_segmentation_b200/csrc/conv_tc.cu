@@ -1354,6 +1354,13 @@ int dafk_conv_tc_wgrad(const void* x, int Cin, int cin_off, int cin_total, const
   rc = make_act_map(&mdy, dy, N, Ho, Wo, Cout, g, 1);
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
+  {
+    // opt-in (DAFK_WGRAD_BN256=1): 128 x 256 accumulator, 0.75x the operand bytes per MAC of the 128 x 128 tile
+    // (96 KB per 128 x 256 x 128 k-block against 64 KB per 128 x 128 x 128), two 96 KB stages
+    const char* e = getenv("DAFK_WGRAD_BN256");
+    if (e != nullptr && atoi(e) != 0 && Cout % 128 == 0 && Cin % 256 == 0)
+      return launch_wgrad<128, 256, 2>(mx, mdy, dw, Cin, cin_off, cin_total, Cout, KH, KW, stride, pad, g, s);
+  }
   if (Cout % 128 == 0 && Cin % 128 == 0)
     return launch_wgrad<128, 128, 3>(mx, mdy, dw, Cin, cin_off, cin_total, Cout, KH, KW, stride, pad, g, s);
   if (Cout % 128 == 0) return launch_wgrad<128, 64, 4>(mx, mdy, dw, Cin, cin_off, cin_total, Cout, KH, KW, stride, pad, g, s);

@@ -9,6 +9,8 @@ export DAFK_TEST_EXPERIMENTAL=1
   timeout 150 python -m pytest tests/test_conv_tc_gpu.py -m gpu -q -k cta_pairs 2>&1 | tail -15
   echo "== tiled-transpose weight packing (DAFK_PACK_TILED)"
   timeout 100 python -m pytest tests/test_conv_tc_gpu.py -m gpu -q -k tiled_transpose 2>&1 | tail -5
+  echo "== 128 x 256 weight-gradient tile (DAFK_WGRAD_BN256)"
+  timeout 100 python -m pytest tests/test_conv_tc_gpu.py -m gpu -q -k wide_tile 2>&1 | tail -5
   echo "== 12-warp raster-strip layout (DAFK_NC_L12)"
   timeout 150 python -m pytest tests/test_conv_nc_gpu.py -m gpu -q -k twelve 2>&1 | tail -5
   echo "== costs.py functional helpers"
@@ -21,6 +23,11 @@ export DAFK_TEST_EXPERIMENTAL=1
     echo "== DAFK_CONV_HALO2=$v"
     DAFK_CONV_HALO2=$v timeout 120 python scripts/bench_tc.py "@224" 20 2>&1 | tail -6
     DAFK_CONV_HALO2=$v timeout 120 python scripts/bench_tc.py "@112" 20 2>&1 | tail -6
+  done
+  for v in 0 1; do
+    echo "== DAFK_WGRAD_BN256=$v"
+    DAFK_WGRAD_BN256=$v timeout 120 python scripts/bench_tc.py "@28" 20 2>&1 | tail -6
+    DAFK_WGRAD_BN256=$v timeout 120 python scripts/bench_tc.py "@14" 20 2>&1 | tail -4
   done
   for v in 0 1; do
     echo "== DAFK_NC_L12=$v"

@@ -139,6 +139,23 @@ def test_conv3x3_tc_wgrad(ops, case):
     assert err < 1e-3, err
 
 
+@pytest.mark.skipif(__import__("os").environ.get("DAFK_TEST_EXPERIMENTAL") != "1",
+                    reason="DAFK_WGRAD_BN256 (128 x 256 weight-gradient tile): compiled, not yet run on a GPU")
+@pytest.mark.parametrize("case", [(4, 14, 14, 256, 256), (2, 28, 28, 256, 128), (3, 7, 7, 512, 384)])
+def test_conv3x3_tc_wgrad_wide_tile(ops, case, monkeypatch):
+    N, H, W, Cin, Cout = case
+    r = np.random.RandomState(sum(case) + 4)
+    x = bf16_round(r.normal(size=(N, H, W, Cin)).astype(np.float32))
+    dy = bf16_round(r.normal(size=(N, H, W, Cout)).astype(np.float32))
+    wt = torch.zeros(3, 3, Cin, Cout, dtype=torch.float64, requires_grad=True)
+    (R.conv2d(t(x, torch.float64), wt, None, 1, "same") * t(dy, torch.float64)).sum().backward()
+    monkeypatch.setenv("DAFK_WGRAD_BN256", "1")
+    dw = ops.zeros(3, 3, Cin, Cout)
+    ops.conv3x3_tc_wgrad(gpu(x, torch.bfloat16), gpu(dy, torch.bfloat16), dw)
+    torch.cuda.synchronize()
+    assert rel_l2(cpu(dw), wt.grad.numpy()) < 1e-3
+
+
 @pytest.mark.parametrize("case", [(2, 16, 16, 64, 64), (1, 24, 40, 64, 64), (3, 37, 21, 64, 64), (2, 16, 32, 128, 128),
                                   (2, 16, 16, 64, 128), (2, 24, 16, 128, 64), (1, 56, 56, 64, 64), (2, 8, 8, 256, 64)])
 def test_conv3x3_tc_wgrad_halo(ops, case):
