@@ -107,30 +107,26 @@ class PairedData(object):
     def expand_pairs(self, offsets, mod_i, neighborhood=2):
         """loaders/MultimodalPairedData.py:91-141: every image of modality `mod_i` becomes `neighborhood` candidate
         images stacked on the channel axis -- channel 0 the expertly paired slice, the others drawn without
-        replacement from the 2*offsets neighbouring slices of the same volume"""
+        replacement from the 2*offsets neighbouring slices of the same volume.  Consumes numpy's global RNG exactly as
+        the reference does (one `choice` per slice, only when the window is larger than the neighbourhood); pinned
+        against the reference's own output in tests/golden/golden_ref.npz."""
         assert mod_i in [0, 1], "mod_i can be in [0, 1]. It defines the neighborhood of which modality to enlarge"
-        all_images = []
+        width = 2 * offsets + 1
+        stacked = []
         for a, b in self.volumes():
-            img_mod1 = self.images[mod_i][a:b]
-            num_images = self.images[1 - mod_i][a:b].shape[0]
-            vol = []
-            for i in range(num_images):
-                if img_mod1.shape[0] < 2 * offsets + 1:
-                    value_range = list(range(0, img_mod1.shape[0])) + [0] * (2 * offsets + 1 - img_mod1.shape[0])
-                elif i < offsets:
-                    value_range = list(range(0, 2 * offsets + 1))
-                elif i + offsets >= num_images:
-                    value_range = list(range(num_images - (2 * offsets + 1), num_images))
-                else:
-                    value_range = list(range(i - offsets, i + offsets + 1))
-                value_range.insert(0, value_range.pop(value_range.index(i)))      # expert pair first
-                assert len(value_range) == 2 * offsets + 1
-                if len(value_range) > neighborhood:
-                    value_range = [value_range[0]] + list(np.random.choice(value_range[1:], size=neighborhood - 1,
-                                                                           replace=False))
-                vol.append(np.concatenate([img_mod1[k:k + 1] for k in value_range], axis=-1))
-            all_images.append(np.concatenate(vol, axis=0))
-        all_images = np.concatenate(all_images, axis=0)
+            src = self.images[mod_i][a:b]
+            n_src, n_dst = src.shape[0], self.images[1 - mod_i][a:b].shape[0]
+            for i in range(n_dst):
+                if n_src < width:                      # volume shorter than the window: padded with slice 0
+                    window = list(range(n_src)) + [0] * (width - n_src)
+                else:                                  # `width` consecutive slices around i, clamped to the volume
+                    start = min(max(i - offsets, 0), n_dst - width)
+                    window = list(range(start, start + width))
+                window.remove(i)                       # the expertly paired slice always leads
+                if width > neighborhood:
+                    window = list(np.random.choice(window, size=neighborhood - 1, replace=False))
+                stacked.append(np.concatenate([src[k] for k in [i] + window], axis=-1))
+        all_images = np.stack(stacked, axis=0)
         assert all_images.shape[-1] == neighborhood, "%s vs %s" % (all_images.shape[-1], neighborhood)
         self.images[mod_i] = all_images
 

@@ -163,6 +163,42 @@ def main():
             sb = (rs.uniform(size=(3, 8, 6, 8)) > 0.6).astype(np.float64)
             out["bal_a"], out["bal_b"] = sa, sb
             out["bal_dice"] = np.asarray(BAL.dice([t(sa), t(sb)]))
+
+            # ---- candidate-pair expansion / re-pairing of the automated-pairing data path
+            #      (loaders/MultimodalPairedData.py:91-166), the reference class executed from its own file
+            #      (skimage's block_reduce, unused here, is the only stand-in); volumes = runs of 8 slices + a short one
+            import importlib.util
+            for name in ("skimage", "skimage.measure"):
+                sys.modules[name] = types.ModuleType(name)
+            sys.modules["skimage.measure"].block_reduce = None
+            pkg = types.ModuleType("loaders")
+            pkg.__path__ = [os.path.join(REF, "loaders")]
+            sys.modules["loaders"] = pkg
+
+            def load(name, rel):
+                spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+                m = importlib.util.module_from_spec(spec)
+                sys.modules[name] = m
+                spec.loader.exec_module(m)
+                return m
+
+            load("loaders.data", "loaders/data.py")
+            MPD = load("loaders.MultimodalPairedData", "loaders/MultimodalPairedData.py").MultimodalPairedData
+            n = 19
+            imgs = np.concatenate([rs.normal(size=(n, 2, 3, 1)) + 100 * m for m in range(2)], -1).astype(np.float32)
+            msks = (rs.uniform(size=(n, 2, 3, 8)) > 0.5).astype(np.float32)
+            index = np.arange(n) // 8
+            out["pairs_images"], out["pairs_masks"] = imgs, msks
+            d = MPD(imgs.copy(), msks.copy(), index)
+            np.random.seed(7)
+            d.expand_pairs(2, 0, neighborhood=3)
+            d.expand_pairs(2, 1, neighborhood=3)
+            out["pairs_expand_mod0"], out["pairs_expand_mod1"] = d.get_images_modi(0), d.get_images_modi(1)
+            d = MPD(imgs.copy(), msks.copy(), index)
+            d.randomise_pairs(length=3, seed=11)
+            out["pairs_randomise_images"], out["pairs_randomise_masks"] = d.get_images_modi(0), d.get_masks_modi(0)
+            for name in ("skimage", "skimage.measure", "loaders", "loaders.data", "loaders.MultimodalPairedData"):
+                sys.modules.pop(name, None)
         finally:
             pass
     path = os.path.join(HERE, "golden_ref.npz")

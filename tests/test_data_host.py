@@ -36,3 +36,28 @@ def test_expand_pairs_keeps_the_expert_pair_first():
             assert all(int(c) in vol for c in cands)                       # neighbours come from the same volume
             if len(vol) >= 5:
                 assert all(abs(int(c) - i) <= 4 for c in cands) and len(set(cands)) == 2 and i not in cands
+
+
+def test_pair_expansion_and_repairing_match_the_reference_class():
+    """golden vectors produced by the reference's own MultimodalPairedData.expand_pairs / randomise_pairs
+    (tests/golden/make_golden.py): same candidates, same order, same consumption of numpy's global RNG"""
+    import os
+    from multimodal_segmentation_b200.loaders.synthetic_chaos import PairedData
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_ref.npz"))
+    imgs, msks = G["pairs_images"], G["pairs_masks"]
+    assert PairedData.SLICES_PER_VOLUME == 8      # the fixture's volume index is i // 8
+
+    def fresh():
+        return PairedData([imgs[..., 0:1].copy(), imgs[..., 1:2].copy()], [msks[..., :4].copy(), msks[..., 4:].copy()])
+
+    d = fresh()
+    np.random.seed(7)
+    d.expand_pairs(2, 0, neighborhood=3)
+    d.expand_pairs(2, 1, neighborhood=3)
+    assert np.array_equal(d.get_images_modi(0), G["pairs_expand_mod0"])
+    assert np.array_equal(d.get_images_modi(1), G["pairs_expand_mod1"])
+    d = fresh()
+    d.randomise_pairs(length=3, seed=11)
+    assert np.array_equal(d.get_images_modi(0), G["pairs_randomise_images"])
+    assert np.array_equal(d.get_masks_modi(0), G["pairs_randomise_masks"])
+    assert np.array_equal(d.get_images_modi(1), imgs[..., 1:2])          # modality 1 stays in place
