@@ -199,6 +199,26 @@ def main():
             out["pairs_randomise_images"], out["pairs_randomise_masks"] = d.get_images_modi(0), d.get_masks_modi(0)
             for name in ("skimage", "skimage.measure", "loaders", "loaders.data", "loaders.MultimodalPairedData"):
                 sys.modules.pop(name, None)
+
+            # ---- stochastic weight averaging (callbacks/swa.py:27-37): the reference callback driven over 6 epochs
+            from callbacks import swa as SWAREF
+            hist = [[rs.normal(size=(3, 4)).astype(np.float32), rs.normal(size=(5,)).astype(np.float32)] for _ in range(6)]
+
+            class _Live(object):
+                def __init__(self):
+                    self.e = 0
+
+                def get_weights(self):
+                    return [w.copy() for w in hist[self.e]]
+
+            cb = SWAREF.SWA(2, lambda: None, None)
+            cb.model = _Live()
+            for e in range(6):
+                cb.model.e = e
+                cb.on_epoch_end(e)
+            for e in range(6):
+                out["swa_hist%d_a" % e], out["swa_hist%d_b" % e] = hist[e]
+            out["swa_avg_a"], out["swa_avg_b"] = cb.swa_weights
         finally:
             pass
     path = os.path.join(HERE, "golden_ref.npz")

@@ -36,6 +36,27 @@ def test_running_average_matches_the_reference_recurrence():
     assert all(np.allclose(a, b) for a, b in zip(m.get_weights(), expect))
 
 
+def test_running_average_matches_the_reference_callback_bit_for_bit():
+    """golden vectors from the reference's own callbacks/swa.py driven over six epochs with swa_epoch=2
+    (tests/golden/make_golden.py): same formula, same evaluation order, identical fp32 result"""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_ref.npz"))
+
+    class Live(object):
+        e = 0
+
+        def get_weights(self):
+            return [G["swa_hist%d_a" % self.e].copy(), G["swa_hist%d_b" % self.e].copy()]
+
+    swa = SWA(2, lambda: None, None)
+    swa.model = Live()
+    for e in range(6):
+        swa.model.e = e
+        swa.on_epoch_end(e)
+    assert swa.swa_weights[0].dtype == np.float32
+    assert np.array_equal(swa.swa_weights[0], G["swa_avg_a"]) and np.array_equal(swa.swa_weights[1], G["swa_avg_b"])
+
+
 def test_on_train_begin_reads_keras_params(capsys):
     swa = SWA(40, lambda: None, None)
     swa.params = {"epochs": 100}
