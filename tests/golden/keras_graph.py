@@ -1,0 +1,324 @@
+"""Define-then-run numpy stand-in for the slice of the Keras 2.1.6 functional API that the reference's BUILDERS use
+(model_components/*.py, models/unet.py, models/discriminator.py, layers/stn_spline.build_locnet): Input, Model (also
+called as a layer), Conv2D, Dense, BatchNormalization (inference phase), Activation, LeakyReLU, MaxPooling2D,
+UpSampling2D, Concatenate, Add, Maximum, Flatten, Reshape, Lambda.
+
+tests/golden/make_golden.py runs the reference's own builder code on top of it, so the golden outputs pin the WIRING of
+every component (which layer feeds which, shared layers, Keras weight order) -- the layer arithmetic itself is the
+documented Keras semantics restated here in float64 numpy (Conv2D SAME/VALID cross-correlation, BatchNormalization with
+epsilon 1e-3 on the moving statistics, LeakyReLU slope 0.3 by default, ...).  Test infrastructure only.
+
+Weights: every weighted layer draws small integers from a generator keyed by its CONSTRUCTION index and scales them
+(w = float32(offset + k * scale)), whatever initializer the builder asked for -- zero-initialised heads would hide wiring
+mistakes.  A model's weight list is "weighted layers reachable from its outputs, by construction index; per layer kernel,
+bias / gamma, beta, moving_mean, moving_var" (for the sequentially built components this is Keras' get_weights order).
+"""
+import numpy as np
+
+STATE = {"ctor": 0, "seed": 1234}
+
+
+def reset(seed=1234):
+    STATE["ctor"] = 0
+    STATE["seed"] = seed
+
+
+class Sym(object):
+    """output `index` of `layer` applied to `inputs` (a Sym or a list of Syms); layer None = placeholder"""
+
+    def __init__(self, layer, inputs, index=0):
+        self.layer, self.inputs, self.index = layer, inputs, index
+
+
+def _has_sym(x):
+    return isinstance(x, Sym) or (isinstance(x, (list, tuple)) and any(isinstance(v, Sym) for v in x))
+
+
+def evaluate(sym, feeds, cache):
+    if id(sym) in cache:
+        return cache[id(sym)]
+    if sym.layer is None:
+        val = feeds[id(sym)]
+    else:
+        key = ("call", id(sym.layer), id(sym.inputs) if isinstance(sym.inputs, Sym) else tuple(id(v) for v in sym.inputs))
+        if key not in cache:
+            if isinstance(sym.inputs, Sym):
+                xin = evaluate(sym.inputs, feeds, cache)
+            else:
+                xin = [evaluate(v, feeds, cache) for v in sym.inputs]
+            cache[key] = sym.layer(xin)
+        out = cache[key]
+        val = out[sym.index] if isinstance(out, (list, tuple)) else out
+    cache[id(sym)] = val
+    return val
+
+
+def sym_call(layer, x):
+    """what tf_shim._Layer.__call__ and the layers below return for symbolic inputs"""
+    s = Sym(layer, list(x) if isinstance(x, (list, tuple)) else x)
+    layer.output = s
+    return s
+
+
+class Layer(object):
+    def __init__(self, name=None, **kwargs):
+        self.name = name
+        self.built = False
+        self.ctor = STATE["ctor"]
+        STATE["ctor"] += 1
+        self.k, self.scale_offset, self.w = [], [], []       # integer draws, (scale, offset), float32 values
+
+    def _draw(self, shape, scale, offset=0.0):
+        rs = np.random.RandomState(STATE["seed"] + 7919 * self.ctor + len(self.k))
+        k = rs.randint(-32, 33, size=shape).astype(np.int8)
+        self.k.append(k)
+        self.scale_offset.append(np.array([scale, offset], np.float64))
+        self.w.append((offset + k.astype(np.float64) * scale).astype(np.float32))
+        return self.w[-1].astype(np.float64)
+
+    def build(self, shape):
+        pass
+
+    def __call__(self, x, **kwargs):
+        if _has_sym(x):
+            return sym_call(self, x)
+        if not self.built:
+            self.build(x[0].shape if isinstance(x, (list, tuple)) else x.shape)
+            self.built = True
+        return self.call(x)
+
+
+def _act(x, name):
+    if name in (None, "linear"):
+        return x
+    if name == "relu":
+        return np.maximum(x, 0.0)
+    if name == "tanh":
+        return np.tanh(x)
+    if name == "sigmoid":
+        return 1.0 / (1.0 + np.exp(-x))
+    if name == "softmax":
+        e = np.exp(x - x.max(-1, keepdims=True))
+        return e / e.sum(-1, keepdims=True)
+    raise ValueError(name)
+
+
+class Input(Sym):
+    def __init__(self, shape=None, **kwargs):
+        Sym.__init__(self, None, None)
+        self.shape_ = tuple(shape)
+
+
+class Conv2D(Layer):
+    def __init__(self, filters, kernel_size, strides=1, padding="valid", activation=None, name=None, **kwargs):
+        Layer.__init__(self, name)
+        self.f, self.ks = int(filters), int(kernel_size if np.isscalar(kernel_size) else kernel_size[0])
+        self.s = int(strides if np.isscalar(strides) else strides[0])
+        self.padding, self.activation = padding, activation
+
+    def build(self, shape):
+        cin = shape[-1]
+        fan_in = self.ks * self.ks * cin
+        self.kernel = self._draw((self.ks, self.ks, cin, self.f), 4.9 / 64.0 / np.sqrt(fan_in))
+        self.bias = self._draw((self.f,), 0.1 / 64.0)
+
+    def call(self, x):
+        x = np.asarray(x, np.float64)
+        k, s = self.ks, self.s
+        if self.padding == "same":      # TensorFlow SAME: out = ceil(in / s), the extra pixel goes to the bottom / right
+            pads = []
+            for n in x.shape[1:3]:
+                out = -(-n // s)
+                tot = max((out - 1) * s + k - n, 0)
+                pads.append((tot // 2, tot - tot // 2))
+            x = np.pad(x, ((0, 0), pads[0], pads[1], (0, 0)))
+        win = np.lib.stride_tricks.sliding_window_view(x, (k, k), axis=(1, 2))[:, ::s, ::s]    # N, Ho, Wo, C, k, k
+        y = np.einsum("nhwcij,ijco->nhwo", win, self.kernel, optimize=True) + self.bias
+        return _act(y, self.activation)
+
+
+class Dense(Layer):
+    def __init__(self, units, activation=None, name=None, **kwargs):
+        Layer.__init__(self, name)
+        self.units, self.activation = int(units), activation
+
+    def build(self, shape):
+        self.kernel = self._draw((shape[-1], self.units), 4.9 / 64.0 / np.sqrt(shape[-1]))
+        self.bias = self._draw((self.units,), 0.1 / 64.0)
+
+    def call(self, x):
+        return _act(np.asarray(x, np.float64) @ self.kernel + self.bias, self.activation)
+
+
+class BatchNormalization(Layer):
+    """inference phase: gamma * (x - moving_mean) / sqrt(moving_var + 1e-3) + beta"""
+
+    def build(self, shape):
+        c = shape[-1]
+        self.gamma = self._draw((c,), 1.0 / 128.0, 1.0)
+        self.beta = self._draw((c,), 1.0 / 256.0)
+        self.mm = self._draw((c,), 1.0 / 256.0)
+        self.mv = self._draw((c,), 1.0 / 128.0, 1.0)
+
+    def call(self, x):
+        return self.gamma * (np.asarray(x, np.float64) - self.mm) / np.sqrt(self.mv + 1e-3) + self.beta
+
+
+class Activation(Layer):
+    def __init__(self, activation, name=None, **kwargs):
+        Layer.__init__(self, name)
+        self.activation = activation
+
+    def call(self, x):
+        return _act(np.asarray(x, np.float64), self.activation)
+
+
+class LeakyReLU(Layer):
+    def __init__(self, alpha=0.3, **kwargs):
+        Layer.__init__(self, kwargs.get("name"))
+        self.alpha = alpha
+
+    def call(self, x):
+        x = np.asarray(x, np.float64)
+        return np.where(x > 0, x, self.alpha * x)
+
+
+class MaxPooling2D(Layer):
+    def __init__(self, pool_size=(2, 2), **kwargs):
+        Layer.__init__(self, kwargs.get("name"))
+        assert tuple(pool_size) == (2, 2)
+
+    def call(self, x):
+        x = np.asarray(x, np.float64)
+        n, h, w, c = x.shape
+        x = x[:, :h // 2 * 2, :w // 2 * 2]
+        return x.reshape(n, h // 2, 2, w // 2, 2, c).max(axis=(2, 4))
+
+
+class UpSampling2D(Layer):
+    def __init__(self, size=2, **kwargs):
+        Layer.__init__(self, kwargs.get("name"))
+        self.size = int(size if np.isscalar(size) else size[0])
+
+    def call(self, x):
+        return np.repeat(np.repeat(np.asarray(x, np.float64), self.size, 1), self.size, 2)
+
+
+class Concatenate(Layer):
+    def __init__(self, axis=-1, **kwargs):
+        Layer.__init__(self, kwargs.get("name"))
+        self.axis = axis
+
+    def call(self, xs):
+        return np.concatenate([np.asarray(v, np.float64) for v in xs], self.axis)
+
+
+class Add(Layer):
+    def call(self, xs):
+        return sum(np.asarray(v, np.float64) for v in xs)
+
+
+class Maximum(Layer):
+    def call(self, xs):
+        out = np.asarray(xs[0], np.float64)
+        for v in xs[1:]:
+            out = np.maximum(out, np.asarray(v, np.float64))
+        return out
+
+
+class Flatten(Layer):
+    def call(self, x):
+        x = np.asarray(x, np.float64)
+        return x.reshape(x.shape[0], -1)
+
+
+class Reshape(Layer):
+    def __init__(self, target_shape, **kwargs):
+        Layer.__init__(self, kwargs.get("name"))
+        self.target = tuple(int(v) for v in target_shape)
+
+    def call(self, x):
+        x = np.asarray(x, np.float64)
+        return x.reshape((x.shape[0],) + self.target)
+
+
+class Lambda(Layer):
+    def __init__(self, function, name=None, **kwargs):
+        Layer.__init__(self, name)
+        self.fn = function
+
+    def call(self, x):
+        return np.asarray(self.fn(x), np.float64)
+
+
+class Model(Layer):
+    def __init__(self, inputs=None, outputs=None, name=None, input=None, output=None, **kwargs):
+        Layer.__init__(self, name)
+        inputs = inputs if inputs is not None else input
+        outputs = outputs if outputs is not None else output
+        self.inputs = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
+        self.single_out = not isinstance(outputs, (list, tuple))
+        self.outputs = [outputs] if self.single_out else list(outputs)
+        self.built = True
+
+    def __call__(self, x, **kwargs):
+        if _has_sym(x):
+            xs = list(x) if isinstance(x, (list, tuple)) else [x]
+            syms = [Sym(self, xs, i) for i in range(len(self.outputs))]
+            self.output = syms[0] if self.single_out else syms
+            return self.output
+        return self.call(x)
+
+    def call(self, x):
+        xs = list(x) if isinstance(x, (list, tuple)) else [x]
+        assert len(xs) == len(self.inputs), (self.name, len(xs), len(self.inputs))
+        feeds = {id(s): np.asarray(v, np.float64) for s, v in zip(self.inputs, xs)}
+        cache = {}
+        return [evaluate(o, feeds, cache) for o in self.outputs]     # always a list; Sym.index picks
+
+    def predict(self, x):
+        out = self.call(x)
+        return out[0] if self.single_out else out
+
+    # ---- the bits of the Keras Model surface the builders touch
+    def summary(self, print_fn=None, **kwargs):
+        return None
+
+    def compile(self, *a, **k):
+        return None
+
+    def _walk(self):
+        seen, order = set(), []
+
+        def visit(s):
+            if id(s) in seen or s.layer is None:
+                return
+            seen.add(id(s))
+            for v in ([s.inputs] if isinstance(s.inputs, Sym) else s.inputs):
+                visit(v)
+            lay = s.layer
+            if isinstance(lay, Model):
+                for l in lay._walk():
+                    if l not in order:
+                        order.append(l)
+            if lay not in order:
+                order.append(lay)
+        for o in self.outputs:
+            visit(o)
+        return order
+
+    @property
+    def layers(self):
+        return sorted(self._walk(), key=lambda l: l.ctor)
+
+    def get_layer(self, name):
+        for l in self.layers:
+            if l.name == name:
+                return l
+        raise ValueError("No such layer: " + str(name))
+
+    def weighted_layers(self):
+        return [l for l in self.layers if getattr(l, "w", None)]
+
+    def get_weights(self):
+        return [w for l in self.weighted_layers() for w in l.w]

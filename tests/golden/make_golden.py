@@ -224,6 +224,114 @@ def main():
     path = os.path.join(HERE, "golden_ref.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024.0))
+    builders()
+
+
+class _Conf(dict):
+    """attribute dictionary (easydict is not installed); the builders only read attributes"""
+    __setattr__ = dict.__setitem__
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
+def builders():
+    """Run the reference's own BUILDER code (model_components/*.py, models/unet.py, models/discriminator.py,
+    layers/stn_spline.build_locnet) on the define-then-run numpy Keras of tests/golden/keras_graph.py and record, per
+    component: the inputs, the outputs (inference phase) and the weights in the component's weight order (int8 draws +
+    [scale, offset]; value = float32(offset + k * scale)).  tests/test_oracle_builders.py loads the weights into this
+    repository's components through set_weights and checks the oracle's restatement of each graph against the outputs."""
+    from tests.golden import keras_graph as KG
+    out = {}
+    rs = np.random.RandomState(4321)
+    S = 48                                  # /16 for the UNet, 48 -> 44 -> 22 -> 18 -> 9 -> 5 in the locnet, 48 -> 23 -> 10 -> 4 -> 1 in D
+    ae = _Conf(input_shape=(S, S, 1), output_shape=(S, S, 8), out_channels=8, filters=2, downsample=4, normalise="batch",
+               rounding=False)
+    conf = _Conf(input_shape=(S, S, 1), num_z=8, num_masks=4, decoder_type="film", n_pairs=3, anatomy_encoder=ae)
+
+    B = 1                                   # one sample keeps the committed fixture small
+
+    def anatomy(n=B):
+        a = rs.uniform(size=(n, S, S, 8))
+        return (a == a.max(-1, keepdims=True)).astype(np.float64)          # one-hot maps, like a rounded softmax
+
+    def f32(a):
+        return np.asarray(a, np.float32).astype(np.float64)                # inputs exactly representable in float32
+
+    def record(tag, model, inputs, outputs):
+        for i, a in enumerate(inputs):
+            a = np.asarray(a)
+            out["%s_in%d" % (tag, i)] = a.astype(np.uint8) if np.array_equal(a, a.astype(np.uint8)) else a.astype(np.float32)
+        for i, a in enumerate(outputs):
+            out["%s_out%d" % (tag, i)] = np.asarray(a, np.float32)
+        ks = [k for l in model.weighted_layers() for k in l.k]
+        sos = [so for l in model.weighted_layers() for so in l.scale_offset]
+        out["%s_wk" % tag] = np.concatenate([k.ravel() for k in ks])                  # all integer draws, flat
+        out["%s_wshape" % tag] = np.array([list(k.shape) + [0] * (4 - k.ndim) for k in ks], np.int32)
+        out["%s_wso" % tag] = np.stack(sos)                                          # [scale, offset] per array
+
+    with tf_shim.installed(REF):
+        for name in ("utils.image_utils", "loaders", "loaders.loader_factory", "model_tester", "keras_contrib",
+                     "keras_contrib.layers"):
+            sys.modules[name] = types.ModuleType(name)
+        sys.modules["loaders"].loader_factory = sys.modules["loaders.loader_factory"]
+        sys.modules["model_tester"].ModelTester = object
+        sys.modules["keras_contrib.layers"].InstanceNormalization = tf_shim._Dummy
+        sys.modules["callbacks.image_callback"] = types.ModuleType("callbacks.image_callback")     # plotting (matplotlib)
+        sys.modules["callbacks.image_callback"].SaveImage = object
+        from model_components import segmentor, modality_encoder, decoder, anatomy_fuser, anatomy_encoder, balancer
+        from models.discriminator import Discriminator
+
+        KG.reset(101)
+        m = segmentor.build(conf)
+        x = anatomy()
+        record("segmentor", m, [x], [m.predict(x)])
+
+        KG.reset(102)
+        m = modality_encoder.build(conf)
+        xs = [anatomy(), f32(rs.uniform(-1, 1, size=(B, S, S, 1)))]
+        head = KG.Model(inputs=m.inputs, outputs=[m.get_layer("z_mean").output, m.get_layer("z_log_var").output,
+                                                  m.get_layer("divergence").output])
+        record("modality_encoder", m, xs, head.predict(xs))          # the sampled z itself is random
+
+        KG.reset(103)
+        m = decoder.build(conf)
+        xs = [anatomy(), f32(rs.normal(size=(B, 8)))]
+        record("decoder_film", m, xs, [m.predict(xs)])
+
+        KG.reset(104)
+        m = anatomy_fuser.build(conf)
+        xs = [anatomy(), anatomy()]
+        theta = KG.Model(inputs=m.inputs, outputs=m.get_layer("stn_locnet").output).predict(xs)
+        record("anatomy_fuser", m, xs, list(m.predict(xs)) + [theta])
+
+        KG.reset(105)
+        m = anatomy_encoder.build(ae)
+        x = f32(rs.uniform(-1, 1, size=(B, S, S, 1)))
+        record("anatomy_encoder", m, [x], [m.predict(x)])
+
+        KG.reset(106)
+        e1, e2 = anatomy_encoder.AnatomyEncoders(["t1", "t2"]).build(ae)
+        x1, x2 = f32(rs.uniform(-1, 1, size=(B, S, S, 1))), f32(rs.uniform(-1, 1, size=(B, S, S, 1)))
+        y1, y2 = e1.predict(x1), e2.predict(x2)
+        record("anatomy_encoders_1", e1, [x1], [y1])
+        record("anatomy_encoders_2", e2, [x2], [y2])
+
+        KG.reset(107)
+        m = Discriminator(_Conf(input_shape=(S, S, 4), name="D_Mask", filters=4, lr=1e-4)).build()
+        x = f32(rs.uniform(size=(B, S, S, 4)))
+        record("discriminator", m, [x], [m.predict(x)])
+
+        KG.reset(108)
+        m = balancer.build(conf)
+        xs = [anatomy(2) for _ in range(4)]
+        record("balancer", m, xs, [m.predict(xs)])
+    path = os.path.join(HERE, "golden_builders.npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024.0))
 
 
 if __name__ == "__main__":

@@ -14,6 +14,8 @@ import types
 
 import numpy as np
 
+from tests.golden import keras_graph as KG
+
 
 class T(np.ndarray):
     """ndarray with the little bit of tf.Tensor surface the reference touches"""
@@ -75,7 +77,8 @@ def _make_tf():
 
     nn = types.ModuleType("tensorflow.nn")
 
-    def softmax(x, axis=-1):
+    def softmax(x, axis=-1, dim=None):          # TF 1.4 spells the axis `dim` (model_components/balancer.py:26)
+        axis = axis if dim is None else dim
         x = np.asarray(x)
         e = np.exp(x - x.max(axis=axis, keepdims=True))
         return t(e / e.sum(axis=axis, keepdims=True))
@@ -191,14 +194,21 @@ def _make_tf():
 
 # ------------------------------------------------------------------------------------------- keras
 class _Layer(object):
+    """keras.engine.topology.Layer for the reference's own layer classes: eager on arrays, a graph node on the symbolic
+    tensors of tests/golden/keras_graph.py (the builders' functional-API use)"""
+
     def __init__(self, **kwargs):
         self.name = kwargs.get("name")
         self.built = False
+        self.ctor = KG.STATE["ctor"]
+        KG.STATE["ctor"] += 1
 
     def build(self, input_shape):
         self.built = True
 
     def __call__(self, x, **kwargs):
+        if KG._has_sym(x):
+            return KG.sym_call(self, x)
         if not self.built:
             self.build(None)
         return self.call(x, **kwargs)
@@ -241,10 +251,13 @@ def _make_keras(rng_holder):
     layers = types.ModuleType("keras.layers")
     for n in ("Concatenate", "MaxPooling2D", "Conv2D", "Flatten", "Dense", "Reshape", "LeakyReLU", "Lambda", "Add",
               "Activation", "UpSampling2D", "BatchNormalization", "Input", "Maximum"):
-        setattr(layers, n, _Dummy)
+        setattr(layers, n, getattr(KG, n))          # define-then-run numpy layers (tests/golden/keras_graph.py)
     keras.layers = layers
-    keras.Input = _Dummy
-    keras.Model = _Dummy
+    keras.Input = KG.Input
+    keras.Model = KG.Model
+    optimizers = types.ModuleType("keras.optimizers")
+    optimizers.Adam = _Dummy
+    keras.optimizers = optimizers
     regularizers = types.ModuleType("keras.regularizers")
     regularizers.Regularizer = object
     keras.regularizers = regularizers
@@ -262,7 +275,8 @@ def _make_keras(rng_holder):
     keras.utils = utils
     return {"keras": keras, "keras.backend": K, "keras.engine": engine, "keras.engine.topology": topology,
             "keras.layers": layers, "keras.regularizers": regularizers, "keras.preprocessing": pre,
-            "keras.preprocessing.image": pimg, "keras.callbacks": cbs, "keras.utils": utils}
+            "keras.preprocessing.image": pimg, "keras.callbacks": cbs, "keras.utils": utils,
+            "keras.optimizers": optimizers}
 
 
 RNG = {"rng": np.random.RandomState(0)}

@@ -1,0 +1,141 @@
+"""The oracle's restatement of every component graph, and this repository's component weight order, pinned by the
+reference's own BUILDER code (CPU).
+
+tests/golden/make_golden.py imports the reference's model_components/*.py, models/unet.py, models/discriminator.py and
+layers/stn_spline.build_locnet unmodified and runs them on a define-then-run numpy Keras (tests/golden/keras_graph.py;
+inference phase, random weights for every layer).  tests/golden/golden_builders.npz holds, per component, the inputs,
+the outputs and the weights in the component's weight order.  Here the weights go into THIS repository's components
+through ``Model.set_weights`` (the Keras-ordered list the executors and the SWA callback use), come back by name through
+``named_weights`` and feed the oracle (oracle/ref_models.py): the outputs must agree.  A layer wired differently, a
+shared layer that is not shared, or a weight list in another order fails here; the CUDA kernels are then checked against
+the same oracle functions in tests/test_models_gpu.py.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_models as RM
+from oracle import ref_ops as R
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_builders.npz"))
+S = 48
+TOL = 2e-6          # float32 storage of the golden outputs
+
+
+def golden_weights(tag):
+    k, shapes, so = G[tag + "_wk"], G[tag + "_wshape"], G[tag + "_wso"]
+    out, pos = [], 0
+    for shp, (scale, offset) in zip(shapes, so):
+        shp = tuple(int(v) for v in shp if v > 0)
+        n = int(np.prod(shp))
+        out.append((offset + k[pos:pos + n].astype(np.float64) * scale).astype(np.float32).reshape(shp))
+        pos += n
+    assert pos == k.size
+    return out
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a, np.float64))
+
+
+def inputs(tag):
+    return [t(G["%s_in%d" % (tag, i)]) for i in range(8) if "%s_in%d" % (tag, i) in G.files]
+
+
+def close(got, key, tol=TOL):
+    ref = G[key].astype(np.float64)
+    got = got.detach().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    assert got.shape == ref.shape, (key, got.shape, ref.shape)
+    err = np.abs(got - ref).max() / max(1.0, np.abs(ref).max())
+    assert err < tol, (key, err)
+
+
+def weights_of(model, tag):
+    ws = golden_weights(tag)
+    assert [tuple(w.shape) for w in ws] == [tuple(p.shape) for p in model.weight_list()], model.name
+    model.set_weights(ws)
+    return {k: t(v) for k, v in model.named_weights().items()}
+
+
+@pytest.fixture(scope="module")
+def net():
+    from multimodal_segmentation_b200.configuration import dafnet_config_chaos
+    from multimodal_segmentation_b200.keras_like import EasyDict
+    from multimodal_segmentation_b200.models.dafnet import DAFNet
+    conf = EasyDict(dafnet_config_chaos.get((S, S, 1)))
+    conf.anatomy_encoder.filters = 2
+    conf.anatomy_encoder.rounding = False
+    conf.d_mask_params.filters = 4
+    conf.d_image_params.filters = 4
+    conf.automatedpairing = True
+    conf.n_pairs = 3
+    conf.folder = "/tmp/dafk_test_no_such_folder"
+    np.random.seed(0)
+    n = DAFNet(conf)
+    n.build()
+    return n
+
+
+def test_segmentor(net):
+    W = weights_of(net.Segmentor, "segmentor")
+    close(RM.segmentor(W, *inputs("segmentor"), RM.BNState(W, False)), "segmentor_out0")
+
+
+def test_modality_encoder(net):
+    W = weights_of(net.Enc_Modality, "modality_encoder")
+    mu, lv = RM.modality_encoder(W, *inputs("modality_encoder"))
+    close(mu, "modality_encoder_out0")
+    close(lv, "modality_encoder_out1")
+    close(R.kl(mu, lv), "modality_encoder_out2")
+
+
+def test_film_decoder(net):
+    W = weights_of(net.Decoder, "decoder_film")
+    close(RM.decoder_film(W, *inputs("decoder_film")), "decoder_film_out0")
+
+
+def test_anatomy_fuser(net):
+    W = weights_of(net.Anatomy_Fuser, "anatomy_fuser")
+    deformed, fused, theta = RM.anatomy_fuser(W, *inputs("anatomy_fuser"))
+    close(theta, "anatomy_fuser_out2")
+    # the reference layer carries the sampling grid through float32 (layers/stn_spline.py:38-53): ~1e-6 pixel, times the
+    # unit slope of a bilinearly sampled one-hot map (measured 1.7e-5)
+    close(deformed, "anatomy_fuser_out0", 1e-4)
+    close(fused, "anatomy_fuser_out1", 1e-4)
+
+
+def test_shared_anatomy_encoders(net):
+    e1, e2 = net.Encoders_Anatomy
+    W = weights_of(e1, "anatomy_encoders_1")
+    W.update(weights_of(e2, "anatomy_encoders_2"))
+    # the up path and the 1x1 head are ONE set of layers in both models (model_components/anatomy_encoder.py:57-70)
+    w1, w2 = golden_weights("anatomy_encoders_1"), golden_weights("anatomy_encoders_2")
+    n_down = len(w1) - sum(1 for a, b in zip(w1[::-1], w2[::-1]) if np.array_equal(a, b))
+    assert 0 < n_down < len(w1) and all(np.array_equal(a, b) for a, b in zip(w1[n_down:], w2[n_down:]))
+    st = RM.BNState(W, False)
+    close(RM.anatomy_encoder(W, *inputs("anatomy_encoders_1"), st, "enc1_", "shared_", rounding=False), "anatomy_encoders_1_out0")
+    close(RM.anatomy_encoder(W, *inputs("anatomy_encoders_2"), st, "enc2_", "shared_", rounding=False), "anatomy_encoders_2_out0")
+
+
+def test_single_anatomy_encoder():
+    from multimodal_segmentation_b200.keras_like import BuildScope, EasyDict
+    from multimodal_segmentation_b200.model_components import anatomy_encoder
+    ae = EasyDict(dict(input_shape=(S, S, 1), output_shape=(S, S, 8), out_channels=8, filters=2, downsample=4,
+                       normalise="batch", rounding=False))
+    with BuildScope(rng=np.random.RandomState(0)):
+        m = anatomy_encoder.build(ae)
+    W = weights_of(m, "anatomy_encoder")
+    close(RM.anatomy_encoder(W, *inputs("anatomy_encoder"), RM.BNState(W, False), "", "", rounding=False), "anatomy_encoder_out0")
+
+
+def test_discriminator(net):
+    W = weights_of(net.D_Mask, "discriminator")
+    close(RM.discriminator(W, "D_Mask", *inputs("discriminator")), "discriminator_out0")
+
+
+def test_balancer(net):
+    W = weights_of(net.Balancer, "balancer")
+    xs = inputs("balancer")
+    close(RM.balancer(W, xs[0], xs[1:]), "balancer_out0")
