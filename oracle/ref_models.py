@@ -248,11 +248,13 @@ def discriminator_trainer_loss(W, name, real, fake, u0s, blocks=3):
     return lr + lf + reg, (lr, lf, reg)
 
 
-def dafnet_generator_loss(W, conf, x1, x2, z1_in, z2_in, eps1, eps2, m1, m2=None, supervised=True):
+def dafnet_generator_loss(W, conf, x1, x2, z1_in, z2_in, eps1, eps2, m1, m2=None, supervised=True, training=True):
     """models/dafnet.py:163-222 (graph) + :145-149 (losses, weights) with the targets fed by
     model_executors/dafnet_executor.py:404-410 / :427-433.  Returns (total, dict of per-output losses,
-    dict of named intermediate tensors, BNState)."""
-    st = BNState(W, training=True)
+    dict of named intermediate tensors, BNState).  ``training=False`` evaluates the same graph in the inference phase
+    (moving BatchNorm statistics): inter["outputs"] is then what the reference trainer's ``predict`` returns
+    (tests/test_oracle_builders.py)."""
+    st = BNState(W, training=training)
     nm = conf["num_masks"]
     dt = conf.get("decoder_type", "film")
     s1 = anatomy_encoder(W, x1, st, "enc1_", "shared_")
@@ -304,6 +306,10 @@ def dafnet_generator_loss(W, conf, x1, x2, z1_in, z2_in, eps1, eps2, m1, m2=None
     total = sum(L.values())
     inter = dict(s1=s1, s2=s2, M1=M1, M2=M2, y1=y1, y2=y2, s1_def=s1_def, s2_def=s2_def, theta1=th1, theta2=th2,
                  z1=z1, z2=z2, mu1=mu1, lv1=lv1, z1_rec=z1_rec, M1_s2_def=M1_s2_def, y1_s2_def=y1_s2_def)
+    # the trainer's output list, models/dafnet.py:214-220
+    inter["outputs"] = ([M1, M2, M1_s2_def, M2_s1_def] if supervised else [M1, M1_s2_def]) + \
+        [adv_m1, adv_m2, adv_m1_s2_def, adv_m2_s1_def] + [y1, y2, y1_s2_def, y2_s1_def] + \
+        [adv_y1, adv_y2, adv_y1_s2_def, adv_y2_s1_def] + [kl1, kl2, z1_rec, z2_rec]
     return total, L, inter, st
 
 

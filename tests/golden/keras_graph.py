@@ -218,6 +218,14 @@ class Add(Layer):
         return sum(np.asarray(v, np.float64) for v in xs)
 
 
+class Multiply(Layer):
+    def call(self, xs):
+        out = np.asarray(xs[0], np.float64)
+        for v in xs[1:]:
+            out = out * np.asarray(v, np.float64)
+        return out
+
+
 class Maximum(Layer):
     def call(self, xs):
         out = np.asarray(xs[0], np.float64)
@@ -286,6 +294,9 @@ class Model(Layer):
 
     def compile(self, *a, **k):
         return None
+
+    def load_weights(self, path):
+        raise IOError("the golden run starts from freshly drawn weights (%s)" % path)
 
     def _walk(self):
         seen, order = set(), []

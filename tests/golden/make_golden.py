@@ -329,6 +329,45 @@ def builders():
         m = balancer.build(conf)
         xs = [anatomy(2) for _ in range(4)]
         record("balancer", m, xs, [m.predict(xs)])
+        # ---- the generator-step graph itself (models/dafnet.py:140-222,336-350): the reference DAFNet class builds its
+        #      components and wires the supervised trainer; its 20 outputs in the inference phase, with the reparametrisation
+        #      noise fixed to one array
+        from models.dafnet import DAFNet
+        import keras.backend as K
+        ae_r = _Conf(ae, rounding=True)
+        dconf = _Conf(conf, n_pairs=1, automatedpairing=False, modality=["t1", "t2"], anatomy_encoder=ae_r,
+                      d_mask_params=_Conf(filters=4, lr=1e-4, name="D_Mask", input_shape=(S, S, 4)),
+                      d_image_params=_Conf(filters=4, lr=1e-4, name="D_Image", input_shape=(S, S, 1)),
+                      w_sup_M=10, w_adv_M=1, w_rec_X=1, w_adv_X=1, w_rec_Z=1, w_kl=0.1, lr=1e-4, folder="/tmp/dafk_no_such_folder")
+        KG.reset(201)
+        net = DAFNet(dconf)
+        net.loader = _Conf(num_masks=4)
+        net.build()
+        xs = [f32(rs.uniform(-1, 1, size=(B, S, S, 1))), f32(rs.uniform(-1, 1, size=(B, S, S, 1))),
+              f32(rs.normal(size=(B, 8))), f32(rs.normal(size=(B, 8)))]
+        eps = f32(rs.normal(size=(B, 8)))
+        K.random_normal = lambda shape, mean=0.0, stddev=1.0: t(eps.copy())
+        outs = net.supervised_trainer.predict(xs)
+        assert len(outs) == 20
+        for i, a in enumerate(xs + [eps]):
+            out["trainer_in%d" % i] = a.astype(np.float32)
+        for i, a in enumerate(outs):
+            a = np.asarray(a, np.float32)
+            out["trainer_out%02d" % i] = a[:, ::2, ::2] if a.ndim == 4 else a       # big maps: every other pixel
+        # the unsupervised trainer is the same graph with two mask outputs less: store which supervised output each of its
+        # 18 outputs equals
+        uouts = net.unsupervised_trainer.predict(xs)
+        assert len(uouts) == 18
+        idx = []
+        for u in uouts:
+            hit = [j for j, a in enumerate(outs) if np.shape(a) == np.shape(u) and np.array_equal(a, u)]
+            assert len(hit) >= 1
+            idx.append(hit[0])
+        out["trainer_unsup_index"] = np.array(idx)
+        for tag, m in (("enc1", net.Encoders_Anatomy[0]), ("enc2", net.Encoders_Anatomy[1]), ("encm", net.Enc_Modality),
+                       ("fuser", net.Anatomy_Fuser), ("seg", net.Segmentor), ("dec", net.Decoder), ("dmask", net.D_Mask),
+                       ("dimg1", net.D_Image1), ("dimg2", net.D_Image2)):
+            record("trainer_" + tag, m, [], [])
     path = os.path.join(HERE, "golden_builders.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024.0))

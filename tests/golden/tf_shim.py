@@ -211,6 +211,9 @@ class _Layer(object):
             return KG.sym_call(self, x)
         if not self.built:
             self.build(None)
+        # arrays coming out of the numpy graph layers get the little bit of tf.Tensor surface back
+        x = [t(v) if isinstance(v, np.ndarray) else v for v in x] if isinstance(x, (list, tuple)) else (
+            t(x) if isinstance(x, np.ndarray) else x)
         return self.call(x, **kwargs)
 
 
@@ -250,7 +253,7 @@ def _make_keras(rng_holder):
     engine.topology = topology
     layers = types.ModuleType("keras.layers")
     for n in ("Concatenate", "MaxPooling2D", "Conv2D", "Flatten", "Dense", "Reshape", "LeakyReLU", "Lambda", "Add",
-              "Activation", "UpSampling2D", "BatchNormalization", "Input", "Maximum"):
+              "Activation", "UpSampling2D", "BatchNormalization", "Input", "Maximum", "Multiply"):
         setattr(layers, n, getattr(KG, n))          # define-then-run numpy layers (tests/golden/keras_graph.py)
     keras.layers = layers
     keras.Input = KG.Input

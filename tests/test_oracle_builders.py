@@ -139,3 +139,47 @@ def test_balancer(net):
     W = weights_of(net.Balancer, "balancer")
     xs = inputs("balancer")
     close(RM.balancer(W, xs[0], xs[1:]), "balancer_out0")
+
+
+def test_generator_step_graph_matches_the_reference_trainer():
+    """models/dafnet.py:140-222,336-350: the reference DAFNet class wires its supervised trainer out of its own
+    components; its 20 outputs (inference phase, fixed reparametrisation noise) against the oracle's restatement of the
+    generator-step graph, with the weights loaded component by component into this repository's DAFNet"""
+    from multimodal_segmentation_b200.configuration import dafnet_config_chaos
+    from multimodal_segmentation_b200.keras_like import EasyDict
+    from multimodal_segmentation_b200.models.dafnet import DAFNet
+    conf = EasyDict(dafnet_config_chaos.get((S, S, 1)))
+    conf.anatomy_encoder.filters = 2
+    conf.d_mask_params.filters = 4
+    conf.d_image_params.filters = 4
+    conf.n_pairs = 1
+    conf.folder = "/tmp/dafk_test_no_such_folder"
+    assert conf.anatomy_encoder.rounding and not conf.automatedpairing
+    np.random.seed(0)
+    n = DAFNet(conf)
+    n.build()
+    W = {}
+    for tag, m in (("enc1", n.Encoders_Anatomy[0]), ("enc2", n.Encoders_Anatomy[1]), ("encm", n.Enc_Modality),
+                   ("fuser", n.Anatomy_Fuser), ("seg", n.Segmentor), ("dec", n.Decoder), ("dmask", n.D_Mask),
+                   ("dimg1", n.D_Image1), ("dimg2", n.D_Image2)):
+        W.update(weights_of(m, "trainer_" + tag))
+    x1, x2, z1, z2, eps = (t(G["trainer_in%d" % i]) for i in range(5))
+    m_dummy = torch.zeros(x1.shape[0], S, S, 5, dtype=torch.float64)
+    c = dict(num_masks=4, decoder_type="film", w_sup_M=10, w_adv_M=1, w_rec_X=1, w_adv_X=1, w_rec_Z=1, w_kl=0.1)
+    _, _, inter, _ = RM.dafnet_generator_loss(W, c, x1, x2, z1, z2, eps, eps, m_dummy, m_dummy, supervised=True,
+                                              training=False)
+    outs = inter["outputs"]
+    assert len(outs) == 20
+    for i, o in enumerate(outs):
+        o = o[:, ::2, ::2] if o.dim() == 4 else o
+        # outputs downstream of the TPS warp inherit its float32 sampling grid (see test_anatomy_fuser); one binarised
+        # anatomy pixel on the 0.5 boundary would show up as an O(1) difference
+        close(o, "trainer_out%02d" % i, 1e-4)
+    # the unsupervised trainer (models/dafnet.py:151-155): 18 outputs, each equal to one of the supervised ones
+    _, _, inter_u, _ = RM.dafnet_generator_loss(W, c, x1, x2, z1, z2, eps, eps, m_dummy, None, supervised=False,
+                                                training=False)
+    idx = G["trainer_unsup_index"]
+    assert len(inter_u["outputs"]) == 18 == len(idx)
+    for o, j in zip(inter_u["outputs"], idx):
+        o = o[:, ::2, ::2] if o.dim() == 4 else o
+        close(o, "trainer_out%02d" % int(j), 1e-4)
