@@ -320,11 +320,13 @@ def balancer(W, s_mod2, s_list):
     return R.softmax(R.dense(l, W["beta/kernel"], W["beta/bias"]))
 
 
-def dafnet_generator_loss_automated(W, conf, x1_lst, x2_lst, z1_in, z2_in, eps1, eps2, m1, m2=None, supervised=True):
+def dafnet_generator_loss_automated(W, conf, x1_lst, x2_lst, z1_in, z2_in, eps1, eps2, m1, m2=None, supervised=True,
+                                    training=True):
     """models/dafnet.py:250-334 (get_params_automated_pairing) + :229-235 (losses, weights) with the targets fed by
     model_executors/dafnet_executor.py:447-454 / :470-477.  n_pairs candidate images per modality; candidate 0 is the
-    expertly paired one.  Every encoder / segmentor call site is a separate application (own BatchNorm statistics)."""
-    st = BNState(W, training=True)
+    expertly paired one.  Every encoder / segmentor call site is a separate application (own BatchNorm statistics).
+    ``training=False``: inference phase; inter["outputs"] is then the reference trainer's ``predict`` output list."""
+    st = BNState(W, training=training)
     nm = conf["num_masks"]
     dt = conf.get("decoder_type", "film")
     x1, x2 = x1_lst[0], x2_lst[0]
@@ -389,6 +391,10 @@ def dafnet_generator_loss_automated(W, conf, x1_lst, x2_lst, z1_in, z2_in, eps1,
     L["ZRec_1"] = conf["w_rec_Z"] * R.mae(z2_in, z2_rec)
     total = sum(L.values())
     inter = dict(s1=s1, s2=s2, w1=w1, w2=w2, M1=M1, y1=y1, s1_def_lst=s1_def_lst, s2_def_lst=s2_def_lst)
+    # the trainer's output list, models/dafnet.py:326-332 (the *_def mask / image entries are the weighted losses)
+    inter["outputs"] = ([M1, M2, m1_s2_def, m2_s1_def] if supervised else [M1, m1_s2_def]) + \
+        [adv_m1, adv_m2, adv_m1_s2_def, adv_m2_s1_def] + [y1, y2, y1_s2_def, y2_s1_def] + \
+        [adv_y1, adv_y2, adv_y1_s2_def, adv_y2_s1_def] + [kl1, kl2, z1_rec, z2_rec]
     return total, L, inter, st
 
 

@@ -250,10 +250,26 @@ class Reshape(Layer):
         return x.reshape((x.shape[0],) + self.target)
 
 
+def _freeze(fn):
+    """Keras runs a Lambda's function while the graph is being BUILT, so a closure over a loop variable
+    (models/dafnet.py:359 `lambda x: x[..., j:j+1]` inside a comprehension) sees that iteration's value.  Here the
+    function only runs at evaluation time: snapshot the closure cells when the layer is applied."""
+    if getattr(fn, "__closure__", None) is None:
+        return fn
+    import types
+    cells = tuple(types.CellType(c.cell_contents) for c in fn.__closure__)
+    return types.FunctionType(fn.__code__, fn.__globals__, fn.__name__, fn.__defaults__, cells)
+
+
 class Lambda(Layer):
     def __init__(self, function, name=None, **kwargs):
         Layer.__init__(self, name)
         self.fn = function
+
+    def __call__(self, x, **kwargs):
+        if _has_sym(x):
+            self.fn = _freeze(self.fn)
+        return Layer.__call__(self, x, **kwargs)
 
     def call(self, x):
         return np.asarray(self.fn(x), np.float64)

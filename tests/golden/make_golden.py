@@ -368,6 +368,33 @@ def builders():
                        ("fuser", net.Anatomy_Fuser), ("seg", net.Segmentor), ("dec", net.Decoder), ("dmask", net.D_Mask),
                        ("dimg1", net.D_Image1), ("dimg2", net.D_Image2)):
             record("trainer_" + tag, m, [], [])
+        # ---- the automated-pairing trainer (models/dafnet.py:224-334,352-361): three candidate images per modality,
+        #      Balancer-weighted per-sample losses computed INSIDE the graph.  Same construction sequence and seed as
+        #      above, hence the same component weights (checked); only the Balancer's are new.
+        first = {tag: [w.copy() for w in m.get_weights()] for tag, m in (("enc1", net.Encoders_Anatomy[0]), ("seg", net.Segmentor),
+                                                                        ("dimg2", net.D_Image2))}
+        aconf = _Conf(dconf, n_pairs=3, automatedpairing=True, input_shape=[S, S, 1])
+        KG.reset(201)
+        anet = DAFNet(aconf)
+        anet.loader = _Conf(num_masks=4)
+        anet.build()
+
+        def masks():
+            lab = rs.randint(0, 5, size=(B, S, S))
+            return np.eye(5)[lab]
+
+        axs = [f32(rs.uniform(-1, 1, size=(B, S, S, 1))) for _ in range(6)] + [masks(), masks()] + \
+            [f32(rs.normal(size=(B, 8))), f32(rs.normal(size=(B, 8)))]
+        aouts = anet.supervised_trainer.predict(axs)
+        assert len(aouts) == 20
+        for tag, m in (("enc1", anet.Encoders_Anatomy[0]), ("seg", anet.Segmentor), ("dimg2", anet.D_Image2)):
+            assert all(np.array_equal(a, b) for a, b in zip(first[tag], m.get_weights())), tag
+        for i, a in enumerate(axs):
+            out["auto_in%d" % i] = a.astype(np.uint8) if np.array_equal(a, a.astype(np.uint8)) else a.astype(np.float32)
+        for i, a in enumerate(aouts):
+            a = np.asarray(a, np.float32)
+            out["auto_out%02d" % i] = a[:, ::2, ::2] if a.ndim == 4 else a
+        record("auto_balancer", anet.Balancer, [], [])
     path = os.path.join(HERE, "golden_builders.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024.0))

@@ -183,3 +183,28 @@ def test_generator_step_graph_matches_the_reference_trainer():
     for o, j in zip(inter_u["outputs"], idx):
         o = o[:, ::2, ::2] if o.dim() == 4 else o
         close(o, "trainer_out%02d" % int(j), 1e-4)
+
+
+def test_automated_pairing_graph_matches_the_reference_trainer(net):
+    """models/dafnet.py:224-334,352-361: three candidates per modality, Balancer weights, per-sample dice + swapped
+    per-batch cross entropy and `mae_single_input` combined INSIDE the graph -- the reference trainer's 20 outputs against
+    the oracle's `dafnet_generator_loss_automated` (inference phase).  Component weights are those of the expert-pairing
+    golden (same construction sequence and seed in the generator), plus the Balancer's."""
+    W = {}
+    for tag, m in (("enc1", net.Encoders_Anatomy[0]), ("enc2", net.Encoders_Anatomy[1]), ("encm", net.Enc_Modality),
+                   ("fuser", net.Anatomy_Fuser), ("seg", net.Segmentor), ("dec", net.Decoder), ("dmask", net.D_Mask),
+                   ("dimg1", net.D_Image1), ("dimg2", net.D_Image2)):
+        W.update(weights_of(m, "trainer_" + tag))
+    W.update(weights_of(net.Balancer, "auto_balancer"))
+    ins = [t(G["auto_in%d" % i]) for i in range(10)]
+    x1_lst, x2_lst, m1, m2, z1, z2 = ins[0:3], ins[3:6], ins[6], ins[7], ins[8], ins[9]
+    eps = t(G["trainer_in4"])
+    c = dict(num_masks=4, decoder_type="film", w_sup_M=10, w_adv_M=1, w_rec_X=1, w_adv_X=1, w_rec_Z=1, w_kl=0.1)
+    # this fixture's network was built with rounding off; the golden run rounds (anatomy_encoder.rounding = True)
+    _, _, inter, _ = RM.dafnet_generator_loss_automated(W, c, x1_lst, x2_lst, z1, z2, eps, eps, m1, m2, supervised=True,
+                                                        training=False)
+    outs = inter["outputs"]
+    assert len(outs) == 20
+    for i, o in enumerate(outs):
+        o = o[:, ::2, ::2] if o.dim() == 4 else o
+        close(o, "auto_out%02d" % i, 1e-4)
