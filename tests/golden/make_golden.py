@@ -266,7 +266,8 @@ def builders():
             a = np.asarray(a)
             out["%s_in%d" % (tag, i)] = a.astype(np.uint8) if np.array_equal(a, a.astype(np.uint8)) else a.astype(np.float32)
         for i, a in enumerate(outputs):
-            out["%s_out%d" % (tag, i)] = np.asarray(a, np.float32)
+            a = np.asarray(a, np.float32)
+            out["%s_out%d" % (tag, i)] = a[:, ::2, ::2] if a.ndim == 4 else a        # maps: every other pixel
         ks = [k for l in model.weighted_layers() for k in l.k]
         sos = [so for l in model.weighted_layers() for so in l.scale_offset]
         out["%s_wk" % tag] = np.concatenate([k.ravel() for k in ks])                  # all integer draws, flat
@@ -354,6 +355,11 @@ def builders():
         for i, a in enumerate(outs):
             a = np.asarray(a, np.float32)
             out["trainer_out%02d" % i] = a[:, ::2, ::2] if a.ndim == 4 else a       # big maps: every other pixel
+        # inference entry point (models/mmsdnet.py:210-232, inherited by DAFNet): all four fusion types
+        for mi, types_ in ((1, ("simple", "def", "max", "maxnostn")), (0, ("simple", "def"))):
+            for ty in types_:
+                pm = net.predict_mask(mi, ty, [xs[0], xs[1]])
+                out["predict_mask_%d_%s" % (mi, ty)] = np.asarray(pm, np.float32)[:, ::2, ::2]
         # the unsupervised trainer is the same graph with two mask outputs less: store which supervised output each of its
         # 18 outputs equals
         uouts = net.unsupervised_trainer.predict(xs)
