@@ -398,12 +398,15 @@ def dafnet_generator_loss_automated(W, conf, x1_lst, x2_lst, z1_in, z2_in, eps1,
     return total, L, inter, st
 
 
-def mmsdnet_generator_loss(W, conf, x1, x2, eps, seg_targets, rec_targets, supervised=True, rounding=True):
+def mmsdnet_generator_loss(W, conf, x1, x2, eps, seg_targets, rec_targets, supervised=True, rounding=True,
+                           training=True, return_outputs=False):
     """models/mmsdnet.py:95-192 (unsupervised / supervised trainer graphs and their loss lists) with the targets fed by
     model_executors/mmsdnet_executor.py:257-260 / :287-290.  Two independent UNets (weights enc1_*, enc2_*), the fused
     (Maximum) anatomies are segmented / decoded and trained, dice only, one D_Mask, six KL terms.
-    Returns (total, dict of per-output losses)."""
-    st = BNState(W, training=True)
+    Returns (total, dict of per-output losses); with ``return_outputs`` also the trainer's output list (masks, D_Mask
+    scores, reconstructions, KL terms) -- in the inference phase (``training=False``) what the reference trainer's
+    ``predict`` returns (tests/test_oracle_builders.py)."""
+    st = BNState(W, training=training)
     nm = conf["num_masks"]
     dt = conf.get("decoder_type", "film")
     x = [x1, x2]
@@ -430,13 +433,17 @@ def mmsdnet_generator_loss(W, conf, x1, x2, eps, seg_targets, rec_targets, super
     L = {}
     for i, (pred, tgt) in enumerate(zip(m_list, seg_targets)):
         L["Segmentor_%d" % i] = conf["w_sup_M"] * R.dice_loss(tgt, pred, nm)
+    adv = []
     for i, m in enumerate(adv_in):
         a = discriminator(W, "D_Mask", m[..., 0:nm])
+        adv.append(a)
         L["D_Mask_%d" % i] = conf["w_adv_M"] * R.mse(torch.ones_like(a), a)
     for i, (y, tgt) in enumerate(zip(rec, rec_targets)):
         L["Decoder_%d" % i] = conf["w_rec_X"] * R.mae(tgt, y)
     for i, k in enumerate(kls):
         L["KL_%d" % i] = conf["w_kl"] * k.mean()
+    if return_outputs:
+        return sum(L.values()), L, m_list + adv + rec + kls
     return sum(L.values()), L
 
 

@@ -401,6 +401,21 @@ def builders():
             a = np.asarray(a, np.float32)
             out["auto_out%02d" % i] = a[:, ::2, ::2] if a.ndim == 4 else a
         record("auto_balancer", anet.Balancer, [], [])
+        # ---- MMSDNet (models/mmsdnet.py:62-192): two independent anatomy encoders, one D_Mask, the deformed AND the fused
+        #      anatomies segmented / re-encoded / decoded; supervised trainer, 24 outputs
+        from models.mmsdnet import MMSDNet
+        KG.reset(301)
+        mnet = MMSDNet(dconf)
+        mnet.loader = _Conf(num_masks=4)
+        mnet.build()
+        mouts = mnet.supervised_trainer.predict([xs[0], xs[1]])
+        assert len(mouts) == 24
+        for i, a in enumerate(mouts):
+            a = np.asarray(a, np.float32)
+            out["mmsd_out%02d" % i] = a[:, ::2, ::2] if a.ndim == 4 else a
+        for tag, m in (("enc1", mnet.Encoders_Anatomy[0]), ("enc2", mnet.Encoders_Anatomy[1]), ("encm", mnet.Enc_Modality),
+                       ("fuser", mnet.Anatomy_Fuser), ("seg", mnet.Segmentor), ("dec", mnet.Decoder), ("dmask", mnet.D_Mask)):
+            record("mmsd_" + tag, m, [], [])
     path = os.path.join(HERE, "golden_builders.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024.0))

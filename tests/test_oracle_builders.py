@@ -224,3 +224,32 @@ def test_automated_pairing_graph_matches_the_reference_trainer(net):
     assert len(outs) == 20
     for i, o in enumerate(outs):
         close(o, "auto_out%02d" % i, 1e-4)
+
+
+def test_mmsdnet_graph_matches_the_reference_trainer():
+    """models/mmsdnet.py:62-192: two independent anatomy encoders (each with its own 1x1 head), the deformed and the
+    fused anatomies segmented, re-encoded and decoded, one D_Mask: the reference supervised trainer's 24 outputs against
+    the oracle's `mmsdnet_generator_loss` (inference phase, one reparametrisation noise array for the six samplings)"""
+    from multimodal_segmentation_b200.configuration import mmsdnet_config_chaos
+    from multimodal_segmentation_b200.keras_like import EasyDict
+    from multimodal_segmentation_b200.models.mmsdnet import MMSDNet
+    conf = EasyDict(mmsdnet_config_chaos.get((S, S, 1)))
+    conf.anatomy_encoder.filters = 2
+    conf.d_mask_params.filters = 4
+    conf.folder = "/tmp/dafk_test_no_such_folder"
+    np.random.seed(0)
+    n = MMSDNet(conf)
+    n.build()
+    W = {}
+    for tag, m in (("enc1", n.Encoders_Anatomy[0]), ("enc2", n.Encoders_Anatomy[1]), ("encm", n.Enc_Modality),
+                   ("fuser", n.Anatomy_Fuser), ("seg", n.Segmentor), ("dec", n.Decoder), ("dmask", n.D_Mask)):
+        W.update(weights_of(m, "mmsd_" + tag))
+    x1, x2, eps = t(G["trainer_in0"]), t(G["trainer_in1"]), t(G["trainer_in4"])
+    dummy_m = [torch.zeros(x1.shape[0], S, S, 5, dtype=torch.float64)] * 6
+    dummy_x = [x1] * 6
+    c = dict(num_masks=4, decoder_type="film", w_sup_M=10, w_adv_M=1, w_rec_X=1, w_kl=0.1)
+    _, _, outs = RM.mmsdnet_generator_loss(W, c, x1, x2, [eps] * 6, dummy_m, dummy_x, supervised=True, rounding=True,
+                                           training=False, return_outputs=True)
+    assert len(outs) == 24
+    for i, o in enumerate(outs):
+        close(o, "mmsd_out%02d" % i, 1e-4)
