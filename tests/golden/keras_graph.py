@@ -23,6 +23,11 @@ def reset(seed=1234):
     STATE["seed"] = seed
 
 
+def _wrap(a):
+    from tests.golden.tf_shim import t     # the tf.Tensor-like ndarray view the reference's loss functions expect
+    return t(a)
+
+
 class Sym(object):
     """output `index` of `layer` applied to `inputs` (a Sym or a list of Syms); layer None = placeholder"""
 
@@ -308,8 +313,32 @@ class Model(Layer):
     def summary(self, print_fn=None, **kwargs):
         return None
 
-    def compile(self, *a, **k):
-        return None
+    def compile(self, optimizer=None, loss=None, loss_weights=None, **kwargs):
+        self.loss, self.loss_weights = loss, loss_weights
+
+    def output_names(self):
+        """Keras names an output after the layer that produced it (duplicates allowed); a loss / weight dictionary is
+        looked up by that name, a list by position (keras/engine/training.py, compile)"""
+        return [o.layer.name for o in self.outputs]
+
+    def loss_values(self, x, targets):
+        """weight_i * mean(loss_i(y_true_i, y_pred_i)) per output, as Keras' total loss sums them (unit sample weights)"""
+        outs = self.call(x)
+        names = self.output_names()
+        vals = []
+        for i, (name, yp, yt) in enumerate(zip(names, outs, targets)):
+            fn = self.loss[name] if isinstance(self.loss, dict) else (self.loss[i] if isinstance(self.loss, (list, tuple)) else self.loss)
+            w = 1.0 if self.loss_weights is None else (self.loss_weights[name] if isinstance(self.loss_weights, dict)
+                                                       else self.loss_weights[i])
+            yp, yt = np.asarray(yp, np.float64), np.asarray(yt, np.float64)
+            if fn == "mse":
+                v = np.mean(np.square(yp - yt), axis=-1)
+            elif fn == "mae":
+                v = np.mean(np.abs(yp - yt), axis=-1)
+            else:
+                v = np.asarray(fn(_wrap(yt), _wrap(yp)), np.float64)
+            vals.append(float(w) * float(np.mean(v)))
+        return vals
 
     def load_weights(self, path):
         raise IOError("the golden run starts from freshly drawn weights (%s)" % path)

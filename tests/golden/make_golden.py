@@ -355,6 +355,16 @@ def builders():
         for i, a in enumerate(outs):
             a = np.asarray(a, np.float32)
             out["trainer_out%02d" % i] = a[:, ::2, ::2] if a.ndim == 4 else a       # big maps: every other pixel
+        # the compiled losses and weights (models/dafnet.py:145-149) on the targets the executor feeds
+        # (model_executors/dafnet_executor.py:404-410): masks, ones for the discriminator scores, the images, a dummy for
+        # the KL outputs (costs.ypred ignores it), the sampled z for the regressor
+        lab1, lab2 = np.eye(5)[rs.randint(0, 5, size=(B, S, S))], np.eye(5)[rs.randint(0, 5, size=(B, S, S))]
+        out["trainer_m1"], out["trainer_m2"] = lab1.astype(np.uint8), lab2.astype(np.uint8)
+        ones, zero = np.ones((B, 1)), np.zeros((B, 1))
+        tg = [lab1, lab2, lab1, lab2] + [ones] * 4 + [xs[0], xs[1], xs[0], xs[1]] + [ones] * 4 + [zero, zero, xs[2], xs[3]]
+        out["trainer_loss"] = np.array(net.supervised_trainer.loss_values(xs, tg))
+        tgu = [lab1, lab1] + tg[4:]
+        out["trainer_unsup_loss"] = np.array(net.unsupervised_trainer.loss_values(xs, tgu))
         # inference entry point (models/mmsdnet.py:210-232, inherited by DAFNet): all four fusion types
         for mi, types_ in ((1, ("simple", "def", "max", "maxnostn")), (0, ("simple", "def"))):
             for ty in types_:
@@ -401,6 +411,9 @@ def builders():
             a = np.asarray(a, np.float32)
             out["auto_out%02d" % i] = a[:, ::2, ::2] if a.ndim == 4 else a
         record("auto_balancer", anet.Balancer, [], [])
+        # targets of the automated-pairing step (dafnet_executor.py:447-454): the *_Def outputs are losses already (ypred)
+        atg = [axs[6], axs[7], zero, zero] + [ones] * 4 + [axs[0], axs[3], zero, zero] + [ones] * 4 + [zero, zero, axs[8], axs[9]]
+        out["auto_loss"] = np.array(anet.supervised_trainer.loss_values(axs, atg))
         # ---- MMSDNet (models/mmsdnet.py:62-192): two independent anatomy encoders, one D_Mask, the deformed AND the fused
         #      anatomies segmented / re-encoded / decoded; supervised trainer, 24 outputs
         from models.mmsdnet import MMSDNet
@@ -416,6 +429,12 @@ def builders():
         for tag, m in (("enc1", mnet.Encoders_Anatomy[0]), ("enc2", mnet.Encoders_Anatomy[1]), ("encm", mnet.Enc_Modality),
                        ("fuser", mnet.Anatomy_Fuser), ("seg", mnet.Segmentor), ("dec", mnet.Decoder), ("dmask", mnet.D_Mask)):
             record("mmsd_" + tag, m, [], [])
+        # loss list of the supervised trainer (models/mmsdnet.py:181-190) on the executor's targets
+        # (model_executors/mmsdnet_executor.py:257-260): masks of modality 1, 2, then 2, 2, 1, 1 for the deformed / fused
+        # anatomies; images x1, x2, x2, x2, x1, x1
+        mtg = [lab1[..., :4], lab2[..., :4], lab2[..., :4], lab2[..., :4], lab1[..., :4], lab1[..., :4]] + [ones] * 6 + \
+            [xs[0], xs[1], xs[1], xs[1], xs[0], xs[0]] + [zero] * 6
+        out["mmsd_loss"] = np.array(mnet.supervised_trainer.loss_values([xs[0], xs[1]], mtg))
     path = os.path.join(HERE, "golden_builders.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024.0))

@@ -172,6 +172,13 @@ def test_generator_step_graph_matches_the_reference_trainer():
                                               training=False)
     outs = inter["outputs"]
     assert len(outs) == 20
+    # the compiled losses and loss weights (models/dafnet.py:145-149) on the executor's targets
+    # (model_executors/dafnet_executor.py:404-410), evaluated by the stand-in as Keras sums them
+    m1, m2 = t(G["trainer_m1"]), t(G["trainer_m2"])
+    _, L, _, _ = RM.dafnet_generator_loss(W, c, x1, x2, z1, z2, eps, eps, m1, m2, supervised=True, training=False)
+    assert np.allclose([v.item() for v in L.values()], G["trainer_loss"], rtol=1e-4, atol=1e-6), (list(L), G["trainer_loss"])
+    _, Lu, _, _ = RM.dafnet_generator_loss(W, c, x1, x2, z1, z2, eps, eps, m1, None, supervised=False, training=False)
+    assert np.allclose([v.item() for v in Lu.values()], G["trainer_unsup_loss"], rtol=1e-4, atol=1e-6)
     for i, o in enumerate(outs):
         # outputs downstream of the TPS warp inherit its float32 sampling grid (see test_anatomy_fuser); one binarised
         # anatomy pixel on the 0.5 boundary would show up as an O(1) difference
@@ -224,6 +231,9 @@ def test_automated_pairing_graph_matches_the_reference_trainer(net):
     assert len(outs) == 20
     for i, o in enumerate(outs):
         close(o, "auto_out%02d" % i, 1e-4)
+    _, L, _, _ = RM.dafnet_generator_loss_automated(W, c, x1_lst, x2_lst, z1, z2, eps, eps, m1, m2, supervised=True,
+                                                    training=False)
+    assert np.allclose([v.item() for v in L.values()], G["auto_loss"], rtol=1e-4, atol=1e-6), (list(L), G["auto_loss"])
 
 
 def test_mmsdnet_graph_matches_the_reference_trainer():
@@ -253,3 +263,9 @@ def test_mmsdnet_graph_matches_the_reference_trainer():
     assert len(outs) == 24
     for i, o in enumerate(outs):
         close(o, "mmsd_out%02d" % i, 1e-4)
+    # loss list and weights of the supervised trainer (models/mmsdnet.py:181-190) on the executor's targets
+    # (model_executors/mmsdnet_executor.py:257-260): masks without the residual channel
+    m1, m2 = t(G["trainer_m1"])[..., :4], t(G["trainer_m2"])[..., :4]
+    _, L = RM.mmsdnet_generator_loss(W, c, x1, x2, [eps] * 6, [m1, m2, m2, m2, m1, m1], [x1, x2, x2, x2, x1, x1],
+                                     supervised=True, rounding=True, training=False)
+    assert np.allclose([v.item() for v in L.values()], G["mmsd_loss"], rtol=1e-4, atol=1e-6), (list(L), G["mmsd_loss"])
