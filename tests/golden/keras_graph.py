@@ -115,17 +115,23 @@ class Input(Sym):
 
 
 class Conv2D(Layer):
-    def __init__(self, filters, kernel_size, strides=1, padding="valid", activation=None, name=None, **kwargs):
+    def __init__(self, filters, kernel_size, strides=1, padding="valid", activation=None, name=None, use_bias=True,
+                 **kwargs):
         Layer.__init__(self, name)
         self.f, self.ks = int(filters), int(kernel_size if np.isscalar(kernel_size) else kernel_size[0])
         self.s = int(strides if np.isscalar(strides) else strides[0])
-        self.padding, self.activation = padding, activation
+        self.padding, self.activation, self.use_bias = padding, activation, use_bias
 
     def build(self, shape):
         cin = shape[-1]
         fan_in = self.ks * self.ks * cin
         self.kernel = self._draw((self.ks, self.ks, cin, self.f), 4.9 / 64.0 / np.sqrt(fan_in))
-        self.bias = self._draw((self.f,), 0.1 / 64.0)
+        self.bias = self._draw((self.f,), 0.1 / 64.0) if self.use_bias else 0.0
+
+    def assign(self, ws):
+        self.kernel = ws[0].astype(np.float64)
+        if self.use_bias:
+            self.bias = ws[1].astype(np.float64)
 
     def call(self, x):
         x = np.asarray(x, np.float64)
@@ -150,6 +156,9 @@ class Dense(Layer):
     def build(self, shape):
         self.kernel = self._draw((shape[-1], self.units), 4.9 / 64.0 / np.sqrt(shape[-1]))
         self.bias = self._draw((self.units,), 0.1 / 64.0)
+
+    def assign(self, ws):
+        self.kernel, self.bias = ws[0].astype(np.float64), ws[1].astype(np.float64)
 
     def call(self, x):
         return _act(np.asarray(x, np.float64) @ self.kernel + self.bias, self.activation)
@@ -267,17 +276,43 @@ def _freeze(fn):
 
 
 class Lambda(Layer):
-    def __init__(self, function, name=None, **kwargs):
+    """`arguments` may hold symbolic tensors (layers/spade.py:30 passes the tensor to resize to): they become extra inputs
+    of the node and are handed to the function by keyword when it runs"""
+
+    def __init__(self, function, name=None, arguments=None, **kwargs):
         Layer.__init__(self, name)
         self.fn = function
+        self.arguments = dict(arguments or {})
+        self.sym_keys = [k for k, v in self.arguments.items() if isinstance(v, Sym)]
 
     def __call__(self, x, **kwargs):
         if _has_sym(x):
             self.fn = _freeze(self.fn)
+            if self.sym_keys:
+                assert isinstance(x, Sym)
+                return sym_call(self, [x] + [self.arguments[k] for k in self.sym_keys])
         return Layer.__call__(self, x, **kwargs)
 
     def call(self, x):
-        return np.asarray(self.fn(x), np.float64)
+        if self.sym_keys:
+            kw = dict(self.arguments)
+            kw.update({k: _wrap(v) for k, v in zip(self.sym_keys, x[1:])})
+            return np.asarray(self.fn(_wrap(x[0]), **kw), np.float64)
+        return np.asarray(self.fn(x, **self.arguments), np.float64)
+
+
+class InstanceNormalization(Layer):
+    """keras_contrib 2.0.8, axis=None, no scale / centre: (x - mean) / (std + epsilon) over all of H, W, C per sample"""
+
+    def __init__(self, axis=None, epsilon=1e-3, center=True, scale=True, **kwargs):
+        Layer.__init__(self, kwargs.get("name"))
+        assert axis is None and not center and not scale
+        self.epsilon = epsilon
+
+    def call(self, x):
+        x = np.asarray(x, np.float64)
+        ax = tuple(range(1, x.ndim))
+        return (x - x.mean(ax, keepdims=True)) / (x.std(ax, keepdims=True) + self.epsilon)
 
 
 class Model(Layer):
@@ -378,3 +413,13 @@ class Model(Layer):
 
     def get_weights(self):
         return [w for l in self.weighted_layers() for w in l.w]
+
+    def set_weights(self, ws):
+        """replace the drawn weights (Conv2D / Dense layers), in get_weights order"""
+        pos = 0
+        for l in self.weighted_layers():
+            n = len(l.w)
+            l.w = [np.asarray(w, np.float32) for w in ws[pos:pos + n]]
+            l.assign(l.w)
+            pos += n
+        assert pos == len(ws)

@@ -227,6 +227,19 @@ def main():
     builders()
 
 
+def seeded_weights(shapes, seed):
+    """weight list drawn from (position, shape) alone: kernels ~ uniform integers scaled to He-like magnitude, biases
+    small; float32.  Shared by the generator and tests/test_oracle_builders.py."""
+    out = []
+    for j, shp in enumerate(shapes):
+        shp = tuple(int(v) for v in shp)
+        k = np.random.RandomState(seed + j).randint(-32, 33, size=shp).astype(np.float64)
+        fan_in = int(np.prod(shp[:-1])) if len(shp) > 1 else 0
+        scale = 4.9 / 64.0 / np.sqrt(fan_in) if fan_in else 0.1 / 64.0
+        out.append((k * scale).astype(np.float32))
+    return out
+
+
 class _Conf(dict):
     """attribute dictionary (easydict is not installed); the builders only read attributes"""
     __setattr__ = dict.__setitem__
@@ -414,6 +427,26 @@ def builders():
         # targets of the automated-pairing step (dafnet_executor.py:447-454): the *_Def outputs are losses already (ypred)
         atg = [axs[6], axs[7], zero, zero] + [ones] * 4 + [axs[0], axs[3], zero, zero] + [ones] * 4 + [zero, zero, axs[8], axs[9]]
         out["auto_loss"] = np.array(anet.supervised_trainer.loss_values(axs, atg))
+        # ---- SPADE decoder (model_components/decoder.py:67-81, layers/spade.py:7-55).  4.3 M parameters: instead of
+        #      storing them, every array of the model's weight list is re-drawn from its position and shape
+        #      (seeded_weights below); the test draws the same list for this repository's component
+        sys.modules["keras_contrib.layers"].InstanceNormalization = KG.InstanceNormalization
+        import importlib
+        from layers import spade as SPADE_MOD
+        importlib.reload(SPADE_MOD)                      # picks up the InstanceNormalization stand-in
+        importlib.reload(decoder)
+        sconf = _Conf(conf, decoder_type="spade", input_shape=(64, 64, 1),
+                      anatomy_encoder=_Conf(ae, input_shape=(64, 64, 1), output_shape=(64, 64, 8)))
+        KG.reset(401)
+        m = decoder.build(sconf)
+        a64 = rs.uniform(size=(1, 64, 64, 8))
+        sx = [(a64 == a64.max(-1, keepdims=True)).astype(np.float64), f32(rs.normal(size=(1, 8)))]
+        m.predict(sx)                                    # creates the layers' weights (shapes)
+        m.set_weights(seeded_weights([w.shape for w in m.get_weights()], 4010))
+        out["decoder_spade_in0"], out["decoder_spade_in1"] = sx[0].astype(np.uint8), sx[1].astype(np.float32)
+        out["decoder_spade_out0"] = np.asarray(m.predict(sx), np.float32)[:, ::2, ::2]
+        out["decoder_spade_nw"] = np.array(len(m.get_weights()))
+
         # ---- MMSDNet (models/mmsdnet.py:62-192): two independent anatomy encoders, one D_Mask, the deformed AND the fused
         #      anatomies segmented / re-encoded / decoded; supervised trainer, 24 outputs
         from models.mmsdnet import MMSDNet

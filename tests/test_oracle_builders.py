@@ -269,3 +269,21 @@ def test_mmsdnet_graph_matches_the_reference_trainer():
     _, L = RM.mmsdnet_generator_loss(W, c, x1, x2, [eps] * 6, [m1, m2, m2, m2, m1, m1], [x1, x2, x2, x2, x1, x1],
                                      supervised=True, rounding=True, training=False)
     assert np.allclose([v.item() for v in L.values()], G["mmsd_loss"], rtol=1e-4, atol=1e-6), (list(L), G["mmsd_loss"])
+
+
+def test_spade_decoder_matches_the_reference_builder():
+    """model_components/decoder.py:67-81 + layers/spade.py:7-55 (config 3): Dense -> 2x2x128, six SPADE blocks with
+    nearest-neighbour up-sampling, per-sample instance normalisation, anatomy resized to every resolution, learnt 1x1
+    shortcuts without bias.  The 4.3 M weights are not stored: both sides draw the same list from (position, shape)."""
+    from tests.golden.make_golden import seeded_weights
+    from multimodal_segmentation_b200.configuration import dafnet_config_chaos
+    from multimodal_segmentation_b200.keras_like import BuildScope, EasyDict
+    from multimodal_segmentation_b200.model_components import decoder
+    conf = EasyDict(dafnet_config_chaos.get((64, 64, 1), decoder_type="spade"))
+    with BuildScope(rng=np.random.RandomState(0)):
+        m = decoder.build(conf)
+    shapes = [tuple(p.shape) for p in m.weight_list()]
+    assert len(shapes) == int(G["decoder_spade_nw"])
+    m.set_weights(seeded_weights(shapes, 4010))
+    W = {k: t(v) for k, v in m.named_weights().items()}
+    close(RM.decoder_spade(W, t(G["decoder_spade_in0"]), t(G["decoder_spade_in1"]))[:, ::2, ::2], "decoder_spade_out0", 1e-5)
