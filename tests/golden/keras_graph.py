@@ -121,6 +121,7 @@ class Conv2D(Layer):
         self.f, self.ks = int(filters), int(kernel_size if np.isscalar(kernel_size) else kernel_size[0])
         self.s = int(strides if np.isscalar(strides) else strides[0])
         self.padding, self.activation, self.use_bias = padding, activation, use_bias
+        self.kernel_regularizer = kwargs.get("kernel_regularizer")
 
     def build(self, shape):
         cin = shape[-1]
@@ -413,6 +414,10 @@ class Model(Layer):
 
     def get_weights(self):
         return [w for l in self.weighted_layers() for w in l.w]
+
+    def regularized_layers(self):
+        """layers whose kernel carries a regulariser (Keras adds regulariser(kernel) to the model's total loss)"""
+        return [l for l in self.weighted_layers() if getattr(l, "kernel_regularizer", None) is not None]
 
     def set_weights(self, ws):
         """replace the drawn weights (Conv2D / Dense layers), in get_weights order"""

@@ -354,6 +354,7 @@ def builders():
                       d_image_params=_Conf(filters=4, lr=1e-4, name="D_Image", input_shape=(S, S, 1)),
                       w_sup_M=10, w_adv_M=1, w_rec_X=1, w_adv_X=1, w_rec_Z=1, w_kl=0.1, lr=1e-4, folder="/tmp/dafk_no_such_folder")
         KG.reset(201)
+        np.random.seed(2010)                 # layers/spectralnorm.py:213 draws its power-iteration vectors from numpy's RNG
         net = DAFNet(dconf)
         net.loader = _Conf(num_masks=4)
         net.build()
@@ -378,6 +379,17 @@ def builders():
         out["trainer_loss"] = np.array(net.supervised_trainer.loss_values(xs, tg))
         tgu = [lab1, lab1] + tg[4:]
         out["trainer_unsup_loss"] = np.array(net.unsupervised_trainer.loss_values(xs, tgu))
+        # the mask-discriminator trainer (models/mmsdnet.py:62-78): mse on D(real) / D(fake) against ones / zeros
+        # (dafnet_executor.py:530-534) plus, as Keras adds them, the Spectral regularisers of its convolutions evaluated on
+        # their kernels from the initial power-iteration vectors
+        real_m = lab1[..., :4]
+        fake_m = np.repeat(xs[0], 4, -1) * 0.5 + 0.5
+        dvals = net.D_Mask_trainer.loss_values([real_m, fake_m], [ones, zero])
+        regs = []
+        for j, l in enumerate(net.D_Mask.regularized_layers()):
+            out["dtrain_u0_%d" % j] = np.asarray(l.kernel_regularizer.u, np.float64).copy()
+            regs.append(float(np.asarray(l.kernel_regularizer(t(l.kernel)))))
+        out["dtrain_loss"] = np.array(dvals + regs)
         # inference entry point (models/mmsdnet.py:210-232, inherited by DAFNet): all four fusion types
         for mi, types_ in ((1, ("simple", "def", "max", "maxnostn")), (0, ("simple", "def"))):
             for ty in types_:

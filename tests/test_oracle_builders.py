@@ -209,6 +209,20 @@ def test_predict_mask_matches_the_reference_method(net, mi, ty):
     close(RM.predict_mask(W, mi, ty, x), "predict_mask_%d_%s" % (mi, ty), 1e-4)
 
 
+def test_mask_discriminator_trainer_loss_matches_the_reference(net):
+    """models/mmsdnet.py:62-78 + models/discriminator.py:36-41 + layers/spectralnorm.py:199-239: mse(D(real), 1),
+    mse(D(fake), 0) and the three Spectral regularisation terms Keras adds for the regularised kernels"""
+    W = _expert_weights(net)
+    real = t(G["trainer_m1"])[..., :4]
+    fake = t(np.repeat(G["trainer_in0"].astype(np.float64), 4, -1) * 0.5 + 0.5)
+    u0s = [t(G["dtrain_u0_%d" % j]) for j in range(3)]
+    total, (lr, lf, reg) = RM.discriminator_trainer_loss(W, "D_Mask", real, fake, u0s)
+    g = G["dtrain_loss"]
+    assert len(g) == 5
+    assert np.allclose([lr.item(), lf.item()], g[:2], rtol=1e-6)
+    assert np.isclose(reg.item(), g[2:].sum(), rtol=1e-6) and np.isclose(total.item(), g.sum(), rtol=1e-6)
+
+
 def test_automated_pairing_graph_matches_the_reference_trainer(net):
     """models/dafnet.py:224-334,352-361: three candidates per modality, Balancer weights, per-sample dice + swapped
     per-batch cross entropy and `mae_single_input` combined INSIDE the graph -- the reference trainer's 20 outputs against
