@@ -439,6 +439,10 @@ def builders():
         # targets of the automated-pairing step (dafnet_executor.py:447-454): the *_Def outputs are losses already (ypred)
         atg = [axs[6], axs[7], zero, zero] + [ones] * 4 + [axs[0], axs[3], zero, zero] + [ones] * 4 + [zero, zero, axs[8], axs[9]]
         out["auto_loss"] = np.array(anet.supervised_trainer.loss_values(axs, atg))
+        # unsupervised variant (no m2 input, 18 outputs; dafnet_executor.py:470-477)
+        uaxs = axs[:7] + axs[8:]
+        uatg = [axs[6], zero] + atg[4:]
+        out["auto_unsup_loss"] = np.array(anet.unsupervised_trainer.loss_values(uaxs, uatg))
         # ---- SPADE decoder (model_components/decoder.py:67-81, layers/spade.py:7-55).  4.3 M parameters: instead of
         #      storing them, every array of the model's weight list is re-drawn from its position and shape
         #      (seeded_weights below); the test draws the same list for this repository's component

@@ -248,6 +248,10 @@ def test_automated_pairing_graph_matches_the_reference_trainer(net):
     _, L, _, _ = RM.dafnet_generator_loss_automated(W, c, x1_lst, x2_lst, z1, z2, eps, eps, m1, m2, supervised=True,
                                                     training=False)
     assert np.allclose([v.item() for v in L.values()], G["auto_loss"], rtol=1e-4, atol=1e-6), (list(L), G["auto_loss"])
+    # unsupervised variant: no masks of modality 2, 18 outputs
+    _, Lu, _, _ = RM.dafnet_generator_loss_automated(W, c, x1_lst, x2_lst, z1, z2, eps, eps, m1, None, supervised=False,
+                                                     training=False)
+    assert np.allclose([v.item() for v in Lu.values()], G["auto_unsup_loss"], rtol=1e-4, atol=1e-6)
 
 
 def test_mmsdnet_graph_matches_the_reference_trainer():
