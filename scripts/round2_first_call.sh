@@ -13,6 +13,8 @@ export DAFK_TEST_EXPERIMENTAL=1
   timeout 100 python -m pytest tests/test_conv_tc_gpu.py -m gpu -q -k wide_tile 2>&1 | tail -5
   echo "== 12-warp raster-strip layout (DAFK_NC_L12)"
   timeout 150 python -m pytest tests/test_conv_nc_gpu.py -m gpu -q -k twelve 2>&1 | tail -5
+  echo "== CUDA components against the reference builders' outputs"
+  timeout 200 python -m pytest tests/test_zz_reference_builders_gpu.py -m gpu -q 2>&1 | tail -12
   echo "== costs.py functional helpers"
   timeout 100 python -m pytest tests/test_costs_gpu.py -m gpu -q 2>&1 | tail -8
   echo "== bf16 decoder (DAFK_DEC_BF16), decoder-level comparison"
