@@ -6,10 +6,20 @@ semantics listed in SURVEY.md Appendix A (Keras 2.1.6, tensorflow 1.4.0, keras-c
 none of which are vendored in /root/reference or installable here).
 
 PARITY PINNING: the reference has no tests, golden vectors or fixtures, and its TF 1.4 stack
-cannot run in this image, so this oracle is "parity unpinned" by the reference's own artefacts.
-It is pinned instead by (tests/test_oracle_*.py): known-answer tests derivable from the reference
-code alone, independent cross-oracles (scipy RBFInterpolator, torch grid_sample, np.round, a
-second pure-numpy loop implementation of conv / BN / pooling) and fp64 finite-difference checks.
+cannot run in this image.  What pins this oracle:
+  * the reference's OWN Python source, imported unmodified from /root/reference on numpy stand-ins
+    for the TF / Keras entry points it calls (tests/golden/make_golden.py, tf_shim.py,
+    keras_graph.py), produced the committed golden vectors:
+      - golden_ref.npz: the custom layers, losses and host-side data functions
+        (tests/test_oracle_golden.py, tests/test_data_host.py, tests/test_swa.py);
+      - golden_builders.npz: every component builder, the DAFNet (expert / unsupervised /
+        automated-pairing) and MMSDNet generator graphs with their compiled losses and weights,
+        predict_mask, the discriminator trainer (tests/test_oracle_builders.py);
+  * for the arithmetic that lives INSIDE TF / Keras ops (Conv2D, BatchNormalization statistics,
+    pooling, Adam, the resampler), which no reference artefact can pin here ("parity unpinned"
+    for those): known-answer tests, independent cross-oracles (scipy RBFInterpolator, torch
+    grid_sample, np.round, a second pure-numpy loop implementation of conv / BN / pooling) and
+    fp64 finite-difference checks (tests/test_oracle_kat.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this package.
