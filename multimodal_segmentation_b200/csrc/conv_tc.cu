@@ -14,6 +14,7 @@
 //     both operands are the same 128-pixel boxes used as MN-major UMMA operands (the reduction
 //     runs over pixels), split-K over pixel tiles, fp32 atomics into the HWIO gradient.
 #include "tc_ptx.cuh"
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -945,7 +946,7 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
                       long long y_sx, int act, cudaStream_t s) {
   constexpr int smem = STAGES * (A_BYTES + BLOCK_N * KBLK * 2) + 1024 + 256;
   static_assert(smem > 116 * 1024 && smem <= 227 * 1024, "one persistent CTA per SM");
-  static bool configured = false;
+  static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_fwd_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_fwd) failed: %s", cudaGetErrorString(e));
@@ -1073,7 +1074,7 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
                        long long y_sx, int act, cudaStream_t s) {
   const int ncb_all = (C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK;
   const int smem = g.SA * g.a_bytes + (g.w_resident ? ncb_all * KH * KW : g.SB) * BLOCK_N * KBLK * 2 + 1024 + 512;
-  static bool configured = false;
+  static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_halo) failed: %s", cudaGetErrorString(e));
@@ -1098,7 +1099,7 @@ static int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   const int ncb_all = (C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK;
   const int smem = g.SA * g.a_bytes + ncb_all * KH * KW * (BLOCK_N / 2) * KBLK * 2 + 1024 + 512;
   DAFK_REQUIRE(smem <= 227 * 1024, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd(halo2): %d bytes of shared memory", smem);
-  static bool configured = false;
+  static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_halo2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_halo2) failed: %s", cudaGetErrorString(e));
@@ -1119,7 +1120,7 @@ template <int BM, int BN, int STAGES>
 static int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mdy, float* dw, int Cin, int cin_off, int cin_total,
                         int Cout, int KH, int KW, int stride, int pad, const TileGeom& g, cudaStream_t s) {
   constexpr int smem = STAGES * ((BM / 64) + (BN / 64)) * A_BYTES + 1024 + 256;
-  static bool configured = false;
+  static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<BM, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_wgrad) failed: %s", cudaGetErrorString(e));

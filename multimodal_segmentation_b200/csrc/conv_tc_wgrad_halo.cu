@@ -17,6 +17,7 @@
 // Operand bytes per tile fall from 9 x 32 KB to 38.5 KB, the MMAs run at M = 128.
 //   warp 0: TMA producer    warps 1, 6: MMA issuers (warp-uniform, one elected lane each)    warps 2-5: epilogue
 #include "tc_ptx.cuh"
+#include <atomic>
 
 namespace dafk {
 
@@ -205,7 +206,7 @@ int dafk_conv3x3_tc_wgrad_halo(const void* x, int Cin, int cin_off, int cin_tota
   if (rc) return rc;
   rc = wh_make_map(&mdy, dy, N, H, W, Cout, WH_TW, WH_TH);
   if (rc) return rc;
-  static bool configured = false;
+  static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM);
     DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_wgrad_halo) failed: %s", cudaGetErrorString(e));
