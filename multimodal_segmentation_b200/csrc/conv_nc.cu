@@ -21,6 +21,7 @@
 //       operand whose 8 "M groups" are the taps q = 0..7 of one filter row (group stride = 16 B = one
 //       position), dY the MN-major B operand, K = positions; accumulated in TMEM over all strips of a CTA.
 #include "tc_ptx.cuh"
+#include <mutex>
 
 namespace dafk {
 
@@ -747,8 +748,10 @@ static bool nc_wg_geom(NcWgP& p, size_t& smem) {
 // done at the first launch and never again -- later launches may be inside a CUDA-graph capture)
 template <typename K>
 static int nc_set_smem(K kernel, size_t smem, const char* name) {
+  static std::mutex mu;
   static const void* done[16];
   static int ndone = 0;
+  std::lock_guard<std::mutex> lk(mu);
   const void* key = reinterpret_cast<const void*>(kernel);
   for (int i = 0; i < ndone; ++i)
     if (done[i] == key) return DAFK_OK;
