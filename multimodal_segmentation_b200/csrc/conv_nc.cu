@@ -21,6 +21,7 @@
 //       operand whose 8 "M groups" are the taps q = 0..7 of one filter row (group stride = 16 B = one
 //       position), dY the MN-major B operand, K = positions; accumulated in TMEM over all strips of a CTA.
 #include "tc_ptx.cuh"
+#include <atomic>
 #include <mutex>
 
 namespace dafk {
@@ -705,7 +706,7 @@ static bool nc_wg_geom(NcWgP& p, size_t& smem) {
   while (p.tmem_cols < cols) p.tmem_cols <<= 1;
   const size_t fixed = (size_t)NC_PROD * 8 * 4 + 256 + 256;
   {
-    static int fold_ok = -2;
+    static std::atomic<int> fold_ok{-2};       // lazily read once; a race only repeats the getenv
     if (fold_ok == -2) { const char* e = getenv("DAFK_NC_WG_FOLD"); fold_ok = e ? atoi(e) : 1; }
     p.fold = (fold_ok && p.COG == 1 && p.KH > 1 && p.KH * 8 <= 256) ? 1 : 0;
   }

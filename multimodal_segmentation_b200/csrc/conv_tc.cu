@@ -879,7 +879,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
+  static std::atomic<PFN_encodeTiled> fn{nullptr};   // a race only repeats the lookup
   if (!fn) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -1175,14 +1175,14 @@ static int conv_tc_fwd_impl(const void* x0, int C0, const void* x1, int C1, cons
   // tap; take it when the estimate says so (DAFK_CONV_HALO=0/1 forces the choice, for the tests and benchmarks)
   const int Kpad = ((C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK) * KBLK;     // K extent of the packed weights
   if (stride == 1 && H == Ho + KH - 1 - 2 * pad && W == Wo + KW - 1 - 2 * pad) {
-    static int force = -2;
+    static std::atomic<int> force{-2};         // lazily read once; a race only repeats the getenv
     if (force == -2) { const char* e = getenv("DAFK_CONV_HALO"); force = e ? atoi(e) : -1; }
     const int bn = Cout % 128 == 0 ? 128 : 64;
     HaloGeom hg;
     double ch = pick_halo_geom(N, Ho, Wo, KH, KW, bn, (Cout + bn - 1) / bn, &hg);
     {
       // resident weights: one output-channel block and all (channel block, tap) tiles fit beside a 2-deep activation ring
-      static int wres_ok = -2;
+      static std::atomic<int> wres_ok{-2};
       if (wres_ok == -2) { const char* e = getenv("DAFK_CONV_WRES"); wres_ok = e ? atoi(e) : 1; }
       const int w_bytes = (Kpad / KBLK) * taps * bn * KBLK * 2;
       if (wres_ok && Cout <= bn && w_bytes <= 150 * 1024) {

@@ -159,7 +159,7 @@ typedef CUresult (*PFN_encodeTiledWH)(CUtensorMap*, CUtensorMapDataType, cuuint3
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static PFN_encodeTiledWH wh_get_encode() {
-  static PFN_encodeTiledWH fn = nullptr;
+  static std::atomic<PFN_encodeTiledWH> fn{nullptr};   // a race only repeats the lookup
   if (!fn) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qres;
