@@ -15,6 +15,8 @@ export DAFK_TEST_EXPERIMENTAL=1
   timeout 150 python -m pytest tests/test_conv_nc_gpu.py -m gpu -q -k twelve 2>&1 | tail -5
   echo "== CUDA components against the reference builders' outputs"
   timeout 200 python -m pytest tests/test_zz_reference_builders_gpu.py -m gpu -q 2>&1 | tail -12
+  echo "== setmaxnreg register split of the raster-strip kernel (DAFK_NC_L16)"
+  timeout 150 python -m pytest tests/test_conv_nc_gpu.py -m gpu -q -k register_split 2>&1 | tail -5
   echo "== costs.py functional helpers"
   timeout 100 python -m pytest tests/test_costs_gpu.py -m gpu -q 2>&1 | tail -8
   echo "== bf16 decoder (DAFK_DEC_BF16), decoder-level comparison"
@@ -31,6 +33,9 @@ export DAFK_TEST_EXPERIMENTAL=1
     DAFK_WGRAD_BN256=$v timeout 120 python scripts/bench_tc.py "@28" 20 2>&1 | tail -6
     DAFK_WGRAD_BN256=$v timeout 120 python scripts/bench_tc.py "@14" 20 2>&1 | tail -4
   done
+  echo "== DAFK_NC_L16=1"
+  DAFK_NC_L16=1 timeout 60 python scripts/bench_nc.py film8x8 50 2>&1 | tail -3
+  DAFK_NC_L16=1 timeout 60 python scripts/bench_nc.py seg8x64 50 2>&1 | tail -3
   for v in 0 1; do
     echo "== DAFK_NC_L12=$v"
     DAFK_NC_L12=$v timeout 60 python scripts/bench_nc.py film8x8 50 2>&1 | tail -3
