@@ -55,6 +55,41 @@ def _adam(W, names, state, lr=1e-4):
         W[n] = torch.from_numpy(p.astype(np.float32))
 
 
+def mask_d_candidates(Wd, x1, x2, nm):
+    """model_executors/dafnet_executor.py:511-545: the fake masks the two D_Mask updates draw from, BEFORE
+    utils.data_utils.sample picks batch_size of them -- modality 1: [Segmentor(s1), Segmentor(Fuser([s2, s1])[0])],
+    modality 2: [Segmentor(s2), Segmentor(Fuser([s1, s2])[0])], each cut to the first `nm` channels and concatenated on
+    the batch axis; inference phase."""
+    inf = RM.BNState(Wd, training=False)
+    s1 = RM.anatomy_encoder(Wd, x1, inf, "enc1_", "shared_")
+    s2 = RM.anatomy_encoder(Wd, x2, inf, "enc2_", "shared_")
+    out = []
+    for s_own, s_a, s_b in ((s1, s2, s1), (s2, s1, s2)):
+        fm = RM.segmentor(Wd, s_own, inf)
+        sdef = RM.anatomy_fuser(Wd, s_a, s_b)[0]
+        fmd = RM.segmentor(Wd, sdef, inf)
+        out.append(torch.cat([fm[..., :nm], fmd[..., :nm]], 0))
+    return out
+
+
+def image_d_candidates(Wd, x1, x2, eps1, eps2, decoder_type="film"):
+    """model_executors/dafnet_executor.py:547-583: the fake images of the two D_Image updates before sampling --
+    y1 = [Dec(s1, z1), Dec(s2_def, z1), Dec(s1_def, z1)], y2 = [Dec(s2, z2), Dec(s1_def, z2), Dec(s2_def, z2)] with
+    s1_def = Fuser([s1, s2])[0], s2_def = Fuser([s2, s1])[0], z_i the SAMPLED code of Enc_Modality([s_i, x_i])."""
+    inf = RM.BNState(Wd, training=False)
+    s1 = RM.anatomy_encoder(Wd, x1, inf, "enc1_", "shared_")
+    s2 = RM.anatomy_encoder(Wd, x2, inf, "enc2_", "shared_")
+    s1d = RM.anatomy_fuser(Wd, s1, s2)[0]
+    s2d = RM.anatomy_fuser(Wd, s2, s1)[0]
+    mu1, lv1 = RM.modality_encoder(Wd, s1, x1)
+    mu2, lv2 = RM.modality_encoder(Wd, s2, x2)
+    z1 = R.sampling(mu1, lv1, eps1)
+    z2 = R.sampling(mu2, lv2, eps2)
+    y1 = torch.cat([RM.decoder(Wd, a, z1, decoder_type) for a in (s1, s2d, s1d)], 0)
+    y2 = torch.cat([RM.decoder(Wd, a, z2, decoder_type) for a in (s2, s1d, s2d)], 0)
+    return y1, y2
+
+
 def dafnet_train_batch_cpu(conf, B, seed=0):
     from multimodal_segmentation_b200.loaders.synthetic_chaos import make_pairs
     W = dict(_weights(conf))
@@ -78,26 +113,13 @@ def dafnet_train_batch_cpu(conf, B, seed=0):
         W[name + "/" + key] = v
     with torch.no_grad():
         Wd = {k: v.detach() for k, v in W.items()}
-        inf = RM.BNState(Wd, training=False)
         # ---- mask discriminator x2 (dafnet_executor.py:511-545)
-        s1 = RM.anatomy_encoder(Wd, T(x1), inf, "enc1_", "shared_")
-        s2 = RM.anatomy_encoder(Wd, T(x2), inf, "enc2_", "shared_")
-        fakes_m = []
-        for s_own, s_a, s_b in ((s1, s2, s1), (s2, s1, s2)):
-            fm = RM.segmentor(Wd, s_own, inf)
-            sdef = RM.anatomy_fuser(Wd, s_a, s_b)[0]
-            fmd = RM.segmentor(Wd, sdef, inf)
-            cat = torch.cat([fm[..., :nm], fmd[..., :nm]], 0)
-            fakes_m.append(cat[rs.choice(2 * B, B, replace=False)])
+        fakes_m = [cat[rs.choice(2 * B, B, replace=False)] for cat in mask_d_candidates(Wd, T(x1), T(x2), nm)]
         # ---- image discriminators (dafnet_executor.py:547-583)
-        s1d = RM.anatomy_fuser(Wd, s1, s2)[0]
-        s2d = RM.anatomy_fuser(Wd, s2, s1)[0]
-        mu1, lv1 = RM.modality_encoder(Wd, s1, T(x1))
-        mu2, lv2 = RM.modality_encoder(Wd, s2, T(x2))
-        z1 = R.sampling(mu1, lv1, T(rs.normal(size=(B, conf.num_z))))
-        z2 = R.sampling(mu2, lv2, T(rs.normal(size=(B, conf.num_z))))
-        y1 = torch.cat([RM.decoder(Wd, a, z1, conf.decoder_type) for a in (s1, s2d, s1d)], 0)[rs.choice(3 * B, B, replace=False)]
-        y2 = torch.cat([RM.decoder(Wd, a, z2, conf.decoder_type) for a in (s2, s1d, s2d)], 0)[rs.choice(3 * B, B, replace=False)]
+        e1, e2 = T(rs.normal(size=(B, conf.num_z))), T(rs.normal(size=(B, conf.num_z)))
+        c1, c2 = image_d_candidates(Wd, T(x1), T(x2), e1, e2, conf.decoder_type)
+        y1 = c1[rs.choice(3 * B, B, replace=False)]
+        y2 = c2[rs.choice(3 * B, B, replace=False)]
     for name, real, fake in (("D_Mask", T(m1), fakes_m[0]), ("D_Mask", T(m2), fakes_m[1]),
                              ("D_Image1", T(x1), y1), ("D_Image2", T(x2), y2)):
         names = [k for k in W if k.startswith(name + "_")]

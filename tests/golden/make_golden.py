@@ -390,6 +390,37 @@ def builders():
             out["dtrain_u0_%d" % j] = np.asarray(l.kernel_regularizer.u, np.float64).copy()
             regs.append(float(np.asarray(l.kernel_regularizer(t(l.kernel)))))
         out["dtrain_loss"] = np.array(dvals + regs)
+        # ---- the executor's discriminator steps (model_executors/dafnet_executor.py:511-583), run unmodified on this
+        #      network: which predictions are concatenated, in which order, before utils.data_utils.sample draws the fakes.
+        #      `fit` of the stand-in records what it is fed.
+        import itertools
+        for name, attr in (("callbacks.dafnet_image_callback", "DAFNetImageCallback"), ("callbacks.loss_callback", "SaveLoss")):
+            sys.modules[name] = types.ModuleType(name)
+            setattr(sys.modules[name], attr, object)
+        from model_executors.dafnet_executor import DAFNetExecutor
+        ex = object.__new__(DAFNetExecutor)
+        ex.conf, ex.model, ex.loader = dconf, net, _Conf(num_masks=4)
+        dx = [f32(rs.uniform(-1, 1, size=(2, S, S, 1))) for _ in range(2)]
+        dm = [np.eye(5)[rs.randint(0, 5, size=(2, S, S))] for _ in range(2)]
+        out["dstep_x1"], out["dstep_x2"] = dx[0].astype(np.float32), dx[1].astype(np.float32)
+        out["dstep_m1"], out["dstep_m2"] = dm[0].astype(np.uint8), dm[1].astype(np.uint8)
+        ex.discriminator_masks = itertools.cycle(dm)
+        ex.discriminator_image = [itertools.cycle([dx[0]]), itertools.cycle([dx[1]])]
+        from collections import defaultdict
+        np.random.seed(31)
+        ex.train_batch_mask_discriminator(defaultdict(list))
+        np.random.seed(32)
+        ex.train_batch_image_discriminator(defaultdict(list))
+        (r1, f1), _ = net.D_Mask_trainer.fit_calls[-2]
+        (r2, f2), _ = net.D_Mask_trainer.fit_calls[-1]
+        out["dstep_mask_real1"], out["dstep_mask_real2"] = r1.astype(np.uint8), r2.astype(np.uint8)
+        out["dstep_mask_fake1"], out["dstep_mask_fake2"] = f1.astype(np.float32), f2.astype(np.float32)
+        (xr1, y1f), tg1 = net.D_Image1_trainer.fit_calls[-1]
+        (xr2, y2f), tg2 = net.D_Image2_trainer.fit_calls[-1]
+        assert np.array_equal(xr1, dx[0]) and np.array_equal(xr2, dx[1])
+        assert np.all(tg1[0] == 1) and np.all(tg1[1] == 0)
+        out["dstep_img_fake1"], out["dstep_img_fake2"] = y1f.astype(np.float32), y2f.astype(np.float32)
+
         # inference entry point (models/mmsdnet.py:210-232, inherited by DAFNet): all four fusion types
         for mi, types_ in ((1, ("simple", "def", "max", "maxnostn")), (0, ("simple", "def"))):
             for ty in types_:

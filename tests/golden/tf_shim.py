@@ -214,7 +214,14 @@ class _Layer(object):
         # arrays coming out of the numpy graph layers get the little bit of tf.Tensor surface back
         x = [t(v) if isinstance(v, np.ndarray) else v for v in x] if isinstance(x, (list, tuple)) else (
             t(x) if isinstance(x, np.ndarray) else x)
-        return self.call(x, **kwargs)
+        # Keras executes `call` ONCE, while the graph is built; here it runs at every evaluation.  Graph-construction side
+        # effects on numpy's global generator (layers/rounding.py:22 draws a random op name) must therefore not leak into
+        # the data path of a training step (utils.data_utils.sample draws from the same generator).
+        state = np.random.get_state()
+        try:
+            return self.call(x, **kwargs)
+        finally:
+            np.random.set_state(state)
 
 
 class _Dummy(object):

@@ -223,6 +223,30 @@ def test_mask_discriminator_trainer_loss_matches_the_reference(net):
     assert np.isclose(reg.item(), g[2:].sum(), rtol=1e-6) and np.isclose(total.item(), g.sum(), rtol=1e-6)
 
 
+def test_discriminator_step_fakes_match_the_reference_executor(net):
+    """model_executors/dafnet_executor.py:511-583 (`train_batch_mask_discriminator`, `train_batch_image_discriminator`)
+    run UNMODIFIED on the reference network of the golden run, its trainers' `fit` recording what they are fed: the real
+    and fake batches of the two D_Mask and the two D_Image updates against the oracle's restatement of the fake
+    generation (oracle/ref_step.py, the CPU-baseline step) followed by this repository's `data_utils.sample`"""
+    from oracle import ref_step as RS
+    from multimodal_segmentation_b200.utils import data_utils
+    W = _expert_weights(net)
+    x1, x2 = t(G["dstep_x1"]), t(G["dstep_x2"])
+    # reals: the executor draws two mask batches in a row and keeps the organ channels
+    assert np.array_equal(G["dstep_mask_real1"], G["dstep_m1"][..., :4]) and np.array_equal(G["dstep_mask_real2"], G["dstep_m2"][..., :4])
+    c1, c2 = RS.mask_d_candidates(W, x1, x2, 4)
+    np.random.seed(31)
+    f1 = data_utils.sample(c1.numpy(), 2)
+    f2 = data_utils.sample(c2.numpy(), 2)
+    close(f1, "dstep_mask_fake1", 1e-4)
+    close(f2, "dstep_mask_fake2", 1e-4)
+    eps = t(G["trainer_in4"]).expand(2, -1)
+    y1, y2 = RS.image_d_candidates(W, x1, x2, eps, eps)
+    np.random.seed(32)
+    close(data_utils.sample(y1.numpy(), 2), "dstep_img_fake1", 1e-4)
+    close(data_utils.sample(y2.numpy(), 2), "dstep_img_fake2", 1e-4)
+
+
 def test_automated_pairing_graph_matches_the_reference_trainer(net):
     """models/dafnet.py:224-334,352-361: three candidates per modality, Balancer weights, per-sample dice + swapped
     per-batch cross entropy and `mae_single_input` combined INSIDE the graph -- the reference trainer's 20 outputs against
