@@ -396,6 +396,7 @@ class Model(Layer):
         if not hasattr(self, "fit_calls"):
             self.fit_calls = []
         self.fit_calls.append((xs, ys))
+        STATE.setdefault("fit_log", []).append(str(self.name))
         vals = self.loss_values(xs, [v.reshape(v.shape[0], -1) if v.ndim == 1 else v for v in ys])
         h = _H()
         h.history = {"loss": [float(np.sum(vals))]}

@@ -421,6 +421,37 @@ def builders():
         assert np.all(tg1[0] == 1) and np.all(tg1[1] == 0)
         out["dstep_img_fake1"], out["dstep_img_fake2"] = y1f.astype(np.float32), y2f.astype(np.float32)
 
+        # ---- the generator steps of the executor, run unmodified (dafnet_executor.py:389-432,482-500): the targets it
+        #      feeds must be the convention used for `tg` / `tgu` above (the oracle's loss functions take the same)
+        gx1, gx2 = f32(rs.uniform(-1, 1, size=(2, S, S, 1))), f32(rs.uniform(-1, 1, size=(2, S, S, 1)))
+        gm1 = np.eye(5)[rs.randint(0, 5, size=(2, S, S))][..., :4]
+        gm2 = np.eye(5)[rs.randint(0, 5, size=(2, S, S))][..., :4]
+        ex.gen_labelled = itertools.cycle([(gx1, gx2, gm1, gm2)])
+        ex.gen_unlabelled = itertools.cycle([(gx1, gx2, gm1)])
+        np.random.seed(33)
+        ex.train_supervised_expert_pairing(defaultdict(list))
+        (i_x1, i_x2, i_z1, i_z2), tgs = net.supervised_trainer.fit_calls[-1]
+        res = lambda m: np.concatenate([m, 1 - m.sum(-1, keepdims=True)], -1)       # base_executor.add_residual on one-hot
+        np.random.seed(33)
+        z1_expect, z2_expect = np.random.normal(0, 1, (2, 8)), np.random.normal(0, 1, (2, 8))
+        assert np.array_equal(i_x1, gx1) and np.array_equal(i_x2, gx2)
+        assert np.array_equal(i_z1, z1_expect) and np.array_equal(i_z2, z2_expect)
+        expect = [res(gm1), res(gm2), res(gm1), res(gm2)] + [np.ones((2, 1))] * 4 + [gx1, gx2, gx1, gx2] + \
+            [np.ones((2, 1))] * 4 + [np.zeros(2), np.zeros(2), z1_expect, z2_expect]
+        assert len(tgs) == 20 and all(np.array_equal(a, b) for a, b in zip(tgs, expect))
+        ex.train_unsupervised_expert_pairing(defaultdict(list))
+        _, tgs_u = net.unsupervised_trainer.fit_calls[-1]
+        assert len(tgs_u) == 18 and np.array_equal(tgs_u[0], res(gm1)) and np.array_equal(tgs_u[1], res(gm1))
+        assert all(np.array_equal(a, b) for a, b in zip(tgs_u[2:14], expect[4:16]))
+        out["executor_targets_checked"] = np.array(1)
+        # the step schedule itself (dafnet_executor.py:369-387): which trainer is fitted in which order by train_batch
+        net.supervised_trainer.name, net.unsupervised_trainer.name = "supervised_trainer", "unsupervised_trainer"
+        for lm in (1, 0.5, 0):
+            KG.STATE["fit_log"] = []
+            ex.conf = _Conf(dconf, l_mix=lm)
+            ex.train_batch(defaultdict(list))
+            out["schedule_l_mix_%s" % lm] = np.array(KG.STATE["fit_log"])
+        ex.conf = dconf
         # inference entry point (models/mmsdnet.py:210-232, inherited by DAFNet): all four fusion types
         for mi, types_ in ((1, ("simple", "def", "max", "maxnostn")), (0, ("simple", "def"))):
             for ty in types_:

@@ -329,3 +329,16 @@ def test_spade_decoder_matches_the_reference_builder():
     m.set_weights(seeded_weights(shapes, 4010))
     W = {k: t(v) for k, v in m.named_weights().items()}
     close(RM.decoder_spade(W, t(G["decoder_spade_in0"]), t(G["decoder_spade_in1"]))[:, ::2, ::2], "decoder_spade_out0", 1e-5)
+
+
+def test_step_schedule_of_the_reference_executor():
+    """model_executors/dafnet_executor.py:369-387 `train_batch`, run unmodified with recording trainers: one generator
+    update, two mask-discriminator updates, the two image-discriminator updates -- once per labelled / unlabelled branch.
+    This is the order DAFNetExecutor.train_batch_on replays (multimodal_segmentation_b200/model_executors/dafnet_executor.py)
+    and oracle/ref_step.py restates; the generator-step inputs and targets were asserted inside the generator
+    (tests/golden/make_golden.py, "executor_targets_checked")."""
+    assert int(G["executor_targets_checked"]) == 1
+    d_steps = ["D_Mask_trainer", "D_Mask_trainer", "D_Image1_trainer", "D_Image2_trainer"]
+    assert list(G["schedule_l_mix_1"]) == ["supervised_trainer"] + d_steps
+    assert list(G["schedule_l_mix_0"]) == ["unsupervised_trainer"] + d_steps
+    assert list(G["schedule_l_mix_0.5"]) == ["supervised_trainer"] + d_steps + ["unsupervised_trainer"] + d_steps
