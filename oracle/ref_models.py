@@ -447,6 +447,13 @@ def mmsdnet_generator_loss(W, conf, x1, x2, eps, seg_targets, rec_targets, super
     return sum(L.values()), L
 
 
+def z_regressor(W, s_list, z_list, decoder_type="film"):
+    """models/mmsdnet.py:194-208 / models/dafnet.py:336-350 `build_z_regressor`: every sampled code z_i is decoded on its
+    anatomy s_i and re-encoded; returns the list of z_mean(Enc_Modality([s_i, Decoder([s_i, z_i])])) the trainer compares
+    with z_i under 'mae' (weight w_rec_Z each)"""
+    return [modality_encoder(W, s, decoder(W, s, z, decoder_type))[0] for s, z in zip(s_list, z_list)]
+
+
 def predict_mask_simple(W, x, down_prefix, up_prefix):
     """models/mmsdnet.py:210-224 type 'simple': Segmentor(Enc_Anatomy(x)) in inference phase"""
     st = BNState(W, training=False)

@@ -540,6 +540,14 @@ def builders():
         for tag, m in (("enc1", mnet.Encoders_Anatomy[0]), ("enc2", mnet.Encoders_Anatomy[1]), ("encm", mnet.Enc_Modality),
                        ("fuser", mnet.Anatomy_Fuser), ("seg", mnet.Segmentor), ("dec", mnet.Decoder), ("dmask", mnet.D_Mask)):
             record("mmsd_" + tag, m, [], [])
+        # the six-input Z regressor (models/mmsdnet.py:194-208): anatomies = one stored map with its channels rolled
+        za = anatomy(1)
+        out["mmsd_zreg_s"] = za.astype(np.uint8)
+        zs = [f32(rs.normal(size=(1, 8))) for _ in range(6)]
+        out["mmsd_zreg_z"] = np.concatenate(zs, 0).astype(np.float32)
+        zr = mnet.Z_Regressor.predict([np.roll(za, i, axis=-1) for i in range(6)] + zs)
+        out["mmsd_zreg_out"] = np.concatenate(zr, 0).astype(np.float32)
+        out["mmsd_zreg_loss"] = np.array(mnet.Z_Regressor.loss_values([np.roll(za, i, axis=-1) for i in range(6)] + zs, zs))
         # loss list of the supervised trainer (models/mmsdnet.py:181-190) on the executor's targets
         # (model_executors/mmsdnet_executor.py:257-260): masks of modality 1, 2, then 2, 2, 1, 1 for the deformed / fused
         # anatomies; images x1, x2, x2, x2, x1, x1

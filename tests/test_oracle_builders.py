@@ -299,12 +299,19 @@ def test_mmsdnet_graph_matches_the_reference_trainer():
     x1, x2, eps = t(G["trainer_in0"]), t(G["trainer_in1"]), t(G["trainer_in4"])
     dummy_m = [torch.zeros(x1.shape[0], S, S, 5, dtype=torch.float64)] * 6
     dummy_x = [x1] * 6
-    c = dict(num_masks=4, decoder_type="film", w_sup_M=10, w_adv_M=1, w_rec_X=1, w_kl=0.1)
+    c = dict(num_masks=4, decoder_type="film", w_sup_M=10, w_adv_M=1, w_rec_X=1, w_kl=0.1, w_rec_Z=1)
     _, _, outs = RM.mmsdnet_generator_loss(W, c, x1, x2, [eps] * 6, dummy_m, dummy_x, supervised=True, rounding=True,
                                            training=False, return_outputs=True)
     assert len(outs) == 24
     for i, o in enumerate(outs):
         close(o, "mmsd_out%02d" % i, 1e-4)
+    # the six-input Z regressor (models/mmsdnet.py:194-208)
+    za, zz = G["mmsd_zreg_s"].astype(np.float64), t(G["mmsd_zreg_z"])
+    s_list = [t(np.roll(za, i, axis=-1)) for i in range(6)]
+    z_list = [zz[i:i + 1] for i in range(6)]
+    zrec = RM.z_regressor(W, s_list, z_list)
+    close(torch.cat(zrec, 0), "mmsd_zreg_out", 1e-5)
+    assert np.allclose([c["w_rec_Z"] * R.mae(z, r).item() for z, r in zip(z_list, zrec)], G["mmsd_zreg_loss"], rtol=1e-5)
     # loss list and weights of the supervised trainer (models/mmsdnet.py:181-190) on the executor's targets
     # (model_executors/mmsdnet_executor.py:257-260): masks without the residual channel
     m1, m2 = t(G["trainer_m1"])[..., :4], t(G["trainer_m2"])[..., :4]
