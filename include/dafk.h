@@ -440,6 +440,22 @@ int dafk_spade_bwd(const float* dy, const float* x, const double* acc, const flo
                    const float* beta, float* dx, float* dgamma, float* dbeta, double* ws, int B,
                    int64_t HWC, float eps, int act, float alpha, void* stream);
 
+/* layers/spade.py:41-58 SPADE_COND as a stand-alone layer (SPADE_COND()([x, gamma, beta]) on an already-normalised x):
+ * y = x*(1+gamma)+beta, all four tensors f32 with n elements.  Backward: dx = dy*(1+gamma), dgamma = dy*x; dbeta is dy
+ * itself (the caller aliases it). */
+int dafk_spade_cond_fwd(const float* x, const float* gamma, const float* beta, float* y, int64_t n, void* stream);
+int dafk_spade_cond_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, int64_t n,
+                        void* stream);
+/* utils/model_utils.py:6-12 normalise('instance') = keras_contrib InstanceNormalization() with its defaults (axis=None,
+ * epsilon 1e-3, center and scale: gamma, beta of shape (1,)): y = act(gamma[0]*(x-mean_b)/(std_b+eps) + beta[0]) with the
+ * per-sample statistics of dafk_in_stats.  Backward: dx through the normalisation, dgamma[0] / dbeta[0] ACCUMULATED
+ * (either may be NULL).  ws: 2*B+2 doubles, zeroed by the callee. */
+int dafk_in_affine_fwd(const float* x, const double* acc, const float* gamma, const float* beta, float* y, int B,
+                       int64_t HWC, float eps, int act, float alpha, void* stream);
+int dafk_in_affine_bwd(const float* dy, const float* x, const double* acc, const float* gamma, const float* beta,
+                       float* dx, float* dgamma, float* dbeta, double* ws, int B, int64_t HWC, float eps, int act,
+                       float alpha, void* stream);
+
 /* ------------------------------------------------------------------ balancer
  * model_components/balancer.py:33-38 soft dice between two anatomies per sample:
  * out[b] = (2*sum(a*b)+1e-12)/(sum(a)+sum(b)+1e-12).  ws: B*3 doubles. */

@@ -184,27 +184,21 @@ constexpr int NC_MAX_STAGES = 4;
 // second epilogue group: group A (warps 9-12) drains TMEM buffer 0, group B (warps 4-7) buffer 1.
 // BULK runs 12 warps (three per scheduler, 168 registers each): 0 = copies, 1 = MMA issuer, 2-3 idle, 4-11 epilogue.
 //
-// MODE 2 (opt-in, DAFK_NC_L12=1): the default role layout has 13 warps, i.e. four on one scheduler, which caps every
-// thread at 128 registers (ptxas spills 16 B).  Twelve warps -- 7 producers, MMA issuer, 4 epilogue -- get 168:
-// the same code then needs 148 registers and no stack (to be timed in round 2).
-//
-// MODE 3 (opt-in, DAFK_NC_L16=1): the register split the stage-isolation measurements ask for.  Sixteen warps = four
-// warpgroups: 0-1 the eight producers, 2 the MMA issuer (+ three idle warps), 3 the epilogue.  Launched at 128 registers
-// per thread (the whole file); the producers give registers back (setmaxnreg.dec 120), the issuer group keeps 40, and the
-// epilogue group grows to 232, which pays for EB = 8 tiles in lock step (eight independent dependency chains per warp).
+// MODE 2 (default for staged inputs; DAFK_NC_L12=0 selects MODE 0): MODE 0's role layout has 13 warps, i.e. four on one
+// scheduler, which caps every thread at 128 registers (ptxas spills 16 B).  Twelve warps -- 7 producers, MMA issuer,
+// 4 epilogue -- get 168: the same code then needs 148 registers and no stack.  Bit-identical outputs; measured on B200
+// (32 x 224^2): 8 -> 8 forward 32.0 -> 30.9 us, 64 -> 8 data gradient 344 -> 324 us.
+// (A setmaxnreg split into four warpgroups with an eight-tile lock-step epilogue was measured too: slower, 34 / 200 us
+// against 32 / 149 us on 8 -> 8 / 8 -> 64, and removed.)
 constexpr int NC_BULK_THREADS = 384;
-constexpr int NC_L16_THREADS = 512;
-constexpr int NC_MODE_DEFAULT = 0, NC_MODE_BULK = 1, NC_MODE_L12 = 2, NC_MODE_L16 = 3;
-
-template <int R> __device__ __forceinline__ void nc_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
-template <int R> __device__ __forceinline__ void nc_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+constexpr int NC_MODE_DEFAULT = 0, NC_MODE_BULK = 1, NC_MODE_L12 = 2;
 
 template <typename TX, int MODE>
-__global__ void __launch_bounds__(MODE == NC_MODE_DEFAULT ? NC_FWD_THREADS : (MODE == NC_MODE_L16 ? NC_L16_THREADS : NC_BULK_THREADS), 1)
+__global__ void __launch_bounds__(MODE == NC_MODE_DEFAULT ? NC_FWD_THREADS : NC_BULK_THREADS, 1)
 conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __restrict__ wp,
                    const float* __restrict__ bias, void* __restrict__ y) {
   constexpr bool BULK = MODE == NC_MODE_BULK;
-  constexpr int THREADS = MODE == NC_MODE_DEFAULT ? NC_FWD_THREADS : (MODE == NC_MODE_L16 ? NC_L16_THREADS : NC_BULK_THREADS);
+  constexpr int THREADS = MODE == NC_MODE_DEFAULT ? NC_FWD_THREADS : NC_BULK_THREADS;
   constexpr int PROD = MODE == NC_MODE_L12 ? 224 : NC_PROD;                 // staging threads (not BULK)
   constexpr int MMA_WARP = BULK ? 1 : PROD / 32;
   extern __shared__ uint8_t smem_raw[];
@@ -295,7 +289,6 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
     }
   } else if (!BULK && warp < MMA_WARP) {
     // ===================== producers =====================
-    if (MODE == NC_MODE_L16) nc_setmaxnreg_dec<120>();
     float dummy[8];
     int it = 0;
     for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x, ++it) {
@@ -310,9 +303,8 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
       fence_proxy_async();
       mbar_arrive(full + st);
     }
-  } else if (warp == MMA_WARP || (MODE == NC_MODE_L16 && warp < 12)) {
-    if (MODE == NC_MODE_L16) nc_setmaxnreg_dec<40>();     // the whole warpgroup (issuer + three idle warps)
-    if (warp == MMA_WARP) {
+  } else if (warp == MMA_WARP) {
+    {
     // ===================== MMA issuer =====================
     // warp-uniform control flow (all lanes walk the loops, one elected lane issues) keeps the operands in
     // uniform registers; the (tap, group) descriptor pairs come from the table built above
@@ -356,7 +348,6 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
     }
   } else {
     // ===================== epilogue =====================
-    if (MODE == NC_MODE_L16) nc_setmaxnreg_inc<232>();
     const int q4 = warp & 3;
     const int egrp = warp >= 8 ? 0 : 1;   // BULK: which TMEM buffer this epilogue group drains
     const uint32_t magicP = (uint32_t)((0x100000000ULL + (uint64_t)p.P - 1) / (uint64_t)p.P);
@@ -374,7 +365,7 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
         const int gt = min(p.G, tiles_here - t0);
         const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * 256);
         // TMEM loads are issued EB tiles ahead of their use (one wait per batch instead of one per tile)
-        constexpr int EB = MODE == NC_MODE_L16 ? 8 : 4;   // MODE 2: 148 registers, no spills; EB = 6 / 8 spill even at 168
+        constexpr int EB = 4;   // MODE 2: 148 registers, no spills; EB = 6 / 8 spill even at 168
         for (int tb = 0; tb < gt; tb += EB) {
           for (int c0 = 0; c0 < p.Cout; c0 += 8) {
             uint32_t v[EB][8];
@@ -855,19 +846,9 @@ int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias,
   // both kernels in one process.  Measured at 32 x 224^2: 8 -> 8 37.1 -> 24.9 us, 8 -> 64 105 -> 123 us (slower).
   int bulk_ok = 0;
   { const char* e = getenv("DAFK_NC_BULK"); bulk_ok = e ? atoi(e) : 0; }
-  int l12 = 0, l16 = 0;
-  { const char* e = getenv("DAFK_NC_L12"); l12 = e ? atoi(e) : 0; }
-  { const char* e = getenv("DAFK_NC_L16"); l16 = e ? atoi(e) : 0; }
-  if (l16 && x_dt == DAFK_F32) {
-    rc = nc_set_smem(conv_nc_fwd_kernel<float, NC_MODE_L16>, smem, "dafk_conv_nc_fwd");
-    if (rc) return rc;
-    conv_nc_fwd_kernel<float, NC_MODE_L16><<<grid, NC_L16_THREADS, smem, s>>>(p, (const float*)x, (const __nv_bfloat16*)wp,
-                                                                             bias, y);
-  } else if (l16 && !(bulk_ok && Cin == 8)) {
-    rc = nc_set_smem(conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_L16>, smem, "dafk_conv_nc_fwd");
-    if (rc) return rc;
-    conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_L16><<<grid, NC_L16_THREADS, smem, s>>>(p, (const __nv_bfloat16*)x,
-                                                                                     (const __nv_bfloat16*)wp, bias, y);
+  int l12 = 1;
+  { const char* e = getenv("DAFK_NC_L12"); l12 = e ? atoi(e) : 1; }
+  if (false) {
   } else if (l12 && x_dt == DAFK_F32) {
     rc = nc_set_smem(conv_nc_fwd_kernel<float, NC_MODE_L12>, smem, "dafk_conv_nc_fwd");
     if (rc) return rc;

@@ -454,7 +454,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
 }
 
 // ---------------------------------------------------------------------------------------------
-// CTA-pair variant of the haloed-tile kernel (opt-in, DAFK_CONV_HALO2=1; resident weights, one output-channel block).
+// CTA-pair variant of the haloed-tile kernel (default where it applies: resident weights, one output-channel block;
+// DAFK_CONV_HALO2=0 selects the single-CTA kernel).  Measured on B200: 64->64 @224^2 217 -> 192 us, 128->128 @112^2 133 -> 119 us.
 // A tcgen05.mma with both operands in shared memory is bound by the 128 B/clk shared-memory read port when N is small:
 // (A 4 KB + B N*32 B) per K=16 step = 48 cycles at N=64, 64 at N=128, against 32 / 64 cycles of tensor work.  Here two
 // CTAs on one TPC form a cluster and issue tcgen05.mma.cta_group::2 with M = 256: each CTA stages ITS OWN haloed tile
@@ -806,7 +807,7 @@ __global__ void pack_w_kernel(const float* __restrict__ w, __nv_bfloat16* __rest
   }
 }
 
-// forward packing as a tiled transpose (opt-in, DAFK_PACK_TILED=1): the kernel above reads HWIO with the input channel
+// forward packing as a tiled transpose (default; DAFK_PACK_TILED=0 selects the kernel above, which reads HWIO with the input channel
 // fastest, i.e. one 4-byte element per 4*Cout-byte stride; here a 32 ci x 32 co tile of one tap is read along co and
 // written along ci through shared memory.  Same values, same rounding.
 __global__ void __launch_bounds__(256) pack_w_fwd_tiled_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
@@ -840,8 +841,8 @@ __global__ void __launch_bounds__(256) pack_w_fwd_tiled_kernel(const float* __re
 }
 
 static bool pack_tiled_enabled() {
-  const char* e = getenv("DAFK_PACK_TILED");     // read per call: a test compares both kernels in one process
-  return e != nullptr && atoi(e) != 0;
+  const char* e = getenv("DAFK_PACK_TILED");     // default on; "0" selects the strided kernel (read per call: a test
+  return e == nullptr || atoi(e) != 0;           // compares both kernels in one process)
 }
 
 static void launch_pack_fwd_tiled(const float* w, __nv_bfloat16* wp, int taps, int Cin, int Cout, int Cip, int Cop,
@@ -1197,8 +1198,8 @@ static int conv_tc_fwd_impl(const void* x0, int C0, const void* x1, int C1, cons
     // the tap-by-tap kernel is L2-bound on the activations); with Cout >= 256 the 128 x 256 tap-by-tap tiles win
     (void)ct;
     const bool prefer_halo = Cout < 256;
-    int halo2 = 0;
-    { const char* e = getenv("DAFK_CONV_HALO2"); halo2 = e ? atoi(e) : 0; }    // opt-in CTA-pair variant, read per call
+    int halo2 = 1;
+    { const char* e = getenv("DAFK_CONV_HALO2"); halo2 = e ? atoi(e) : 1; }    // CTA-pair variant (default; "0" = single CTA), read per call
     if (halo2 && force != 0 && prefer_halo && Cout <= bn) {
       // each CTA of the pair keeps half of every weight tile resident
       const int w_half = (Kpad / KBLK) * taps * (bn / 2) * KBLK * 2;
@@ -1355,13 +1356,6 @@ int dafk_conv_tc_wgrad(const void* x, int Cin, int cin_off, int cin_total, const
   rc = make_act_map(&mdy, dy, N, Ho, Wo, Cout, g, 1);
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
-  {
-    // opt-in (DAFK_WGRAD_BN256=1): 128 x 256 accumulator, 0.75x the operand bytes per MAC of the 128 x 128 tile
-    // (96 KB per 128 x 256 x 128 k-block against 64 KB per 128 x 128 x 128), two 96 KB stages
-    const char* e = getenv("DAFK_WGRAD_BN256");
-    if (e != nullptr && atoi(e) != 0 && Cout % 128 == 0 && Cin % 256 == 0)
-      return launch_wgrad<128, 256, 2>(mx, mdy, dw, Cin, cin_off, cin_total, Cout, KH, KW, stride, pad, g, s);
-  }
   if (Cout % 128 == 0 && Cin % 128 == 0)
     return launch_wgrad<128, 128, 3>(mx, mdy, dw, Cin, cin_off, cin_total, Cout, KH, KW, stride, pad, g, s);
   if (Cout % 128 == 0) return launch_wgrad<128, 64, 4>(mx, mdy, dw, Cin, cin_off, cin_total, Cout, KH, KW, stride, pad, g, s);

@@ -321,6 +321,133 @@ __global__ void __launch_bounds__(TPB) spade_bwd2_kernel(const float* __restrict
   }
 }
 
+
+// ---------------------------------------------------------------- SPADE_COND alone (layers/spade.py:41-58)
+// y = x*(1+gamma) + beta on an already-normalised input; backward dx = dy*(1+gamma), dgamma = dy*x (dbeta = dy)
+__global__ void __launch_bounds__(TPB) spade_cond_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* __restrict__ y,
+                                                             int64_t n) {
+  int64_t n4 = n >> 2;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = ldg_stream4(x + 4 * i), g = ldg_stream4(gamma + 4 * i), t = ldg_stream4(beta + 4 * i), r;
+    r.x = v.x * (1.f + g.x) + t.x; r.y = v.y * (1.f + g.y) + t.y;
+    r.z = v.z * (1.f + g.z) + t.z; r.w = v.w * (1.f + g.w) + t.w;
+    stg_stream4(y + 4 * i, r);
+  }
+  int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) y[t] = x[t] * (1.f + gamma[t]) + beta[t];
+}
+__global__ void __launch_bounds__(TPB) spade_cond_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                             const float* __restrict__ gamma, float* __restrict__ dx,
+                                                             float* __restrict__ dgamma, int64_t n) {
+  int64_t n4 = n >> 2;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 d = ldg_stream4(dy + 4 * i), v = ldg_stream4(x + 4 * i), g = ldg_stream4(gamma + 4 * i), a, b;
+    a.x = d.x * (1.f + g.x); a.y = d.y * (1.f + g.y); a.z = d.z * (1.f + g.z); a.w = d.w * (1.f + g.w);
+    b.x = d.x * v.x; b.y = d.y * v.y; b.z = d.z * v.z; b.w = d.w * v.w;
+    stg_stream4(dx + 4 * i, a);
+    stg_stream4(dgamma + 4 * i, b);
+  }
+  int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) { dx[t] = dy[t] * (1.f + gamma[t]); dgamma[t] = dy[t] * x[t]; }
+}
+
+// ---------------------------------------------------------------- InstanceNormalization(axis=None) with its scalar affine
+// utils/model_utils.py:6-12 normalise('instance') = keras_contrib InstanceNormalization(): per-sample statistics over
+// H,W,C jointly, y = act(gamma * (x-mean)/(std+eps) + beta), gamma and beta of shape (1,).  grid = (chunks, B)
+__global__ void __launch_bounds__(TPB) in_affine_fwd_kernel(const float* __restrict__ x, const double* __restrict__ acc,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* __restrict__ y, int64_t HWC, float eps, int act,
+                                                            float alpha) {
+  int b = blockIdx.y;
+  float mean, sd, inv;
+  in_moments(acc, b, HWC, eps, mean, sd, inv);
+  const float g = gamma[0], t = beta[0];
+  int64_t off = (int64_t)b * HWC;
+  int64_t n4 = HWC >> 2;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = ldg_stream4(x + off + 4 * i), r;
+    r.x = act_apply((v.x - mean) * inv * g + t, act, alpha);
+    r.y = act_apply((v.y - mean) * inv * g + t, act, alpha);
+    r.z = act_apply((v.z - mean) * inv * g + t, act, alpha);
+    r.w = act_apply((v.w - mean) * inv * g + t, act, alpha);
+    stg_stream4(y + off + 4 * i, r);
+  }
+}
+// pass 1: dz = dy*act'(z) (stored in dx), per-sample S1 = sum dz*gamma, S2 = sum dz*gamma*(x-mean); dgamma += sum dz*xn,
+// dbeta += sum dz over the whole batch (double accumulators wsg[0..1])
+__global__ void __launch_bounds__(TPB) in_affine_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                             const double* __restrict__ acc, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* __restrict__ dz_out,
+                                                             double* __restrict__ ws, double* __restrict__ wsg,
+                                                             int64_t HWC, float eps, int act, float alpha) {
+  __shared__ float red[TPB / 32];
+  int b = blockIdx.y;
+  float mean, sd, inv;
+  in_moments(acc, b, HWC, eps, mean, sd, inv);
+  const float g = gamma[0], t = beta[0];
+  int64_t off = (int64_t)b * HWC;
+  int64_t n4 = HWC >> 2;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float s1 = 0.f, s2 = 0.f, sg = 0.f, sb = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v4 = ldg_stream4(x + off + 4 * i), d4 = ldg_stream4(dy + off + 4 * i);
+    float v[4] = {v4.x, v4.y, v4.z, v4.w}, d[4] = {d4.x, d4.y, d4.z, d4.w}, o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float xc = v[k] - mean, xn = xc * inv;
+      float dz = d[k] * act_grad(xn * g + t, act, alpha);
+      o[k] = dz;
+      sg += dz * xn;
+      sb += dz;
+      s1 += dz * g;
+      s2 += dz * g * xc;
+    }
+    Vec4<float>::store(dz_out + off + 4 * i, o);
+  }
+  float t1 = block_sum<TPB>(s1, red), t2 = block_sum<TPB>(s2, red);
+  float tg = block_sum<TPB>(sg, red), tb = block_sum<TPB>(sb, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(ws + 2 * b, (double)t1);
+    atomicAdd(ws + 2 * b + 1, (double)t2);
+    atomicAdd(wsg, (double)tg);
+    atomicAdd(wsg + 1, (double)tb);
+  }
+}
+// pass 2 (in place on dz): dx = (dz*gamma - S1/n)/s' - (x-mean)*S2/(n*sd*s'^2); block (0,0) adds the parameter gradients
+__global__ void __launch_bounds__(TPB) in_affine_bwd2_kernel(float* __restrict__ dx, const float* __restrict__ x,
+                                                             const double* __restrict__ acc, const float* __restrict__ gamma,
+                                                             const double* __restrict__ ws, const double* __restrict__ wsg,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                             int64_t HWC, float eps) {
+  int b = blockIdx.y;
+  float mean, sd, inv;
+  in_moments(acc, b, HWC, eps, mean, sd, inv);
+  const float g = gamma[0];
+  const float m1 = (float)(ws[2 * b] / (double)HWC);
+  const float k2 = sd > 0.f ? (float)(ws[2 * b + 1] / (double)HWC) * inv * inv / sd : 0.f;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    if (dgamma) dgamma[0] += (float)wsg[0];
+    if (dbeta) dbeta[0] += (float)wsg[1];
+  }
+  int64_t off = (int64_t)b * HWC;
+  int64_t n4 = HWC >> 2;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v4 = ldg_stream4(x + off + 4 * i);
+    float4 z4 = *reinterpret_cast<const float4*>(dx + off + 4 * i);
+    float4 r;
+    r.x = (z4.x * g - m1) * inv - (v4.x - mean) * k2;
+    r.y = (z4.y * g - m1) * inv - (v4.y - mean) * k2;
+    r.z = (z4.z * g - m1) * inv - (v4.z - mean) * k2;
+    r.w = (z4.w * g - m1) * inv - (v4.w - mean) * k2;
+    *reinterpret_cast<float4*>(dx + off + 4 * i) = r;
+  }
+}
+
 // model_components/balancer.py:33-38
 __global__ void __launch_bounds__(TPB) pair_dice_kernel(const float* __restrict__ a, const float* __restrict__ bb,
                                                         double* __restrict__ ws, int64_t HWC) {
@@ -355,6 +482,20 @@ static inline int per_sample_chunks(int64_t n4, int B) {
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   return (int)chunks;
+}
+
+// any channel count (f32 in / out): one thread per element.  Only reached when C is not a power of two in [4,1024]
+// (e.g. a 2-filter UNet level); forward only.
+__global__ void __launch_bounds__(TPB) bn_apply_any_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ out,
+                                                           int64_t n, int C, int act) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int c = (int)(i % C);
+    float z = (x[i] - mean[c]) * rstd[c] * gamma[c] + beta[c];
+    out[i] = (act == DAFK_ACT_RELU && !(z > 0.f)) ? 0.f : z;
+  }
 }
 
 }  // namespace dafk
@@ -397,8 +538,13 @@ int dafk_bn_apply(const void* x, int x_dt, const float* mean, const float* rstd,
   DAFK_REQUIRE(M >= 0 && C > 0, DAFK_ERR_BAD_ARG, "dafk_bn_apply: bad shape");
   if (M == 0) return DAFK_OK;
   DAFK_REQUIRE(x && mean && rstd && gamma && beta && out, DAFK_ERR_BAD_ARG, "dafk_bn_apply: null pointer");
-  DAFK_REQUIRE(bn_channels_ok(C), DAFK_ERR_UNSUPPORTED, "dafk_bn_apply: C must be a power of two in [4,1024] (got %d)", C);
   DAFK_REQUIRE(act == DAFK_ACT_NONE || act == DAFK_ACT_RELU, DAFK_ERR_UNSUPPORTED, "dafk_bn_apply: act must be NONE or RELU");
+  if (!bn_channels_ok(C) && x_dt == DAFK_F32 && out_dt == DAFK_F32) {
+    bn_apply_any_kernel<<<bw_grid(M * C, TPB), TPB, 0, as_stream(stream)>>>((const float*)x, mean, rstd, gamma, beta,
+                                                                           (float*)out, M * C, C, act);
+    return check_launch("dafk_bn_apply(any C)");
+  }
+  DAFK_REQUIRE(bn_channels_ok(C), DAFK_ERR_UNSUPPORTED, "dafk_bn_apply: C must be a power of two in [4,1024] (got %d)", C);
   DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(out), DAFK_ERR_ALIGN, "dafk_bn_apply: alignment");
   int64_t n4 = M * C / 4;
   cudaStream_t s = as_stream(stream);
@@ -587,6 +733,57 @@ int dafk_spade_bwd(const float* dy, const float* x, const double* acc, const flo
   if (rc) return rc;
   spade_bwd2_kernel<<<grid, TPB, 0, s>>>(dbeta, x, acc, gamma, ws, dx, HWC, eps);
   return check_launch("dafk_spade_bwd(2)");
+}
+
+int dafk_spade_cond_fwd(const float* x, const float* gamma, const float* beta, float* y, int64_t n, void* stream) {
+  DAFK_REQUIRE(n >= 0, DAFK_ERR_BAD_ARG, "dafk_spade_cond_fwd: negative size");
+  if (n == 0) return DAFK_OK;
+  DAFK_REQUIRE(x && gamma && beta && y, DAFK_ERR_BAD_ARG, "dafk_spade_cond_fwd: null pointer");
+  DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(gamma) && DAFK_ALIGNED16(beta) && DAFK_ALIGNED16(y), DAFK_ERR_ALIGN,
+               "dafk_spade_cond_fwd: alignment");
+  spade_cond_fwd_kernel<<<bw_grid((n + 3) / 4, TPB), TPB, 0, as_stream(stream)>>>(x, gamma, beta, y, n);
+  return check_launch("dafk_spade_cond_fwd");
+}
+
+int dafk_spade_cond_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, int64_t n,
+                        void* stream) {
+  DAFK_REQUIRE(n >= 0, DAFK_ERR_BAD_ARG, "dafk_spade_cond_bwd: negative size");
+  if (n == 0) return DAFK_OK;
+  DAFK_REQUIRE(dy && x && gamma && dx && dgamma, DAFK_ERR_BAD_ARG, "dafk_spade_cond_bwd: null pointer");
+  DAFK_REQUIRE(DAFK_ALIGNED16(dy) && DAFK_ALIGNED16(x) && DAFK_ALIGNED16(gamma) && DAFK_ALIGNED16(dx) &&
+               DAFK_ALIGNED16(dgamma), DAFK_ERR_ALIGN, "dafk_spade_cond_bwd: alignment");
+  spade_cond_bwd_kernel<<<bw_grid((n + 3) / 4, TPB), TPB, 0, as_stream(stream)>>>(dy, x, gamma, dx, dgamma, n);
+  return check_launch("dafk_spade_cond_bwd");
+}
+
+int dafk_in_affine_fwd(const float* x, const double* acc, const float* gamma, const float* beta, float* y, int B,
+                       int64_t HWC, float eps, int act, float alpha, void* stream) {
+  DAFK_REQUIRE(B >= 0 && HWC >= 0, DAFK_ERR_BAD_ARG, "dafk_in_affine_fwd: bad shape");
+  if (B == 0 || HWC == 0) return DAFK_OK;
+  DAFK_REQUIRE(x && acc && gamma && beta && y, DAFK_ERR_BAD_ARG, "dafk_in_affine_fwd: null pointer");
+  DAFK_REQUIRE(HWC % 4 == 0, DAFK_ERR_UNSUPPORTED, "dafk_in_affine_fwd: H*W*C must be a multiple of 4");
+  DAFK_REQUIRE(DAFK_ALIGNED16(x) && DAFK_ALIGNED16(y), DAFK_ERR_ALIGN, "dafk_in_affine_fwd: alignment");
+  in_affine_fwd_kernel<<<dim3(per_sample_chunks(HWC / 4, B), B), TPB, 0, as_stream(stream)>>>(x, acc, gamma, beta, y,
+                                                                                             HWC, eps, act, alpha);
+  return check_launch("dafk_in_affine_fwd");
+}
+
+int dafk_in_affine_bwd(const float* dy, const float* x, const double* acc, const float* gamma, const float* beta,
+                       float* dx, float* dgamma, float* dbeta, double* ws, int B, int64_t HWC, float eps, int act,
+                       float alpha, void* stream) {
+  DAFK_REQUIRE(B >= 0 && HWC >= 0, DAFK_ERR_BAD_ARG, "dafk_in_affine_bwd: bad shape");
+  if (B == 0 || HWC == 0) return DAFK_OK;
+  DAFK_REQUIRE(dy && x && acc && gamma && beta && dx && ws, DAFK_ERR_BAD_ARG, "dafk_in_affine_bwd: null pointer");
+  DAFK_REQUIRE(HWC % 4 == 0, DAFK_ERR_UNSUPPORTED, "dafk_in_affine_bwd: H*W*C must be a multiple of 4");
+  DAFK_REQUIRE(DAFK_ALIGNED16(dy) && DAFK_ALIGNED16(x) && DAFK_ALIGNED16(dx), DAFK_ERR_ALIGN, "dafk_in_affine_bwd: alignment");
+  cudaStream_t s = as_stream(stream);
+  cudaMemsetAsync(ws, 0, sizeof(double) * (2 * B + 2), s);
+  dim3 grid(per_sample_chunks(HWC / 4, B), B);
+  in_affine_bwd1_kernel<<<grid, TPB, 0, s>>>(dy, x, acc, gamma, beta, dx, ws, ws + 2 * B, HWC, eps, act, alpha);
+  int rc = check_launch("dafk_in_affine_bwd(1)");
+  if (rc) return rc;
+  in_affine_bwd2_kernel<<<grid, TPB, 0, s>>>(dx, x, acc, gamma, ws, ws + 2 * B, dgamma, dbeta, HWC, eps);
+  return check_launch("dafk_in_affine_bwd(2)");
 }
 
 int dafk_pair_dice(const float* a, const float* b, float* out, double* ws, int B, int64_t HWC, void* stream) {

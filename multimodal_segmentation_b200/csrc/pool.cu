@@ -287,6 +287,23 @@ __global__ void __launch_bounds__(TPB) resize_nn_bwd_kernel(const float* __restr
   }
 }
 
+// any channel count (f32): one thread per output element.  Only reached for C % 4 != 0 (e.g. a 2-filter UNet level).
+__global__ void __launch_bounds__(TPB) maxpool2_fwd_any_kernel(const float* __restrict__ x, float* __restrict__ y, int N,
+                                                               int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int c = (int)(i % C);
+    int64_t r = i / C;
+    int wo = (int)(r % Wo); r /= Wo;
+    int ho = (int)(r % Ho);
+    int n = (int)(r / Ho);
+    const float* p = x + (((int64_t)n * H + 2 * ho) * W + 2 * wo) * C + c;
+    y[i] = fmaxf(fmaxf(p[0], p[C]), fmaxf(p[(int64_t)W * C], p[(int64_t)W * C + C]));
+  }
+}
+
 }  // namespace dafk
 
 using namespace dafk;
@@ -299,6 +316,13 @@ using namespace dafk;
 extern "C" {
 
 int dafk_maxpool2_fwd(const void* x, void* y, int dt, int N, int H, int W, int C, void* stream) {
+  if (C > 0 && C % 4 != 0 && dt == DAFK_F32 && N >= 0 && H >= 0 && W >= 0) {
+    int64_t tot = (int64_t)N * (H / 2) * (W / 2) * C;
+    if (tot == 0) return DAFK_OK;
+    DAFK_REQUIRE(x && y, DAFK_ERR_BAD_ARG, "dafk_maxpool2_fwd: null pointer");
+    maxpool2_fwd_any_kernel<<<bw_grid(tot, TPB), TPB, 0, as_stream(stream)>>>((const float*)x, (float*)y, N, H, W, C);
+    return check_launch("dafk_maxpool2_fwd(any C)");
+  }
   POOL_CHECKS("dafk_maxpool2_fwd");
   int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 4);
   if (total == 0) return DAFK_OK;

@@ -647,6 +647,48 @@ class BatchNorm:
         return y
 
 
+class InstanceNorm:
+    """keras_contrib InstanceNormalization() with its defaults (axis=None, epsilon 1e-3, center and scale with gamma,
+    beta of shape (1,)): utils/model_utils.py:6-12 normalise('instance').  Per-sample statistics over H, W, C jointly,
+    the same in the training and the inference phase (no moving statistics)."""
+    EPS = 1e-3
+
+    def __init__(self, arena, name):
+        self.name = name
+        self.gamma = arena.add(name + "/gamma", (1,), np.ones(1, np.float32))
+        self.beta = arena.add(name + "/beta", (1,), np.zeros(1, np.float32))
+
+    def params(self):
+        return [self.gamma, self.beta]
+
+    def __call__(self, ctx, x, act=None, out_dtype=torch.float32):
+        code = ACT[act]
+        xin = x if x.data.dtype == torch.float32 else _cast_var(ctx, x, torch.float32)
+        acc = ops.in_stats(xin.data)
+        out = ops.in_affine_fwd(xin.data, acc, self.gamma.data, self.beta.data, code, 0.0, self.EPS)
+        y = Var(out)
+        if ctx.rec(xin, self.gamma):
+            y.requires_grad = True
+
+            def bw():
+                g = y.grad
+                y.grad = None
+                if g is None:
+                    return
+                if g.dtype != torch.float32:
+                    g = ops.cast(g, torch.float32)
+                tr = self.gamma.requires_grad
+                # x.bias_sink stays with the producing convolution: under joint H,W,C statistics its bias does not cancel
+                dx = ops.in_affine_bwd(g, xin.data, acc, self.gamma.data, self.beta.data,
+                                       self.gamma.grad if tr else None, self.beta.grad if tr else None, code, 0.0, self.EPS)
+                accumulate(xin, dx)
+
+            ctx.tape.record(bw)
+        if out_dtype != torch.float32:
+            return _cast_var(ctx, y, out_dtype)
+        return y
+
+
 class Dense:
     def __init__(self, arena, rng, name, cin, cout, init="glorot_uniform", bias_init="zeros"):
         self.name, self.cin, self.cout = name, cin, cout
@@ -688,6 +730,8 @@ def conv_bn(ctx, conv, bn, x, act=None, out_dtype=torch.float32):
     statistics, apply).  Inference phase on the tensor-core path: one kernel (Conv2D.forward_folded)."""
     srcs = list(x) if isinstance(x, (list, tuple)) else [x]
     code = ACT[act]
+    if isinstance(bn, InstanceNorm):      # no moving statistics: nothing to fold
+        return bn(ctx, conv(ctx, x), act, out_dtype)
     if (FOLD_BN and USE_TC and not ctx.training and ctx.tape is None and code in (ACT_NONE, ACT_RELU)
             and len(srcs) <= 2 and conv.stride == 1 and conv.tc_eligible(srcs)):
         return conv.forward_folded(srcs, bn, code, out_dtype)
@@ -1027,6 +1071,26 @@ def spade_norm(ctx, x, gamma, beta, act="lrelu", alpha=0.2):
             accumulate(x, dx)
             accumulate(gamma, dg)
             accumulate(beta, db)
+
+        ctx.tape.record(bw)
+    return y
+
+
+def spade_cond(ctx, x, gamma, beta):
+    """SPADE_COND()([x, gamma, beta]) = x*(1+gamma)+beta on an already-normalised x (layers/spade.py:41-58)"""
+    y = Var(ops.spade_cond_fwd(x.data, gamma.data, beta.data))
+    if ctx.rec(x, gamma, beta):
+        y.requires_grad = True
+
+        def bw():
+            g = y.grad
+            y.grad = None
+            if g is None:
+                return
+            dx, dg = ops.spade_cond_bwd(g, x.data, gamma.data)
+            accumulate(x, dx)
+            accumulate(gamma, dg)
+            accumulate(beta, g, owned=False)
 
         ctx.tape.record(bw)
     return y

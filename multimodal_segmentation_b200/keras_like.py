@@ -68,10 +68,82 @@ class BuildScope:
         return s
 
 
-class Model:
-    """A named component: an ordered list of layers and a forward function over ``Var``s."""
+class InputSpec(object):
+    """one entry of ``Model.inputs`` (keras Input tensor stand-in): the owning model, its position and shape"""
 
-    def __init__(self, name, layers, forward, input_shapes, output_shapes, scope):
+    def __init__(self, model, index, shape):
+        self.model, self.index, self.shape = model, index, (None,) + tuple(shape)
+
+    def __repr__(self):
+        return "<Input %d of %s %s>" % (self.index, self.model.name, self.shape)
+
+
+class LayerOutput(object):
+    """``model.get_layer(name).output``: the value of an inner layer, usable as the output of a sub-model
+    ``Model(model.inputs, model.get_layer('z_mean').output)`` (models/dafnet.py:126, models/mmsdnet.py:51,87)"""
+
+    def __init__(self, model, layer):
+        self.model, self.layer = model, layer
+
+
+class LayerHandle(object):
+    """``model.get_layer(name)``: name, weights and ``.output`` of one layer of a component"""
+
+    def __init__(self, model, layer):
+        self.model, self.layer, self.name = model, layer, layer.name
+
+    def _weights(self):
+        ws = list(self.layer.params())
+        if isinstance(self.layer, E.BatchNorm):
+            ws += [self.layer.moving_mean, self.layer.moving_var]
+        return ws
+
+    def get_weights(self):
+        self.model._ensure_device()
+        torch.cuda.synchronize() if torch.cuda.is_available() else None
+        return [p.numpy() for p in self._weights()]
+
+    def set_weights(self, weights):
+        self.model._ensure_device()
+        ws = self._weights()
+        assert len(ws) == len(weights), "%s: expected %d arrays, got %d" % (self.name, len(ws), len(weights))
+        for p, w in zip(ws, weights):
+            w = np.asarray(w, np.float32)
+            assert tuple(w.shape) == p.shape, (p.name, w.shape, p.shape)
+            p.data.copy_(torch.from_numpy(np.ascontiguousarray(w)))
+        self.model._scope.arena.version += 1
+        self.model._scope.state.version += 1
+
+    @property
+    def output(self):
+        if self.name not in self.model._taps:
+            raise ValueError("layer %r of %s has no registered output tap (taps: %s)"
+                             % (self.name, self.model.name, sorted(self.model._taps)))
+        return LayerOutput(self.model, self.layer)
+
+
+class Model:
+    """A named component: an ordered list of layers and a forward function over ``Var``s.
+
+    Two constructors, as in Keras: the builders' ``Model(name, layers, forward, input_shapes, output_shapes, scope)`` and
+    the functional ``Model(model.inputs, model.get_layer(name).output[, name=...])`` for a sub-graph that shares the
+    parent's layers (and therefore its weights)."""
+
+    def __init__(self, *args, **kw):
+        first = args[0] if args else kw.get("inputs")
+        if isinstance(first, (list, tuple)) and len(first) > 0 and isinstance(first[0], InputSpec):
+            inputs = first
+            out = args[1] if len(args) > 1 else kw.get("outputs")
+            if not isinstance(out, LayerOutput):
+                raise TypeError("Model(inputs, outputs): outputs must be model.get_layer(name).output")
+            parent = out.model
+            if list(inputs) != list(parent.inputs):
+                raise ValueError("Model(inputs, outputs): inputs must be the parent model's .inputs")
+            forward, layers, oshape = parent._taps[out.layer.name]
+            name = kw.get("name") or (parent.name + "_" + out.layer.name)
+            input_shapes, output_shapes, scope = parent.input_shapes, [oshape], parent._scope
+        else:
+            name, layers, forward, input_shapes, output_shapes, scope = args
         self.name = name
         self.layers = layers                  # creation order == Keras weight order
         self._forward = forward
@@ -79,6 +151,8 @@ class Model:
         self.output_shapes = output_shapes
         self._scope = scope
         self._trainable = True
+        self._taps = {}                       # layer name -> (forward up to that layer, its layers, output shape)
+        self._inputs = None
 
     # -- device placement ------------------------------------------------------------------
     def _ensure_device(self):
@@ -94,6 +168,30 @@ class Model:
         return self._forward(ctx, *inputs)
 
     # -- keras protocol ------------------------------------------------------------------------
+    @property
+    def inputs(self):
+        if self._inputs is None:
+            self._inputs = [InputSpec(self, i, s) for i, s in enumerate(self.input_shapes)]
+        return self._inputs
+
+    @property
+    def input_shape(self):
+        shp = [(None,) + tuple(s) for s in self.input_shapes]
+        return shp[0] if len(shp) == 1 else shp
+
+    def register_tap(self, layer_name, forward, layers, output_shape):
+        """make ``get_layer(layer_name).output`` usable as the output of a sub-model"""
+        self._taps[layer_name] = (forward, layers, tuple(output_shape))
+
+    def get_layer(self, name=None, index=None):
+        """keras ``Model.get_layer``: by name, or by position in the layer list"""
+        if index is not None:
+            return LayerHandle(self, self.layers[index])
+        for l in self.layers:
+            if getattr(l, "name", None) == name:
+                return LayerHandle(self, l)
+        raise ValueError("No such layer: %s" % name)
+
     @property
     def output_shape(self):
         shp = [(None,) + tuple(s) for s in self.output_shapes]

@@ -13,20 +13,25 @@ from .. import engine as E
 
 
 class SPADE_COND(object):
-    """x * (1 + gamma) + beta on already-normalised input (spade.py:41-58), no activation."""
+    """SPADE_COND()([x, gamma, beta]) = x * (1 + gamma) + beta on an already-normalised input (spade.py:41-58), no
+    activation: one kernel each way (``dafk_spade_cond_fwd/bwd``).  The decoder uses the fused ``_Spade`` below, which
+    also carries the instance normalisation and the LeakyReLU."""
 
     def __init__(self, **kwargs):
         self.name = kwargs.get("name", "spade_cond")
 
-    def __call__(self, ctx, x):
-        h, gamma, beta = x
-        one = E.Var(E.ops.fill_(E.ops.f32(*gamma.shape), 1.0))
-        return E.add(ctx, _mul(ctx, h, E.add(ctx, gamma, one)), beta)
+    def params(self):
+        return []
 
+    def __call__(self, ctx, x=None):
+        if x is None:                      # keras call style: SPADE_COND()([x, gamma, beta]) -> no-gradient context
+            ctx, x = E.Ctx(None, training=False), ctx
+        h, gamma, beta = [_as_f32(ctx, v if isinstance(v, E.Var) else E.Var(v)) for v in x]
+        return E.spade_cond(ctx, h, gamma, beta)
 
-def _mul(ctx, a, b):
-    raise NotImplementedError("standalone SPADE_COND on pre-normalised input is not on the hot path; "
-                              "use _Spade (fused instance-norm + SPADE_COND)")
+    def compute_output_shape(self, input_shape):
+        return input_shape[0] if isinstance(input_shape, (list, tuple)) and isinstance(input_shape[0], (list, tuple)) \
+            else input_shape
 
 
 class _Spade:

@@ -45,6 +45,12 @@ def build(conf):
 
     m = Model("Enc_Modality", convs + [d1, z_mean, z_log_var], fwd,
               [tuple(conf.anatomy_encoder.output_shape), tuple(conf.input_shape)], [(conf.num_z,), (conf.num_z,)], scope)
+    def fwd_lv(ctx, anatomy, image):
+        return z_log_var(ctx, trunk(ctx, anatomy, image))
+
     m.forward_mu = fwd_mu
-    m.mu_layers = convs + [d1, z_mean]          # Enc_Modality_mu = Model(inputs, get_layer('z_mean').output)
+    m.mu_layers = convs + [d1, z_mean]
+    # Enc_Modality_mu = Model(Enc_Modality.inputs, Enc_Modality.get_layer('z_mean').output)   (models/dafnet.py:126)
+    m.register_tap("z_mean", fwd_mu, convs + [d1, z_mean], (conf.num_z,))
+    m.register_tap("z_log_var", fwd_lv, convs + [d1, z_log_var], (conf.num_z,))
     return m

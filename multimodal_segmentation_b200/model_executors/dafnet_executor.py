@@ -51,9 +51,12 @@ class DAFNetExecutor(Executor):
 
     # ------------------------------------------------------------------ stochastic weight averaging
     SWA_EPOCH = 40
+    USE_SWA = True          # the reference's MMSDNet executor has no SWA (mmsdnet_executor.py:159-208): subclass sets False
 
     def init_swa_models(self):
         """dafnet_executor.py:41-56"""
+        if not self.USE_SWA:
+            return
         e = self.SWA_EPOCH
         self.swa_D_Mask = SWA(e, Discriminator(self.conf.d_mask_params).build, None)
         has_dimg = hasattr(self.conf, "d_image_params")
@@ -70,6 +73,8 @@ class DAFNetExecutor(Executor):
 
     def set_swa_model_weights(self):
         """dafnet_executor.py:58-68"""
+        if not self.USE_SWA:
+            return
         M = self.model
         self.swa_D_Mask.model = M.D_Mask
         if self.swa_D_Image1 is not None:
@@ -86,14 +91,16 @@ class DAFNetExecutor(Executor):
 
     def get_swa_models(self):
         """dafnet_executor.py:207-210"""
+        if not self.USE_SWA:
+            return []
         lst = [self.swa_D_Mask, self.swa_D_Image1, self.swa_D_Image2, self.swa_Enc_Anatomy1, self.swa_Enc_Anatomy2,
                self.swa_Enc_Modality, self.swa_Anatomy_Fuser, self.swa_Segmentor, self.swa_Decoder, self.swa_Balancer]
         return [m for m in lst if m is not None and m.model is not None]
 
     def save_models(self, postfix=""):
         """dafnet_executor.py:286-301: the files hold the SWA weights (identical to the live ones until SWA_EPOCH)"""
-        if not hasattr(self.model, "_components"):
-            return self.model.save_models()         # MMSDNet keeps its single-file format (models/mmsdnet.py:42-60)
+        if not self.USE_SWA or not hasattr(self.model, "_components"):
+            return self.model.save_models()         # MMSDNet: live weights, single-file format (models/mmsdnet.py:42-60)
         model_folder = self.conf.folder + "/models/"
         os.makedirs(model_folder, exist_ok=True)
         names = [("D_Mask", self.swa_D_Mask), ("D_Image1", self.swa_D_Image1), ("D_Image2", self.swa_D_Image2),
@@ -245,7 +252,8 @@ class DAFNetExecutor(Executor):
         real0, real1 = valid.get_masks_modi(0)[..., :nm], valid.get_masks_modi(1)[..., :nm]
         # the reference validates through the SWA clones (dafnet_executor.py:319-331); up to SWA_EPOCH their weights ARE
         # the live weights, so the clones are only built once averaging has started
-        averaging = getattr(self, "epoch", 0) > self.SWA_EPOCH and self.swa_Segmentor.swa_weights is not None
+        averaging = (self.USE_SWA and getattr(self, "epoch", 0) > self.SWA_EPOCH
+                     and self.swa_Segmentor.swa_weights is not None)
         pick = (lambda swa_m, live: swa_m.get_clone_model()) if averaging else (lambda swa_m, live: live)
         enc0 = pick(self.swa_Enc_Anatomy1, self.model.Encoders_Anatomy[0])
         enc1 = pick(self.swa_Enc_Anatomy2, self.model.Encoders_Anatomy[1])

@@ -18,6 +18,10 @@ log = logging.getLogger("mmsdnet_executor")
 
 
 class MMSDNetExecutor(DAFNetExecutor):
+    # mmsdnet_executor.py:159-236: no stochastic weight averaging -- validation (and with it the early-stopping metric
+    # val_loss_mod2_fused) runs on the LIVE models and model.save_models() writes the live weights
+    USE_SWA = False
+
     def get_loss_names(self):
         return ["adv_M", "rec_X", "dis_M", "val_loss", "val_loss_mod1", "val_loss_mod2", "val_loss_mod2_s1def",
                 "val_loss_mod2_fused", "supervised_Mask", "loss", "KL", "rec_Z"]

@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 from .. import engine as E
-from ..keras_like import BuildScope
+from ..keras_like import BuildScope, Model
 from ..model_components import anatomy_encoder, anatomy_fuser, decoder, modality_encoder, segmentor
 from .basenet import BaseNet
 from .discriminator import Discriminator
@@ -16,15 +16,10 @@ from .trainers import DiscriminatorTrainer, Trainer
 log = logging.getLogger("mmsdnet")
 
 
-class MuModel(object):
-    """Enc_Modality_mu = Model(Enc_Modality.inputs, Enc_Modality.get_layer('z_mean').output)"""
-
-    def __init__(self, enc):
-        self.enc = enc
-        self.name = "Enc_Modality_mu"
-
-    def __call__(self, ctx, anatomy, image):
-        return self.enc.forward_mu(ctx, anatomy, image)
+def MuModel(enc):
+    """Enc_Modality_mu = Model(Enc_Modality.inputs, Enc_Modality.get_layer('z_mean').output)   (models/mmsdnet.py:51,87;
+    models/dafnet.py:126): a sub-model that shares the encoder's layers up to ``z_mean``"""
+    return Model(enc.inputs, enc.get_layer("z_mean").output, name="Enc_Modality_mu")
 
 
 class MMSDNetGeneratorTrainer(Trainer):

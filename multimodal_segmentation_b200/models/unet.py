@@ -9,11 +9,12 @@ from .. import engine as E
 
 
 def normalise(arena, state, name, c, norm):
-    """utils/model_utils.py:6-12 -- 'batch' -> BatchNormalization(); None -> identity."""
+    """utils/model_utils.py:6-12 -- 'batch' -> BatchNormalization(); 'instance' -> keras_contrib
+    InstanceNormalization() (axis=None, scalar gamma / beta); anything else -> identity."""
     if norm == "batch":
         return E.BatchNorm(arena, state, name, c)
     if norm == "instance":
-        raise NotImplementedError("normalise='instance' is not used by any shipped configuration")
+        return E.InstanceNorm(arena, name)
     return None
 
 

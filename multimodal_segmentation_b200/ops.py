@@ -337,6 +337,8 @@ def maxpool2_bwd(x, dy):
 def upsample2_fwd(x):
     _chk(x)
     N, H, W, C = x.shape
+    if C % 4 != 0 and x.dtype == torch.float32:
+        return resize_nn_fwd(x, 2 * H, 2 * W)       # any channel count: nearest resize by 2 is the same map
     y = torch.empty((N, 2 * H, 2 * W, C), dtype=x.dtype, device=x.device)
     call("upsample2_fwd", x, y, _dt(x), N, H, W, C, _S())
     return y
@@ -898,6 +900,41 @@ def spade_bwd(dy, x, acc, gamma, beta, act=ACT_LRELU, alpha=0.2, eps=1e-3):
     ws = torch.empty(2 * B, dtype=torch.float64, device=x.device)
     call("spade_bwd", dy, x, acc, gamma, beta, dx, dg, db, ws, B, x.numel() // B, float(eps), act, float(alpha), _S())
     return dx, dg, db
+
+
+def spade_cond_fwd(x, gamma, beta):
+    """layers/spade.py:41-58: x*(1+gamma)+beta"""
+    _chk(x, gamma, beta)
+    assert x.shape == gamma.shape == beta.shape and x.dtype == torch.float32
+    y = torch.empty_like(x)
+    call("spade_cond_fwd", x, gamma, beta, y, x.numel(), _S())
+    return y
+
+
+def spade_cond_bwd(dy, x, gamma):
+    _chk(dy, x, gamma)
+    dx, dg = torch.empty_like(x), torch.empty_like(x)
+    call("spade_cond_bwd", dy, x, gamma, dx, dg, x.numel(), _S())
+    return dx, dg
+
+
+def in_affine_fwd(x, acc, gamma, beta, act=ACT_NONE, alpha=0.0, eps=1e-3):
+    """keras_contrib InstanceNormalization(axis=None) with scalar gamma/beta + activation"""
+    _chk(x, gamma, beta)
+    B = x.shape[0]
+    y = torch.empty_like(x)
+    call("in_affine_fwd", x, acc, gamma, beta, y, B, x.numel() // B, float(eps), act, float(alpha), _S())
+    return y
+
+
+def in_affine_bwd(dy, x, acc, gamma, beta, dgamma, dbeta, act=ACT_NONE, alpha=0.0, eps=1e-3):
+    """returns dx; accumulates the scalar parameter gradients into dgamma / dbeta (None = frozen)"""
+    _chk(dy, x, gamma, beta)
+    B = x.shape[0]
+    dx = torch.empty_like(x)
+    ws = torch.empty(2 * B + 2, dtype=torch.float64, device=x.device)
+    call("in_affine_bwd", dy, x, acc, gamma, beta, dx, dgamma, dbeta, ws, B, x.numel() // B, float(eps), act, float(alpha), _S())
+    return dx
 
 
 def pair_dice(a, b, want_ws=False):

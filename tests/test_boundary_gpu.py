@@ -1,0 +1,196 @@
+"""Public-layer boundary of the reference that round 1 left stubbed ("What's missing" 3-5):
+
+  * ``SPADE_COND()([x, gamma, beta])`` as a layer call (layers/spade.py:41-58) -- against the reference layer's own
+    output (tests/golden/golden_ref.npz) and, forward + backward, against the oracle;
+  * ``normalise('instance')`` = keras_contrib InstanceNormalization() (utils/model_utils.py:6-12) -- forward + backward
+    against a float64 restatement, and inside the UNet conv block (models/unet.py:94-101);
+  * ``Model.inputs`` / ``Model.get_layer(name).output`` and the functional sub-model
+    ``Model(Enc_Modality.inputs, Enc_Modality.get_layer('z_mean').output)`` (models/dafnet.py:126);
+  * MMSDNet runs have no stochastic weight averaging (mmsdnet_executor.py:159-236).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops as R
+from tests.util import cpu, gpu, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_ref.npz"))
+
+
+def test_spade_cond_layer_matches_reference_layer():
+    from multimodal_segmentation_b200 import engine as E
+    from multimodal_segmentation_b200.layers.spade import SPADE_COND
+    x, g, b = gpu(G["film_x"]), gpu(G["spade_gamma"]), gpu(G["spade_beta"])
+    y = SPADE_COND()([E.Var(x), E.Var(g), E.Var(b)])            # keras call style, no-gradient context
+    assert rel_l2(cpu(y.data), G["spade_y"]) < 1e-6
+    assert SPADE_COND().compute_output_shape([(None, 6, 5, 8)] * 3) == (None, 6, 5, 8)
+
+
+@pytest.mark.parametrize("shape", [(2, 6, 5, 8), (3, 16, 24, 128), (1, 7, 3, 3)])
+def test_spade_cond_forward_backward(shape):
+    from multimodal_segmentation_b200 import engine as E
+    from multimodal_segmentation_b200.layers.spade import SPADE_COND
+    rs = np.random.RandomState(sum(shape))
+    x, g, b, dy = [rs.normal(size=shape).astype(np.float32) for _ in range(4)]
+    xt, gt, bt = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, g, b)]
+    yr = R.spade_cond(xt, gt, bt)
+    (yr * torch.tensor(dy, dtype=torch.float64)).sum().backward()
+    tape = E.Tape()
+    ctx = E.Ctx(tape, True)
+    vx, vg, vb = E.Var(gpu(x), True), E.Var(gpu(g), True), E.Var(gpu(b), True)
+    y = SPADE_COND()(ctx, [vx, vg, vb])
+    y.grad = gpu(dy)
+    tape.backward()
+    assert rel_l2(cpu(y.data), yr.detach().numpy()) < 1e-6
+    assert rel_l2(cpu(vx.grad), xt.grad.numpy()) < 1e-6
+    assert rel_l2(cpu(vg.grad), gt.grad.numpy()) < 1e-6
+    assert rel_l2(cpu(vb.grad), bt.grad.numpy()) < 1e-6
+
+
+def _instance_norm_ref(x, gamma, beta, act, eps=1e-3):
+    """keras_contrib InstanceNormalization(axis=None): (x - mean) / (std + eps) * gamma + beta, per sample over H,W,C"""
+    mean = x.mean(dim=(1, 2, 3), keepdim=True)
+    std = torch.sqrt(((x - mean) ** 2).mean(dim=(1, 2, 3), keepdim=True))
+    y = (x - mean) / (std + eps) * gamma + beta
+    return torch.relu(y) if act == "relu" else y
+
+
+@pytest.mark.parametrize("act", [None, "relu"])
+@pytest.mark.parametrize("shape", [(2, 8, 8, 4), (3, 20, 12, 64)])
+def test_instance_norm_layer(shape, act):
+    from multimodal_segmentation_b200 import engine as E
+    rs = np.random.RandomState(sum(shape) + (act is not None))
+    x = (rs.normal(size=shape) * 2 + 0.7).astype(np.float32)
+    dy = rs.normal(size=shape).astype(np.float32)
+    arena = E.Arena(True)
+    layer = E.InstanceNorm(arena, "in")
+    arena.to_device()
+    layer.gamma.data.fill_(1.3)
+    layer.beta.data.fill_(-0.2)
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    gt = torch.tensor(1.3, dtype=torch.float64, requires_grad=True)
+    bt = torch.tensor(-0.2, dtype=torch.float64, requires_grad=True)
+    yr = _instance_norm_ref(xt, gt, bt, act)
+    (yr * torch.tensor(dy, dtype=torch.float64)).sum().backward()
+    tape = E.Tape()
+    vx = E.Var(gpu(x), True)
+    y = layer(E.Ctx(tape, True), vx, act)
+    y.grad = gpu(dy)
+    tape.backward()
+    assert rel_l2(cpu(y.data), yr.detach().numpy()) < 1e-5
+    assert rel_l2(cpu(vx.grad), xt.grad.numpy()) < 1e-4
+    assert abs(float(layer.gamma.grad.item()) - float(gt.grad)) < 1e-4 * max(1.0, abs(float(gt.grad)))
+    assert abs(float(layer.beta.grad.item()) - float(bt.grad)) < 1e-4 * max(1.0, abs(float(bt.grad)))
+    # the inference phase uses the same per-sample statistics (no moving averages)
+    y2 = layer(E.Ctx(None, False), E.Var(gpu(x)), act)
+    assert torch.equal(y2.data, y.data)
+
+
+def test_unet_conv_block_with_instance_normalisation():
+    """models/unet.py:94-101 with conf.normalise = 'instance'"""
+    from multimodal_segmentation_b200 import engine as E
+    from multimodal_segmentation_b200.keras_like import BuildScope
+    from multimodal_segmentation_b200.models.unet import ConvBlock, normalise
+    old = E.USE_TC
+    E.USE_TC = False
+    try:
+        with BuildScope(seed=3) as sc:
+            blk = ConvBlock(sc, "b", 4, 8, "instance")
+            assert isinstance(normalise(sc.arena, sc.state, "x", 8, "instance"), E.InstanceNorm)
+            assert normalise(sc.arena, sc.state, "y", 8, None) is None
+        sc.arena.to_device()
+        sc.state.to_device()
+        rs = np.random.RandomState(0)
+        x = rs.normal(size=(2, 12, 12, 4)).astype(np.float32)
+        tape = E.Tape()
+        vx = E.Var(gpu(x), True)
+        y = blk(E.Ctx(tape, True), vx)
+        y.grad = gpu(rs.normal(size=(2, 12, 12, 8)).astype(np.float32))
+        tape.backward()
+        W = {p.name: torch.tensor(p.numpy(), dtype=torch.float64) for l in blk.layers() for p in l.params()}
+        xt = torch.tensor(x, dtype=torch.float64)
+        h = R.conv2d(xt, W["b_conv1/kernel"], W["b_conv1/bias"], 1, "same")
+        h = _instance_norm_ref(h, W["b_bn1/gamma"], W["b_bn1/beta"], "relu")
+        h = R.conv2d(h, W["b_conv2/kernel"], W["b_conv2/bias"], 1, "same")
+        h = _instance_norm_ref(h, W["b_bn2/gamma"], W["b_bn2/beta"], "relu")
+        assert rel_l2(cpu(y.data), h.numpy()) < 1e-4
+        assert vx.grad is not None and np.isfinite(cpu(vx.grad)).all()
+    finally:
+        E.USE_TC = old
+
+
+def test_model_inputs_get_layer_and_functional_submodel():
+    """models/dafnet.py:126: Enc_Modality_mu = Model(Enc_Modality.inputs, Enc_Modality.get_layer('z_mean').output)"""
+    from multimodal_segmentation_b200 import engine as E
+    from multimodal_segmentation_b200.configuration import dafnet_config_chaos
+    from multimodal_segmentation_b200.keras_like import EasyDict, Model
+    from multimodal_segmentation_b200.models.dafnet import DAFNet
+    old = E.USE_TC
+    E.USE_TC = False
+    try:
+        conf = EasyDict(dafnet_config_chaos.get((64, 64, 1)))
+        conf.anatomy_encoder.filters = 16
+        conf.n_pairs = 1
+        conf.folder = "/tmp/dafk_test_no_such_folder"
+        net = DAFNet(conf)
+        net.build()
+        enc = net.Enc_Modality
+        assert [i.shape for i in enc.inputs] == [(None, 64, 64, 8), (None, 64, 64, 1)]
+        assert enc.input_shape == [(None, 64, 64, 8), (None, 64, 64, 1)]
+        lay = enc.get_layer("z_mean")
+        assert lay.name == "z_mean" and [w.shape for w in lay.get_weights()] == [(32, 8), (8,)]
+        with pytest.raises(ValueError):
+            enc.get_layer("no_such_layer")
+        mu_model = Model(enc.inputs, enc.get_layer("z_mean").output)
+        assert mu_model.output_shape == (None, 8) and mu_model.layers[-1] is lay.layer
+        assert net.Enc_Modality_mu.name == "Enc_Modality_mu"
+        rs = np.random.RandomState(1)
+        s = rs.uniform(size=(3, 64, 64, 8)).astype(np.float32)
+        x = rs.uniform(-1, 1, size=(3, 64, 64, 1)).astype(np.float32)
+        mu, lv = enc.predict([s, x])
+        assert np.array_equal(mu_model.predict([s, x]), mu)
+        assert np.array_equal(net.Enc_Modality_mu.predict([s, x]), mu)
+        lv_model = Model(enc.inputs, enc.get_layer("z_log_var").output, name="lv")
+        assert np.array_equal(lv_model.predict([s, x]), lv)
+        # the sub-model shares the weights: changing the layer changes both
+        w, b = lay.get_weights()
+        lay.set_weights([w * 0.0, b + 1.0])
+        assert np.allclose(mu_model.predict([s, x]), 1.0) and np.allclose(enc.predict([s, x])[0], 1.0)
+        with pytest.raises(ValueError):
+            enc.get_layer("encm_conv1").output          # no tap registered for that layer
+    finally:
+        E.USE_TC = old
+
+
+def test_mmsdnet_executor_has_no_weight_averaging(tmp_path, monkeypatch):
+    """mmsdnet_executor.py:159-236: validation and the saved file use the LIVE weights at any epoch"""
+    from multimodal_segmentation_b200 import engine as E
+    from multimodal_segmentation_b200.configuration import mmsdnet_config_chaos
+    from multimodal_segmentation_b200.keras_like import EasyDict
+    from multimodal_segmentation_b200.model_executors.mmsdnet_executor import MMSDNetExecutor
+    from multimodal_segmentation_b200.models.mmsdnet import MMSDNet
+    monkeypatch.setenv("DAFK_INPUT_SHAPE", "64x64x1")
+    monkeypatch.setenv("DAFK_TRAIN_PAIRS", "8")
+    E.USE_TC = True
+    conf = EasyDict(mmsdnet_config_chaos.get((64, 64, 1)))
+    conf.anatomy_encoder.filters = 16
+    conf.l_mix, conf.batch_size, conf.seed = 1.0, 4, 3
+    conf.folder = str(tmp_path / "run")
+    net = MMSDNet(conf)
+    net.build()
+    ex = MMSDNetExecutor(conf, net)
+    assert ex.USE_SWA is False and ex.get_swa_models() == []
+    ex.epoch = ex.SWA_EPOCH + 5                      # DAFNet would validate on the averaged clones from here on
+    losses = {n: [] for n in ex.get_loss_names()}
+    ex.validate(losses)
+    assert len(losses["val_loss_mod2_fused"]) == 1 and np.isfinite(losses["val_loss"][0])
+    ex.save_models()
+    z = np.load(os.path.join(conf.folder, "supervised_trainer.npz"))
+    live = net.Segmentor.get_weights()
+    for p, w in zip(net.Segmentor.weight_list(), live):
+        assert np.array_equal(z[net.Segmentor.name + "/" + p.name], w)

@@ -153,8 +153,6 @@ def test_conv_nc_bulk_rows_forward(ops, case, monkeypatch):
         assert torch.equal(y0, y1) and torch.equal(a0, a1)      # same operands, same MMA order: bit-identical
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DAFK_TEST_EXPERIMENTAL") != "1",
-                    reason="DAFK_NC_L12 role layout: compiled, not yet run on a GPU (no GPU minutes left in round 1)")
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("xdt", ["f32", "bf16"])
 def test_conv_nc_twelve_warp_layout(ops, case, xdt, monkeypatch):
@@ -169,28 +167,6 @@ def test_conv_nc_twelve_warp_layout(ops, case, xdt, monkeypatch):
     y1 = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad)
     torch.cuda.synchronize()
     assert torch.equal(y0, y1)
-
-
-@pytest.mark.skipif(__import__("os").environ.get("DAFK_TEST_EXPERIMENTAL") != "1",
-                    reason="DAFK_NC_L16 (setmaxnreg register split, EB = 8): compiled, not yet run on a GPU")
-@pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("xdt", ["f32", "bf16"])
-def test_conv_nc_register_split_layout(ops, case, xdt, monkeypatch):
-    """four warpgroups with setmaxnreg (producers 120, issuer group 40, epilogue 232 registers; eight tiles in lock step
-    per epilogue warp) must give the default kernel's bits"""
-    from multimodal_segmentation_b200._lib import ACT_LRELU
-    N, H, W, Cin, Cout, k, pad = case
-    r, x, w, b = _mk(case, sum(case) + 9)
-    wp = ops.pack_conv_nc(gpu(w), 0)
-    xg = gpu(x, torch.float32 if xdt == "f32" else torch.bfloat16)
-    monkeypatch.setenv("DAFK_NC_L16", "0")
-    y0 = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad)
-    a0 = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad, ACT_LRELU, 0.3, torch.bfloat16)
-    monkeypatch.setenv("DAFK_NC_L16", "1")
-    y1 = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad)
-    a1 = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad, ACT_LRELU, 0.3, torch.bfloat16)
-    torch.cuda.synchronize()
-    assert torch.equal(y0, y1) and torch.equal(a0, a1)
 
 
 # ------------------------------------------------------------------ stride-2 valid layers through space-to-depth

@@ -68,8 +68,6 @@ PAIR_CASES = [
 ]
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DAFK_TEST_EXPERIMENTAL") != "1",
-                    reason="DAFK_CONV_HALO2 (cta_group::2 pairs): compiled, not yet run on a GPU (round 1 budget spent)")
 @pytest.mark.parametrize("case", PAIR_CASES)
 def test_conv3x3_tc_forward_cta_pairs(ops, case, monkeypatch):
     """tcgen05.mma.cta_group::2 variant of the haloed-tile kernel against the oracle and the single-CTA kernel"""
@@ -93,8 +91,6 @@ def test_conv3x3_tc_forward_cta_pairs(ops, case, monkeypatch):
         assert rel_l2(cpu(y1), cpu(y0)) < 1e-6      # same K order per accumulator
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DAFK_TEST_EXPERIMENTAL") != "1",
-                    reason="DAFK_PACK_TILED (tiled-transpose weight packing): compiled, not yet run on a GPU")
 @pytest.mark.parametrize("shape", [(3, 64, 64), (3, 64, 128), (3, 80, 72), (4, 4, 64), (3, 1024, 512), (1, 128, 8)])
 def test_pack_conv_tiled_transpose_is_bit_identical(ops, shape, monkeypatch):
     k, Cin, Cout = shape
@@ -137,23 +133,6 @@ def test_conv3x3_tc_wgrad(ops, case):
     ops.conv3x3_tc_wgrad(gpu(x, torch.bfloat16), gpu(dy, torch.bfloat16), dw)
     err = rel_l2(cpu(dw), wt.grad.numpy())
     assert err < 1e-3, err
-
-
-@pytest.mark.skipif(__import__("os").environ.get("DAFK_TEST_EXPERIMENTAL") != "1",
-                    reason="DAFK_WGRAD_BN256 (128 x 256 weight-gradient tile): compiled, not yet run on a GPU")
-@pytest.mark.parametrize("case", [(4, 14, 14, 256, 256), (2, 28, 28, 256, 128), (3, 7, 7, 512, 384)])
-def test_conv3x3_tc_wgrad_wide_tile(ops, case, monkeypatch):
-    N, H, W, Cin, Cout = case
-    r = np.random.RandomState(sum(case) + 4)
-    x = bf16_round(r.normal(size=(N, H, W, Cin)).astype(np.float32))
-    dy = bf16_round(r.normal(size=(N, H, W, Cout)).astype(np.float32))
-    wt = torch.zeros(3, 3, Cin, Cout, dtype=torch.float64, requires_grad=True)
-    (R.conv2d(t(x, torch.float64), wt, None, 1, "same") * t(dy, torch.float64)).sum().backward()
-    monkeypatch.setenv("DAFK_WGRAD_BN256", "1")
-    dw = ops.zeros(3, 3, Cin, Cout)
-    ops.conv3x3_tc_wgrad(gpu(x, torch.bfloat16), gpu(dy, torch.bfloat16), dw)
-    torch.cuda.synchronize()
-    assert rel_l2(cpu(dw), wt.grad.numpy()) < 1e-3
 
 
 @pytest.mark.parametrize("case", [(2, 16, 16, 64, 64), (1, 24, 40, 64, 64), (3, 37, 21, 64, 64), (2, 16, 32, 128, 128),

@@ -10,9 +10,7 @@ import torch
 from oracle import ref_ops as R
 from tests.util import rel_l2
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DAFK_TEST_EXPERIMENTAL") != "1",
-                                 reason="wrappers written after the round's GPU minutes were spent; enable once run")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _pair(seed, B=3, H=20, W=24, C=5):

@@ -3,8 +3,8 @@ by tests/golden/make_golden.py from the reference's model_components / models so
 for the same fixtures against the oracle on the CPU).  Weights go in through ``Model.set_weights`` in Keras order, the
 inputs through ``Model.predict`` (inference phase, strict fp32 kernels): fp32 bound 1e-4 relative L2.
 
-Written after the round's GPU minutes were spent: skipped unless DAFK_TEST_EXPERIMENTAL=1 (scripts/round2_first_call.sh
-runs it), and named to run last.
+The golden UNets have 2 filters (the numpy Keras stand-in that produced them is slow): their 2-channel levels take the
+any-channel-count forward kernels (bn_apply / maxpool / nearest resize).  Named to run last.
 """
 import os
 
@@ -13,10 +13,7 @@ import pytest
 
 from tests.util import rel_l2
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DAFK_TEST_EXPERIMENTAL") != "1",
-                                 reason="never run on a GPU yet (2-channel UNet levels, 4-filter discriminator: shapes the "
-                                        "other GPU tests do not use); enable with DAFK_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_builders.npz"))
 S = 48
