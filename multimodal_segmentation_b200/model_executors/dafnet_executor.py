@@ -331,10 +331,22 @@ class DAFNetExecutor(Executor):
         """train_batch on pre-staged (HBM-resident) inputs"""
         if self._graph is not None:
             return self.train_batch_graph(step)
+        self._run_step(step)
+
+    def _run_step(self, step):
+        """the device work of one train_batch on staged inputs (entries whose part is None are skipped)"""
         for kind, g, dm, di in step:
-            self._run_generator(kind == "sup", g)
-            self._run_mask_d(dm)
-            self._run_image_d(di)
+            if g is not None:
+                self._run_generator(kind == "sup", g)
+            if dm is not None:
+                self._run_mask_d(dm)
+            if di is not None and len(di):
+                self._run_image_d(di)
+
+    @staticmethod
+    def _flat(step):
+        """all staged device tensors of a step, in a fixed order"""
+        return [t for _, g, dm, di in step for part in (g, dm, di) if part is not None for t in part]
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
     def enable_cuda_graph(self, warmup=2):
@@ -350,19 +362,13 @@ class DAFNetExecutor(Executor):
         with torch.cuda.stream(side):
             for _ in range(warmup):          # steady state: allocator warm, weights packed, attributes set
                 self._pending = []
-                for kind, g, dm, di in self._static:
-                    self._run_generator(kind == "sup", g)
-                    self._run_mask_d(dm)
-                    self._run_image_d(di)
+                self._run_step(self._static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._pending = []
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            for kind, g, dm, di in self._static:
-                self._run_generator(kind == "sup", g)
-                self._run_mask_d(dm)
-                self._run_image_d(di)
+            self._run_step(self._static)
         self._graph_pending = list(self._pending)     # loss snapshots live in the graph's memory pool
         self._pending = []
         self._graph = graph
@@ -370,18 +376,16 @@ class DAFNetExecutor(Executor):
 
     def train_batch_graph(self, step):
         if step is not self._static:
-            same = all(tuple(a.shape) == tuple(b.shape)
-                       for (_, g, dm, di), (_, sg, sdm, sdi) in zip(step, self._static)
-                       for a, b in zip(list(g) + list(dm) + list(di), list(sg) + list(sdm) + list(sdi)))
+            src_l, dst_l = self._flat(step), self._flat(self._static)
+            same = len(src_l) == len(dst_l) and all(tuple(a.shape) == tuple(b.shape) for a, b in zip(src_l, dst_l))
             if not same:          # ragged last batch of an epoch: run this one step eagerly
                 graph, self._graph = self._graph, None
                 try:
                     return self.train_batch_on(step)
                 finally:
                     self._graph = graph
-            for (_, g, dm, di), (_, sg, sdm, sdi) in zip(step, self._static):
-                for src, dst in zip(list(g) + list(dm) + list(di), list(sg) + list(sdm) + list(sdi)):
-                    dst.copy_(src, non_blocking=True)
+            for src, dst in zip(src_l, dst_l):
+                dst.copy_(src, non_blocking=True)
         self._graph.replay()
         self._pending = list(self._graph_pending)
 

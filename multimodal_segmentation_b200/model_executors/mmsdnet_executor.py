@@ -64,27 +64,34 @@ class MMSDNetExecutor(DAFNetExecutor):
         return [x1[:B].contiguous(), x2[:B].contiguous(), m[:B, ..., 0:nm].contiguous(), self._sample_idx(4 * B, B)]
 
     def stage_step_inputs(self):
+        """mmsdnet_executor.py:238-240: train_batch = the generator updates of the labelled and / or the unlabelled
+        branch (each followed by its Z-regressor update), then ONE mask-discriminator update whatever l_mix.  Step
+        entries are (kind, generator inputs or None, mask-discriminator inputs or None, [])."""
         step = []
         if self.conf.l_mix > 0:
-            step.append(("sup", self._stage_generator(True), self._stage_mask_d(), []))
+            step.append(("sup", self._stage_generator(True), None, []))
         if self.conf.l_mix < 1:
-            step.append(("unsup", self._stage_generator(False), self._stage_mask_d(), []))
+            step.append(("unsup", self._stage_generator(False), None, []))
+        step.append(("dmask", None, self._stage_mask_d(), []))
         return step
+
+    def _run_step(self, step):
+        for kind, g, dm, _ in step:
+            if g is not None:
+                self._run_generator(kind == "sup", g)
+            if dm is not None:
+                self._run_mask_d(dm)
 
     # ------------------------------------------------------------------ step (mmsdnet_executor.py:238-331)
     def train_batch(self, epoch_loss):
         if self._graph is not None:
             return super(MMSDNetExecutor, self).train_batch(epoch_loss)
-        for kind, g, dm, _ in self.stage_step_inputs():
-            self._run_generator(kind == "sup", g)
-            self._run_mask_d(dm)
+        self._run_step(self.stage_step_inputs())
 
     def train_batch_on(self, step):
         if self._graph is not None:
             return self.train_batch_graph(step)
-        for kind, g, dm, _ in step:
-            self._run_generator(kind == "sup", g)
-            self._run_mask_d(dm)
+        self._run_step(step)
 
     def train_batch_generators(self, epoch_loss):
         if self.conf.l_mix > 0:

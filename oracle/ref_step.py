@@ -130,3 +130,113 @@ def dafnet_train_batch_cpu(conf, B, seed=0):
         loss.backward()
         _adam(W, names, {})
     return float(total)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# MMSDNet (model_executors/mmsdnet_executor.py:238-331): generator update, Z-regressor update, one mask-discriminator update
+# ----------------------------------------------------------------------------------------------------------------
+def _mm_enc(Wd, x, i, st, rounding=True):
+    p = "enc%d_" % (i + 1)
+    return RM.anatomy_encoder(Wd, x, st, p, p, rounding=rounding, head_prefix=p)
+
+
+def mmsdnet_zreg_anatomies(Wd, x1, x2, rounding=True):
+    """mmsdnet_executor.py:266-271: the six anatomies the Z regressor is fitted on, predicted in the inference phase --
+    [s1, s2, s1_def, s1_fused, s2_def, s2_fused] with (s1_def, s1_fused) = Fuser([s1, s2]), (s2_def, s2_fused) =
+    Fuser([s2, s1])"""
+    inf = RM.BNState(Wd, training=False)
+    s1, s2 = _mm_enc(Wd, x1, 0, inf, rounding), _mm_enc(Wd, x2, 1, inf, rounding)
+    s1_def, s1_fused, _ = RM.anatomy_fuser(Wd, s1, s2)
+    s2_def, s2_fused, _ = RM.anatomy_fuser(Wd, s2, s1)
+    return [s1, s2, s1_def, s1_fused, s2_def, s2_fused]
+
+
+def mmsdnet_mask_d_candidates(Wd, x1, x2, nm, rounding=True):
+    """mmsdnet_executor.py:319-325: the 4*B fake masks utils.data_utils.sample draws batch_size from --
+    [Segmentor(s1), Segmentor(s2), Segmentor(s1_def), Segmentor(s1_fused)] with (s1_def, s1_fused) = Fuser([s1, s2]),
+    concatenated on the batch axis and cut to the first `nm` channels; inference phase"""
+    inf = RM.BNState(Wd, training=False)
+    s1, s2 = _mm_enc(Wd, x1, 0, inf, rounding), _mm_enc(Wd, x2, 1, inf, rounding)
+    s1_def, s1_fused, _ = RM.anatomy_fuser(Wd, s1, s2)
+    return torch.cat([RM.segmentor(Wd, a, inf)[..., :nm] for a in (s1, s2, s1_def, s1_fused)], 0)
+
+
+def mmsdnet_zreg_loss(W, conf, s_list, z_list):
+    """models/mmsdnet.py:194-208 compiled with 'mae', weight w_rec_Z per output: returns (total, list of the six terms)"""
+    zrec = RM.z_regressor(W, s_list, z_list, conf.get("decoder_type", "film"))
+    terms = [conf["w_rec_Z"] * R.mae(z, r) for z, r in zip(z_list, zrec)]
+    return sum(terms), terms
+
+
+def _mmsdnet_weights(conf):
+    key = ("mmsdnet", tuple(conf.input_shape), conf.decoder_type)
+    if key in _cache:
+        return _cache[key]
+    from multimodal_segmentation_b200.keras_like import BuildScope, EasyDict
+    from multimodal_segmentation_b200.model_components import anatomy_encoder, anatomy_fuser, decoder, modality_encoder, segmentor
+    from multimodal_segmentation_b200.models.discriminator import Discriminator
+    rng = np.random.RandomState(0)
+    W = {}
+    with BuildScope(rng=rng) as sc:
+        encs = [anatomy_encoder.build(conf.anatomy_encoder, "Enc_Anatomy_%s" % m) for m in conf.modality]
+        for i, m in enumerate(encs):
+            for p in m.weight_list():
+                p.name = "enc%d_%s" % (i + 1, p.name)
+        anatomy_fuser.build(conf)
+        modality_encoder.build(conf)
+        segmentor.build(conf)
+        decoder.build(conf)
+        prm = dict(conf.d_mask_params)
+        prm["name"] = "D_Mask"
+        Discriminator(EasyDict(prm)).build()
+    for p in sc.arena.params + sc.state.params:
+        W[p.name] = torch.from_numpy(p.init.copy())
+    _cache[key] = W
+    return W
+
+
+def mmsdnet_train_batch_cpu(conf, B, seed=0):
+    """one MMSDNet `train_batch` (l_mix = 1) on the CPU: supervised generator update, Z-regressor update, mask-discriminator
+    update (mmsdnet_executor.py:238-331).  BASELINE.json config 1 is 66 of these at B = 4."""
+    from multimodal_segmentation_b200.loaders.synthetic_chaos import make_pairs
+    W = dict(_mmsdnet_weights(conf))
+    H = conf.input_shape[0]
+    nm = conf.num_masks
+    rs = np.random.RandomState(seed)
+    x1, x2, m1, m2 = make_pairs(B, (H, H, 1), nm, seed=seed)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32))
+    c = dict(num_masks=nm, decoder_type=conf.decoder_type, w_sup_M=conf.w_sup_M, w_adv_M=conf.w_adv_M,
+             w_rec_X=conf.w_rec_X, w_kl=conf.w_kl, w_rec_Z=conf.w_rec_Z)
+    gen_names = [k for k in W if not k.startswith("D_") and "moving_" not in k]
+    for k in gen_names:
+        W[k] = W[k].clone().requires_grad_(True)
+    eps = [T(rs.normal(size=(B, conf.num_z))) for _ in range(6)]
+    tm1, tm2, tx1, tx2 = T(m1), T(m2), T(x1), T(x2)
+    total, L = RM.mmsdnet_generator_loss(W, c, tx1, tx2, eps, [tm1, tm2, tm2, tm2, tm1, tm1],
+                                         [tx1, tx2, tx2, tx2, tx1, tx1], supervised=True)
+    total.backward()
+    st = {}
+    _adam(W, gen_names, st)
+    # ---- Z regressor (its own optimizer over Decoder + Enc_Modality; the anatomies are inference-phase predictions)
+    with torch.no_grad():
+        Wd = {k: v.detach() for k, v in W.items()}
+        s_list = mmsdnet_zreg_anatomies(Wd, tx1, tx2)
+    z_list = [T(rs.normal(size=(B, conf.num_z))) for _ in range(6)]
+    zr_names = [k for k in gen_names if k.startswith("dec_") or k.startswith("encm_") or k.startswith("z_")]
+    for k in zr_names:
+        W[k] = W[k].detach().clone().requires_grad_(True)
+    ztot, _ = mmsdnet_zreg_loss(W, c, s_list, z_list)
+    ztot.backward()
+    _adam(W, zr_names, {})
+    # ---- mask discriminator
+    with torch.no_grad():
+        Wd = {k: v.detach() for k, v in W.items()}
+        fake = mmsdnet_mask_d_candidates(Wd, tx1, tx2, nm)[rs.choice(4 * B, B, replace=False)]
+    names = [k for k in W if k.startswith("D_Mask_")]
+    for k in names:
+        W[k] = W[k].detach().clone().requires_grad_(True)
+    u0s = [T(rs.uniform(-1, 1, size=(W["D_Mask_conv%d/kernel" % (i + 1)].shape[2] * 16, 1))) for i in range(3)]
+    loss, _ = RM.discriminator_trainer_loss(W, "D_Mask", tm1, fake, u0s)
+    loss.backward()
+    _adam(W, names, {})
+    return float(total.detach())

@@ -401,8 +401,9 @@ class Model(Layer):
         h = _H()
         h.history = {"loss": [float(np.sum(vals))]}
         for name, v in zip(self.output_names(), vals):
-            h.history.setdefault(name + "_loss", [0.0])
-            h.history[name + "_loss"][0] += v
+            key = "%s_loss" % name                    # unnamed sub-models (Enc_Modality_mu): Keras would auto-name them
+            h.history.setdefault(key, [0.0])
+            h.history[key][0] += v
         return h
 
     def load_weights(self, path):

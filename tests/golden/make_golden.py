@@ -554,6 +554,47 @@ def builders():
         mtg = [lab1[..., :4], lab2[..., :4], lab2[..., :4], lab2[..., :4], lab1[..., :4], lab1[..., :4]] + [ones] * 6 + \
             [xs[0], xs[1], xs[1], xs[1], xs[0], xs[0]] + [zero] * 6
         out["mmsd_loss"] = np.array(mnet.supervised_trainer.loss_values([xs[0], xs[1]], mtg))
+        # ---- the MMSDNet executor's step (model_executors/mmsdnet_executor.py:238-331), run UNMODIFIED on this network with
+        #      recording trainers: which anatomies the Z regressor is fitted on, which fake masks the single D_Mask update
+        #      draws from, and the trainer order of train_batch for l_mix in {1, 0.5, 0}
+        from model_executors.mmsdnet_executor import MMSDNetExecutor
+        mex = object.__new__(MMSDNetExecutor)
+        mex.conf, mex.model, mex.loader = dconf, mnet, _Conf(num_masks=4)
+        mx = [f32(rs.uniform(-1, 1, size=(2, S, S, 1))) for _ in range(2)]
+        mm = [np.eye(5)[rs.randint(0, 5, size=(2, S, S))] for _ in range(2)]
+        out["mstep_x1"], out["mstep_x2"] = mx[0].astype(np.float32), mx[1].astype(np.float32)
+        out["mstep_m1"], out["mstep_m2"] = mm[0].astype(np.uint8), mm[1].astype(np.uint8)
+        mex.discriminator_masks = itertools.cycle([mm[0]])
+        mex.discriminator_image = [itertools.cycle([mx[0]]), itertools.cycle([mx[1]])]
+        np.random.seed(41)
+        mex.train_batch_mask_discriminator(defaultdict(list))
+        (mr, mf), mtg_d = mnet.D_Mask_trainer.fit_calls[-1]
+        assert np.array_equal(mr, mm[0][..., :4]) and np.all(mtg_d[0] == 1) and np.all(mtg_d[1] == 0)
+        out["mstep_mask_fake"] = mf.astype(np.float32)
+        mex.gen_labelled = itertools.cycle([(mx[0], mx[1], mm[0][..., :4], mm[1][..., :4])])
+        mex.gen_unlabelled = itertools.cycle([(mx[0], mx[1], mm[0][..., :4])])
+        mnet.supervised_trainer.name, mnet.unsupervised_trainer.name = "supervised_trainer", "unsupervised_trainer"
+        mnet.Z_Regressor.name = "Z_Regressor"
+        for lm in (1, 0.5, 0):
+            KG.STATE["fit_log"] = []
+            mex.conf = _Conf(dconf, l_mix=lm)
+            np.random.seed(42)
+            mex.train_batch(defaultdict(list))
+            out["mmsd_schedule_l_mix_%s" % lm] = np.array(KG.STATE["fit_log"])
+        mex.conf = _Conf(dconf, l_mix=1)
+        np.random.seed(43)
+        mex.train_batch_generators(defaultdict(list))
+        (g_in, g_tg) = mnet.supervised_trainer.fit_calls[-1]
+        m14a, m14b = mm[0][..., :4], mm[1][..., :4]
+        exp_tg = [m14a, m14b, m14b, m14b, m14a, m14a] + [np.ones((2, 1))] * 6 + [mx[0], mx[1], mx[1], mx[1], mx[0], mx[0]] + \
+            [np.zeros(2)] * 6
+        assert len(g_in) == 2 and np.array_equal(g_in[0], mx[0]) and np.array_equal(g_in[1], mx[1])
+        assert len(g_tg) == 24 and all(np.array_equal(a, b) for a, b in zip(g_tg, exp_tg))
+        (z_in, z_tg) = mnet.Z_Regressor.fit_calls[-1]
+        assert len(z_in) == 12 and len(z_tg) == 6 and all(np.array_equal(a, b) for a, b in zip(z_in[6:], z_tg))
+        for i in range(6):
+            out["mstep_zreg_s%d" % i] = np.asarray(z_in[i], np.float32)[:, ::2, ::2]
+        out["mmsd_executor_targets_checked"] = np.array(1)
     path = os.path.join(HERE, "golden_builders.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024.0))

@@ -278,10 +278,7 @@ def test_automated_pairing_graph_matches_the_reference_trainer(net):
     assert np.allclose([v.item() for v in Lu.values()], G["auto_unsup_loss"], rtol=1e-4, atol=1e-6)
 
 
-def test_mmsdnet_graph_matches_the_reference_trainer():
-    """models/mmsdnet.py:62-192: two independent anatomy encoders (each with its own 1x1 head), the deformed and the
-    fused anatomies segmented, re-encoded and decoded, one D_Mask: the reference supervised trainer's 24 outputs against
-    the oracle's `mmsdnet_generator_loss` (inference phase, one reparametrisation noise array for the six samplings)"""
+def _mmsdnet_golden_weights():
     from multimodal_segmentation_b200.configuration import mmsdnet_config_chaos
     from multimodal_segmentation_b200.keras_like import EasyDict
     from multimodal_segmentation_b200.models.mmsdnet import MMSDNet
@@ -296,6 +293,36 @@ def test_mmsdnet_graph_matches_the_reference_trainer():
     for tag, m in (("enc1", n.Encoders_Anatomy[0]), ("enc2", n.Encoders_Anatomy[1]), ("encm", n.Enc_Modality),
                    ("fuser", n.Anatomy_Fuser), ("seg", n.Segmentor), ("dec", n.Decoder), ("dmask", n.D_Mask)):
         W.update(weights_of(m, "mmsd_" + tag))
+    return W
+
+
+def test_mmsdnet_step_matches_the_reference_executor():
+    """model_executors/mmsdnet_executor.py:238-331 run UNMODIFIED on the reference MMSDNet of the golden run (recording
+    trainers): the 4*B fake masks the single D_Mask update samples from, the six inference-phase anatomies the Z regressor
+    is fitted on, the trainer order of `train_batch` for l_mix in {1, 0.5, 0} -- ONE mask-discriminator update per
+    train_batch whatever l_mix -- and (asserted inside the generator) the 24 targets of the supervised trainer."""
+    from oracle import ref_step as RS
+    from multimodal_segmentation_b200.utils import data_utils
+    assert int(G["mmsd_executor_targets_checked"]) == 1
+    W = _mmsdnet_golden_weights()
+    x1, x2 = t(G["mstep_x1"]), t(G["mstep_x2"])
+    cand = RS.mmsdnet_mask_d_candidates(W, x1, x2, 4)
+    assert tuple(cand.shape) == (8, S, S, 4)
+    np.random.seed(41)
+    close(data_utils.sample(cand.numpy(), 2), "mstep_mask_fake", 1e-4)
+    for i, a in enumerate(RS.mmsdnet_zreg_anatomies(W, x1, x2)):
+        close(a[:, ::2, ::2], "mstep_zreg_s%d" % i, 1e-4)
+    assert list(G["mmsd_schedule_l_mix_1"]) == ["supervised_trainer", "Z_Regressor", "D_Mask_trainer"]
+    assert list(G["mmsd_schedule_l_mix_0"]) == ["unsupervised_trainer", "Z_Regressor", "D_Mask_trainer"]
+    assert list(G["mmsd_schedule_l_mix_0.5"]) == ["supervised_trainer", "Z_Regressor", "unsupervised_trainer", "Z_Regressor",
+                                                  "D_Mask_trainer"]
+
+
+def test_mmsdnet_graph_matches_the_reference_trainer():
+    """models/mmsdnet.py:62-192: two independent anatomy encoders (each with its own 1x1 head), the deformed and the
+    fused anatomies segmented, re-encoded and decoded, one D_Mask: the reference supervised trainer's 24 outputs against
+    the oracle's `mmsdnet_generator_loss` (inference phase, one reparametrisation noise array for the six samplings)"""
+    W = _mmsdnet_golden_weights()
     x1, x2, eps = t(G["trainer_in0"]), t(G["trainer_in1"]), t(G["trainer_in4"])
     dummy_m = [torch.zeros(x1.shape[0], S, S, 5, dtype=torch.float64)] * 6
     dummy_x = [x1] * 6
