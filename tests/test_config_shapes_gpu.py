@@ -1,0 +1,258 @@
+"""Parity at the shapes bench.py runs: the kernel tests elsewhere use small maps; here the
+tensor-core, raster-strip and BatchNorm kernels run at 224 x 224 (config 2) and the inference path at 512 x 512
+(config 5), against torch-CPU on the same bf16-rounded operands.
+
+Oracle arithmetic: fp32 on the CPU (fp64 would take minutes at these sizes); its own accumulation error over K <= 18432
+is ~1e-6, the bound is 1e-4 (fp32 tolerance of north_star; operands are rounded to bf16 first, so the comparison is
+"same operands, different accumulation order").
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def _bf(a):
+    return torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(BF).float()
+
+
+def _conv_ref(x, w, b, stride, pad):
+    """x NHWC fp32 (CPU), w HWIO"""
+    y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, stride=stride, padding=pad)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from multimodal_segmentation_b200 import ops as O
+    return O
+
+
+# N, H, W, C0, C1, Cout   -- UNet level 0 (models/unet.py:94-101), its concat layer (:68-69), the bottleneck at B = 32
+TC_CASES = [(2, 224, 224, 64, 0, 64), (2, 224, 224, 64, 64, 64), (32, 14, 14, 1024, 0, 1024)]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_forward_dgrad_wgrad_at_config_shapes(ops, case):
+    N, H, W, C0, C1, Cout = case
+    Cin = C0 + C1
+    rs = np.random.RandomState(sum(case))
+    x = _bf(rs.normal(size=(N, H, W, Cin)))
+    w = _bf(rs.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin))
+    b = torch.from_numpy(rs.normal(size=Cout).astype(np.float32))
+    dy = _bf(rs.normal(size=(N, H, W, Cout)))
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    yr = _conv_ref(xr, wr, b, 1, 1)
+    (yr * dy).sum().backward()
+    xg, wg, dyg = x.cuda().to(BF), w.cuda(), dy.cuda().to(BF)
+    x0 = xg[..., :C0].contiguous()
+    x1 = xg[..., C0:].contiguous() if C1 else None
+    y = ops.conv_tc_fwd(x0, x1, ops.pack_conv(wg, 0), b.cuda(), Cout, 3, 3, 1, 1)
+    assert rel_l2(y.cpu().numpy(), yr.detach().numpy()) < 1e-4
+    # data gradient towards each source (mirrored packed weights, row window = the source's channels)
+    wpd = ops.pack_conv(wg, 1)
+    off = 0
+    for c in ([C0, C1] if C1 else [C0]):
+        dx = ops.conv_tc_fwd(dyg, None, wpd, None, c, 3, 3, 1, 1, torch.float32, row_off=off)
+        assert rel_l2(dx.cpu().numpy(), xr.grad[..., off:off + c].numpy()) < 1e-4
+        off += c
+    # weight gradient (split-K over pixel tiles, fp32 atomics): 1e-3 as in the small-shape tests
+    dw = ops.zeros(3, 3, Cin, Cout)
+    off = 0
+    for src in ([x0, x1] if C1 else [x0]):
+        ops.conv_tc_wgrad(src, dyg, dw, off, 3, 3, 1, 1)
+        off += src.shape[-1]
+    torch.cuda.synchronize()
+    assert rel_l2(dw.cpu().numpy(), wr.grad.numpy()) < 1e-3
+
+
+def test_discriminator_stride2_layer_at_224(ops):
+    """models/discriminator.py:24,39: 4x4 stride-2 valid convolutions; 64 -> 128 on the 111 x 111 map of a 224 x 224 input"""
+    N, H, Cin, Cout = 2, 111, 64, 128
+    rs = np.random.RandomState(3)
+    x = _bf(rs.normal(size=(N, H, H, Cin)))
+    w = _bf(rs.normal(size=(4, 4, Cin, Cout)) / np.sqrt(16 * Cin))
+    b = torch.from_numpy(rs.normal(size=Cout).astype(np.float32))
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = _conv_ref(xr, wr, b, 2, 0)
+    dy = _bf(rs.normal(size=tuple(yr.shape)))
+    (yr * dy).sum().backward()
+    xg, wg, dyg = x.cuda().to(BF), w.cuda(), dy.cuda().to(BF)
+    y = ops.conv_tc_fwd(xg, None, ops.pack_conv(wg, 0), b.cuda(), Cout, 4, 4, 2, 0)
+    assert tuple(y.shape) == tuple(yr.shape) and rel_l2(y.cpu().numpy(), yr.detach().numpy()) < 1e-4
+    dx = torch.zeros((N, H, H, Cin), dtype=torch.float32, device="cuda")      # row / column 110 gets no gradient
+    for pa in (0, 1):
+        for pb in (0, 1):
+            view = dx[:, pa::2, pb::2, :]
+            ops.conv_tc_fwd(dyg, None, ops.pack_conv(wg, 2, pa, pb), None, Cin, 2, 2, 1, 1, torch.float32, out=view)
+    assert rel_l2(dx.cpu().numpy(), xr.grad.numpy()) < 1e-4
+    dw = ops.zeros(4, 4, Cin, Cout)
+    ops.conv_tc_wgrad(xg, dyg, dw, 0, 4, 4, 2, 0)
+    torch.cuda.synchronize()
+    assert rel_l2(dw.cpu().numpy(), wr.grad.numpy()) < 1e-3
+
+
+def test_discriminator_first_layer_at_224():
+    """models/discriminator.py:24: C -> 64, 4x4 stride 2 on the 224 x 224 input (space-to-depth + raster-strip kernels),
+    through the engine layer: forward, input gradient, kernel and bias gradients"""
+    from multimodal_segmentation_b200 import engine as E
+    old = E.USE_TC
+    E.USE_TC = True
+    try:
+        for C in (1, 4):
+            rs = np.random.RandomState(10 + C)
+            arena = E.Arena(True)
+            conv = E.Conv2D(arena, rs, "d0", C, 64, 4, 2, "valid", "he_normal")
+            arena.to_device()
+            x = rs.normal(size=(2, 224, 224, C)).astype(np.float32)
+            xr = _bf(x).requires_grad_(True)
+            wr = _bf(conv.kernel.numpy()).requires_grad_(True)
+            br = torch.from_numpy(conv.bias.numpy()).requires_grad_(True)
+            yr = F.leaky_relu(_conv_ref(xr, wr, br, 2, 0), 0.2)
+            dy = _bf(rs.normal(size=tuple(yr.shape)))
+            (yr * dy).sum().backward()
+            tape = E.Tape()
+            vx = E.Var(torch.from_numpy(x).cuda(), True)
+            y = conv(E.Ctx(tape, True), vx, "lrelu", 0.2)
+            y.grad = dy.cuda()
+            tape.backward()
+            torch.cuda.synchronize()
+            assert rel_l2(y.data.float().cpu().numpy(), yr.detach().numpy()) < 1e-4
+            assert rel_l2(vx.grad.float().cpu().numpy(), xr.grad.numpy()) < 5e-3        # data gradient leaves in bf16
+            assert rel_l2(conv.kernel.grad.cpu().numpy(), wr.grad.numpy()) < 1e-3
+            assert rel_l2(conv.bias.grad.cpu().numpy(), br.grad.numpy()) < 1e-3
+    finally:
+        E.USE_TC = old
+
+
+# FiLM decoder 8 -> 8 (decoder.py:44-54) and the segmentor's first layer 8 -> 64 (segmentor.py:15), full resolution
+@pytest.mark.parametrize("case", [(2, 224, 224, 8, 8), (2, 224, 224, 8, 64), (2, 224, 224, 1, 64)])
+@pytest.mark.parametrize("xdt", ["f32", "bf16"])
+def test_conv_nc_at_config_shapes(ops, case, xdt):
+    N, H, W, Cin, Cout = case
+    rs = np.random.RandomState(sum(case) + 1)
+    x = _bf(rs.normal(size=(N, H, W, Cin)))
+    w = _bf(rs.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin))
+    b = torch.from_numpy(rs.normal(size=Cout).astype(np.float32))
+    dy = _bf(rs.normal(size=(N, H, W, Cout)))
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = _conv_ref(xr, wr, b, 1, 1)
+    (yr * dy).sum().backward()
+    xg = x.cuda() if xdt == "f32" else x.cuda().to(BF)
+    wg, dyg = w.cuda(), dy.cuda()
+    y = ops.conv_nc_fwd(xg, ops.pack_conv_nc(wg, 0), b.cuda(), Cout, 3, 3, 1)
+    assert rel_l2(y.cpu().numpy(), yr.detach().numpy()) < 1e-4
+    if ops.nc_supported(Cin, Cout, 3, 3, W, 1, 1):
+        dx = ops.conv_nc_fwd(dyg, ops.pack_conv_nc(wg, 1), None, Cin, 3, 3, 1)
+        assert rel_l2(dx.cpu().numpy(), xr.grad.numpy()) < 1e-4
+    dw, db = ops.zeros(3, 3, Cin, Cout), ops.zeros(Cout)
+    ops.conv_nc_wgrad(xg, dyg, dw, db, 1)
+    torch.cuda.synchronize()
+    assert rel_l2(dw.cpu().numpy(), wr.grad.numpy()) < 1e-3
+    assert rel_l2(db.cpu().numpy(), dy.sum((0, 1, 2)).numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f32"])
+def test_batchnorm_at_config_shape(ops, dt):
+    """BatchNormalization() on the largest map of the step, 32 x 224 x 224 x 64 (1e8 elements): statistics, moving
+    averages, apply + ReLU and the backward against float64 on the CPU"""
+    from multimodal_segmentation_b200._lib import ACT_RELU
+    N, H, W, C = 32, 224, 224, 64
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(N * H * W, C, generator=g) * 1.5 + 0.3).to(BF).float()
+    dy = torch.randn(N * H * W, C, generator=g).to(BF).float()
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.1
+    xd = x.double()
+    mean = xd.mean(0)
+    var = xd.var(0, unbiased=False)
+    rstd = 1.0 / torch.sqrt(var + 1e-3)
+    xn = (xd - mean) * rstd
+    z = xn * gamma.double() + beta.double()
+    yr = torch.relu(z)
+    dz = dy.double() * (z > 0)
+    dgamma, dbeta = (dz * xn).sum(0), dz.sum(0)
+    M = xd.shape[0]
+    dxr = (gamma.double() * rstd) * (dz - dbeta / M - xn * dgamma / M)
+    tdt = BF if dt == "bf16" else torch.float32
+    xg = x.cuda().to(tdt).view(N, H, W, C)
+    mm, mv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    gmean, grstd = ops.bn_stats_finalize(xg, 1e-3, 0.99, mm, mv)
+    assert rel_l2(gmean.cpu().numpy(), mean.numpy()) < 1e-5
+    assert rel_l2(grstd.cpu().numpy(), rstd.numpy()) < 1e-5
+    assert rel_l2(mm.cpu().numpy(), (0.01 * mean).numpy()) < 1e-5
+    assert rel_l2(mv.cpu().numpy(), (0.99 + 0.01 * var * M / (M - 1)).numpy()) < 1e-5
+    y = ops.bn_apply(xg, gmean, grstd, gamma.cuda(), beta.cuda(), ACT_RELU, tdt)
+    tol = 4e-3 if dt == "bf16" else 1e-5
+    assert rel_l2(y.float().cpu().numpy().reshape(-1, C), yr.numpy()) < tol
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx = ops.bn_bwd(dy.cuda().to(tdt).view(N, H, W, C), xg, gmean, grstd, gamma.cuda(), beta.cuda(), ACT_RELU, dg, db,
+                    dx_dtype=tdt)
+    torch.cuda.synchronize()
+    assert rel_l2(dg.cpu().numpy(), dgamma.numpy()) < 1e-4
+    assert rel_l2(db.cpu().numpy(), dbeta.numpy()) < 1e-4
+    assert rel_l2(dx.float().cpu().numpy().reshape(-1, C), dxr.numpy()) < tol
+
+
+# ------------------------------------------------------------------------------------------------ config 5
+def _inference_net(H):
+    from tests.test_models_gpu import build_net
+    net, conf = build_net(H=H, filters=64, rounding=True, use_tc=True)
+    # move the BatchNorm moving statistics off (0, 1) so that the folded inference path is exercised with real values
+    rs = np.random.RandomState(1)
+    from multimodal_segmentation_b200 import engine as E
+    for m in list(net.Encoders_Anatomy) + [net.Segmentor]:
+        for l in m.layers:
+            if isinstance(l, E.BatchNorm):
+                l.moving_mean.data.copy_(torch.from_numpy(rs.normal(size=l.c).astype(np.float32) * 0.1))
+                l.moving_var.data.copy_(torch.from_numpy(rs.uniform(0.5, 1.5, size=l.c).astype(np.float32)))
+        m._scope.state.version += 1
+    return net, conf
+
+
+def test_predict_mask_at_512_matches_oracle_and_batch_128_is_self_consistent():
+    """BASELINE config 5: segmentor-only inference (anatomy_encoder + segmentor, models/mmsdnet.py:210-224 'simple') at
+    512 x 512.  (1) B = 2 against the fp32 oracle on the CPU: bf16 tensor-core path, Dice within 0.5 %, argmax mismatch
+    below 1 %.  (2) B = 128 (2.1e9 elements per 64-channel map, past 2^31): rows 0..1 of the B = 128 output are the
+    B = 2 output bit for bit, and so are rows 126..127 when the same two images sit there -- any 32-bit index overflow in
+    a kernel breaks this."""
+    from oracle import ref_models as RM
+    from oracle import ref_ops as R
+    from tests.test_models_gpu import all_weights
+    net, conf = _inference_net(512)
+    rs = np.random.RandomState(12)
+    x = rs.uniform(-1, 1, size=(2, 512, 512, 1)).astype(np.float32)
+    W = all_weights(net, torch.float32)
+    with torch.no_grad():
+        ref = RM.predict_mask_simple(W, torch.from_numpy(x), "enc2_", "shared_").numpy()
+    xg = torch.from_numpy(x).cuda()
+    s = net.Encoders_Anatomy[1].predict_device(xg)
+    got = net.Segmentor.predict_device(s).float()
+    got2 = got.cpu().numpy()
+    assert got2.shape == ref.shape == (2, 512, 512, 5)
+    mism = float(np.mean(np.argmax(got2, -1) != np.argmax(ref, -1)))
+    lab = np.eye(5, dtype=np.float64)[np.argmax(ref, -1)][..., :4]
+    d_ref = R.np_dice(lab, ref.astype(np.float64)[..., :4])
+    d_got = R.np_dice(lab, got2.astype(np.float64)[..., :4])
+    print("512^2 B=2: argmax mismatch %.5f, soft dice vs oracle labels: product %.5f oracle %.5f" % (mism, d_got, d_ref))
+    assert mism < 0.01, mism
+    assert abs(d_got - d_ref) <= 0.005 * d_ref, (d_got, d_ref)
+    # ---- B = 128: the same two images first and last, other content in between
+    big = torch.empty((128, 512, 512, 1), dtype=torch.float32, device="cuda")
+    big.uniform_(-1, 1, generator=torch.Generator(device="cuda").manual_seed(3))
+    big[0:2] = xg
+    big[126:128] = xg
+    s_big = net.Encoders_Anatomy[1].predict_device(big)
+    assert s_big.shape[0] == 128 and s_big.numel() == 128 * 512 * 512 * 8
+    out_big = net.Segmentor.predict_device(s_big).float()
+    torch.cuda.synchronize()
+    assert torch.equal(s_big[0:2], s) and torch.equal(s_big[126:128], s)
+    assert torch.equal(out_big[0:2], got) and torch.equal(out_big[126:128], got)
+    assert torch.isfinite(out_big).all()
