@@ -254,11 +254,11 @@ class DAFNetExecutor(Executor):
         # the live weights, so the clones are only built once averaging has started
         averaging = (self.USE_SWA and getattr(self, "epoch", 0) > self.SWA_EPOCH
                      and self.swa_Segmentor.swa_weights is not None)
-        pick = (lambda swa_m, live: swa_m.get_clone_model()) if averaging else (lambda swa_m, live: live)
-        enc0 = pick(self.swa_Enc_Anatomy1, self.model.Encoders_Anatomy[0])
-        enc1 = pick(self.swa_Enc_Anatomy2, self.model.Encoders_Anatomy[1])
-        seg = pick(self.swa_Segmentor, self.model.Segmentor)
-        fuser = pick(self.swa_Anatomy_Fuser, self.model.Anatomy_Fuser)
+        pick = (lambda name, live: getattr(self, name).get_clone_model()) if averaging else (lambda name, live: live)
+        enc0 = pick("swa_Enc_Anatomy1", self.model.Encoders_Anatomy[0])
+        enc1 = pick("swa_Enc_Anatomy2", self.model.Encoders_Anatomy[1])
+        seg = pick("swa_Segmentor", self.model.Segmentor)
+        fuser = pick("swa_Anatomy_Fuser", self.model.Anatomy_Fuser)
         s0 = enc0.predict(x0)
         s1 = enc1.predict(x1)
         mask1 = seg.predict(s0)

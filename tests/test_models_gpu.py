@@ -22,7 +22,7 @@ from tests.util import rel_l2
 pytestmark = pytest.mark.gpu
 
 
-def build_net(H=64, filters=16, rounding=False, use_tc=False, decoder_type="film", seed=3, lr=None):
+def build_net(H=64, filters=16, rounding=False, use_tc=False, decoder_type="film", seed=3, lr=None, downsample=None):
     from multimodal_segmentation_b200 import engine as E
     from multimodal_segmentation_b200.configuration import dafnet_config_chaos
     from multimodal_segmentation_b200.keras_like import EasyDict
@@ -31,6 +31,8 @@ def build_net(H=64, filters=16, rounding=False, use_tc=False, decoder_type="film
     conf = EasyDict(dafnet_config_chaos.get((H, H, 1), decoder_type=decoder_type))
     conf.anatomy_encoder.filters = filters
     conf.anatomy_encoder.rounding = rounding
+    if downsample is not None:
+        conf.anatomy_encoder.downsample = downsample
     conf.n_pairs = 1
     conf.seed = seed
     conf.folder = "/tmp/dafk_test_no_such_folder"
@@ -67,7 +69,7 @@ def make_batch(conf, B, seed=1):
     return x1, x2, z1, z2, e1, e2, res(m1), res(m2)
 
 
-def oracle_step(net, conf, batch, supervised=True, dtype=torch.float64):
+def oracle_step(net, conf, batch, supervised=True, dtype=torch.float64, downsample=None):
     W = all_weights(net, dtype)
     train_names = {p.name for p in net.generator_params()}
     for k in W:
@@ -76,14 +78,18 @@ def oracle_step(net, conf, batch, supervised=True, dtype=torch.float64):
     tb = [torch.from_numpy(a).to(dtype) for a in batch]
     c = dict(num_masks=conf.num_masks, decoder_type=conf.decoder_type, w_sup_M=conf.w_sup_M, w_adv_M=conf.w_adv_M,
              w_rec_X=conf.w_rec_X, w_adv_X=conf.w_adv_X, w_kl=conf.w_kl, w_rec_Z=conf.w_rec_Z)
+    orig = RM.anatomy_encoder
+    extra = {}
     if not conf.anatomy_encoder.rounding:
-        orig = RM.anatomy_encoder
-        RM.anatomy_encoder = lambda *a, **k: orig(*a, rounding=False, **k)
+        extra["rounding"] = False
+    if downsample is not None:
+        extra["downsample"] = downsample
+    if extra:
+        RM.anatomy_encoder = lambda *a, **k: orig(*a, **dict(k, **extra))
     try:
         total, L, inter, st = RM.dafnet_generator_loss(W, c, *tb[:6], tb[6], tb[7] if supervised else None, supervised)
     finally:
-        if not conf.anatomy_encoder.rounding:
-            RM.anatomy_encoder = orig
+        RM.anatomy_encoder = orig
     total.backward()
     return W, total, L, inter, st
 
