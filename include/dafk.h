@@ -273,6 +273,13 @@ int dafk_colsum(const void* x, int x_dt, float* out, int64_t M, int C, void* str
  * The packed weight matrix has w_rows_per_tap rows per tap; this call produces the Cout output
  * channels whose rows start at w_row_off (w_rows_per_tap = Cout, w_row_off = 0 for a plain
  * forward; a data-gradient towards one source of a Concatenate uses a row window). */
+/* Data gradient of a VALID stride-2 convolution with an even kernel (models/discriminator.py:24,39: 4x4 stride 2) as
+ * ONE launch over the four output-parity classes dx[:, pa::2, pb::2, :] (each is a stride-1 convolution of dy with
+ * KH/2 x KW/2 taps).  dy: bf16 [N,Ho,Wo,Cout]; wp4: the four dafk_pack_conv(mode 2, pa, pb) matrices stored back to back
+ * in class order c = 2*pa + pb; w_rows_per_tap / w_row_off select the Cin rows of this source as in dafk_conv_tc_fwd;
+ * dx: [N,H,W,Cin] f32 or bf16, every element written (rows / columns the convolution never read get 0). */
+int dafk_conv_tc_dgrad_s2(const void* dy, int Cout, const void* wp4, int w_rows_per_tap, int w_row_off, void* dx,
+                          int dx_dt, int N, int Ho, int Wo, int Cin, int KH, int KW, int H, int W, void* stream);
 /* dafk_conv_tc_fwd with a fused epilogue activation (NONE or RELU), and the folding of an inference-mode
  * BatchNormalization (utils/model_utils.py:10, Keras learning phase 0) into the convolution that feeds it:
  *   dafk_bn_fold:          scale[c] = gamma / sqrt(moving_var + eps),  bias_out[c] = (conv_bias - moving_mean) * scale + beta
@@ -424,6 +431,27 @@ int dafk_adam_tick(float* state, float lr, float beta1, float beta2, void* strea
 int dafk_adam_step_dev(float* p, const float* g, float* m, float* v, void* bf16_shadow, int64_t n,
                        const float* state, float beta1, float beta2, float eps, float grad_scale,
                        void* stream);
+
+/* ------------------------------------------------------------------ narrow-channel convolutions, HBM-bound ("warp-strip")
+ * Stride-1 convolutions with few channels (Cin <= 64, Cout <= 64 in groups of 8): the FiLM decoder's 8 -> 8 layers
+ * (model_components/decoder.py:44-54), the first layers of the segmentor / UNet / discriminators (8 -> 64, 1 -> 64; the
+ * strided ones through space-to-depth), the modality encoder (model_components/modality_encoder.py:36-42) and the
+ * locnet's 5x5 layers (layers/stn_spline.py:106-112).  csrc/conv_ws.cu: bf16 raster in shared memory, mma.sync with the
+ * accumulators in registers, several CTAs per SM.  Weights are read straight from the fp32 HWIO tensor (no packing pass).
+ *
+ * dafk_conv_ws_fwd: y = act(conv(x, w') + bias).  mode 0: w' = w * scale[Cout] (scale optional: folded inference
+ *   BatchNorm), w_hwio [KH,KW,wCin = Cin,wCout = Cout].  mode 1 (data gradient of a layer with kernel [KH,KW,wCin,wCout]):
+ *   x = dy [N,H,W,Cin = wCout], y = dx [.., Cout = wCin], w'[r,q,co,ci] = w[KH-1-r,KW-1-q,ci,co], pad = KH-1-pad_fwd.
+ *   ya / gact / galpha (optional, gact != DAFK_ACT_NONE): the activation backward of the producing layer fused into the
+ *   staging of the input, x := x * act'(ya) with ya the layer's activation OUTPUT (same shape as x; f32 or bf16).
+ * dafk_conv_ws_wgrad: dw[KH,KW,Cin,Cout] += X (*) dY, db[Cout] += sum dY (db may be NULL); dy := dy * act'(ya) as above.
+ * dafk_conv_ws_supported: kind 0 / 1 forward-type kernel, 2 weight gradient (kernel-view channel counts). */
+int dafk_conv_ws_supported(int Cin, int Cout, int KH, int KW, int W, int pad, int kind);
+int dafk_conv_ws_fwd(const void* x, int x_dt, const void* ya, int ya_dt, int gact, float galpha, const float* w_hwio,
+                     int wCin, int wCout, int mode, const float* scale, const float* bias, void* y, int y_dt, int N, int H,
+                     int W, int Cin, int Cout, int KH, int KW, int pad, int act, float alpha, void* stream);
+int dafk_conv_ws_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, const void* ya, int ya_dt, int gact, float galpha,
+                       float* dw, float* db, int N, int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream);
 
 /* ------------------------------------------------------------------ instance norm + SPADE
  * keras_contrib InstanceNormalization(axis=None, scale=False, center=False) layers/spade.py:27:

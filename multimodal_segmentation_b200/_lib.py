@@ -111,6 +111,17 @@ def call(name, *args):
     L = lib()
     full = name if name.startswith("dafk_") else "dafk_" + name
     f = L.fn[full]
+    from . import instrument as _ins
+    if _ins.trace is not None:        # diagnostic: ordered list of calls with their tensor operands, event-timed
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = f(*[_ptr(a) for a in args])
+        e1.record()
+        _ins.trace.append((name, [(tuple(a.shape), str(a.dtype)[6:]) for a in args if hasattr(a, "numel")], e0, e1))
+        if f.restype is ctypes.c_int and rc != 0:
+            raise DafkError("%s failed (%d): %s" % (full, rc, L.last_error()))
+        return rc
     if PROFILE_ALL:
         from . import instrument
         if instrument.enabled:

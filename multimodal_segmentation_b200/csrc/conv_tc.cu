@@ -31,6 +31,15 @@ struct TileGeom {
   int tiles_x, tiles_y, tiles_n;
 };
 
+// Output-parity classes of a stride-2 data gradient run as ONE launch (n = 4) instead of four small ones: class
+// c = 2*pa + pb reads the same dY pixels with its own packed weights (rows_per_cls further down the weight matrix) and
+// writes dx[:, pa::2, pb::2, :] (element offset pa*off_y + pb*off_x; valid extents (Hf - pa + 1)/2 x (Wf - pb + 1)/2).
+// The class index is the fastest tile coordinate, so the CTAs that run side by side share the dY tile in L2.  n = 1: off.
+struct ClsGeom {
+  int n, rows_per_cls, Hf, Wf;
+  long long off_y, off_x;
+};
+
 // ---------------------------------------------------------------------------------------------
 // forward / dgrad kernel: persistent, one CTA per SM.  Tiles (128 pixels x BLOCK_N channels) are walked
 // round-robin with the channel block fastest (CTAs that run side by side share the activation tile in L2).
@@ -47,7 +56,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
                                                                     int KH, int KW, int stride, int pad, TileGeom g,
                                                                     int n_blocks, int w_rows_per_tap, int w_row_off,
                                                                     long long y_sn, long long y_sy, long long y_sx,
-                                                                    int total_tiles, int act) {
+                                                                    int total_tiles, int act, ClsGeom cg) {
   constexpr int B_BYTES = BLOCK_N * KBLK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;     // two accumulator buffers
@@ -86,12 +95,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
     if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nb = tile % n_blocks;
-        int mt = tile / n_blocks;
+        const int cls = tile % cg.n;
+        const int t2 = tile / cg.n;
+        const int nb = t2 % n_blocks;
+        int mt = t2 / n_blocks;
         const int txi = mt % g.tiles_x; mt /= g.tiles_x;
         const int tyi = mt % g.tiles_y; mt /= g.tiles_y;
         const int x0 = txi * g.TW, y0 = tyi * g.TH, img0 = mt * g.TN;
-        const int n0 = nb * BLOCK_N;
+        const int n0 = nb * BLOCK_N + cls * cg.rows_per_cls;
         for (int src = 0; src < 2; ++src) {
           const int ncbs = src == 0 ? ncb0 : ncb1;
           const CUtensorMap* mA = src == 0 ? &tmA0 : &tmA1;
@@ -151,17 +162,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
     const int tx = m % g.TW, ty = (m / g.TW) % g.TH, tn = m / (g.TW * g.TH);
     int tc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
-      const int nb = tile % n_blocks;
-      int mt = tile / n_blocks;
+      const int cls = tile % cg.n;
+      const int t2 = tile / cg.n;
+      const int nb = t2 % n_blocks;
+      int mt = t2 / n_blocks;
       const int txi = mt % g.tiles_x; mt /= g.tiles_x;
       const int tyi = mt % g.tiles_y; mt /= g.tiles_y;
       const int px = txi * g.TW + tx, py = tyi * g.TH + ty, img = mt * g.TN + tn;
       const int n0 = nb * BLOCK_N;
-      const bool live = px < Wo && py < Ho && img < N;
+      const int pa = cls >> 1, pb = cls & 1;
+      const int Ho_c = cg.n > 1 ? (cg.Hf - pa + 1) / 2 : Ho, Wo_c = cg.n > 1 ? (cg.Wf - pb + 1) / 2 : Wo;
+      const bool live = px < Wo_c && py < Ho_c && img < N;
       const uint32_t b = (uint32_t)tc & 1u;
       mbar_wait(tfull_bar + b, ((uint32_t)tc >> 1) & 1u);
       tc_fence_after();
-      const int64_t obase = (int64_t)img * y_sn + (int64_t)py * y_sy + (int64_t)px * y_sx + n0;
+      const int64_t obase = (int64_t)img * y_sn + (int64_t)py * y_sy + (int64_t)px * y_sx + n0 +
+                            (int64_t)pa * cg.off_y + (int64_t)pb * cg.off_x;
       const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * BLOCK_N;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
@@ -944,7 +960,7 @@ template <int BLOCK_N, int STAGES>
 static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const float* bias, void* y,
                       int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int stride, int pad,
                       const TileGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
-                      long long y_sx, int act, cudaStream_t s) {
+                      long long y_sx, int act, cudaStream_t s, const ClsGeom& cg = ClsGeom{1, 0, 0, 0, 0, 0}) {
   constexpr int smem = STAGES * (A_BYTES + BLOCK_N * KBLK * 2) + 1024 + 256;
   static_assert(smem > 116 * 1024 && smem <= 227 * 1024, "one persistent CTA per SM");
   static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
@@ -954,12 +970,12 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
     configured = true;
   }
   int n_blocks = (Cout + BLOCK_N - 1) / BLOCK_N;
-  int64_t tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n * n_blocks;
+  int64_t tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n * n_blocks * cg.n;
   DAFK_REQUIRE(tiles < (1LL << 31), DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd: too many tiles");
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
   conv_tc_fwd_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1,
                                                                     KH, KW, stride, pad, g, n_blocks, w_rows_per_tap,
-                                                                    w_row_off, y_sn, y_sy, y_sx, (int)tiles, act);
+                                                                    w_row_off, y_sn, y_sy, y_sx, (int)tiles, act, cg);
   return check_launch("dafk_conv_tc_fwd");
 }
 
@@ -1271,6 +1287,44 @@ int dafk_conv_tc_fwd_act(const void* x0, int C0, const void* x1, int C1, const v
   DAFK_REQUIRE(act == DAFK_ACT_NONE || act == DAFK_ACT_RELU, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd_act: act must be NONE or RELU");
   return conv_tc_fwd_impl(x0, C0, x1, C1, wp, w_rows_per_tap, w_row_off, bias, y, y_dt, N, H, W, Cout, KH, KW, stride, pad,
                           Ho, Wo, y_sn, y_sy, y_sx, act, stream);
+}
+
+int dafk_conv_tc_dgrad_s2(const void* dy, int Cout, const void* wp4, int w_rows_per_tap, int w_row_off, void* dx,
+                          int dx_dt, int N, int Ho, int Wo, int Cin, int KH, int KW, int H, int W, void* stream) {
+  DAFK_REQUIRE(N > 0 && Ho > 0 && Wo > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, DAFK_ERR_BAD_ARG,
+               "dafk_conv_tc_dgrad_s2: bad shape");
+  DAFK_REQUIRE(KH % 2 == 0 && KW % 2 == 0, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_dgrad_s2: even kernels only");
+  DAFK_REQUIRE(Ho == (H - KH) / 2 + 1 && Wo == (W - KW) / 2 + 1, DAFK_ERR_BAD_ARG,
+               "dafk_conv_tc_dgrad_s2: dy is not the output of a valid stride-2 convolution of dx");
+  DAFK_REQUIRE(dy && wp4 && dx, DAFK_ERR_BAD_ARG, "dafk_conv_tc_dgrad_s2: null pointer");
+  DAFK_REQUIRE(Cout % 16 == 0 && Cin % 8 == 0, DAFK_ERR_UNSUPPORTED,
+               "dafk_conv_tc_dgrad_s2: Cout must be a multiple of 16, Cin of 8 (Cout=%d Cin=%d)", Cout, Cin);
+  DAFK_REQUIRE(dx_dt == DAFK_F32 || dx_dt == DAFK_BF16, DAFK_ERR_BAD_ARG, "dafk_conv_tc_dgrad_s2: bad output dtype");
+  DAFK_REQUIRE(w_row_off >= 0 && w_row_off + Cin <= w_rows_per_tap, DAFK_ERR_BAD_ARG,
+               "dafk_conv_tc_dgrad_s2: weight row window outside the packed matrix");
+  DAFK_REQUIRE(DAFK_ALIGNED16(dy) && DAFK_ALIGNED16(wp4) && DAFK_ALIGNED16(dx), DAFK_ERR_ALIGN,
+               "dafk_conv_tc_dgrad_s2: pointers must be 16-byte aligned");
+  // every class is a stride-1 convolution of dy with KH/2 x KW/2 taps, padding KH/2 - 1, onto (H+1)/2 x (W+1)/2 outputs
+  const int kh = KH / 2, kw = KW / 2, Hc = (H + 1) / 2, Wc = (W + 1) / 2;
+  TileGeom g = pick_geom(N, Hc, Wc, 1);
+  CUtensorMap a0, b;
+  int rc = make_act_map(&a0, dy, N, Ho, Wo, Cout, g, 1);
+  if (rc) return rc;
+  const int taps = kh * kw;
+  const int Kpad = (Cout + KBLK - 1) / KBLK * KBLK;
+  ClsGeom cg{4, taps * w_rows_per_tap, H, W, (long long)W * Cin, (long long)Cin};
+  const long long y_sn = (long long)H * W * Cin, y_sy = 2LL * W * Cin, y_sx = 2LL * Cin;
+  cudaStream_t s = as_stream(stream);
+  if (Cin % 128 == 0) {
+    rc = make_w_map(&b, wp4, 4 * taps * w_rows_per_tap, Kpad, 128);
+    if (rc) return rc;
+    return launch_fwd<128, 6>(a0, a0, b, nullptr, dx, dx_dt, N, Hc, Wc, Cin, Cout, 0, kh, kw, 1, kh - 1, g, w_rows_per_tap,
+                              w_row_off, y_sn, y_sy, y_sx, DAFK_ACT_NONE, s, cg);
+  }
+  rc = make_w_map(&b, wp4, 4 * taps * w_rows_per_tap, Kpad, 64);
+  if (rc) return rc;
+  return launch_fwd<64, 8>(a0, a0, b, nullptr, dx, dx_dt, N, Hc, Wc, Cin, Cout, 0, kh, kw, 1, kh - 1, g, w_rows_per_tap,
+                           w_row_off, y_sn, y_sy, y_sx, DAFK_ACT_NONE, s, cg);
 }
 
 int dafk_conv3x3_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,

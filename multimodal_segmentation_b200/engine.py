@@ -301,9 +301,8 @@ class Conv2D:
             old = self._packed
             if self.stride == 1:
                 d = ops.pack_conv(w, 1, out=None if old is None else old[2])
-            else:
-                d = {(pa, pb): ops.pack_conv(w, 2, pa, pb, out=None if old is None else old[2][(pa, pb)])
-                     for pa in (0, 1) for pb in (0, 1)}
+            else:       # the four output-parity classes back to back: one data-gradient launch covers them all
+                d = ops.pack_conv_s2_all(w, out=None if old is None else old[2])
             self._packed = (ver, ops.pack_conv(w, 0, out=None if old is None else old[1]), d)
         return self._packed[1], self._packed[2]
 
@@ -314,13 +313,8 @@ class Conv2D:
         if self.stride == 1:
             out = torch.empty((N, H, W, c), dtype=out_dtype, device=g.device)
             return ops.conv_tc_fwd(g, None, wp_d, None, c, k, k, 1, k - 1 - self.pad, out_dtype, row_off=off, out=out)
-        dx = torch.empty((N, H, W, c), dtype=out_dtype, device=g.device)
-        for (pa, pb), wp in wp_d.items():
-            view = dx[:, pa::2, pb::2, :]
-            if view.shape[1] == 0 or view.shape[2] == 0:
-                continue
-            ops.conv_tc_fwd(g, None, wp, None, c, k // 2, k // 2, 1, k // 2 - 1, out_dtype, row_off=off, out=view)
-        return dx
+        return ops.conv_tc_dgrad_s2(g, wp_d, (N, H, W, c), c, k, k, out_dtype, row_off=off,
+                                    rows_per_tap=(self.cin + 63) // 64 * 64)
 
     def __call__(self, ctx, x, act=None, alpha=0.0, out_dtype=None):
         """out_dtype: storage of the convolution output.  The layers that feed a BatchNorm ask for the feature dtype

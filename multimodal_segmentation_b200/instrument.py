@@ -7,6 +7,7 @@ import os
 enabled = False
 by_shape = bool(os.environ.get("DAFK_PROFILE_SHAPES"))    # diagnostic: one record per (family, layer shape)
 _records = {}
+trace = None        # a list while an ordered trace of every C-ABI call is being taken (scripts/trace_step.py)
 
 
 def reset():

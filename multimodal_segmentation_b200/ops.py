@@ -523,6 +523,34 @@ def conv_tc_fwd(x0, x1, wp, bias, Cout, KH, KW, stride, pad, out_dtype=torch.flo
 WGRAD_HALO = os.environ.get("DAFK_WGRAD_HALO", "auto")     # "0" / "1" force the choice (tests, benchmarks)
 
 
+def pack_conv_s2_all(w_hwio, out=None):
+    """the four stride-2 data-gradient operands (dafk_pack_conv mode 2) back to back in class order 2*pa + pb"""
+    KH, KW, Cin, Cout = w_hwio.shape
+    Cip, Cop = (Cin + 63) // 64 * 64, (Cout + 63) // 64 * 64
+    n = (KH // 2) * (KW // 2) * Cip * Cop
+    if out is None:
+        out = torch.empty(4 * n, dtype=torch.bfloat16, device=w_hwio.device)
+    for pa in (0, 1):
+        for pb in (0, 1):
+            pack_conv(w_hwio, 2, pa, pb, out=out[(2 * pa + pb) * n:(2 * pa + pb + 1) * n])
+    return out
+
+
+def conv_tc_dgrad_s2(dy, wp4, x_shape, Cin, KH, KW, out_dtype=torch.float32, row_off=0, rows_per_tap=None):
+    """dx of a valid stride-2 convolution with an even kernel, all four parity classes in one launch"""
+    _chk(dy, wp4)
+    N, H, W, _ = x_shape
+    _, Ho, Wo, Cout = dy.shape
+    rpt = rows_per_tap if rows_per_tap is not None else (Cin + 63) // 64 * 64
+    dx = torch.empty((N, H, W, Cin), dtype=out_dtype, device=dy.device)
+    flops = 2.0 * N * Ho * Wo * KH * KW * Cin * Cout
+    nb = dy.numel() * 2.0 + dx.numel() * dx.element_size()
+    instrument.timed("conv_tc_fwd+dgrad (tcgen05)", flops, nb,
+                     lambda: call("conv_tc_dgrad_s2", dy, Cout, wp4, rpt, row_off, dx, _dt(dx), N, Ho, Wo, Cin, KH, KW, H, W, _S()),
+                     tag=(N, Ho, Wo, Cout, Cin, KH, "s2-dgrad"))
+    return dx
+
+
 def _wgrad_halo(Cin, Cout, KH, KW, stride, pad):
     if not (KH == 3 and KW == 3 and stride == 1 and pad == 1 and Cin % 64 == 0 and Cout % 64 == 0):
         return False
@@ -624,6 +652,50 @@ def conv_nc_wgrad(x, dy, dw, db, pad):
     instrument.timed("conv_nc_wgrad (tcgen05)", fl, nb,
                      lambda: call("conv_nc_wgrad", x, _dt(x), dy, _dt(dy), dw, db, N, H, W, Cin, Cout, KH, KW, pad, _S()),
                      tag=(N, H, W, Cin, Cout, KH, pad, str(x.dtype)[6:], str(dy.dtype)[6:]))
+
+
+# ---------------------------------------------------------------------------- narrow-channel convolutions, warp-strip kernels
+USE_WS = os.environ.get("DAFK_CONV_WS", "1") != "0"       # "0": fall back to the tcgen05 raster-strip kernels (conv_nc)
+
+
+def ws_supported(Cin, Cout, KH, KW, W, pad, kind):
+    """csrc/conv_ws.cu handles this layer (kernel-view channel counts; kind 0/1 forward-type, 2 weight gradient)"""
+    return USE_WS and bool(_lib.lib().fn["dafk_conv_ws_supported"](Cin, Cout, KH, KW, W, pad, kind))
+
+
+def conv_ws_fwd(x, w, bias, pad, act=ACT_NONE, alpha=0.0, out_dtype=torch.float32, mode=0, scale=None, ya=None,
+                gact=ACT_NONE, galpha=0.0):
+    """mode 0: y = act(conv(x, w [* scale]) + bias), stride 1, w the fp32 HWIO kernel [KH,KW,Cin,Cout].
+    mode 1: data gradient of that layer: x = dy [N,Ho,Wo,Cout] -> dx [N,H,W,Cin]; `pad` is the padding of the
+    gradient convolution (KH - 1 - pad_forward).  ya/gact/galpha: x := x * act'(ya) while it is staged."""
+    _chk(x, w, bias, scale, ya)
+    N, H, W, Cx = x.shape
+    KH, KW, wCin, wCout = w.shape
+    Cin, Cout = (wCin, wCout) if mode == 0 else (wCout, wCin)
+    assert Cx == Cin, (tuple(x.shape), tuple(w.shape), mode)
+    Ho, Wo = H + 2 * pad - KH + 1, W + 2 * pad - KW + 1
+    y = torch.empty((N, Ho, Wo, Cout), dtype=out_dtype, device=x.device)
+    fl = 2.0 * N * Ho * Wo * Cout * KH * KW * Cin
+    nb = x.numel() * x.element_size() + y.numel() * y.element_size() + (0 if ya is None else ya.numel() * ya.element_size())
+    instrument.timed("conv_ws_fwd+dgrad (mma.sync, HBM-bound)", fl, nb,
+                     lambda: call("conv_ws_fwd", x, _dt(x), ya, 0 if ya is None else _dt(ya), int(gact), float(galpha), w, wCin,
+                                  wCout, mode, scale, bias, y, _dt(y), N, H, W, Cin, Cout, KH, KW, pad, int(act), float(alpha),
+                                  _S()),
+                     tag=(N, H, W, Cin, Cout, KH, pad, str(x.dtype)[6:], str(out_dtype)[6:], "g" if ya is not None else ""))
+    return y
+
+
+def conv_ws_wgrad(x, dy, dw, db, pad, ya=None, gact=ACT_NONE, galpha=0.0):
+    """dw[KH,KW,Cin,Cout] += x (*) dy', db += sum dy' (db may be None), dy' = dy * act'(ya); stride 1"""
+    _chk(x, dy, dw, db, ya)
+    N, H, W, Cin = x.shape
+    KH, KW, _, Cout = dw.shape
+    fl = 2.0 * dy.numel() * KH * KW * Cin
+    nb = x.numel() * x.element_size() + dy.numel() * dy.element_size() + (0 if ya is None else ya.numel() * ya.element_size())
+    instrument.timed("conv_ws_wgrad (mma.sync, HBM-bound)", fl, nb,
+                     lambda: call("conv_ws_wgrad", x, _dt(x), dy, _dt(dy), ya, 0 if ya is None else _dt(ya), int(gact),
+                                  float(galpha), dw, db, N, H, W, Cin, Cout, KH, KW, pad, _S()),
+                     tag=(N, H, W, Cin, Cout, KH, pad, str(x.dtype)[6:], str(dy.dtype)[6:], "g" if ya is not None else ""))
 
 
 # ---------------------------------------------------------------------------- pointwise 64 -> <=8 heads

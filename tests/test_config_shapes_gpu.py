@@ -93,6 +93,10 @@ def test_discriminator_stride2_layer_at_224(ops):
             view = dx[:, pa::2, pb::2, :]
             ops.conv_tc_fwd(dyg, None, ops.pack_conv(wg, 2, pa, pb), None, Cin, 2, 2, 1, 1, torch.float32, out=view)
     assert rel_l2(dx.cpu().numpy(), xr.grad.numpy()) < 1e-4
+    # the same four parity classes as ONE launch (what the engine uses): bit-identical to the per-class launches
+    dx4 = ops.conv_tc_dgrad_s2(dyg, ops.pack_conv_s2_all(wg), (N, H, H, Cin), Cin, 4, 4)
+    torch.cuda.synchronize()
+    assert torch.equal(dx4, dx)
     dw = ops.zeros(4, 4, Cin, Cout)
     ops.conv_tc_wgrad(xg, dyg, dw, 0, 4, 4, 2, 0)
     torch.cuda.synchronize()
@@ -259,7 +263,14 @@ def test_predict_mask_at_512_batch_128_is_self_consistent_and_matches_oracle():
     real = fixed[7][:2, ..., :4].astype(np.float64)
     d_ref = R.np_dice(real, ref.astype(np.float64)[..., :4])
     d_got = R.np_dice(real, got2.astype(np.float64)[..., :4])
+    # the Dice the reference reports is always the binarised one (model_tester.py:74, dafnet_executor.py:341-347)
+    b_ref = R.np_dice(real, ref.astype(np.float64)[..., :4], binarise=True)
+    b_got = R.np_dice(real, got2.astype(np.float64)[..., :4], binarise=True)
     err = rel_l2(got2, ref)
-    print("512^2 B=2: soft masks rel-L2 %.4f, argmax mismatch %.5f, soft dice product %.5f oracle %.5f" % (err, mism, d_got, d_ref))
+    print("512^2 B=2: soft masks rel-L2 %.4f, argmax mismatch %.5f, dice(binarised) product %.5f oracle %.5f, soft dice %.5f / %.5f"
+          % (err, mism, b_got, b_ref, d_got, d_ref))
     assert mism < 0.01, mism
-    assert abs(d_got - d_ref) <= 0.005 * max(d_ref, 1e-9), (d_got, d_ref)
+    assert err < 5e-2, err
+    if b_ref > 0.02:                         # the briefly trained net predicts organs (else the ratio measures nothing)
+        assert abs(b_got - b_ref) <= 0.005 * b_ref, (b_got, b_ref)
+    assert abs(d_got - d_ref) <= 0.02 * max(d_ref, 1e-9), (d_got, d_ref)

@@ -226,3 +226,28 @@ def test_conv_tc_general_fwd_dgrad_wgrad(ops, case):
     assert rel_l2(cpu(xv.grad), xt.grad.numpy()) < 5e-3          # dx is stored as bf16
     assert rel_l2(cpu(conv.kernel.grad), wt.grad.numpy()) < 1e-3
     assert rel_l2(cpu(conv.bias.grad), dy.sum((0, 1, 2))) < 1e-3
+
+
+@pytest.mark.parametrize("case", [(2, 20, 20, 64, 64, 4), (2, 21, 23, 64, 128, 4), (3, 14, 13, 128, 64, 4), (1, 9, 10, 128, 256, 2),
+                                  (33, 27, 27, 64, 128, 4)])
+def test_conv_tc_stride2_dgrad_all_parity_classes_in_one_launch(ops, case):
+    """dafk_conv_tc_dgrad_s2: data gradient of a valid stride-2 convolution with an even kernel (models/discriminator.py:
+    24,39) -- odd and even input extents (rows / columns the convolution never read must come out 0), Cin of 64 and 128
+    (both tile widths), a batch that does not divide the image box"""
+    N, H, W, Cin, Cout, k = case
+    r = np.random.RandomState(sum(case) + 3)
+    w = bf16_round((r.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(np.float32))
+    Ho, Wo = (H - k) // 2 + 1, (W - k) // 2 + 1
+    dy = bf16_round(r.normal(size=(N, Ho, Wo, Cout)).astype(np.float32))
+    xt = torch.zeros(N, H, W, Cin, dtype=torch.float64, requires_grad=True)
+    (R.conv2d(xt, t(w, torch.float64), None, 2, "valid") * t(dy, torch.float64)).sum().backward()
+    wp4 = ops.pack_conv_s2_all(gpu(w))
+    for dt in (torch.float32, torch.bfloat16):
+        dx = ops.conv_tc_dgrad_s2(gpu(dy, torch.bfloat16), wp4, (N, H, W, Cin), Cin, k, k, dt)
+        assert dx.dtype == dt and tuple(dx.shape) == (N, H, W, Cin)
+        assert rel_l2(cpu(dx), xt.grad.numpy()) < (1e-4 if dt == torch.float32 else 4e-3)
+    # a source that is a channel window of a wider kernel (second source of a Concatenate)
+    if Cin == 128:
+        dxw = ops.conv_tc_dgrad_s2(gpu(dy, torch.bfloat16), wp4, (N, H, W, 64), 64, k, k, torch.float32, row_off=64,
+                                   rows_per_tap=128)
+        assert rel_l2(cpu(dxw), xt.grad.numpy()[..., 64:]) < 1e-4
