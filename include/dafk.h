@@ -71,6 +71,10 @@ int dafk_act_fwd(const float* x, float* y, int64_t n, int act, float alpha, void
 int dafk_act_bwd(const float* dy, const float* y, float* dx, int64_t n, int act, float alpha,
                  void* stream);
 /* same, with dx written as bf16 (operand dtype of the tensor-core gradient kernels); n % 4 == 0 */
+/* dx = (dy1 + dy2) * act'(y): the two gradients of a map with two consumers (model_components/decoder.py:44-54: l1 feeds
+ * conv2 and the residual Add) summed inside the activation backward; dx may alias dy1 or dy2; n % 4 == 0. */
+int dafk_add_act_bwd(const float* dy1, const float* dy2, const float* y, float* dx, int64_t n, int act, float alpha,
+                     void* stream);
 int dafk_act_bwd_bf16(const float* dy, const float* y, void* dx, int64_t n, int act, float alpha, void* stream);
 /* out = a + b (keras Add, decoder.py:53, spade.py:23); out may alias a or b */
 int dafk_add(const float* a, const float* b, float* out, int64_t n, void* stream);
@@ -284,11 +288,13 @@ int dafk_conv_tc_dgrad_s2(const void* dy, int Cout, const void* wp4, int w_rows_
  * BatchNormalization (utils/model_utils.py:10, Keras learning phase 0) into the convolution that feeds it:
  *   dafk_bn_fold:          scale[c] = gamma / sqrt(moving_var + eps),  bias_out[c] = (conv_bias - moving_mean) * scale + beta
  *   dafk_pack_conv_scaled: forward operand of w[KH,KW,Cin,Cout] * scale[Cout] (as dafk_pack_conv mode 0)
- * conv -> BN -> ReLU of a predict pass then is ONE kernel: dafk_conv_tc_fwd_act(..., bias_out, ..., DAFK_ACT_RELU). */
+ * conv -> BN -> ReLU of a predict pass then is ONE kernel: dafk_conv_tc_fwd_act(..., bias_out, ..., DAFK_ACT_RELU, 0).
+ * DAFK_ACT_LRELU with `alpha`: the discriminator's Conv2D -> LeakyReLU(0.2) pairs (models/discriminator.py:24-25,39-40),
+ * whose convolution output is only ever used through the activation. */
 int dafk_conv_tc_fwd_act(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,
                          int w_row_off, const float* bias, void* y, int y_dt, int N, int H, int W, int Cout, int KH,
                          int KW, int stride, int pad, int Ho, int Wo, int64_t y_sn, int64_t y_sy, int64_t y_sx, int act,
-                         void* stream);
+                         float alpha, void* stream);
 int dafk_bn_fold(const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
                  const float* conv_bias, float eps, float* scale, float* bias_out, int C, void* stream);
 int dafk_pack_conv_scaled(const float* w_hwio, const float* scale, void* wp, int KH, int KW, int Cin, int Cout, void* stream);
@@ -431,27 +437,6 @@ int dafk_adam_tick(float* state, float lr, float beta1, float beta2, void* strea
 int dafk_adam_step_dev(float* p, const float* g, float* m, float* v, void* bf16_shadow, int64_t n,
                        const float* state, float beta1, float beta2, float eps, float grad_scale,
                        void* stream);
-
-/* ------------------------------------------------------------------ narrow-channel convolutions, HBM-bound ("warp-strip")
- * Stride-1 convolutions with few channels (Cin <= 64, Cout <= 64 in groups of 8): the FiLM decoder's 8 -> 8 layers
- * (model_components/decoder.py:44-54), the first layers of the segmentor / UNet / discriminators (8 -> 64, 1 -> 64; the
- * strided ones through space-to-depth), the modality encoder (model_components/modality_encoder.py:36-42) and the
- * locnet's 5x5 layers (layers/stn_spline.py:106-112).  csrc/conv_ws.cu: bf16 raster in shared memory, mma.sync with the
- * accumulators in registers, several CTAs per SM.  Weights are read straight from the fp32 HWIO tensor (no packing pass).
- *
- * dafk_conv_ws_fwd: y = act(conv(x, w') + bias).  mode 0: w' = w * scale[Cout] (scale optional: folded inference
- *   BatchNorm), w_hwio [KH,KW,wCin = Cin,wCout = Cout].  mode 1 (data gradient of a layer with kernel [KH,KW,wCin,wCout]):
- *   x = dy [N,H,W,Cin = wCout], y = dx [.., Cout = wCin], w'[r,q,co,ci] = w[KH-1-r,KW-1-q,ci,co], pad = KH-1-pad_fwd.
- *   ya / gact / galpha (optional, gact != DAFK_ACT_NONE): the activation backward of the producing layer fused into the
- *   staging of the input, x := x * act'(ya) with ya the layer's activation OUTPUT (same shape as x; f32 or bf16).
- * dafk_conv_ws_wgrad: dw[KH,KW,Cin,Cout] += X (*) dY, db[Cout] += sum dY (db may be NULL); dy := dy * act'(ya) as above.
- * dafk_conv_ws_supported: kind 0 / 1 forward-type kernel, 2 weight gradient (kernel-view channel counts). */
-int dafk_conv_ws_supported(int Cin, int Cout, int KH, int KW, int W, int pad, int kind);
-int dafk_conv_ws_fwd(const void* x, int x_dt, const void* ya, int ya_dt, int gact, float galpha, const float* w_hwio,
-                     int wCin, int wCout, int mode, const float* scale, const float* bias, void* y, int y_dt, int N, int H,
-                     int W, int Cin, int Cout, int KH, int KW, int pad, int act, float alpha, void* stream);
-int dafk_conv_ws_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, const void* ya, int ya_dt, int gact, float galpha,
-                       float* dw, float* db, int N, int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream);
 
 /* ------------------------------------------------------------------ instance norm + SPADE
  * keras_contrib InstanceNormalization(axis=None, scale=False, center=False) layers/spade.py:27:

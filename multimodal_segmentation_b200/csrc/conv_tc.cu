@@ -35,6 +35,18 @@ struct TileGeom {
 // c = 2*pa + pb reads the same dY pixels with its own packed weights (rows_per_cls further down the weight matrix) and
 // writes dx[:, pa::2, pb::2, :] (element offset pa*off_y + pb*off_x; valid extents (Hf - pa + 1)/2 x (Wf - pb + 1)/2).
 // The class index is the fastest tile coordinate, so the CTAs that run side by side share the dY tile in L2.  n = 1: off.
+// epilogue activation: NONE, RELU (inference-mode BatchNorm + ReLU folded into the convolution) or LeakyReLU(alpha)
+// (models/discriminator.py:25,40: the convolution output is only ever used through its activation)
+struct Epi {
+  int code;
+  float alpha;
+};
+// selects only; the caller tests code != NONE once per 32-column chunk
+__device__ __forceinline__ float epi_act(float v, int code, float alpha) {
+  const float neg = code == DAFK_ACT_RELU ? 0.f : __fmul_rn(v, alpha);
+  return v > 0.f ? v : neg;
+}
+
 struct ClsGeom {
   int n, rows_per_cls, Hf, Wf;
   long long off_y, off_x;
@@ -56,7 +68,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
                                                                     int KH, int KW, int stride, int pad, TileGeom g,
                                                                     int n_blocks, int w_rows_per_tap, int w_row_off,
                                                                     long long y_sn, long long y_sy, long long y_sx,
-                                                                    int total_tiles, int act, ClsGeom cg) {
+                                                                    int total_tiles, Epi ep, ClsGeom cg) {
   constexpr int B_BYTES = BLOCK_N * KBLK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;     // two accumulator buffers
@@ -161,6 +173,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
     const int m = q4 * 32 + lane;            // row of the tile = pixel
     const int tx = m % g.TW, ty = (m / g.TW) % g.TH, tn = m / (g.TW * g.TH);
     int tc = 0;
+    const int ep_code = ep.code;
+    const float ep_alpha = ep.alpha;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
       const int cls = tile % cg.n;
       const int t2 = tile / cg.n;
@@ -191,8 +205,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
               f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + n0 + c + j) : 0.f);
-              if (act == DAFK_ACT_RELU) f[j] = fmaxf(f[j], 0.f);     // folded inference-mode BatchNorm + ReLU
             }
+          if (ep_code != DAFK_ACT_NONE) {       // uniform branch per chunk (a per-element branch made the epilogue 2.5x slower)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = epi_act(f[j], ep_code, ep_alpha);
+          }
           if (y_dt == DAFK_F32) {
             float* o = reinterpret_cast<float*>(y) + obase + c;
 #pragma unroll
@@ -262,7 +279,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
                                                                      int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1,
                                                                      int KH, int KW, int pad, HaloGeom g, int n_blocks,
                                                                      int w_rows_per_tap, int w_row_off, long long y_sn,
-                                                                     long long y_sy, long long y_sx, int total_tiles, int act) {
+                                                                     long long y_sy, long long y_sx, int total_tiles, Epi ep) {
   constexpr int B_BYTES = BLOCK_N * KBLK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -403,6 +420,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
     const int q4 = warp & 3;
     const int img_pos = g.RS * g.Pp;
     int tc = 0;
+    const int ep_code = ep.code;
+    const float ep_alpha = ep.alpha;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
       const int nb = tile % n_blocks;
       int mt = tile / n_blocks;
@@ -434,7 +453,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + n0 + c + j) : 0.f);
-              if (act == DAFK_ACT_RELU) f[j] = fmaxf(f[j], 0.f);     // folded inference-mode BatchNorm + ReLU
+            }
+            if (ep_code != DAFK_ACT_NONE) {       // uniform branch per chunk (a per-element branch made the epilogue 2.5x slower)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = epi_act(f[j], ep_code, ep_alpha);
             }
             if (y_dt == DAFK_F32) {
               float* o = reinterpret_cast<float*>(y) + obase + c;
@@ -488,7 +510,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
                      const __grid_constant__ CUtensorMap tmBh, const float* __restrict__ bias, void* __restrict__ y, int y_dt,
                      int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int pad, HaloGeom g,
                      int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy, long long y_sx, int total_tiles,
-                     int act) {
+                     Epi ep) {
   constexpr int HB_BYTES = (BLOCK_N / 2) * KBLK * 2;       // this CTA's half of one (channel block, tap) weight tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -603,6 +625,8 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
     const int q4 = warp & 3;
     const int img_pos = g.RS * g.Pp;
     int tc = 0;
+    const int ep_code = ep.code;
+    const float ep_alpha = ep.alpha;
     for (int pt = cluster_id; pt < pair_tiles; pt += n_clusters, ++tc) {
       int mt = 2 * pt + (int)rank;
       const bool tile_live = mt < total_tiles;
@@ -633,7 +657,10 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + c + j) : 0.f);
-              if (act == DAFK_ACT_RELU) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (ep_code != DAFK_ACT_NONE) {       // uniform branch per chunk (a per-element branch made the epilogue 2.5x slower)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = epi_act(f[j], ep_code, ep_alpha);
             }
             if (y_dt == DAFK_F32) {
               float* o = reinterpret_cast<float*>(y) + obase + c;
@@ -960,7 +987,7 @@ template <int BLOCK_N, int STAGES>
 static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const float* bias, void* y,
                       int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int stride, int pad,
                       const TileGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
-                      long long y_sx, int act, cudaStream_t s, const ClsGeom& cg = ClsGeom{1, 0, 0, 0, 0, 0}) {
+                      long long y_sx, Epi ep, cudaStream_t s, const ClsGeom& cg = ClsGeom{1, 0, 0, 0, 0, 0}) {
   constexpr int smem = STAGES * (A_BYTES + BLOCK_N * KBLK * 2) + 1024 + 256;
   static_assert(smem > 116 * 1024 && smem <= 227 * 1024, "one persistent CTA per SM");
   static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
@@ -975,7 +1002,7 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
   conv_tc_fwd_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1,
                                                                     KH, KW, stride, pad, g, n_blocks, w_rows_per_tap,
-                                                                    w_row_off, y_sn, y_sy, y_sx, (int)tiles, act, cg);
+                                                                    w_row_off, y_sn, y_sy, y_sx, (int)tiles, ep, cg);
   return check_launch("dafk_conv_tc_fwd");
 }
 
@@ -1088,7 +1115,7 @@ template <int BLOCK_N>
 static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const float* bias, void* y,
                        int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int pad,
                        const HaloGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
-                       long long y_sx, int act, cudaStream_t s) {
+                       long long y_sx, Epi ep, cudaStream_t s) {
   const int ncb_all = (C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK;
   const int smem = g.SA * g.a_bytes + (g.w_resident ? ncb_all * KH * KW : g.SB) * BLOCK_N * KBLK * 2 + 1024 + 512;
   static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
@@ -1104,7 +1131,7 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
   conv_tc_halo_kernel<BLOCK_N><<<grid, HALO_THREADS, smem_req, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW,
                                                                  pad, g, n_blocks, w_rows_per_tap, w_row_off, y_sn, y_sy,
-                                                                 y_sx, (int)tiles, act);
+                                                                 y_sx, (int)tiles, ep);
   return check_launch("dafk_conv_tc_fwd(halo)");
 }
 
@@ -1112,7 +1139,7 @@ template <int BLOCK_N>
 static int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& bh, const float* bias, void* y,
                         int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int pad,
                         const HaloGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
-                        long long y_sx, int act, cudaStream_t s) {
+                        long long y_sx, Epi ep, cudaStream_t s) {
   const int ncb_all = (C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK;
   const int smem = g.SA * g.a_bytes + ncb_all * KH * KW * (BLOCK_N / 2) * KBLK * 2 + 1024 + 512;
   DAFK_REQUIRE(smem <= 227 * 1024, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd(halo2): %d bytes of shared memory", smem);
@@ -1129,7 +1156,7 @@ static int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   const int clusters = (int)(pairs < kNumSMs / 2 ? pairs : kNumSMs / 2);
   conv_tc_halo2_kernel<BLOCK_N><<<dim3(2 * clusters), HALO_THREADS, smem_req, s>>>(
       a0, a1, bh, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, g, w_rows_per_tap, w_row_off, y_sn, y_sy, y_sx,
-      (int)tiles, act);
+      (int)tiles, ep);
   return check_launch("dafk_conv_tc_fwd(halo2)");
 }
 
@@ -1164,7 +1191,7 @@ extern "C" {
 static int conv_tc_fwd_impl(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,
                             int w_row_off, const float* bias, void* y, int y_dt, int N, int H, int W, int Cout, int KH,
                             int KW, int stride, int pad, int Ho, int Wo, int64_t y_sn, int64_t y_sy, int64_t y_sx,
-                            int act, void* stream) {
+                            int act, float alpha, void* stream) {
   DAFK_REQUIRE(N > 0 && H > 0 && W > 0 && C0 > 0 && C1 >= 0 && Cout > 0 && KH > 0 && KW > 0 && Ho > 0 && Wo > 0,
                DAFK_ERR_BAD_ARG, "dafk_conv_tc_fwd: bad shape");
   DAFK_REQUIRE(stride == 1 || stride == 2, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd: stride must be 1 or 2");
@@ -1182,6 +1209,7 @@ static int conv_tc_fwd_impl(const void* x0, int C0, const void* x1, int C1, cons
                "dafk_conv_tc_fwd: output strides must be multiples of 8 elements");
   TileGeom g = pick_geom(N, Ho, Wo, stride);
   CUtensorMap a0, a1, b;
+  const Epi ep{act, alpha};
   int rc = make_act_map(&a0, x0, N, H, W, C0, g, stride);
   if (rc) return rc;
   if (C1 > 0) { rc = make_act_map(&a1, x1, N, H, W, C1, g, stride); if (rc) return rc; } else a1 = a0;
@@ -1229,9 +1257,9 @@ static int conv_tc_fwd_impl(const void* x0, int C0, const void* x1, int C1, cons
         if (rc) return rc;
         if (bn == 128)
           return launch_halo2<128>(h0, h1, bh, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, h2, w_rows_per_tap,
-                                   w_row_off, y_sn, y_sy, y_sx, act, s);
+                                   w_row_off, y_sn, y_sy, y_sx, ep, s);
         return launch_halo2<64>(h0, h1, bh, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, h2, w_rows_per_tap,
-                                w_row_off, y_sn, y_sy, y_sx, act, s);
+                                w_row_off, y_sn, y_sy, y_sx, ep, s);
       }
     }
     if (ch < 1e29 && force != 0 && (force == 1 || prefer_halo)) {
@@ -1243,9 +1271,9 @@ static int conv_tc_fwd_impl(const void* x0, int C0, const void* x1, int C1, cons
       if (rc) return rc;
       if (bn == 128)
         return launch_halo<128>(h0, h1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, hg, w_rows_per_tap, w_row_off,
-                                y_sn, y_sy, y_sx, act, s);
+                                y_sn, y_sy, y_sx, ep, s);
       return launch_halo<64>(h0, h1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, hg, w_rows_per_tap, w_row_off,
-                             y_sn, y_sy, y_sx, act, s);
+                             y_sn, y_sy, y_sx, ep, s);
     }
   }
   if (Cout % 256 == 0) {
@@ -1257,19 +1285,19 @@ static int conv_tc_fwd_impl(const void* x0, int C0, const void* x1, int C1, cons
       rc = make_w_map(&b, wp, taps * w_rows_per_tap, Kpad, 256);
       if (rc) return rc;
       return launch_fwd<256, 4>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
-                                w_row_off, y_sn, y_sy, y_sx, act, s);
+                                w_row_off, y_sn, y_sy, y_sx, ep, s);
     }
   }
   if (Cout % 128 == 0) {
     rc = make_w_map(&b, wp, taps * w_rows_per_tap, Kpad, 128);
     if (rc) return rc;
     return launch_fwd<128, 6>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
-                              w_row_off, y_sn, y_sy, y_sx, act, s);
+                              w_row_off, y_sn, y_sy, y_sx, ep, s);
   }
   rc = make_w_map(&b, wp, taps * w_rows_per_tap, Kpad, 64);
   if (rc) return rc;
   return launch_fwd<64, 8>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, stride, pad, g, w_rows_per_tap,
-                           w_row_off, y_sn, y_sy, y_sx, act, s);
+                           w_row_off, y_sn, y_sy, y_sx, ep, s);
 }
 
 int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,
@@ -1277,16 +1305,17 @@ int dafk_conv_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void*
                      int KW, int stride, int pad, int Ho, int Wo, int64_t y_sn, int64_t y_sy, int64_t y_sx,
                      void* stream) {
   return conv_tc_fwd_impl(x0, C0, x1, C1, wp, w_rows_per_tap, w_row_off, bias, y, y_dt, N, H, W, Cout, KH, KW, stride, pad,
-                          Ho, Wo, y_sn, y_sy, y_sx, DAFK_ACT_NONE, stream);
+                          Ho, Wo, y_sn, y_sy, y_sx, DAFK_ACT_NONE, 0.f, stream);
 }
 
 int dafk_conv_tc_fwd_act(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,
                          int w_row_off, const float* bias, void* y, int y_dt, int N, int H, int W, int Cout, int KH,
                          int KW, int stride, int pad, int Ho, int Wo, int64_t y_sn, int64_t y_sy, int64_t y_sx, int act,
-                         void* stream) {
-  DAFK_REQUIRE(act == DAFK_ACT_NONE || act == DAFK_ACT_RELU, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd_act: act must be NONE or RELU");
+                         float alpha, void* stream) {
+  DAFK_REQUIRE(act == DAFK_ACT_NONE || act == DAFK_ACT_RELU || act == DAFK_ACT_LRELU, DAFK_ERR_UNSUPPORTED,
+               "dafk_conv_tc_fwd_act: act must be NONE, RELU or LRELU");
   return conv_tc_fwd_impl(x0, C0, x1, C1, wp, w_rows_per_tap, w_row_off, bias, y, y_dt, N, H, W, Cout, KH, KW, stride, pad,
-                          Ho, Wo, y_sn, y_sy, y_sx, act, stream);
+                          Ho, Wo, y_sn, y_sy, y_sx, act, alpha, stream);
 }
 
 int dafk_conv_tc_dgrad_s2(const void* dy, int Cout, const void* wp4, int w_rows_per_tap, int w_row_off, void* dx,
@@ -1319,12 +1348,12 @@ int dafk_conv_tc_dgrad_s2(const void* dy, int Cout, const void* wp4, int w_rows_
     rc = make_w_map(&b, wp4, 4 * taps * w_rows_per_tap, Kpad, 128);
     if (rc) return rc;
     return launch_fwd<128, 6>(a0, a0, b, nullptr, dx, dx_dt, N, Hc, Wc, Cin, Cout, 0, kh, kw, 1, kh - 1, g, w_rows_per_tap,
-                              w_row_off, y_sn, y_sy, y_sx, DAFK_ACT_NONE, s, cg);
+                              w_row_off, y_sn, y_sy, y_sx, Epi{DAFK_ACT_NONE, 0.f}, s, cg);
   }
   rc = make_w_map(&b, wp4, 4 * taps * w_rows_per_tap, Kpad, 64);
   if (rc) return rc;
   return launch_fwd<64, 8>(a0, a0, b, nullptr, dx, dx_dt, N, Hc, Wc, Cin, Cout, 0, kh, kw, 1, kh - 1, g, w_rows_per_tap,
-                           w_row_off, y_sn, y_sy, y_sx, DAFK_ACT_NONE, s, cg);
+                           w_row_off, y_sn, y_sy, y_sx, Epi{DAFK_ACT_NONE, 0.f}, s, cg);
 }
 
 int dafk_conv3x3_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,

@@ -52,16 +52,43 @@ def feat_dtype():
 # tape
 # --------------------------------------------------------------------------------------------
 class Var:
-    """A value in the forward graph.  ``data`` is a CUDA tensor (f32 or bf16)."""
-    __slots__ = ("data", "grad", "requires_grad", "grad_dtype", "grad_owned", "bias_sink")
+    """A value in the forward graph.  ``data`` is a CUDA tensor (f32 or bf16).
+
+    Gradients: the first contribution is kept as it arrives; a second one is held back in ``_grad2`` instead of being
+    added at once, so that a consumer that applies an activation backward next can sum the two inside that pass
+    (``take_grad_pair``); reading ``grad`` materialises the sum."""
+    __slots__ = ("data", "_grad", "_grad2", "requires_grad", "grad_dtype", "grad_owned", "bias_sink")
 
     def __init__(self, data, requires_grad=False, grad_dtype=None):
         self.data = data
-        self.grad = None
+        self._grad = None
+        self._grad2 = None
         self.requires_grad = requires_grad
         self.grad_dtype = grad_dtype if grad_dtype is not None else data.dtype
         self.grad_owned = False
         self.bias_sink = None
+
+    @property
+    def grad(self):
+        if self._grad2 is not None:
+            g2, self._grad2 = self._grad2, None
+            if self.grad_owned:
+                ops.add_(self._grad, g2)
+            else:
+                self._grad = ops.add(self._grad, g2)
+                self.grad_owned = True
+        return self._grad
+
+    @grad.setter
+    def grad(self, g):
+        self._grad = g
+        self._grad2 = None
+
+    def take_grad_pair(self):
+        """(g1, g2 or None, g1 is ours to overwrite) and clear: for consumers that fuse the sum into their own first pass"""
+        g1, g2, owned = self._grad, self._grad2, self.grad_owned
+        self._grad = self._grad2 = None
+        return g1, g2, owned
 
     @property
     def shape(self):
@@ -100,13 +127,15 @@ def accumulate(var, g, owned=True):
     if g.dtype != var.grad_dtype:
         g = ops.cast(g, var.grad_dtype)
         owned = True
-    if var.grad is None:
+    if var._grad is None:
         var.grad = g
         var.grad_owned = owned
+    elif var._grad2 is None:
+        var._grad2 = g               # summed by whoever reads the gradient (possibly inside its activation backward)
     elif var.grad_owned:
-        ops.add_(var.grad, g)
+        ops.add_(var._grad, g)
     else:
-        var.grad = ops.add(var.grad, g)
+        var._grad = ops.add(var._grad, g)
         var.grad_owned = True
 
 
@@ -391,7 +420,7 @@ class Conv2D:
         c4 = 4 * self.cin
         return all(ops.nc_supported(c4, self.cout, k2, k2, W2, 0, kind) for kind in (0, 1))
 
-    def _call_s2d(self, ctx, srcs, act, alpha):
+    def _call_s2d(self, ctx, srcs, act, alpha, od=torch.float32):
         code = ACT[act]
         xin = srcs[0] if len(srcs) == 1 else concat(ctx, [s if s.data.dtype == torch.float32 else
                                                           _cast_var(ctx, s, torch.float32) for s in srcs])
@@ -402,11 +431,19 @@ class Conv2D:
         x2 = ops.space_to_depth2(xin.data)
         bias = self.bias.data if self.bias is not None else None
         wp_f, wp_d = self.packed_s2d()
+        # bf16 storage of the activated output (and a bf16 gradient) only where every consumer below takes it
+        lo = od == torch.bfloat16 and code in (ACT_NONE, ACT_RELU, ACT_LRELU) and (wide or nc_w)
+        ydt = torch.bfloat16 if lo else torch.float32
         if wide:
-            raw = ops.conv_tc_fwd(x2, None, wp_f, bias, self.cout, k2, k2, 1, 0, torch.float32)
-            y = Var(raw if code == ACT_NONE else ops.act_fwd(raw, code, alpha, inplace=True))
+            if code in (ACT_NONE, ACT_RELU, ACT_LRELU):
+                y = Var(ops.conv_tc_fwd(x2, None, wp_f, bias, self.cout, k2, k2, 1, 0, ydt, act=code, alpha=alpha))
+            else:
+                raw = ops.conv_tc_fwd(x2, None, wp_f, bias, self.cout, k2, k2, 1, 0, torch.float32)
+                y = Var(ops.act_fwd(raw, code, alpha, inplace=True))
         else:
-            y = Var(ops.conv_nc_fwd(x2, wp_f, bias, self.cout, k2, k2, 0, code, alpha))
+            y = Var(ops.conv_nc_fwd(x2, wp_f, bias, self.cout, k2, k2, 0, code, alpha, ydt))
+        if lo:
+            y.grad_dtype = torch.bfloat16
         if ctx.rec(xin, self.kernel):
             y.requires_grad = True
 
@@ -415,12 +452,14 @@ class Conv2D:
                 y.grad = None
                 if g is None:
                     return
-                if g.dtype != torch.float32:
-                    g = ops.cast(g, torch.float32)
-                if wide and code != ACT_NONE and g.numel() % 4 == 0:
-                    gb = ops.act_bwd_bf16(g, y.data, code, alpha)       # activation backward straight into bf16
-                    g = None
+                gb = None
+                if lo or (wide and code != ACT_NONE):
+                    gb = _act_bwd_to_bf16(g, y.data, code, alpha) if code != ACT_NONE else (
+                        g if g.dtype == torch.bfloat16 else ops.cast(g, torch.bfloat16))
+                    g = gb if not wide else None         # the raster-strip kernels take the bf16 gradient as it is
                 else:
+                    if g.dtype != torch.float32:
+                        g = ops.cast(g, torch.float32)
                     if code != ACT_NONE:
                         g = ops.act_bwd(g, y.data, code, alpha)
                     gb = ops.cast(g, torch.bfloat16) if wide else None
@@ -453,7 +492,7 @@ class Conv2D:
     # ---- narrow layers: raster-strip tcgen05 kernels (stride 1) or the CUDA-core kernels (fp32)
     def _call_generic(self, ctx, srcs, act, alpha, od=torch.float32):
         if self.s2d_eligible(srcs):
-            return self._call_s2d(ctx, srcs, act, alpha)
+            return self._call_s2d(ctx, srcs, act, alpha, od)
         code = ACT[act]
         if (USE_TC and self.k == 1 and self.stride == 1 and len(srcs) == 1 and code == ACT_NONE
                 and od == torch.float32 and srcs[0].data.dtype == torch.bfloat16
@@ -470,6 +509,10 @@ class Conv2D:
             f32srcs = [s if s.data.dtype == torch.float32 else _cast_var(ctx, s, torch.float32) for s in srcs]
             xin = f32srcs[0] if len(f32srcs) == 1 else concat(ctx, f32srcs)
         bias = self.bias.data if self.bias is not None else None
+        # bf16 output gradients only on request (FiLM decoder under DEC_BF16).  Measured on B200 for the 8 -> 64 / 1 -> 64 first
+        # layers (the gradient comes from a BatchNorm backward that could write bf16): the raster-strip kernels stage
+        # (pixel, 8-channel) units, so halving the bytes per unit does not make them faster -- weight gradient 191 -> 289 us,
+        # 64 -> 8 data gradient 326 -> 596 us -- and fp32 stays
         bf16_bw = self.bf16_grad and nc_f and nc_w and od == torch.bfloat16
         if nc_f:
             y = Var(ops.conv_nc_fwd(xin.data, self.packed_nc()[0], bias, self.cout, self.k, self.k, self.pad, code, alpha, od),
@@ -481,18 +524,24 @@ class Conv2D:
             tape_x = xin
 
             def bw():
-                g = y.grad
-                y.grad = None
-                if g is None:
-                    return
-                if bf16_bw and g.dtype == torch.bfloat16 and g.numel() % 8 == 0:
-                    if code != ACT_NONE:                  # bf16 gradient x bf16 activation output, no fp32 intermediate
-                        g = ops.act_bwd_bf16io(g, y.data, code, alpha)
+                if (y._grad2 is not None and code != ACT_NONE and y._grad.dtype == y._grad2.dtype == y.data.dtype == torch.float32
+                        and y.data.numel() % 4 == 0):
+                    # two consumers (FiLM block: conv2 and the residual Add): sum + activation backward in one pass
+                    g1, g2, owned = y.take_grad_pair()
+                    g = ops.add_act_bwd(g1, g2, y.data, code, alpha, out=g1 if owned else None)
                 else:
-                    if g.dtype != torch.float32:
-                        g = ops.cast(g, torch.float32)
-                    if code != ACT_NONE:
-                        g = ops.act_bwd(g, y.data, code, alpha)
+                    g = y.grad
+                    y.grad = None
+                    if g is None:
+                        return
+                    if bf16_bw and g.dtype == torch.bfloat16 and g.numel() % 8 == 0:
+                        if code != ACT_NONE:                  # bf16 gradient x bf16 activation output, no fp32 intermediate
+                            g = ops.act_bwd_bf16io(g, y.data, code, alpha)
+                    else:
+                        if g.dtype != torch.float32:
+                            g = ops.cast(g, torch.float32)
+                        if code != ACT_NONE:
+                            g = ops.act_bwd(g, y.data, code, alpha)
                 if self.kernel.requires_grad:
                     db = self.bias.grad if (self.bias is not None and self.bias.requires_grad) else None
                     if nc_w:
@@ -549,13 +598,19 @@ class Conv2D:
         bias = self.bias.data if self.bias is not None else None
         x0 = bsrcs[0]
         x1 = bsrcs[1] if len(bsrcs) > 1 else None
+        code = ACT[act]
+        fuse = code in (ACT_RELU, ACT_LRELU)      # the activation runs in the epilogue: y = act(conv + bias), stored once
         raw = ops.conv_tc_fwd(x0.data, None if x1 is None else x1.data, wp_f, bias, self.cout, self.k, self.k,
-                              self.stride, self.pad, torch.float32 if ACT[act] != ACT_NONE else od)
-        y = Var(raw, grad_dtype=torch.bfloat16)
+                              self.stride, self.pad, od if (fuse or code == ACT_NONE) else torch.float32,
+                              act=code if fuse else ACT_NONE, alpha=alpha)
+        # an fp32-stored activated output (last discriminator layer, feeds a Dense) takes its gradient in fp32 and
+        # converts while the activation backward runs; everything else hands bf16 to the gradient kernels
+        y = Var(raw, grad_dtype=torch.float32 if (fuse and raw.dtype == torch.float32) else torch.bfloat16)
         rec = ctx.rec(*bsrcs, self.kernel)
         if rec:
             y.requires_grad = True
-            if self.bias is not None and self.bias.requires_grad:
+            want_db = self.bias is not None and self.bias.requires_grad
+            if want_db and not fuse:
                 y.bias_sink = self.bias       # a following BatchNorm backward folds the bias gradient in
 
             def bw():
@@ -563,10 +618,15 @@ class Conv2D:
                 y.grad = None
                 if g is None:
                     return
-                if g.dtype != torch.bfloat16:
-                    g = ops.cast(g, torch.bfloat16)
-                if y.bias_sink is not None:   # nobody consumed it: reduce here
-                    ops.colsum_(g, self.bias.grad)
+                if fuse:
+                    g = _act_bwd_to_bf16(g, y.data, code, alpha)
+                    if want_db:
+                        ops.colsum_(g, self.bias.grad)
+                else:
+                    if g.dtype != torch.bfloat16:
+                        g = ops.cast(g, torch.bfloat16)
+                    if y.bias_sink is not None:   # nobody consumed it: reduce here
+                        ops.colsum_(g, self.bias.grad)
                 off = 0
                 for s in bsrcs:
                     c = s.shape[-1]
@@ -577,9 +637,20 @@ class Conv2D:
                     off += c
 
             ctx.tape.record(bw)
-        if ACT[act] != ACT_NONE:
+        if code != ACT_NONE and not fuse:
             return activation(ctx, y, act, alpha)
         return y
+
+
+def _act_bwd_to_bf16(g, y, code, alpha):
+    """bf16(g * act'(y)) for an activation output y stored in bf16 or fp32 (one pass whenever the dtypes pair up)"""
+    if g.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and g.numel() % 8 == 0:
+        return ops.act_bwd_bf16io(g, y, code, alpha)
+    if g.dtype == torch.float32 and y.dtype == torch.float32 and g.numel() % 4 == 0:
+        return ops.act_bwd_bf16(g, y, code, alpha)
+    gf = g if g.dtype == torch.float32 else ops.cast(g, torch.float32)
+    yf = y if y.dtype == torch.float32 else ops.cast(y, torch.float32)
+    return ops.cast(ops.act_bwd(gf, yf, code, alpha), torch.bfloat16)
 
 
 def _cast_var(ctx, v, dtype):

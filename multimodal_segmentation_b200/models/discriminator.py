@@ -38,8 +38,9 @@ class Discriminator(object):
 
         def fwd(ctx, x):
             l = x
-            for cv in convs:
-                l = cv(ctx, l, "lrelu", 0.2)
+            for i, cv in enumerate(convs):      # activated maps between the convolutions in the feature dtype (bf16 on the
+                l = cv(ctx, l, "lrelu", 0.2,    # tensor-core path: the next convolution's operand); the last one feeds Dense
+                       out_dtype=E.feat_dtype() if i + 1 < len(convs) else None)
             return dense(ctx, l)
 
         self.model = Model(conf.name, convs + [dense], fwd, [(H, W, C)], [(1,)], scope)

@@ -76,6 +76,15 @@ def act_bwd(dy, y, act, alpha=0.0, inplace=False):
     return dx
 
 
+def add_act_bwd(dy1, dy2, y, act, alpha=0.0, out=None):
+    """(dy1 + dy2) * act'(y) in one pass (fp32); ``out`` may be dy1 or dy2"""
+    _chk(dy1, dy2, y)
+    assert dy1.dtype == dy2.dtype == y.dtype == torch.float32 and dy1.shape == dy2.shape == y.shape
+    dx = torch.empty_like(dy1) if out is None else out
+    call("add_act_bwd", dy1, dy2, y, dx, y.numel(), act, float(alpha), _S())
+    return dx
+
+
 def act_bwd_bf16(dy, y, act, alpha=0.0):
     """bf16(act'(y) * dy) in one pass (fp32 in)"""
     _chk(dy, y)
@@ -498,7 +507,8 @@ def pack_conv_scaled(w_hwio, scale, out=None):
     return wp
 
 
-def conv_tc_fwd(x0, x1, wp, bias, Cout, KH, KW, stride, pad, out_dtype=torch.float32, row_off=0, out=None, act=ACT_NONE):
+def conv_tc_fwd(x0, x1, wp, bias, Cout, KH, KW, stride, pad, out_dtype=torch.float32, row_off=0, out=None, act=ACT_NONE,
+                alpha=0.0):
     """general tcgen05 convolution.  ``out`` may be a strided NHWC view (e.g. dx[:, pa::2, pb::2, :]); its
     spatial extent defines the logical output size."""
     _chk(x0, x1, wp, bias)
@@ -515,7 +525,7 @@ def conv_tc_fwd(x0, x1, wp, bias, Cout, KH, KW, stride, pad, out_dtype=torch.flo
     instrument.timed("conv_tc_fwd+dgrad (tcgen05)", fl, nb,
                      lambda: call("conv_tc_fwd_act", x0, C0, x1, C1, wp, wp.shape[1], row_off, bias, out, _dt(out), N, H, W,
                                   Cout, KH, KW, stride, pad, Ho, Wo, out.stride(0), out.stride(1), out.stride(2), int(act),
-                                  _S()),
+                                  float(alpha), _S()),
                      tag=(N, H, W, C0 + C1, Cout, KH, stride, str(out.dtype)[6:], Ho))
     return out
 
@@ -652,50 +662,6 @@ def conv_nc_wgrad(x, dy, dw, db, pad):
     instrument.timed("conv_nc_wgrad (tcgen05)", fl, nb,
                      lambda: call("conv_nc_wgrad", x, _dt(x), dy, _dt(dy), dw, db, N, H, W, Cin, Cout, KH, KW, pad, _S()),
                      tag=(N, H, W, Cin, Cout, KH, pad, str(x.dtype)[6:], str(dy.dtype)[6:]))
-
-
-# ---------------------------------------------------------------------------- narrow-channel convolutions, warp-strip kernels
-USE_WS = os.environ.get("DAFK_CONV_WS", "1") != "0"       # "0": fall back to the tcgen05 raster-strip kernels (conv_nc)
-
-
-def ws_supported(Cin, Cout, KH, KW, W, pad, kind):
-    """csrc/conv_ws.cu handles this layer (kernel-view channel counts; kind 0/1 forward-type, 2 weight gradient)"""
-    return USE_WS and bool(_lib.lib().fn["dafk_conv_ws_supported"](Cin, Cout, KH, KW, W, pad, kind))
-
-
-def conv_ws_fwd(x, w, bias, pad, act=ACT_NONE, alpha=0.0, out_dtype=torch.float32, mode=0, scale=None, ya=None,
-                gact=ACT_NONE, galpha=0.0):
-    """mode 0: y = act(conv(x, w [* scale]) + bias), stride 1, w the fp32 HWIO kernel [KH,KW,Cin,Cout].
-    mode 1: data gradient of that layer: x = dy [N,Ho,Wo,Cout] -> dx [N,H,W,Cin]; `pad` is the padding of the
-    gradient convolution (KH - 1 - pad_forward).  ya/gact/galpha: x := x * act'(ya) while it is staged."""
-    _chk(x, w, bias, scale, ya)
-    N, H, W, Cx = x.shape
-    KH, KW, wCin, wCout = w.shape
-    Cin, Cout = (wCin, wCout) if mode == 0 else (wCout, wCin)
-    assert Cx == Cin, (tuple(x.shape), tuple(w.shape), mode)
-    Ho, Wo = H + 2 * pad - KH + 1, W + 2 * pad - KW + 1
-    y = torch.empty((N, Ho, Wo, Cout), dtype=out_dtype, device=x.device)
-    fl = 2.0 * N * Ho * Wo * Cout * KH * KW * Cin
-    nb = x.numel() * x.element_size() + y.numel() * y.element_size() + (0 if ya is None else ya.numel() * ya.element_size())
-    instrument.timed("conv_ws_fwd+dgrad (mma.sync, HBM-bound)", fl, nb,
-                     lambda: call("conv_ws_fwd", x, _dt(x), ya, 0 if ya is None else _dt(ya), int(gact), float(galpha), w, wCin,
-                                  wCout, mode, scale, bias, y, _dt(y), N, H, W, Cin, Cout, KH, KW, pad, int(act), float(alpha),
-                                  _S()),
-                     tag=(N, H, W, Cin, Cout, KH, pad, str(x.dtype)[6:], str(out_dtype)[6:], "g" if ya is not None else ""))
-    return y
-
-
-def conv_ws_wgrad(x, dy, dw, db, pad, ya=None, gact=ACT_NONE, galpha=0.0):
-    """dw[KH,KW,Cin,Cout] += x (*) dy', db += sum dy' (db may be None), dy' = dy * act'(ya); stride 1"""
-    _chk(x, dy, dw, db, ya)
-    N, H, W, Cin = x.shape
-    KH, KW, _, Cout = dw.shape
-    fl = 2.0 * dy.numel() * KH * KW * Cin
-    nb = x.numel() * x.element_size() + dy.numel() * dy.element_size() + (0 if ya is None else ya.numel() * ya.element_size())
-    instrument.timed("conv_ws_wgrad (mma.sync, HBM-bound)", fl, nb,
-                     lambda: call("conv_ws_wgrad", x, _dt(x), dy, _dt(dy), ya, 0 if ya is None else _dt(ya), int(gact),
-                                  float(galpha), dw, db, N, H, W, Cin, Cout, KH, KW, pad, _S()),
-                     tag=(N, H, W, Cin, Cout, KH, pad, str(x.dtype)[6:], str(dy.dtype)[6:], "g" if ya is not None else ""))
 
 
 # ---------------------------------------------------------------------------- pointwise 64 -> <=8 heads

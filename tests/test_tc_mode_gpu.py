@@ -97,10 +97,10 @@ def test_tensor_core_step_against_precision_matched_oracle(depth):
     for c in d_prod:
         assert d_prod[c] <= 2.0 * max(d_intr[c], d_fp[c]) + 1e-2, (c, d_prod[c], d_intr[c], d_fp[c])
     if depth == 1:
-        # the better-conditioned graph: no further from the emulated oracle than 1.5x its own 1e-6 input sensitivity
-        # (5e-2 floor), and the components downstream of the UNet within 5e-2 outright
+        # the better-conditioned graph: no further from the emulated oracle than 1.5x the larger of its own 1e-6 input
+        # sensitivity and the cost of bf16 itself (5e-2 floor), and the components downstream of the UNet within 5e-2 outright
         for c in d_prod:
-            assert d_prod[c] < max(5e-2, 1.5 * d_intr[c]), (c, d_prod[c], d_intr[c])
+            assert d_prod[c] < max(5e-2, 1.5 * max(d_intr[c], d_fp[c])), (c, d_prod[c], d_intr[c], d_fp[c])
         assert d_prod["Decoder"] < 5e-2 and d_prod["Enc_Modality"] < 5e-2
 
 
