@@ -244,6 +244,14 @@ int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias,
 /* dw[KH,KW,Cin,Cout] (HWIO f32) += x (*) dy ; db[Cout] += sum_pixels dy (db may be NULL) */
 int dafk_conv_nc_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float* dw, float* db, int N,
                        int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream);
+/* The same two kernels on Concatenate([xa, xb]) without materialising it (the locnet's input, layers/stn_spline.py:104:
+ * two 8-channel anatomies): channels [0,Ca) of the kernel's Cin = Ca + Cb come from xa [N,H,W,Ca], the rest from xb
+ * [N,H,W,Cb]; both sources have dtype x_dt; Ca must be a multiple of 8 (a channel group never straddles the sources). */
+int dafk_conv_nc_fwd_cat(const void* xa, int Ca, const void* xb, int Cb, int x_dt, const void* wp, const float* bias,
+                         void* y, int y_dt, int N, int H, int W, int Cout, int KH, int KW, int pad, int act, float alpha,
+                         void* stream);
+int dafk_conv_nc_wgrad_cat(const void* xa, int Ca, const void* xb, int Cb, int x_dt, const void* dy, int dy_dt, float* dw,
+                           float* db, int N, int H, int W, int Cout, int KH, int KW, int pad, void* stream);
 /* Pointwise heads on a 64-channel bf16 feature map (csrc/conv_1x1.cu): `conv_anatomy` 64 -> 8
  * (model_components/anatomy_encoder.py:26) and the segmentor's 64 -> num_masks+1 (model_components/segmentor.py:24).
  * x / dx: bf16 [M,64]; w: f32 [64,Cout] (HWIO with KH=KW=1); y / dy: f32 [M,Cout]; M = N*H*W pixels.
@@ -262,6 +270,13 @@ int dafk_conv1x1_wgrad(const void* x, const float* dy, float* dw, float* db, int
  * the stride-2 narrow layers (model_components/modality_encoder.py:36-42, models/discriminator.py:24) run on
  * dafk_conv_nc_* this way. */
 int dafk_space_to_depth2(const void* x, int x_dt, void* y_bf16, int N, int H, int W, int C, void* stream);
+/* The same rearrangement of Concatenate([xa, xb]) (model_components/modality_encoder.py:34) without materialising the
+ * concatenation: channels [0,Ca) of every pixel come from xa [N,H,W,Ca], [Ca,Ca+Cb) from xb [N,H,W,Cb]; and the backward,
+ * which writes the fp32 gradients of the two sources straight from the rearranged gradient (ga / gb may be NULL). */
+int dafk_space_to_depth2_cat(const void* xa, int xa_dt, int Ca, const void* xb, int xb_dt, int Cb, void* y_bf16, int N,
+                             int H, int W, void* stream);
+int dafk_depth_to_space2_split(const void* y, int y_dt, float* ga, int Ca, float* gb, int Cb, int N, int H, int W,
+                               void* stream);
 int dafk_depth_to_space2(const void* y, int y_dt, void* x, int x_dt, int N, int H, int W, int C,
                          void* stream);
 int dafk_conv_s2d_weights(float* w, float* w2, int KH, int KW, int C, int Cout, int backward,
@@ -370,8 +385,9 @@ int dafk_tps_build_constants(int cp_h, int cp_w, float* consts_host);
 int dafk_tps_warp_fwd(const float* vol, const float* theta, const float* consts, float* out,
                       float* locs, int B, int H, int W, int C, int n_cp, void* stream);
 /* Same warp with phi(|q - c|^2) read from a per-geometry table instead of evaluated per pixel (25 logf):
- * dafk_tps_phi_table fills table[n_cp][H*W] (dafk_tps_phi_table_floats floats, caller-owned, reusable for every call
- * with the same H, W and control grid) with exactly the values the in-kernel evaluation produces.  The spline
+ * dafk_tps_phi_table fills table[n_cp + 2][H*W] (dafk_tps_phi_table_floats floats, caller-owned, reusable for every call
+ * with the same H, W and control grid) with exactly the values the in-kernel evaluation produces; rows n_cp and n_cp + 1
+ * hold the normalised pixel coordinates row/(H-1), col/(W-1) that the affine part of the spline reads.  The spline
  * coefficients of the batch are computed once per call into coef_ws (B*(n_cp+3)*2 floats, caller-owned) instead of
  * once per CTA. */
 int64_t dafk_tps_phi_table_floats(int H, int W, int n_cp);
@@ -384,6 +400,10 @@ int dafk_tps_warp_fwd_tab(const float* vol, const float* theta, const float* con
 int dafk_tps_warp_bwd(const float* vol, const float* theta, const float* consts, const float* dout,
                       float* dvol, float* dtheta, double* ws, int B, int H, int W, int C, int n_cp,
                       void* stream);
+/* the same with phi and the pixel coordinates read from the geometry's table (dafk_tps_phi_table: (n_cp + 2) rows) */
+int dafk_tps_warp_bwd_tab(const float* vol, const float* theta, const float* consts, const float* phi_table,
+                          const float* dout, float* dvol, float* dtheta, double* ws, int B, int H, int W, int C, int n_cp,
+                          void* stream);
 /* plain tf.contrib.resampler forward for arbitrary warp[b,m,2] */
 int dafk_resampler_fwd(const float* vol, const float* warp, float* out, int B, int H, int W, int C,
                        int64_t m, void* stream);

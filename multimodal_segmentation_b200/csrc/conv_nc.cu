@@ -38,6 +38,7 @@ struct NcFwdP {
   int x_dt, y_dt, act;
   float alpha;
   int dbg;
+  int Ca, Cb;                        // two concatenated sources (Cb > 0): channels [0,Ca) from x, [Ca,Ca+Cb) from xb; Ca % 8 == 0
 };
 
 struct NcWgP {
@@ -51,6 +52,7 @@ struct NcWgP {
   int tmem_cols;
   int fold;                          // Cout <= 8: the KH filter rows are folded into the MMA's N dimension
   int yoff;                          // fold: positions of zero halo in front of the dY rows = (KH-1)*P
+  int Ca, Cb;                        // two concatenated input sources, as in NcFwdP
 };
 
 // load 8 consecutive channels starting at p (nvalid of them exist) as floats
@@ -119,12 +121,17 @@ constexpr int NC_U_WG = 6;       // same, weight-gradient kernel (two tensors ar
 // `col0` is the raster column of image column 0 (= pad for inputs, 0 for output gradients).  With BSUM the
 // per-thread channel sums are accumulated (bias gradient): every thread then stays on ONE channel group,
 // which needs the thread count to be a multiple of `groups` (nthr = (NC_PROD / groups) * groups).
+// Two concatenated sources (srcb != nullptr; the locnet's Concatenate([s1, s2]), layers/stn_spline.py:104): the first
+// `C` channels (a whole number of 8-channel groups) come from src, the other Cb from srcb -- the concatenation is never
+// materialised, a channel group simply picks its base pointer.
 template <typename T, bool BSUM, int NC_U>
 __device__ __forceinline__ void nc_stage_rows(const T* __restrict__ src, uint8_t* planes, int plane_pos, int n, int Himg,
                                               int wcols, int C, int groups, int iy0, int rows, int P, int col0, int ptid,
-                                              int nthr, float (&bsum)[8]) {
+                                              int nthr, float (&bsum)[8], const T* __restrict__ srcb = nullptr, int Cb = 0) {
   if (ptid >= nthr) return;
-  const bool vec = (sizeof(T) == 4) ? ((C & 3) == 0) : ((C & 7) == 0);
+  const int ga = srcb != nullptr ? C >> 3 : groups;          // channel groups that live in the first source
+  const bool vec = (sizeof(T) == 4) ? (((C | Cb) & 3) == 0) : (((C | Cb) & 7) == 0);
+  const T* imgb = srcb != nullptr ? srcb + (int64_t)n * Himg * wcols * Cb : nullptr;
   const int units_row = wcols * groups;
   const int total = rows * units_row;
   const int gshift = (groups & (groups - 1)) == 0 ? 31 - __clz(groups) : -1;
@@ -146,7 +153,8 @@ __device__ __forceinline__ void nc_stage_rows(const T* __restrict__ src, uint8_t
         const int iy = iy0 + row;
         dst[k] = cg * plane_pos + row * P + col0 + px;
         if (iy >= 0 && iy < Himg) {
-          nc_load8<T>(img + ((int64_t)iy * wcols + px) * C + cg * 8, min(8, C - cg * 8), vec, v[k]);
+          if (cg < ga) nc_load8<T>(img + ((int64_t)iy * wcols + px) * C + cg * 8, min(8, C - cg * 8), vec, v[k]);
+          else nc_load8<T>(imgb + ((int64_t)iy * wcols + px) * Cb + (cg - ga) * 8, min(8, Cb - (cg - ga) * 8), vec, v[k]);
         } else {
 #pragma unroll
           for (int c = 0; c < 8; ++c) v[k][c] = 0.f;
@@ -196,7 +204,7 @@ constexpr int NC_MODE_DEFAULT = 0, NC_MODE_BULK = 1, NC_MODE_L12 = 2;
 template <typename TX, int MODE>
 __global__ void __launch_bounds__(MODE == NC_MODE_DEFAULT ? NC_FWD_THREADS : NC_BULK_THREADS, 1)
 conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __restrict__ wp,
-                   const float* __restrict__ bias, void* __restrict__ y) {
+                   const float* __restrict__ bias, void* __restrict__ y, const TX* __restrict__ xb = nullptr) {
   constexpr bool BULK = MODE == NC_MODE_BULK;
   constexpr int THREADS = MODE == NC_MODE_DEFAULT ? NC_FWD_THREADS : NC_BULK_THREADS;
   constexpr int PROD = MODE == NC_MODE_L12 ? 224 : NC_PROD;                 // staging threads (not BULK)
@@ -298,8 +306,8 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
       const int y0 = (s - n * p.strips_per_img) * p.R;
       mbar_wait(empty + st, ph ^ 1u);
       if (!(p.dbg & 4))
-      nc_stage_rows<TX, false, NC_U_FWD>(x, s_x + (size_t)st * st_bytes, p.plane, n, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P,
-                                 p.pad, tid, PROD, dummy);
+      nc_stage_rows<TX, false, NC_U_FWD>(x, s_x + (size_t)st * st_bytes, p.plane, n, p.H, p.W, p.Cb > 0 ? p.Ca : p.Cin, p.CG,
+                                 y0 - p.pad, p.RS, p.P, p.pad, tid, PROD, dummy, xb, p.Cb);
       fence_proxy_async();
       mbar_arrive(full + st);
     }
@@ -470,7 +478,8 @@ constexpr int NC_WG_THREADS = NC_PROD + 32;
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p, const TX* __restrict__ x,
                                                                          const TY* __restrict__ dy,
-                                                                         float* __restrict__ dw, float* __restrict__ db) {
+                                                                         float* __restrict__ dw, float* __restrict__ db,
+                                                                         const TX* __restrict__ xb = nullptr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int x_bytes = p.CG * p.planeX * 16;
@@ -510,7 +519,8 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
       const int y0 = (s - n * p.strips_per_img) * p.R;
       uint8_t* sx = smem + (size_t)st * st_bytes;
       mbar_wait(empty + st, ph ^ 1u);
-      nc_stage_rows<TX, false, NC_U_WG>(x, sx, p.planeX, n, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P, p.pad, tid, NC_PROD, dummy);
+      nc_stage_rows<TX, false, NC_U_WG>(x, sx, p.planeX, n, p.H, p.W, p.Cb > 0 ? p.Ca : p.Cin, p.CG, y0 - p.pad, p.RS, p.P, p.pad, tid,
+                                        NC_PROD, dummy, xb, p.Cb);
       uint8_t* sy = sx + x_bytes + (size_t)p.yoff * 16;      // fold: (KH-1) zero rows stay in front of (and behind) the dY rows
       if (db != nullptr)
         nc_stage_rows<TY, true, NC_U_WG>(dy, sy, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, nthr_y, bsum);
@@ -817,8 +827,9 @@ int dafk_pack_conv_nc_scaled(const float* w_hwio, const float* scale, void* wp, 
   return check_launch("dafk_pack_conv_nc_scaled");
 }
 
-int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias, void* y, int y_dt, int N, int H,
-                     int W, int Cin, int Cout, int KH, int KW, int pad, int act, float alpha, void* stream) {
+static int conv_nc_fwd_impl(const void* x, const void* xb, int Ca, int Cb, int x_dt, const void* wp, const float* bias, void* y,
+                           int y_dt, int N, int H, int W, int Cin, int Cout, int KH, int KW, int pad, int act, float alpha,
+                           void* stream) {
   DAFK_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && pad >= 0, DAFK_ERR_BAD_ARG,
                "dafk_conv_nc_fwd: bad shape");
   if (N == 0) return DAFK_OK;
@@ -833,6 +844,7 @@ int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias,
   p.Wo = W + 2 * pad - KW + 1;
   DAFK_REQUIRE(p.Ho > 0 && p.Wo > 0, DAFK_ERR_BAD_ARG, "dafk_conv_nc_fwd: empty output");
   p.x_dt = x_dt; p.y_dt = y_dt; p.act = act; p.alpha = alpha;
+  p.Ca = Ca; p.Cb = Cb;
   { const char* e = getenv("DAFK_NC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   size_t smem;
   DAFK_REQUIRE(nc_fwd_geom(p, smem), DAFK_ERR_UNSUPPORTED,
@@ -853,17 +865,19 @@ int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias,
     rc = nc_set_smem(conv_nc_fwd_kernel<float, NC_MODE_L12>, smem, "dafk_conv_nc_fwd");
     if (rc) return rc;
     conv_nc_fwd_kernel<float, NC_MODE_L12><<<grid, NC_BULK_THREADS, smem, s>>>(p, (const float*)x, (const __nv_bfloat16*)wp,
-                                                                              bias, y);
-  } else if (l12 && !(bulk_ok && Cin == 8)) {
+                                                                              bias, y, (const float*)xb);
+  } else if (l12 && !(bulk_ok && Cin == 8 && Cb == 0)) {
     rc = nc_set_smem(conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_L12>, smem, "dafk_conv_nc_fwd");
     if (rc) return rc;
     conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_L12><<<grid, NC_BULK_THREADS, smem, s>>>(p, (const __nv_bfloat16*)x,
-                                                                                      (const __nv_bfloat16*)wp, bias, y);
+                                                                                      (const __nv_bfloat16*)wp, bias, y,
+                                                                                      (const __nv_bfloat16*)xb);
   } else if (x_dt == DAFK_F32) {
     rc = nc_set_smem(conv_nc_fwd_kernel<float, NC_MODE_DEFAULT>, smem, "dafk_conv_nc_fwd");
     if (rc) return rc;
-    conv_nc_fwd_kernel<float, NC_MODE_DEFAULT><<<grid, NC_FWD_THREADS, smem, s>>>(p, (const float*)x, (const __nv_bfloat16*)wp, bias, y);
-  } else if (bulk_ok && Cin == 8) {
+    conv_nc_fwd_kernel<float, NC_MODE_DEFAULT><<<grid, NC_FWD_THREADS, smem, s>>>(p, (const float*)x, (const __nv_bfloat16*)wp, bias, y,
+                                                                                 (const float*)xb);
+  } else if (bulk_ok && Cin == 8 && Cb == 0) {
     // one pixel = 16 B = one raster position: rows are staged by the TMA engine, two epilogue groups
     rc = nc_set_smem(conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_BULK>, smem, "dafk_conv_nc_fwd");
     if (rc) return rc;
@@ -873,13 +887,28 @@ int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias,
     rc = nc_set_smem(conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_DEFAULT>, smem, "dafk_conv_nc_fwd");
     if (rc) return rc;
     conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_DEFAULT><<<grid, NC_FWD_THREADS, smem, s>>>(p, (const __nv_bfloat16*)x,
-                                                                               (const __nv_bfloat16*)wp, bias, y);
+                                                                               (const __nv_bfloat16*)wp, bias, y,
+                                                                               (const __nv_bfloat16*)xb);
   }
   return check_launch("dafk_conv_nc_fwd");
 }
 
-int dafk_conv_nc_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float* dw, float* db, int N, int H, int W,
-                       int Cin, int Cout, int KH, int KW, int pad, void* stream) {
+int dafk_conv_nc_fwd(const void* x, int x_dt, const void* wp, const float* bias, void* y, int y_dt, int N, int H,
+                     int W, int Cin, int Cout, int KH, int KW, int pad, int act, float alpha, void* stream) {
+  return conv_nc_fwd_impl(x, nullptr, Cin, 0, x_dt, wp, bias, y, y_dt, N, H, W, Cin, Cout, KH, KW, pad, act, alpha, stream);
+}
+
+int dafk_conv_nc_fwd_cat(const void* xa, int Ca, const void* xb, int Cb, int x_dt, const void* wp, const float* bias,
+                         void* y, int y_dt, int N, int H, int W, int Cout, int KH, int KW, int pad, int act, float alpha,
+                         void* stream) {
+  DAFK_REQUIRE(Ca > 0 && Cb > 0 && Ca % 8 == 0, DAFK_ERR_UNSUPPORTED,
+               "dafk_conv_nc_fwd_cat: the first source must hold a whole number of 8-channel groups (Ca=%d Cb=%d)", Ca, Cb);
+  DAFK_REQUIRE(xb && DAFK_ALIGNED16(xb), DAFK_ERR_BAD_ARG, "dafk_conv_nc_fwd_cat: second source missing or misaligned");
+  return conv_nc_fwd_impl(xa, xb, Ca, Cb, x_dt, wp, bias, y, y_dt, N, H, W, Ca + Cb, Cout, KH, KW, pad, act, alpha, stream);
+}
+
+static int conv_nc_wgrad_impl(const void* x, const void* xb, int Ca, int Cb, int x_dt, const void* dy, int dy_dt, float* dw,
+                              float* db, int N, int H, int W, int Cin, int Cout, int KH, int KW, int pad, void* stream) {
   DAFK_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && pad >= 0, DAFK_ERR_BAD_ARG,
                "dafk_conv_nc_wgrad: bad shape");
   if (N == 0) return DAFK_OK;
@@ -893,6 +922,7 @@ int dafk_conv_nc_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float
   p.Wo = W + 2 * pad - KW + 1;
   DAFK_REQUIRE(p.Ho > 0 && p.Wo > 0, DAFK_ERR_BAD_ARG, "dafk_conv_nc_wgrad: empty output");
   p.x_dt = x_dt; p.dy_dt = dy_dt;
+  p.Ca = Ca; p.Cb = Cb;
   size_t smem;
   DAFK_REQUIRE(nc_wg_geom(p, smem), DAFK_ERR_UNSUPPORTED,
                "dafk_conv_nc_wgrad: geometry does not fit (Cin=%d Cout=%d k=%dx%d W=%d)", Cin, Cout, KH, KW, W);
@@ -904,7 +934,7 @@ int dafk_conv_nc_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float
   do {                                                                                                  \
     rc = nc_set_smem(conv_nc_wgrad_kernel<TX, TY>, smem, "dafk_conv_nc_wgrad");                           \
     if (rc) return rc;                                                                                  \
-    conv_nc_wgrad_kernel<TX, TY><<<grid, NC_WG_THREADS, smem, s>>>(p, (const TX*)x, (const TY*)dy, dw, db);  \
+    conv_nc_wgrad_kernel<TX, TY><<<grid, NC_WG_THREADS, smem, s>>>(p, (const TX*)x, (const TY*)dy, dw, db, (const TX*)xb);  \
   } while (0)
   if (x_dt == DAFK_F32 && dy_dt == DAFK_F32) NC_WG(float, float);
   else if (x_dt == DAFK_F32) NC_WG(float, __nv_bfloat16);
@@ -912,6 +942,19 @@ int dafk_conv_nc_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float
   else NC_WG(__nv_bfloat16, __nv_bfloat16);
 #undef NC_WG
   return check_launch("dafk_conv_nc_wgrad");
+}
+
+int dafk_conv_nc_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float* dw, float* db, int N, int H, int W,
+                       int Cin, int Cout, int KH, int KW, int pad, void* stream) {
+  return conv_nc_wgrad_impl(x, nullptr, Cin, 0, x_dt, dy, dy_dt, dw, db, N, H, W, Cin, Cout, KH, KW, pad, stream);
+}
+
+int dafk_conv_nc_wgrad_cat(const void* xa, int Ca, const void* xb, int Cb, int x_dt, const void* dy, int dy_dt, float* dw,
+                           float* db, int N, int H, int W, int Cout, int KH, int KW, int pad, void* stream) {
+  DAFK_REQUIRE(Ca > 0 && Cb > 0 && Ca % 8 == 0, DAFK_ERR_UNSUPPORTED,
+               "dafk_conv_nc_wgrad_cat: the first source must hold a whole number of 8-channel groups (Ca=%d Cb=%d)", Ca, Cb);
+  DAFK_REQUIRE(xb && DAFK_ALIGNED16(xb), DAFK_ERR_BAD_ARG, "dafk_conv_nc_wgrad_cat: second source missing or misaligned");
+  return conv_nc_wgrad_impl(xa, xb, Ca, Cb, x_dt, dy, dy_dt, dw, db, N, H, W, Ca + Cb, Cout, KH, KW, pad, stream);
 }
 
 }  // extern "C"

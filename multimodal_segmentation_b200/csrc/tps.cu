@@ -280,6 +280,10 @@ __global__ void __launch_bounds__(TPS_T) tps_phi_table_kernel(const float* __res
     const float r = qq - 2.f * (q0 * c0 + q1 * c1) + (c0 * c0 + c1 * c1);
     tab[(int64_t)t * HW + m] = 0.5f * r * logf(fmaxf(r, TPS_EPS));
   }
+  // rows n, n+1: the normalised pixel coordinates themselves (the affine part of the spline reads them; computing them in
+  // the warp kernels costs an integer division and two double-precision divisions per thread)
+  tab[(int64_t)n * HW + m] = q0;
+  tab[(int64_t)(n + 1) * HW + m] = q1;
 }
 
 constexpr int TPS_BS_TAB = 1;      // samples per thread when phi comes from the table (1: most thread-level parallelism, fewest registers)
@@ -305,7 +309,10 @@ __global__ void tps_coef_kernel(const float* __restrict__ theta, const float* __
   coef[e] = acc;
 }
 
-template <int C>
+// NCP > 0: the control-point count is a compile-time constant (25 for the 5x5 grid every configuration uses): the
+// 32-iteration predicated loops of the generic kernel (NCP = 0) made it instruction-bound -- ncu: 33.5 M warp
+// instructions, 66 % issue-active, 50 us at 32 x 224^2 x 8; same arithmetic in the same order, bit-identical output.
+template <int C, int NCP>
 __global__ void __launch_bounds__(TPS_T) tps_warp_fwd_tab_kernel(const float* __restrict__ vol,
                                                                  const float* __restrict__ coef_g,
                                                                  const float* __restrict__ tab, float* __restrict__ out,
@@ -322,19 +329,20 @@ __global__ void __launch_bounds__(TPS_T) tps_warp_fwd_tab_kernel(const float* __
   const int HW = H * W;
   const int m = blockIdx.x * TPS_T + threadIdx.x;
   if (m >= HW) return;
-  const int row = m / W, col = m - row * W;
-  const float q0 = (float)((double)row / (double)(H - 1));
-  const float q1 = (float)((double)col / (double)(W - 1));
-  float ph[TPS_MAXN];
+  constexpr int NT = NCP > 0 ? NCP : TPS_MAXN;
+  float ph[NT];
+  const float* tp = tab + m;
 #pragma unroll
-  for (int t = 0; t < TPS_MAXN; ++t) ph[t] = t < n ? __ldg(tab + (int64_t)t * HW + m) : 0.f;
+  for (int t = 0; t < NT; ++t) ph[t] = (NCP > 0 || t < n) ? __ldg(tp + (size_t)t * (size_t)HW) : 0.f;
+  const float q0 = __ldg(tp + (size_t)n * (size_t)HW);            // row / (H - 1), col / (W - 1): rows n, n+1 of the table
+  const float q1 = __ldg(tp + (size_t)(n + 1) * (size_t)HW);
 #pragma unroll 2
   for (int s = 0; s < nb; ++s) {
     const float* cf = coef + s * (TPS_MAXN + 3) * 2;
     float lr = 0.f, lc = 0.f;
 #pragma unroll
-    for (int t = 0; t < TPS_MAXN; ++t) {
-      if (t < n) { lr = fmaf(ph[t], cf[2 * t], lr); lc = fmaf(ph[t], cf[2 * t + 1], lc); }
+    for (int t = 0; t < NT; ++t) {
+      if (NCP > 0 || t < n) { lr = fmaf(ph[t], cf[2 * t], lr); lc = fmaf(ph[t], cf[2 * t + 1], lc); }
     }
     lr += q0 * cf[2 * n] + q1 * cf[2 * (n + 1)] + cf[2 * (n + 2)];
     lc += q0 * cf[2 * n + 1] + q1 * cf[2 * (n + 1) + 1] + cf[2 * (n + 2) + 1];
@@ -347,23 +355,28 @@ __global__ void __launch_bounds__(TPS_T) tps_warp_fwd_tab_kernel(const float* __
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.f;
     if (bl.valid) {
+      // branch-free corners: an out-of-range corner is read at a clamped (in-range) address with weight 0 -- the same
+      // sums in the same order as four guarded blocks (adding 0 * v leaves a finite accumulator unchanged); 32-bit
+      // offsets inside one image
       const float* vb = vol + (int64_t)b * HW * C;
       const int cx = bl.fx + 1, cy = bl.fy + 1;
-      const float w00 = bl.dx * bl.dy, w11 = (1.f - bl.dx) * (1.f - bl.dy);
-      const float w01 = bl.dx * (1.f - bl.dy), w10 = (1.f - bl.dx) * bl.dy;
       const bool fxin = bl.fx >= 0 && bl.fx <= W - 1, cxin = cx >= 0 && cx <= W - 1;
       const bool fyin = bl.fy >= 0 && bl.fy <= H - 1, cyin = cy >= 0 && cy <= H - 1;
+      const float w00 = (fxin && fyin) ? bl.dx * bl.dy : 0.f, w11 = (cxin && cyin) ? (1.f - bl.dx) * (1.f - bl.dy) : 0.f;
+      const float w01 = (fxin && cyin) ? bl.dx * (1.f - bl.dy) : 0.f, w10 = (cxin && fyin) ? (1.f - bl.dx) * bl.dy : 0.f;
+      const int fxc = min(max(bl.fx, 0), W - 1), cxc = min(max(cx, 0), W - 1);
+      const int fyc = min(max(bl.fy, 0), H - 1), cyc = min(max(cy, 0), H - 1);
+      const int o00 = (fyc * W + fxc) * C, o11 = (cyc * W + cxc) * C, o01 = (cyc * W + fxc) * C, o10 = (fyc * W + cxc) * C;
 #pragma unroll
       for (int c = 0; c < C; c += 4) {
-        float4 v;
-        if (fxin && fyin) { v = *reinterpret_cast<const float4*>(vb + ((int64_t)bl.fy * W + bl.fx) * C + c);
-          acc[c] += w00 * v.x; acc[c + 1] += w00 * v.y; acc[c + 2] += w00 * v.z; acc[c + 3] += w00 * v.w; }
-        if (cxin && cyin) { v = *reinterpret_cast<const float4*>(vb + ((int64_t)cy * W + cx) * C + c);
-          acc[c] += w11 * v.x; acc[c + 1] += w11 * v.y; acc[c + 2] += w11 * v.z; acc[c + 3] += w11 * v.w; }
-        if (fxin && cyin) { v = *reinterpret_cast<const float4*>(vb + ((int64_t)cy * W + bl.fx) * C + c);
-          acc[c] += w01 * v.x; acc[c + 1] += w01 * v.y; acc[c + 2] += w01 * v.z; acc[c + 3] += w01 * v.w; }
-        if (cxin && fyin) { v = *reinterpret_cast<const float4*>(vb + ((int64_t)bl.fy * W + cx) * C + c);
-          acc[c] += w10 * v.x; acc[c + 1] += w10 * v.y; acc[c + 2] += w10 * v.z; acc[c + 3] += w10 * v.w; }
+        const float4 v00 = *reinterpret_cast<const float4*>(vb + o00 + c);
+        const float4 v11 = *reinterpret_cast<const float4*>(vb + o11 + c);
+        const float4 v01 = *reinterpret_cast<const float4*>(vb + o01 + c);
+        const float4 v10 = *reinterpret_cast<const float4*>(vb + o10 + c);
+        acc[c] += w00 * v00.x; acc[c + 1] += w00 * v00.y; acc[c + 2] += w00 * v00.z; acc[c + 3] += w00 * v00.w;
+        acc[c] += w11 * v11.x; acc[c + 1] += w11 * v11.y; acc[c + 2] += w11 * v11.z; acc[c + 3] += w11 * v11.w;
+        acc[c] += w01 * v01.x; acc[c + 1] += w01 * v01.y; acc[c + 2] += w01 * v01.z; acc[c + 3] += w01 * v01.w;
+        acc[c] += w10 * v10.x; acc[c + 1] += w10 * v10.y; acc[c + 2] += w10 * v10.z; acc[c + 3] += w10 * v10.w;
       }
     }
     float* ob = out + ((int64_t)b * HW + m) * C;
@@ -373,13 +386,17 @@ __global__ void __launch_bounds__(TPS_T) tps_warp_fwd_tab_kernel(const float* __
 }
 
 // backward.  smem: Phi[(n+3)][257] and D[2*TPS_BS][257]; G[b][j][2] += Phi^T D
-template <int C>
+// tab != nullptr: phi and the normalised pixel coordinates come from the geometry's table (tps_phi_table_kernel: the
+// same values bit for bit) instead of 25 logf + an integer and two double divisions per thread; NCP > 0: compile-time
+// control-point count (see the forward kernel).
+template <int C, int NCP>
 __global__ void __launch_bounds__(TPS_T) tps_warp_bwd_kernel(const float* __restrict__ vol, const float* __restrict__ theta,
                                                              const float* __restrict__ consts, const float* __restrict__ dout,
                                                              float* __restrict__ dvol, double* __restrict__ G, int B, int H,
-                                                             int W, int n) {
+                                                             int W, int n, const float* __restrict__ tab) {
   extern __shared__ float dyn[];
   constexpr int LD = TPS_T + 1;
+  constexpr int NT = NCP > 0 ? NCP : TPS_MAXN;
   float* Phi = dyn;                          // [(TPS_MAXN+3)][LD]
   float* D = Phi + (TPS_MAXN + 3) * LD;      // [2*TPS_BS][LD]
   __shared__ float cst[TPS_MAXN * (TPS_MAXN + 5)];
@@ -393,20 +410,32 @@ __global__ void __launch_bounds__(TPS_T) tps_warp_bwd_kernel(const float* __rest
   const int HW = H * W;
   const int m = blockIdx.x * TPS_T + threadIdx.x;
   const bool live = m < HW;
-  const int row = live ? m / W : 0, col = live ? m - row * W : 0;
-  const float q0 = (float)((double)row / (double)(H - 1));
-  const float q1 = (float)((double)col / (double)(W - 1));
-  const float qq = q0 * q0 + q1 * q1;
-  float ph[TPS_MAXN];
+  float q0, q1;
+  float ph[NT];
+  if (tab != nullptr) {
+    const float* tp = tab + (live ? m : 0);
 #pragma unroll
-  for (int t = 0; t < TPS_MAXN; ++t) {
-    if (t < n) {
-      float c0 = cs[2 * t], c1 = cs[2 * t + 1];
-      float r = qq - 2.f * (q0 * c0 + q1 * c1) + (c0 * c0 + c1 * c1);
-      ph[t] = live ? 0.5f * r * logf(fmaxf(r, TPS_EPS)) : 0.f;
-      Phi[t * LD + threadIdx.x] = ph[t];
-    } else {
-      ph[t] = 0.f;
+    for (int t = 0; t < NT; ++t) {
+      ph[t] = (live && (NCP > 0 || t < n)) ? __ldg(tp + (size_t)t * (size_t)HW) : 0.f;
+      if (NCP > 0 || t < n) Phi[t * LD + threadIdx.x] = ph[t];
+    }
+    q0 = live ? __ldg(tp + (size_t)n * (size_t)HW) : 0.f;
+    q1 = live ? __ldg(tp + (size_t)(n + 1) * (size_t)HW) : 0.f;
+  } else {
+    const int row = live ? m / W : 0, col = live ? m - row * W : 0;
+    q0 = (float)((double)row / (double)(H - 1));
+    q1 = (float)((double)col / (double)(W - 1));
+    const float qq = q0 * q0 + q1 * q1;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (NCP > 0 || t < n) {
+        float c0 = cs[2 * t], c1 = cs[2 * t + 1];
+        float r = qq - 2.f * (q0 * c0 + q1 * c1) + (c0 * c0 + c1 * c1);
+        ph[t] = live ? 0.5f * r * logf(fmaxf(r, TPS_EPS)) : 0.f;
+        Phi[t * LD + threadIdx.x] = ph[t];
+      } else {
+        ph[t] = 0.f;
+      }
     }
   }
   Phi[(n + 0) * LD + threadIdx.x] = live ? q0 : 0.f;
@@ -419,8 +448,8 @@ __global__ void __launch_bounds__(TPS_T) tps_warp_bwd_kernel(const float* __rest
       const float* cf = coef + s * (TPS_MAXN + 3) * 2;
       float lr = 0.f, lc = 0.f;
 #pragma unroll
-      for (int t = 0; t < TPS_MAXN; ++t) {
-        if (t < n) { lr = fmaf(ph[t], cf[2 * t], lr); lc = fmaf(ph[t], cf[2 * t + 1], lc); }
+      for (int t = 0; t < NT; ++t) {
+        if (NCP > 0 || t < n) { lr = fmaf(ph[t], cf[2 * t], lr); lc = fmaf(ph[t], cf[2 * t + 1], lc); }
       }
       lr += q0 * cf[2 * n] + q1 * cf[2 * (n + 1)] + cf[2 * (n + 2)];
       lc += q0 * cf[2 * n + 1] + q1 * cf[2 * (n + 1) + 1] + cf[2 * (n + 2) + 1];
@@ -659,7 +688,7 @@ int dafk_tps_warp_fwd(const float* vol, const float* theta, const float* consts,
   return check_launch("dafk_tps_warp_fwd");
 }
 
-int64_t dafk_tps_phi_table_floats(int H, int W, int n_cp) { return (int64_t)H * W * n_cp; }
+int64_t dafk_tps_phi_table_floats(int H, int W, int n_cp) { return (int64_t)H * W * (n_cp + 2); }
 
 int dafk_tps_phi_table(const float* consts, float* table, int H, int W, int n_cp, void* stream) {
   DAFK_REQUIRE(H > 1 && W > 1 && n_cp > 0 && n_cp <= TPS_MAXN, DAFK_ERR_BAD_ARG, "dafk_tps_phi_table: bad shape");
@@ -682,17 +711,22 @@ int dafk_tps_warp_fwd_tab(const float* vol, const float* theta, const float* con
   int rc = check_launch("dafk_tps_warp_fwd_tab(coef)");
   if (rc) return rc;
   dim3 grid((H * W + TPS_T - 1) / TPS_T, (B + TPS_BS_TAB - 1) / TPS_BS_TAB);
+  if (n_cp == 25 && C == 8) {        // the shipped geometry: 5 x 5 control points on the 8-channel anatomy
+    tps_warp_fwd_tab_kernel<8, 25><<<grid, TPS_T, 0, s>>>(vol, coef_ws, phi_table, out, locs, B, H, W, n_cp);
+    return check_launch("dafk_tps_warp_fwd_tab");
+  }
   switch (C) {
-    case 4: tps_warp_fwd_tab_kernel<4><<<grid, TPS_T, 0, s>>>(vol, coef_ws, phi_table, out, locs, B, H, W, n_cp); break;
-    case 8: tps_warp_fwd_tab_kernel<8><<<grid, TPS_T, 0, s>>>(vol, coef_ws, phi_table, out, locs, B, H, W, n_cp); break;
-    case 16: tps_warp_fwd_tab_kernel<16><<<grid, TPS_T, 0, s>>>(vol, coef_ws, phi_table, out, locs, B, H, W, n_cp); break;
+    case 4: tps_warp_fwd_tab_kernel<4, 0><<<grid, TPS_T, 0, s>>>(vol, coef_ws, phi_table, out, locs, B, H, W, n_cp); break;
+    case 8: tps_warp_fwd_tab_kernel<8, 0><<<grid, TPS_T, 0, s>>>(vol, coef_ws, phi_table, out, locs, B, H, W, n_cp); break;
+    case 16: tps_warp_fwd_tab_kernel<16, 0><<<grid, TPS_T, 0, s>>>(vol, coef_ws, phi_table, out, locs, B, H, W, n_cp); break;
     default: set_error("dafk_tps_warp_fwd_tab: C must be 4, 8 or 16 (got %d)", C); return DAFK_ERR_UNSUPPORTED;
   }
   return check_launch("dafk_tps_warp_fwd_tab");
 }
 
-int dafk_tps_warp_bwd(const float* vol, const float* theta, const float* consts, const float* dout, float* dvol,
-                      float* dtheta, double* ws, int B, int H, int W, int C, int n_cp, void* stream) {
+static int tps_warp_bwd_impl(const float* vol, const float* theta, const float* consts, const float* phi_table,
+                             const float* dout, float* dvol, float* dtheta, double* ws, int B, int H, int W, int C, int n_cp,
+                             void* stream) {
   DAFK_REQUIRE(B >= 0 && H > 1 && W > 1 && C > 0 && n_cp > 0, DAFK_ERR_BAD_ARG, "dafk_tps_warp_bwd: bad shape");
   DAFK_REQUIRE(n_cp <= TPS_MAXN, DAFK_ERR_UNSUPPORTED, "dafk_tps_warp_bwd: at most %d control points", TPS_MAXN);
   if (B == 0) return DAFK_OK;
@@ -702,25 +736,34 @@ int dafk_tps_warp_bwd(const float* vol, const float* theta, const float* consts,
   cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)B * (n_cp + 3) * 2, s);
   dim3 grid((H * W + TPS_T - 1) / TPS_T, (B + TPS_BS - 1) / TPS_BS);
   size_t smem = sizeof(float) * (size_t)((TPS_MAXN + 3) + 2 * TPS_BS) * (TPS_T + 1);
-  cudaError_t e = cudaSuccess;
-  switch (C) {
-    case 4:
-      e = cudaFuncSetAttribute(tps_warp_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      tps_warp_bwd_kernel<4><<<grid, TPS_T, smem, s>>>(vol, theta, consts, dout, dvol, ws, B, H, W, n_cp); break;
-    case 8:
-      e = cudaFuncSetAttribute(tps_warp_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      tps_warp_bwd_kernel<8><<<grid, TPS_T, smem, s>>>(vol, theta, consts, dout, dvol, ws, B, H, W, n_cp); break;
-    case 16:
-      e = cudaFuncSetAttribute(tps_warp_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      tps_warp_bwd_kernel<16><<<grid, TPS_T, smem, s>>>(vol, theta, consts, dout, dvol, ws, B, H, W, n_cp); break;
-    default: set_error("dafk_tps_warp_bwd: C must be 4, 8 or 16 (got %d)", C); return DAFK_ERR_UNSUPPORTED;
-  }
-  (void)e;
+#define TPS_BWD(CC, NN)                                                                                            \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(tps_warp_bwd_kernel<CC, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    tps_warp_bwd_kernel<CC, NN><<<grid, TPS_T, smem, s>>>(vol, theta, consts, dout, dvol, ws, B, H, W, n_cp, phi_table); \
+  } while (0)
+  if (C == 8 && n_cp == 25) TPS_BWD(8, 25);            // the shipped geometry
+  else if (C == 4) TPS_BWD(4, 0);
+  else if (C == 8) TPS_BWD(8, 0);
+  else if (C == 16) TPS_BWD(16, 0);
+  else { set_error("dafk_tps_warp_bwd: C must be 4, 8 or 16 (got %d)", C); return DAFK_ERR_UNSUPPORTED; }
+#undef TPS_BWD
   int rc = check_launch("dafk_tps_warp_bwd");
   if (rc) return rc;
   int total = B * n_cp * 2;
   tps_dtheta_kernel<<<(total + 127) / 128, 128, 0, s>>>(ws, consts, dtheta, B, n_cp);
   return check_launch("dafk_tps_warp_bwd(dtheta)");
+}
+
+int dafk_tps_warp_bwd(const float* vol, const float* theta, const float* consts, const float* dout, float* dvol,
+                      float* dtheta, double* ws, int B, int H, int W, int C, int n_cp, void* stream) {
+  return tps_warp_bwd_impl(vol, theta, consts, nullptr, dout, dvol, dtheta, ws, B, H, W, C, n_cp, stream);
+}
+
+int dafk_tps_warp_bwd_tab(const float* vol, const float* theta, const float* consts, const float* phi_table,
+                          const float* dout, float* dvol, float* dtheta, double* ws, int B, int H, int W, int C, int n_cp,
+                          void* stream) {
+  DAFK_REQUIRE(phi_table, DAFK_ERR_BAD_ARG, "dafk_tps_warp_bwd_tab: null table");
+  return tps_warp_bwd_impl(vol, theta, consts, phi_table, dout, dvol, dtheta, ws, B, H, W, C, n_cp, stream);
 }
 
 int dafk_resampler_fwd(const float* vol, const float* warp, float* out, int B, int H, int W, int C, int64_t m,

@@ -104,20 +104,46 @@ class Ctx:
         self.training = training
 
     def rec(self, *inputs):
-        return self.tape is not None and any(v.requires_grad for v in inputs if v is not None)
+        if self.tape is None:
+            return False
+        # the parameters a node is about to be recorded for: Tape.record() attaches them to the node, so that the data-parallel
+        # trainer knows after which node of the backward pass a range of the gradient arena is final (Tape.last_writers)
+        self.tape._pending = [v for v in inputs if isinstance(v, Param) and v.requires_grad]
+        return any(v.requires_grad for v in inputs if v is not None)
 
 
 class Tape:
     def __init__(self):
         self.nodes = []
+        self.node_params = []
+        self._pending = []
 
     def record(self, fn):
         self.nodes.append(fn)
+        self.node_params.append(self._pending)
+        self._pending = []
 
-    def backward(self):
-        for fn in reversed(self.nodes):
-            fn()
+    def backward(self, after_node=None):
+        """run the recorded nodes in reverse; ``after_node(i)`` is called when node i (forward order) has run"""
+        for i in range(len(self.nodes) - 1, -1, -1):
+            self.nodes[i]()
+            if after_node is not None:
+                after_node(i)
         self.nodes = []
+        self.node_params = []
+
+    def last_writers(self, ranges):
+        """for every (arena, a, b) range of a gradient arena: the forward index of the FIRST node that touches a parameter
+        inside it -- the backward pass runs the nodes in reverse, so once that node has run the range is final.
+        None: no recorded node writes there (frozen or unused parameters)."""
+        first = [None] * len(ranges)
+        for i, ps in enumerate(self.node_params):
+            for p in ps:
+                lo, hi = p.offset, p.offset + p.size
+                for k, (arena, a, b) in enumerate(ranges):
+                    if first[k] is None and p.arena is arena and lo < b and hi > a:
+                        first[k] = i
+        return first
 
 
 def accumulate(var, g, owned=True):
@@ -422,13 +448,21 @@ class Conv2D:
 
     def _call_s2d(self, ctx, srcs, act, alpha, od=torch.float32):
         code = ACT[act]
-        xin = srcs[0] if len(srcs) == 1 else concat(ctx, [s if s.data.dtype == torch.float32 else
-                                                          _cast_var(ctx, s, torch.float32) for s in srcs])
-        N, H, W, C = xin.shape
         k2 = (self.k + 1) // 2
         wide = self._s2d_wide()
+        N, H, W = srcs[0].shape[0], srcs[0].shape[1], srcs[0].shape[2]
+        C = sum(s.shape[-1] for s in srcs)
         nc_w = (not wide) and ops.nc_supported(4 * C, self.cout, k2, k2, (W + 1) // 2, 0, 2)
-        x2 = ops.space_to_depth2(xin.data)
+        # Concatenate([a, b]) -> stride-2 convolution (modality encoder): the two sources are rearranged where they lie and
+        # the gradient of the rearranged map is split straight back to them (no concatenated copy in either direction)
+        fused2 = len(srcs) == 2 and (wide or nc_w) and all(s.grad_dtype == torch.float32 for s in srcs)
+        if fused2:
+            xin = None
+            x2 = ops.space_to_depth2_cat(srcs[0].data, srcs[1].data)
+        else:
+            xin = srcs[0] if len(srcs) == 1 else concat(ctx, [s if s.data.dtype == torch.float32 else
+                                                              _cast_var(ctx, s, torch.float32) for s in srcs])
+            x2 = ops.space_to_depth2(xin.data)
         bias = self.bias.data if self.bias is not None else None
         wp_f, wp_d = self.packed_s2d()
         # bf16 storage of the activated output (and a bf16 gradient) only where every consumer below takes it
@@ -444,7 +478,8 @@ class Conv2D:
             y = Var(ops.conv_nc_fwd(x2, wp_f, bias, self.cout, k2, k2, 0, code, alpha, ydt))
         if lo:
             y.grad_dtype = torch.bfloat16
-        if ctx.rec(xin, self.kernel):
+        ins = list(srcs) if fused2 else [xin]
+        if ctx.rec(*ins, *self.params()):
             y.requires_grad = True
 
             def bw():
@@ -478,13 +513,19 @@ class Conv2D:
                     else:
                         xf = xin.data if xin.data.dtype == torch.float32 else ops.cast(xin.data, torch.float32)
                         ops.conv2d_wgrad(xf, g, self.kernel.grad, db, self.stride, self.pad)
-                if xin.requires_grad:
+                if any(v.requires_grad for v in ins):
                     if wide:
                         dx2 = torch.empty((N, (H + 1) // 2, (W + 1) // 2, 4 * C), dtype=torch.bfloat16, device=gb.device)
                         ops.conv_tc_fwd(gb, None, wp_d, None, 4 * C, k2, k2, 1, k2 - 1, torch.bfloat16, out=dx2)
                     else:
                         dx2 = ops.conv_nc_fwd(g, wp_d, None, 4 * C, k2, k2, k2 - 1, out_dtype=torch.bfloat16)
-                    accumulate(xin, ops.depth_to_space2(dx2, H, W, xin.grad_dtype))
+                    if fused2:
+                        ga, gb2 = ops.depth_to_space2_split(dx2, H, W, ins[0].shape[-1], ins[1].shape[-1],
+                                                            ins[0].requires_grad, ins[1].requires_grad)
+                        accumulate(ins[0], ga)
+                        accumulate(ins[1], gb2)
+                    else:
+                        accumulate(xin, ops.depth_to_space2(dx2, H, W, xin.grad_dtype))
 
             ctx.tape.record(bw)
         return y
@@ -503,7 +544,13 @@ class Conv2D:
         nc_f = nc and ops.nc_supported(self.cin, self.cout, self.k, self.k, W, self.pad, 0)
         nc_d = nc and ops.nc_supported(self.cin, self.cout, self.k, self.k, W, self.pad, 1)
         nc_w = nc and ops.nc_supported(self.cin, self.cout, self.k, self.k, W, self.pad, 2)
-        if len(srcs) == 1 and nc_f and nc_w:
+        # Concatenate([a, b]) -> narrow convolution (locnet, layers/stn_spline.py:104-106): both kernels read the two
+        # sources where they lie (a channel group picks its base pointer); only the data gradient is split afterwards
+        cat2 = (len(srcs) == 2 and nc_f and nc_w and nc_d and srcs[0].data.dtype == srcs[1].data.dtype
+                and srcs[0].shape[-1] % 8 == 0)
+        if cat2:
+            xin = None
+        elif len(srcs) == 1 and nc_f and nc_w:
             xin = srcs[0]                      # f32 or bf16: converted while it is staged
         else:
             f32srcs = [s if s.data.dtype == torch.float32 else _cast_var(ctx, s, torch.float32) for s in srcs]
@@ -514,12 +561,16 @@ class Conv2D:
         # (pixel, 8-channel) units, so halving the bytes per unit does not make them faster -- weight gradient 191 -> 289 us,
         # 64 -> 8 data gradient 326 -> 596 us -- and fp32 stays
         bf16_bw = self.bf16_grad and nc_f and nc_w and od == torch.bfloat16
-        if nc_f:
+        if cat2:
+            y = Var(ops.conv_nc_fwd_cat(srcs[0].data, srcs[1].data, self.packed_nc()[0], bias, self.cout, self.k, self.k,
+                                        self.pad, code, alpha, od))
+        elif nc_f:
             y = Var(ops.conv_nc_fwd(xin.data, self.packed_nc()[0], bias, self.cout, self.k, self.k, self.pad, code, alpha, od),
                     grad_dtype=torch.bfloat16 if bf16_bw else torch.float32)
         else:
             y = Var(ops.conv2d_fwd(xin.data, self.kernel.data, bias, self.stride, self.pad, code, alpha))
-        if ctx.rec(xin, self.kernel):
+        ins = list(srcs) if cat2 else [xin]
+        if ctx.rec(*ins, *self.params()):
             y.requires_grad = True
             tape_x = xin
 
@@ -544,11 +595,21 @@ class Conv2D:
                             g = ops.act_bwd(g, y.data, code, alpha)
                 if self.kernel.requires_grad:
                     db = self.bias.grad if (self.bias is not None and self.bias.requires_grad) else None
-                    if nc_w:
+                    if cat2:
+                        ops.conv_nc_wgrad_cat(ins[0].data, ins[1].data, g, self.kernel.grad, db, self.pad)
+                    elif nc_w:
                         ops.conv_nc_wgrad(tape_x.data, g, self.kernel.grad, db, self.pad)
                     else:
                         ops.conv2d_wgrad(tape_x.data, g, self.kernel.grad, db, self.stride, self.pad)
-                if tape_x.requires_grad:
+                if cat2:
+                    if any(v.requires_grad for v in ins):
+                        dx = ops.conv_nc_fwd(g, self.packed_nc()[1], None, self.cin, self.k, self.k, self.k - 1 - self.pad)
+                        off = 0
+                        for v in ins:
+                            if v.requires_grad:
+                                accumulate(v, ops.slice_channels(dx, off, v.shape[-1]))
+                            off += v.shape[-1]
+                elif tape_x.requires_grad:
                     if nc_d:
                         dx = ops.conv_nc_fwd(g, self.packed_nc()[1], None, self.cin, self.k, self.k, self.k - 1 - self.pad,
                                              out_dtype=tape_x.grad_dtype)
@@ -572,7 +633,7 @@ class Conv2D:
     def _call_1x1(self, ctx, xin):
         bias = self.bias.data if self.bias is not None else None
         y = Var(ops.conv1x1_fwd(xin.data, self.kernel.data, bias), grad_dtype=torch.float32)
-        if ctx.rec(xin, self.kernel):
+        if ctx.rec(xin, *self.params()):
             y.requires_grad = True
 
             def bw():
@@ -606,7 +667,7 @@ class Conv2D:
         # an fp32-stored activated output (last discriminator layer, feeds a Dense) takes its gradient in fp32 and
         # converts while the activation backward runs; everything else hands bf16 to the gradient kernels
         y = Var(raw, grad_dtype=torch.float32 if (fuse and raw.dtype == torch.float32) else torch.bfloat16)
-        rec = ctx.rec(*bsrcs, self.kernel)
+        rec = ctx.rec(*bsrcs, *self.params())
         if rec:
             y.requires_grad = True
             want_db = self.bias is not None and self.bias.requires_grad
@@ -691,7 +752,7 @@ class BatchNorm:
         else:
             mean, rstd = self.moving_mean.data, ops.bn_rstd_from_var(self.moving_var.data, self.EPS)
         y = Var(ops.bn_apply(x.data, mean, rstd, self.gamma.data, self.beta.data, code, out_dtype))
-        if ctx.rec(x, self.gamma):
+        if ctx.rec(x, *self.params()):
             assert ctx.training, "BatchNorm backward is only recorded in training mode"
             y.requires_grad = True
 
@@ -732,7 +793,7 @@ class InstanceNorm:
         acc = ops.in_stats(xin.data)
         out = ops.in_affine_fwd(xin.data, acc, self.gamma.data, self.beta.data, code, 0.0, self.EPS)
         y = Var(out)
-        if ctx.rec(xin, self.gamma):
+        if ctx.rec(xin, *self.params()):
             y.requires_grad = True
 
             def bw():
@@ -767,7 +828,7 @@ class Dense:
         x2 = x.data.reshape(x.shape[0], -1)
         assert x2.shape[1] == self.cin, (self.name, tuple(x.shape), self.cin)
         y = Var(ops.dense_fwd(x2, self.kernel.data, self.bias.data))
-        if ctx.rec(x, self.kernel):
+        if ctx.rec(x, *self.params()):
             y.requires_grad = True
 
             def bw():

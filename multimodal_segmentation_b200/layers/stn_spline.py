@@ -80,8 +80,8 @@ def build_locnet(input_shape1, input_shape2, output_shape):
     d2 = E.Dense(a, r, "loc_theta", 100, output_shape, "zeros")
 
     def fwd(ctx, x1, x2):
-        l = E.concat(ctx, [x1, x2])
-        l = E.maxpool2(ctx, c1(ctx, l, "lrelu", 0.3))
+        # Concatenate([x1, x2]): the first convolution reads the two maps where they lie
+        l = E.maxpool2(ctx, c1(ctx, [x1, x2], "lrelu", 0.3))
         l = E.maxpool2(ctx, c2(ctx, l, "lrelu", 0.3))
         l = c3(ctx, l, "lrelu", 0.3)
         l = d1(ctx, l, "tanh")

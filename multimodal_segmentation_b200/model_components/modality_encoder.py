@@ -31,7 +31,7 @@ def build(conf):
     z_log_var = E.Dense(a, r, "z_log_var", 32, conf.num_z)
 
     def trunk(ctx, anatomy, image):
-        l = E.concat(ctx, [anatomy, image])
+        l = [anatomy, image]          # Concatenate()([anatomy, image]): the first convolution reads the two sources where they lie
         for cv in convs:
             l = cv(ctx, l, "lrelu", 0.3)
         return d1(ctx, l, "lrelu", 0.3)

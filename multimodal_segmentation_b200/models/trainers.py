@@ -79,28 +79,65 @@ class Trainer(object):
         self.forward_backward(*inputs)
         self.apply_gradients()
 
+    AR_CHUNK = 8 << 20      # floats per all-reduce piece (32 MB): large enough for NVLink bandwidth, small enough to overlap
+
     def forward_backward(self, *inputs):
-        """loss + gradients into the flat bucket (no weight update)"""
+        """loss + gradients into the flat bucket (no weight update).  Data-parallel: a piece of the gradient arena is
+        all-reduced (asynchronously, on NCCL's stream) as soon as the last node of the backward pass that writes into it
+        has run, so the collective overlaps the rest of the backward pass; apply_gradients() waits for the pieces."""
         self.book.reset()
         self.opt.zero_grad()
         tape = E.Tape()
         ctx = E.Ctx(tape, training=True)
         for m in self.frozen_models:
             m.trainable = False
+        self._ar_works, self._ar_done = [], set()
         try:
             self.graph(ctx, self.book, *inputs)
-            tape.backward()
+            after = None
+            d = Trainer.dist
+            overlap = (d is not None and d.world_size > 1 and getattr(d, "overlap", False)
+                       and type(self).extra_grads is Trainer.extra_grads)     # regulariser gradients are added after the tape
+            if overlap:
+                pieces = self._ar_pieces()
+                first = tape.last_writers(pieces)
+                by_node = {}
+                for k, i in enumerate(first):
+                    if i is not None:
+                        by_node.setdefault(i, []).append(k)
+
+                def after(i):
+                    for k in by_node.get(i, ()):
+                        arena, a, b = pieces[k]
+                        self._ar_works.append(d.allreduce_async(arena.gflat[a:b]))
+                        self._ar_done.add((id(arena), a, b))
+            tape.backward(after)
         finally:
             for m in self.frozen_models:
                 m.trainable = True
         self.extra_grads(self.book)
 
+    def _ar_pieces(self):
+        out = []
+        for arena, a, b in self.opt.ranges:
+            for lo in range(a, b, self.AR_CHUNK):
+                out.append((arena, lo, min(b, lo + self.AR_CHUNK)))
+        return out
+
     def apply_gradients(self):
         """(all-reduce when data-parallel) + one fused Adam launch per bucket"""
         scale = 1.0
-        if Trainer.dist is not None and Trainer.dist.world_size > 1:
-            Trainer.dist.allreduce_(self.opt.grad_buckets())
-            scale = 1.0 / Trainer.dist.world_size
+        d = Trainer.dist
+        if d is not None and d.world_size > 1:
+            done = getattr(self, "_ar_done", set())
+            if done:
+                rest = [arena.gflat[a:b] for arena, a, b in self._ar_pieces() if (id(arena), a, b) not in done]
+                d.allreduce_(rest)
+                d.wait(self._ar_works)
+                self._ar_works, self._ar_done = [], set()
+            else:
+                d.allreduce_(self.opt.grad_buckets())
+            scale = 1.0 / d.world_size
         self.opt.step(grad_scale=scale)
 
     def fit(self, inputs, targets, epochs=1, verbose=0, batch_size=32):

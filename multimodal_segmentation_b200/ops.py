@@ -652,6 +652,38 @@ def conv_nc_fwd(x, wp, bias, Cout, KH, KW, pad, act=ACT_NONE, alpha=0.0, out_dty
     return y
 
 
+def conv_nc_fwd_cat(xa, xb, wp, bias, Cout, KH, KW, pad, act=ACT_NONE, alpha=0.0, out_dtype=torch.float32):
+    """conv_nc_fwd on concat([xa, xb], -1) read where the sources lie (same dtype, xa a multiple of 8 channels)"""
+    _chk(xa, xb, wp, bias)
+    N, H, W, Ca = xa.shape
+    Cb = xb.shape[-1]
+    assert xa.dtype == xb.dtype and tuple(xb.shape[:3]) == (N, H, W) and Ca % 8 == 0
+    Ho, Wo = H + 2 * pad - KH + 1, W + 2 * pad - KW + 1
+    y = torch.empty((N, Ho, Wo, Cout), dtype=out_dtype, device=xa.device)
+    fl = 2.0 * N * Ho * Wo * Cout * KH * KW * (Ca + Cb)
+    nb = (xa.numel() + xb.numel()) * xa.element_size() + y.numel() * y.element_size()
+    instrument.timed("conv_nc_fwd+dgrad (tcgen05)", fl, nb,
+                     lambda: call("conv_nc_fwd_cat", xa, Ca, xb, Cb, _dt(xa), wp, bias, y, _dt(y), N, H, W, Cout, KH, KW, pad, act,
+                                  float(alpha), _S()),
+                     tag=(N, H, W, Ca + Cb, Cout, KH, pad, str(xa.dtype)[6:], str(out_dtype)[6:], "cat"))
+    return y
+
+
+def conv_nc_wgrad_cat(xa, xb, dy, dw, db, pad):
+    """conv_nc_wgrad with x = concat([xa, xb], -1) read where the sources lie"""
+    _chk(xa, xb, dy, dw, db)
+    N, H, W, Ca = xa.shape
+    Cb = xb.shape[-1]
+    KH, KW, Cin, Cout = dw.shape
+    assert Cin == Ca + Cb and xa.dtype == xb.dtype
+    fl = 2.0 * dy.numel() * KH * KW * Cin
+    nb = (xa.numel() + xb.numel()) * xa.element_size() + dy.numel() * dy.element_size()
+    instrument.timed("conv_nc_wgrad (tcgen05)", fl, nb,
+                     lambda: call("conv_nc_wgrad_cat", xa, Ca, xb, Cb, _dt(xa), dy, _dt(dy), dw, db, N, H, W, Cout, KH, KW, pad,
+                                  _S()),
+                     tag=(N, H, W, Cin, Cout, KH, pad, str(xa.dtype)[6:], str(dy.dtype)[6:], "cat"))
+
+
 def conv_nc_wgrad(x, dy, dw, db, pad):
     """dw[KH,KW,Cin,Cout] += x (*) dy; db += sum dy (db may be None); stride 1"""
     _chk(x, dy, dw, db)
@@ -710,6 +742,28 @@ def space_to_depth2(x):
     y = torch.empty((N, (H + 1) // 2, (W + 1) // 2, 4 * C), dtype=torch.bfloat16, device=x.device)
     call("space_to_depth2", x, _dt(x), y, N, H, W, C, _S())
     return y
+
+
+def space_to_depth2_cat(xa, xb):
+    """space_to_depth2(concat([xa, xb], -1)) without the concatenated copy"""
+    _chk(xa, xb)
+    N, H, W, Ca = xa.shape
+    Cb = xb.shape[-1]
+    assert tuple(xb.shape[:3]) == (N, H, W)
+    y = torch.empty((N, (H + 1) // 2, (W + 1) // 2, 4 * (Ca + Cb)), dtype=torch.bfloat16, device=xa.device)
+    call("space_to_depth2_cat", xa, _dt(xa), Ca, xb, _dt(xb), Cb, y, N, H, W, _S())
+    return y
+
+
+def depth_to_space2_split(y, H, W, Ca, Cb, want_a=True, want_b=True):
+    """inverse of space_to_depth2_cat for gradients: fp32 [N,H,W,Ca] and [N,H,W,Cb] (None where not wanted)"""
+    _chk(y)
+    N = y.shape[0]
+    assert y.shape[-1] == 4 * (Ca + Cb)
+    ga = torch.empty((N, H, W, Ca), dtype=torch.float32, device=y.device) if want_a else None
+    gb = torch.empty((N, H, W, Cb), dtype=torch.float32, device=y.device) if want_b else None
+    call("depth_to_space2_split", y, _dt(y), ga, Ca, gb, Cb, N, H, W, _S())
+    return ga, gb
 
 
 def depth_to_space2(y, H, W, out_dtype=torch.float32):
@@ -819,6 +873,11 @@ def tps_warp_bwd(vol, theta, dout, cp=(5, 5), need_dvol=True):
         dvol = zero_(torch.empty_like(vol))
     dtheta = f32(B, n, 2)
     ws = torch.empty(B * (n + 3) * 2, dtype=torch.float64, device=vol.device)
+    if TPS_PHI_TABLE:
+        tab = tps_phi_table(H, W, cp, vol.device)
+        instrument.timed("tps_warp_bwd", 0, 12.0 * vol.numel(),
+                         lambda: call("tps_warp_bwd_tab", vol, theta, consts, tab, dout, dvol, dtheta, ws, B, H, W, C, n, _S()))
+        return dvol, dtheta
     instrument.timed("tps_warp_bwd", 0, 12.0 * vol.numel(),
                      lambda: call("tps_warp_bwd", vol, theta, consts, dout, dvol, dtheta, ws, B, H, W, C, n, _S()))
     return dvol, dtheta

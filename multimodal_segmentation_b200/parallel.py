@@ -2,6 +2,8 @@
 bucket per optimizer step, 1/world folded into the fused Adam launch.  Nothing else shards
 (SURVEY.md 8e): BatchNorm statistics and the cross-entropy class weights stay per-shard, exactly what
 Keras' fit() would do with 32-sample mini-batches."""
+import os
+
 import torch.distributed as dist
 
 from .models.trainers import Trainer
@@ -12,9 +14,21 @@ class _Dist(object):
         self.world_size = dist.get_world_size()
         self.rank = dist.get_rank()
 
+    # all-reduce pieces of the gradient arena while the backward pass is still running (Trainer.forward_backward);
+    # DAFK_AR_OVERLAP=0 falls back to one all-reduce per bucket after the backward pass
+    overlap = os.environ.get("DAFK_AR_OVERLAP", "1") != "0"
+
     def allreduce_(self, buckets):
         for b in buckets:
             dist.all_reduce(b, op=dist.ReduceOp.SUM)
+
+    def allreduce_async(self, t):
+        """enqueue on NCCL's own stream (it first waits for the work queued so far on the current stream); returns the handle"""
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
+
+    def wait(self, works):
+        for w in works:
+            w.wait()          # the current stream waits for the collective (no host synchronisation)
 
 
 def broadcast_weights(net):

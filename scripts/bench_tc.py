@@ -48,12 +48,13 @@ def main():
         w = torch.randn(3, 3, Cin, Cout, device="cuda") * 0.05
         wp = ops.pack_conv(w, 0)
         bias = torch.zeros(Cout, device="cuda")
-        y = torch.empty(B, H, H, Cout, device="cuda")
+        ybf = os.environ.get("TC_YBF16", "1") == "1"       # output stored in bf16 as in the benched step (engine.RAW_BF16)
+        y = torch.empty(B, H, H, Cout, device="cuda", dtype=torch.bfloat16 if ybf else torch.float32)
         dy = torch.randn(B, H, H, Cout, device="cuda").to(torch.bfloat16)
         dw = ops.zeros(3, 3, Cin, Cout)
         fl = 2.0 * B * H * H * Cout * 9 * Cin
         f = L["dafk_conv_tc_fwd"]
-        args = [x0.data_ptr(), C0, x1.data_ptr() if C1 else None, C1, wp.data_ptr(), Cout, 0, bias.data_ptr(), y.data_ptr(), 0,
+        args = [x0.data_ptr(), C0, x1.data_ptr() if C1 else None, C1, wp.data_ptr(), Cout, 0, bias.data_ptr(), y.data_ptr(), 1 if ybf else 0,
                 B, H, H, Cout, 3, 3, 1, 1, H, H, H * H * Cout, H * Cout, Cout, S]
         t = timeit(lambda: f(*args), reps)
         g = L["dafk_conv_tc_wgrad"]

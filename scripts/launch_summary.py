@@ -8,6 +8,21 @@ from collections import defaultdict
 rows = []
 with open(sys.argv[1], newline="") as f:
     lines = [l for l in f if not l.startswith("==")]
+dram = defaultdict(float)
+if lines and "gpu__time_duration.sum" in lines[0]:
+    # `--page raw` list: one row per launch, one column per metric, units in the second row
+    table = list(csv.reader(l for l in lines if l.startswith('"')))
+    header, units = table[0], dict(zip(table[0], table[1]))
+    tscale = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3}[units["gpu__time_duration.sum"]]
+    bscale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in table[2:]:
+        d = dict(zip(header, r))
+        name = re.sub(r"\(.*$", "", d["Kernel Name"]).replace("void ", "").replace("dafk::", "")
+        rows.append((name, float(d["gpu__time_duration.sum"].replace(",", "")) * tscale))
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            if d.get(k):
+                dram[name] += float(d[k].replace(",", "")) * bscale[units[k]]
+    lines = []
 for r in csv.DictReader(lines):
     if r.get("Metric Name") != "gpu__time_duration.sum":
         continue
@@ -26,6 +41,6 @@ tot = sum(v[1] for v in agg.values())
 print("# %s" % (sys.argv[2] if len(sys.argv) > 2 else ""))
 print("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes")
 print("# %d launches, %.1f ms summed kernel time" % (len(rows), tot / 1000.0))
-print("%-70s %5s %12s %7s" % ("kernel", "n", "total_us", "share"))
+print("%-70s %5s %12s %7s %14s" % ("kernel", "n", "total_us", "share", "dram MB/launch"))
 for n, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print("%-70s %5d %12.1f %6.1f%%" % (n[:70], c, us, 100.0 * us / tot))
+    print("%-70s %5d %12.1f %6.1f%% %14s" % (n[:70], c, us, 100.0 * us / tot, ("%.2f" % (dram[n] / c / 1e6)) if n in dram else "-"))

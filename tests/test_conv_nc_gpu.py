@@ -213,3 +213,109 @@ def test_stride2_conv_through_space_to_depth(ops, case):
     assert rel_l2(cpu(xv.grad), xt.grad.numpy()) < 5e-3
     assert rel_l2(cpu(conv.kernel.grad), wt.grad.numpy()) < 5e-3
     assert rel_l2(cpu(conv.bias.grad), (dy * (yr.detach().numpy() > 0) + 0.3 * dy * (yr.detach().numpy() < 0)).sum((0, 1, 2))) < 5e-3
+
+
+def _s2d_ref(x):
+    """y[n, i, j, (dy*2+dx)*C + c] = x[n, 2i+dy, 2j+dx, c], zero beyond odd sizes (csrc/s2d.cu)"""
+    N, H, W, C = x.shape
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    xp = np.zeros((N, 2 * H2, 2 * W2, C), x.dtype)
+    xp[:, :H, :W] = x
+    return xp.reshape(N, H2, 2, W2, 2, C).transpose(0, 1, 3, 2, 4, 5).reshape(N, H2, W2, 4 * C)
+
+
+@pytest.mark.parametrize("shape", [(2, 9, 11, 9), (3, 14, 14, 4), (2, 13, 12, 16), (2, 7, 8, 64), (1, 5, 5, 1)])
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_space_to_depth_kernels_bit_exact(ops, shape, dt, monkeypatch):
+    """both forward kernels (one thread per pixel quadrant = default, one per element) and the inverse, odd and even
+    extents, vector (C % 8 == 0) and scalar channel counts"""
+    r = np.random.RandomState(sum(shape))
+    x = bf16_round(r.normal(size=shape).astype(np.float32))
+    xg = gpu(x, torch.bfloat16 if dt == "bf16" else torch.float32)
+    want = _s2d_ref(x)
+    y = ops.space_to_depth2(xg)
+    assert y.dtype == torch.bfloat16 and np.array_equal(cpu(y), want)
+    back = ops.depth_to_space2(y, shape[1], shape[2])
+    assert np.array_equal(cpu(back), x)
+
+
+@pytest.mark.parametrize("shape", [(2, 9, 11, 8, 1), (2, 14, 14, 1, 8), (1, 7, 6, 3, 5), (2, 12, 13, 8, 8)])
+def test_space_to_depth_of_a_concatenation_and_its_split_backward(ops, shape):
+    """dafk_space_to_depth2_cat == space_to_depth2(concat) bit for bit (mixed source dtypes); depth_to_space2_split hands
+    each source its slice of the rearranged gradient"""
+    N, H, W, Ca, Cb = shape
+    r = np.random.RandomState(sum(shape))
+    a = bf16_round(r.normal(size=(N, H, W, Ca)).astype(np.float32))
+    b = bf16_round(r.normal(size=(N, H, W, Cb)).astype(np.float32))
+    want = _s2d_ref(np.concatenate([a, b], -1))
+    for da, db in ((torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.float32)):
+        y = ops.space_to_depth2_cat(gpu(a, da), gpu(b, db))
+        assert np.array_equal(cpu(y), want)
+    g = bf16_round(r.normal(size=want.shape).astype(np.float32))
+    for gdt in (torch.float32, torch.bfloat16):
+        ga, gb = ops.depth_to_space2_split(gpu(g, gdt), H, W, Ca, Cb)
+        full = cpu(ops.depth_to_space2(gpu(g, gdt), H, W))
+        assert np.array_equal(cpu(ga), full[..., :Ca]) and np.array_equal(cpu(gb), full[..., Ca:])
+    ga, gb = ops.depth_to_space2_split(gpu(g), H, W, Ca, Cb, want_a=False)
+    assert ga is None and np.array_equal(cpu(gb), full[..., Ca:])
+
+
+def test_modality_encoder_first_layer_reads_two_sources(ops):
+    """Concatenate([anatomy, image]) -> Conv2D(3x3, stride 2) (model_components/modality_encoder.py:34-38): the fused
+    two-source path against the oracle convolution of the concatenation, forward and all gradients"""
+    from multimodal_segmentation_b200 import engine as E
+    N, H, W, Ca, Cb, Cout, k = 2, 33, 31, 8, 1, 16, 3
+    r = np.random.RandomState(5)
+    a = bf16_round(r.normal(size=(N, H, W, Ca)).astype(np.float32))
+    b = bf16_round(r.normal(size=(N, H, W, Cb)).astype(np.float32))
+    w = bf16_round((r.normal(size=(k, k, Ca + Cb, Cout)) / np.sqrt(k * k * (Ca + Cb))).astype(np.float32))
+    bias = r.normal(size=Cout).astype(np.float32)
+    at, bt, wt = t(a, torch.float64, grad=True), t(b, torch.float64, grad=True), t(w, torch.float64, grad=True)
+    yr = R.leaky_relu(R.conv2d(torch.cat([at, bt], -1), wt, t(bias, torch.float64), 2, "valid"), 0.3)
+    dy = bf16_round(r.normal(size=tuple(yr.shape)).astype(np.float32))
+    (yr * t(dy, torch.float64)).sum().backward()
+    E.USE_TC = True
+    arena = E.Arena(True)
+    conv = E.Conv2D(arena, r, "c", Ca + Cb, Cout, k, 2, "valid")
+    arena.to_device()
+    conv.kernel.data.copy_(gpu(w))
+    conv.bias.data.copy_(gpu(bias))
+    tape = E.Tape()
+    ctx = E.Ctx(tape, True)
+    av, bv = E.Var(gpu(a), True), E.Var(gpu(b), True)
+    n0 = ops._lib.launch_count()
+    y = conv(ctx, [av, bv], "lrelu", 0.3)
+    assert ops._lib.launch_count() - n0 <= 5           # rearrangement + weight operands + convolution, no concatenation
+    assert rel_l2(cpu(y.data), yr.detach().numpy()) < 1e-4
+    y.grad = gpu(dy)
+    tape.backward()
+    assert rel_l2(cpu(av.grad), at.grad.numpy()) < 5e-3 and rel_l2(cpu(bv.grad), bt.grad.numpy()) < 5e-3
+    assert rel_l2(cpu(conv.kernel.grad), wt.grad.numpy()) < 5e-3
+
+
+@pytest.mark.parametrize("case", [(2, 20, 24, 8, 8, 20, 5, 0, "f32"), (3, 17, 19, 8, 8, 20, 5, 0, "bf16"), (2, 12, 14, 16, 8, 16, 3, 1, "f32"),
+                                  (2, 12, 14, 8, 4, 8, 3, 1, "f32")])
+def test_conv_nc_two_concatenated_sources(ops, case):
+    """dafk_conv_nc_fwd_cat / dafk_conv_nc_wgrad_cat (the locnet's Concatenate([s1, s2]) -> Conv2D(20, 5),
+    layers/stn_spline.py:104-106): bit-identical to the single-source kernels on the materialised concatenation"""
+    from multimodal_segmentation_b200._lib import ACT_LRELU
+    N, H, W, Ca, Cb, Cout, k, pad, dt = case
+    tdt = torch.bfloat16 if dt == "bf16" else torch.float32
+    r = np.random.RandomState(sum(case[:8]))
+    a = gpu(bf16_round(r.normal(size=(N, H, W, Ca)).astype(np.float32)), tdt)
+    b = gpu(bf16_round(r.normal(size=(N, H, W, Cb)).astype(np.float32)), tdt)
+    w = gpu((r.normal(size=(k, k, Ca + Cb, Cout)) / np.sqrt(k * k * (Ca + Cb))).astype(np.float32))
+    bias = gpu(r.normal(size=Cout).astype(np.float32))
+    cat = torch.cat([a, b], -1).contiguous()
+    assert ops.nc_supported(Ca + Cb, Cout, k, k, W, pad, 0) and ops.nc_supported(Ca + Cb, Cout, k, k, W, pad, 2)
+    wp = ops.pack_conv_nc(w, 0)
+    y1 = ops.conv_nc_fwd(cat, wp, bias, Cout, k, k, pad, ACT_LRELU, 0.3)
+    y2 = ops.conv_nc_fwd_cat(a, b, wp, bias, Cout, k, k, pad, ACT_LRELU, 0.3)
+    assert torch.equal(y1, y2)
+    dy = gpu(r.normal(size=tuple(y1.shape)).astype(np.float32))
+    dw1, db1, dw2, db2 = ops.zeros(k, k, Ca + Cb, Cout), ops.zeros(Cout), ops.zeros(k, k, Ca + Cb, Cout), ops.zeros(Cout)
+    ops.conv_nc_wgrad(cat, dy, dw1, db1, pad)
+    ops.conv_nc_wgrad_cat(a, b, dy, dw2, db2, pad)
+    torch.cuda.synchronize()
+    # the weight gradient accumulates per-CTA partial sums with atomics: same terms, order may differ
+    assert rel_l2(cpu(dw2), cpu(dw1)) < 1e-5 and rel_l2(cpu(db2), cpu(db1)) < 1e-5

@@ -575,3 +575,27 @@ def test_tps_phi_table_path_is_bit_identical(ops):
     finally:
         ops.TPS_PHI_TABLE = old
     assert torch.equal(a, b) and torch.equal(la, lb)
+    # backward: the table kernel (compile-time 25 control points, phi and pixel coordinates from the table) against the
+    # in-kernel evaluation -- same arithmetic; the scatter into the volume uses atomics, so compare to round-off
+    dout = gpu(rng(2).normal(size=(B, H, W, C)).astype(np.float32))
+    try:
+        ops.TPS_PHI_TABLE = True
+        dv_a, dt_a = ops.tps_warp_bwd(vol, theta, dout)
+        ops.TPS_PHI_TABLE = False
+        dv_b, dt_b = ops.tps_warp_bwd(vol, theta, dout)
+    finally:
+        ops.TPS_PHI_TABLE = old
+    assert rel_l2(cpu(dv_a), cpu(dv_b)) < 1e-6 and rel_l2(cpu(dt_a), cpu(dt_b)) < 1e-6
+    # other channel counts / control grids take the generic kernels
+    vol4 = gpu(rng(3).uniform(size=(3, 20, 22, 4)).astype(np.float32))
+    th9 = gpu((rng(4).normal(size=(3, 9, 2)) * 0.05).astype(np.float32))
+    try:
+        ops.TPS_PHI_TABLE = True
+        a4, _ = ops.tps_warp_fwd(vol4, th9, cp=(3, 3))
+        g4 = ops.tps_warp_bwd(vol4, th9, a4, cp=(3, 3))
+        ops.TPS_PHI_TABLE = False
+        b4, _ = ops.tps_warp_fwd(vol4, th9, cp=(3, 3))
+        h4 = ops.tps_warp_bwd(vol4, th9, a4, cp=(3, 3))
+    finally:
+        ops.TPS_PHI_TABLE = old
+    assert torch.equal(a4, b4) and rel_l2(cpu(g4[0]), cpu(h4[0])) < 1e-6 and rel_l2(cpu(g4[1]), cpu(h4[1])) < 1e-6

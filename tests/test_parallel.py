@@ -212,3 +212,79 @@ def test_reference_arm_line_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["metric"].startswith("DAFNet train slices/s") and "workload" in d["config"]
+
+
+# ------------------------------------------------------------------------------------------------ overlapped all-reduce
+def test_tape_last_writers_maps_arena_ranges_to_backward_nodes():
+    """host logic of the overlapped all-reduce: a range of the gradient arena is final once the FIRST recorded node (in
+    forward order) that owns a parameter inside it has run in the backward pass; ranges nobody writes report None"""
+    sys.path.insert(0, ROOT)
+    from multimodal_segmentation_b200 import engine as E
+    arena, other = E.Arena(), E.Arena()
+    ps = [arena.add("p%d" % i, (10,), np.zeros(10, np.float32)) for i in range(4)]      # offsets 0, 12, 24, 36
+    q = other.add("q", (10,), np.zeros(10, np.float32))
+    for p in ps + [q]:
+        p.requires_grad = True
+    ps[3].requires_grad = False                                                          # frozen: never recorded
+    tape = E.Tape()
+    ctx = E.Ctx(tape, training=True)
+    x = E.Var(torch.zeros(1), requires_grad=True)
+    for used in ([ps[0]], [ps[1], q], [ps[0], ps[2]], [ps[3]]):                          # p0 is used by nodes 0 and 2
+        assert ctx.rec(x, *used)
+        tape.record(lambda: None)
+    assert [len(n) for n in tape.node_params] == [1, 2, 2, 0]
+    ranges = [(arena, 0, 12), (arena, 12, 24), (arena, 24, 36), (arena, 36, 48), (arena, 0, 48), (other, 0, 12), (arena, 8, 14)]
+    assert tape.last_writers(ranges) == [0, 1, 2, None, 0, 1, 0]
+    order = []
+    tape.backward(order.append)
+    assert order == [3, 2, 1, 0] and tape.nodes == []
+
+
+@pytest.mark.gpu
+def test_overlapped_allreduce_fires_each_piece_after_its_last_write():
+    """one generator forward/backward with a recording stand-in for the process group: every piece of the gradient arena
+    handed to the asynchronous all-reduce during the backward pass must already hold its FINAL value (nothing writes into
+    it afterwards), most of the arena must go out before the backward pass ends, and the pieces + the remainder that
+    apply_gradients() reduces cover the bucket exactly once"""
+    from multimodal_segmentation_b200.models.trainers import Trainer
+    from tests.test_models_gpu import make_batch
+
+    class Recorder(object):
+        world_size, rank, overlap = 2, 0, True
+
+        def __init__(self):
+            self.fired, self.rest, self.waited = [], [], 0
+
+        def allreduce_async(self, t):
+            self.fired.append((t, t.clone()))
+            return None
+
+        def allreduce_(self, buckets):
+            self.rest.extend(buckets)
+
+        def wait(self, works):
+            self.waited += len(works)
+
+    net = _gpu_setup(5)
+    from multimodal_segmentation_b200 import engine as E
+    E.USE_TC = True
+    tr = net.supervised_trainer
+    old_chunk, old_dist = Trainer.AR_CHUNK, Trainer.dist
+    Trainer.AR_CHUNK, Trainer.dist = 1 << 15, Recorder()
+    try:
+        dev = [torch.from_numpy(a).cuda() for a in make_batch(_tiny_conf(0), 2, seed=21)]
+        tr.forward_backward(*dev)
+        torch.cuda.synchronize()
+        rec = Trainer.dist
+        total = sum(b.numel() for b in tr.opt.grad_buckets())
+        assert len(rec.fired) > 4 and sum(t.numel() for t, _ in rec.fired) > 0.9 * total
+        for t, snap in rec.fired:
+            assert torch.equal(t, snap)                       # final when it was handed to the collective
+        assert any(float(snap.abs().sum()) > 0 for _, snap in rec.fired)
+        tr.apply_gradients()
+        torch.cuda.synchronize()
+        assert rec.waited == len(rec.fired)
+        assert sum(t.numel() for t, _ in rec.fired) + sum(b.numel() for b in rec.rest) == total
+    finally:
+        Trainer.AR_CHUNK, Trainer.dist = old_chunk, old_dist
+        E.USE_TC = True
