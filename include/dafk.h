@@ -310,6 +310,13 @@ int dafk_conv_tc_fwd_act(const void* x0, int C0, const void* x1, int C1, const v
                          int w_row_off, const float* bias, void* y, int y_dt, int N, int H, int W, int Cout, int KH,
                          int KW, int stride, int pad, int Ho, int Wo, int64_t y_sn, int64_t y_sy, int64_t y_sx, int act,
                          float alpha, void* stream);
+/* Conv2D -> BatchNormalization in the training phase (models/unet.py:95-96, utils/model_utils.py:10): the convolution
+ * writes its output y [N,Ho,Wo,Cout] in bf16 and ALSO accumulates the batch statistics of exactly those stored values,
+ * bn_acc[c] += sum y[..,c], bn_acc[Cout + c] += sum y[..,c]^2 (fp64, caller zeroes it), from its epilogue; dafk_bn_finalize
+ * turns them into mean / rstd and updates the moving statistics -- the separate statistics pass over y disappears. */
+int dafk_conv_tc_fwd_bn(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap, int w_row_off,
+                        const float* bias, void* y_bf16, double* bn_acc, int N, int H, int W, int Cout, int KH, int KW,
+                        int stride, int pad, void* stream);
 int dafk_bn_fold(const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
                  const float* conv_bias, float eps, float* scale, float* bias_out, int C, void* stream);
 int dafk_pack_conv_scaled(const float* w_hwio, const float* scale, void* wp, int KH, int KW, int Cin, int Cout, void* stream);

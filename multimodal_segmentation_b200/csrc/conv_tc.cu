@@ -40,7 +40,48 @@ struct TileGeom {
 struct Epi {
   int code;
   float alpha;
+  double* bn_acc;      // != nullptr: per-channel sum / sum of squares of the STORED (bf16-rounded) outputs, [2][Cout] doubles
 };
+
+// BatchNormalization batch statistics from the producing convolution's epilogue (utils/model_utils.py:10 after
+// models/unet.py:95): the separate statistics pass re-read the whole map (1.4 ms of an 82 ms step).  A warp's 32 output
+// rows x 32 channels of one chunk are staged as bf16 in a warp-private shared-memory tile (80-byte row pitch: conflict-free
+// 16-byte row stores and 2-byte column reads); lane L then sums channel L over the 32 rows (fp32) and adds to the warp's
+// running sums in shared memory, which go to the global fp64 accumulators once per CTA (one output-channel block) or once
+// per tile.  The values summed are exactly the bf16 values that BatchNorm later normalises.
+constexpr int EPI_BN_PITCH = 80;
+constexpr int EPI_BN_TILE = 32 * EPI_BN_PITCH;
+constexpr int EPI_BN_RUN = 2 * 256;                                  // floats per warp: [sum | sum of squares][BLOCK_N <= 256]
+constexpr int EPI_BN_BYTES = 4 * EPI_BN_TILE + 4 * EPI_BN_RUN * 4;   // four epilogue warps
+
+__device__ __forceinline__ void epi_bn_chunk(uint8_t* tile, float* run, int lane, int c, const uint32_t (&pk)[16], bool live) {
+  uint4* row = reinterpret_cast<uint4*>(tile + lane * EPI_BN_PITCH);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    row[i] = live ? make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]) : make_uint4(0u, 0u, 0u, 0u);
+  __syncwarp();
+  const unsigned short* col = reinterpret_cast<const unsigned short*>(tile) + lane;
+  float sm = 0.f, sq = 0.f;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const float x = __uint_as_float((uint32_t)col[r * (EPI_BN_PITCH / 2)] << 16);
+    sm += x;
+    sq = fmaf(x, x, sq);
+  }
+  __syncwarp();
+  run[c + lane] += sm;
+  run[256 + c + lane] += sq;
+}
+__device__ __forceinline__ void epi_bn_flush(float* run, int lane, double* acc, int n0, int Cout, int block_n) {
+  for (int c = lane; c < block_n; c += 32) {
+    if (n0 + c < Cout) {
+      atomicAdd(acc + n0 + c, (double)run[c]);
+      atomicAdd(acc + Cout + n0 + c, (double)run[256 + c]);
+    }
+    run[c] = 0.f;
+    run[256 + c] = 0.f;
+  }
+}
 // selects only; the caller tests code != NONE once per 32-column chunk
 __device__ __forceinline__ float epi_act(float v, int code, float alpha) {
   const float neg = code == DAFK_ACT_RELU ? 0.f : __fmul_rn(v, alpha);
@@ -59,7 +100,7 @@ struct ClsGeom {
 //   warp 1   MMA issuer   : accumulates tile t into TMEM buffer t&1 while the epilogue drains tile t-1
 //   warps 2-5 epilogue    : TMEM -> registers -> (+bias) -> global
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                     const __grid_constant__ CUtensorMap tmA1,
                                                                     const __grid_constant__ CUtensorMap tmB,
@@ -175,6 +216,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
     int tc = 0;
     const int ep_code = ep.code;
     const float ep_alpha = ep.alpha;
+    // BatchNorm statistics of the stored outputs (Epi::bn_acc): warp-private staging tile + running sums after the barriers
+    double* const bn_acc = BN ? ep.bn_acc : nullptr;     // BN = false: the statistics code is compiled out
+    uint8_t* const s_epi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot) + 31) & ~(uintptr_t)15);
+    uint8_t* const bn_tile = s_epi + q4 * EPI_BN_TILE;
+    float* const bn_run = reinterpret_cast<float*>(s_epi + 4 * EPI_BN_TILE) + q4 * EPI_BN_RUN;
+    if (bn_acc != nullptr) {
+      for (int i = lane; i < EPI_BN_RUN; i += 32) bn_run[i] = 0.f;
+      __syncwarp();
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
       const int cls = tile % cg.n;
       const int t2 = tile / cg.n;
@@ -199,6 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
         tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
         tmem_ld16(taddr + (uint32_t)c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
         tmem_ld_wait();
+        uint32_t pkb[BN ? 16 : 1];          // BN: the whole chunk packed, for the statistics tile
         if (live) {
           float f[32];
           const int cvalid = Cout - (n0 + c);            // channels of this chunk that exist (Cout % 8 == 0)
@@ -224,15 +275,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
               for (int i = 0; i < 4; ++i) {
                 __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * i], f[j + 2 * i + 1]);
                 pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                if (BN) pkb[BN ? j / 2 + i : 0] = pk[i];
               }
               if (j < cvalid) *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
         }
+        if constexpr (BN) {
+          if (bn_acc != nullptr) epi_bn_chunk(bn_tile, bn_run, lane, c, pkb, live);
+        }
       }
+      if (bn_acc != nullptr && n_blocks > 1) epi_bn_flush(bn_run, lane, bn_acc, n0, Cout, BLOCK_N);
       tc_fence_before();
       mbar_arrive(tempty_bar + b);
     }
+    if (bn_acc != nullptr && n_blocks == 1) epi_bn_flush(bn_run, lane, bn_acc, 0, Cout, BLOCK_N);
   }
   tc_fence_before();
   __syncthreads();
@@ -271,7 +328,7 @@ struct HaloGeom {
 constexpr int HALO_THREADS = 224;
 constexpr int HALO_MMA2_WARP = 6;
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool BN>
 __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                      const __grid_constant__ CUtensorMap tmA1,
                                                                      const __grid_constant__ CUtensorMap tmB,
@@ -422,6 +479,15 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
     int tc = 0;
     const int ep_code = ep.code;
     const float ep_alpha = ep.alpha;
+    // BatchNorm statistics of the stored outputs (Epi::bn_acc): warp-private staging tile + running sums after the barriers
+    double* const bn_acc = BN ? ep.bn_acc : nullptr;     // BN = false: the statistics code is compiled out
+    uint8_t* const s_epi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot) + 31) & ~(uintptr_t)15);
+    uint8_t* const bn_tile = s_epi + q4 * EPI_BN_TILE;
+    float* const bn_run = reinterpret_cast<float*>(s_epi + 4 * EPI_BN_TILE) + q4 * EPI_BN_RUN;
+    if (bn_acc != nullptr) {
+      for (int i = lane; i < EPI_BN_RUN; i += 32) bn_run[i] = 0.f;
+      __syncwarp();
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
       const int nb = tile % n_blocks;
       int mt = tile / n_blocks;
@@ -447,6 +513,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
           tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
           tmem_ld16(taddr + (uint32_t)c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
           tmem_ld_wait();
+          uint32_t pkb[BN ? 16 : 1];          // BN: the whole chunk packed, for the statistics tile
           if (live) {
             float f[32];
             const int cvalid = Cout - (n0 + c);            // channels of this chunk that exist (Cout % 8 == 0)
@@ -472,16 +539,22 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
                 for (int i = 0; i < 4; ++i) {
                   __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * i], f[j + 2 * i + 1]);
                   pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                  if (BN) pkb[BN ? j / 2 + i : 0] = pk[i];
                 }
                 if (j < cvalid) *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
             }
           }
+          if constexpr (BN) {
+            if (bn_acc != nullptr) epi_bn_chunk(bn_tile, bn_run, lane, c, pkb, live);
+          }
         }
       }
+      if (bn_acc != nullptr && n_blocks > 1) epi_bn_flush(bn_run, lane, bn_acc, n0, Cout, BLOCK_N);
       tc_fence_before();
       mbar_arrive(tempty_bar + buf);
     }
+    if (bn_acc != nullptr && n_blocks == 1) epi_bn_flush(bn_run, lane, bn_acc, 0, Cout, BLOCK_N);
   }
   tc_fence_before();
   __syncthreads();
@@ -504,7 +577,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
 //   leader only warps 1 and 6: MMA issuers (even / odd accumulators); every tcgen05.commit is multicast to both CTAs
 // "TMEM empty" lives on the leader: 2 x 128 epilogue threads arrive there (the peer's through shared::cluster).
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, bool BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, 1)
 conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                      const __grid_constant__ CUtensorMap tmBh, const float* __restrict__ bias, void* __restrict__ y, int y_dt,
@@ -627,6 +700,15 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
     int tc = 0;
     const int ep_code = ep.code;
     const float ep_alpha = ep.alpha;
+    // BatchNorm statistics of the stored outputs (Epi::bn_acc): warp-private staging tile + running sums after the barriers
+    double* const bn_acc = BN ? ep.bn_acc : nullptr;     // BN = false: the statistics code is compiled out
+    uint8_t* const s_epi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot) + 31) & ~(uintptr_t)15);
+    uint8_t* const bn_tile = s_epi + q4 * EPI_BN_TILE;
+    float* const bn_run = reinterpret_cast<float*>(s_epi + 4 * EPI_BN_TILE) + q4 * EPI_BN_RUN;
+    if (bn_acc != nullptr) {
+      for (int i = lane; i < EPI_BN_RUN; i += 32) bn_run[i] = 0.f;
+      __syncwarp();
+    }
     for (int pt = cluster_id; pt < pair_tiles; pt += n_clusters, ++tc) {
       int mt = 2 * pt + (int)rank;
       const bool tile_live = mt < total_tiles;
@@ -651,6 +733,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
           tmem_ld16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
           tmem_ld16(taddr + (uint32_t)c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
           tmem_ld_wait();
+          uint32_t pkb[BN ? 16 : 1];          // BN: the whole chunk packed, for the statistics tile
           if (live) {
             float f[32];
             const int cvalid = Cout - c;
@@ -676,16 +759,21 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
                 for (int i = 0; i < 4; ++i) {
                   __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * i], f[j + 2 * i + 1]);
                   pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                  if (BN) pkb[BN ? j / 2 + i : 0] = pk[i];
                 }
                 if (j < cvalid) *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
             }
+          }
+          if constexpr (BN) {
+            if (bn_acc != nullptr) epi_bn_chunk(bn_tile, bn_run, lane, c, pkb, live);
           }
         }
       }
       tc_fence_before();
       mbar_arrive_leader(tempty_bar + buf);
     }
+    if (bn_acc != nullptr) epi_bn_flush(bn_run, lane, bn_acc, 0, Cout, BLOCK_N);     // one output-channel block per layer here
   }
   // the leader's MMAs read the peer's shared memory and write its TMEM: nobody leaves before both CTAs are done
   tc_fence_before();
@@ -988,11 +1076,13 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
                       int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int stride, int pad,
                       const TileGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
                       long long y_sx, Epi ep, cudaStream_t s, const ClsGeom& cg = ClsGeom{1, 0, 0, 0, 0, 0}) {
-  constexpr int smem = STAGES * (A_BYTES + BLOCK_N * KBLK * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (A_BYTES + BLOCK_N * KBLK * 2) + 1024 + 256 + EPI_BN_BYTES;
   static_assert(smem > 116 * 1024 && smem <= 227 * 1024, "one persistent CTA per SM");
   static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_fwd_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_fwd_kernel<BLOCK_N, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_fwd_kernel<BLOCK_N, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_fwd) failed: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -1000,9 +1090,14 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
   int64_t tiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_n * n_blocks * cg.n;
   DAFK_REQUIRE(tiles < (1LL << 31), DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd: too many tiles");
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
-  conv_tc_fwd_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1,
-                                                                    KH, KW, stride, pad, g, n_blocks, w_rows_per_tap,
-                                                                    w_row_off, y_sn, y_sy, y_sx, (int)tiles, ep, cg);
+  if (ep.bn_acc != nullptr)
+    conv_tc_fwd_kernel<BLOCK_N, STAGES, true><<<grid, TC_THREADS, smem, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1,
+                                                                            KH, KW, stride, pad, g, n_blocks, w_rows_per_tap,
+                                                                            w_row_off, y_sn, y_sy, y_sx, (int)tiles, ep, cg);
+  else
+    conv_tc_fwd_kernel<BLOCK_N, STAGES, false><<<grid, TC_THREADS, smem, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1,
+                                                                             KH, KW, stride, pad, g, n_blocks, w_rows_per_tap,
+                                                                             w_row_off, y_sn, y_sy, y_sx, (int)tiles, ep, cg);
   return check_launch("dafk_conv_tc_fwd");
 }
 
@@ -1117,10 +1212,12 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
                        const HaloGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
                        long long y_sx, Epi ep, cudaStream_t s) {
   const int ncb_all = (C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK;
-  const int smem = g.SA * g.a_bytes + (g.w_resident ? ncb_all * KH * KW : g.SB) * BLOCK_N * KBLK * 2 + 1024 + 512;
+  const int smem = g.SA * g.a_bytes + (g.w_resident ? ncb_all * KH * KW : g.SB) * BLOCK_N * KBLK * 2 + 1024 + 512 + EPI_BN_BYTES;
   static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_halo_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_halo) failed: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -1129,9 +1226,14 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   DAFK_REQUIRE(tiles < (1LL << 31), DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd: too many tiles");
   const int smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;      // one persistent CTA per SM
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
-  conv_tc_halo_kernel<BLOCK_N><<<grid, HALO_THREADS, smem_req, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW,
-                                                                 pad, g, n_blocks, w_rows_per_tap, w_row_off, y_sn, y_sy,
-                                                                 y_sx, (int)tiles, ep);
+  if (ep.bn_acc != nullptr)
+    conv_tc_halo_kernel<BLOCK_N, true><<<grid, HALO_THREADS, smem_req, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH,
+                                                                         KW, pad, g, n_blocks, w_rows_per_tap, w_row_off, y_sn,
+                                                                         y_sy, y_sx, (int)tiles, ep);
+  else
+    conv_tc_halo_kernel<BLOCK_N, false><<<grid, HALO_THREADS, smem_req, s>>>(a0, a1, b, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH,
+                                                                          KW, pad, g, n_blocks, w_rows_per_tap, w_row_off, y_sn,
+                                                                          y_sy, y_sx, (int)tiles, ep);
   return check_launch("dafk_conv_tc_fwd(halo)");
 }
 
@@ -1141,11 +1243,13 @@ static int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
                         const HaloGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
                         long long y_sx, Epi ep, cudaStream_t s) {
   const int ncb_all = (C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK;
-  const int smem = g.SA * g.a_bytes + ncb_all * KH * KW * (BLOCK_N / 2) * KBLK * 2 + 1024 + 512;
+  const int smem = g.SA * g.a_bytes + ncb_all * KH * KW * (BLOCK_N / 2) * KBLK * 2 + 1024 + 512 + EPI_BN_BYTES;
   DAFK_REQUIRE(smem <= 227 * 1024, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd(halo2): %d bytes of shared memory", smem);
   static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo2_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_halo2_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "cudaFuncSetAttribute(conv_tc_halo2) failed: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -1154,9 +1258,14 @@ static int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
   const int smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;      // one persistent CTA per SM
   const int64_t pairs = (tiles + 1) / 2;
   const int clusters = (int)(pairs < kNumSMs / 2 ? pairs : kNumSMs / 2);
-  conv_tc_halo2_kernel<BLOCK_N><<<dim3(2 * clusters), HALO_THREADS, smem_req, s>>>(
-      a0, a1, bh, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, g, w_rows_per_tap, w_row_off, y_sn, y_sy, y_sx,
-      (int)tiles, ep);
+  if (ep.bn_acc != nullptr)
+    conv_tc_halo2_kernel<BLOCK_N, true><<<dim3(2 * clusters), HALO_THREADS, smem_req, s>>>(
+        a0, a1, bh, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, g, w_rows_per_tap, w_row_off, y_sn, y_sy, y_sx,
+        (int)tiles, ep);
+  else
+    conv_tc_halo2_kernel<BLOCK_N, false><<<dim3(2 * clusters), HALO_THREADS, smem_req, s>>>(
+        a0, a1, bh, bias, y, y_dt, N, Ho, Wo, Cout, C0, C1, KH, KW, pad, g, w_rows_per_tap, w_row_off, y_sn, y_sy, y_sx,
+        (int)tiles, ep);
   return check_launch("dafk_conv_tc_fwd(halo2)");
 }
 
@@ -1191,7 +1300,7 @@ extern "C" {
 static int conv_tc_fwd_impl(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,
                             int w_row_off, const float* bias, void* y, int y_dt, int N, int H, int W, int Cout, int KH,
                             int KW, int stride, int pad, int Ho, int Wo, int64_t y_sn, int64_t y_sy, int64_t y_sx,
-                            int act, float alpha, void* stream) {
+                            int act, float alpha, void* stream, double* bn_acc = nullptr) {
   DAFK_REQUIRE(N > 0 && H > 0 && W > 0 && C0 > 0 && C1 >= 0 && Cout > 0 && KH > 0 && KW > 0 && Ho > 0 && Wo > 0,
                DAFK_ERR_BAD_ARG, "dafk_conv_tc_fwd: bad shape");
   DAFK_REQUIRE(stride == 1 || stride == 2, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd: stride must be 1 or 2");
@@ -1209,7 +1318,9 @@ static int conv_tc_fwd_impl(const void* x0, int C0, const void* x1, int C1, cons
                "dafk_conv_tc_fwd: output strides must be multiples of 8 elements");
   TileGeom g = pick_geom(N, Ho, Wo, stride);
   CUtensorMap a0, a1, b;
-  const Epi ep{act, alpha};
+  const Epi ep{act, alpha, bn_acc};
+  DAFK_REQUIRE(bn_acc == nullptr || y_dt == DAFK_BF16, DAFK_ERR_UNSUPPORTED,
+               "dafk_conv_tc_fwd_bn: batch statistics are taken from the stored bf16 outputs (y must be bf16)");
   int rc = make_act_map(&a0, x0, N, H, W, C0, g, stride);
   if (rc) return rc;
   if (C1 > 0) { rc = make_act_map(&a1, x1, N, H, W, C1, g, stride); if (rc) return rc; } else a1 = a0;
@@ -1318,6 +1429,15 @@ int dafk_conv_tc_fwd_act(const void* x0, int C0, const void* x1, int C1, const v
                           Ho, Wo, y_sn, y_sy, y_sx, act, alpha, stream);
 }
 
+int dafk_conv_tc_fwd_bn(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap, int w_row_off,
+                        const float* bias, void* y_bf16, double* bn_acc, int N, int H, int W, int Cout, int KH, int KW,
+                        int stride, int pad, void* stream) {
+  DAFK_REQUIRE(bn_acc != nullptr, DAFK_ERR_BAD_ARG, "dafk_conv_tc_fwd_bn: null accumulator");
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  return conv_tc_fwd_impl(x0, C0, x1, C1, wp, w_rows_per_tap, w_row_off, bias, y_bf16, DAFK_BF16, N, H, W, Cout, KH, KW, stride,
+                          pad, Ho, Wo, (int64_t)Ho * Wo * Cout, (int64_t)Wo * Cout, Cout, DAFK_ACT_NONE, 0.f, stream, bn_acc);
+}
+
 int dafk_conv_tc_dgrad_s2(const void* dy, int Cout, const void* wp4, int w_rows_per_tap, int w_row_off, void* dx,
                           int dx_dt, int N, int Ho, int Wo, int Cin, int KH, int KW, int H, int W, void* stream) {
   DAFK_REQUIRE(N > 0 && Ho > 0 && Wo > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, DAFK_ERR_BAD_ARG,
@@ -1348,12 +1468,12 @@ int dafk_conv_tc_dgrad_s2(const void* dy, int Cout, const void* wp4, int w_rows_
     rc = make_w_map(&b, wp4, 4 * taps * w_rows_per_tap, Kpad, 128);
     if (rc) return rc;
     return launch_fwd<128, 6>(a0, a0, b, nullptr, dx, dx_dt, N, Hc, Wc, Cin, Cout, 0, kh, kw, 1, kh - 1, g, w_rows_per_tap,
-                              w_row_off, y_sn, y_sy, y_sx, Epi{DAFK_ACT_NONE, 0.f}, s, cg);
+                              w_row_off, y_sn, y_sy, y_sx, Epi{DAFK_ACT_NONE, 0.f, nullptr}, s, cg);
   }
   rc = make_w_map(&b, wp4, 4 * taps * w_rows_per_tap, Kpad, 64);
   if (rc) return rc;
   return launch_fwd<64, 8>(a0, a0, b, nullptr, dx, dx_dt, N, Hc, Wc, Cin, Cout, 0, kh, kw, 1, kh - 1, g, w_rows_per_tap,
-                           w_row_off, y_sn, y_sy, y_sx, Epi{DAFK_ACT_NONE, 0.f}, s, cg);
+                           w_row_off, y_sn, y_sy, y_sx, Epi{DAFK_ACT_NONE, 0.f, nullptr}, s, cg);
 }
 
 int dafk_conv3x3_tc_fwd(const void* x0, int C0, const void* x1, int C1, const void* wp, int w_rows_per_tap,

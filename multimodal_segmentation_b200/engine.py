@@ -57,7 +57,7 @@ class Var:
     Gradients: the first contribution is kept as it arrives; a second one is held back in ``_grad2`` instead of being
     added at once, so that a consumer that applies an activation backward next can sum the two inside that pass
     (``take_grad_pair``); reading ``grad`` materialises the sum."""
-    __slots__ = ("data", "_grad", "_grad2", "requires_grad", "grad_dtype", "grad_owned", "bias_sink")
+    __slots__ = ("data", "_grad", "_grad2", "requires_grad", "grad_dtype", "grad_owned", "bias_sink", "bn_acc")
 
     def __init__(self, data, requires_grad=False, grad_dtype=None):
         self.data = data
@@ -67,6 +67,7 @@ class Var:
         self.grad_dtype = grad_dtype if grad_dtype is not None else data.dtype
         self.grad_owned = False
         self.bias_sink = None
+        self.bn_acc = None       # fp64 [2C] sum / sum of squares of `data`, when the producing convolution took them
 
     @property
     def grad(self):
@@ -371,7 +372,7 @@ class Conv2D:
         return ops.conv_tc_dgrad_s2(g, wp_d, (N, H, W, c), c, k, k, out_dtype, row_off=off,
                                     rows_per_tap=(self.cin + 63) // 64 * 64)
 
-    def __call__(self, ctx, x, act=None, alpha=0.0, out_dtype=None):
+    def __call__(self, ctx, x, act=None, alpha=0.0, out_dtype=None, bn_stats=False):
         """out_dtype: storage of the convolution output.  The layers that feed a BatchNorm ask for the feature dtype
         (bf16 on the tensor-core path): halves the bytes of the largest tensors of the step; the batch statistics are
         then taken from exactly the values that get normalised."""
@@ -379,7 +380,7 @@ class Conv2D:
         assert sum(s.shape[-1] for s in srcs) == self.cin, (self.name, [tuple(s.shape) for s in srcs], self.cin)
         od = torch.float32 if (out_dtype is None or not USE_TC or not RAW_BF16) else out_dtype
         if self.tc_eligible(srcs) and len(srcs) <= 2:
-            return self._call_tc(ctx, srcs, act, alpha, od)
+            return self._call_tc(ctx, srcs, act, alpha, od, bn_stats)
         return self._call_generic(ctx, srcs, act, alpha, od)
 
     def packed_nc(self):
@@ -653,7 +654,7 @@ class Conv2D:
         return y
 
     # ---- tcgen05 path (bf16 operands, fp32 accumulate in TMEM)
-    def _call_tc(self, ctx, srcs, act, alpha, od=torch.float32):
+    def _call_tc(self, ctx, srcs, act, alpha, od=torch.float32, bn_stats=False):
         bsrcs = [s if s.data.dtype == torch.bfloat16 else _cast_var(ctx, s, torch.bfloat16) for s in srcs]
         wp_f, wp_d = self.packed()
         bias = self.bias.data if self.bias is not None else None
@@ -661,12 +662,22 @@ class Conv2D:
         x1 = bsrcs[1] if len(bsrcs) > 1 else None
         code = ACT[act]
         fuse = code in (ACT_RELU, ACT_LRELU)      # the activation runs in the epilogue: y = act(conv + bias), stored once
-        raw = ops.conv_tc_fwd(x0.data, None if x1 is None else x1.data, wp_f, bias, self.cout, self.k, self.k,
-                              self.stride, self.pad, od if (fuse or code == ACT_NONE) else torch.float32,
-                              act=code if fuse else ACT_NONE, alpha=alpha)
+        acc = None
+        if bn_stats and code == ACT_NONE and od == torch.bfloat16 and self.cout >= 128:
+            # a training-phase BatchNorm follows: its batch statistics come out of this kernel's epilogue.  Measured on
+            # B200 (B = 32): the statistics add 6 - 12 us to layers with >= 128 outputs and replace a 19 - 27 us pass;
+            # on the 64-channel 224^2 layers the epilogue warps are the critical path (143 -> 201 us against a 38 us
+            # statistics pass), so those keep the separate pass
+            raw, acc = ops.conv_tc_fwd_bn(x0.data, None if x1 is None else x1.data, wp_f, bias, self.cout, self.k, self.k,
+                                          self.stride, self.pad)
+        else:
+            raw = ops.conv_tc_fwd(x0.data, None if x1 is None else x1.data, wp_f, bias, self.cout, self.k, self.k,
+                                  self.stride, self.pad, od if (fuse or code == ACT_NONE) else torch.float32,
+                                  act=code if fuse else ACT_NONE, alpha=alpha)
         # an fp32-stored activated output (last discriminator layer, feeds a Dense) takes its gradient in fp32 and
         # converts while the activation backward runs; everything else hands bf16 to the gradient kernels
         y = Var(raw, grad_dtype=torch.float32 if (fuse and raw.dtype == torch.float32) else torch.bfloat16)
+        y.bn_acc = acc
         rec = ctx.rec(*bsrcs, *self.params())
         if rec:
             y.requires_grad = True
@@ -747,7 +758,13 @@ class BatchNorm:
     def __call__(self, ctx, x, act=None, out_dtype=torch.float32):
         code = ACT[act]
         if ctx.training:
-            mean, rstd = ops.bn_stats_finalize(x.data, self.EPS, self.MOMENTUM, self.moving_mean.data, self.moving_var.data)
+            if x.bn_acc is not None:       # the producing convolution already summed its stored outputs
+                mean, rstd = ops.bn_finalize_acc(x.bn_acc, x.data.numel() // self.c, self.EPS, self.MOMENTUM,
+                                                 self.moving_mean.data, self.moving_var.data)
+                x.bn_acc = None
+            else:
+                mean, rstd = ops.bn_stats_finalize(x.data, self.EPS, self.MOMENTUM, self.moving_mean.data,
+                                                   self.moving_var.data)
             self.moving_mean.arena.version += 1        # folded inference copies (Conv2D.forward_folded) are stale now
         else:
             mean, rstd = self.moving_mean.data, ops.bn_rstd_from_var(self.moving_var.data, self.EPS)
@@ -865,7 +882,7 @@ def conv_bn(ctx, conv, bn, x, act=None, out_dtype=torch.float32):
             and conv.stride == 1 and not conv.tc_eligible(srcs)
             and ops.nc_supported(conv.cin, conv.cout, conv.k, conv.k, srcs[0].shape[2], conv.pad, 0)):
         return conv.forward_folded(srcs, bn, code, out_dtype, narrow=True)      # first layers: 1 -> 64, 8 -> 64
-    return bn(ctx, conv(ctx, x, out_dtype=feat_dtype()), act, out_dtype)
+    return bn(ctx, conv(ctx, x, out_dtype=feat_dtype(), bn_stats=ctx.training and ops.FUSE_BN_STATS), act, out_dtype)
 
 
 # --------------------------------------------------------------------------------------------

@@ -530,6 +530,35 @@ def conv_tc_fwd(x0, x1, wp, bias, Cout, KH, KW, stride, pad, out_dtype=torch.flo
     return out
 
 
+FUSE_BN_STATS = os.environ.get("DAFK_FUSE_BN_STATS", "1") != "0"     # batch statistics from the convolution's epilogue
+
+
+def conv_tc_fwd_bn(x0, x1, wp, bias, Cout, KH, KW, stride, pad):
+    """tcgen05 convolution that stores y in bf16 and accumulates sum / sum of squares per channel of the stored values
+    into a fresh fp64 accumulator [2*Cout] (for bn_finalize): returns (y, acc)"""
+    _chk(x0, x1, wp, bias)
+    N, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[-1]
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x0.device)
+    acc = zero_(torch.empty(2 * Cout, dtype=torch.float64, device=x0.device))
+    fl = 2.0 * N * Ho * Wo * Cout * KH * KW * (C0 + C1)
+    nb = 2.0 * x0.numel() + (0 if x1 is None else 2.0 * x1.numel()) + 2.0 * y.numel()
+    instrument.timed("conv_tc_fwd+dgrad (tcgen05)", fl, nb,
+                     lambda: call("conv_tc_fwd_bn", x0, C0, x1, C1, wp, wp.shape[1], 0, bias, y, acc, N, H, W, Cout, KH, KW,
+                                  stride, pad, _S()),
+                     tag=(N, H, W, C0 + C1, Cout, KH, stride, "bfloat16+bn", Ho))
+    return y, acc
+
+
+def bn_finalize_acc(acc, M, eps, momentum, moving_mean=None, moving_var=None):
+    """mean / rstd (and the moving-statistics update) from per-channel fp64 sums [2*C] over M values per channel"""
+    C = acc.numel() // 2
+    mean, rstd = f32(C), f32(C)
+    call("bn_finalize", acc, M, C, float(eps), float(momentum), mean, rstd, moving_mean, moving_var, _S())
+    return mean, rstd
+
+
 WGRAD_HALO = os.environ.get("DAFK_WGRAD_HALO", "auto")     # "0" / "1" force the choice (tests, benchmarks)
 
 

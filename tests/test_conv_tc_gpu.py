@@ -251,3 +251,87 @@ def test_conv_tc_stride2_dgrad_all_parity_classes_in_one_launch(ops, case):
         dxw = ops.conv_tc_dgrad_s2(gpu(dy, torch.bfloat16), wp4, (N, H, W, 64), 64, k, k, torch.float32, row_off=64,
                                    rows_per_tap=128)
         assert rel_l2(cpu(dxw), xt.grad.numpy()[..., 64:]) < 1e-4
+
+
+BN_CASES = [
+    # N, H, W, C0, C1, Cout, k, stride     -- every forward kernel: CTA-pair haloed (64 / 128 outputs, resident weights),
+    (2, 56, 56, 64, 0, 64, 3, 1),          #    single-CTA haloed, tap-by-tap with one and with several output-channel blocks
+    (3, 24, 40, 64, 0, 64, 3, 1),          # partial tiles: dead rows must contribute nothing
+    (2, 28, 28, 128, 0, 128, 3, 1),
+    (2, 28, 28, 64, 64, 64, 3, 1),         # two sources
+    (2, 20, 20, 256, 0, 256, 3, 1),
+    (3, 14, 14, 512, 0, 1024, 3, 1),       # four 256-wide output-channel blocks: per-tile flush of the running sums
+    (2, 13, 15, 64, 0, 128, 3, 1),
+    (1, 9, 9, 1024, 0, 512, 3, 1),
+    (5, 64, 64, 64, 0, 64, 3, 1),          # many tiles per CTA: running sums persist across tiles
+    (2, 21, 23, 64, 0, 128, 4, 2),         # strided layer (tap-by-tap kernel)
+    (2, 16, 16, 64, 0, 96, 3, 1),          # Cout not a multiple of the chunk width
+]
+
+
+@pytest.mark.parametrize("case", BN_CASES)
+def test_conv_tc_forward_with_batchnorm_statistics(ops, case, monkeypatch):
+    """dafk_conv_tc_fwd_bn: the stored bf16 output is bit-identical to the plain kernel's, and the fp64 accumulators hold
+    the per-channel sum / sum of squares of exactly those stored values (what a BatchNormalization after the convolution
+    normalises, utils/model_utils.py:10); dafk_bn_finalize on them equals dafk_bn_stats_fused on the map."""
+    N, H, W, C0, C1, Cout, k, stride = case
+    r = np.random.RandomState(sum(case))
+    Cin = C0 + C1
+    pad = 1 if (k == 3 and stride == 1) else 0
+    x = bf16_round(r.normal(size=(N, H, W, Cin)).astype(np.float32))
+    w = bf16_round((r.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(np.float32))
+    b = r.normal(size=Cout).astype(np.float32)
+    wp = ops.pack_conv(gpu(w), 0)
+    x0 = gpu(x[..., :C0], torch.bfloat16)
+    x1 = gpu(x[..., C0:], torch.bfloat16) if C1 else None
+    for halo2 in ("1", "0"):                      # CTA-pair and single-CTA haloed kernels where both apply
+        monkeypatch.setenv("DAFK_CONV_HALO2", halo2)
+        y_ref = ops.conv_tc_fwd(x0, x1, wp, gpu(b), Cout, k, k, stride, pad, torch.bfloat16)
+        y, acc = ops.conv_tc_fwd_bn(x0, x1, wp, gpu(b), Cout, k, k, stride, pad)
+        torch.cuda.synchronize()
+        assert torch.equal(y, y_ref)
+        yd = y.double().reshape(-1, Cout)
+        want = torch.cat([yd.sum(0), (yd * yd).sum(0)])
+        got = acc.double()
+        assert torch.allclose(got, want, rtol=2e-6, atol=1e-4), (got - want).abs().max().item()
+    M = y.numel() // Cout
+    mean, rstd = ops.bn_finalize_acc(acc, M, 1e-3, 0.99)
+    if Cout & (Cout - 1) == 0:                    # the stand-alone statistics kernels take power-of-two channel counts
+        mean2, rstd2 = ops.bn_stats_finalize(y, 1e-3, 0.99)
+        assert rel_l2(cpu(mean), cpu(mean2)) < 1e-5 and rel_l2(cpu(rstd), cpu(rstd2)) < 1e-5
+    yd = y.double().reshape(-1, Cout)
+    assert rel_l2(cpu(mean), yd.mean(0).cpu().numpy()) < 1e-5
+    assert rel_l2(cpu(rstd), (1.0 / torch.sqrt(yd.var(0, unbiased=False) + 1e-3)).cpu().numpy()) < 1e-5
+
+
+def test_conv_bn_block_uses_the_fused_statistics(ops, monkeypatch):
+    """engine.conv_bn in the training phase: same outputs, moving statistics and gradients with the statistics taken in
+    the convolution's epilogue (default) as with the separate statistics pass (DAFK_FUSE_BN_STATS=0), one launch fewer"""
+    from multimodal_segmentation_b200 import engine as E
+
+    def run(fuse):
+        monkeypatch.setattr(ops, "FUSE_BN_STATS", fuse)
+        E.USE_TC = True
+        rs = np.random.RandomState(3)
+        arena, state = E.Arena(True), E.Arena(False)
+        conv = E.Conv2D(arena, rs, "c", 64, 128, 3, 1, "same")       # >= 128 outputs: the layers that use the fused statistics
+        bn = E.BatchNorm(arena, state, "n", 128)
+        arena.to_device()
+        state.to_device()
+        x = E.Var(gpu(bf16_round(rs.normal(size=(2, 24, 24, 64)).astype(np.float32)), torch.bfloat16), True)
+        tape = E.Tape()
+        ctx = E.Ctx(tape, True)
+        n0 = ops._lib.launch_count()
+        y = E.conv_bn(ctx, conv, bn, x, "relu", torch.bfloat16)
+        launches = ops._lib.launch_count() - n0
+        y.grad = gpu(bf16_round(rs.normal(size=tuple(y.shape)).astype(np.float32)), torch.bfloat16)
+        tape.backward()
+        torch.cuda.synchronize()
+        return (launches, cpu(y.data), cpu(bn.moving_mean.data), cpu(bn.moving_var.data), cpu(x.grad), cpu(conv.kernel.grad),
+                cpu(bn.gamma.grad))
+
+    a, b = run(True), run(False)
+    assert a[0] < b[0] + 2            # (memset + finalize) replace the statistics kernel; never more than one extra launch
+    assert np.array_equal(a[1], b[1]) or rel_l2(a[1], b[1]) < 1e-2      # bf16 outputs: identical up to last-bit statistics
+    for i in range(2, 7):
+        assert rel_l2(a[i], b[i]) < 2e-3, (i, rel_l2(a[i], b[i]))
