@@ -349,15 +349,18 @@ def run_b200(args):
     if kern:
         dom = max(kern.values(), key=lambda k: k["ms"])
         ach = dom["flops"] / (dom["ms"] / 1000.0) / 1e12 if dom["ms"] > 0 else 0.0
-        # DRAM traffic cannot be read without a profiler: it comes from the committed `ncu --set full` capture of
-        # representative launches of this family, stored TOGETHER with the algorithmic bytes of those same launches
-        traffic, traffic_detail = None, {"note": "no ncu capture found under profiles/"}
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "conv_tc_traffic.json")))
-            traffic = tj["dram_bytes_per_launch"]
-            traffic_detail = {k: tj[k] for k in tj if k != "dram_bytes_per_launch"}
-        except Exception:
-            pass
+        # DRAM traffic cannot be read without a profiler: it comes from the committed ncu launch list of THIS workload
+        # (scripts/ncu_traffic.py: dram__bytes_read.sum + dram__bytes_write.sum over EVERY launch of the family in
+        # host-launched train_batch calls, mean per launch) -- the same population of launches as
+        # algorithmic_bytes_per_launch_step_mean, so the two are comparable; other workloads report null
+        traffic, traffic_detail = None, {"note": "no ncu capture of this workload under profiles/"}
+        if args.workload == "dafnet_film" and args.batch == 32 and args.size == 224 and args.l_mix == 1.0 and E.USE_TC:
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "conv_tc_traffic.json")))
+                traffic = tj["dram_bytes_per_launch"]
+                traffic_detail = {k: tj[k] for k in tj if k != "dram_bytes_per_launch"}
+            except Exception:
+                pass
         roof = {"bound": "tensor", "kernel": dom["name"], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": ach / peak_tf, "frac_of_burst_peak": ach / peak_burst, "peak_burst": peak_burst,
                 "traffic": traffic, "traffic_detail": traffic_detail,
