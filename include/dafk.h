@@ -532,6 +532,9 @@ int dafk_pair_combine(const float* w, const float* L, float weight, float* loss,
  * rotation_range=20 -> scipy.ndimage.affine_transform(order=1, mode='nearest') about the image centre).
  * x, y: f32 [B,H,W,C] (C in 1..5 or 8), distinct buffers; theta[B]: rotation angle per sample in radians. */
 int dafk_rotate_bilinear(const float* x, const float* theta, float* y, int B, int H, int W, int C, void* stream);
+/* Executor.add_residual (model_executors/base_executor.py:83-87) applied to the AUGMENTED batch as the reference does
+ * (dafnet_executor.py:493-494): m[p, C-1] = 0 if any m[p, c < C-1] == 1 else 1, in place; m: f32 [pixels, C]. */
+int dafk_mask_residual(float* m, int64_t pixels, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,19 @@ __global__ void __launch_bounds__(256) rotate_bilinear_kernel(const float* __res
   }
 }
 
+// Executor.add_residual (model_executors/base_executor.py:83-87) on a staged batch: the reference builds the background
+// channel AFTER the augmentation (dafnet_executor.py:493-494), so it is 1 wherever no rotated mask channel is exactly 1.
+// m: [pixels, C], channel C-1 is rewritten from channels 0..C-2.
+__global__ void __launch_bounds__(256) mask_residual_kernel(float* __restrict__ m, int64_t pixels, int C) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += (int64_t)gridDim.x * blockDim.x) {
+    float* q = m + p * C;
+    float r = 1.f;
+    for (int c = 0; c < C - 1; ++c)
+      if (q[c] == 1.f) r = 0.f;
+    q[C - 1] = r;
+  }
+}
+
 }  // namespace dafk
 
 using namespace dafk;
@@ -65,6 +78,14 @@ int dafk_rotate_bilinear(const float* x, const float* theta, float* y, int B, in
     default: set_error("dafk_rotate_bilinear: C must be 1..5 or 8 (got %d)", C); return DAFK_ERR_UNSUPPORTED;
   }
   return check_launch("dafk_rotate_bilinear");
+}
+
+int dafk_mask_residual(float* m, int64_t pixels, int C, void* stream) {
+  DAFK_REQUIRE(pixels >= 0 && C >= 2, DAFK_ERR_BAD_ARG, "dafk_mask_residual: bad shape");
+  if (pixels == 0) return DAFK_OK;
+  DAFK_REQUIRE(m, DAFK_ERR_BAD_ARG, "dafk_mask_residual: null pointer");
+  mask_residual_kernel<<<bw_grid(pixels, 256), 256, 0, as_stream(stream)>>>(m, pixels, C);
+  return check_launch("dafk_mask_residual");
 }
 
 }  // extern "C"

@@ -71,8 +71,11 @@ class BatchFlow(object):
 class FlowGroup(object):
     """zip of aligned BatchFlows (same seed -> same order), yields a tensor or a tuple of tensors"""
 
-    def __init__(self, flows):
+    def __init__(self, flows, residual_items=()):
         self.flows = flows
+        # positions of the mask arrays whose last channel is the add_residual background: the reference builds it AFTER
+        # the augmentation (dafnet_executor.py:493-494), so the stager rebuilds it once the batch has been rotated
+        self.residual_items = tuple(residual_items)
 
     def __iter__(self):
         return self
@@ -110,21 +113,23 @@ class Executor(object):
     def train(self):
         pass
 
-    def get_data_generator(self, train_images=None, train_labels=None):
+    def get_data_generator(self, train_images=None, train_labels=None, labels_have_residual=False):
         """base_executor.py:37-78: zip of one flow per array, all seeded with conf.seed so that the image and
         label streams stay aligned"""
-        gens = []
-        for arrs in (train_images, train_labels):
+        gens, residual = [], []
+        for is_label, arrs in ((False, train_images), (True, train_labels)):
             if arrs is None:
                 continue
             if type(arrs) != list:
                 arrs = [arrs]
             for a in arrs:
+                if labels_have_residual and is_label:
+                    residual.append(len(gens))
                 gens.append(BatchFlow(a, self.conf.batch_size, self.conf.seed,
                                       self.get_datagen_params()["rotation_range"] if getattr(self.conf, "augment", True) else 0.0))
         if len(gens) == 0:
             raise Exception("No data to iterate.")
-        return FlowGroup(gens)
+        return FlowGroup(gens, residual)
 
     def validate(self, epoch_loss):
         pass

@@ -131,9 +131,11 @@ class DAFNetExecutor(Executor):
         self._pair_up(self.data)
         self.data_len = self.data.size()
         nm = self.loader.num_masks
-        # add_residual (dafnet_executor.py:493-494) applied once when the labelled set is staged
+        # add_residual (dafnet_executor.py:493-494): the channel is allocated here; with augmentation the stager rebuilds
+        # it from the ROTATED mask channels, as the reference does (the background is 1 wherever no channel is exactly 1)
         masks = [self.add_residual(self.data.get_masks_modi(i)[..., 0:nm]) for i in range(2)]
-        return self.get_data_generator(train_images=[self.data.get_images_modi(i) for i in range(2)], train_labels=masks)
+        return self.get_data_generator(train_images=[self.data.get_images_modi(i) for i in range(2)], train_labels=masks,
+                                       labels_have_residual=True)
 
     def _init_unlabelled_data_generator(self):
         if self.conf.l_mix == 1:
@@ -145,7 +147,8 @@ class DAFNetExecutor(Executor):
             self.data_len = self.ul_data.size()
         nm = self.loader.num_masks
         return self.get_data_generator(train_images=[self.ul_data.get_images_modi(i) for i in range(2)],
-                                       train_labels=[self.add_residual(self.ul_data.get_masks_modi(0)[..., 0:nm])])
+                                       train_labels=[self.add_residual(self.ul_data.get_masks_modi(0)[..., 0:nm])],
+                                       labels_have_residual=True)
 
     def _pair_up(self, data):
         """dafnet_executor.py:89-93,127-131: candidate pairs for the automated-pairing trainers (images get n_pairs
@@ -188,6 +191,8 @@ class DAFNetExecutor(Executor):
             th = torch.from_numpy(theta[:n]).cuda(non_blocking=True)
             self.h2d_bytes += th.numel() * 4
             out = [ops.rotate_bilinear(t.contiguous(), th) for t in out]
+            for i in getattr(gen, "residual_items", ()):
+                ops.mask_residual_(out[i])          # background channel of the rotated masks (dafnet_executor.py:493-494)
         return out
 
     def _sample_z(self, B):

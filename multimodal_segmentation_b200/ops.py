@@ -1092,6 +1092,14 @@ def rotate_bilinear(x, theta):
     return y
 
 
+def mask_residual_(m):
+    """rebuild the background channel (last) of a staged mask batch from its other channels, in place"""
+    _chk(m)
+    C = m.shape[-1]
+    call("mask_residual", m, m.numel() // C, C, _S())
+    return m
+
+
 # ---------------------------------------------------------------------------- automated-pairing losses
 def segloss_pb_fwd(pred, target, nch, L_row, lambda_bce=0.01):
     """per-sample dice + lambda * swapped per-batch wBCE (costs.py:88-108,138-143) -> L_row[B]; returns the workspace"""

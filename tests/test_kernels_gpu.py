@@ -599,3 +599,29 @@ def test_tps_phi_table_path_is_bit_identical(ops):
     finally:
         ops.TPS_PHI_TABLE = old
     assert torch.equal(a4, b4) and rel_l2(cpu(g4[0]), cpu(h4[0])) < 1e-6 and rel_l2(cpu(g4[1]), cpu(h4[1])) < 1e-6
+
+
+def test_residual_channel_is_rebuilt_after_the_rotation(ops):
+    """the reference augments the nm-channel masks and calls add_residual on the AUGMENTED batch
+    (model_executors/dafnet_executor.py:493-494, base_executor.py:83-87), so the background channel is 1 wherever the
+    bilinearly rotated mask is not exactly 1.  dafk_mask_residual on the staged batch against the reference order of
+    operations in numpy, and the executor's stager applies it to the label arrays of its generators."""
+    shape = (3, 33, 29, 5)
+    r = rng(3)
+    m = (r.uniform(size=shape[:3] + (4,)) > 0.6).astype(np.float32)
+    theta = r.uniform(-0.3, 0.3, size=3).astype(np.float32)
+    staged = np.concatenate([m, np.ones(shape[:3] + (1,), np.float32)], -1)          # residual channel allocated, stale
+    rot = ops.rotate_bilinear(gpu(staged), gpu(theta))
+    ops.mask_residual_(rot)
+    got = cpu(rot)
+    rot_masks = np.stack([_keras_rotate(m[b].astype(np.float64), float(theta[b])) for b in range(3)], 0).astype(np.float32)
+    want_res = np.ones(shape[:3] + (1,), np.float32)
+    for i in range(4):
+        want_res[cpu(rot)[..., i:i + 1] == 1] = 0                                   # add_residual on the rotated channels
+    assert np.array_equal(got[..., 4:5], want_res)
+    assert np.abs(got[..., :4] - rot_masks).max() < 1e-5
+    assert 0 < want_res.mean() < 1 and (want_res != (1 - np.clip(rot_masks.sum(-1, keepdims=True), 0, 1))).any()
+    # host plumbing: label arrays of a generator are flagged, image arrays are not
+    from multimodal_segmentation_b200.model_executors.base_executor import BatchFlow, FlowGroup
+    g = FlowGroup([BatchFlow(np.zeros((4, 8, 8, 1), np.float32), 2, 0, 0.0), BatchFlow(np.zeros((4, 8, 8, 5), np.float32), 2, 0, 0.0)], [1])
+    assert g.residual_items == (1,)
