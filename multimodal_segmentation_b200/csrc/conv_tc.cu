@@ -53,6 +53,9 @@ constexpr int EPI_BN_PITCH = 80;
 constexpr int EPI_BN_TILE = 32 * EPI_BN_PITCH;
 constexpr int EPI_BN_RUN = 2 * 256;                                  // floats per warp: [sum | sum of squares][BLOCK_N <= 256]
 constexpr int EPI_BN_BYTES = 4 * EPI_BN_TILE + 4 * EPI_BN_RUN * 4;   // four epilogue warps
+// + a warp-private copy of the tile's bias block (the epilogue read 32 predicated __ldg per 32-column chunk and thread)
+constexpr int EPI_BIAS_BYTES = 4 * 256 * 4;
+constexpr int EPI_BYTES = EPI_BN_BYTES + EPI_BIAS_BYTES;
 
 __device__ __forceinline__ void epi_bn_chunk(uint8_t* tile, float* run, int lane, int c, const uint32_t (&pk)[16], bool live) {
   uint4* row = reinterpret_cast<uint4*>(tile + lane * EPI_BN_PITCH);
@@ -221,6 +224,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
     uint8_t* const s_epi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot) + 31) & ~(uintptr_t)15);
     uint8_t* const bn_tile = s_epi + q4 * EPI_BN_TILE;
     float* const bn_run = reinterpret_cast<float*>(s_epi + 4 * EPI_BN_TILE) + q4 * EPI_BN_RUN;
+    float* const wbias = reinterpret_cast<float*>(s_epi + EPI_BN_BYTES) + q4 * 256;     // this warp's copy of bias[n0 .. n0+BLOCK_N)
+    int wbias_n0 = -1;
     if (bn_acc != nullptr) {
       for (int i = lane; i < EPI_BN_RUN; i += 32) bn_run[i] = 0.f;
       __syncwarp();
@@ -238,6 +243,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
       const int Ho_c = cg.n > 1 ? (cg.Hf - pa + 1) / 2 : Ho, Wo_c = cg.n > 1 ? (cg.Wf - pb + 1) / 2 : Wo;
       const bool live = px < Wo_c && py < Ho_c && img < N;
       const uint32_t b = (uint32_t)tc & 1u;
+      if (wbias_n0 != n0) {          // (re)load this warp's bias block; once per CTA when there is one output-channel block
+        __syncwarp();
+        for (int i = lane; i < BLOCK_N; i += 32) wbias[i] = (bias != nullptr && n0 + i < Cout) ? __ldg(bias + n0 + i) : 0.f;
+        __syncwarp();
+        wbias_n0 = n0;
+      }
       mbar_wait(tfull_bar + b, ((uint32_t)tc >> 1) & 1u);
       tc_fence_after();
       const int64_t obase = (int64_t)img * y_sn + (int64_t)py * y_sy + (int64_t)px * y_sx + n0 +
@@ -254,9 +265,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_fwd_kernel(const __grid
           float f[32];
           const int cvalid = Cout - (n0 + c);            // channels of this chunk that exist (Cout % 8 == 0)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-              f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + n0 + c + j) : 0.f);
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(wbias + c + j);
+            f[j] = __uint_as_float(v[j]) + bb.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + bb.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+          }
           if (ep_code != DAFK_ACT_NONE) {       // uniform branch per chunk (a per-element branch made the epilogue 2.5x slower)
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = epi_act(f[j], ep_code, ep_alpha);
@@ -484,6 +499,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
     uint8_t* const s_epi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot) + 31) & ~(uintptr_t)15);
     uint8_t* const bn_tile = s_epi + q4 * EPI_BN_TILE;
     float* const bn_run = reinterpret_cast<float*>(s_epi + 4 * EPI_BN_TILE) + q4 * EPI_BN_RUN;
+    float* const wbias = reinterpret_cast<float*>(s_epi + EPI_BN_BYTES) + q4 * 256;     // this warp's copy of bias[n0 .. n0+BLOCK_N)
+    int wbias_n0 = -1;
     if (bn_acc != nullptr) {
       for (int i = lane; i < EPI_BN_RUN; i += 32) bn_run[i] = 0.f;
       __syncwarp();
@@ -496,6 +513,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
       const int x0 = txi * g.TWo, y0 = tyi * g.TH, img0 = mt * g.TN;
       const int n0 = nb * BLOCK_N;
       const uint32_t buf = (uint32_t)tc & 1u;
+      if (wbias_n0 != n0) {          // (re)load this warp's bias block; once per CTA when there is one output-channel block
+        __syncwarp();
+        for (int i = lane; i < BLOCK_N; i += 32) wbias[i] = (bias != nullptr && n0 + i < Cout) ? __ldg(bias + n0 + i) : 0.f;
+        __syncwarp();
+        wbias_n0 = n0;
+      }
       mbar_wait(tfull_bar + buf, ((uint32_t)tc >> 1) & 1u);
       tc_fence_after();
       for (int gi = 0; gi < g.G; ++gi) {
@@ -518,8 +541,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_tc_halo_kernel(const __g
             float f[32];
             const int cvalid = Cout - (n0 + c);            // channels of this chunk that exist (Cout % 8 == 0)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + n0 + c + j) : 0.f);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(wbias + c + j);
+              f[j] = __uint_as_float(v[j]) + bb.x;
+              f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + bb.z;
+              f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
             }
             if (ep_code != DAFK_ACT_NONE) {       // uniform branch per chunk (a per-element branch made the epilogue 2.5x slower)
 #pragma unroll
@@ -705,6 +732,8 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
     uint8_t* const s_epi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot) + 31) & ~(uintptr_t)15);
     uint8_t* const bn_tile = s_epi + q4 * EPI_BN_TILE;
     float* const bn_run = reinterpret_cast<float*>(s_epi + 4 * EPI_BN_TILE) + q4 * EPI_BN_RUN;
+    float* const wbias = reinterpret_cast<float*>(s_epi + EPI_BN_BYTES) + q4 * 256;     // this warp's copy of bias[n0 .. n0+BLOCK_N)
+    int wbias_n0 = -1;
     if (bn_acc != nullptr) {
       for (int i = lane; i < EPI_BN_RUN; i += 32) bn_run[i] = 0.f;
       __syncwarp();
@@ -716,6 +745,12 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
       const int tyi = mt % g.tiles_y; mt /= g.tiles_y;
       const int x0 = txi * g.TWo, y0 = tyi * g.TH, img0 = mt * g.TN;
       const uint32_t buf = (uint32_t)tc & 1u;
+      if (wbias_n0 != 0) {          // (re)load this warp's bias block; once per CTA when there is one output-channel block
+        __syncwarp();
+        for (int i = lane; i < BLOCK_N; i += 32) wbias[i] = (bias != nullptr && 0 + i < Cout) ? __ldg(bias + 0 + i) : 0.f;
+        __syncwarp();
+        wbias_n0 = 0;
+      }
       mbar_wait(tfull_bar + buf, ((uint32_t)tc >> 1) & 1u);
       tc_fence_after();
       for (int gi = 0; gi < g.G && tile_live; ++gi) {
@@ -738,8 +773,12 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
             float f[32];
             const int cvalid = Cout - c;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              f[j] = __uint_as_float(v[j]) + ((bias && j < cvalid) ? __ldg(bias + c + j) : 0.f);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(wbias + c + j);
+              f[j] = __uint_as_float(v[j]) + bb.x;
+              f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + bb.z;
+              f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
             }
             if (ep_code != DAFK_ACT_NONE) {       // uniform branch per chunk (a per-element branch made the epilogue 2.5x slower)
 #pragma unroll
@@ -1076,7 +1115,7 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
                       int y_dt, int N, int Ho, int Wo, int Cout, int C0, int C1, int KH, int KW, int stride, int pad,
                       const TileGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
                       long long y_sx, Epi ep, cudaStream_t s, const ClsGeom& cg = ClsGeom{1, 0, 0, 0, 0, 0}) {
-  constexpr int smem = STAGES * (A_BYTES + BLOCK_N * KBLK * 2) + 1024 + 256 + EPI_BN_BYTES;
+  constexpr int smem = STAGES * (A_BYTES + BLOCK_N * KBLK * 2) + 1024 + 256 + EPI_BYTES;
   static_assert(smem > 116 * 1024 && smem <= 227 * 1024, "one persistent CTA per SM");
   static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
   if (!configured) {
@@ -1212,7 +1251,7 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
                        const HaloGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
                        long long y_sx, Epi ep, cudaStream_t s) {
   const int ncb_all = (C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK;
-  const int smem = g.SA * g.a_bytes + (g.w_resident ? ncb_all * KH * KW : g.SB) * BLOCK_N * KBLK * 2 + 1024 + 512 + EPI_BN_BYTES;
+  const int smem = g.SA * g.a_bytes + (g.w_resident ? ncb_all * KH * KW : g.SB) * BLOCK_N * KBLK * 2 + 1024 + 512 + EPI_BYTES;
   static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1243,7 +1282,7 @@ static int launch_halo2(const CUtensorMap& a0, const CUtensorMap& a1, const CUte
                         const HaloGeom& g, int w_rows_per_tap, int w_row_off, long long y_sn, long long y_sy,
                         long long y_sx, Epi ep, cudaStream_t s) {
   const int ncb_all = (C0 + KBLK - 1) / KBLK + (C1 + KBLK - 1) / KBLK;
-  const int smem = g.SA * g.a_bytes + ncb_all * KH * KW * (BLOCK_N / 2) * KBLK * 2 + 1024 + 512 + EPI_BN_BYTES;
+  const int smem = g.SA * g.a_bytes + ncb_all * KH * KW * (BLOCK_N / 2) * KBLK * 2 + 1024 + 512 + EPI_BYTES;
   DAFK_REQUIRE(smem <= 227 * 1024, DAFK_ERR_UNSUPPORTED, "dafk_conv_tc_fwd(halo2): %d bytes of shared memory", smem);
   static std::atomic<bool> configured{false};   // idempotent one-time attribute set: a race only repeats it
   if (!configured) {
