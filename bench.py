@@ -192,11 +192,20 @@ def run_reference(args):
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def nccl_env():
-    """stdout carries exactly one JSON line: NCCL's INFO log (the driver counts the ranks of the communicator in it) goes to
-    stderr instead of being switched off"""
-    os.environ.setdefault("NCCL_DEBUG", "INFO")
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    """stdout carries exactly one JSON line; NCCL's INFO log (the driver counts the ranks of the communicator in it) must
+    still be visible.  NCCL writes it to the C-level stdout, and NCCL_DEBUG_FILE=/dev/stderr truncates the log when stderr
+    is a regular file, so file descriptor 1 is pointed at stderr for native code and Python's sys.stdout keeps the real
+    stdout for the JSON line."""
+    # forced, not setdefault: the boxes export NCCL_DEBUG=VERSION, which prints the version line only
+    os.environ["NCCL_DEBUG"] = os.environ.get("DAFK_NCCL_DEBUG", "INFO")
+    os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("DAFK_NCCL_DEBUG_SUBSYS", "INIT")
+    os.environ.pop("NCCL_DEBUG_FILE", None)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not getattr(nccl_env, "done", False):
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
+        nccl_env.done = True
 
 
 def run_b200(args):
