@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(DT) dense_fwd_kernel(const float* __restrict__
       }
       __syncthreads();
       if (active) {
+#pragma unroll 4
         for (int k = g; k < kc; k += groups) {
           float wv = __ldg(w + (k0 + k) * N + nbase + n);
 #pragma unroll
@@ -79,6 +80,135 @@ __global__ void __launch_bounds__(DT) dense_fwd_kernel(const float* __restrict__
       atomicAdd(y + (int64_t)(b0 + b) * N + nbase + c, part[e]);
     }
     __syncthreads();
+  }
+}
+
+// Short reduction axis (K <= 2048: the FiLM gamma / beta heads 8 -> 8, z_mean / z_log_var 32 -> 8, locnet 100 -> 50):
+// one thread per output, bias included, ONE launch (the split-K path needs an initialisation launch and atomics, and a
+// single CTA walking K with dependent loads took 25 us for a 32 x 100 x 50 product).
+__global__ void __launch_bounds__(DT) dense_fwd_shortk_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ y, int B,
+                                                              int K, int N) {
+  const int o = blockIdx.x * DT + threadIdx.x;
+  if (o >= B * N) return;
+  const int b = o / N, n = o - b * N;
+  const float* xr = x + (int64_t)b * K;
+  const float* wc = w + n;
+  float acc = bias ? bias[n] : 0.f;
+#pragma unroll 8
+  for (int k = 0; k < K; ++k) acc = fmaf(__ldg(xr + k), __ldg(wc + (int64_t)k * N), acc);
+  y[o] = acc;
+}
+
+// Register-tiled forward for N % 4 == 0 (locnet Dense(100) over 48 020 features, layers/stn_spline.py:114; modality
+// encoder Dense(32) over 21 632, model_components/modality_encoder.py:44): the kernel above reads one shared-memory word
+// per FMA (32 broadcast LDS per weight element) and ran the 19 MB weight stream at 230 GB/s.  Here a thread owns an
+// 8 (batch rows) x 4 (columns) tile: per k it reads its 8 x values as two 128-bit shared-memory loads (x staged transposed,
+// [k][batch], 36-float pitch) and 4 weights as one 128-bit global load -> 32 FMAs per 3 loads.  NG = N/4 column groups x 4
+// batch groups = one k-slice; 256 / (4*NG) slices walk the chunk in parallel and are reduced through shared memory.
+constexpr int RT_PITCH = 36;
+__global__ void __launch_bounds__(DT) dense_fwd_rt_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          float* __restrict__ y, int B, int64_t K, int N, int64_t k_per_cta) {
+  __shared__ __align__(16) float xs[KC * RT_PITCH];
+  extern __shared__ float part[];   // [MAXB][N]
+  const int b0 = blockIdx.y * MAXB;
+  const int nb = min(MAXB, B - b0);
+  const int64_t kbeg = (int64_t)blockIdx.x * k_per_cta;
+  const int64_t kend = min(K, kbeg + k_per_cta);
+  const int NG = N >> 2;
+  const int per_slice = 4 * NG;
+  const int slices = DT / per_slice;
+  const int sl = threadIdx.x / per_slice;
+  const int r = threadIdx.x - sl * per_slice;
+  const int bg = r / NG, ng = r - bg * NG;
+  const bool active = sl < slices;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int e = threadIdx.x; e < MAXB * N; e += DT) part[e] = 0.f;
+  for (int64_t k0 = kbeg; k0 < kend; k0 += KC) {
+    const int kc = (int)min((int64_t)KC, kend - k0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < MAXB * KC; e += DT) {      // coalesced along k, transposed into [k][batch]
+      const int b = e / KC, k = e - b * KC;
+      xs[k * RT_PITCH + b] = (b < nb && k < kc) ? x[(int64_t)(b0 + b) * K + k0 + k] : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      const float* wp = w + k0 * N + ng * 4;
+      // the weight stream is the only HBM traffic: eight independent 128-bit loads in flight per thread (one per
+      // iteration left each thread waiting a full DRAM latency per k: 85 us for 19 MB)
+#pragma unroll 8
+      for (int k = sl; k < kc; k += slices) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)k * N));
+        const float4 xa = *reinterpret_cast<const float4*>(xs + k * RT_PITCH + bg * 8);
+        const float4 xb = *reinterpret_cast<const float4*>(xs + k * RT_PITCH + bg * 8 + 4);
+        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], wj[j], acc[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&part[(bg * 8 + i) * N + ng * 4 + j], acc[i][j]);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nb * N; e += DT) atomicAdd(y + (int64_t)b0 * N + e, part[e]);
+}
+
+// Register-tiled weight gradient for N % 4 == 0, K % 4 == 0: a thread owns 4 (k) x 4 (n) outputs; per batch row it reads x
+// as one 128-bit global load (coalesced along k) and dy as one 128-bit shared-memory load -> 16 FMAs per 2 loads (the
+// kernel below: 2 loads per FMA).
+__global__ void __launch_bounds__(DT) dense_bwd_weight_rt_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 float* __restrict__ dw, float* __restrict__ db, int B,
+                                                                 int64_t K, int N) {
+  extern __shared__ __align__(16) float dys[];  // [B][N]
+  for (int e = threadIdx.x; e < B * N; e += DT) dys[e] = dy[e];
+  __syncthreads();
+  if (db && blockIdx.x == 0) {
+    for (int n = threadIdx.x; n < N; n += DT) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += dys[b * N + n];
+      db[n] += s;
+    }
+  }
+  const int NG = N >> 2;
+  const int64_t tiles = (K >> 2) * NG;
+  for (int64_t t = (int64_t)blockIdx.x * DT + threadIdx.x; t < tiles; t += (int64_t)gridDim.x * DT) {
+    const int64_t kq = t / NG;
+    const int ng = (int)(t - kq * NG);
+    const int64_t k = kq << 2;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (int64_t)b * K + k));
+      const float4 dv = *reinterpret_cast<const float4*>(dys + b * N + ng * 4);
+      const float xi[4] = {xv.x, xv.y, xv.z, xv.w};
+      const float dj[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xi[i], dj[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4* o = reinterpret_cast<float4*>(dw + (k + i) * N + ng * 4);
+      float4 cur = *o;
+      cur.x += acc[i][0]; cur.y += acc[i][1]; cur.z += acc[i][2]; cur.w += acc[i][3];
+      *o = cur;
+    }
   }
 }
 
@@ -142,6 +272,7 @@ __global__ void __launch_bounds__(DT) dense_bwd_data_kernel(const float* __restr
 #pragma unroll
   for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
   const float* wr = w + k * N;
+#pragma unroll 4
   for (int n = 0; n < N; ++n) {
     float wv = __ldg(wr + n);
 #pragma unroll
@@ -225,6 +356,10 @@ int dafk_dense_fwd(const float* x, const float* w, const float* bias, float* y, 
   if (B == 0) return DAFK_OK;
   DAFK_REQUIRE(x && w && y, DAFK_ERR_BAD_ARG, "dafk_dense_fwd: null pointer");
   cudaStream_t s = as_stream(stream);
+  if (K <= 2048 && (int64_t)B * Nout >= 64) {
+    dense_fwd_shortk_kernel<<<(B * Nout + DT - 1) / DT, DT, 0, s>>>(x, w, bias, y, B, (int)K, Nout);
+    return check_launch("dafk_dense_fwd");
+  }
   dense_init_kernel<<<(B * Nout + 255) / 256, 256, 0, s>>>(y, bias, B, Nout);
   int rc = check_launch("dafk_dense_fwd(init)");
   if (rc) return rc;
@@ -247,6 +382,11 @@ int dafk_dense_fwd(const float* x, const float* w, const float* bias, float* y, 
   int64_t want = 2 * kNumSMs;
   int64_t k_per_cta = ((slabs + want - 1) / want) * KC;
   dim3 grid((unsigned)((K + k_per_cta - 1) / k_per_cta), (B + MAXB - 1) / MAXB);
+  if (Nout % 4 == 0 && Nout >= 8 && 4 * (Nout / 4) <= DT && K >= 4 * KC && DAFK_ALIGNED16(w) &&
+      sizeof(float) * MAXB * Nout + sizeof(float) * KC * RT_PITCH <= 48 * 1024) {
+    dense_fwd_rt_kernel<<<grid, DT, sizeof(float) * MAXB * Nout, s>>>(x, w, y, B, K, Nout, k_per_cta);
+    return check_launch("dafk_dense_fwd");
+  }
   size_t smem = sizeof(float) * MAXB * (Nout < DT ? Nout : DT);
   dense_fwd_kernel<<<grid, DT, smem, s>>>(x, w, y, B, K, Nout, k_per_cta);
   return check_launch("dafk_dense_fwd");
@@ -277,6 +417,11 @@ int dafk_dense_bwd_weight(const float* x, const float* dy, float* dw, float* db,
   int grid = bw_grid(total, DT, 8);
   if (smem > 48 * 1024) {
     dense_bwd_weight_wide_kernel<<<grid, DT, 0, as_stream(stream)>>>(x, dy, dw, db, B, K, Nout);
+    return check_launch("dafk_dense_bwd_weight");
+  }
+  if (Nout % 4 == 0 && K % 4 == 0 && K >= 1024 && DAFK_ALIGNED16(x) && DAFK_ALIGNED16(dw)) {
+    const int g4 = bw_grid(total / 16, DT, 8);
+    dense_bwd_weight_rt_kernel<<<g4, DT, smem, as_stream(stream)>>>(x, dy, dw, db, B, K, Nout);
     return check_launch("dafk_dense_bwd_weight");
   }
   dense_bwd_weight_kernel<<<grid, DT, smem, as_stream(stream)>>>(x, dy, dw, db, B, K, Nout);

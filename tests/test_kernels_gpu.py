@@ -303,7 +303,8 @@ def test_conv_fused_activation(ops):
 
 # ------------------------------------------------------------------ dense
 @pytest.mark.parametrize("B,K,N", [(4, 1000, 32), (32, 21632, 32), (3, 4802, 100), (5, 270848 // 8, 1), (2, 8, 300), (32, 8, 6272), (192, 8, 6272),
-                                   (32, 270848, 1), (3, 1000, 2), (7, 4004, 4), (4, 1002, 1), (33, 512, 3)])
+                                   (32, 270848, 1), (3, 1000, 2), (7, 4004, 4), (4, 1002, 1), (33, 512, 3),
+                                   (32, 48020, 100), (5, 1028, 8), (40, 4100, 52), (32, 2052, 64), (9, 1500, 100)])
 def test_dense(ops, B, K, N):
     r = rng(B + N)
     x = r.normal(size=(B, K)).astype(np.float32)
