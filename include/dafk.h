@@ -226,6 +226,11 @@ int dafk_conv_small_wgrad(const dafk_conv_desc* d, const float* x, const float* 
  * converted to bf16 while it is staged; accumulation is fp32 in tensor memory.
  * kind: 0 forward, 1 data gradient, 2 weight gradient.  Returns 1 if the geometry fits in shared memory. */
 int dafk_conv_nc_supported(int Cin, int Cout, int KH, int KW, int W, int pad, int kind);
+/* 1 if dafk_conv_nc_wgrad would bring x / dy rows of these dtypes (DAFK_F32 / DAFK_BF16) into shared memory with bulk
+ * copies (large maps with 16-byte-multiple rows): a bf16 output gradient is then read at half the bytes, while the
+ * register-staged kernel is slower on bf16 than on fp32.  The host engine asks before it lets the BatchNormalization
+ * backward of a first layer (models/unet.py:95, model_components/segmentor.py:15) write its gradient in bf16. */
+int dafk_conv_nc_wgrad_stages_raw(int N, int H, int W, int Cin, int Cout, int KH, int KW, int pad, int x_dt, int dy_dt);
 /* number of bf16 elements of the packed weight buffer for a kernel that reduces over Cin_k channels
  * and produces Cout_k channels */
 int64_t dafk_conv_nc_packed_elems(int Cin_k, int Cout_k, int KH, int KW);

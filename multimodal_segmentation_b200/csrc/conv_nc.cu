@@ -39,6 +39,8 @@ struct NcFwdP {
   float alpha;
   int dbg;
   int Ca, Cb;                        // two concatenated sources (Cb > 0): channels [0,Ca) from x, [Ca,Ca+Cb) from xb; Ca % 8 == 0
+  int raw_slots, raw_slot_bytes;     // RAW mode: ring of row segments filled by the TMA engine (0 slots = not used)
+  int seg_px, nseg;                  //           pixels per segment, segments per image row
 };
 
 struct NcWgP {
@@ -53,6 +55,8 @@ struct NcWgP {
   int fold;                          // Cout <= 8: the KH filter rows are folded into the MMA's N dimension
   int yoff;                          // fold: positions of zero halo in front of the dY rows = (KH-1)*P
   int Ca, Cb;                        // two concatenated input sources, as in NcFwdP
+  int raw_slots, raw_slot_bytes;     // RAW mode: ring of row segments (X rows and dY rows share it)
+  int seg_px, nseg, seg_px_y, nseg_y;
 };
 
 // load 8 consecutive channels starting at p (nvalid of them exist) as floats
@@ -175,6 +179,133 @@ __device__ __forceinline__ void nc_stage_rows(const T* __restrict__ src, uint8_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// RAW staging: the rows of a strip are brought into shared memory AS THEY LIE in global memory (fp32 or bf16, C channels
+// per pixel) by 1-D cp.async.bulk copies, one per row segment, into a ring of slots; converter warps turn each segment
+// into bf16 raster units (smem -> smem).  The register-staged path above keeps at most NC_U loads per thread in flight and
+// pays a full DRAM latency per batch (8 -> 8 @ 192 x 224^2: 4.1 TB/s forward, 2.4 TB/s weight gradient); here the bytes in
+// flight are the ring (>= 8 segments of up to 8 KB per SM, issued by one lane, no registers), and the issuer runs ahead of
+// the converters across strip boundaries.  A segment = seg_px pixels of one image row (a whole row when it fits 8 KB).
+// Both sides walk the same (row, segment) sequence; rows outside the image are not copied, the converters zero them.
+// ---------------------------------------------------------------------------------------------
+constexpr int NC_RAW_MAX_SLOTS = 16;
+constexpr int NC_RAW_SEG_MAX = 8192;
+constexpr int NC_RAW_CONV = 192;      // converter threads (six warps)
+
+struct NcRing {
+  uint8_t* base;
+  uint64_t* full;     // [slots] count 1 + transaction bytes
+  uint64_t* empty;    // [slots] count 1: the converter warp that owns the segment
+  int slots, slot_bytes;
+  int slot;           // position of this thread's walk
+  uint32_t ph;
+  int turn;           // converter warp that owns the segment at `slot` (segments go round-robin over the warps)
+};
+
+template <typename T>
+__device__ __forceinline__ void nc_raw_issue(NcRing& r, const T* __restrict__ src, int n, int Himg, int wcols, int C, int iy0,
+                                             int rows, int seg_px, int nseg) {
+  const size_t px_bytes = (size_t)C * sizeof(T);
+  const size_t row_bytes = (size_t)wcols * px_bytes;
+  const uint8_t* img = reinterpret_cast<const uint8_t*>(src) + (size_t)n * Himg * row_bytes;
+  for (int row = 0; row < rows; ++row) {
+    const int iy = iy0 + row;
+    if (iy < 0 || iy >= Himg) continue;
+    for (int sg = 0; sg < nseg; ++sg) {
+      const int px0 = sg * seg_px;
+      const uint32_t bytes = (uint32_t)(min(seg_px, wcols - px0) * px_bytes);
+      mbar_wait(r.empty + r.slot, r.ph ^ 1u);
+      mbar_expect_tx(r.full + r.slot, bytes);
+      bulk_load_1d(r.base + (size_t)r.slot * r.slot_bytes, img + (size_t)iy * row_bytes + (size_t)px0 * px_bytes, bytes,
+                   r.full + r.slot);
+      if (++r.slot == r.slots) { r.slot = 0; r.ph ^= 1u; }
+    }
+  }
+}
+
+// 8 channels of a staged pixel (shared memory) as floats; bf16 rows need C % 8 == 0, fp32 rows take any C (vector reads
+// when C % 4 == 0: a group is then whole or holds exactly 4 valid channels)
+__device__ __forceinline__ void nc_raw_load8(const float* p, int nvalid, bool vec, float (&v)[8]) {
+  if (!vec) {        // channel counts that are not multiples of 4 (the 1-channel images): scalar reads
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = c < nvalid ? p[c] : 0.f;
+    return;
+  }
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  if (nvalid >= 8) {
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else { v[4] = v[5] = v[6] = v[7] = 0.f; }
+}
+
+// Converter side, called by every converter warp (cw = its index among the ncw of them).  A segment belongs to ONE warp:
+// the warps work on different segments at the same time, and nothing but that warp's arrival frees the slot (a segment
+// shared by all warps cost a barrier round trip of all 192 threads per image row: the load path alone took 117 us for
+// 8 -> 8 @ 192 x 224^2 against 93 us with register staging).  `lanes` of the warp convert (32, or a multiple of `groups`
+// when the per-lane channel sums of the bias gradient need every lane to stay on one channel group).
+template <typename T, bool BSUM>
+__device__ __forceinline__ void nc_raw_convert(NcRing& r, uint8_t* planes, int plane_pos, int Himg, int wcols, int C, int groups,
+                                               int iy0, int rows, int P, int col0, int cw, int ncw, int lanes, int seg_px,
+                                               int nseg, int lane, float (&bsum)[8]) {
+  const int gshift = (groups & (groups - 1)) == 0 ? 31 - __clz(groups) : -1;
+  for (int row = 0; row < rows; ++row) {
+    const int iy = iy0 + row;
+    uint8_t* prow = planes + (size_t)(row * P + col0) * 16;
+    if (iy < 0 || iy >= Himg) {      // the raster of this stage still holds a row of an earlier strip
+      for (int u = cw * 32 + lane; u < wcols * groups; u += ncw * 32) {
+        int cg, px;
+        if (gshift >= 0) { cg = u & (groups - 1); px = u >> gshift; }
+        else { px = u / groups; cg = u - px * groups; }
+        *reinterpret_cast<uint4*>(prow + ((size_t)cg * plane_pos + px) * 16) = make_uint4(0, 0, 0, 0);
+      }
+      continue;
+    }
+    for (int sg = 0; sg < nseg; ++sg) {
+      if (r.turn == cw) {
+        const int px0 = sg * seg_px;
+        const int units = min(seg_px, wcols - px0) * groups;
+        mbar_wait(r.full + r.slot, r.ph);
+        const T* raw = reinterpret_cast<const T*>(r.base + (size_t)r.slot * r.slot_bytes);
+        if (lane < lanes) {
+#pragma unroll 4
+          for (int u = lane; u < units; u += lanes) {
+            int cg, px;
+            if (gshift >= 0) { cg = u & (groups - 1); px = u >> gshift; }
+            else { px = u / groups; cg = u - px * groups; }
+            uint4 packed;
+            if (sizeof(T) == 4) {
+              float v[8];
+              nc_raw_load8(reinterpret_cast<const float*>(raw) + px * C + cg * 8, C - cg * 8, (C & 3) == 0, v);
+              packed = nc_pack8(v);
+              if (BSUM) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) bsum[c] += v[c];
+              }
+            } else {
+              packed = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(raw) + px * C + cg * 8);
+              if (BSUM) {
+                const uint32_t w[4] = {packed.x, packed.y, packed.z, packed.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+                  bsum[2 * i] += __low2float(h);
+                  bsum[2 * i + 1] += __high2float(h);
+                }
+              }
+            }
+            *reinterpret_cast<uint4*>(prow + ((size_t)cg * plane_pos + px0 + px) * 16) = packed;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(r.empty + r.slot);
+      }
+      if (++r.slot == r.slots) { r.slot = 0; r.ph ^= 1u; }
+      if (++r.turn == ncw) r.turn = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // forward / stride-1 data gradient.  Warp-specialised persistent CTA (one per SM):
 //   warps 0-7  producers : global -> bf16 raster planes of stage s           (full[s] / empty[s] ring)
 //   warp  8    MMA issuer: per 128-position tile E/2 tcgen05.mma into one of two TMEM buffers
@@ -182,7 +313,6 @@ __device__ __forceinline__ void nc_stage_rows(const T* __restrict__ src, uint8_t
 // smem: [wp: E*Npad*16][S stages x CG*plane*16][descA: E/2 u64][descB: E/2 u64][bias: Npad f32][barriers]
 // ---------------------------------------------------------------------------------------------
 constexpr int NC_FWD_THREADS = NC_PROD + 32 + 128;
-constexpr int NC_MMA_WARP = NC_PROD / 32;
 constexpr int NC_MAX_STAGES = 4;
 
 //
@@ -199,15 +329,19 @@ constexpr int NC_MAX_STAGES = 4;
 // (A setmaxnreg split into four warpgroups with an eight-tile lock-step epilogue was measured too: slower, 34 / 200 us
 // against 32 / 149 us on 8 -> 8 / 8 -> 64, and removed.)
 constexpr int NC_BULK_THREADS = 384;
-constexpr int NC_MODE_DEFAULT = 0, NC_MODE_BULK = 1, NC_MODE_L12 = 2;
+//
+// MODE 3 (RAW): MODE 2's layout with the staging split in two -- warp 0 issues the bulk copies of the row segments, warps 1-6
+// convert them into the raster (nc_raw_issue / nc_raw_convert above).
+constexpr int NC_MODE_DEFAULT = 0, NC_MODE_BULK = 1, NC_MODE_L12 = 2, NC_MODE_RAW = 3;
 
 template <typename TX, int MODE>
 __global__ void __launch_bounds__(MODE == NC_MODE_DEFAULT ? NC_FWD_THREADS : NC_BULK_THREADS, 1)
 conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __restrict__ wp,
                    const float* __restrict__ bias, void* __restrict__ y, const TX* __restrict__ xb = nullptr) {
   constexpr bool BULK = MODE == NC_MODE_BULK;
+  constexpr bool RAW = MODE == NC_MODE_RAW;
   constexpr int THREADS = MODE == NC_MODE_DEFAULT ? NC_FWD_THREADS : NC_BULK_THREADS;
-  constexpr int PROD = MODE == NC_MODE_L12 ? 224 : NC_PROD;                 // staging threads (not BULK)
+  constexpr int PROD = (MODE == NC_MODE_L12 || RAW) ? 224 : NC_PROD;         // staging threads (not BULK)
   constexpr int MMA_WARP = BULK ? 1 : PROD / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -223,6 +357,9 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
   uint64_t* tfull = empty + NC_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rfull = reinterpret_cast<uint64_t*>(tmem_slot + 2);            // RAW: segment ring barriers + ring
+  uint64_t* rempty = rfull + NC_RAW_MAX_SLOTS;
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rempty + NC_RAW_MAX_SLOTS) + 127) & ~(uintptr_t)127);
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
 
   // one-time setup: weights, bias, zeroed rasters (halo columns and slack stay zero for the CTA's lifetime)
@@ -247,8 +384,10 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
     s_descB[j] = make_smem_desc_ns(smem_u32(s_w) + (uint32_t)(2 * j * p.Npad * 16), (uint32_t)p.Npad * 16, 128);
   }
   if (tid == 0) {
-    for (int i = 0; i < p.S; ++i) { mbar_init(full + i, BULK ? 1 : PROD); mbar_init(empty + i, 1); }
+    for (int i = 0; i < p.S; ++i) { mbar_init(full + i, BULK ? 1 : (RAW ? NC_RAW_CONV : PROD)); mbar_init(empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 128); }
+    if (RAW)
+      for (int i = 0; i < p.raw_slots; ++i) { mbar_init(rfull + i, 1); mbar_init(rempty + i, 1); }
     fence_barrier_init();
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -294,6 +433,33 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
         }
         __syncwarp();
       }
+    }
+  } else if (RAW && warp == 0) {
+    // ===================== RAW: bulk-copy issuer (one lane walks every strip of this CTA, bounded only by the ring) =====
+    if (lane == 0) {
+      NcRing r{ring, rfull, rempty, p.raw_slots, p.raw_slot_bytes, 0, 0u, 0};
+      for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x) {
+        const int n = s / p.strips_per_img;
+        const int y0 = (s - n * p.strips_per_img) * p.R;
+        nc_raw_issue<TX>(r, x, n, p.H, p.W, p.Cin, y0 - p.pad, p.RS, p.seg_px, p.nseg);
+      }
+    }
+    __syncwarp();
+  } else if (RAW && warp < MMA_WARP) {
+    // ===================== RAW: converters (warps 1-6) =====================
+    float dummy[8];
+    NcRing r{ring, rfull, rempty, p.raw_slots, p.raw_slot_bytes, 0, 0u, 0};
+    int it = 0;
+    for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x, ++it) {
+      const int st = it % p.S;
+      const uint32_t ph = (uint32_t)(it / p.S) & 1u;
+      const int n = s / p.strips_per_img;
+      const int y0 = (s - n * p.strips_per_img) * p.R;
+      mbar_wait(empty + st, ph ^ 1u);
+      nc_raw_convert<TX, false>(r, s_x + (size_t)st * st_bytes, p.plane, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P, p.pad,
+                                warp - 1, NC_RAW_CONV / 32, 32, p.seg_px, p.nseg, lane, dummy);
+      fence_proxy_async();
+      mbar_arrive(full + st);
     }
   } else if (!BULK && warp < MMA_WARP) {
     // ===================== producers =====================
@@ -370,6 +536,11 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
         if (BULK && b != egrp) continue;
         mbar_wait(tfull + b, (uint32_t)(gc >> 1) & 1u);
         tc_fence_after();
+        if (p.dbg & 8) {          // diagnostic: accumulators are dropped
+          tc_fence_before();
+          mbar_arrive(tempty + b);
+          continue;
+        }
         const int gt = min(p.G, tiles_here - t0);
         const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * 256);
         // TMEM loads are issued EB tiles ahead of their use (one wait per batch instead of one per tile)
@@ -394,7 +565,7 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
               const int m = (t0 + tb + e) * 128 + q4 * 32 + lane;
               const int orow = (int)__umulhi((uint32_t)m, magicP);
               const int ocol = m - orow * p.P;
-              ok[e] = (tb + e < gt) && orow < rows_here && ocol < p.Wo;
+              ok[e] = (tb + e < gt) && orow < rows_here && ocol < p.Wo && !(p.dbg & 2);
               obase[e] = (((int64_t)n * p.Ho + y0 + orow) * p.Wo + ocol) * p.Cout + c0;
             }
             float f[EB][8];
@@ -473,44 +644,91 @@ conv_nc_fwd_kernel(NcFwdP p, const TX* __restrict__ x, const __nv_bfloat16* __re
 //   the end with fp32 atomics into the HWIO gradient.
 // smem: [S stages x (CG*planeX + COG*planeY)*16][bsum scratch: 128*8 f32][barriers]
 // ---------------------------------------------------------------------------------------------
-constexpr int NC_WG_THREADS = NC_PROD + 32;
+// Role layouts: staged (RAW = false): warps 0-7 producers, warp 8 MMA issuer (288 threads).  RAW: warp 0 issues the bulk
+// copies, warps 1-6 convert, warp 7 is the MMA issuer (256 threads = two warps per scheduler).
+constexpr int NC_WG_PROD = 256;
+constexpr int NC_WG_THREADS = NC_WG_PROD + 32;
+constexpr int NC_WG_RAW_THREADS = 256;
 
-template <typename TX, typename TY>
-__global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p, const TX* __restrict__ x,
-                                                                         const TY* __restrict__ dy,
-                                                                         float* __restrict__ dw, float* __restrict__ db,
-                                                                         const TX* __restrict__ xb = nullptr) {
+template <typename TX, typename TY, bool RAW>
+__global__ void __launch_bounds__(RAW ? NC_WG_RAW_THREADS : NC_WG_THREADS, 1)
+conv_nc_wgrad_kernel(NcWgP p, const TX* __restrict__ x, const TY* __restrict__ dy, float* __restrict__ dw,
+                     float* __restrict__ db, const TX* __restrict__ xb = nullptr) {
+  constexpr int THREADS = RAW ? NC_WG_RAW_THREADS : NC_WG_THREADS;
+  constexpr int MMA_WARP = RAW ? 7 : NC_WG_PROD / 32;
+  constexpr int NSTAGE = RAW ? NC_RAW_CONV : NC_WG_PROD;       // threads that fill the raster
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int x_bytes = p.CG * p.planeX * 16;
   const int y_bytes = p.COG * p.planeY * 16;
   const int st_bytes = x_bytes + y_bytes;
   float* s_bsum = reinterpret_cast<float*>(smem + (size_t)p.S * st_bytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_bsum + NC_PROD * 8);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_bsum + NC_WG_PROD * 8);
   uint64_t* empty = full + NC_MAX_STAGES;
   uint64_t* done = empty + NC_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* rfull = reinterpret_cast<uint64_t*>(tmem_slot + 2);
+  uint64_t* rempty = rfull + NC_RAW_MAX_SLOTS;
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rempty + NC_RAW_MAX_SLOTS) + 127) & ~(uintptr_t)127);
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
 
-  for (int i = tid; i < p.S * st_bytes / 16; i += NC_WG_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < p.S * st_bytes / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    for (int i = 0; i < p.S; ++i) { mbar_init(full + i, NC_PROD); mbar_init(empty + i, 1); }
+    for (int i = 0; i < p.S; ++i) { mbar_init(full + i, NSTAGE); mbar_init(empty + i, 1); }
     mbar_init(done, 1);
+    if (RAW)
+      for (int i = 0; i < p.raw_slots; ++i) { mbar_init(rfull + i, 1); mbar_init(rempty + i, 1); }
     fence_barrier_init();
   }
-  if (warp == NC_MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const bool any = (int)blockIdx.x < p.total_strips;
-  const int nthr_y = (NC_PROD / p.COG) * p.COG;
+  const int nthr_y = (NSTAGE / p.COG) * p.COG;
+  const int raw_lanes_y = (32 / p.COG) * p.COG;     // RAW: lanes of a converter warp that take part in a dY segment (COG <= 32)
 
-  if (warp < NC_MMA_WARP) {
+  if (warp < MMA_WARP) {
     float bsum[8], dummy[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
+    const int stid = RAW ? tid - 32 : tid;          // index among the threads that fill the raster (RAW: warp 0 is the issuer)
+    if (RAW && warp == 0) {
+      if (lane == 0) {
+        NcRing r{ring, rfull, rempty, p.raw_slots, p.raw_slot_bytes, 0, 0u, 0};
+        for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x) {
+          const int n = s / p.strips_per_img;
+          const int y0 = (s - n * p.strips_per_img) * p.R;
+          nc_raw_issue<TX>(r, x, n, p.H, p.W, p.Cin, y0 - p.pad, p.RS, p.seg_px, p.nseg);
+          nc_raw_issue<TY>(r, dy, n, p.Ho, p.Wo, p.Cout, y0, p.R, p.seg_px_y, p.nseg_y);
+        }
+      }
+      __syncwarp();
+    } else if (RAW) {
+      NcRing r{ring, rfull, rempty, p.raw_slots, p.raw_slot_bytes, 0, 0u, 0};
+      int it = 0;
+      for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x, ++it) {
+        const int st = it % p.S;
+        const uint32_t ph = (uint32_t)(it / p.S) & 1u;
+        const int n = s / p.strips_per_img;
+        const int y0 = (s - n * p.strips_per_img) * p.R;
+        uint8_t* sx = smem + (size_t)st * st_bytes;
+        uint8_t* sy = sx + x_bytes + (size_t)p.yoff * 16;
+        mbar_wait(empty + st, ph ^ 1u);
+        nc_raw_convert<TX, false>(r, sx, p.planeX, p.H, p.W, p.Cin, p.CG, y0 - p.pad, p.RS, p.P, p.pad, warp - 1,
+                                  NC_RAW_CONV / 32, 32, p.seg_px, p.nseg, lane, dummy);
+        if (db != nullptr)
+          nc_raw_convert<TY, true>(r, sy, p.planeY, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, warp - 1, NC_RAW_CONV / 32,
+                                   raw_lanes_y, p.seg_px_y, p.nseg_y, lane, bsum);
+        else
+          nc_raw_convert<TY, false>(r, sy, p.planeY, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, warp - 1, NC_RAW_CONV / 32, 32,
+                                    p.seg_px_y, p.nseg_y, lane, dummy);
+        fence_proxy_async();
+        mbar_arrive(full + st);
+      }
+    } else {
     int it = 0;
     for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x, ++it) {
       const int st = it % p.S;
@@ -520,26 +738,32 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
       uint8_t* sx = smem + (size_t)st * st_bytes;
       mbar_wait(empty + st, ph ^ 1u);
       nc_stage_rows<TX, false, NC_U_WG>(x, sx, p.planeX, n, p.H, p.W, p.Cb > 0 ? p.Ca : p.Cin, p.CG, y0 - p.pad, p.RS, p.P, p.pad, tid,
-                                        NC_PROD, dummy, xb, p.Cb);
+                                        NC_WG_PROD, dummy, xb, p.Cb);
       uint8_t* sy = sx + x_bytes + (size_t)p.yoff * 16;      // fold: (KH-1) zero rows stay in front of (and behind) the dY rows
       if (db != nullptr)
         nc_stage_rows<TY, true, NC_U_WG>(dy, sy, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, nthr_y, bsum);
       else
-        nc_stage_rows<TY, false, NC_U_WG>(dy, sy, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, NC_PROD, dummy);
+        nc_stage_rows<TY, false, NC_U_WG>(dy, sy, p.planeY, n, p.Ho, p.Wo, p.Cout, p.COG, y0, p.R, p.P, 0, tid, NC_WG_PROD, dummy);
       fence_proxy_async();
       mbar_arrive(full + st);
     }
+    }
     if (any) {
       // bias gradient: per-thread partial sums -> scratch -> one atomic per channel per CTA
-      if (db != nullptr) {
+      if (db != nullptr && !(RAW && warp == 0)) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) s_bsum[tid * 8 + c] = tid < nthr_y ? bsum[c] : 0.f;
-        asm volatile("bar.sync 1, %0;" ::"n"(NC_PROD) : "memory");
-        if (tid < p.Cout) {
-          const int cog = tid >> 3, c = tid & 7;
+        for (int c = 0; c < 8; ++c) s_bsum[stid * 8 + c] = (RAW ? lane < raw_lanes_y : stid < nthr_y) ? bsum[c] : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(NSTAGE) : "memory");
+        if (stid < p.Cout) {
+          const int cog = stid >> 3, c = stid & 7;
           float acc = 0.f;
-          for (int t = cog; t < nthr_y; t += p.COG) acc += s_bsum[t * 8 + c];
-          atomicAdd(db + tid, acc);
+          if (RAW) {       // lane l of every converter warp summed channel group l % COG
+            for (int wv = 0; wv < NC_RAW_CONV / 32; ++wv)
+              for (int l = cog; l < raw_lanes_y; l += p.COG) acc += s_bsum[(wv * 32 + l) * 8 + c];
+          } else {
+            for (int t = cog; t < nthr_y; t += p.COG) acc += s_bsum[t * 8 + c];
+          }
+          atomicAdd(db + stid, acc);
         }
       }
       mbar_wait(done, 0);
@@ -628,7 +852,7 @@ __global__ void __launch_bounds__(NC_WG_THREADS, 1) conv_nc_wgrad_kernel(NcWgP p
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == NC_MMA_WARP) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -671,7 +895,59 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // cost of a choice is  rounds(R) * bytes moved per strip; the candidates must fit S >= 2 stages in shared memory.
 static const size_t kNcSmemMax = 200 * 1024;
 
-static bool nc_fwd_geom(NcFwdP& p, size_t& smem) {
+// Tuning knobs of the geometry search, read per call (diagnostic; scripts/bench_nc_sweep.py): DAFK_NC_R / DAFK_NC_WG_R
+// force the rows per strip, DAFK_NC_S caps the ring depth, DAFK_NC_FIXED is the per-strip fixed cost in byte
+// equivalents, DAFK_NC_ANYR=1 lets the search use every R in 1..32 instead of the powers of two.
+struct NcTune { int fwd_R, wg_R, max_S, any_R; double fixed; int s1; };
+// rows per strip the search may pick: powers of two and 1.5 x powers of two (any_R = 2: every R up to 32)
+static bool nc_r_candidate(int R, int any_R) {
+  if (any_R >= 2 || (R & (R - 1)) == 0) return true;
+  return any_R == 1 && (R == 6 || R == 12 || R == 24);
+}
+static NcTune nc_tune() {
+  NcTune t{0, 0, 3, 1, 20000.0, 1};
+  if (const char* e = getenv("DAFK_NC_R")) t.fwd_R = atoi(e);
+  if (const char* e = getenv("DAFK_NC_WG_R")) t.wg_R = atoi(e);
+  if (const char* e = getenv("DAFK_NC_S")) { t.max_S = atoi(e); if (t.max_S < 2) t.max_S = 2; if (t.max_S > NC_MAX_STAGES) t.max_S = NC_MAX_STAGES; }
+  if (const char* e = getenv("DAFK_NC_ANYR")) t.any_R = atoi(e);
+  if (const char* e = getenv("DAFK_NC_FIXED")) t.fixed = atof(e);
+  if (const char* e = getenv("DAFK_NC_S1")) t.s1 = atoi(e);
+  return t;
+}
+
+// RAW staging of a [.., W, C] tensor of `esz`-byte elements: segment = whole row if it fits NC_RAW_SEG_MAX, else the largest
+// pixel count whose bytes are a multiple of 16.  False when the layout does not allow 16-byte bulk copies / vector reads.
+static bool nc_raw_seg(int W, int C, int esz, int& seg_px, int& nseg, int& seg_bytes) {
+  const int px_bytes = C * esz;
+  if (esz != 4 && C % 8 != 0) return false;
+  if (((int64_t)W * px_bytes) % 16 != 0) return false;
+  if ((int64_t)W * px_bytes <= NC_RAW_SEG_MAX) { seg_px = W; nseg = 1; seg_bytes = W * px_bytes; return true; }
+  int m = 1;
+  while ((m * px_bytes) % 16 != 0) m <<= 1;      // esz = 4: at most 4 pixels
+  seg_px = (NC_RAW_SEG_MAX / px_bytes) / m * m;
+  if (seg_px <= 0) return false;
+  nseg = (W + seg_px - 1) / seg_px;
+  seg_bytes = seg_px * px_bytes;
+  return true;
+}
+static const size_t kNcSmemMaxRaw = 220 * 1024;
+// RAW is selected by default for maps of at least 64 MB staged per launch whose segments are at least 2 KB (measured on
+// B200, gpurun_out/r2t_sweep.txt: 8 -> 8 @ 192 x 224^2 forward 147 -> 126 us, weight gradient 256 -> 205 us, 8 -> 64 weight
+// gradient 201 -> 144 us; small maps (56^2, 110^2) and 896-byte rows were 10 - 40 % slower)
+static const int64_t kNcRawMinBytes = 64ll << 20;
+static const int kNcRawMinSeg = 2048;
+static const int kNcRawReserveSlots = 8;
+
+static bool nc_fwd_geom(NcFwdP& p, size_t& smem, bool raw = false, double* cost_out = nullptr, int* seg_bytes_out = nullptr) {
+  int slot_bytes = 0;
+  p.raw_slots = 0;
+  if (raw) {
+    int sb;
+    if (p.Cb > 0 || !nc_raw_seg(p.W, p.Cin, p.x_dt == DAFK_F32 ? 4 : 2, p.seg_px, p.nseg, sb)) return false;
+    slot_bytes = round_up(sb, 128);
+    if (seg_bytes_out) *seg_bytes_out = sb;
+  }
+  const size_t cap = raw ? kNcSmemMaxRaw - 512 - (size_t)kNcRawReserveSlots * slot_bytes : kNcSmemMax;
   p.P = p.W + 2 * p.pad;
   p.CG = (p.Cin + 7) / 8;
   p.E = round_up(p.CG * p.KH * p.KW, 2);
@@ -682,22 +958,33 @@ static bool nc_fwd_geom(NcFwdP& p, size_t& smem) {
   double best_cost = 0;
   int best = 0, best_S = 0;
   size_t best_smem = 0;
-  for (int R = 1; R <= 16; R *= 2) {
-    if (R > 1 && R / 2 >= p.Ho) break;
+  const NcTune tune = nc_tune();
+  for (int R = 1; R <= 32; ++R) {
+    if (tune.fwd_R > 0 ? R != tune.fwd_R : !nc_r_candidate(R, tune.any_R)) continue;
+    if (R > 1 && R / 2 >= p.Ho && tune.fwd_R <= 0) break;
     const int T = (R * p.P + 127) / 128;
     const int plane = round_up(128 * T + (p.KH - 1) * p.P + p.KW + 8, 8);
     const size_t stage = (size_t)p.CG * plane * 16;
-    int S = (int)((kNcSmemMax - fixed) / stage);
-    if (S > 3) S = 3;
-    if (S < 2) continue;
+    // RAW may run on ONE raster stage (the ring keeps the loads going while the MMAs read the raster; conversion and MMAs
+    // of successive strips then alternate, costed at 1.5 x): wide inputs (64 channels = 8 planes) otherwise only fit
+    // R = 1, i.e. every input row staged KH times
+    const int min_S = (raw && tune.s1) ? 1 : 2;
+    if (cap < fixed + min_S * stage) continue;
+    int S = (int)((cap - fixed) / stage);
+    if (S > tune.max_S) S = tune.max_S;
+    if (raw && S > 2) S = 2;          // the issuer runs ahead through the ring, not through raster stages
     const int64_t strips = (int64_t)p.N * ((p.Ho + R - 1) / R);
     const int64_t rounds = (strips + kNumSMs - 1) / kNumSMs;
-    const double cost = (double)rounds * ((double)R * p.Wo * p.Cout * 4.0 + (double)(R + p.KH - 1) * p.W * p.Cin * 2.0 + 600.0);
+    // (rounds + 1): filling and draining the CTA's pipeline costs about one strip (one strip per CTA has no overlap at all)
+    const double in_b = p.x_dt == DAFK_F32 ? 4.0 : 2.0;
+    const double cost = (double)(rounds + 1) * (S == 1 ? 1.5 : 1.0) *
+                        ((double)R * p.Wo * p.Cout * 4.0 + (double)(R + p.KH - 1) * p.W * p.Cin * in_b + tune.fixed);
     if (!best || cost < best_cost) {
       best = R; best_S = S; best_cost = cost; best_smem = fixed + S * stage;
     }
   }
   if (!best) return false;
+  if (cost_out) *cost_out = best_cost;
   p.R = best;
   p.S = best_S;
   p.RS = p.R + p.KH - 1;
@@ -706,20 +993,37 @@ static bool nc_fwd_geom(NcFwdP& p, size_t& smem) {
   p.strips_per_img = (p.Ho + p.R - 1) / p.R;
   p.total_strips = p.N * p.strips_per_img;
   smem = best_smem;
+  if (raw) {
+    int slots = (int)((kNcSmemMaxRaw - 512 - best_smem) / slot_bytes);
+    p.raw_slots = slots > NC_RAW_MAX_SLOTS ? NC_RAW_MAX_SLOTS : slots;
+    p.raw_slot_bytes = slot_bytes;
+    smem = best_smem + 512 + (size_t)p.raw_slots * slot_bytes;
+  }
   return true;
 }
 
-static bool nc_wg_geom(NcWgP& p, size_t& smem) {
+static bool nc_wg_geom(NcWgP& p, size_t& smem, bool raw = false, double* cost_out = nullptr, int* seg_bytes_out = nullptr) {
+  int slot_bytes = 0;
+  p.raw_slots = 0;
+  if (raw) {
+    int sbx, sby;
+    if (p.Cb > 0 || p.Cout > NC_RAW_CONV || !nc_raw_seg(p.W, p.Cin, p.x_dt == DAFK_F32 ? 4 : 2, p.seg_px, p.nseg, sbx)) return false;
+    p.Wo = p.W + 2 * p.pad - p.KW + 1;
+    if (!nc_raw_seg(p.Wo, p.Cout, p.dy_dt == DAFK_F32 ? 4 : 2, p.seg_px_y, p.nseg_y, sby)) return false;
+    slot_bytes = round_up(sbx > sby ? sbx : sby, 128);
+    if (seg_bytes_out) *seg_bytes_out = sbx > sby ? sbx : sby;   // one wide tensor is enough (1 -> 64: 896-byte image rows)
+  }
+  const size_t cap = raw ? kNcSmemMaxRaw - 512 - (size_t)kNcRawReserveSlots * slot_bytes : kNcSmemMax;
   p.P = p.W + 2 * p.pad;
   p.CG = (p.Cin + 7) / 8;
   p.COG = (p.Cout + 7) / 8;
   p.N8 = p.COG * 8;
-  if (p.KW > 8 || p.N8 > 256 || p.COG > NC_PROD) return false;
+  if (p.KW > 8 || p.N8 > 256 || p.COG > NC_WG_PROD) return false;
   const int cols = p.KH * p.CG * p.N8;
   if (cols > 512) return false;
   p.tmem_cols = 32;
   while (p.tmem_cols < cols) p.tmem_cols <<= 1;
-  const size_t fixed = (size_t)NC_PROD * 8 * 4 + 256 + 256;
+  const size_t fixed = (size_t)NC_WG_PROD * 8 * 4 + 256 + 256;
   {
     static std::atomic<int> fold_ok{-2};       // lazily read once; a race only repeats the getenv
     if (fold_ok == -2) { const char* e = getenv("DAFK_NC_WG_FOLD"); fold_ok = e ? atoi(e) : 1; }
@@ -729,24 +1033,29 @@ static bool nc_wg_geom(NcWgP& p, size_t& smem) {
   double best_cost = 0;
   int best = 0, best_S = 0;
   size_t best_smem = 0;
-  for (int R = 1; R <= 16; R *= 2) {
-    if (R > 1 && R / 2 >= p.Ho) break;
+  const NcTune tune = nc_tune();
+  for (int R = 1; R <= 32; ++R) {
+    if (tune.wg_R > 0 ? R != tune.wg_R : !nc_r_candidate(R, tune.any_R)) continue;
+    if (R > 1 && R / 2 >= p.Ho && tune.wg_R <= 0) break;
     // fold: K covers the R+KH-1 input rows; the dY plane carries KH-1 zero rows on either side of its R rows
     const int kpos = round_up((p.fold ? R + p.KH - 1 : R) * p.P, 16);
     const int planeX = kpos + (p.fold ? 0 : (p.KH - 1) * p.P) + 16;
     const int planeYc = p.fold ? kpos + (p.KH - 1) * p.P + 16 : kpos;
     const size_t stage = (size_t)p.CG * planeX * 16 + (size_t)p.COG * planeYc * 16;
-    int S = (int)((kNcSmemMax - fixed) / stage);
-    if (S > 3) S = 3;
+    if (cap < fixed + 2 * stage) continue;
+    int S = (int)((cap - fixed) / stage);
+    if (S > tune.max_S) S = tune.max_S;
+    if (raw && S > 2) S = 2;
     if (S < 2) continue;
     const int64_t strips = (int64_t)p.N * ((p.Ho + R - 1) / R);
     const int64_t rounds = (strips + kNumSMs - 1) / kNumSMs;
-    const double cost = (double)rounds * ((double)R * p.Wo * p.Cout * 2.0 + (double)(R + p.KH - 1) * p.W * p.Cin * 2.0 + 600.0);
+    const double cost = (double)(rounds + 1) * ((double)R * p.Wo * p.Cout * 2.0 + (double)(R + p.KH - 1) * p.W * p.Cin * 2.0 + tune.fixed);
     if (!best || cost < best_cost) {
       best = R; best_S = S; best_cost = cost; best_smem = fixed + S * stage;
     }
   }
   if (!best) return false;
+  if (cost_out) *cost_out = best_cost;
   p.R = best;
   p.S = best_S;
   p.RS = p.R + p.KH - 1;
@@ -757,6 +1066,12 @@ static bool nc_wg_geom(NcWgP& p, size_t& smem) {
   p.strips_per_img = (p.Ho + p.R - 1) / p.R;
   p.total_strips = p.N * p.strips_per_img;
   smem = best_smem;
+  if (raw) {
+    int slots = (int)((kNcSmemMaxRaw - 512 - best_smem) / slot_bytes);
+    p.raw_slots = slots > NC_RAW_MAX_SLOTS ? NC_RAW_MAX_SLOTS : slots;
+    p.raw_slot_bytes = slot_bytes;
+    smem = best_smem + 512 + (size_t)p.raw_slots * slot_bytes;
+  }
   return true;
 }
 
@@ -765,7 +1080,7 @@ static bool nc_wg_geom(NcWgP& p, size_t& smem) {
 template <typename K>
 static int nc_set_smem(K kernel, size_t smem, const char* name) {
   static std::mutex mu;
-  static const void* done[16];
+  static const void* done[32];
   static int ndone = 0;
   std::lock_guard<std::mutex> lk(mu);
   const void* key = reinterpret_cast<const void*>(kernel);
@@ -774,8 +1089,26 @@ static int nc_set_smem(K kernel, size_t smem, const char* name) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   DAFK_REQUIRE(e == cudaSuccess, DAFK_ERR_CUDA, "%s: cudaFuncSetAttribute(%zu bytes) failed: %s", name, smem,
                cudaGetErrorString(e));
-  if (ndone < 16) done[ndone++] = key;
+  if (ndone < 32) done[ndone++] = key;
   return DAFK_OK;
+}
+
+// Geometry + staging mode of a weight-gradient launch (p holds the shape and dtypes).  DAFK_NC_RAW: unset = RAW where it
+// measured faster, 1 = wherever the layout allows it, 0 = never.
+static bool nc_wg_select(NcWgP& p, size_t& smem, bool& raw) {
+  int raw_mode = -1;
+  { const char* e = getenv("DAFK_NC_RAW"); raw_mode = e ? atoi(e) : -1; }
+  NcWgP pn = p;
+  size_t smem_n = 0;
+  double cost_r = 0, cost_n = 0;
+  int seg_bytes = 0;
+  const bool ok_n = nc_wg_geom(pn, smem_n, false, &cost_n);
+  const bool ok_r = raw_mode != 0 && nc_wg_geom(p, smem, true, &cost_r, &seg_bytes);
+  const int64_t in_bytes = (int64_t)p.N * p.H * p.W * p.Cin * (p.x_dt == DAFK_F32 ? 4 : 2) +
+                           (int64_t)p.N * p.Ho * p.Wo * p.Cout * (p.dy_dt == DAFK_F32 ? 4 : 2);
+  raw = ok_r && (raw_mode > 0 || !ok_n || (in_bytes >= kNcRawMinBytes && seg_bytes >= kNcRawMinSeg && cost_r <= 1.15 * cost_n));
+  if (!raw) { p = pn; smem = smem_n; }
+  return raw || ok_n;
 }
 
 }  // namespace dafk
@@ -795,6 +1128,18 @@ int dafk_conv_nc_supported(int Cin, int Cout, int KH, int KW, int W, int pad, in
   p.H = p.Ho = 1 << 20; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad;
   size_t smem;
   return nc_fwd_geom(p, smem) ? 1 : 0;
+}
+
+int dafk_conv_nc_wgrad_stages_raw(int N, int H, int W, int Cin, int Cout, int KH, int KW, int pad, int x_dt, int dy_dt) {
+  NcWgP p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad;
+  p.Ho = H + 2 * pad - KH + 1;
+  p.Wo = W + 2 * pad - KW + 1;
+  if (N <= 0 || p.Ho <= 0 || p.Wo <= 0) return 0;
+  p.x_dt = x_dt; p.dy_dt = dy_dt;
+  size_t smem;
+  bool raw = false;
+  return nc_wg_select(p, smem, raw) && raw ? 1 : 0;
 }
 
 int64_t dafk_conv_nc_packed_elems(int Cin_k, int Cout_k, int KH, int KW) {
@@ -847,8 +1192,26 @@ static int conv_nc_fwd_impl(const void* x, const void* xb, int Ca, int Cb, int x
   p.Ca = Ca; p.Cb = Cb;
   { const char* e = getenv("DAFK_NC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   size_t smem;
-  DAFK_REQUIRE(nc_fwd_geom(p, smem), DAFK_ERR_UNSUPPORTED,
-               "dafk_conv_nc_fwd: geometry does not fit (Cin=%d Cout=%d k=%dx%d W=%d)", Cin, Cout, KH, KW, W);
+  // RAW staging (rows by cp.async.bulk + converter warps) whenever the layout allows it; DAFK_NC_RAW=0 keeps the
+  // register-staged kernel (read per call so that a test can compare both in one process)
+  // DAFK_NC_RAW: unset = where it measured faster (large maps whose RAW geometry costs no more than the staged one);
+  // 1 = wherever the layout allows it; 0 = never
+  int raw_mode = -1;
+  { const char* e = getenv("DAFK_NC_RAW"); raw_mode = e ? atoi(e) : -1; }
+  bool raw = false;
+  {
+    NcFwdP pn = p;
+    size_t smem_n = 0;
+    double cost_r = 0, cost_n = 0;
+    int seg_bytes = 0;
+    const bool ok_n = nc_fwd_geom(pn, smem_n, false, &cost_n);
+    const bool ok_r = raw_mode != 0 && nc_fwd_geom(p, smem, true, &cost_r, &seg_bytes);
+    const int64_t in_bytes = (int64_t)N * H * W * Cin * (x_dt == DAFK_F32 ? 4 : 2);
+    raw = ok_r && (raw_mode > 0 || !ok_n || (in_bytes >= kNcRawMinBytes && seg_bytes >= kNcRawMinSeg && cost_r <= 1.15 * cost_n));
+    DAFK_REQUIRE(raw || ok_n, DAFK_ERR_UNSUPPORTED,
+                 "dafk_conv_nc_fwd: geometry does not fit (Cin=%d Cout=%d k=%dx%d W=%d)", Cin, Cout, KH, KW, W);
+    if (!raw) { p = pn; smem = smem_n; }
+  }
   // one persistent CTA per SM (it owns all 512 TMEM columns): request more than half of the shared memory
   if (smem < 120 * 1024) smem = 120 * 1024;
   int grid = kNumSMs < p.total_strips ? kNumSMs : p.total_strips;
@@ -860,7 +1223,16 @@ static int conv_nc_fwd_impl(const void* x, const void* xb, int Ca, int Cb, int x
   { const char* e = getenv("DAFK_NC_BULK"); bulk_ok = e ? atoi(e) : 0; }
   int l12 = 1;
   { const char* e = getenv("DAFK_NC_L12"); l12 = e ? atoi(e) : 1; }
-  if (false) {
+  if (raw && x_dt == DAFK_F32) {
+    rc = nc_set_smem(conv_nc_fwd_kernel<float, NC_MODE_RAW>, smem, "dafk_conv_nc_fwd");
+    if (rc) return rc;
+    conv_nc_fwd_kernel<float, NC_MODE_RAW><<<grid, NC_BULK_THREADS, smem, s>>>(p, (const float*)x, (const __nv_bfloat16*)wp,
+                                                                              bias, y);
+  } else if (raw) {
+    rc = nc_set_smem(conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_RAW>, smem, "dafk_conv_nc_fwd");
+    if (rc) return rc;
+    conv_nc_fwd_kernel<__nv_bfloat16, NC_MODE_RAW><<<grid, NC_BULK_THREADS, smem, s>>>(p, (const __nv_bfloat16*)x,
+                                                                                      (const __nv_bfloat16*)wp, bias, y);
   } else if (l12 && x_dt == DAFK_F32) {
     rc = nc_set_smem(conv_nc_fwd_kernel<float, NC_MODE_L12>, smem, "dafk_conv_nc_fwd");
     if (rc) return rc;
@@ -924,7 +1296,8 @@ static int conv_nc_wgrad_impl(const void* x, const void* xb, int Ca, int Cb, int
   p.x_dt = x_dt; p.dy_dt = dy_dt;
   p.Ca = Ca; p.Cb = Cb;
   size_t smem;
-  DAFK_REQUIRE(nc_wg_geom(p, smem), DAFK_ERR_UNSUPPORTED,
+  bool raw = false;
+  DAFK_REQUIRE(nc_wg_select(p, smem, raw), DAFK_ERR_UNSUPPORTED,
                "dafk_conv_nc_wgrad: geometry does not fit (Cin=%d Cout=%d k=%dx%d W=%d)", Cin, Cout, KH, KW, W);
   if (smem < 120 * 1024) smem = 120 * 1024;     // one persistent CTA per SM
   int grid = kNumSMs < p.total_strips ? kNumSMs : p.total_strips;
@@ -932,9 +1305,15 @@ static int conv_nc_wgrad_impl(const void* x, const void* xb, int Ca, int Cb, int
   int rc;
 #define NC_WG(TX, TY)                                                                                   \
   do {                                                                                                  \
-    rc = nc_set_smem(conv_nc_wgrad_kernel<TX, TY>, smem, "dafk_conv_nc_wgrad");                           \
-    if (rc) return rc;                                                                                  \
-    conv_nc_wgrad_kernel<TX, TY><<<grid, NC_WG_THREADS, smem, s>>>(p, (const TX*)x, (const TY*)dy, dw, db, (const TX*)xb);  \
+    if (raw) {                                                                                          \
+      rc = nc_set_smem(conv_nc_wgrad_kernel<TX, TY, true>, smem, "dafk_conv_nc_wgrad");                   \
+      if (rc) return rc;                                                                                \
+      conv_nc_wgrad_kernel<TX, TY, true><<<grid, NC_WG_RAW_THREADS, smem, s>>>(p, (const TX*)x, (const TY*)dy, dw, db); \
+    } else {                                                                                            \
+      rc = nc_set_smem(conv_nc_wgrad_kernel<TX, TY, false>, smem, "dafk_conv_nc_wgrad");                  \
+      if (rc) return rc;                                                                                \
+      conv_nc_wgrad_kernel<TX, TY, false><<<grid, NC_WG_THREADS, smem, s>>>(p, (const TX*)x, (const TY*)dy, dw, db, (const TX*)xb); \
+    }                                                                                                   \
   } while (0)
   if (x_dt == DAFK_F32 && dy_dt == DAFK_F32) NC_WG(float, float);
   else if (x_dt == DAFK_F32) NC_WG(float, __nv_bfloat16);

@@ -562,6 +562,17 @@ class Conv2D:
         # (pixel, 8-channel) units, so halving the bytes per unit does not make them faster -- weight gradient 191 -> 289 us,
         # 64 -> 8 data gradient 326 -> 596 us -- and fp32 stays
         bf16_bw = self.bf16_grad and nc_f and nc_w and od == torch.bfloat16
+        # Wide first layers (8 -> 64 segmentor / discriminator conv1, 1 -> 64 UNet conv1; models/unet.py:95,
+        # model_components/segmentor.py:15) whose output is stored in bf16: the BatchNormalization backward writes the
+        # output gradient in bf16 when the weight-gradient kernel stages rows with bulk copies (141 us against 157 us from
+        # fp32), and the 64 -> 8 data gradient then runs on the swizzled tcgen05 kernel (94 us against 334 us on the
+        # raster-strip kernel).  Same numbers either way: the raster-strip kernels round the gradient to bf16 while staging.
+        tc_dg = nc and self.k > 1 and self.cout % 16 == 0 and self.cout >= 32 and self.cin % 8 == 0
+        wide_bf16 = (WIDE_BF16_GRAD and nc_f and nc_w and not cat2 and od == torch.bfloat16 and self.cout >= 32
+                     and self.cout % 16 == 0 and xin.data.dtype == torch.float32 and ctx.training
+                     and (tc_dg or not xin.requires_grad)
+                     and ops.nc_wgrad_stages_raw(tuple(xin.shape), torch.float32, self.cout, self.k, self.pad))
+        bf16_bw = bf16_bw or wide_bf16
         if cat2:
             y = Var(ops.conv_nc_fwd_cat(srcs[0].data, srcs[1].data, self.packed_nc()[0], bias, self.cout, self.k, self.k,
                                         self.pad, code, alpha, od))
@@ -611,10 +622,17 @@ class Conv2D:
                                 accumulate(v, ops.slice_channels(dx, off, v.shape[-1]))
                             off += v.shape[-1]
                 elif tape_x.requires_grad:
-                    if nc_d:
+                    if tc_dg and g.dtype == torch.bfloat16:
+                        ver = self.kernel.arena.version
+                        if self._packed_dg is None or self._packed_dg[0] != ver:
+                            self._packed_dg = (ver, ops.pack_conv(self.kernel.data, 1,
+                                                                  out=None if self._packed_dg is None else self._packed_dg[1]))
+                        dx = ops.conv_tc_fwd(g, None, self._packed_dg[1], None, self.cin, self.k, self.k, 1,
+                                             self.k - 1 - self.pad, tape_x.grad_dtype)
+                    elif nc_d:
                         dx = ops.conv_nc_fwd(g, self.packed_nc()[1], None, self.cin, self.k, self.k, self.k - 1 - self.pad,
                                              out_dtype=tape_x.grad_dtype)
-                    elif nc and self.k > 1 and self.cout % 16 == 0 and self.cout >= 32 and self.cin % 8 == 0:
+                    elif tc_dg:
                         # few inputs <- many outputs (SPADE's 8 -> 128 anatomy convolution, layers/spade.py:29): the data
                         # gradient is a wide-in / narrow-out convolution for the swizzled tcgen05 kernel
                         ver = self.kernel.arena.version
@@ -864,6 +882,7 @@ class Dense:
         return y
 
 
+WIDE_BF16_GRAD = True     # bf16 output gradients into the wide first layers (Conv2D.__call__)
 FOLD_BN = True      # predict passes: fold BatchNorm (+ReLU) into the tensor-core convolution that feeds it
 
 

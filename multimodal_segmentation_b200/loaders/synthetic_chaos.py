@@ -57,18 +57,51 @@ def make_pairs(n, shape, num_masks=4, seed=10):
 
 
 class PairedData(object):
-    """the slice of loaders/MultimodalPairedData.py used by the executors"""
+    """the slice of loaders/MultimodalPairedData.py + loaders/data.py used by the executors: two modalities' images and
+    masks, and `index`, the volume every slice belongs to (synthetic "volumes" = runs of SLICES_PER_VOLUME items)"""
 
-    def __init__(self, images, masks, volumes_per_item=12):
+    SLICES_PER_VOLUME = 8
+
+    def __init__(self, images, masks, index=None):
         self.images = images          # list of two arrays
         self.masks = masks
-        self.num_volumes = volumes_per_item
+        n = images[0].shape[0]
+        self.index = np.arange(n) // self.SLICES_PER_VOLUME if index is None else np.asarray(index)
+        self.num_volumes = len(self.volume_ids())
 
     def size(self):
-        return self.images[0].shape[0]
+        return max(im.shape[0] for im in self.images)      # loaders/MultimodalPairedData.py:74-75
+
+    def volume_ids(self):
+        """loaders/data.py `volumes()`: the sorted set of volume ids"""
+        return sorted(set(self.index.tolist()))
+
+    def get_sample_volumes(self, num, seed=-1):
+        """loaders/data.py:123-129: `num` volume ids drawn without replacement from numpy's global generator"""
+        if seed > -1:
+            np.random.seed(seed)
+        return np.random.choice(self.volume_ids(), size=num, replace=False)
 
     def sample(self, nb_samples, seed=-1):
-        pass  # all synthetic volumes are kept (the reference sub-samples labelled volumes by l_mix)
+        """loaders/data.py:131-136: keep `nb_samples` randomly chosen volumes (the labelled share l_mix of the data)"""
+        if nb_samples == self.num_volumes:
+            return
+        self.filter_volumes(self.get_sample_volumes(nb_samples, seed))
+
+    def filter_volumes(self, volumes):
+        """loaders/MultimodalPairedData.py:46-62: keep the slices of the listed volumes, in the order listed"""
+        volumes = list(volumes)
+        if len(volumes) == 0:
+            self.images = [im[0:0] for im in self.images]
+            self.masks = [m[0:0] for m in self.masks]
+            self.index = self.index[0:0]
+            self.num_volumes = 0
+            return
+        keep = np.concatenate([np.nonzero(self.index == v)[0] for v in volumes], axis=0)
+        self.images = [im[keep] for im in self.images]
+        self.masks = [m[keep] for m in self.masks]
+        self.index = self.index[keep]
+        self.num_volumes = len(volumes)
 
     def get_images_modi(self, i):
         return self.images[i]
@@ -76,11 +109,13 @@ class PairedData(object):
     def get_masks_modi(self, i):
         return self.masks[i]
 
-    SLICES_PER_VOLUME = 8        # synthetic "volumes": runs of consecutive items
-
     def volumes(self):
-        n = self.size()
-        return [(a, min(n, a + self.SLICES_PER_VOLUME)) for a in range(0, n, self.SLICES_PER_VOLUME)]
+        """[a, b) item ranges of the volumes, in storage order (filter_volumes keeps a volume's slices together)"""
+        n = self.index.shape[0]
+        if n == 0:
+            return []
+        cuts = [0] + [i for i in range(1, n) if self.index[i] != self.index[i - 1]] + [n]
+        return list(zip(cuts[:-1], cuts[1:]))
 
     def randomise_pairs(self, length=3, seed=None):
         """loaders/MultimodalPairedData.py:143-166: re-pair modality 0 with a slice up to `length` positions away

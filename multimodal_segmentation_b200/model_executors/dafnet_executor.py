@@ -140,15 +140,24 @@ class DAFNetExecutor(Executor):
     def _init_unlabelled_data_generator(self):
         if self.conf.l_mix == 1:
             return None
-        self.ul_data = self.loader.load_all_modalities_concatenated(self.conf.split, "training", self.conf.image_downsample,
-                                                                   seed=self.conf.seed + 77)
-        self._pair_up(self.ul_data)
+        self.ul_data = self._load_unlabelled_data("training")
         if self.data is None or self.ul_data.size() > self.data.size():
             self.data_len = self.ul_data.size()
         nm = self.loader.num_masks
         return self.get_data_generator(train_images=[self.ul_data.get_images_modi(i) for i in range(2)],
                                        train_labels=[self.add_residual(self.ul_data.get_masks_modi(0)[..., 0:nm])],
                                        labels_have_residual=True)
+
+    def _load_unlabelled_data(self, split_type):
+        """dafnet_executor.py:117-145 ('ul'): the training volumes that are NOT labelled -- the same draw of
+        round(l_mix * num_volumes) volumes as Data.sample made for the labelled set (same seed), removed"""
+        ul_data = self.loader.load_all_modalities_concatenated(self.conf.split, split_type, self.conf.image_downsample)
+        self._pair_up(ul_data)
+        if self.conf.l_mix > 0:
+            num_lb_vols = int(np.round(self.conf.l_mix * ul_data.num_volumes))
+            labelled = set(np.asarray(ul_data.get_sample_volumes(num_lb_vols, seed=self.conf.seed)).tolist())
+            ul_data.filter_volumes([v for v in ul_data.volume_ids() if v not in labelled])
+        return ul_data
 
     def _pair_up(self, data):
         """dafnet_executor.py:89-93,127-131: candidate pairs for the automated-pairing trainers (images get n_pairs
@@ -161,15 +170,23 @@ class DAFNetExecutor(Executor):
             data.expand_pairs(self.conf.n_pairs - 1, 1, neighborhood=self.conf.n_pairs)
 
     def _init_disciminator_mask_generator(self):
-        """real masks for D_Mask: a separate draw (dafnet_executor.py:516-519)"""
-        d = self.loader.load_all_modalities_concatenated(self.conf.split, "training", self.conf.image_downsample,
-                                                         seed=self.conf.seed + 177)
-        masks = np.concatenate([d.get_masks_modi(0), d.get_masks_modi(1)], axis=0)
+        """real masks for D_Mask (dafnet_executor.py:147-176): both modalities' masks of the labelled volumes and modality
+        1's masks of the unlabelled ones"""
+        masks = []
+        if self.data is not None:
+            masks.append(np.concatenate([self.data.get_masks_modi(0), self.data.get_masks_modi(1)], axis=0))
+        if self.ul_data is not None and self.ul_data.size() > 0:
+            masks.append(self.ul_data.get_masks_modi(0))
+        if masks:
+            masks = np.concatenate(masks, axis=0)
+        else:
+            masks = np.empty((0,) + tuple(self.conf.input_shape[:-1]) + (self.loader.num_masks,), np.float32)
+        assert masks.shape[1:3] == tuple(self.conf.input_shape[:2]), masks.shape
         return self.get_data_generator(train_images=None, train_labels=[masks])
 
     def _init_discriminator_image_generator(self, modality):
-        d = self.loader.load_all_modalities_concatenated(self.conf.split, "training", self.conf.image_downsample,
-                                                         seed=self.conf.seed + 277)
+        """every training image of one modality, labelled or not (dafnet_executor.py:178-184, data_type 'all')"""
+        d = self.loader.load_all_modalities_concatenated(self.conf.split, "training", self.conf.image_downsample)
         i = self.model.modalities.index(modality)
         return self.get_data_generator(train_images=[d.get_images_modi(i)], train_labels=None)
 
@@ -314,7 +331,9 @@ class DAFNetExecutor(Executor):
         (x1,) = self._stage(self.discriminator_image[0])
         (x2,) = self._stage(self.discriminator_image[1])
         B = min(t.shape[0] for t in (x1, x2, m1, m2))
-        return [x1[:B], x2[:B], m1[:B].contiguous(), m2[:B].contiguous(), self._sample_idx(2 * B, B), self._sample_idx(2 * B, B)]
+        nm = self.conf.num_masks                 # dafnet_executor.py:516-517: [..., 0:conf.num_masks]
+        return [x1[:B], x2[:B], m1[:B, ..., 0:nm].contiguous(), m2[:B, ..., 0:nm].contiguous(), self._sample_idx(2 * B, B),
+                self._sample_idx(2 * B, B)]
 
     def _stage_image_d(self):
         (x1,) = self._stage(self.discriminator_image[0])

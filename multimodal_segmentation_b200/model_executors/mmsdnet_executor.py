@@ -40,8 +40,7 @@ class MMSDNetExecutor(DAFNetExecutor):
     def _init_unlabelled_data_generator(self):
         if self.conf.l_mix == 1:
             return None
-        self.ul_data = self.loader.load_all_modalities_concatenated(self.conf.split, "training", self.conf.image_downsample,
-                                                                   seed=self.conf.seed + 77)
+        self.ul_data = self._load_unlabelled_data("training")        # the volumes the labelled sample left out
         if self.data is None or self.ul_data.size() > self.data.size():
             self.data_len = self.ul_data.size()
         nm = self.loader.num_masks

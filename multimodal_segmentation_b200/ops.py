@@ -647,6 +647,15 @@ def nc_supported(Cin, Cout, KH, KW, W, pad, kind):
     return bool(f(Cin, Cout, KH, KW, W, pad, kind))
 
 
+def nc_wgrad_stages_raw(x_shape, x_dtype, Cout, k, pad, dy_dtype=torch.bfloat16):
+    """would conv_nc_wgrad bring rows of these dtypes in with bulk copies (fast on a bf16 output gradient)?"""
+    if not USE_NC:
+        return False
+    N, H, W, Cin = x_shape
+    code = {torch.float32: DAFK_F32, torch.bfloat16: DAFK_BF16}
+    return bool(_lib.lib().fn["dafk_conv_nc_wgrad_stages_raw"](N, H, W, Cin, Cout, k, k, pad, code[x_dtype], code[dy_dtype]))
+
+
 def pack_conv_nc(w_hwio, mode, out=None):
     """mode 0: forward operand; mode 1: stride-1 data-gradient operand (mirrored taps, transposed channels)"""
     _chk(w_hwio)

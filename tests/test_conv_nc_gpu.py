@@ -169,6 +169,50 @@ def test_conv_nc_twelve_warp_layout(ops, case, xdt, monkeypatch):
     assert torch.equal(y0, y1)
 
 
+RAW_CASES = CASES + [
+    (2, 24, 40, 64, 8, 3, 1),       # rows wider than one 8 KB segment (fp32: 2 segments of 32 pixels)
+    (1, 20, 72, 64, 8, 3, 1),       # 3 segments, the last one short
+    (2, 9, 136, 20, 20, 5, 0),      # 80 B pixels: segment = 102 pixels rounded to a 16-byte multiple
+    (5, 50, 32, 8, 8, 3, 1),        # more strips than ring slots, rows above / below the image in most strips
+    (2, 31, 33, 16, 64, 2, 0),      # space-to-depth form of a discriminator layer
+]
+
+
+@pytest.mark.parametrize("case", RAW_CASES)
+@pytest.mark.parametrize("xdt", ["f32", "bf16"])
+def test_conv_nc_raw_staging_matches_register_staging(ops, case, xdt, monkeypatch):
+    """rows brought in by cp.async.bulk + converter warps (DAFK_NC_RAW=1, the default where the layout allows it) must
+    give the register-staged kernel's bits: same bf16 rounding, same raster, same MMA order.  The weight gradient ends in
+    atomics across CTAs, so it is compared at the accumulation-order tolerance and against the oracle."""
+    from multimodal_segmentation_b200._lib import ACT_LRELU
+    N, H, W, Cin, Cout, k, pad = case
+    r, x, w, b = _mk(case, sum(case) + 11)
+    dt = torch.float32 if xdt == "f32" else torch.bfloat16
+    wp = ops.pack_conv_nc(gpu(w), 0)
+    xg = gpu(x, dt)
+    Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    dy = bf16_round(r.normal(size=(N, Ho, Wo, Cout)).astype(np.float32))
+    dyg = gpu(dy, dt)
+    wt = torch.zeros(k, k, Cin, Cout, dtype=torch.float64, requires_grad=True)
+    (R.conv2d(t(x, torch.float64), wt, None, 1, "same" if pad else "valid") * t(dy, torch.float64)).sum().backward()
+    out = {}
+    for raw in ("0", "1", "1"):             # the repeat: nothing may depend on leftovers of an earlier launch
+        monkeypatch.setenv("DAFK_NC_RAW", raw)
+        y = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad)
+        a = ops.conv_nc_fwd(xg, wp, gpu(b), Cout, k, k, pad, ACT_LRELU, 0.3, torch.bfloat16)
+        dw, db = ops.zeros(k, k, Cin, Cout), ops.zeros(Cout)
+        ops.conv_nc_wgrad(xg, dyg, dw, db, pad)
+        torch.cuda.synchronize()
+        if raw == "0":
+            out = dict(y=y, a=a, dw=dw, db=db)
+            continue
+        assert torch.equal(out["y"], y) and torch.equal(out["a"], a)
+        assert rel_l2(cpu(dw), cpu(out["dw"])) < 1e-5 and rel_l2(cpu(db), cpu(out["db"])) < 1e-5
+        assert rel_l2(cpu(dw), wt.grad.numpy()) < 1e-3
+        assert rel_l2(cpu(db), dy.sum((0, 1, 2))) < 1e-3
+    assert rel_l2(cpu(y), _ref_conv(x, w, b, pad).numpy()) < 1e-4
+
+
 # ------------------------------------------------------------------ stride-2 valid layers through space-to-depth
 S2_CASES = [
     # N, H, W, Cin, Cout, k     (models/discriminator.py:24 first layer; model_components/modality_encoder.py:36-42)

@@ -61,3 +61,37 @@ def test_pair_expansion_and_repairing_match_the_reference_class():
     assert np.array_equal(d.get_images_modi(0), G["pairs_randomise_images"])
     assert np.array_equal(d.get_masks_modi(0), G["pairs_randomise_masks"])
     assert np.array_equal(d.get_images_modi(1), imgs[..., 1:2])          # modality 1 stays in place
+
+
+def test_l_mix_volume_sampling_partitions_the_training_volumes():
+    """loaders/data.py:123-151 + dafnet_executor.py:87-88,136-142: Data.sample keeps round(l_mix * num_volumes) volumes drawn
+    with the configuration's seed; the unlabelled set is what the SAME draw leaves out (filter_volumes keeps the slices of a
+    volume together and in the order the volumes are listed)."""
+    from multimodal_segmentation_b200.loaders.synthetic_chaos import PairedData
+    n = 5 * PairedData.SLICES_PER_VOLUME + 3                       # five whole volumes and a short one
+    tag = np.arange(n, dtype=np.float32).reshape(n, 1, 1, 1)
+
+    def mk():
+        return PairedData([tag.copy(), tag.copy() + 1000], [np.zeros((n, 1, 1, 4), np.float32)] * 2)
+
+    lab = mk()
+    assert lab.num_volumes == 6 and lab.volume_ids() == [0, 1, 2, 3, 4, 5] and lab.size() == n
+    lab.sample(lab.num_volumes, seed=3)                            # everything labelled: untouched, no draw
+    assert lab.size() == n
+    num = int(np.round(0.5 * lab.num_volumes))
+    lab.sample(num, seed=3)
+    np.random.seed(3)
+    want = np.random.choice([0, 1, 2, 3, 4, 5], size=num, replace=False)           # the reference's draw
+    assert lab.num_volumes == num and list(dict.fromkeys(lab.index.tolist())) == want.tolist()
+    assert np.array_equal(lab.images[1], lab.images[0] + 1000)                    # modalities stay paired
+    for a, b in lab.volumes():                                                     # whole volumes, slices in order
+        ids = lab.images[0][a:b, 0, 0, 0]
+        assert len(set((ids // PairedData.SLICES_PER_VOLUME).tolist())) == 1 and np.all(np.diff(ids) == 1)
+    ul = mk()
+    labelled = set(ul.get_sample_volumes(num, seed=3).tolist())
+    ul.filter_volumes([v for v in ul.volume_ids() if v not in labelled])
+    assert labelled == set(want.tolist())
+    got = sorted(lab.images[0].ravel().tolist() + ul.images[0].ravel().tolist())
+    assert got == tag.ravel().tolist()                                             # a partition of the training slices
+    ul.filter_volumes([])
+    assert ul.size() == 0 and ul.num_volumes == 0 and ul.volumes() == []

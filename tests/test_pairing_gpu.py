@@ -169,7 +169,7 @@ def test_experiment_automated_pairing_one_epoch(tmp_path, monkeypatch):
     import os
     from multimodal_segmentation_b200.experiment import Experiment
     monkeypatch.chdir(tmp_path)
-    monkeypatch.setenv("DAFK_TRAIN_PAIRS", "8")
+    monkeypatch.setenv("DAFK_TRAIN_PAIRS", "16")     # two volumes: l_mix = 0.5 labels one of them, the other is unlabelled
     Experiment().run(["--config", "dafnet_config_chaos", "--split", "0", "--l_mix", "0.5", "--input_size", "64",
                       "--epochs", "1", "--batch_size", "4", "--automatedpairing", "1"])
     folder = [f for f in os.listdir(".") if f.startswith("dafnet_chaos_automatedpairing_l05")][0]
