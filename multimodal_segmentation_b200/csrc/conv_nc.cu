@@ -187,7 +187,7 @@ __device__ __forceinline__ void nc_stage_rows(const T* __restrict__ src, uint8_t
 // the converters across strip boundaries.  A segment = seg_px pixels of one image row (a whole row when it fits 8 KB).
 // Both sides walk the same (row, segment) sequence; rows outside the image are not copied, the converters zero them.
 // ---------------------------------------------------------------------------------------------
-constexpr int NC_RAW_MAX_SLOTS = 16;
+constexpr int NC_RAW_MAX_SLOTS = 12;     // a multiple of the converter warps, see nc_raw_convert
 constexpr int NC_RAW_SEG_MAX = 8192;
 constexpr int NC_RAW_CONV = 192;      // converter threads (six warps)
 
@@ -238,7 +238,8 @@ __device__ __forceinline__ void nc_raw_load8(const float* p, int nvalid, bool ve
   } else { v[4] = v[5] = v[6] = v[7] = 0.f; }
 }
 
-// Converter side, called by every converter warp (cw = its index among the ncw of them).  A segment belongs to ONE warp:
+// Converter side, called by every converter warp (cw = its index among the ncw of them).  A segment belongs to ONE warp
+// and, the slot count being a multiple of ncw (nc_raw_slots), so does every slot:
 // the warps work on different segments at the same time, and nothing but that warp's arrival frees the slot (a segment
 // shared by all warps cost a barrier round trip of all 192 threads per image row: the load path alone took 117 us for
 // 8 -> 8 @ 192 x 224^2 against 93 us with register staging).  `lanes` of the warp convert (32, or a multiple of `groups`
@@ -931,12 +932,22 @@ static bool nc_raw_seg(int W, int C, int esz, int& seg_px, int& nseg, int& seg_b
   return true;
 }
 static const size_t kNcSmemMaxRaw = 220 * 1024;
+// Ring slots: a multiple of the converter warps, so that segment g (slot g % slots, owner warp g % warps) gives every slot
+// ONE owner.  A slot's "full" barrier is waited on by parity: a warp that waits for wrap k of a slot must have seen wrap
+// k - 1 complete, which only holds if it consumed wrap k - 1 itself -- with 8 or 16 slots and 6 warps a warp could reach its
+// wait while another warp's earlier segment of the same slot was still in flight (bulk copies complete out of order), pass
+// at once on the stale parity, convert garbage and release the slot (caught by scripts/stress_nc.py as a trapped launch).
+static int nc_raw_slots(int fit) {
+  const int w = NC_RAW_CONV / 32;
+  const int slots = fit / w * w;
+  return slots > NC_RAW_MAX_SLOTS ? NC_RAW_MAX_SLOTS : slots;
+}
 // RAW is selected by default for maps of at least 64 MB staged per launch whose segments are at least 2 KB (measured on
 // B200, gpurun_out/r2t_sweep.txt: 8 -> 8 @ 192 x 224^2 forward 147 -> 126 us, weight gradient 256 -> 205 us, 8 -> 64 weight
 // gradient 201 -> 144 us; small maps (56^2, 110^2) and 896-byte rows were 10 - 40 % slower)
 static const int64_t kNcRawMinBytes = 64ll << 20;
 static const int kNcRawMinSeg = 2048;
-static const int kNcRawReserveSlots = 8;
+static const int kNcRawReserveSlots = 6;
 
 static bool nc_fwd_geom(NcFwdP& p, size_t& smem, bool raw = false, double* cost_out = nullptr, int* seg_bytes_out = nullptr) {
   int slot_bytes = 0;
@@ -994,8 +1005,7 @@ static bool nc_fwd_geom(NcFwdP& p, size_t& smem, bool raw = false, double* cost_
   p.total_strips = p.N * p.strips_per_img;
   smem = best_smem;
   if (raw) {
-    int slots = (int)((kNcSmemMaxRaw - 512 - best_smem) / slot_bytes);
-    p.raw_slots = slots > NC_RAW_MAX_SLOTS ? NC_RAW_MAX_SLOTS : slots;
+    p.raw_slots = nc_raw_slots((int)((kNcSmemMaxRaw - 512 - best_smem) / slot_bytes));
     p.raw_slot_bytes = slot_bytes;
     smem = best_smem + 512 + (size_t)p.raw_slots * slot_bytes;
   }
@@ -1067,8 +1077,7 @@ static bool nc_wg_geom(NcWgP& p, size_t& smem, bool raw = false, double* cost_ou
   p.total_strips = p.N * p.strips_per_img;
   smem = best_smem;
   if (raw) {
-    int slots = (int)((kNcSmemMaxRaw - 512 - best_smem) / slot_bytes);
-    p.raw_slots = slots > NC_RAW_MAX_SLOTS ? NC_RAW_MAX_SLOTS : slots;
+    p.raw_slots = nc_raw_slots((int)((kNcSmemMaxRaw - 512 - best_smem) / slot_bytes));
     p.raw_slot_bytes = slot_bytes;
     smem = best_smem + 512 + (size_t)p.raw_slots * slot_bytes;
   }

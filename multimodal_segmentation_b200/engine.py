@@ -882,7 +882,7 @@ class Dense:
         return y
 
 
-WIDE_BF16_GRAD = True     # bf16 output gradients into the wide first layers (Conv2D.__call__)
+WIDE_BF16_GRAD = os.environ.get("DAFK_WIDE_BF16", "1") != "0"     # bf16 output gradients into the wide first layers (Conv2D.__call__)
 FOLD_BN = True      # predict passes: fold BatchNorm (+ReLU) into the tensor-core convolution that feeds it
 
 

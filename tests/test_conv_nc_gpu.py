@@ -363,3 +363,27 @@ def test_conv_nc_two_concatenated_sources(ops, case):
     torch.cuda.synchronize()
     # the weight gradient accumulates per-CTA partial sums with atomics: same terms, order may differ
     assert rel_l2(cpu(dw2), cpu(dw1)) < 1e-5 and rel_l2(cpu(db2), cpu(db1)) < 1e-5
+
+
+@pytest.mark.parametrize("case", [
+    (8, 220, 220, 20, 16, 5, 4),        # locnet data gradient: 3 segments per row, 3 channel groups, one raster stage
+    (8, 224, 224, 64, 8, 3, 1),         # 64 -> 8 data gradient: 7 segments per row, 8 channel groups
+    (8, 224, 224, 8, 8, 3, 1),          # FiLM layer: one segment per row
+])
+def test_conv_nc_raw_staging_repeated_launches_are_identical(ops, case, monkeypatch):
+    """200 launches with bulk-copy staging forced must all give the first launch's bits.  Bulk copies complete out of order:
+    with a ring whose slots were shared between converter warps a warp could pass a slot's parity wait on a stale phase and
+    convert a segment that had not arrived (found by scripts/stress_nc.py as a rare trapped launch); the ring now has a
+    multiple of the converter warps as slot count, so that every slot has one owner."""
+    N, H, W, Cin, Cout, k, pad = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(k, k, Cin, Cout, device="cuda", generator=g) * 0.1
+    wp = ops.pack_conv_nc(w, 0)
+    monkeypatch.setenv("DAFK_NC_RAW", "0")
+    ref = ops.conv_nc_fwd(x, wp, None, Cout, k, k, pad)
+    monkeypatch.setenv("DAFK_NC_RAW", "1")
+    outs = [ops.conv_nc_fwd(x, wp, None, Cout, k, k, pad) for _ in range(200)]
+    torch.cuda.synchronize()
+    bad = [i for i, o in enumerate(outs) if not torch.equal(o, ref)]
+    assert not bad, bad[:10]
