@@ -40,7 +40,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) {
       // one line per warp (the barrier's shared-memory offset names it), then a pause so that the other stuck warps of the
       // CTA get their line out before the trap ends the launch
-      if ((threadIdx.x & 31) == 0 || true)
+      if ((threadIdx.x & 31) == 0)
         printf("dafk: mbarrier wait timed out (block %d thread %d parity %u barrier@%u)\n", (int)blockIdx.x, (int)threadIdx.x,
                parity, smem_u32(bar));
       const long long t1 = clock64();
