@@ -330,7 +330,7 @@ def run_b200(args):
         dt = float(tt.item())
         e2e = {"value": world * pairs_per_step * args.steps / dt, "unit": "slices/s",
                "h2d_bytes_per_step": int(ex.h2d_bytes / args.steps), "d2h_bytes_per_step": int(ex.d2h_bytes / args.steps),
-               "last_loss": float(np.mean(losses["loss"][-1:])) if losses["loss"] else None}
+               "last_loss": float(np.mean(losses["loss"][-1:])) if losses.get("loss") else None}
 
     def finish():
         """multi-rank teardown: a captured CUDA graph that contains NCCL collectives makes

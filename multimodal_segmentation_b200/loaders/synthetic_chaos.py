@@ -103,6 +103,14 @@ class PairedData(object):
         self.index = self.index[keep]
         self.num_volumes = len(volumes)
 
+    def crop(self, shape):
+        """loaders/MultimodalPairedData.py:64-72: images and masks of every modality cropped / padded to `shape`"""
+        from ..utils.data_utils import crop_same
+        for i in range(len(self.images)):
+            [self.images[i]], [self.masks[i]] = crop_same([self.images[i]], [self.masks[i]], size=shape, pad_mode="constant")
+            assert self.images[i].shape[1:-1] == self.masks[i].shape[1:-1] == tuple(shape), \
+                "Invalid shapes: %s %s %s" % (self.images[i].shape[1:-1], self.masks[i].shape[1:-1], shape)
+
     def get_images_modi(self, i):
         return self.images[i]
 

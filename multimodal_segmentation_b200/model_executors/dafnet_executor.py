@@ -227,8 +227,10 @@ class DAFNetExecutor(Executor):
 
     # ------------------------------------------------------------------ training loop
     def get_loss_names(self):
-        return ["adv_M", "adv_X1", "adv_X2", "rec_X", "dis_M", "dis_X1", "dis_X2", "val_loss", "val_loss_mod1",
-                "val_loss_mod2", "val_loss_mod2_s1def", "val_loss_mod2_fused", "supervised_Mask", "loss", "KL", "rec_Z"]
+        """dafnet_executor.py:200-205 (the columns of training.csv, in the reference's order)"""
+        return ["adv_M", "adv_X1", "adv_X2", "rec_X", "dis_M", "dis_X1", "dis_X2", "val_loss", "val_loss_mod1", "val_loss_mod2",
+                "val_loss_mod2_mod1def", "val_loss_mod1_mod2def", "val_loss_mod2_fused", "val_loss_mod1_fused",
+                "val_weight_0", "val_weight_1", "val_weight_2", "supervised_Mask", "KL", "rec_Z"]
 
     def train(self):
         log.info("Training Model")
@@ -268,14 +270,17 @@ class DAFNetExecutor(Executor):
                     break
 
     def validate(self, epoch_loss):
-        """dafnet_executor.py:303-367 (expert pairing): 1 - Dice(binarised) for modality 1, modality 2 'simple',
-        's1def' and 'fused' on the validation split"""
+        """dafnet_executor.py:303-367: 1 - Dice(binarised) on the validation split for both modalities -- from their own
+        anatomy, from the other modality's anatomy deformed onto them and from the fused anatomy -- through the SWA clones;
+        with automated pairing also the Balancer's mean weight per candidate (live models, as the reference)."""
         valid = self.loader.load_all_modalities_concatenated(self.conf.split, "validation", self.conf.image_downsample)
+        if getattr(self.conf, "randomise", False):
+            valid.randomise_pairs(length=self.conf.n_pairs - 1)
+        valid.crop(self.conf.input_shape[:2])
         nm = self.loader.num_masks
         x0, x1 = valid.get_images_modi(0), valid.get_images_modi(1)
         real0, real1 = valid.get_masks_modi(0)[..., :nm], valid.get_masks_modi(1)[..., :nm]
-        # the reference validates through the SWA clones (dafnet_executor.py:319-331); up to SWA_EPOCH their weights ARE
-        # the live weights, so the clones are only built once averaging has started
+        # up to SWA_EPOCH the clones' weights ARE the live weights, so the clones are only built once averaging has started
         averaging = (self.USE_SWA and getattr(self, "epoch", 0) > self.SWA_EPOCH
                      and self.swa_Segmentor.swa_weights is not None)
         pick = (lambda name, live: getattr(self, name).get_clone_model()) if averaging else (lambda name, live: live)
@@ -283,24 +288,30 @@ class DAFNetExecutor(Executor):
         enc1 = pick("swa_Enc_Anatomy2", self.model.Encoders_Anatomy[1])
         seg = pick("swa_Segmentor", self.model.Segmentor)
         fuser = pick("swa_Anatomy_Fuser", self.model.Anatomy_Fuser)
-        s0 = enc0.predict(x0)
-        s1 = enc1.predict(x1)
-        mask1 = seg.predict(s0)
-        mask2 = seg.predict(s1)
-        s0_def, s_fused = fuser.predict([s0, s1])
-        mask3 = seg.predict(s0_def)
-        mask4 = seg.predict(s_fused)
-        l1 = 1 - costs.dice(real0, mask1, binarise=True)
-        l2 = 1 - costs.dice(real1, mask2, binarise=True)
-        l3 = 1 - costs.dice(real1, mask3, binarise=True)
-        l4 = 1 - costs.dice(real1, mask4, binarise=True)
-        epoch_loss["val_loss_mod1"].append(l1)
-        epoch_loss["val_loss_mod2"].append(l2)
-        epoch_loss["val_loss_mod2_s1def"].append(l3)
-        epoch_loss["val_loss_mod2_fused"].append(l4)
-        epoch_loss["val_loss"].append(np.mean([l1, l2, l3, l4]))
+        s1 = enc0.predict(x0)
+        s2 = enc1.predict(x1)
+        s1_deformed, s2_fused = fuser.predict([s1, s2])
+        s2_deformed, s1_fused = fuser.predict([s2, s1])
+        loss = lambda real, s: 1 - costs.dice(real, seg.predict(s), binarise=True)
+        dice_m1s1, dice_m1s2def, dice_m1fused = loss(real0, s1), loss(real0, s2_deformed), loss(real0, s1_fused)
+        dice_m2s2, dice_m2s1def, dice_m2fused = loss(real1, s2), loss(real1, s1_deformed), loss(real1, s2_fused)
+        epoch_loss["val_loss_mod2"].append(dice_m2s2)
+        epoch_loss["val_loss_mod2_mod1def"].append(dice_m2s1def)
+        epoch_loss["val_loss_mod2_fused"].append(dice_m2fused)
+        epoch_loss["val_loss_mod1_mod2def"].append(dice_m1s2def)
+        epoch_loss["val_loss_mod1_fused"].append(dice_m1fused)
+        epoch_loss["val_loss_mod1"].append(dice_m1s1)
+        epoch_loss["val_loss"].append(np.mean([dice_m1s1, dice_m2s2, dice_m2s1def, dice_m2fused]))
+        if getattr(self.conf, "automatedpairing", False):
+            valid.expand_pairs(self.conf.n_pairs - 1, 0, neighborhood=self.conf.n_pairs)
+            x0p = valid.get_images_modi(0)
+            s1_list = [self.model.Encoders_Anatomy[0].predict(np.ascontiguousarray(x0p[..., i:i + 1]))
+                       for i in range(x0p.shape[-1])]
+            s2_live = self.model.Encoders_Anatomy[1].predict(valid.get_images_modi(1))
+            weights = self.model.Balancer.predict([s2_live] + s1_list)
+            for j in range(weights.shape[-1]):
+                epoch_loss.setdefault("val_weight_%d" % j, []).append(float(np.mean(weights[..., j])))
 
-    # ------------------------------------------------------------------ one step
     def train_batch(self, epoch_loss):
         """dafnet_executor.py:369-387"""
         if self._graph is not None:
@@ -542,7 +553,8 @@ class DAFNetExecutor(Executor):
                 epoch_loss["adv_X2"].append(h["D_Image2_loss"][0])
                 epoch_loss["KL"].append(h["Enc_Modality_loss"][0])
                 epoch_loss["rec_Z"].append(h["ZReconstruct_loss"][0])
-                epoch_loss["loss"].append(h["loss"][0])
+                epoch_loss.setdefault("loss", []).append(h["loss"][0])       # sum of the weighted terms (not a column of the
+                #                                                              reference's DAFNet csv; MMSDNet lists it)
             else:
                 epoch_loss[kind].append(h["loss"][0])
         self._pending = []

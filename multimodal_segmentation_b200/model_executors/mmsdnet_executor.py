@@ -11,7 +11,7 @@ import logging
 import numpy as np
 import torch
 
-from .. import ops
+from .. import costs, ops
 from .dafnet_executor import DAFNetExecutor
 
 log = logging.getLogger("mmsdnet_executor")
@@ -46,6 +46,27 @@ class MMSDNetExecutor(DAFNetExecutor):
         nm = self.loader.num_masks
         return self.get_data_generator(train_images=[self.ul_data.get_images_modi(i) for i in range(2)],
                                        train_labels=[np.ascontiguousarray(self.ul_data.get_masks_modi(0)[..., 0:nm])])
+
+    def validate(self, epoch_loss):
+        """mmsdnet_executor.py:210-236: 1 - Dice(binarised) on the validation split through the LIVE models: modality 1,
+        modality 2 from its own anatomy, from the deformed modality-1 anatomy ('s1def') and from the fused anatomy"""
+        valid = self.loader.load_all_modalities_concatenated(self.conf.split, "validation", self.conf.image_downsample)
+        valid.crop(self.conf.input_shape[:2])
+        nm = self.loader.num_masks
+        x0, x1 = valid.get_images_modi(0), valid.get_images_modi(1)
+        real0, real1 = valid.get_masks_modi(0)[..., :nm], valid.get_masks_modi(1)[..., :nm]
+        M = self.model
+        s1 = M.Encoders_Anatomy[0].predict(x0)
+        s2 = M.Encoders_Anatomy[1].predict(x1)
+        s1_deformed, s_fused = M.Anatomy_Fuser.predict([s1, s2])
+        loss = lambda real, s: 1 - costs.dice(real, M.Segmentor.predict(s), binarise=True)
+        l_mod1, l_mod2 = loss(real0, s1), loss(real1, s2)
+        l_mod2_s1def, l_mod2_fused = loss(real1, s1_deformed), loss(real1, s_fused)
+        epoch_loss["val_loss_mod2"].append(l_mod2)
+        epoch_loss["val_loss_mod2_s1def"].append(l_mod2_s1def)
+        epoch_loss["val_loss_mod2_fused"].append(l_mod2_fused)
+        epoch_loss["val_loss_mod1"].append(l_mod1)
+        epoch_loss["val_loss"].append(np.mean([l_mod1, l_mod2, l_mod2_s1def, l_mod2_fused]))
 
     # ------------------------------------------------------------------ staging
     def _stage_generator(self, supervised):

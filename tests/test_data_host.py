@@ -95,3 +95,24 @@ def test_l_mix_volume_sampling_partitions_the_training_volumes():
     assert got == tag.ravel().tolist()                                             # a partition of the training slices
     ul.filter_volumes([])
     assert ul.size() == 0 and ul.num_volumes == 0 and ul.volumes() == []
+
+
+def test_crop_same_matches_the_reference_function():
+    """utils/data_utils.py:37-123 (validation data are cropped / padded to conf.input_shape, dafnet_executor.py:313): golden
+    vectors from the reference's own crop_same (tests/golden/make_golden_crop.py), incl. its odd-difference behaviour
+    ('equal' removes ceil(diff / 2) pixels from each side and the pad step puts one back) and min-valued constant padding."""
+    import os
+    from multimodal_segmentation_b200.utils.data_utils import crop_same
+    from tests.golden.make_golden_crop import CASES, inputs
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_crop.npz"))
+    for i, ((h, w), size) in enumerate(CASES):
+        for mode in ("equal", "left", "right"):
+            for pad_mode in ("edge", "constant"):
+                im, m = inputs(i, h, w)
+                [a], [b] = crop_same([im], [m], size=size, mode=mode, pad_mode=pad_mode)
+                assert np.array_equal(a, G["%d_%s_%s_image" % (i, mode, pad_mode)])
+                assert np.array_equal(b, G["%d_%s_%s_mask" % (i, mode, pad_mode)])
+    from multimodal_segmentation_b200.loaders.synthetic_chaos import PairedData
+    d = PairedData([np.ones((4, 10, 12, 1), np.float32), np.ones((4, 10, 12, 1), np.float32)], [np.zeros((4, 10, 12, 4), np.float32)] * 2)
+    d.crop((8, 8))
+    assert d.images[0].shape == (4, 8, 8, 1) and d.masks[1].shape == (4, 8, 8, 4)

@@ -176,6 +176,12 @@ def test_experiment_automated_pairing_one_epoch(tmp_path, monkeypatch):
     rows = open(os.path.join(folder, "training.csv")).read().strip().split("\n")
     assert len(rows) == 2
     vals = dict(zip(rows[0].split(","), rows[1].split(",")))
-    assert np.isfinite(float(vals["loss"])) and float(vals["supervised_Mask"]) > 0
+    assert np.isfinite(float(vals["rec_X"])) and float(vals["supervised_Mask"]) > 0
+    # the reference's columns (dafnet_executor.py:200-205), incl. both deformation directions and the Balancer's weights
+    for col in ("val_loss_mod2_mod1def", "val_loss_mod1_mod2def", "val_loss_mod1_fused", "val_weight_0", "val_weight_2"):
+        assert col in vals and np.isfinite(float(vals[col])), col
+    assert "loss" not in vals
+    w = [float(vals["val_weight_%d" % j]) for j in range(3)]          # --automatedpairing 1 sets n_pairs = 3
+    assert all(0.0 <= v <= 1.0 for v in w) and abs(sum(w) - 1.0) < 1e-3          # softmax over the n_pairs candidates
     assert os.path.exists(os.path.join(folder, "models", "Balancer.npz")) or \
         any(f.startswith("Balancer") for f in os.listdir(os.path.join(folder, "models")))
