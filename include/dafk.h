@@ -231,6 +231,12 @@ int dafk_conv_nc_supported(int Cin, int Cout, int KH, int KW, int W, int pad, in
  * register-staged kernel is slower on bf16 than on fp32.  The host engine asks before it lets the BatchNormalization
  * backward of a first layer (models/unet.py:95, model_components/segmentor.py:15) write its gradient in bf16. */
 int dafk_conv_nc_wgrad_stages_raw(int N, int H, int W, int Cin, int Cout, int KH, int KW, int pad, int x_dt, int dy_dt);
+/* The launch plan dafk_conv_nc_fwd (kind 0; dy_dt = the output dtype) or dafk_conv_nc_wgrad (kind 2) would use for this
+ * shape, without launching anything (host only): plan[0..9] = {bulk-copy staging 0/1, rows per strip, raster stages,
+ * ring slots, bytes per slot, pixels per segment and segments per row of x, the same of dy (kind 2), dynamic shared
+ * memory bytes}.  DAFK_ERR_UNSUPPORTED if the geometry does not fit.  Tests assert the plan's invariants on the CPU. */
+int dafk_conv_nc_plan(int kind, int N, int H, int W, int Cin, int Cout, int KH, int KW, int pad, int x_dt, int dy_dt,
+                      int64_t* plan);
 /* number of bf16 elements of the packed weight buffer for a kernel that reduces over Cin_k channels
  * and produces Cout_k channels */
 int64_t dafk_conv_nc_packed_elems(int Cin_k, int Cout_k, int KH, int KW);

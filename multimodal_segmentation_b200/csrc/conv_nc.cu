@@ -1102,6 +1102,25 @@ static int nc_set_smem(K kernel, size_t smem, const char* name) {
   return DAFK_OK;
 }
 
+// Geometry + staging mode of a forward / data-gradient launch (p holds the shape and dtypes).  RAW staging (rows by
+// cp.async.bulk + converter warps): DAFK_NC_RAW unset = where it measured faster (large maps whose RAW geometry costs no more
+// than the staged one); 1 = wherever the layout allows it; 0 = never (read per call so that a test can compare both kernels
+// in one process).
+static bool nc_fwd_select(NcFwdP& p, size_t& smem, bool& raw) {
+  int raw_mode = -1;
+  { const char* e = getenv("DAFK_NC_RAW"); raw_mode = e ? atoi(e) : -1; }
+  NcFwdP pn = p;
+  size_t smem_n = 0;
+  double cost_r = 0, cost_n = 0;
+  int seg_bytes = 0;
+  const bool ok_n = nc_fwd_geom(pn, smem_n, false, &cost_n);
+  const bool ok_r = raw_mode != 0 && nc_fwd_geom(p, smem, true, &cost_r, &seg_bytes);
+  const int64_t in_bytes = (int64_t)p.N * p.H * p.W * p.Cin * (p.x_dt == DAFK_F32 ? 4 : 2);
+  raw = ok_r && (raw_mode > 0 || !ok_n || (in_bytes >= kNcRawMinBytes && seg_bytes >= kNcRawMinSeg && cost_r <= 1.15 * cost_n));
+  if (!raw) { p = pn; smem = smem_n; }
+  return raw || ok_n;
+}
+
 // Geometry + staging mode of a weight-gradient launch (p holds the shape and dtypes).  DAFK_NC_RAW: unset = RAW where it
 // measured faster, 1 = wherever the layout allows it, 0 = never.
 static bool nc_wg_select(NcWgP& p, size_t& smem, bool& raw) {
@@ -1149,6 +1168,34 @@ int dafk_conv_nc_wgrad_stages_raw(int N, int H, int W, int Cin, int Cout, int KH
   size_t smem;
   bool raw = false;
   return nc_wg_select(p, smem, raw) && raw ? 1 : 0;
+}
+
+int dafk_conv_nc_plan(int kind, int N, int H, int W, int Cin, int Cout, int KH, int KW, int pad, int x_dt, int dy_dt,
+                      int64_t* plan) {
+  DAFK_REQUIRE(plan != nullptr && (kind == 0 || kind == 2), DAFK_ERR_BAD_ARG, "dafk_conv_nc_plan: bad argument");
+  size_t smem = 0;
+  bool raw = false;
+  if (kind == 2) {
+    NcWgP p{};
+    p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad;
+    p.Ho = H + 2 * pad - KH + 1;
+    p.Wo = W + 2 * pad - KW + 1;
+    p.x_dt = x_dt; p.dy_dt = dy_dt;
+    if (N <= 0 || p.Ho <= 0 || p.Wo <= 0 || !nc_wg_select(p, smem, raw)) return DAFK_ERR_UNSUPPORTED;
+    const int64_t v[10] = {raw, p.R, p.S, p.raw_slots, p.raw_slot_bytes, p.seg_px, p.nseg, p.seg_px_y, p.nseg_y, (int64_t)smem};
+    for (int i = 0; i < 10; ++i) plan[i] = v[i];
+    return DAFK_OK;
+  }
+  NcFwdP p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.pad = pad;
+  p.Ho = H + 2 * pad - KH + 1;
+  p.Wo = W + 2 * pad - KW + 1;
+  p.x_dt = x_dt; p.y_dt = dy_dt;
+  p.Ca = Cin;
+  if (N <= 0 || p.Ho <= 0 || p.Wo <= 0 || !nc_fwd_select(p, smem, raw)) return DAFK_ERR_UNSUPPORTED;
+  const int64_t v[10] = {raw, p.R, p.S, p.raw_slots, p.raw_slot_bytes, p.seg_px, p.nseg, 0, 0, (int64_t)smem};
+  for (int i = 0; i < 10; ++i) plan[i] = v[i];
+  return DAFK_OK;
 }
 
 int64_t dafk_conv_nc_packed_elems(int Cin_k, int Cout_k, int KH, int KW) {
@@ -1201,26 +1248,9 @@ static int conv_nc_fwd_impl(const void* x, const void* xb, int Ca, int Cb, int x
   p.Ca = Ca; p.Cb = Cb;
   { const char* e = getenv("DAFK_NC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   size_t smem;
-  // RAW staging (rows by cp.async.bulk + converter warps) whenever the layout allows it; DAFK_NC_RAW=0 keeps the
-  // register-staged kernel (read per call so that a test can compare both in one process)
-  // DAFK_NC_RAW: unset = where it measured faster (large maps whose RAW geometry costs no more than the staged one);
-  // 1 = wherever the layout allows it; 0 = never
-  int raw_mode = -1;
-  { const char* e = getenv("DAFK_NC_RAW"); raw_mode = e ? atoi(e) : -1; }
   bool raw = false;
-  {
-    NcFwdP pn = p;
-    size_t smem_n = 0;
-    double cost_r = 0, cost_n = 0;
-    int seg_bytes = 0;
-    const bool ok_n = nc_fwd_geom(pn, smem_n, false, &cost_n);
-    const bool ok_r = raw_mode != 0 && nc_fwd_geom(p, smem, true, &cost_r, &seg_bytes);
-    const int64_t in_bytes = (int64_t)N * H * W * Cin * (x_dt == DAFK_F32 ? 4 : 2);
-    raw = ok_r && (raw_mode > 0 || !ok_n || (in_bytes >= kNcRawMinBytes && seg_bytes >= kNcRawMinSeg && cost_r <= 1.15 * cost_n));
-    DAFK_REQUIRE(raw || ok_n, DAFK_ERR_UNSUPPORTED,
-                 "dafk_conv_nc_fwd: geometry does not fit (Cin=%d Cout=%d k=%dx%d W=%d)", Cin, Cout, KH, KW, W);
-    if (!raw) { p = pn; smem = smem_n; }
-  }
+  DAFK_REQUIRE(nc_fwd_select(p, smem, raw), DAFK_ERR_UNSUPPORTED,
+               "dafk_conv_nc_fwd: geometry does not fit (Cin=%d Cout=%d k=%dx%d W=%d)", Cin, Cout, KH, KW, W);
   // one persistent CTA per SM (it owns all 512 TMEM columns): request more than half of the shared memory
   if (smem < 120 * 1024) smem = 120 * 1024;
   int grid = kNumSMs < p.total_strips ? kNumSMs : p.total_strips;
