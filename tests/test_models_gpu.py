@@ -11,6 +11,8 @@ the GPU against the CPU oracle graph (oracle/ref_models.py), same weights, same 
   0.5, so masks are compared by mismatch fraction and losses loosely;
 * tensor-core mode (bf16 operands): the north-star bound 1e-2.
 """
+import types
+
 import numpy as np
 import pytest
 import torch
@@ -497,3 +499,92 @@ def test_tensor_core_inference_dice_within_half_percent():
         assert abs(d_got - d_ref) <= 0.005 * d_ref, (d_got, d_ref)  # a chaotic trajectory may end with none): 0.24 % measured
     assert abs(soft_got - soft_ref) <= 0.005 * soft_ref, (soft_got, soft_ref)
     assert mism < 0.01, mism                                        # measured: 0.2 % of the pixels change class
+
+
+def _cell_has_value(c):
+    try:
+        c.cell_contents
+        return True
+    except ValueError:
+        return False
+
+
+def _device_tensors(*roots):
+    """every CUDA tensor reachable from the given objects (attributes, lists, tuples, dicts), one per storage"""
+    seen, out, stack = set(), {}, list(roots)
+    while stack:
+        o = stack.pop()
+        if id(o) in seen:
+            continue
+        seen.add(id(o))
+        if isinstance(o, torch.Tensor):
+            if o.is_cuda and o.numel() > 0:
+                key = o.untyped_storage().data_ptr()
+                if key not in out or o.numel() > out[key].numel():
+                    out[key] = o
+            continue
+        if isinstance(o, (str, bytes, int, float, bool, type(None), np.ndarray, torch.cuda.CUDAGraph, torch.cuda.Stream,
+                          torch.cuda.Event)):
+            continue
+        if isinstance(o, dict):
+            stack.extend(o.values())
+        elif isinstance(o, (list, tuple, set)):
+            stack.extend(o)
+        elif isinstance(o, (types.FunctionType, types.MethodType)):
+            f = o.__func__ if isinstance(o, types.MethodType) else o
+            stack.extend(c.cell_contents for c in (f.__closure__ or ()) if _cell_has_value(c))
+            if isinstance(o, types.MethodType):
+                stack.append(o.__self__)
+        elif isinstance(o, (type, types.ModuleType)):
+            continue
+        else:
+            if hasattr(o, "__dict__"):
+                stack.extend(vars(o).values())
+            for slot in getattr(type(o), "__slots__", ()):
+                if hasattr(o, slot):
+                    stack.append(getattr(o, slot))
+    return list(out.values())
+
+
+def test_one_graph_replay_equals_one_host_launched_step_from_the_same_state():
+    """a deterministic graph-vs-eager comparison.  After the warm-up steps and the capture, every
+    device tensor reachable from the network and the executor (weights, Adam moments and step counters, BatchNorm moving
+    statistics, spectral vectors, loss books) is saved; ONE replay of the captured train_batch runs; the state is put back;
+    the same train_batch is launched kernel by kernel.  Both start from identical state and inputs, so the eleven losses
+    differ only by the order of fp32 atomics inside one step (no chaotic amplification over steps) and the weight
+    updates point the same way."""
+    names = ["supervised_Mask", "adv_M", "rec_X", "adv_X1", "adv_X2", "KL", "rec_Z", "loss", "dis_M", "dis_X1", "dis_X2"]
+    net, ex = _executor()
+    step = ex.stage_step_inputs()
+    ex._static = None
+    ex.enable_cuda_graph(warmup=2)
+    torch.cuda.synchronize()
+    state = _device_tensors(net, ex)
+    saved = [t.clone() for t in state]
+    w_ref = net.Segmentor.layers[0].kernel.data
+    w0 = w_ref.clone()
+
+    def run():
+        losses = {n: [] for n in ex.get_loss_names()}
+        ex.train_batch_on(step)
+        ex.flush_losses(losses)
+        torch.cuda.synchronize()
+        return np.array([float(np.mean(losses[n])) for n in names]), w_ref.clone()
+
+    l_g, w_g = run()
+    for t, s in zip(state, saved):
+        t.copy_(s)
+    torch.cuda.synchronize()
+    graph, ex._graph = ex._graph, None
+    try:
+        l_e, w_e = run()
+    finally:
+        ex._graph = graph
+    assert np.all(np.isfinite(l_g)) and np.all(np.isfinite(l_e))
+    assert np.abs(l_g - l_e).max() <= 5e-4 * np.abs(l_e).max(), (l_g, l_e)      # measured 3e-5 - 6e-5
+    dg, de = (w_g - w0).flatten().double(), (w_e - w0).flatten().double()
+    assert dg.norm().item() > 0 and de.norm().item() > 0
+    cos = (dg @ de / (dg.norm() * de.norm())).item()
+    print("graph replay vs host-launched step from the same state: max loss difference %.2e (relative to the largest loss), "
+          "update cosine %.6f" % (np.abs(l_g - l_e).max() / np.abs(l_e).max(), cos))
+    assert cos > 0.99, cos                                                        # measured 1.000000
