@@ -116,3 +116,33 @@ def test_crop_same_matches_the_reference_function():
     d = PairedData([np.ones((4, 10, 12, 1), np.float32), np.ones((4, 10, 12, 1), np.float32)], [np.zeros((4, 10, 12, 4), np.float32)] * 2)
     d.crop((8, 8))
     assert d.images[0].shape == (4, 8, 8, 1) and d.masks[1].shape == (4, 8, 8, 4)
+
+
+def test_volume_sampling_matches_the_reference_classes():
+    """golden vectors from the reference's own MultimodalPairedData.sample / get_sample_volumes / filter_volumes
+    (tests/golden/make_golden_sampling.py): the labelled slices for l_mix in {0.25, 0.5, 0.75, 1} and the unlabelled complement
+    that dafnet_executor.py:136-142 builds from the same draw, slice by slice and in the reference's order."""
+    import os
+    from multimodal_segmentation_b200.loaders.synthetic_chaos import PairedData
+    from tests.golden.make_golden_sampling import CASES, PER_VOLUME, inputs
+    assert PairedData.SLICES_PER_VOLUME == PER_VOLUME
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_sampling.npz"))
+
+    def mk():
+        images, masks, index = inputs()
+        return PairedData([images[..., 0:1].copy(), images[..., 1:2].copy()], [masks[..., :4].copy(), masks[..., 4:].copy()], index.copy())
+
+    for l_mix, seed in CASES:
+        key = "l%s_s%d" % (str(l_mix).replace(".", ""), seed)
+        lab = mk()
+        num = int(np.round(l_mix * lab.num_volumes))
+        lab.sample(num, seed=seed)
+        assert np.array_equal(lab.get_images_modi(0), G[key + "_lab_images0"])
+        assert np.array_equal(lab.get_masks_modi(1), G[key + "_lab_masks1"])
+        assert np.array_equal(lab.index, G[key + "_lab_index"])
+        ul = mk()
+        labelled = set(np.asarray(ul.get_sample_volumes(num, seed=seed)).tolist())
+        ul.filter_volumes([v for v in ul.volume_ids() if v not in labelled])
+        assert np.array_equal(ul.index, G[key + "_ul_index"])
+        if ul.size() > 0:
+            assert np.array_equal(ul.get_images_modi(1), G[key + "_ul_images1"])
